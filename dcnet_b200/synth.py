@@ -1,0 +1,47 @@
+"""Seeded synthetic inputs for the hot path.  Shared by tests, smoke() and bench.py.
+Pure torch-CPU generators: the same seed gives the same tensors here and on the GPU box (same image)."""
+import random
+
+import numpy as np
+import torch
+
+CH = (1024, 512, 256)
+
+
+def seed_all(seed=13):
+    random.seed(seed)
+    np.random.seed(seed + 1)
+    torch.manual_seed(seed + 2)
+
+
+def grids(size):
+    return [size // 32, size // 16, size // 8]
+
+
+def make_raw_fvisu(pairs, size, gen=None, corr=0.9):
+    """3 x [2P, C_s, g_s, g_s]; frame 2 = corr*frame 1 + sqrt(1-corr^2)*noise (VID-like temporal correlation)."""
+    out = []
+    for c, g in zip(CH, grids(size)):
+        a = torch.randn(pairs, c, g, g, generator=gen)
+        b = corr * a + (1 - corr * corr) ** 0.5 * torch.randn(pairs, c, g, g, generator=gen)
+        out.append(torch.stack([a, b], 1).reshape(2 * pairs, c, g, g).contiguous())
+    return out
+
+
+def make_words(pairs, vocab=1000, T=20, gen=None):
+    """[2P,T] int64; lengths U{5..20}, zero padded, first pair full length; both frames share the phrase."""
+    ids = torch.randint(1, vocab, (pairs, T), generator=gen)
+    lens = torch.randint(5, T + 1, (pairs,), generator=gen)
+    lens[0] = T
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    ids = ids * mask
+    return ids.repeat_interleave(2, 0).contiguous()
+
+
+def make_boxes(pairs, size, gen=None):
+    """[2P,4] xyxy fp32 clamped to [0,size-1]; frame-2 box = frame-1 box + U(-4,4)."""
+    xy = torch.rand(pairs, 2, generator=gen) * size / 2
+    wh = size / 8 + torch.rand(pairs, 2, generator=gen) * (size / 2 - size / 8)
+    b1 = torch.cat([xy, xy + wh], 1)
+    b2 = b1 + (torch.rand(pairs, 4, generator=gen) * 8 - 4)
+    return torch.stack([b1, b2], 1).reshape(2 * pairs, 4).clamp(0, size - 1).contiguous()
