@@ -1,0 +1,123 @@
+// a5 / a20: co-attention (model/DCNet_model.py:449-459; model/test_DCNet_model.py:247-274), one direction per problem.
+//   S = Fa^T Fb,  P = softmax_j(tau S),  O = Fb P^T.
+// This file holds the fp32 composition used for exactness checks and as the backward of round 1: the score matrix
+// lives in caller-provided scratch.  The tcgen05 path (umma_coattn.cu) keeps S/P in TMEM/SMEM and is selected by
+// dcnet_coattn_fwd when the shape is supported.
+#include "common.cuh"
+
+int umma_coattn_fwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob, float* out, float* lse,
+                    int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st);  // umma_coattn.cu
+bool umma_coattn_supported(int C, int N);
+
+namespace {
+
+// rows of S' = tau*S (already scaled): P = softmax(row), lse = max + log(sum).  One warp per row.
+__global__ void softmax_rows_kernel(float* __restrict__ S, float* __restrict__ lse, long long rows, int N) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* p = S + row * N;
+  float m = -INFINITY;
+  for (int j = lane; j < N; j += 32) m = fmaxf(m, p[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    const float e = __expf(p[j] - m);
+    p[j] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+  for (int j = lane; j < N; j += 32) p[j] *= inv;
+  if (lane == 0) lse[row] = m + logf(s);
+}
+
+// P = exp(S' - lse[row])
+__global__ void exp_lse_kernel(float* __restrict__ S, const float* __restrict__ lse, long long rows, int N) {
+  const long long total = rows * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    S[i] = __expf(S[i] - lse[i / N]);
+}
+
+// dS = tau * P o (dP - delta 1^T), delta_i = sum_j P_ij dP_ij; in place over dP.  One warp per row.
+__global__ void softmax_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dP, long long rows, int N, float tau) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = P + row * N;
+  float* d = dP + row * N;
+  float dl = 0.f;
+  for (int j = lane; j < N; j += 32) dl = fmaf(p[j], d[j], dl);
+  dl = warp_sum(dl);
+  for (int j = lane; j < N; j += 32) d[j] = tau * p[j] * (d[j] - dl);
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t dcnet_coattn_workspace_bytes(int nprob, int C, int N) {
+  (void)C;
+  if (nprob <= 0 || N <= 0) return 256;
+  return 2 * align256((size_t)nprob * N * N * sizeof(float)) + 256;
+}
+
+extern "C" int dcnet_coattn_fwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob,
+                                float* out, float* lse, int C, int N, float tau, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  DCNET_CHECK_ARG(frames && qa && kb && oidx && out && lse && nprob >= 0 && C > 0 && N > 0, "coattn_fwd: bad arguments");
+  if (nprob == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (umma_coattn_supported(C, N))
+    return umma_coattn_fwd(frames, qa, kb, oidx, nprob, out, lse, C, N, tau, workspace, workspace_bytes, st);
+  DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(nprob, C, N), "coattn_fwd: workspace too small");
+  float* S = (float*)workspace;
+  const long long CN = (long long)C * N, NN = (long long)N * N;
+  // S' = tau Fa^T Fb
+  DCNET_TRY(sgemm_launch(frames, frames, S, N, N, C, nprob, 1, 1, N, CN, 0, N, 1, CN, 0, N, 1, NN, qa, kb, nullptr, tau, 0.f,
+                         nullptr, 0, 0, st));
+  const long long rows = (long long)nprob * N;
+  softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(S, lse, rows, N);
+  DCNET_LAUNCH_OK("coattn_fwd.softmax");
+  // O[c,i] = sum_j Fb[c,j] P[i,j]
+  DCNET_TRY(sgemm_launch(frames, S, out, C, N, N, nprob, 1, N, 1, CN, 0, 1, N, NN, 0, N, 1, CN, kb, nullptr, oidx, 1.f, 0.f,
+                         nullptr, 0, 0, st));
+  return 0;
+}
+
+extern "C" int dcnet_coattn_bwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob,
+                                const float* out, const float* lse, const float* dout, float* dframes,
+                                int C, int N, float tau, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)out;
+  DCNET_CHECK_ARG(frames && qa && kb && oidx && lse && dout && dframes && nprob >= 0 && C > 0 && N > 0, "coattn_bwd: bad arguments");
+  if (nprob == 0) return 0;
+  DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(nprob, C, N), "coattn_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const long long CN = (long long)C * N, NN = (long long)N * N;
+  float* P = (float*)workspace;
+  float* dP = (float*)((char*)workspace + align256((size_t)nprob * NN * sizeof(float)));
+  const long long rows = (long long)nprob * N;
+  // recompute P = exp(tau S - lse)
+  DCNET_TRY(sgemm_launch(frames, frames, P, N, N, C, nprob, 1, 1, N, CN, 0, N, 1, CN, 0, N, 1, NN, qa, kb, nullptr, tau, 0.f,
+                         nullptr, 0, 0, st));
+  {
+    long long g = (rows * N + 255) / 256;
+    exp_lse_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, st>>>(P, lse, rows, N);
+    DCNET_LAUNCH_OK("coattn_bwd.exp");
+  }
+  // dP[i,j] = sum_c dO[c,i] Fb[c,j]
+  DCNET_TRY(sgemm_launch(dout, frames, dP, N, N, C, nprob, 1, 1, N, CN, 0, N, 1, CN, 0, N, 1, NN, oidx, kb, nullptr, 1.f, 0.f,
+                         nullptr, 0, 0, st));
+  // dFb += dO P   (uses P and dO before dP is overwritten by dS? independent buffers: order free)
+  DCNET_TRY(sgemm_launch(dout, P, dframes, C, N, N, nprob, 1, N, 1, CN, 0, N, 1, NN, 0, N, 1, CN, oidx, nullptr, kb, 1.f, 0.f,
+                         nullptr, 0, 1, st));
+  softmax_bwd_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, dP, rows, N, tau);
+  DCNET_LAUNCH_OK("coattn_bwd.softmax");
+  // dFa[c,i] += sum_j Fb[c,j] dS[i,j]
+  DCNET_TRY(sgemm_launch(frames, dP, dframes, C, N, N, nprob, 1, N, 1, CN, 0, 1, N, NN, 0, N, 1, CN, kb, nullptr, qa, 1.f, 0.f,
+                         nullptr, 0, 1, st));
+  // dFb[c,j] += sum_i Fa[c,i] dS[i,j]
+  DCNET_TRY(sgemm_launch(frames, dP, dframes, C, N, N, nprob, 1, N, 1, CN, 0, N, 1, NN, 0, N, 1, CN, qa, nullptr, kb, 1.f, 0.f,
+                         nullptr, 0, 1, st));
+  return 0;
+}

@@ -1,0 +1,79 @@
+// Shared device/host helpers for libdcnet_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dcnet_b200.h"
+#include "host_error.h"
+
+#define DCNET_CHECK_ARG(cond, ...)                         \
+  do {                                                     \
+    if (!(cond)) return dcnet_set_error(-1, __VA_ARGS__);  \
+  } while (0)
+
+// after a kernel launch: count it and surface launch errors (no synchronisation)
+#define DCNET_LAUNCH_OK(name)                                                              \
+  do {                                                                                     \
+    dcnet_count_launch(1);                                                                 \
+    cudaError_t e__ = cudaPeekAtLastError();                                               \
+    if (e__ != cudaSuccess) {                                                              \
+      cudaGetLastError();                                                                  \
+      return dcnet_set_error((int)e__, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+    }                                                                                      \
+  } while (0)
+
+#define DCNET_CUDA(call, name)                                                             \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) return dcnet_set_error((int)e__, "%s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define DCNET_TRY(call)          \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `sh` must hold >= 32 floats; result valid in all threads
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? sh[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? sh[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// internal launcher of the generic fp32 GEMM (sgemm.cu)
+int sgemm_launch(const float* A, const float* B, float* C, int M, int N, int K, int batch, int kbatch,
+                 long long sAm, long long sAk, long long sAb, long long sAkb,
+                 long long sBk, long long sBn, long long sBb, long long sBkb,
+                 long long sCm, long long sCn, long long sCb,
+                 const int* idxA, const int* idxB, const int* idxC,
+                 float alpha, float beta, const float* colscale, long long sColB, int atomic, cudaStream_t st);

@@ -1,0 +1,416 @@
+// a1/a2/a6/a8: 1x1 conv + BatchNorm + ReLU (+ L2 norm over channels, + pixel-to-text dots), forward and backward.
+// Replaces ConvBatchNormReLU (model/darknet.py:118-156) + F.normalize(dim=1) (model/DCNet_model.py:359,469) and the
+// sim_score products (model/DCNet_model.py:530-535, train_DCNet.py:623-627).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// z[b,c,n] = u[b,c] + cc[c,n]   (text + coordinate terms of the split-weight fusion)
+// ------------------------------------------------------------------------------------------------------
+__global__ void init_bias_kernel(float* __restrict__ z, const float* __restrict__ u, const float* __restrict__ cc,
+                                 int B, int C, int N) {
+  const long long total = (long long)B * C * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const long long bc = i / N;
+    const int c = (int)(bc % C);
+    float v = 0.f;
+    if (u) v += u[bc];
+    if (cc) v += cc[(long long)c * N + n];
+    z[i] = v;
+  }
+}
+
+// du[b,c] = sum_n dz[b,c,n]   (one warp per row)
+__global__ void rowsum_kernel(const float* __restrict__ dz, float* __restrict__ du, long long rows, int N) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = dz + row * N;
+  float s = 0.f;
+  for (int n = lane; n < N; n += 32) s += p[n];
+  s = warp_sum(s);
+  if (lane == 0) du[row] = s;
+}
+
+// dcc[c,n] = sum_b dz[b,c,n]
+__global__ void batchsum_kernel(const float* __restrict__ dz, float* __restrict__ dcc, int B, long long CN) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < CN; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; b++) s += dz[(long long)b * CN + i];
+    dcc[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// BatchNorm batch statistics: one CTA per channel, two passes (mean, then centred second moment) so the
+// variance has no E[z^2]-E[z]^2 cancellation (fp32 path: <= 1e-5 relative).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ z, int B, int C, int N, float eps, float momentum,
+                                                       float* __restrict__ mean, float* __restrict__ invstd,
+                                                       float* __restrict__ rmean, float* __restrict__ rvar) {
+  __shared__ float sh[32];
+  const int c = blockIdx.x;
+  const long long M = (long long)B * N;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < M; i += blockDim.x) {
+    const long long b = i / N;
+    const int n = (int)(i - b * N);
+    s += z[(b * C + c) * N + n];
+  }
+  const float mu = block_sum(s, sh) / (float)M;
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < M; i += blockDim.x) {
+    const long long b = i / N;
+    const int n = (int)(i - b * N);
+    const float d = z[(b * C + c) * N + n] - mu;
+    q = fmaf(d, d, q);
+  }
+  const float ssq = block_sum(q, sh);
+  if (threadIdx.x == 0) {
+    const float var = ssq / (float)M;
+    mean[c] = mu;
+    invstd[c] = 1.0f / sqrtf(var + eps);
+    if (rmean) {
+      const float unb = (M > 1) ? ssq / (float)(M - 1) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mu;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * unb;
+    }
+  }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar, int C, float eps,
+                                     float* __restrict__ mean, float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    mean[c] = rmean[c];
+    invstd[c] = 1.0f / sqrtf(rvar[c] + eps);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// y = act(bn(z)) (+ channel L2 norm, + text dots).  CTA = 32 positions x 8 channel groups (256 threads); a warp
+// holds 32 consecutive positions of one channel -> every global access is a full 128-B line.  Each thread keeps
+// its CPT = C/8 channel values of one position in registers, so z is read once and y written once.
+// ------------------------------------------------------------------------------------------------------
+template <int CPT>
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float slope, int l2norm,
+                                                         float* __restrict__ y, const float* __restrict__ fa,
+                                                         float* __restrict__ sim, float* __restrict__ neg_sim, int B, int N) {
+  constexpr int C = CPT * 8;
+  __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
+  __shared__ float red[3][8][33];
+  const int b = blockIdx.y;
+  const int pl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + pl;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float sc = gamma[c] * invstd[c];
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - mean[c] * sc;
+    if (fa) {
+      s_fa[c] = fa[(long long)b * C + c];
+      s_fr[c] = fa[(long long)(B - 1 - b) * C + c];
+    }
+  }
+  __syncthreads();
+  const bool valid = n < N;
+  const float* zp = z + (long long)b * C * N + n;
+  float v[CPT];
+  float ss = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPT; i++) {
+    const int c = g + 8 * i;
+    float a = valid ? zp[(long long)c * N] : 0.f;
+    a = fmaf(a, s_scale[c], s_shift[c]);
+    a = a > 0.f ? a : a * slope;
+    v[i] = a;
+    ss = fmaf(a, a, ss);
+    if (fa) {
+      d1 = fmaf(a, s_fa[c], d1);
+      d2 = fmaf(a, s_fr[c], d2);
+    }
+  }
+  float inv = 1.f;
+  if (l2norm || fa) {
+    red[0][g][pl] = ss;
+    red[1][g][pl] = d1;
+    red[2][g][pl] = d2;
+    __syncthreads();
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      t0 += red[0][k][pl];
+      t1 += red[1][k][pl];
+      t2 += red[2][k][pl];
+    }
+    if (l2norm) inv = 1.f / fmaxf(sqrtf(t0), 1e-12f);
+    if (fa && g == 0 && valid) {
+      sim[(long long)b * N + n] = t1 * inv;
+      neg_sim[(long long)b * N + n] = t2 * inv;
+    }
+  }
+  if (valid) {
+    float* yp = y + (long long)b * C * N + n;
+#pragma unroll
+    for (int i = 0; i < CPT; i++) yp[(long long)(g + 8 * i) * N] = v[i] * inv;
+  }
+}
+
+// backward, phase 1 (see header).  Same tiling; recomputes the forward from z.
+template <int CPT>
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
+    const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float slope, int l2norm, const float* __restrict__ dy, const float* __restrict__ fa,
+    const float* __restrict__ dsim, const float* __restrict__ dneg, float* __restrict__ dv, float* __restrict__ sum_dv,
+    float* __restrict__ sum_dvz, float* __restrict__ dfa, int B, int N) {
+  constexpr int C = CPT * 8;
+  __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
+  __shared__ float red[2][8][33];
+  const int b = blockIdx.y;
+  const int pl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + pl;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float sc = gamma[c] * invstd[c];
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - mean[c] * sc;
+    if (fa) {
+      s_fa[c] = fa[(long long)b * C + c];
+      s_fr[c] = fa[(long long)(B - 1 - b) * C + c];
+    }
+  }
+  __syncthreads();
+  const bool valid = n < N;
+  const long long base = (long long)b * C * N + n;
+  const float ds = (fa && dsim && valid) ? dsim[(long long)b * N + n] : 0.f;
+  const float dn = (fa && dneg && valid) ? dneg[(long long)b * N + n] : 0.f;
+  float a[CPT], gr[CPT];
+  float ss = 0.f, dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPT; i++) {
+    const int c = g + 8 * i;
+    float t = valid ? z[base + (long long)c * N] : 0.f;
+    t = fmaf(t, s_scale[c], s_shift[c]);
+    const float act = t > 0.f ? t : t * slope;
+    a[i] = t;               // keep the pre-activation; act recomputed below
+    ss = fmaf(act, act, ss);
+    float gg = (valid && dy) ? dy[base + (long long)c * N] : 0.f;
+    if (fa) gg = fmaf(s_fa[c], ds, fmaf(s_fr[c], dn, gg));
+    gr[i] = gg;
+    dot = fmaf(gg, act, dot);
+  }
+  float inv = 1.f, dotn = 0.f;
+  if (l2norm) {
+    red[0][g][pl] = ss;
+    red[1][g][pl] = dot;
+    __syncthreads();
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      t0 += red[0][k][pl];
+      t1 += red[1][k][pl];
+    }
+    const float nrm = fmaxf(sqrtf(t0), 1e-12f);
+    inv = 1.f / nrm;
+    dotn = t1 * inv * inv;  // <g, yhat> / nrm, with yhat = act * inv
+  }
+  const int lane = pl;
+#pragma unroll
+  for (int i = 0; i < CPT; i++) {
+    const int c = g + 8 * i;
+    const float t = a[i];
+    const float act = t > 0.f ? t : t * slope;
+    // d(act): l2norm backward  (g - yhat <g,yhat>) / nrm
+    float da = l2norm ? (gr[i] * inv - act * inv * dotn) : gr[i];
+    const float dpre = valid ? da * (t > 0.f ? 1.f : slope) : 0.f;
+    if (valid) dv[base + (long long)c * N] = dpre;
+    // zhat = (z-mean)*invstd = (t - beta)/gamma  -- recompute from z to stay exact when gamma == 0
+    const float zh = valid ? (z[base + (long long)c * N] - mean[c]) * invstd[c] : 0.f;
+    const float s1 = warp_sum(dpre);
+    const float s2 = warp_sum(dpre * zh);
+    if (lane == 0) {
+      atomicAdd(sum_dv + c, s1);
+      atomicAdd(sum_dvz + c, s2);
+    }
+    if (fa && dfa) {
+      const float yh = act * inv;
+      const float f1 = warp_sum(ds * yh);
+      const float f2 = warp_sum(dn * yh);
+      if (lane == 0) {
+        atomicAdd(dfa + (long long)b * C + c, f1);
+        atomicAdd(dfa + (long long)(B - 1 - b) * C + c, f2);
+      }
+    }
+  }
+}
+
+__global__ void bn_act_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                        const float* __restrict__ gamma, const float* __restrict__ dv,
+                                        const float* __restrict__ sum_dv, const float* __restrict__ sum_dvz, int train,
+                                        float* __restrict__ dz, int B, int C, int N) {
+  const long long total = (long long)B * C * N;
+  const float invM = 1.f / (float)((long long)B * N);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / N) % C);
+    const float sc = gamma[c] * invstd[c];
+    float d = dv[i];
+    if (train) {
+      const float zh = (z[i] - mean[c]) * invstd[c];
+      d = d - sum_dv[c] * invM - zh * sum_dvz[c] * invM;
+    }
+    dz[i] = sc * d;
+  }
+}
+
+__global__ void coord_map_kernel(float* __restrict__ coord, int h, int w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  const float r = (float)(i / w), c = (float)(i % w);
+  const float fw = (float)w, fh = (float)h;
+  const float x0 = (r * 2.f - fw) / fw, y0 = (c * 2.f - fh) / fh;
+  const float x1 = ((r + 1.f) * 2.f - fw) / fw, y1 = ((c + 1.f) * 2.f - fh) / fh;
+  const int hw = h * w;
+  coord[0 * hw + i] = x0;
+  coord[1 * hw + i] = y0;
+  coord[2 * hw + i] = x1;
+  coord[3 * hw + i] = y1;
+  coord[4 * hw + i] = (x0 + x1) / 2.f;
+  coord[5 * hw + i] = (y0 + y1) / 2.f;
+  coord[6 * hw + i] = 1.f / fh;
+  coord[7 * hw + i] = 1.f / fw;
+}
+
+inline int ew_grid(long long total) {
+  long long g = (total + 255) / 256;
+  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+}  // namespace
+
+extern "C" int dcnet_conv1x1_fwd(const float* x1, int K1, const float* x2, int K2, const float* W, int ldw,
+                                 const float* u, const float* cc, float* z, int B, int C, int N, void* stream) {
+  DCNET_CHECK_ARG(x1 && W && z && K1 > 0 && B > 0 && C > 0 && N > 0, "conv1x1_fwd: bad arguments");
+  DCNET_CHECK_ARG((x2 != nullptr) == (K2 > 0) && ldw >= K1 + K2, "conv1x1_fwd: x2/K2/ldw inconsistent");
+  cudaStream_t st = as_stream(stream);
+  float beta = 0.f;
+  if (u || cc) {
+    init_bias_kernel<<<ew_grid((long long)B * C * N), 256, 0, st>>>(z, u, cc, B, C, N);
+    DCNET_LAUNCH_OK("conv1x1_fwd.init");
+    beta = 1.f;
+  }
+  DCNET_TRY(sgemm_launch(W, x1, z, C, N, K1, B, 1, ldw, 1, 0, 0, N, 1, (long long)K1 * N, 0, N, 1, (long long)C * N,
+                         nullptr, nullptr, nullptr, 1.f, beta, nullptr, 0, 0, st));
+  if (x2)
+    DCNET_TRY(sgemm_launch(W + K1, x2, z, C, N, K2, B, 1, ldw, 1, 0, 0, N, 1, (long long)K2 * N, 0, N, 1, (long long)C * N,
+                           nullptr, nullptr, nullptr, 1.f, 1.f, nullptr, 0, 0, st));
+  return 0;
+}
+
+extern "C" int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, float* dx1, int K1, float* dx2, int K2,
+                                      int B, int C, int N, void* stream) {
+  DCNET_CHECK_ARG(dz && W && B > 0 && C > 0 && N > 0 && ldw >= K1 + K2, "conv1x1_bwd_data: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (dx1)
+    DCNET_TRY(sgemm_launch(W, dz, dx1, K1, N, C, B, 1, 1, ldw, 0, 0, N, 1, (long long)C * N, 0, N, 1, (long long)K1 * N,
+                           nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 0, st));
+  if (dx2)
+    DCNET_TRY(sgemm_launch(W + K1, dz, dx2, K2, N, C, B, 1, 1, ldw, 0, 0, N, 1, (long long)C * N, 0, N, 1, (long long)K2 * N,
+                           nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 0, st));
+  return 0;
+}
+
+extern "C" int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1, const float* x2, int K2,
+                                        float* dW, int ldw, float* du, float* dcc, int B, int C, int N, void* stream) {
+  DCNET_CHECK_ARG(dz && B > 0 && C > 0 && N > 0 && ldw >= K1 + K2, "conv1x1_bwd_weight: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (dW && x1) {
+    // split the (b,n) reduction over CTAs along b; fp32 atomics into the zeroed columns
+    DCNET_CUDA(cudaMemset2DAsync(dW, (size_t)ldw * sizeof(float), 0, (size_t)(K1 + K2) * sizeof(float), C, st), "conv1x1_bwd_weight.memset");
+    DCNET_TRY(sgemm_launch(dz, x1, dW, C, K1, N, B, 1, N, 1, (long long)C * N, 0, 1, N, (long long)K1 * N, 0, ldw, 1, 0,
+                           nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 1, st));
+    if (x2)
+      DCNET_TRY(sgemm_launch(dz, x2, dW + K1, C, K2, N, B, 1, N, 1, (long long)C * N, 0, 1, N, (long long)K2 * N, 0, ldw, 1, 0,
+                             nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 1, st));
+  }
+  if (du) {
+    const long long rows = (long long)B * C;
+    rowsum_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(dz, du, rows, N);
+    DCNET_LAUNCH_OK("conv1x1_bwd_weight.du");
+  }
+  if (dcc) {
+    batchsum_kernel<<<ew_grid((long long)C * N), 256, 0, st>>>(dz, dcc, B, (long long)C * N);
+    DCNET_LAUNCH_OK("conv1x1_bwd_weight.dcc");
+  }
+  return 0;
+}
+
+extern "C" int dcnet_bn_stats(const float* z, int B, int C, int N, float eps, float momentum,
+                              float* mean, float* invstd, float* running_mean, float* running_var, void* stream) {
+  DCNET_CHECK_ARG(z && mean && invstd && B > 0 && C > 0 && N > 0, "bn_stats: bad arguments");
+  DCNET_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_stats: running_mean/var must both be given");
+  bn_stats_kernel<<<C, 256, 0, as_stream(stream)>>>(z, B, C, N, eps, momentum, mean, invstd, running_mean, running_var);
+  DCNET_LAUNCH_OK("bn_stats");
+  return 0;
+}
+
+extern "C" int dcnet_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
+                                   float* mean, float* invstd, void* stream) {
+  DCNET_CHECK_ARG(running_mean && running_var && mean && invstd && C > 0, "bn_eval_stats: bad arguments");
+  bn_eval_stats_kernel<<<ceil_div(C, 256), 256, 0, as_stream(stream)>>>(running_mean, running_var, C, eps, mean, invstd);
+  DCNET_LAUNCH_OK("bn_eval_stats");
+  return 0;
+}
+
+extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                float slope, int l2norm, float* y, const float* fa, float* sim, float* neg_sim,
+                                int B, int C, int N, void* stream) {
+  DCNET_CHECK_ARG(z && mean && invstd && gamma && beta && y && B > 0 && N > 0, "bn_act_fwd: bad arguments");
+  DCNET_CHECK_ARG(C == 512 || C == 256, "bn_act_fwd: C=%d unsupported (512 or 256)", C);
+  DCNET_CHECK_ARG(!fa || (sim && neg_sim), "bn_act_fwd: fa given without sim/neg_sim outputs");
+  DCNET_CHECK_ARG(B <= 65535, "bn_act_fwd: B too large");
+  dim3 grid(ceil_div(N, 32), B);
+  if (C == 512)
+    bn_act_fwd_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, sim, neg_sim, B, N);
+  else
+    bn_act_fwd_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, sim, neg_sim, B, N);
+  DCNET_LAUNCH_OK("bn_act_fwd");
+  return 0;
+}
+
+extern "C" int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                       float slope, int l2norm, const float* dy, const float* fa, const float* dsim,
+                                       const float* dneg_sim, float* dv, float* sum_dv, float* sum_dvz, float* dfa,
+                                       int B, int C, int N, void* stream) {
+  DCNET_CHECK_ARG(z && mean && invstd && gamma && beta && dv && sum_dv && sum_dvz && B > 0 && N > 0, "bn_act_bwd_reduce: bad arguments");
+  DCNET_CHECK_ARG(dy || fa, "bn_act_bwd_reduce: no incoming gradient");
+  DCNET_CHECK_ARG(C == 512 || C == 256, "bn_act_bwd_reduce: C=%d unsupported (512 or 256)", C);
+  dim3 grid(ceil_div(N, 32), B);
+  if (C == 512)
+    bn_act_bwd_reduce_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, dsim,
+                                                                         dneg_sim, dv, sum_dv, sum_dvz, dfa, B, N);
+  else
+    bn_act_bwd_reduce_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, dsim,
+                                                                         dneg_sim, dv, sum_dv, sum_dvz, dfa, B, N);
+  DCNET_LAUNCH_OK("bn_act_bwd_reduce");
+  return 0;
+}
+
+extern "C" int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const float* invstd, const float* gamma,
+                                      const float* dv, const float* sum_dv, const float* sum_dvz, int train,
+                                      float* dz, int B, int C, int N, void* stream) {
+  DCNET_CHECK_ARG(z && mean && invstd && gamma && dv && dz && B > 0 && C > 0 && N > 0, "bn_act_bwd_apply: bad arguments");
+  DCNET_CHECK_ARG(!train || (sum_dv && sum_dvz), "bn_act_bwd_apply: train mode needs the channel sums");
+  bn_act_bwd_apply_kernel<<<ew_grid((long long)B * C * N), 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, dv, sum_dv, sum_dvz,
+                                                                                            train, dz, B, C, N);
+  DCNET_LAUNCH_OK("bn_act_bwd_apply");
+  return 0;
+}
+
+extern "C" int dcnet_coord_map(float* coord, int h, int w, void* stream) {
+  DCNET_CHECK_ARG(coord && h > 0 && w > 0, "coord_map: bad arguments");
+  coord_map_kernel<<<ceil_div(h * w, 256), 256, 0, as_stream(stream)>>>(coord, h, w);
+  DCNET_LAUNCH_OK("coord_map");
+  return 0;
+}

@@ -1,0 +1,310 @@
+"""Drop-in for the reference's model/DCNet_model.py: same constructor, same forward(image, word_id, word_mask)
+signature and return tuples (model/DCNet_model.py:340, :646-650), same parameter names and shapes.
+The dense-correspondence hot path (:356-469, :489-505, :525-552, :612-637) runs on hand-written sm_100a kernels through
+dcnet_b200.ops; the text encoder, the 3x3 head and the location branch stay PyTorch like in the reference."""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .darknet import ConvBatchNormReLU
+
+TOP_K, NEG_N, CROSS_NEG_N = 30, 10, 5      # model/DCNet_model.py:391-392, :53
+
+
+class PackedList(list):
+    """A python list of per-rank / per-pixel tensors (what the reference returns) that remembers the packed tensor
+    it is a view of, so the fused losses can consume it without re-stacking."""
+    packed = None
+
+
+def _packed_list(t):
+    out = PackedList(t.unbind(0))
+    out.packed = t
+    return out
+
+
+def generate_coord(batch, height, width, device="cuda"):
+    """[batch,8,h,w] coordinate map (model/DCNet_model.py:23-39), generated on the device."""
+    return ops.coord_map(height, width, device).unsqueeze(0).repeat(batch, 1, 1, 1)
+
+
+class RNNEncoder(nn.Module):
+    """model/DCNet_model.py:124-188 (stays PyTorch / cuDNN)."""
+
+    def __init__(self, vocab_size, word_embedding_size, word_vec_size, hidden_size, bidirectional=False,
+                 input_dropout_p=0, dropout_p=0, n_layers=1, rnn_type='lstm', variable_lengths=True):
+        super().__init__()
+        self.variable_lengths = variable_lengths
+        self.embedding = nn.Embedding(vocab_size, word_embedding_size)
+        self.input_dropout = nn.Dropout(input_dropout_p)
+        self.mlp = nn.Sequential(nn.Linear(word_embedding_size, word_vec_size), nn.ReLU())
+        self.rnn_type = rnn_type
+        self.rnn = getattr(nn, rnn_type.upper())(word_vec_size, hidden_size, n_layers, batch_first=True,
+                                                 bidirectional=bidirectional, dropout=dropout_p)
+        self.num_dirs = 2 if bidirectional else 1
+
+    def forward(self, input_labels):
+        lengths = (input_labels != 0).sum(1).cpu().numpy().tolist()
+        assert max(lengths) == input_labels.size(1)
+        sort_ixs = np.argsort(lengths)[::-1].tolist()              # descending, same tie order as the reference
+        sorted_lengths = [lengths[i] for i in sort_ixs]
+        recover = [0] * len(lengths)
+        for r, s in enumerate(sort_ixs):
+            recover[s] = r
+        sort_t = torch.tensor(sort_ixs, device=input_labels.device, dtype=torch.long)
+        recover_t = torch.tensor(recover, device=input_labels.device, dtype=torch.long)
+        embedded = self.mlp(self.input_dropout(self.embedding(input_labels[sort_t])))
+        packed = nn.utils.rnn.pack_padded_sequence(embedded, sorted_lengths, batch_first=True)
+        output, _ = self.rnn(packed)
+        embedded = embedded[recover_t]           # already padded: pack/unpack of `embedded` is the identity up to zeroed pads
+        mask = (torch.arange(embedded.shape[1], device=embedded.device)[None, :] <
+                torch.tensor(lengths, device=embedded.device)[:, None])
+        embedded = embedded * mask[:, :, None].to(embedded.dtype)
+        output, _ = nn.utils.rnn.pad_packed_sequence(output, batch_first=True)
+        output = output[recover_t]
+        last = torch.tensor([l - 1 for l in lengths], device=output.device, dtype=torch.long)
+        sent = output[torch.arange(output.shape[0], device=output.device), last]
+        return sent, output, embedded
+
+
+class PhraseAttention(nn.Module):
+    """model/DCNet_model.py:190-219"""
+
+    def __init__(self, input_dim):
+        super().__init__()
+        self.fc = nn.Linear(input_dim, 1)
+
+    def forward(self, context, embedded, input_labels):
+        attn = F.softmax(self.fc(context).squeeze(2), dim=1)
+        attn = attn * (input_labels != 0).float()
+        attn = attn / attn.sum(1, keepdim=True)
+        return attn, torch.bmm(attn.unsqueeze(1), embedded).squeeze(1)
+
+
+class grounding_model(nn.Module):
+    def __init__(self, corpus=None, emb_size=256, jemb_drop_out=0.1, bert_model='bert-base-uncased',
+                 coordmap=True, leaky=False, dataset=None, light=False, visumodel=None, size=256):
+        """Extra keyword arguments (both optional, defaults = reference behaviour):
+        visumodel -- the Darknet backbone instance (reference: Darknet('./model/yolov3.cfg') + yolov3.weights);
+                     when None the surrounding checkout's model.darknet.Darknet is imported (drop-in use).
+        size      -- input resolution; sizes the location branch's Linear (1344 positions at 256, :259)."""
+        super().__init__()
+        self.coordmap = coordmap
+        self.light = light
+        self.lstm = corpus is not None
+        self.emb_size = emb_size
+        if not self.lstm:
+            raise NotImplementedError("BERT text branch needs pytorch_pretrained_bert (not in scope; use --lstm, README.md:36)")
+        if visumodel is None:
+            try:
+                from model.darknet import Darknet          # the host checkout's backbone (unchanged)
+            except Exception as e:                          # pragma: no cover
+                raise RuntimeError("grounding_model: pass visumodel=<Darknet instance>; could not import model.darknet (%s)" % e)
+            visumodel = Darknet(config_path='./model/yolov3.cfg')
+            visumodel.load_weights('./saved_models/yolov3.weights')
+        self.visumodel = visumodel
+        self.textdim, self.embdim = 1024, 512
+        self.textmodel = RNNEncoder(vocab_size=len(corpus), word_embedding_size=self.embdim, word_vec_size=self.textdim // 2,
+                                    hidden_size=self.textdim // 2, bidirectional=True, input_dropout_p=0.2, variable_lengths=True)
+        self.temperature = 10.
+        self.n_pos = sum((size // s) ** 2 for s in (32, 16, 8))
+        self.sub_attn = PhraseAttention(self.textdim)
+        self.loc_embedding = nn.Sequential(nn.Linear(8, 8), nn.BatchNorm1d(8), nn.ReLU())
+        self.loc_text_embedding = nn.Sequential(nn.Linear(self.n_pos, self.embdim), nn.BatchNorm1d(self.embdim), nn.ReLU())
+        self.loc_attn = PhraseAttention(self.textdim)
+        self.mapping_visu = nn.Sequential(OrderedDict([
+            ('0', ConvBatchNormReLU(1024, emb_size, 1, 1, 0, 1, leaky=leaky)),
+            ('1', ConvBatchNormReLU(512, emb_size, 1, 1, 0, 1, leaky=leaky)),
+            ('2', ConvBatchNormReLU(256, emb_size, 1, 1, 0, 1, leaky=leaky))]))
+        self.mapping_lang = nn.Sequential(
+            nn.Linear(self.textdim, emb_size), nn.BatchNorm1d(emb_size), nn.ReLU(), nn.Dropout(jemb_drop_out),
+            nn.Linear(emb_size, emb_size), nn.BatchNorm1d(emb_size), nn.ReLU())
+        self.corr_conv = nn.Sequential(OrderedDict([
+            (str(i), nn.Sequential(ConvBatchNormReLU(emb_size * 2, emb_size, 1, 1, 0, 1, leaky=leaky))) for i in range(3)]))
+        self.feature_map = nn.Sequential(nn.Conv1d(20, 20, stride=1, kernel_size=3, padding=1, bias=True), nn.Softmax(dim=1))
+        embin_size = emb_size * 2 + (8 if coordmap else 0)
+        if light:
+            self.fcn_emb = nn.Sequential(OrderedDict([
+                (str(i), nn.Sequential(ConvBatchNormReLU(embin_size, emb_size, 1, 1, 0, 1, leaky=leaky))) for i in range(3)]))
+            self.fcn_out = nn.Sequential(OrderedDict([
+                (str(i), nn.Sequential(nn.Conv2d(emb_size, 3 * 5, kernel_size=1))) for i in range(3)]))
+        else:
+            self.fcn_emb = nn.Sequential(OrderedDict([
+                (str(i), nn.Sequential(ConvBatchNormReLU(embin_size, emb_size, 1, 1, 0, 1, leaky=leaky),
+                                       ConvBatchNormReLU(emb_size, emb_size, 3, 1, 1, 1, leaky=leaky),
+                                       ConvBatchNormReLU(emb_size, emb_size, 1, 1, 0, 1, leaky=leaky))) for i in range(3)]))
+            self.fcn_out = nn.Sequential(OrderedDict([
+                (str(i), nn.Sequential(ConvBatchNormReLU(emb_size, emb_size // 2, 1, 1, 0, 1, leaky=leaky),
+                                       nn.Conv2d(emb_size // 2, 3 * 5, kernel_size=1))) for i in range(3)]))
+        self.exact_sampling = True     # reproduce the reference's random.sample stream
+        self._idx_cache = {}
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _pair_index(self, B, device):
+        key = ("pair", B, str(device))
+        if key not in self._idx_cache:
+            qa = torch.arange(B, device=device, dtype=torch.int32)
+            self._idx_cache[key] = (qa, qa ^ 1)
+        return self._idx_cache[key]
+
+    def map_visual(self, raw_fvisu):
+        """a2: fvisu[s] = normalize_c(ConvBNReLU_1x1(raw[s]))   (:356-359) -> 3 x [B,C,N_s]"""
+        return [self.mapping_visu._modules[str(s)].fused(raw_fvisu[s].flatten(2), l2norm=True) for s in range(3)]
+
+    def interframe(self, fv0):
+        """a4 (:381-430) -> packed q [30,P,C], k [30,P,C], neg [30,P,10,C]"""
+        B, C, N0 = fv0.shape
+        P = B // 2
+        dev = fv0.device
+        idx, _ = ops.interframe_topk(fv0.detach(), TOP_K)
+        negpos = torch.from_numpy(ops.pyrandom_interframe(P, TOP_K, N0, NEG_N)).to(dev, non_blocking=True)
+        negidx = ops.interframe_negidx(idx, negpos, N0)
+        pair = torch.arange(P, device=dev, dtype=torch.int32)[:, None]
+        img = torch.cat([(2 * pair).expand(P, TOP_K), (2 * pair + 1).expand(P, TOP_K),
+                         (2 * pair + 1).expand(P, TOP_K * NEG_N)], 1).reshape(-1)
+        col = torch.cat([idx // N0, idx % N0, negidx.reshape(P, -1)], 1).reshape(-1)
+        g = ops.gather_cols(fv0, img.contiguous(), col.contiguous()).view(P, TOP_K * (2 + NEG_N), C)
+        q = g[:, :TOP_K].transpose(0, 1)
+        k = g[:, TOP_K:2 * TOP_K].transpose(0, 1)
+        neg = g[:, 2 * TOP_K:].reshape(P, TOP_K, NEG_N, C).transpose(0, 1)
+        return q, k, neg, idx, negidx
+
+    def correspondence(self, fv, fa):
+        """a5 + a6 + a9 (:449-469, :525-535): co-attention both directions, corr_conv on [fvisu | attention] without a
+        cat, channel L2 norm, and the pixel-to-text dots fused into the same pass."""
+        B = fv[0].shape[0]
+        qa, kb = self._pair_index(B, fv[0].device)
+        corr, sim, neg_sim = [], [], []
+        for s in range(3):
+            attn = ops.coattention(fv[s], qa, kb, tau=self.temperature)
+            y, sm, ng = self.corr_conv._modules[str(s)][0].fused(fv[s], x2=attn, fa=fa, l2norm=True)
+            corr.append(y); sim.append(sm); neg_sim.append(ng)
+        return corr, sim, neg_sim
+
+    def fuse(self, corr, flang, coords):
+        """a7 + a8 (:489-505): split-weight form of cat([corr, flang_tile, coord]) -> 1x1 conv.
+        coords: 3 x [8,N_s] from ops.coord_map."""
+        out = []
+        C = corr[0].shape[1]
+        for s in range(3):
+            m = self.fcn_emb._modules[str(s)][0]
+            w = m.conv.weight.view(m.conv.weight.shape[0], -1)
+            u = F.linear(flang, w[:, C:2 * C])                                   # text term  W_l flang        [B,C]
+            cc = None
+            if self.coordmap:
+                cc = w[:, 2 * C:] @ coords[s]                                    # coord term W_c coord        [C,N]
+            out.append(m.fused(corr[s], u=u, cc=cc, l2norm=False))
+        return out
+
+    def crossmodal(self, fv0, context):
+        """a11 (:625-637, :41-112) -> packed q [N0,B,C], k [N0,B,1,C], neg [N0,B,5,C]"""
+        B, C, N0 = fv0.shape
+        dev = fv0.device
+        vit = ops.rownorm(fv0)                                   # F.normalize over the spatial axis (:629)
+        lag = ops.lagnorm(context)                               # [B,T,C]
+        fm = self.feature_map[0]
+        word, _ = ops.crossmodal_words(lag.detach(), vit.detach(), fm.weight, fm.bias)
+        negidx = torch.from_numpy(ops.pyrandom_crossmodal(B, N0, CROSS_NEG_N)).to(dev, non_blocking=True)
+        key = ("cm", B, N0, str(dev))
+        if key not in self._idx_cache:
+            b = torch.arange(B, device=dev, dtype=torch.int32)
+            pix = torch.arange(N0, device=dev, dtype=torch.long)
+            self._idx_cache[key] = (b[None, :].expand(N0, B).reshape(-1).contiguous(), pix[:, None].expand(N0, B).reshape(-1).contiguous(),
+                                    torch.full((N0 * B * CROSS_NEG_N,), B - 1, device=dev, dtype=torch.int32))
+        img_q, col_q, img_n = self._idx_cache[key]
+        T = lag.shape[1]
+        q = ops.gather_cols(vit, img_q, col_q).view(N0, B, C)
+        widx = (torch.arange(B, device=dev)[:, None] * T + word).t().reshape(-1)              # rows ordered (pixel, image)
+        k = lag.reshape(B * T, C).index_select(0, widx).view(N0, B, 1, C)
+        neg = ops.gather_cols(vit, img_n, negidx.permute(1, 0, 2).reshape(-1).contiguous()).view(N0, B, CROSS_NEG_N, C)
+        return q, k, neg, word, negidx
+
+    def location_branch(self, coords, obj_score, context, embedded, word_id):
+        """:556-610, stays PyTorch; written for any number of positions."""
+        B = obj_score[0].shape[0]
+        _, flang_loc = self.loc_attn(context, embedded, word_id)
+        flang_loc = F.normalize(flang_loc, p=2, dim=1)
+        coord_map_ = torch.cat([c.t() for c in coords], 0)[None].expand(B, -1, -1)
+        obj = F.normalize(torch.cat(obj_score, 1), p=2, dim=1)
+        SN = obj.shape[1]
+        emb = self.loc_embedding(coord_map_.reshape(-1, 8)).reshape(B, SN, -1)
+        emb = F.normalize(emb, p=2, dim=2)
+        rel = torch.bmm(emb, emb.transpose(1, 2)) * obj[:, None, :]
+        rel = self.loc_text_embedding(rel.reshape(-1, SN)).reshape(B, SN, -1).permute(0, 2, 1)
+        rel = F.normalize(rel, p=2, dim=1)
+        m = (rel * flang_loc[:, :, None]).sum(1)
+        mn, mx = m.min(1)[0][:, None], m.max(1)[0][:, None]
+        return (m - mn) / (mx - mn + 1e-6)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def forward(self, image, word_id, word_mask):
+        raw_fvisu = self.visumodel(image)
+        if not raw_fvisu[0].is_cuda:
+            raise RuntimeError("dcnet_b200.grounding_model: feature maps are on %s; the hot path has no CPU fallback" % raw_fvisu[0].device)
+        B = raw_fvisu[0].shape[0]
+        hw = [(m.shape[2], m.shape[3]) for m in raw_fvisu]
+        fv = self.map_visual(raw_fvisu)
+        if self.training:
+            q_if, k_if, neg_if, _, _ = self.interframe(fv[0])
+
+        max_len = int((word_id != 0).sum(1).max().item())
+        word_id = word_id[:, :max_len]
+        raw_flang, context, embedded = self.textmodel(word_id)
+        flang = F.normalize(self.mapping_lang(raw_flang), p=2, dim=1)
+        _, fa = self.sub_attn(context, embedded, word_id)
+        fa = F.normalize(fa, p=2, dim=1)
+
+        corr, sim, neg_sim = self.correspondence(fv, fa)
+        coords = [ops.coord_map(h, w, fa.device).flatten(1) for (h, w) in hw]
+        inter = self.fuse(corr, flang, coords)
+        outbox_raw = []
+        for s in range(3):
+            y = inter[s].view(B, -1, hw[s][0], hw[s][1])
+            for m in list(self.fcn_emb._modules[str(s)])[1:]:
+                y = m(y)
+            outbox_raw.append(self.fcn_out._modules[str(s)](y).flatten(2))
+
+        oo, obj = zip(*[ops.only_obj(outbox_raw[s], sim[s]) for s in range(3)])
+        locmap = self.location_branch(coords, list(obj), context, embedded, word_id)
+        loc, st = [], 0
+        for s in range(3):
+            n = hw[s][0] * hw[s][1]
+            loc.append(locmap[:, st:st + n].contiguous()); st += n
+        outbox = [ops.modulate_conf(outbox_raw[s], sim[s], loc[s]) for s in range(3)]
+
+        shp = lambda t, s: t.view(t.shape[:-1] + hw[s])
+        outbox = [shp(outbox[s], s) for s in range(3)]
+        sim_score = [shp(sim[s], s) for s in range(3)]
+        loc_score = [shp(loc[s], s) for s in range(3)]
+        if not self.training:
+            return outbox, sim_score, loc_score, [shp(o, s) for s, o in enumerate(oo)]
+        q_cm, k_cm, neg_cm, _, _ = self.crossmodal(fv[0], context)
+        self.last_neg_sim_score = [shp(neg_sim[s], s) for s in range(3)]      # train_DCNet.py:623-627, fused
+        corr_feat = [shp(corr[s], s) for s in range(3)]
+        return (outbox, sim_score, loc_score, corr_feat, fa[:, :, None, None],
+                _packed_list(q_if), _packed_list(k_if), _packed_list(neg_if),
+                _packed_list(q_cm), _packed_list(k_cm), _packed_list(neg_cm))
+
+
+def Crossmodal_corrspondence(lag_feature, vit_feature, lag_vit_map, top_k=1):
+    """Signature of model/DCNet_model.py:41.  lag_feature [B,T,C], vit_feature [B,C,N0], lag_vit_map [B,T,N0] (after
+    feature_map).  Returns the three python lists of the reference; negatives follow the reference's random.sample stream."""
+    assert top_k == 1
+    B, C, N0 = vit_feature.shape
+    dev = vit_feature.device
+    T = lag_feature.shape[1]
+    word = lag_vit_map.argmax(dim=1)
+    negidx = torch.from_numpy(ops.pyrandom_crossmodal(B, N0, CROSS_NEG_N)).to(dev)
+    b = torch.arange(B, device=dev, dtype=torch.int32)
+    pix = torch.arange(N0, device=dev, dtype=torch.long)
+    q = ops.gather_cols(vit_feature, b[None, :].expand(N0, B).reshape(-1).contiguous(),
+                        pix[:, None].expand(N0, B).reshape(-1).contiguous()).view(N0, B, C)
+    widx = (torch.arange(B, device=dev)[:, None] * T + word).t().reshape(-1)
+    k = lag_feature.reshape(B * T, C).index_select(0, widx).view(N0, B, 1, C)
+    neg = ops.gather_cols(vit_feature, torch.full((N0 * B * CROSS_NEG_N,), B - 1, device=dev, dtype=torch.int32),
+                          negidx.permute(1, 0, 2).reshape(-1).contiguous()).view(N0, B, CROSS_NEG_N, C)
+    return _packed_list(q), _packed_list(k), _packed_list(neg)

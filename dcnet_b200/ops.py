@@ -1,0 +1,508 @@
+"""torch.autograd wrappers over the C ABI (include/dcnet_b200.h).  PyTorch is plumbing here: it owns device memory,
+streams and the autograd tape; every forward/backward body is a call into libdcnet_sm100.so.  CPU tensors are rejected:
+there is no fallback path."""
+import random
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F32 = torch.float32
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _c(t, dtype=F32, name="tensor"):
+    """checked contiguous CUDA tensor of the expected dtype"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("dcnet_b200: %s is on %s -- the hot path is CUDA-only (no CPU fallback)" % (name, t.device))
+    if t.dtype != dtype:
+        raise RuntimeError("dcnet_b200: %s has dtype %s, expected %s" % (name, t.dtype, dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# host RNG (exact CPython random.sample stream)
+# ------------------------------------------------------------------------------------------------------------------
+def _rng_call(fn, out, *args):
+    st = random.getstate()
+    arr = np.array(st[1], dtype=np.uint32)
+    rc = fn(arr.ctypes.data, *args, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(_lib.last_error())
+    random.setstate((st[0], tuple(arr.tolist()), st[2]))
+    return out
+
+
+def pyrandom_interframe(P, top_k, N0, neg_n):
+    """positions [P,top_k,neg_n] int32 drawn exactly like model/DCNet_model.py:411-413 would advance `random`."""
+    out = np.empty((P, top_k, neg_n), dtype=np.int32)
+    return _rng_call(_lib.lib().dcnet_pyrandom_interframe, out, P, top_k, N0, neg_n)
+
+
+def pyrandom_crossmodal(B, N0, neg_n):
+    """pixel indices [B,N0,neg_n] int64 of image B-1, consuming the stream like model/DCNet_model.py:81-96."""
+    out = np.empty((B, N0, neg_n), dtype=np.int64)
+    return _rng_call(_lib.lib().dcnet_pyrandom_crossmodal, out, B, N0, neg_n)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# plain (non-differentiable) entry points
+# ------------------------------------------------------------------------------------------------------------------
+def sgemm(A, B, C, M, N, K, batch=1, kbatch=1, sA=(0, 0, 0, 0), sB=(0, 0, 0, 0), sC=(0, 0, 0), idxA=None, idxB=None, idxC=None,
+          alpha=1.0, beta=0.0, colscale=None, s_colscale=0, atomic=0):
+    _lib.call("dcnet_sgemm", _p(A), _p(B), _p(C), M, N, K, batch, kbatch, *sA, *sB, *sC, _p(idxA), _p(idxB), _p(idxC),
+              alpha, beta, _p(colscale), s_colscale, atomic, _st())
+    return C
+
+
+def coord_map(h, w, device):
+    out = torch.empty(8, h, w, device=device, dtype=F32)
+    _lib.call("dcnet_coord_map", _p(out), h, w, _st())
+    return out
+
+
+def interframe_topk(fv0, top_k=30):
+    """fv0 [2P,C,N0] -> idx [P,top_k] int64 (flat row*N0+col, descending, ties -> lower index)."""
+    fv0 = _c(fv0, name="fv0")
+    B, C, N0 = fv0.shape
+    P = B // 2
+    S0 = torch.empty(P, N0, N0, device=fv0.device, dtype=F32)
+    idx = torch.empty(P, top_k, device=fv0.device, dtype=torch.long)
+    _lib.call("dcnet_interframe_topk", _p(fv0), P, C, N0, top_k, _p(S0), _p(idx), _st())
+    return idx, S0
+
+
+def interframe_negidx(idx, negpos, N0):
+    P, top_k = idx.shape
+    neg_n = negpos.shape[-1]
+    out = torch.empty(P, top_k, neg_n, device=idx.device, dtype=torch.long)
+    _lib.call("dcnet_interframe_negidx", _p(idx), _p(_c(negpos, torch.int32, "negpos")), P, N0, top_k, neg_n, _p(out), _st())
+    return out
+
+
+def crossmodal_words(lag, vit, fm_w, fm_b):
+    lag, vit = _c(lag, name="lag"), _c(vit, name="vit")
+    B, T, C = lag.shape
+    N0 = vit.shape[2]
+    M = torch.empty(B, T, N0, device=lag.device, dtype=F32)
+    word = torch.empty(B, N0, device=lag.device, dtype=torch.long)
+    _lib.call("dcnet_crossmodal_words", _p(lag), _p(vit), _p(_c(fm_w.detach(), name="fm_w")), _p(_c(fm_b.detach(), name="fm_b")),
+              _p(M), _p(word), B, T, C, N0, _st())
+    return word, M
+
+
+def _anchors_arr(anchors):
+    a = np.ascontiguousarray(np.array(anchors, dtype=np.float32).reshape(-1))
+    return a
+
+
+def build_target(bbox, size, anchor_imsize, anchors_full, dense=False):
+    """-> (best_n, gi, gj [B] int64, t5 [B,5], gt list|None, gt_center list|None)   (train_DCNet.py:265-332)"""
+    bbox = _c(bbox.float(), name="bbox")
+    B = bbox.shape[0]
+    dev = bbox.device
+    best_n = torch.empty(B, device=dev, dtype=torch.long)
+    gi = torch.empty_like(best_n)
+    gj = torch.empty_like(best_n)
+    t5 = torch.empty(B, 5, device=dev, dtype=F32)
+    gt = gtc = None
+    ptrs = [None] * 6
+    if dense:
+        gs = [size // 32, size // 16, size // 8]
+        gt = [torch.empty(B, 3, 5, g, g, device=dev, dtype=F32) for g in gs]
+        gtc = [torch.empty(B, 5, g, g, device=dev, dtype=F32) for g in gs]
+        ptrs = [_p(t) for t in gt + gtc]
+    an = _anchors_arr(anchors_full)
+    assert an.size == 18
+    _lib.call("dcnet_build_target", _p(bbox), B, int(size), float(anchor_imsize), an.ctypes.data, _p(best_n), _p(gi), _p(gj), _p(t5),
+              *ptrs, _st())
+    return best_n, gi, gj, t5, gt, gtc
+
+
+def decode(pred, size, anchor_imsize, anchors_full, best_n=None, gi=None, gj=None, target=None):
+    """pred 3 x [B,15,N_s] (or [B,3,5,g,g]).  With (best_n,gi,gj): decode at that cell (train_DCNet.py:656-672); without:
+    arg-max decode (:766-816).  -> boxes [B,4] xyxy, iou [B]|None, best_n, gi, gj."""
+    pred = [_c(p.detach(), name="pred") for p in pred]
+    B = pred[0].shape[0]
+    dev = pred[0].device
+    mode = 0 if best_n is not None else 1
+    if mode == 1:
+        best_n = torch.empty(B, device=dev, dtype=torch.long)
+        gi = torch.empty_like(best_n)
+        gj = torch.empty_like(best_n)
+    boxes = torch.empty(B, 4, device=dev, dtype=F32)
+    iou = torch.empty(B, device=dev, dtype=F32) if target is not None else None
+    tgt = _c(target.float(), name="target") if target is not None else None
+    an = _anchors_arr(anchors_full)
+    _lib.call("dcnet_decode", _p(pred[0]), _p(pred[1]), _p(pred[2]), B, int(size) // 32, int(size), float(anchor_imsize), an.ctypes.data,
+              mode, _p(best_n), _p(gi), _p(gj), _p(boxes), _p(tgt), _p(iou), _st())
+    return boxes, iou, best_n, gi, gj
+
+
+def bbox_iou(b1, b2, x1y1x2y2=True):
+    b1, b2 = _c(b1.float(), name="box1"), _c(b2.float(), name="box2")
+    out = torch.empty(b1.shape[0], device=b1.device, dtype=F32)
+    _lib.call("dcnet_bbox_iou", _p(b1), _p(b2), b1.shape[0], int(bool(x1y1x2y2)), _p(out), _st())
+    return out
+
+
+def yolo_layer_decode(x, anchors, num_classes, image_dim):
+    x = _c(x, name="x")
+    B, _, g, _ = x.shape
+    A = len(anchors)
+    out = torch.empty(B, A * g * g, 5 + num_classes, device=x.device, dtype=F32)
+    an = _anchors_arr(anchors)
+    _lib.call("dcnet_yolo_layer_decode", _p(x), _p(out), B, A, num_classes, g, float(image_dim), an.ctypes.data, _st())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# differentiable ops
+# ------------------------------------------------------------------------------------------------------------------
+class _ConvBNAct(torch.autograd.Function):
+    """a1/a2/a6/a8: y = [l2norm_c] act(BN(W[:, :K1] x1 + W[:, K1:K1+K2] x2 + u 1^T + cc)), plus the fused a9 dots."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, running_mean, running_var, training, momentum, eps, slope, l2norm):
+        x1 = _c(x1, name="x1")
+        x2 = _c(x2, name="x2")
+        weight = _c(weight, name="weight")
+        u, cc, fa = _c(u, name="u"), _c(cc, name="cc"), _c(fa, name="fa")
+        gamma, beta = _c(gamma, name="gamma"), _c(beta, name="beta")
+        B, K1, N = x1.shape
+        K2 = 0 if x2 is None else x2.shape[1]
+        C, ldw = weight.shape
+        dev = x1.device
+        st = _st()
+        z = torch.empty(B, C, N, device=dev, dtype=F32)
+        _lib.call("dcnet_conv1x1_fwd", _p(x1), K1, _p(x2), K2, _p(weight), ldw, _p(u), _p(cc), _p(z), B, C, N, st)
+        mean = torch.empty(C, device=dev, dtype=F32)
+        invstd = torch.empty(C, device=dev, dtype=F32)
+        if training:
+            _lib.call("dcnet_bn_stats", _p(z), B, C, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
+        else:
+            _lib.call("dcnet_bn_eval_stats", _p(running_mean), _p(running_var), C, eps, _p(mean), _p(invstd), st)
+        y = torch.empty_like(z)
+        sim = neg = None
+        if fa is not None:
+            sim = torch.empty(B, N, device=dev, dtype=F32)
+            neg = torch.empty(B, N, device=dev, dtype=F32)
+        _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm), _p(y), _p(fa), _p(sim), _p(neg),
+                  B, C, N, st)
+        ctx.save_for_backward(x1, x2, weight, gamma, beta, fa, z, mean, invstd)
+        ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None)
+        if fa is None:
+            return y
+        return y, sim, neg
+
+    @staticmethod
+    def backward(ctx, dy, dsim=None, dneg=None):
+        x1, x2, weight, gamma, beta, fa, z, mean, invstd = ctx.saved_tensors
+        training, slope, l2norm, has_u, has_cc = ctx.cfg
+        B, K1, N = x1.shape
+        K2 = 0 if x2 is None else x2.shape[1]
+        C, ldw = weight.shape
+        dev = x1.device
+        st = _st()
+        dy = _c(dy, name="dy")
+        dsim = _c(dsim, name="dsim") if fa is not None else None
+        dneg = _c(dneg, name="dneg") if fa is not None else None
+        dv = torch.empty_like(z)
+        sums = torch.zeros(2, C, device=dev, dtype=F32)
+        dfa = torch.zeros(B, C, device=dev, dtype=F32) if (fa is not None and ctx.needs_input_grad[7]) else None
+        _lib.call("dcnet_bn_act_bwd_reduce", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, l2norm, _p(dy), _p(fa), _p(dsim),
+                  _p(dneg), _p(dv), _p(sums[0]), _p(sums[1]), _p(dfa), B, C, N, st)
+        _lib.call("dcnet_bn_act_bwd_apply", _p(z), _p(mean), _p(invstd), _p(gamma), _p(dv), _p(sums[0]), _p(sums[1]), int(training), _p(dv),
+                  B, C, N, st)
+        dz = dv
+        dx1 = torch.empty_like(x1) if ctx.needs_input_grad[0] else None
+        dx2 = torch.empty_like(x2) if (x2 is not None and ctx.needs_input_grad[1]) else None
+        if dx1 is not None or dx2 is not None:
+            _lib.call("dcnet_conv1x1_bwd_data", _p(dz), _p(weight), ldw, _p(dx1), K1, _p(dx2), K2, B, C, N, st)
+        dW = du = dcc = None
+        need_w = ctx.needs_input_grad[2]
+        if need_w:
+            dW = torch.zeros(C, ldw, device=dev, dtype=F32)
+        if has_u and ctx.needs_input_grad[5]:
+            du = torch.empty(B, C, device=dev, dtype=F32)
+        if has_cc and ctx.needs_input_grad[6]:
+            dcc = torch.empty(C, N, device=dev, dtype=F32)
+        if need_w or du is not None or dcc is not None:
+            _lib.call("dcnet_conv1x1_bwd_weight", _p(dz), _p(x1) if need_w else None, K1, _p(x2) if need_w else None, K2,
+                      _p(dW), ldw, _p(du), _p(dcc), B, C, N, st)
+        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, None, None, None, None, None, None, None)
+
+
+def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
+                momentum=0.999, eps=1e-5, slope=0.0, l2norm=False):
+    """x1 [B,K1,N] (+x2 [B,K2,N]); weight [C,ldw].  Returns y [B,C,N] or (y, sim, neg_sim) when fa [B,C] is given."""
+    return _ConvBNAct.apply(x1, x2, weight, gamma, beta, u, cc, fa, running_mean, running_var, bool(training), float(momentum),
+                            float(eps), float(slope), bool(l2norm))
+
+
+class _CoAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, frames, qa, kb, oidx, n_out, tau):
+        frames = _c(frames, name="frames")
+        qa, kb, oidx = (_c(t, torch.int32, "index") for t in (qa, kb, oidx))
+        F_, C, N = frames.shape
+        nprob = qa.numel()
+        out = torch.empty(n_out, C, N, device=frames.device, dtype=F32) if n_out == nprob else \
+            torch.zeros(n_out, C, N, device=frames.device, dtype=F32)
+        lse = torch.empty(nprob, N, device=frames.device, dtype=F32)
+        nbytes = _lib.lib().dcnet_coattn_workspace_bytes(nprob, C, N)
+        ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
+        _lib.call("dcnet_coattn_fwd", _p(frames), _p(qa), _p(kb), _p(oidx), nprob, _p(out), _p(lse), C, N, tau, _p(ws), nbytes, _st())
+        ctx.save_for_backward(frames, qa, kb, oidx, out, lse)
+        ctx.tau = tau
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        frames, qa, kb, oidx, out, lse = ctx.saved_tensors
+        F_, C, N = frames.shape
+        nprob = qa.numel()
+        dout = _c(dout, name="dout")
+        dframes = torch.zeros_like(frames)
+        nbytes = _lib.lib().dcnet_coattn_workspace_bytes(nprob, C, N)
+        ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
+        _lib.call("dcnet_coattn_bwd", _p(frames), _p(qa), _p(kb), _p(oidx), nprob, _p(out), _p(lse), _p(dout), _p(dframes), C, N, ctx.tau,
+                  _p(ws), nbytes, _st())
+        return dframes, None, None, None, None, None
+
+
+def coattention(frames, qa, kb, oidx=None, n_out=None, tau=10.0):
+    """frames [F,C,N]; problem i: queries frame qa[i] attend to frame kb[i]; result row oidx[i] of out [n_out,C,N]."""
+    if oidx is None:
+        oidx = torch.arange(qa.numel(), device=qa.device, dtype=torch.int32)
+    if n_out is None:
+        n_out = qa.numel()
+    return _CoAttn.apply(frames, qa, kb, oidx, int(n_out), float(tau))
+
+
+class _GatherCols(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, img, col):
+        src = _c(src, name="src")
+        img = _c(img, torch.int32, "img")
+        col = _c(col, torch.long, "col")
+        F_, C, N = src.shape
+        n = img.numel()
+        out = torch.empty(n, C, device=src.device, dtype=F32)
+        _lib.call("dcnet_gather_cols", _p(src), _p(img), _p(col), n, _p(out), C, N, _st())
+        ctx.save_for_backward(img, col)
+        ctx.shape = (F_, C, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, col = ctx.saved_tensors
+        F_, C, N = ctx.shape
+        dout = _c(dout, name="dout")
+        dsrc = torch.zeros(F_, C, N, device=dout.device, dtype=F32)
+        _lib.call("dcnet_scatter_cols_add", _p(dout), _p(img), _p(col), img.numel(), _p(dsrc), C, N, _st())
+        return dsrc, None, None
+
+
+def gather_cols(src, img, col):
+    """out[i,:] = src[img[i], :, col[i]]"""
+    return _GatherCols.apply(src, img, col)
+
+
+class _InfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, neg, T):
+        q, k, neg = _c(q, name="q"), _c(k, name="k"), _c(neg, name="neg")
+        G, C = q.shape
+        n = neg.shape[1]
+        out = torch.empty(G, device=q.device, dtype=F32)
+        _lib.call("dcnet_infonce_fwd", _p(q), _p(k), _p(neg), G, n, C, T, _p(out), _st())
+        ctx.save_for_backward(q, k, neg)
+        ctx.T = T
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, neg = ctx.saved_tensors
+        G, C = q.shape
+        n = neg.shape[1]
+        g = _c(g, name="grad")
+        dq, dk, dneg = torch.empty_like(q), torch.empty_like(k), torch.empty_like(neg)
+        _lib.call("dcnet_infonce_bwd", _p(q), _p(k), _p(neg), G, n, C, ctx.T, _p(g), 1, _p(dq), _p(dk), _p(dneg), _st())
+        return dq, dk, dneg, None
+
+
+def infonce_rows(q, k, neg, T=0.07):
+    """q,k [G,C]; neg [G,n,C] -> per-group CE loss [G]"""
+    return _InfoNCE.apply(q, k, neg, float(T))
+
+
+class _RowNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x, name="x")
+        L = x.shape[-1]
+        R = x.numel() // L
+        y = torch.empty_like(x)
+        nrm = torch.empty(R, device=x.device, dtype=F32)
+        _lib.call("dcnet_rownorm_fwd", _p(x), _p(y), _p(nrm), R, L, _st())
+        ctx.save_for_backward(y, nrm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, nrm = ctx.saved_tensors
+        dy = _c(dy, name="dy")
+        L = y.shape[-1]
+        dx = torch.empty_like(y)
+        _lib.call("dcnet_rownorm_bwd", _p(y), _p(nrm), _p(dy), _p(dx), y.numel() // L, L, _st())
+        return dx
+
+
+def rownorm(x):
+    """F.normalize over the innermost axis (model/DCNet_model.py:629 on the flattened spatial axis)"""
+    return _RowNorm.apply(x)
+
+
+class _LagNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, context):
+        context = _c(context, name="context")
+        B, T, C2 = context.shape
+        C = C2 // 2
+        lag = torch.empty(B, T, C, device=context.device, dtype=F32)
+        nrm = torch.empty(B, C, device=context.device, dtype=F32)
+        _lib.call("dcnet_lagnorm_fwd", _p(context), _p(lag), _p(nrm), B, T, C, _st())
+        ctx.save_for_backward(lag, nrm)
+        return lag
+
+    @staticmethod
+    def backward(ctx, dlag):
+        lag, nrm = ctx.saved_tensors
+        B, T, C = lag.shape
+        dlag = _c(dlag, name="dlag")
+        dctx = torch.empty(B, T, 2 * C, device=lag.device, dtype=F32)
+        _lib.call("dcnet_lagnorm_bwd", _p(lag), _p(nrm), _p(dlag), _p(dctx), B, T, C, _st())
+        return dctx
+
+
+def lagnorm(context):
+    """context [B,T,2C] -> normalize_words(context[:, :, 0::2])  (model/DCNet_model.py:631-632)"""
+    return _LagNorm.apply(context)
+
+
+class _OnlyObj(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, sim):
+        raw, sim = _c(raw, name="outbox"), _c(sim, name="sim")
+        B, _, N = raw.shape
+        oo = torch.empty(B, N, device=raw.device, dtype=F32)
+        obj = torch.empty(B, N, device=raw.device, dtype=F32)
+        _lib.call("dcnet_only_obj", _p(raw), _p(sim), _p(oo), _p(obj), B, N, _st())
+        ctx.save_for_backward(sim, oo)
+        return oo, obj
+
+    @staticmethod
+    def backward(ctx, doo, dobj):
+        sim, oo = ctx.saved_tensors
+        B, N = sim.shape
+        d = (doo + dobj * sim) / 3.0
+        draw = torch.zeros(B, 3, 5, N, device=sim.device, dtype=F32)
+        draw[:, :, 4] = d[:, None]
+        return draw.view(B, 15, N), dobj * oo
+
+
+def only_obj(raw, sim):
+    """raw [B,15,N], sim [B,N] -> (only_obj, obj_score) [B,N]   (model/DCNet_model.py:545-552)"""
+    return _OnlyObj.apply(raw, sim)
+
+
+class _Modulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, sim, loc):
+        raw, sim, loc = _c(raw, name="outbox"), _c(sim, name="sim"), _c(loc, name="loc")
+        B, _, N = raw.shape
+        out = torch.empty_like(raw)
+        _lib.call("dcnet_modulate_conf_fwd", _p(raw), _p(sim), _p(loc), _p(out), B, N, _st())
+        ctx.save_for_backward(raw, sim, loc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        raw, sim, loc = ctx.saved_tensors
+        B, _, N = raw.shape
+        dout = _c(dout, name="dout")
+        draw, dsim, dloc = torch.empty_like(raw), torch.empty_like(sim), torch.empty_like(loc)
+        _lib.call("dcnet_modulate_conf_bwd", _p(raw), _p(sim), _p(loc), _p(dout), _p(draw), _p(dsim), _p(dloc), B, N, _st())
+        return draw, dsim, dloc
+
+
+def modulate_conf(raw, sim, loc):
+    """conf logits (channels 5a+4) *= sim*loc   (model/DCNet_model.py:612-621)"""
+    return _Modulate.apply(raw, sim, loc)
+
+
+class _GroundLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, best_n, gi, gj, t5, w_coord, margin, *maps):
+        maps = [_c(m, name="map") for m in maps]   # pred0..2, sim0..2, neg0..2, loc0..2
+        B = maps[0].shape[0]
+        g0 = int(round(maps[3].shape[1] ** 0.5))
+        dev = maps[0].device
+        losses = torch.empty(3, device=dev, dtype=F32)
+        lse = torch.empty(2, B, device=dev, dtype=F32)
+        _lib.call("dcnet_ground_loss_fwd", *[_p(m) for m in maps], _p(best_n), _p(gi), _p(gj), _p(t5), B, g0, w_coord, margin,
+                  _p(losses), _p(lse[0]), _p(lse[1]), _st())
+        ctx.save_for_backward(best_n, gi, gj, t5, lse, *maps)
+        ctx.cfg = (B, g0, w_coord, margin)
+        return losses
+
+    @staticmethod
+    def backward(ctx, gl):
+        best_n, gi, gj, t5, lse = ctx.saved_tensors[:5]
+        maps = ctx.saved_tensors[5:]
+        B, g0, w_coord, margin = ctx.cfg
+        gl = _c(gl, name="grad")
+        grads = [torch.empty_like(m) for m in maps]
+        _lib.call("dcnet_ground_loss_bwd", *[_p(m) for m in maps], _p(best_n), _p(gi), _p(gj), _p(t5), B, g0, w_coord, margin,
+                  _p(lse[0]), _p(lse[1]), _p(gl), *[_p(g) for g in grads], _st())
+        return (None, None, None, None, None, None, *grads)
+
+
+def ground_losses(pred, sim, neg_sim, loc, best_n, gi, gj, t5, w_coord=5.0, margin=0.1):
+    """pred 3 x [B,15,N_s]; sim/neg_sim/loc 3 x [B,N_s] -> tensor [yolo_loss, rank_loss, loc_loss] (train_DCNet.py:45-72,173-220)."""
+    flat = [p.reshape(p.shape[0], 15, -1) for p in pred] + [s.reshape(s.shape[0], -1) for s in sim] + \
+           [s.reshape(s.shape[0], -1) for s in neg_sim] + [s.reshape(s.shape[0], -1) for s in loc]
+    return _GroundLoss.apply(best_n, gi, gj, t5, float(w_coord), float(margin), *flat)
+
+
+class _IoULoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, t, size_average):
+        x, t = _c(x, name="input"), _c(t.to(x.dtype), name="target")
+        acc = torch.zeros(2, device=x.device, dtype=F32)
+        _lib.call("dcnet_iou_loss_sums", _p(x), _p(t), x.numel(), _p(acc), _st())
+        ctx.save_for_backward(x, t, acc)
+        ctx.scale = (1.0 / x.shape[0]) if size_average else 1.0
+        return (x.shape[0] - acc[0] / acc[1]) * ctx.scale
+
+    @staticmethod
+    def backward(ctx, g):
+        x, t, acc = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        _lib.call("dcnet_iou_loss_bwd", _p(x), _p(t), x.numel(), _p(acc), float(g.item()) * ctx.scale, _p(dx), _st())
+        return dx, None, None
+
+
+def iou_loss(x, target, size_average=True):
+    return _IoULoss.apply(x, target, bool(size_average))

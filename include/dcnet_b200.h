@@ -1,0 +1,217 @@
+/*
+ * dcnet_b200.h -- C ABI of libdcnet_sm100.so, the B200-native (sm_100a) implementation of the
+ * DCNet dense-correspondence hot path (mengcaopku/DCNet, model/DCNet_model.py:356-650 and the loss /
+ * target / decode functions of train_DCNet.py:45-332).
+ *
+ * The reference has no FFI of its own (it is 100 % PyTorch); each entry point below names the reference
+ * lines it replaces.  Conventions:
+ *   - plain pointers and sizes only; every buffer (inputs, outputs, workspace) is DEVICE memory owned by
+ *     the caller unless the name starts with h_ (host memory); the library never allocates, frees or
+ *     retains pointers;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no implicit synchronisation;
+ *   - return 0 on success, <0 for an argument error, >0 = cudaError_t of the failed launch;
+ *     dcnet_last_error() returns a thread-local message;
+ *   - feature maps are fp32 [B, C, N] = flattened NCHW exactly as the reference holds them
+ *     (N = h*w innermost); images 2p and 2p+1 are the two frames of pair p (model/DCNet_model.py:365-374);
+ *   - int64 index outputs match torch.long in the reference API.
+ */
+#ifndef DCNET_B200_H_
+#define DCNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCNET_ABI_VERSION 1
+#define DCNET_API __attribute__((visibility("default")))
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+DCNET_API int dcnet_abi_version(void);
+DCNET_API const char* dcnet_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+DCNET_API long long dcnet_launch_count(void);
+
+/* ---- generic strided batched fp32 GEMM (building block; exact-fp32 path) ------------------------------
+ * C[b](m,n) = alpha * sum_{kb<kbatch} sum_k A[b](m,k;kb) * B[b](k,n;kb) * colscale[b](n) + beta * C[b](m,n)
+ * element (m,k) of A for batch b, k-batch kb: A + ia(b)*sAb + kb*sAkb + m*sAm + k*sAk   (ia(b) = idxA ? idxA[b] : b)
+ * atomic != 0: C is updated with atomicAdd (beta ignored, caller pre-zeroes).                           */
+DCNET_API int dcnet_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int batch, int kbatch,
+                          long long sAm, long long sAk, long long sAb, long long sAkb,
+                          long long sBk, long long sBn, long long sBb, long long sBkb,
+                          long long sCm, long long sCn, long long sCb,
+                          const int* idxA, const int* idxB, const int* idxC,
+                          float alpha, float beta, const float* colscale, long long sColscaleB,
+                          int atomic, void* stream);
+
+/* ---- a1/a2/a6/a8: 1x1 conv (no bias) + BatchNorm + ReLU (+ L2 norm over channels) ---------------------
+ * replaces ConvBatchNormReLU (model/darknet.py:118-156) as used by mapping_visu (:356-359), corr_conv
+ * (:467-469) and fcn_emb[s][0] (:505), and F.normalize(dim=1).
+ *
+ * conv1x1_fwd:  z[b] = W[:, 0:K1] x1[b] + W[:, K1:K1+K2] x2[b] + u[b] 1^T + cc
+ *   x1 [B,K1,N]; x2 [B,K2,N] or NULL (two-source K loop: corr_conv reads [fvisu | attention] without a cat);
+ *   W [C, ldw] row-major (ldw >= K1+K2); u [B,C] or NULL (text term W_l flang of the fusion, Appendix A.9);
+ *   cc [C,N] or NULL (coordinate term W_c coord); z [B,C,N].                                              */
+DCNET_API int dcnet_conv1x1_fwd(const float* x1, int K1, const float* x2, int K2, const float* W, int ldw,
+                                const float* u, const float* cc, float* z, int B, int C, int N, void* stream);
+/* dx1 = W[:,0:K1]^T dz, dx2 = W[:,K1:]^T dz (either may be NULL) */
+DCNET_API int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, float* dx1, int K1, float* dx2, int K2,
+                                     int B, int C, int N, void* stream);
+/* dW[:,0:K1] = sum_b dz[b] x1[b]^T, dW[:,K1:] = sum_b dz[b] x2[b]^T  (overwrites those columns of dW [C,ldw]);
+ * du [B,C] = sum_n dz (or NULL); dcc [C,N] = sum_b dz (or NULL)                                           */
+DCNET_API int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1, const float* x2, int K2,
+                                       float* dW, int ldw, float* du, float* dcc, int B, int C, int N, void* stream);
+
+/* BatchNorm statistics of z [B,C,N] over (B,N): mean[C], invstd[C] = 1/sqrt(biased var + eps); when
+ * running_mean/var are non-NULL they are updated in place with `momentum` and the UNBIASED variance
+ * (PyTorch convention; the reference uses momentum 0.999, eps 1e-5, model/darknet.py:145).               */
+DCNET_API int dcnet_bn_stats(const float* z, int B, int C, int N, float eps, float momentum,
+                             float* mean, float* invstd, float* running_mean, float* running_var, void* stream);
+/* eval mode: mean = running_mean, invstd = 1/sqrt(running_var + eps) */
+DCNET_API int dcnet_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
+                                  float* mean, float* invstd, void* stream);
+/* y = act(gamma (z-mean) invstd + beta), act = ReLU (slope 0) or LeakyReLU(slope); if l2norm: y /= max(||y||_c, 1e-12).
+ * If fa != NULL (text vectors [B,C], a9): sim[b,n] = <fa[b], y[b,:,n]>, neg_sim[b,n] = <fa[B-1-b], y[b,:,n]>
+ * (model/DCNet_model.py:530-535, train_DCNet.py:623-627), fused so corr_feat is read once.               */
+DCNET_API int dcnet_bn_act_fwd(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                               float slope, int l2norm, float* y, const float* fa, float* sim, float* neg_sim,
+                               int B, int C, int N, void* stream);
+/* Backward of bn_act_fwd in train mode (batch statistics).  Two launches:
+ *   reduce: dv = d(pre-activation) from dy (+ dsim/dneg_sim), written to `dv` [B,C,N]; accumulates
+ *           sum_dv[C], sum_dvz[C] (caller zeroes), dfa [B,C] (caller zeroes, may be NULL);
+ *   apply : dz = gamma invstd (dv - sum_dv/M - zhat sum_dvz/M)  (in place allowed: dz == dv);
+ *           dgamma = sum_dvz, dbeta = sum_dv.
+ * train == 0 (running statistics): dz = gamma invstd dv.                                                  */
+DCNET_API int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                      float slope, int l2norm, const float* dy, const float* fa, const float* dsim,
+                                      const float* dneg_sim, float* dv, float* sum_dv, float* sum_dvz, float* dfa,
+                                      int B, int C, int N, void* stream);
+DCNET_API int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const float* invstd, const float* gamma,
+                                     const float* dv, const float* sum_dv, const float* sum_dvz, int train,
+                                     float* dz, int B, int C, int N, void* stream);
+
+/* ---- a7: coordinate map (model/DCNet_model.py:23-39), [8,h,w], batch independent ---------------------- */
+DCNET_API int dcnet_coord_map(float* coord, int h, int w, void* stream);
+
+/* ---- a5/a20: co-attention (model/DCNet_model.py:449-459, model/test_DCNet_model.py:247-274) -----------
+ * One "problem" i is one direction: queries = frame qa[i], keys/values = frame kb[i] of frames [F,C,N]:
+ *   S = Fa^T Fb,  P = softmax_j(tau S),  out[oidx[i]] = Fb P^T  ([C,N]),  lse[i][n] = log sum_j exp(tau S[n,j]).
+ * A training pair p is the two problems (2p,2p+1) and (2p+1,2p); the test-time clip path uses the centre
+ * direction only.  S / P never leave the chip in the tcgen05 path; workspace is scratch for the rest.     */
+DCNET_API size_t dcnet_coattn_workspace_bytes(int nprob, int C, int N);
+DCNET_API int dcnet_coattn_fwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob,
+                               float* out, float* lse, int C, int N, float tau, void* workspace, size_t workspace_bytes,
+                               void* stream);
+/* dframes [F,C,N] += gradient (caller zeroes); dout/out indexed by oidx like the forward */
+DCNET_API int dcnet_coattn_bwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob,
+                               const float* out, const float* lse, const float* dout, float* dframes,
+                               int C, int N, float tau, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a4: inter-frame patch correspondence (model/DCNet_model.py:381-430) ------------------------------
+ * fv0 [2P,C,N0].  S0[p] = F1^T F2 in exact fp32; idx[p, r] = flat index (row*N0+col) of the r-th largest
+ * entry (descending; ties -> lower flat index first).  S0 scratch [P,N0,N0] is caller-provided.           */
+DCNET_API int dcnet_interframe_topk(const float* fv0, int P, int C, int N0, int top_k, float* S0, long long* idx, void* stream);
+/* negative index mapping: the host draws POSITIONS pos in [0,N0-2] with the reference's RNG stream
+ * (random.sample over a population of N0-1, :411-413); the kernel maps them to pixels skipping col:
+ * pix = pos + (pos >= col).  negidx [P,top_k,neg_n] int64 out.                                            */
+DCNET_API int dcnet_interframe_negidx(const long long* idx, const int* negpos, int P, int N0, int top_k, int neg_n,
+                                      long long* negidx, void* stream);
+
+/* ---- generic column gather / scatter-add (a4, a11 gathers and their backward) -------------------------
+ * out[i, :] = src[img[i], :, col[i]]   (src [F,C,N]; out [n,C]);  backward: dsrc[img[i], :, col[i]] += dout[i,:] */
+DCNET_API int dcnet_gather_cols(const float* src, const int* img, const long long* col, int n, float* out, int C, int N, void* stream);
+DCNET_API int dcnet_scatter_cols_add(const float* dout, const int* img, const long long* col, int n, float* dsrc, int C, int N, void* stream);
+
+/* ---- a12/a13: InfoNCE-style contrastive loss (train_DCNet.py:114-166) ----------------------------------
+ * q [G,C], k [G,C], neg [G,n,C] (G = ranks*pairs or pixels*images).  loss_g = CE([q^.k^, q^.n^_j]/T, 0) with every
+ * vector L2-normalised (eps 1e-12).  rowloss [G]; the mean is taken by the caller (all groups have equal size).
+ * bwd: dq,dk,dneg given gscale[g*gstride] = dL/d(rowloss_g) (gstride 0 = one shared scalar).                                            */
+DCNET_API int dcnet_infonce_fwd(const float* q, const float* k, const float* neg, int G, int n, int C, float T, float* rowloss, void* stream);
+DCNET_API int dcnet_infonce_bwd(const float* q, const float* k, const float* neg, int G, int n, int C, float T, const float* gscale,
+                                int gstride, float* dq, float* dk, float* dneg, void* stream);
+
+/* ---- a11: cross-modal block (model/DCNet_model.py:625-637, :41-112) ------------------------------------
+ * axis-normalisations used only there: rows = F.normalize over the innermost axis of [R, L] rows
+ * (vit: over the spatial axis, :629); lag: context [B,T,2C] -> even channels (nearest 0.5x, :631) normalised over
+ * the WORD axis (:632) -> lag [B,T,C].                                                                    */
+DCNET_API int dcnet_rownorm_fwd(const float* x, float* y, float* nrm, long long R, int L, void* stream);
+DCNET_API int dcnet_rownorm_bwd(const float* y, const float* nrm, const float* dy, float* dx, long long R, int L, void* stream);
+DCNET_API int dcnet_lagnorm_fwd(const float* context, float* lag, float* nrm, int B, int T, int C, void* stream);
+DCNET_API int dcnet_lagnorm_bwd(const float* lag, const float* nrm, const float* dlag, float* dcontext, int B, int T, int C, void* stream);
+/* word[b,n] = argmax_t softmax_t(Conv1d_{T->T,k=3,pad=1}(M)[b,t,n]) (first maximum), M = lag . vit [B,T,N0]
+ * computed inside (scratch M [B,T,N0] caller-provided).  fm_w [T,T,3], fm_b [T].                          */
+DCNET_API int dcnet_crossmodal_words(const float* lag, const float* vit, const float* fm_w, const float* fm_b,
+                                     float* M, long long* word, int B, int T, int C, int N0, void* stream);
+
+/* ---- a14: build_target (train_DCNet.py:265-332) -------------------------------------------------------
+ * bbox [B,4] xyxy (pixels, already clamped).  Per sample: best_n (0..8, first maximum of the 9 anchor IoUs),
+ * gi, gj (cell of the box centre at the best scale), t = (tx,ty,tw,th,1).  anchors: 9 (w,h) pairs, largest first.
+ * If gt0..2 / gtc0..2 are non-NULL they receive the dense targets [B,3,5,g,g] / [B,5,g,g] (zero filled + scatter). */
+DCNET_API int dcnet_build_target(const float* bbox, int B, int size, float anchor_imsize, const float* h_anchors9x2,
+                                 long long* best_n, long long* gi, long long* gj, float* t5,
+                                 float* gt0, float* gt1, float* gt2, float* gtc0, float* gtc1, float* gtc2, void* stream);
+
+/* ---- a10: objectness / confidence modulation (model/DCNet_model.py:545-552, :612-621) -------------------
+ * raw [B,15,N] -> only_obj [B,N] = mean_a raw[b,5a+4,n]; obj [B,N] = only_obj*sim;  (either out may be NULL)  */
+DCNET_API int dcnet_only_obj(const float* raw, const float* sim, float* only_obj, float* obj, int B, int N, void* stream);
+/* out = raw with channels 5a+4 multiplied by sim*loc */
+DCNET_API int dcnet_modulate_conf_fwd(const float* raw, const float* sim, const float* loc, float* out, int B, int N, void* stream);
+DCNET_API int dcnet_modulate_conf_bwd(const float* raw, const float* sim, const float* loc, const float* dout,
+                                      float* draw, float* dsim, float* dloc, int B, int N, void* stream);
+
+/* ---- a16/a17: grounding losses (train_DCNet.py:45-72, :173-220) ----------------------------------------
+ * pred0..2 [B,15,N_s] (modulated), sim/neg_sim/loc 0..2 [B,N_s]; targets from dcnet_build_target.
+ * losses[0..2] = yolo_loss, rank_loss, loc_loss (batch means as in the reference).
+ * bwd: gl[3] = dL/d(yolo,rank,loc) (device); writes dpred (dense, zero elsewhere), dsim, dneg_sim, dloc.      */
+DCNET_API int dcnet_ground_loss_fwd(const float* pred0, const float* pred1, const float* pred2,
+                                    const float* sim0, const float* sim1, const float* sim2,
+                                    const float* neg0, const float* neg1, const float* neg2,
+                                    const float* loc0, const float* loc1, const float* loc2,
+                                    const long long* best_n, const long long* gi, const long long* gj, const float* t5,
+                                    int B, int g0, float w_coord, float margin, float* losses, float* lse_conf, float* lse_loc,
+                                    void* stream);
+DCNET_API int dcnet_ground_loss_bwd(const float* pred0, const float* pred1, const float* pred2,
+                                    const float* sim0, const float* sim1, const float* sim2,
+                                    const float* neg0, const float* neg1, const float* neg2,
+                                    const float* loc0, const float* loc1, const float* loc2,
+                                    const long long* best_n, const long long* gi, const long long* gj, const float* t5,
+                                    int B, int g0, float w_coord, float margin, const float* lse_conf, const float* lse_loc,
+                                    const float* gl,
+                                    float* dpred0, float* dpred1, float* dpred2, float* dsim0, float* dsim1, float* dsim2,
+                                    float* dneg0, float* dneg1, float* dneg2, float* dloc0, float* dloc1, float* dloc2,
+                                    void* stream);
+
+/* ---- a18: decode (train_DCNet.py:656-690 at the GT cell; :766-816 arg-max) + a15 bbox_iou ---------------
+ * mode 0: decode at the given (best_n, gi, gj); mode 1: arg-max over the 3*SN conf logits (first maximum in
+ * (scale, anchor, gj, gi) order) and the cell is written to best_n/gi/gj.  boxes [B,4] xyxy pixels;
+ * iou [B] vs target boxes (NULL to skip).                                                                  */
+DCNET_API int dcnet_decode(const float* pred0, const float* pred1, const float* pred2, int B, int g0, int size,
+                           float anchor_imsize, const float* h_anchors9x2, int mode,
+                           long long* best_n, long long* gi, long long* gj, float* boxes, const float* target, float* iou,
+                           void* stream);
+DCNET_API int dcnet_bbox_iou(const float* b1, const float* b2, int n, int x1y1x2y2, float* iou, void* stream);
+
+/* ---- a19: YOLOLayer COCO-head decode (model/darknet.py:262-296, :365-375) -------------------------------
+ * x [B, A*(5+nc), g, g] -> out [B, A*g*g, 5+nc]; anchors A (w,h) pairs (un-scaled, pixels at 416).         */
+DCNET_API int dcnet_yolo_layer_decode(const float* x, float* out, int B, int A, int nc, int g, float image_dim,
+                                      const float* h_anchorsAx2, void* stream);
+
+/* ---- a21: IoULoss (utils/losses.py:26-34): acc[0] += sum(sig(x) t), acc[1] += sum(sig(x)+t-sig(x) t) -- */
+DCNET_API int dcnet_iou_loss_sums(const float* x, const float* t, long long n, float* acc2, void* stream);
+DCNET_API int dcnet_iou_loss_bwd(const float* x, const float* t, long long n, const float* acc2, float gscale, float* dx, void* stream);
+
+/* ---- host: exact emulation of CPython's random.sample() stream (model/DCNet_model.py:87, :413) --------
+ * state625: the 625 uint32 words of random.getstate()[1] (624 MT19937 words + position), updated in place so
+ * the caller can random.setstate() afterwards.  No device work.                                           */
+/* negpos [P*top_k*neg_n]: random.sample(population of N0-1, neg_n) positions, pairs outer, ranks inner */
+DCNET_API int dcnet_pyrandom_interframe(uint32_t* h_state625, int P, int top_k, int N0, int neg_n, int* h_negpos);
+/* negidx [B*N0*neg_n]: for every (image ii, pixel jj) the reference draws B samples (population N0-1 when
+ * index==ii else N0) and keeps the last (index=B-1); returned as pixel indices of image B-1.               */
+DCNET_API int dcnet_pyrandom_crossmodal(uint32_t* h_state625, int B, int N0, int neg_n, long long* h_negidx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DCNET_B200_H_ */

@@ -1,0 +1,119 @@
+"""CPU-side checks (-m "not gpu"): C-ABI library loads and exports every declared symbol, host RNG emulation is exact,
+the model mirror has the reference's parameter names/shapes, and the product path refuses to run without CUDA."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from dcnet_b200 import _lib, ops
+from dcnet_b200.model.DCNet_model import grounding_model
+from oracle import ref_loader
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+class StubBackbone(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.maps = None
+
+    def forward(self, x):
+        return list(self.maps)
+
+
+def test_library_exports_every_declared_symbol():
+    protos = _lib.parse_header()
+    assert len(protos) >= 40
+    L = _lib.lib()
+    for name in protos:
+        assert hasattr(L, name), name
+    assert L.dcnet_abi_version() == 1
+    assert isinstance(_lib.launch_count(), int)
+
+
+def test_argument_errors_are_reported_not_thrown_across_abi():
+    L = _lib.lib()
+    rc = L.dcnet_coord_map(None, 0, 0, None)
+    assert rc < 0 and "coord_map" in _lib.last_error()
+    with pytest.raises(RuntimeError, match="coord_map"):
+        _lib.call("dcnet_coord_map", None, 0, 0, None)
+
+
+@pytest.mark.parametrize("P,K,N0,n", [(3, 30, 64, 10), (2, 30, 169, 10), (1, 30, 12, 10)])
+def test_pyrandom_interframe_matches_cpython(P, K, N0, n):
+    random.seed(42)
+    got = ops.pyrandom_interframe(P, K, N0, n)
+    after = random.random()
+    random.seed(42)
+    ref = [random.sample(list(range(N0 - 1)), n) for _ in range(P * K)]
+    assert (np.array(ref).reshape(P, K, n) == got).all()
+    assert after == random.random()          # stream left exactly where the reference would leave it
+
+
+@pytest.mark.parametrize("B,N0,n", [(4, 64, 5), (6, 169, 5), (2, 16, 5)])
+def test_pyrandom_crossmodal_matches_cpython(B, N0, n):
+    random.seed(7)
+    got = ops.pyrandom_crossmodal(B, N0, n)
+    after = random.random()
+    random.seed(7)
+    ref = []
+    for ii in range(B):
+        for jj in range(N0):
+            for index in range(B):
+                pool = list(range(N0))
+                if index == ii:
+                    pool.remove(jj)
+                last = random.sample(pool, n)
+            ref.append(last)
+    assert (np.array(ref).reshape(B, N0, n) == got).all()
+    assert after == random.random()
+
+
+def test_state_dict_names_and_shapes_match_reference_fixture():
+    net = grounding_model(corpus=list(range(1000)), emb_size=512, visumodel=StubBackbone())
+    mine = {k: list(v.shape) for k, v in net.state_dict().items()}
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_shapes.json")))
+    assert mine == ref
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not mounted")
+def test_same_seed_gives_reference_weights_and_text_branch():
+    """The mirror constructs its modules in the reference's order, so the same seed reproduces the reference's
+    random init; with equal weights the stays-PyTorch neighbours (text encoder, head, location branch) restated in
+    the mirror must reproduce the reference forward when driven through the oracle's restated blocks."""
+    from dcnet_b200 import synth
+    from oracle import dcnet_oracle as O
+    T, M, MT = ref_loader.load(256)
+    synth.seed_all(13)
+    ref = M.grounding_model(corpus=list(range(1000)), emb_size=512, coordmap=True)
+    synth.seed_all(13)
+    mine = grounding_model(corpus=list(range(1000)), emb_size=512, visumodel=StubBackbone())
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+    g = torch.Generator().manual_seed(5)
+    maps = synth.make_raw_fvisu(2, 256, g)
+    wid = synth.make_words(2, gen=g)
+    ref.train(); mine.train()
+    ref.visumodel.set_maps(maps)
+    random.seed(3); torch.manual_seed(4)
+    r = ref(torch.zeros(4, 1, 1, 1), wid, torch.zeros_like(wid))
+    random.seed(3); torch.manual_seed(4)
+    o = O.forward_restated(mine, maps, wid)
+    for i, n in enumerate(['outbox', 'sim_score', 'loc_score', 'corr_feat']):
+        for s in range(3):
+            torch.testing.assert_close(o[n][s], r[i][s], rtol=2e-5, atol=2e-4 if n == 'loc_score' else 2e-5)
+
+
+def test_product_path_refuses_cpu_tensors():
+    net = grounding_model(corpus=list(range(1000)), emb_size=512, visumodel=StubBackbone())
+    net.visumodel.maps = [torch.zeros(2, c, g, g) for c, g in ((1024, 8), (512, 16), (256, 32))]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(2, 1, 1, 1), torch.ones(2, 20, dtype=torch.long), None)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        ops.rownorm(torch.zeros(4, 8))
