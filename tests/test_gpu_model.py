@@ -1,0 +1,186 @@
+"""-m gpu: whole-path parity.  (1) product (CUDA kernels through the C ABI) vs the CPU oracle on the same seeded inputs and
+weights, forward + losses + gradients, at 256 and 416; (2) product vs the committed golden vectors that were produced by
+the UNMODIFIED reference (tests/golden/make_golden.py)."""
+import copy
+import os
+import random
+
+import pytest
+import torch
+import torch.nn as nn
+
+from dcnet_b200 import losses as LS
+from dcnet_b200 import synth
+from dcnet_b200.model.DCNet_model import grounding_model
+from oracle import dcnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "dcnet_256_b4.pt")
+
+
+class StubBackbone(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.maps = None
+
+    def forward(self, x):
+        return list(self.maps)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def make_net(size, seed=13):
+    synth.seed_all(seed)
+    net = grounding_model(corpus=list(range(1000)), emb_size=512, visumodel=StubBackbone(), size=size)
+    for m in net.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0          # CPU and CUDA dropout streams differ; the text branch is not the path under test
+    return net
+
+
+def sub(t):
+    t = t.detach()
+    if t.numel() <= 20000:
+        return t.clone()
+    return t.flatten()[::max(1, t.numel() // 10007)].clone()
+
+
+@pytest.mark.parametrize("size,pairs", [(256, 2), (416, 1)])
+def test_train_forward_losses_gradients_vs_oracle(size, pairs):
+    net = make_net(size)
+    g = torch.Generator().manual_seed(100 + size)
+    maps = synth.make_raw_fvisu(pairs, size, g)
+    wid = synth.make_words(pairs, gen=g)
+    bbox = synth.make_boxes(pairs, size, g)
+    cpu_net = copy.deepcopy(net).train()
+    net = net.to(DEV).train()
+    LS.configure(size=size, anchor_imsize=416, anchors_full=O.ANCHORS_FULL)
+
+    # ---- oracle (CPU)
+    maps_r = [m.clone().requires_grad_(True) for m in maps]
+    random.seed(21)
+    o = O.forward_restated(cpu_net, maps_r, wid, return_internals=True)
+    ol = O.losses_restated(o, bbox, size)
+    ol['loss'].backward()
+
+    # ---- product (CUDA)
+    maps_c = [m.to(DEV).requires_grad_(True) for m in maps]
+    net.visumodel.maps = maps_c
+    random.seed(21)
+    out = net(torch.zeros(2 * pairs, 1, 1, 1, device=DEV), wid.to(DEV), None)
+    after_product = random.random()
+    outbox, sim, loc, corr, fa, q_if, k_if, neg_if, q_cm, k_cm, neg_cm = out
+    names = dict(outbox=outbox, sim_score=sim, loc_score=loc, corr_feat=corr)
+    for n, lst in names.items():
+        for s in range(3):
+            tol = 5e-4 if n in ('loc_score', 'outbox') else 2e-5
+            assert lst[s].shape == o[n][s].shape
+            assert rel(lst[s], o[n][s]) < tol, (n, s, rel(lst[s], o[n][s]))
+    assert rel(fa, o['flang_attn']) < 1e-5
+    # lists: the reference API returns python lists of per-rank / per-pixel tensors
+    assert isinstance(q_if, list) and len(q_if) == 30 and q_if[0].shape == (pairs, 512) and neg_if[0].shape == (pairs, 10, 512)
+    N0 = (size // 32) ** 2
+    assert len(q_cm) == N0 and k_cm[0].shape == (2 * pairs, 1, 512) and neg_cm[0].shape == (2 * pairs, 5, 512)
+    for mine, key in ((q_if, 'frame_feature'), (k_if, 'corrspendence_feature'), (neg_if, 'neg_feature'),
+                      (q_cm, 'vit_posit'), (k_cm, 'lag_posit'), (neg_cm, 'neg_cross')):
+        assert rel(torch.stack(list(mine)), o[key]) < 2e-5, key      # gathered vectors: equal iff the indices agree
+    # the host RNG stream is left exactly where the reference would leave it
+    random.seed(21)
+    O.interframe_sample(o['fvisu'][0].view(pairs, 2, 512, -1)[:, 0].detach(), o['fvisu'][0].view(pairs, 2, 512, -1)[:, 1].detach(), random)
+    O.crossmodal_sample(o['vit'].detach(), o['lag'].detach(), o['cross_map'].detach(), random)
+    assert after_product == random.random()
+
+    # ---- losses (train_DCNet.py:615-642)
+    loss, comp, (bn, gi, gj, t5) = LS.fused_losses(outbox, sim, net.last_neg_sim_score, loc, bbox.to(DEV), q_if, k_if, neg_if, q_cm, k_cm, neg_cm)
+    assert torch.equal(bn.cpu(), ol['best_n']) and torch.equal(gi.cpu(), ol['gi']) and torch.equal(gj.cpu(), ol['gj'])
+    for k in ('yolo', 'rank', 'loc', 'interframe', 'cross'):
+        assert abs(float(comp[k]) - float(ol[k])) < 2e-4 * max(1.0, abs(float(ol[k]))), (k, float(comp[k]), float(ol[k]))
+    # reference-named entry points on the reference's list API give the same numbers
+    gt, gil, gjl, bnl, gtc = LS.build_target(bbox.to(DEV), outbox)
+    pa = [p.view(p.size(0), 3, 5, p.size(2), p.size(3)) for p in outbox]
+    assert abs(float(LS.yolo_loss(pa, gt, gil, gjl, bnl)) - float(ol['yolo'])) < 2e-4 * abs(float(ol['yolo']))
+    assert abs(float(LS.rank_loss(sim, LS.negative_sim_score(fa, corr), gtc, gil, gjl, bnl, w_coord=0.)) - float(ol['rank'])) < 2e-4
+    assert abs(float(LS.loc_loss(loc, sim, gtc)) - float(ol['loc'])) < 2e-4 * abs(float(ol['loc']))
+    assert abs(float(LS.Interframe_contrastive_loss(list(q_if), list(k_if), list(neg_if))) - float(ol['interframe'])) < 2e-4
+
+    # ---- gradients
+    loss.backward()
+    for s in range(3):
+        assert rel(maps_c[s].grad, maps_r[s].grad) < 2e-3, ("d raw_fvisu", s, rel(maps_c[s].grad, maps_r[s].grad))
+    pc, pr = dict(net.named_parameters()), dict(cpu_net.named_parameters())
+    worst = {}
+    for k, v in pr.items():
+        if v.grad is None:
+            assert pc[k].grad is None or float(pc[k].grad.abs().max()) == 0.0, k
+            continue
+        if float(v.grad.norm()) < 1e-12:
+            continue
+        worst[k] = rel(pc[k].grad, v.grad)
+    bad = {k: e for k, e in worst.items() if e > 5e-3}
+    assert not bad, bad
+
+
+def test_eval_forward_vs_oracle():
+    net = make_net(256)
+    g = torch.Generator().manual_seed(9)
+    for m in net.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.running_mean.normal_(0, 0.1, generator=g); m.running_var.uniform_(0.5, 1.5, generator=g)
+    maps = synth.make_raw_fvisu(2, 256, g)
+    wid = synth.make_words(2, gen=g)
+    cpu_net = copy.deepcopy(net).eval()
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        o = O.forward_restated(cpu_net, maps, wid)
+        net.visumodel.maps = [m.to(DEV) for m in maps]
+        state = random.getstate()
+        out = net(torch.zeros(4, 1, 1, 1, device=DEV), wid.to(DEV), None)
+        assert random.getstate() == state            # eval skips the sampling blocks
+    assert len(out) == 4
+    for i, n in enumerate(['outbox', 'sim_score', 'loc_score', 'only_obj']):
+        for s in range(3):
+            assert rel(out[i][s], o[n][s]) < (5e-4 if n in ('loc_score', 'outbox') else 2e-5), (n, s)
+
+
+def test_against_reference_golden_vectors():
+    """The fixture holds outputs of the UNMODIFIED reference; weights and inputs are regenerated from the same seeds."""
+    fix = torch.load(GOLDEN)
+    meta = fix['meta']
+    net = make_net(meta['size'], meta['seed']).to(DEV).train()
+    LS.configure(size=meta['size'], anchor_imsize=416, anchors_full=O.ANCHORS_FULL)
+    g = torch.Generator().manual_seed(meta['input_seed'])
+    pairs = meta['pairs']
+    maps = [m.to(DEV).requires_grad_(True) for m in synth.make_raw_fvisu(pairs, meta['size'], g)]
+    wid = synth.make_words(pairs, gen=g).to(DEV)
+    bbox = synth.make_boxes(pairs, meta['size'], g).to(DEV)
+    net.visumodel.maps = maps
+    random.seed(meta['py_seed'])
+    outbox, sim, loc, corr, fa, q_if, k_if, neg_if, q_cm, k_cm, neg_cm = net(torch.zeros(2 * pairs, 1, 1, 1, device=DEV), wid, None)
+    for n, lst in dict(outbox=outbox, sim_score=sim, loc_score=loc, corr_feat=corr, neg_sim=net.last_neg_sim_score).items():
+        for s in range(3):
+            assert rel(sub(lst[s]), fix[n][s]) < (5e-4 if n in ('loc_score', 'outbox') else 2e-5), (n, s)
+    assert rel(sub(fa), fix['flang_attn']) < 1e-5
+    for mine, key in ((q_if, 'frame_feature'), (k_if, 'corrspendence_feature'), (neg_if, 'neg_feature'),
+                      (q_cm, 'vit_posit'), (k_cm, 'lag_posit'), (neg_cm, 'neg_cross')):
+        assert rel(sub(torch.stack(list(mine))), fix[key]) < 2e-5, key
+    loss, comp, (bn, gi, gj, t5) = LS.fused_losses(outbox, sim, net.last_neg_sim_score, loc, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm)
+    assert bn.tolist() == fix['best_n'] and gi.tolist() == fix['gi'] and gj.tolist() == fix['gj']
+    for k, v in fix['losses'].items():
+        assert abs(float(comp[k]) - v) < 2e-4 * max(1.0, abs(v)), (k, float(comp[k]), v)
+    loss.backward()
+    for s in range(3):
+        assert rel(sub(maps[s].grad), fix['grad_raw'][s]) < 2e-3, s
+        assert abs(float(maps[s].grad.norm()) - fix['grad_raw_norm'][s]) < 2e-3 * fix['grad_raw_norm'][s]
+    params = dict(net.named_parameters())
+    for k, gref in fix['grad_param'].items():
+        assert rel(sub(params[k].grad), gref) < 5e-3, (k, rel(sub(params[k].grad), gref))
+    net.eval()
+    with torch.no_grad():
+        ev = net(torch.zeros(2 * pairs, 1, 1, 1, device=DEV), wid, None)
+    for i, n in ((0, 'outbox'), (1, 'sim_score'), (3, 'only_obj')):
+        for s in range(3):
+            assert rel(sub(ev[i][s]), fix['eval'][n][s]) < (5e-4 if n == 'outbox' else 5e-5), (n, s)

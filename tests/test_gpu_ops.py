@@ -1,0 +1,385 @@
+"""-m gpu: per-kernel parity of the CUDA path (through the C ABI) against the CPU oracle on seeded inputs.
+fp32 paths: <= 1e-5 norm-relative (stated per test); integer / index outputs: exact."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from dcnet_b200 import ops, synth
+from oracle import dcnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,batch", [(64, 64, 512, 3), (169, 169, 512, 2), (512, 100, 1032, 2), (20, 64, 512, 4), (130, 257, 33, 1)])
+def test_sgemm_strided(M, N, K, batch):
+    g = gen(1)
+    A = torch.randn(batch, K, M, generator=g)        # stored transposed: A(m,k) = A[b,k,m]
+    B = torch.randn(batch, K, N, generator=g)
+    C = torch.empty(batch, M, N, device=DEV)
+    ops.sgemm(A.to(DEV), B.to(DEV), C, M, N, K, batch=batch, sA=(1, M, K * M, 0), sB=(N, 1, K * N, 0), sC=(N, 1, M * N))
+    ref = torch.bmm(A.double().transpose(1, 2), B.double())
+    assert rel(C, ref) < 2e-6
+
+
+def test_sgemm_kbatch_atomic_colscale():
+    g = gen(2)
+    Bt, C_, N, K = 3, 96, 40, 70
+    dz = torch.randn(Bt, C_, N, generator=g); x = torch.randn(Bt, K, N, generator=g)
+    out = torch.zeros(C_, K, device=DEV)
+    # dW = sum_b dz[b] x[b]^T with the batch folded into the reduction
+    ops.sgemm(dz.to(DEV), x.to(DEV), out, C_, K, N, batch=1, kbatch=Bt, sA=(N, 1, 0, C_ * N), sB=(1, N, 0, K * N), sC=(K, 1, 0))
+    ref = torch.einsum('bcn,bkn->ck', dz.double(), x.double())
+    assert rel(out, ref) < 2e-6
+    out2 = torch.zeros(C_, K, device=DEV)
+    ops.sgemm(dz.to(DEV), x.to(DEV), out2, C_, K, N, batch=Bt, sA=(N, 1, C_ * N, 0), sB=(1, N, K * N, 0), sC=(K, 1, 0), atomic=1)
+    assert rel(out2, ref) < 2e-6
+    cs = torch.rand(K, generator=g) + 0.5
+    out3 = torch.empty(C_, K, device=DEV)
+    ops.sgemm(dz.to(DEV), x.to(DEV), out3, C_, K, N, batch=1, kbatch=Bt, sA=(N, 1, 0, C_ * N), sB=(1, N, 0, K * N), sC=(K, 1, 0),
+              colscale=cs.to(DEV), alpha=2.0)
+    assert rel(out3, 2 * ref * cs.double()[None]) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _cbr_case(B, K1, K2, N, use_u, use_cc, use_fa, l2, training, seed):
+    g = gen(seed)
+    C = 512
+    d = dict(x1=torch.randn(B, K1, N, generator=g), w=torch.randn(C, K1 + K2 + (8 if use_cc else 0), generator=g) / (K1 + K2) ** 0.5,
+             gamma=torch.rand(C, generator=g) + 0.5, beta=torch.randn(C, generator=g) * 0.1,
+             rm=torch.randn(C, generator=g) * 0.1, rv=torch.rand(C, generator=g) + 0.5)
+    d['x2'] = torch.randn(B, K2, N, generator=g) if K2 else None
+    d['u'] = torch.randn(B, C, generator=g) * 0.3 if use_u else None
+    d['cc'] = torch.randn(C, N, generator=g) * 0.3 if use_cc else None
+    d['fa'] = torch.nn.functional.normalize(torch.randn(B, C, generator=g).abs(), dim=1) if use_fa else None
+    return d
+
+
+def _cbr_oracle(d, l2, training):
+    """fp64 oracle of the fused op, built from the oracle's blocks"""
+    t = {k: (v.double().requires_grad_(k not in ('rm', 'rv')) if v is not None else None) for k, v in d.items()}
+    K1 = t['x1'].shape[1]
+    K2 = 0 if t['x2'] is None else t['x2'].shape[1]
+    x = t['x1'] if t['x2'] is None else torch.cat([t['x1'], t['x2']], 1)
+    z = torch.einsum('ck,bkn->bcn', t['w'][:, :K1 + K2], x)
+    if t['u'] is not None:
+        z = z + t['u'][:, :, None]
+    if t['cc'] is not None:
+        z = z + t['cc'][None]
+    if training:
+        mean, var = z.mean(dim=(0, 2)), z.var(dim=(0, 2), unbiased=False)
+    else:
+        mean, var = t['rm'], t['rv']
+    y = torch.relu((z - mean[None, :, None]) / torch.sqrt(var[None, :, None] + O.BN_EPS) * t['gamma'][None, :, None] + t['beta'][None, :, None])
+    if l2:
+        y = O.l2norm_channels(y)
+    outs = [y]
+    if t['fa'] is not None:
+        outs += list(O.pix2text(y, t['fa']))
+    return t, outs, (z, mean, var)
+
+
+@pytest.mark.parametrize("B,K1,K2,N,use_u,use_cc,use_fa,l2,training", [
+    (4, 1024, 0, 64, False, False, False, True, True),      # mapping_visu scale 0
+    (4, 256, 0, 1024, False, False, False, True, True),     # mapping_visu scale 2
+    (4, 512, 512, 256, False, False, True, True, True),     # corr_conv: two-source K loop + pix2text
+    (4, 512, 0, 169, True, True, False, False, True),       # fusion: split-weight, odd N (416 scale 0)
+    (2, 512, 512, 64, False, False, True, True, False),     # eval mode (running statistics)
+])
+def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, training):
+    d = _cbr_case(B, K1, K2, N, use_u, use_cc, use_fa, l2, training, seed=10 + N)
+    t, outs_ref, (z_ref, mean_ref, var_ref) = _cbr_oracle(d, l2, training)
+    c = {k: (v.to(DEV).requires_grad_(k not in ('rm', 'rv')) if v is not None else None) for k, v in d.items()}
+    rm0, rv0 = c['rm'].clone(), c['rv'].clone()
+    out = ops.conv_bn_act(c['x1'], c['w'], c['gamma'], c['beta'], c['rm'], c['rv'], training, x2=c['x2'], u=c['u'], cc=c['cc'], fa=c['fa'],
+                          l2norm=l2)
+    outs = list(out) if isinstance(out, tuple) else [out]
+    for o, r in zip(outs, outs_ref):
+        assert rel(o, r) < 1e-5
+    if training:   # running statistics: momentum 0.999, unbiased variance
+        n = B * N
+        assert rel(c['rm'], 0.001 * rm0.cpu().double() + 0.999 * mean_ref) < 1e-5
+        assert rel(c['rv'], 0.001 * rv0.cpu().double() + 0.999 * var_ref * n / (n - 1)) < 1e-5
+    g = gen(99)
+    gouts = [torch.randn(o.shape, generator=g) for o in outs_ref]
+    torch.autograd.backward(outs_ref, [x.double() for x in gouts])
+    torch.autograd.backward(outs, [x.to(DEV) for x in gouts])
+    K = K1 + K2
+    for k in ('x1', 'x2', 'gamma', 'beta', 'u', 'cc', 'fa'):
+        if d[k] is not None:
+            assert rel(c[k].grad, t[k].grad) < 2e-5, k
+    assert rel(c['w'].grad[:, :K], t['w'].grad[:, :K]) < 2e-5
+    assert float(c['w'].grad[:, K:].abs().max()) == 0.0 if c['w'].shape[1] > K else True
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("P,N", [(2, 64), (2, 169), (1, 256)])
+def test_coattention_forward_backward(P, N):
+    g = gen(20 + N)
+    C = 512
+    fr = torch.nn.functional.normalize(torch.randn(2 * P, C, N, generator=g).abs(), dim=1)
+    ref_in = fr.double().requires_grad_(True)
+    f1, f2 = ref_in.view(P, 2, C, N)[:, 0], ref_in.view(P, 2, C, N)[:, 1]
+    o1, o2 = O.coattention(f1, f2, 10.0)
+    ref = O.interleave_pairs(o1, o2)
+    x = fr.to(DEV).requires_grad_(True)
+    qa = torch.arange(2 * P, device=DEV, dtype=torch.int32)
+    out = ops.coattention(x, qa, qa ^ 1, tau=10.0)
+    assert rel(out, ref) < 1e-5
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go.double())
+    out.backward(go.to(DEV))
+    assert rel(x.grad, ref_in.grad) < 2e-5
+
+
+def test_coattention_clip_mode_centre_vs_others():
+    """model/test_DCNet_model.py:303-332: centre frame attends to each other frame (one direction), mean of results."""
+    g = gen(31)
+    C, N, nf = 512, 64, 5
+    fr = torch.nn.functional.normalize(torch.randn(nf, C, N, generator=g).abs(), dim=1)
+    centre = nf // 2
+    others = [i for i in range(nf) if i != centre]
+    qa = torch.full((len(others),), centre, device=DEV, dtype=torch.int32)
+    kb = torch.tensor(others, device=DEV, dtype=torch.int32)
+    out = ops.coattention(fr.to(DEV), qa, kb, tau=10.0)
+    for i, o in enumerate(others):
+        o1, _ = O.coattention(fr[centre:centre + 1].double(), fr[o:o + 1].double(), 10.0)
+        assert rel(out[i], o1[0]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("P,N0", [(3, 64), (2, 169)])
+def test_interframe_topk_and_gather(P, N0):
+    g = gen(40 + N0)
+    C = 512
+    fv0 = torch.nn.functional.normalize(torch.relu(synth.make_raw_fvisu(P, 32 * int(N0 ** 0.5), g)[0].flatten(2)[:, :C]), dim=1)
+    idx, S0 = ops.interframe_topk(fv0.to(DEV), 30)
+    f1, f2 = fv0.view(P, 2, C, N0)[:, 0], fv0.view(P, 2, C, N0)[:, 1]
+    S64 = torch.bmm(f1.double().transpose(1, 2), f2.double()).flatten(1)
+    assert rel(S0.flatten(1), S64) < 2e-6
+    # (1) the kernel's selection is exactly the canonical top-k of ITS OWN fp32 scores (value desc, lower index first)
+    for p in range(P):
+        _, want = O.canonical_topk(S0[p].flatten().cpu(), 30)
+        assert torch.equal(idx[p].cpu(), want)
+    # (2) against the fp64 scores the selection agrees except where consecutive values are closer than fp32 round-off
+    for p in range(P):
+        v, want = O.canonical_topk(S64[p], 31)
+        got = idx[p].cpu()
+        for r in range(30):
+            if got[r] != want[r]:
+                assert abs(float(S64[p][got[r]] - S64[p][want[r]])) < 1e-6, (p, r)
+    # negative mapping + gather
+    random.seed(5)
+    negpos = torch.from_numpy(ops.pyrandom_interframe(P, 30, N0, 10)).to(DEV)
+    negidx = ops.interframe_negidx(idx, negpos, N0)
+    col = (idx % N0).cpu()
+    random.seed(5)
+    for p in range(P):
+        for r in range(30):
+            pool = list(range(N0)); pool.remove(int(col[p, r]))
+            assert random.sample(pool, 10) == negidx[p, r].cpu().tolist()
+    img = torch.full((P * 30,), 1, device=DEV, dtype=torch.int32) + 2 * torch.arange(P, device=DEV, dtype=torch.int32).repeat_interleave(30)
+    src = fv0.to(DEV).requires_grad_(True)
+    out = ops.gather_cols(src, img, (idx % N0).reshape(-1))
+    want = torch.stack([f2[p][:, col[p, r]] for p in range(P) for r in range(30)])
+    assert torch.equal(out.cpu(), want)
+    go = torch.randn(out.shape, generator=g)
+    out.backward(go.to(DEV))
+    ref_src = fv0.clone().requires_grad_(True)
+    f2r = ref_src.view(P, 2, C, N0)[:, 1]
+    torch.stack([f2r[p][:, col[p, r]] for p in range(P) for r in range(30)]).backward(go)
+    assert rel(src.grad, ref_src.grad) < 1e-6
+
+
+def test_topk_tie_rule_lower_index_first():
+    # two identical frames with duplicated columns -> exact ties in S0
+    g = gen(3)
+    C, N0 = 512, 16
+    f = torch.nn.functional.normalize(torch.randn(C, N0, generator=g).abs(), dim=0)
+    f[:, 5] = f[:, 2]
+    fv0 = torch.stack([f, f])
+    idx, S0 = ops.interframe_topk(fv0.to(DEV), 30)
+    _, want = O.canonical_topk(S0[0].flatten().cpu(), 30)
+    assert torch.equal(idx[0].cpu(), want)
+
+
+@pytest.mark.parametrize("R,Bq,n", [(30, 3, 10), (64, 4, 5)])
+def test_infonce_forward_backward(R, Bq, n):
+    g = gen(50 + n)
+    C = 512
+    q = torch.randn(R, Bq, C, generator=g); k = torch.randn(R, Bq, C, generator=g); neg = torch.randn(R, Bq, n, C, generator=g)
+    tr = [x.double().requires_grad_(True) for x in (q, k, neg)]
+    ref = O.interframe_contrastive_loss(*tr)
+    tc = [x.to(DEV).requires_grad_(True) for x in (q, k, neg)]
+    rows = ops.infonce_rows(tc[0].reshape(R * Bq, C), tc[1].reshape(R * Bq, C), tc[2].reshape(R * Bq, n, C), 0.07)
+    loss = rows.mean()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    ref.backward(); loss.backward()
+    for a, b in zip(tc, tr):
+        assert rel(a.grad, b.grad) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N0", [(4, 64), (3, 169)])
+def test_crossmodal_block(B, N0):
+    g = gen(60 + N0)
+    C, T = 512, 20
+    fv0 = torch.nn.functional.normalize(torch.randn(B, C, N0, generator=g).abs(), dim=1)
+    ctx = torch.randn(B, T, 2 * C, generator=g)
+    ctx[1, 12:] = 0                                    # padded words (pad_packed_sequence zeros)
+    fw = torch.randn(T, T, 3, generator=g) * 0.2; fb = torch.randn(T, generator=g) * 0.1
+    vit_r, lag_r, M_r = O.crossmodal_features(fv0.double(), ctx.double(), fw.double(), fb.double())
+    x = fv0.to(DEV).requires_grad_(True); cx = ctx.to(DEV).requires_grad_(True)
+    vit = ops.rownorm(x); lag = ops.lagnorm(cx)
+    assert rel(vit, vit_r) < 1e-6 and rel(lag, lag_r) < 1e-6
+    word, M = ops.crossmodal_words(lag.detach(), vit.detach(), fw.to(DEV), fb.to(DEV))
+    word_r = M_r.argmax(1)
+    # arg-max agrees except where the two best softmax values are within fp32 round-off of each other
+    top2 = M_r.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-6
+    assert torch.equal(word.cpu()[safe], word_r[safe])
+    assert safe.float().mean() > 0.99
+    # backward of the two normalisations
+    gv = torch.randn(vit_r.shape, generator=g); gl = torch.randn(lag_r.shape, generator=g)
+    xr = fv0.double().requires_grad_(True); cr = ctx.double().requires_grad_(True)
+    vr, lr, _ = O.crossmodal_features(xr, cr, fw.double(), fb.double())
+    torch.autograd.backward([vr, lr], [gv.double(), gl.double()])
+    torch.autograd.backward([vit, lag], [gv.to(DEV), gl.to(DEV)])
+    assert rel(x.grad, xr.grad) < 1e-5 and rel(cx.grad, cr.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [256, 416])
+def test_build_target_exact_indices(size):
+    g = gen(70 + size)
+    bbox = synth.make_boxes(128, size, g)
+    bbox[0] = torch.tensor([0., 0., size - 1., size - 1.])           # maximum box
+    bbox[1] = torch.tensor([10., 10., 10.5, 10.5])                   # tiny box
+    bn, gi, gj, t5, gt, gtc = ops.build_target(bbox.to(DEV), size, 416, O.ANCHORS_FULL, dense=True)
+    ogt, ogi, ogj, obn, ogtc = O.build_target(bbox, size)
+    assert torch.equal(bn.cpu(), obn) and torch.equal(gi.cpu(), ogi) and torch.equal(gj.cpu(), ogj)
+    for s in range(3):
+        torch.testing.assert_close(gt[s].cpu(), ogt[s], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(gtc[s].cpu(), ogtc[s], rtol=1e-6, atol=1e-6)
+        assert torch.equal(gt[s].cpu() != 0, ogt[s] != 0)
+
+
+@pytest.mark.parametrize("size,B", [(256, 6), (416, 4)])
+def test_ground_losses_forward_backward(size, B):
+    g = gen(80 + size)
+    gs = [size // 32, size // 16, size // 8]
+    bbox = synth.make_boxes(B // 2, size, g)
+    pred = [torch.randn(B, 15, x * x, generator=g) for x in gs]
+    sim = [torch.rand(B, x * x, generator=g) for x in gs]
+    neg = [torch.rand(B, x * x, generator=g) for x in gs]
+    loc = [torch.rand(B, x * x, generator=g) for x in gs]
+    ogt, ogi, ogj, obn, ogtc = O.build_target(bbox, size)
+    tr = [[t.double().requires_grad_(True) for t in grp] for grp in (pred, sim, neg, loc)]
+    pr5 = [p.view(B, 3, 5, x, x) for p, x in zip(tr[0], gs)]
+    ref = torch.stack([O.yolo_loss(pr5, [t.double() for t in ogt], ogi, ogj, obn),
+                       O.rank_loss([s.view(B, x, x) for s, x in zip(tr[1], gs)], [s.view(B, x, x) for s, x in zip(tr[2], gs)],
+                                   [t.double() for t in ogtc]),
+                       O.loc_loss([s.view(B, x, x) for s, x in zip(tr[3], gs)], [t.double() for t in ogtc])])
+    bn, gi, gj, t5, _, _ = ops.build_target(bbox.to(DEV), size, 416, O.ANCHORS_FULL)
+    tc = [[t.to(DEV).requires_grad_(True) for t in grp] for grp in (pred, sim, neg, loc)]
+    out = ops.ground_losses(tc[0], tc[1], tc[2], tc[3], bn, gi, gj, t5)
+    assert rel(out, ref) < 1e-5
+    w = torch.tensor([1.0, 100.0, 1.0])
+    (ref * w.double()).sum().backward()
+    (out * w.to(DEV)).sum().backward()
+    for grp_c, grp_r, name in zip(tc, tr, ("pred", "sim", "neg", "loc")):
+        for a, b in zip(grp_c, grp_r):
+            if b.grad is None:
+                assert a.grad is None or float(a.grad.abs().max()) == 0
+            else:
+                assert rel(a.grad, b.grad) < 2e-5, name
+
+
+@pytest.mark.parametrize("size", [256, 416])
+def test_decode_and_iou(size):
+    g = gen(90 + size)
+    B = 8
+    gs = [size // 32, size // 16, size // 8]
+    pred = [torch.randn(B, 15, x * x, generator=g) for x in gs]
+    bbox = synth.make_boxes(B // 2, size, g)
+    pr5 = [p.view(B, 3, 5, x, x) for p, x in zip(pred, gs)]
+    # arg-max decode: integers exact
+    boxes, iou, bn, gi, gj = ops.decode([p.to(DEV) for p in pred], size, 416, O.ANCHORS_FULL, target=bbox.to(DEV))
+    rb, S, A, GJ, GI = O.decode_argmax(pr5, size)
+    assert torch.equal(bn.cpu(), 3 * S + A) and torch.equal(gi.cpu(), GI) and torch.equal(gj.cpu(), GJ)
+    torch.testing.assert_close(boxes.cpu(), rb, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(iou.cpu(), O.bbox_iou(rb, bbox), rtol=1e-4, atol=1e-6)
+    # decode at the GT cell
+    ogt, ogi, ogj, obn, _ = O.build_target(bbox, size)
+    boxes2, iou2, _, _, _ = ops.decode([p.to(DEV) for p in pred], size, 416, O.ANCHORS_FULL, obn.to(DEV), ogi.to(DEV), ogj.to(DEV), bbox.to(DEV))
+    rb2 = O.decode_at(pr5, ogi, ogj, obn, size)
+    torch.testing.assert_close(boxes2.cpu(), rb2, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(ops.bbox_iou(rb2.to(DEV), bbox.to(DEV)).cpu(), O.bbox_iou(rb2, bbox), rtol=1e-6, atol=1e-7)
+    # ties: equal maxima -> first in (scale, anchor, gj, gi) order
+    tie = [torch.zeros(2, 15, x * x) for x in gs]
+    tie[1][0, 9, 7] = 5.0; tie[2][0, 4, 3] = 5.0; tie[0][1, 14, 2] = 1.0; tie[0][1, 4, 60] = 1.0
+    _, _, bn, gi, gj = ops.decode([p.to(DEV) for p in tie], size, 416, O.ANCHORS_FULL)
+    _, S, A, GJ, GI = O.decode_argmax([p.view(2, 3, 5, x, x) for p, x in zip(tie, gs)], size)
+    assert torch.equal(bn.cpu(), 3 * S + A) and torch.equal(gi.cpu(), GI) and torch.equal(gj.cpu(), GJ)
+
+
+def test_only_obj_and_modulate():
+    g = gen(100)
+    B, N = 4, 256
+    raw = torch.randn(B, 15, N, generator=g); sim = torch.rand(B, N, generator=g); loc = torch.rand(B, N, generator=g)
+    tr = [x.double().requires_grad_(True) for x in (raw, sim, loc)]
+    tc = [x.to(DEV).requires_grad_(True) for x in (raw, sim, loc)]
+    oo_r = O.only_obj(tr[0]); obj_r = oo_r * tr[1]; mod_r = O.modulate_conf(tr[0], tr[1], tr[2])
+    oo, obj = ops.only_obj(tc[0], tc[1]); mod = ops.modulate_conf(tc[0], tc[1], tc[2])
+    assert rel(oo, oo_r) < 1e-6 and rel(obj, obj_r) < 1e-6 and rel(mod, mod_r) < 1e-6
+    gs_ = [torch.randn(x.shape, generator=g) for x in (oo_r, obj_r, mod_r)]
+    torch.autograd.backward([oo_r, obj_r, mod_r], [x.double() for x in gs_])
+    torch.autograd.backward([oo, obj, mod], [x.to(DEV) for x in gs_])
+    for a, b in zip(tc, tr):
+        assert rel(a.grad, b.grad) < 1e-5
+
+
+@pytest.mark.parametrize("g_", [8, 13, 32])
+def test_yolo_layer_decode(g_):
+    gg = gen(110 + g_)
+    anchors = [(116, 90), (156, 198), (373, 326)]
+    x = torch.randn(3, 255, g_, g_, generator=gg)
+    ref = O.yolo_layer_decode(x, anchors, 80, 256)
+    out = ops.yolo_layer_decode(x.to(DEV), anchors, 80, 256)
+    torch.testing.assert_close(out.cpu(), ref, rtol=2e-5, atol=1e-5)
+
+
+def test_iou_loss():
+    g = gen(120)
+    x = torch.randn(4, 1, 32, 32, generator=g); t = (torch.rand(4, 1, 32, 32, generator=g) > 0.7).float()
+    xr = x.double().requires_grad_(True)
+    ref = O.iou_loss(xr, t.double())
+    xc = x.to(DEV).requires_grad_(True)
+    out = ops.iou_loss(xc, t.to(DEV))
+    assert abs(float(out) - float(ref)) < 1e-5
+    ref.backward(); out.backward()
+    assert rel(xc.grad, xr.grad) < 1e-4
+
+
+def test_coord_map_matches_reference_convention():
+    for h, w in [(8, 8), (13, 13), (16, 32)]:
+        torch.testing.assert_close(ops.coord_map(h, w, DEV).cpu(), O.coord_map(h, w), rtol=1e-6, atol=1e-7)
+
+
+def test_empty_inputs_are_noops():
+    e = torch.empty(0, device=DEV)
+    assert ops.gather_cols(torch.zeros(2, 512, 4, device=DEV), torch.empty(0, device=DEV, dtype=torch.int32),
+                           torch.empty(0, device=DEV, dtype=torch.long)).shape == (0, 512)
+    assert ops.infonce_rows(torch.empty(0, 512, device=DEV), torch.empty(0, 512, device=DEV), torch.empty(0, 5, 512, device=DEV)).shape == (0,)
