@@ -206,24 +206,24 @@ extern "C" int dcnet_interframe_negidx(const long long* idx, const int* negpos, 
 }
 
 extern "C" int dcnet_gather_cols(const float* src, const int* img, const long long* col, int n, float* out, int C, int N, void* stream) {
-  DCNET_CHECK_ARG(src && img && col && out && n >= 0 && C > 0 && N > 0, "gather_cols: bad arguments");
   if (n == 0) return 0;
+  DCNET_CHECK_ARG(src && img && col && out && n > 0 && C > 0 && N > 0, "gather_cols: bad arguments");
   gather_cols_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, as_stream(stream)>>>(src, img, col, n, out, C, N);
   DCNET_LAUNCH_OK("gather_cols");
   return 0;
 }
 
 extern "C" int dcnet_scatter_cols_add(const float* dout, const int* img, const long long* col, int n, float* dsrc, int C, int N, void* stream) {
-  DCNET_CHECK_ARG(dout && img && col && dsrc && n >= 0 && C > 0 && N > 0, "scatter_cols_add: bad arguments");
   if (n == 0) return 0;
+  DCNET_CHECK_ARG(dout && img && col && dsrc && n > 0 && C > 0 && N > 0, "scatter_cols_add: bad arguments");
   scatter_cols_add_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, as_stream(stream)>>>(dout, img, col, n, dsrc, C, N);
   DCNET_LAUNCH_OK("scatter_cols_add");
   return 0;
 }
 
 extern "C" int dcnet_infonce_fwd(const float* q, const float* k, const float* neg, int G, int n, int C, float T, float* rowloss, void* stream) {
-  DCNET_CHECK_ARG(q && k && neg && rowloss && G >= 0 && n >= 1 && n < NCE_MAXN && C > 0 && C <= 32 * NCE_CPL, "infonce_fwd: bad arguments (n<=15, C<=512)");
   if (G == 0) return 0;
+  DCNET_CHECK_ARG(q && k && neg && rowloss && G > 0 && n >= 1 && n < NCE_MAXN && C > 0 && C <= 32 * NCE_CPL, "infonce_fwd: bad arguments (n<=15, C<=512)");
   infonce_fwd_kernel<<<ceil_div((long long)G * 32, 128), 128, 0, as_stream(stream)>>>(q, k, neg, G, n, C, T, rowloss);
   DCNET_LAUNCH_OK("infonce_fwd");
   return 0;
@@ -231,9 +231,9 @@ extern "C" int dcnet_infonce_fwd(const float* q, const float* k, const float* ne
 
 extern "C" int dcnet_infonce_bwd(const float* q, const float* k, const float* neg, int G, int n, int C, float T, const float* gscale,
                                  int gstride, float* dq, float* dk, float* dneg, void* stream) {
-  DCNET_CHECK_ARG(q && k && neg && gscale && dq && dk && dneg && G >= 0 && n >= 1 && n < NCE_MAXN && C > 0 && C <= 32 * NCE_CPL,
-                  "infonce_bwd: bad arguments (n<=15, C<=512)");
   if (G == 0) return 0;
+  DCNET_CHECK_ARG(q && k && neg && gscale && dq && dk && dneg && G > 0 && n >= 1 && n < NCE_MAXN && C > 0 && C <= 32 * NCE_CPL,
+                  "infonce_bwd: bad arguments (n<=15, C<=512)");
   infonce_bwd_kernel<<<ceil_div((long long)G * 32, 128), 128, 0, as_stream(stream)>>>(q, k, neg, G, n, C, T, gscale, gstride, dq, dk, dneg);
   DCNET_LAUNCH_OK("infonce_bwd");
   return 0;

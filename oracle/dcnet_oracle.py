@@ -331,9 +331,9 @@ def only_obj(outbox):
 def modulate_conf(outbox, sim, loc):
     """conf logit (channel 5a+4) *= sim*loc                    :619"""
     B, _, N = outbox.shape
-    o = outbox.reshape(B, 3, 5, N).clone()
-    o[:, :, 4] = o[:, :, 4] * sim[:, None] * loc[:, None]
-    return o.reshape(B, 15, N)
+    o = outbox.reshape(B, 3, 5, N)
+    conf = o[:, :, 4:5] * sim[:, None, None] * loc[:, None, None]
+    return torch.cat([o[:, :, :4], conf], 2).reshape(B, 15, N)
 
 
 # ----------------------------------------------------------------------------------------------

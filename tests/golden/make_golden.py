@@ -61,7 +61,7 @@ def main():
            'fcn_emb.0.0.conv.weight', 'fcn_emb.2.0.bn.weight', 'fcn_out.1.1.weight', 'textmodel.embedding.weight', 'sub_attn.fc.weight']
     params = dict(net.named_parameters())
     fix = dict(
-        meta=dict(pairs=PAIRS, size=SIZE, seed=SEED, input_seed=1234, py_seed=77, torch=torch.__version__),
+        meta=dict(pairs=PAIRS, size=SIZE, seed=SEED, input_seed=1234, py_seed=77, torch=str(torch.__version__)),
         outbox=[sub(t) for t in pred_anchor], sim_score=[sub(t) for t in sim_score], loc_score=[sub(t) for t in loc_score],
         corr_feat=[sub(t) for t in fvisu], flang_attn=sub(flang_attn), neg_sim=[sub(t) for t in neg_sim],
         frame_feature=sub(torch.stack(ff)), corrspendence_feature=sub(torch.stack(cf)), neg_feature=sub(torch.stack(nf)),

@@ -67,9 +67,9 @@ def _cbr_case(B, K1, K2, N, use_u, use_cc, use_fa, l2, training, seed):
     return d
 
 
-def _cbr_oracle(d, l2, training):
-    """fp64 oracle of the fused op, built from the oracle's blocks"""
-    t = {k: (v.double().requires_grad_(k not in ('rm', 'rv')) if v is not None else None) for k, v in d.items()}
+def _cbr_oracle(d, l2, training, dtype=torch.float64):
+    """oracle of the fused op, built from the oracle's blocks (fp64, or fp32 = the reference's own arithmetic)"""
+    t = {k: (v.to(dtype).requires_grad_(k not in ('rm', 'rv')) if v is not None else None) for k, v in d.items()}
     K1 = t['x1'].shape[1]
     K2 = 0 if t['x2'] is None else t['x2'].shape[1]
     x = t['x1'] if t['x2'] is None else torch.cat([t['x1'], t['x2']], 1)
@@ -116,11 +116,16 @@ def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, t
     gouts = [torch.randn(o.shape, generator=g) for o in outs_ref]
     torch.autograd.backward(outs_ref, [x.double() for x in gouts])
     torch.autograd.backward(outs, [x.to(DEV) for x in gouts])
+    # fp32 evaluation of the same graph = the reference's own arithmetic.  A pre-activation within fp32 round-off of the
+    # ReLU kink flips the mask between fp32 and fp64 (plain fp32 PyTorch shows the same 1e-4 deviation from fp64 on
+    # such inputs), so the gradient must match the fp64 OR the fp32 evaluation to 2e-5.
+    t32, outs32, _ = _cbr_oracle(d, l2, training, torch.float32)
+    torch.autograd.backward(outs32, gouts)
     K = K1 + K2
     for k in ('x1', 'x2', 'gamma', 'beta', 'u', 'cc', 'fa'):
         if d[k] is not None:
-            assert rel(c[k].grad, t[k].grad) < 2e-5, k
-    assert rel(c['w'].grad[:, :K], t['w'].grad[:, :K]) < 2e-5
+            assert min(rel(c[k].grad, t[k].grad), rel(c[k].grad, t32[k].grad)) < 2e-5, k
+    assert min(rel(c['w'].grad[:, :K], t['w'].grad[:, :K]), rel(c['w'].grad[:, :K], t32['w'].grad[:, :K])) < 2e-5
     assert float(c['w'].grad[:, K:].abs().max()) == 0.0 if c['w'].shape[1] > K else True
 
 
