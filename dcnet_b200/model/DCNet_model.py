@@ -142,6 +142,7 @@ class grounding_model(nn.Module):
                                        nn.Conv2d(emb_size // 2, 3 * 5, kernel_size=1))) for i in range(3)]))
         self.exact_sampling = True     # reproduce the reference's random.sample stream
         self._idx_cache = {}
+        self._capture = None
 
     # ---------------------------------------------------------------------------------------------------------
     def _pair_index(self, B, device):
@@ -258,6 +259,10 @@ class grounding_model(nn.Module):
         _, fa = self.sub_attn(context, embedded, word_id)
         fa = F.normalize(fa, p=2, dim=1)
 
+        if self._capture is not None:      # debugging / tests: expose the text-side tensors entering the hot path
+            for name, t in (("flang", flang), ("fa", fa), ("context", context)):
+                t.retain_grad()
+                self._capture[name] = t
         corr, sim, neg_sim = self.correspondence(fv, fa)
         coords = [ops.coord_map(h, w, fa.device).flatten(1) for (h, w) in hw]
         inter = self.fuse(corr, flang, coords)

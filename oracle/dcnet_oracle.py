@@ -68,17 +68,18 @@ def l2norm_channels(x, eps=1e-12):
 # ----------------------------------------------------------------------------------------------
 # a7  generate_coord                                           model/DCNet_model.py:23-39
 # ----------------------------------------------------------------------------------------------
-def coord_map(h, w, dtype=torch.float32):
+def coord_map(h, w, dtype=torch.float32, device=None):
     """[8,h,w].  NOTE the transposed convention of the reference: meshgrid('ij') of (arange(h), arange(w))
     puts the ROW index in the 'x' channels, normalised by the WIDTH."""
-    r = torch.arange(h, dtype=dtype)[:, None].expand(h, w)
-    c = torch.arange(w, dtype=dtype)[None, :].expand(h, w)
+    r = torch.arange(h, dtype=dtype, device=device)[:, None].expand(h, w)
+    c = torch.arange(w, dtype=dtype, device=device)[None, :].expand(h, w)
     x0 = (r * 2 - w) / w
     y0 = (c * 2 - h) / h
     x1 = ((r + 1) * 2 - w) / w
     y1 = ((c + 1) * 2 - h) / h
     return torch.stack([x0, y0, x1, y1, (x0 + x1) / 2, (y0 + y1) / 2,
-                        torch.full((h, w), 1.0 / h, dtype=dtype), torch.full((h, w), 1.0 / w, dtype=dtype)], 0)
+                        torch.full((h, w), 1.0 / h, dtype=dtype, device=device),
+                        torch.full((h, w), 1.0 / w, dtype=dtype, device=device)], 0)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -88,7 +89,7 @@ def canonical_topk(flat, k):
     """Top-k of a 1-D tensor, descending, ties broken by LOWER index first (torch.topk leaves tie
     order unspecified; this is the documented tie rule of the CUDA path)."""
     order = np.lexsort((np.arange(flat.numel()), -flat.detach().cpu().double().numpy()))
-    idx = torch.from_numpy(order[:k].copy()).long()
+    idx = torch.from_numpy(order[:k].copy()).long().to(flat.device)
     return flat[idx], idx
 
 
@@ -110,7 +111,7 @@ def interframe_sample(f1, f2, rng=_pyrandom, top_k=TOP_K, neg_n=NEG_N, topk_fn=N
             pool = list(range(N0))
             pool.remove(int(col[j]))                             # :411-412
             nidx.append(rng.sample(pool, neg_n))                 # :413
-        nidx = torch.tensor(nidx, dtype=torch.long)
+        nidx = torch.tensor(nidx, dtype=torch.long, device=f1.device)
         qs.append(f1[p][:, row].t())                             # [top_k,C]
         ks.append(f2[p][:, col].t())
         negs.append(f2[p][:, nidx.flatten()].t().reshape(top_k, neg_n, C))
@@ -171,6 +172,7 @@ def crossmodal_sample(vit, lag, M, rng=_pyrandom, neg_n=CROSS_NEG_N):
     B, C, N0 = vit.shape
     word = M.argmax(dim=1)                                       # topk(1) over words :48  -> [B,N0]
     negidx = torch.empty(B, N0, neg_n, dtype=torch.long)
+    word = word.to(M.device)
     for ii in range(B):
         for jj in range(N0):
             last = None
@@ -180,6 +182,7 @@ def crossmodal_sample(vit, lag, M, rng=_pyrandom, neg_n=CROSS_NEG_N):
                     pool.remove(jj)
                 last = rng.sample(pool, neg_n)
             negidx[ii, jj] = torch.tensor(last)
+    negidx = negidx.to(vit.device)
     q = vit.permute(2, 0, 1).contiguous()                        # [N0,B,C]  :70
     k = torch.gather(lag, 1, word[:, :, None].expand(B, N0, C)).permute(1, 0, 2).unsqueeze(2).contiguous()
     neg = vit[B - 1].t()[negidx.reshape(-1)].reshape(B, N0, neg_n, C).permute(1, 0, 2, 3).contiguous()
@@ -198,7 +201,7 @@ def interframe_contrastive_loss(q, k, neg, T=T_NCE):
     l_neg = torch.einsum('rpc,rpnc->rpn', qn, nn_)
     logits = torch.cat([l_pos, l_neg], 2) / T
     R, P, L = logits.shape
-    ce = F.cross_entropy(logits.reshape(R * P, L), torch.zeros(R * P, dtype=torch.long), reduction='none')
+    ce = F.cross_entropy(logits.reshape(R * P, L), torch.zeros(R * P, dtype=torch.long, device=logits.device), reduction='none')
     return ce.reshape(R, P).mean(1).mean(0)
 
 
@@ -457,7 +460,7 @@ def forward_restated(net, raw_fvisu, word_id, rng=_pyrandom, topk_fn=None, retur
     word_id = word_id[:, :max_len]
     raw_flang, context, embedded = net.textmodel(word_id)
     flang = F.normalize(net.mapping_lang(raw_flang), p=2, dim=1)
-    coords = [coord_map(h, w).flatten(1) for (h, w) in hw]
+    coords = [coord_map(h, w, device=raw_fvisu[0].device).flatten(1) for (h, w) in hw]
     inter, outbox = [], []
     for s in range(3):                                                            # :489-506
         N = corr[s].shape[2]
@@ -496,7 +499,9 @@ def forward_restated(net, raw_fvisu, word_id, rng=_pyrandom, topk_fn=None, retur
 
 def losses_restated(out, bbox, size):
     """train_DCNet.py:615-642 on the dict returned by forward_restated (train mode)."""
-    gt, gi, gj, best_n, gtc = build_target(bbox, size)
+    dev = out['outbox'][0].device
+    gt, gi, gj, best_n, gtc = build_target(bbox.detach().cpu(), size)
+    gt, gtc = [t.to(dev) for t in gt], [t.to(dev) for t in gtc]
     pred = [o.reshape(o.shape[0], 3, 5, o.shape[2], o.shape[3]) for o in out['outbox']]
     fa = out['flang_attn'][:, :, 0, 0]
     neg_sim = [pix2text(c.flatten(2), fa)[1].reshape(s.shape) for c, s in zip(out['corr_feat'], out['sim_score'])]
