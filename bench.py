@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/sec through the DCNet dense-correspondence hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...          (one rank per GPU, NCCL)
+
+A step is one forward+backward pass of the hot path (a2-a18 of SURVEY.md section 8: visual mapping, inter-frame top-k
+sampling, co-attention, corr_conv, pixel-to-text, fusion, cross-modal block, targets, five losses, decode + IoU, and the
+backward of all of it) over one batch of synthetic VID-shaped frame pairs; Darknet, the text encoder, the 3x3 head and the
+location branch are represented by synthetic tensors (dcnet_b200/hotpath.py).  Default workload = BASELINE.json configs[1]:
+8 frame-pairs at 256x256 per GPU.  Prints ONE JSON line (rank 0).
+
+  value : device-timed (CUDA events around each step, inputs resident in HBM, L2 flushed between steps), whole job.
+  e2e   : the same metric through HotPath.step with HOST buffers: host RNG draw + pinned H2D of every input + step +
+          D2H of the losses/IoU inside the (wall-clock, synchronised) timed region.
+  --impl reference : the CPU restatement of the reference's algorithm for this path (oracle/dcnet_oracle.py; the
+          reference itself is pure PyTorch and is not present on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "c2": dict(pairs=8, size=256, name="C2: 8 frame-pairs 256x256 per GPU (32x32 finest map), fwd+bwd of correspondence/fusion/decode path"),
+    "c3": dict(pairs=16, size=416, name="C3: 16 frame-pairs 416x416 per GPU (52x52 finest map, 2704x2704 similarity), fwd+bwd"),
+}
+C_EMB = 512
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def reference_arm(args, wl, rank, world):
+    """CPU implementation of the path (the oracle port) on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from dcnet_b200 import synth
+    from dcnet_b200.hotpath import HotPath
+    from oracle import dcnet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    size = wl["size"]
+    synth.seed_all(13)
+    net = HotPath(size).net.train()      # parameters only (CPU); every op below is the oracle's
+    g = torch.Generator().manual_seed(4242)
+
+    def one(pairs):
+        b = synth.make_hotpath_batch(pairs, size, g)
+        mk = lambda t: t.clone().requires_grad_(True)
+        net.zero_grad(set_to_none=True)
+        t0 = time.perf_counter()
+        O.hotpath_restated(net, [mk(t) for t in b['raw']], mk(b['flang']), mk(b['fa']), mk(b['context']), [mk(t) for t in b['head']],
+                           [mk(t) for t in b['loc']], b['dy_head'], b['bbox'], size)
+        return time.perf_counter() - t0
+
+    random.seed(13)
+    pairs = 2
+    t_probe = one(pairs)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    while pairs * 2 <= wl["pairs"] and t_probe * 2.5 < budget:
+        pairs *= 2
+        t_probe = one(pairs)
+    for _ in range(args.warmup):
+        one(pairs)
+    ts = [one(pairs) for _ in range(args.steps)]
+    tot = sum(ts)
+    val = pairs * args.steps / tot
+    sample = "%d of %d frame-pairs per step at %dx%d, fwd+loss+bwd, torch CPU fp32 (oracle port of the reference algorithm)" % (pairs, wl["pairs"], size, size)
+    line = dict(metric="frame_pairs_per_sec", value=val, unit="frame-pairs/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * tot / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference", config=dict(workload=wl["name"], sample=sample),
+                cpu_baseline=dict(value=val, unit="frame-pairs/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=val, unit="frame-pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-allreduce", action="store_true", help="N>1: skip the data-parallel gradient all-reduce of the hot-path parameters")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, wl, rank, world)
+
+    import torch.distributed as dist
+    from dcnet_b200 import _lib, synth
+    from dcnet_b200.hotpath import HotPath
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pairs, size = wl["pairs"], wl["size"]
+    B = 2 * pairs
+    synth.seed_all(13)                       # identical replicas (DDP broadcast equivalent)
+    hp = HotPath(size).to(dev).train()
+    random.seed(1000 + rank)
+    g = torch.Generator().manual_seed(9000 + rank)
+
+    # ---- host batches (pinned) and static device buffers
+    NB = 2
+    host = []
+    for _ in range(NB):
+        b = synth.make_hotpath_batch(pairs, size, g)
+        flat = dict(raw=b['raw'], flang=[b['flang']], fa=[b['fa']], context=[b['context']], head=b['head'], loc=b['loc'], dy_head=b['dy_head'],
+                    bbox=[b['bbox']])
+        host.append({k: [t.pin_memory() for t in v] for k, v in flat.items()})
+    grad_keys = ('raw', 'flang', 'fa', 'context', 'head', 'loc')
+    static = {k: [t.to(dev).requires_grad_(k in grad_keys) for t in v] for k, v in host[0].items()}
+    np_, ni_ = hp.draw_indices(B)
+    h_negpos, h_negidx = torch.from_numpy(np_).pin_memory(), torch.from_numpy(ni_).pin_memory()
+    s_negpos, s_negidx = h_negpos.to(dev), h_negidx.to(dev)
+    h2d_bytes = sum(t.numel() * t.element_size() for v in host[0].values() for t in v) + h_negpos.numel() * 4 + h_negidx.numel() * 8
+    h_out = torch.empty(6 + B, dtype=torch.float32).pin_memory()
+    d2h_bytes = h_out.numel() * 4
+
+    def run_step():
+        return hp.step(static['raw'], static['flang'][0], static['fa'][0], static['context'][0], static['head'], static['loc'],
+                       static['dy_head'], static['bbox'][0], s_negpos, s_negidx)
+
+    def clear_grads():
+        for p in hp.parameters():
+            p.grad = None
+        for k in grad_keys:
+            for t in static[k]:
+                t.grad = None
+
+    # ---- eager warm-up (also counts this library's launches per step)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(3):
+            clear_grads()
+            n0 = _lib.launch_count()
+            res = run_step()
+            launches_per_step = _lib.launch_count() - n0
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        clear_grads()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            res = run_step()
+    hot_grads = [p.grad for p in hp.hot_parameters if p.grad is not None] if graph is not None else None
+
+    def do_step():
+        nonlocal res
+        if graph is not None:
+            graph.replay()
+        else:
+            clear_grads()
+            res = run_step()
+        if world > 1 and not args.no_allreduce:
+            gs = hot_grads if hot_grads is not None else [p.grad for p in hp.hot_parameters if p.grad is not None]
+            flat = torch.cat([x.reshape(-1) for x in gs])
+            dist.all_reduce(flat)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: device-timed, inputs resident
+    for _ in range(args.warmup):
+        flush.zero_()
+        do_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        do_step()
+        b.record()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- e2e: host buffers, wall clock, H2D + D2H inside
+    def e2e_step(i):
+        hb = host[i % NB]
+        npos, nidx = hp.draw_indices(B)                                   # host RNG (exact reference stream)
+        h_negpos.copy_(torch.from_numpy(npos)); h_negidx.copy_(torch.from_numpy(nidx))
+        with torch.no_grad():
+            for k, v in hb.items():
+                for dst, src in zip(static[k], v):
+                    dst.copy_(src, non_blocking=True)
+            s_negpos.copy_(h_negpos, non_blocking=True); s_negidx.copy_(h_negidx, non_blocking=True)
+        do_step()
+        h_out.copy_(res, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(h_out[0])
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        loss_val = e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    value = world * pairs * args.steps / (dev_ms / 1e3)
+    e2e_val = world * pairs * args.steps / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel: co-attention forward at the finest scale (all pairs of the batch, one launch set)
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        from dcnet_b200 import ops
+        peaks = load_peaks()
+        N2 = (size // 8) ** 2
+        fr = torch.nn.functional.normalize(torch.randn(B, C_EMB, N2, device=dev).abs(), dim=1)
+        qa = torch.arange(B, device=dev, dtype=torch.int32)
+        kb = qa ^ 1
+        for _ in range(3):
+            ops.coattention(fr, qa, kb, tau=10.0)
+        reps = 10
+        tt = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ops.coattention(fr, qa, kb, tau=10.0); b.record()
+            torch.cuda.synchronize()
+            tt += a.elapsed_time(b)
+        ms = tt / reps
+        flops = 6.0 * C_EMB * N2 * N2 * pairs            # 6*c*N^2 per pair forward (both directions share S)
+        ach = flops / (ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="coattn_fwd (finest scale, N=%d, %d pairs)" % (N2, pairs), achieved=ach, peak=peaks["tensor_burst"],
+                    unit="TFLOP/s", frac=ach / peaks["tensor_burst"], traffic=None, ms=ms, peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import dcnet_oracle as O
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cpu_net = HotPath(size).net.train()
+            sp = 2
+            gb = torch.Generator().manual_seed(4242)
+
+            def one():
+                b = synth.make_hotpath_batch(sp, size, gb)
+                mk = lambda x: x.clone().requires_grad_(True)
+                cpu_net.zero_grad(set_to_none=True)
+                t0 = time.perf_counter()
+                O.hotpath_restated(cpu_net, [mk(x) for x in b['raw']], mk(b['flang']), mk(b['fa']), mk(b['context']), [mk(x) for x in b['head']],
+                                   [mk(x) for x in b['loc']], b['dy_head'], b['bbox'], size)
+                return time.perf_counter() - t0
+            one()
+            ts, t_all = [], time.perf_counter()
+            while len(ts) < 8 and time.perf_counter() - t_all < 20.0:
+                ts.append(one())
+            cpu_base = dict(value=sp * len(ts) / sum(ts), unit="frame-pairs/s", cores=cores, kind="port",
+                            sample="%d x (%d frame-pairs at %dx%d, fwd+loss+bwd) of the oracle port, torch CPU fp32, %d threads" % (len(ts), sp, size, size, cores))
+
+    if rank == 0:
+        line = dict(metric="frame_pairs_per_sec", value=value, unit="frame-pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=wl["name"], pairs_per_gpu=pairs, size=size, l2="flushed (256 MiB write) before every timed step",
+                                launch="CUDA graph replay" if graph is not None else "eager",
+                                sampling="exact reference random.sample stream (host C emulation)",
+                                grad_allreduce=bool(world > 1 and not args.no_allreduce)),
+                    clocks=clocks,
+                    e2e=dict(value=e2e_val, unit="frame-pairs/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
+                             ms_per_step=e2e_ms / args.steps, last_loss=loss_val),
+                    gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
+                    roofline=roof, cpu_baseline=cpu_base)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

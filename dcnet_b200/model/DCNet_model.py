@@ -156,13 +156,15 @@ class grounding_model(nn.Module):
         """a2: fvisu[s] = normalize_c(ConvBNReLU_1x1(raw[s]))   (:356-359) -> 3 x [B,C,N_s]"""
         return [self.mapping_visu._modules[str(s)].fused(raw_fvisu[s].flatten(2), l2norm=True) for s in range(3)]
 
-    def interframe(self, fv0):
-        """a4 (:381-430) -> packed q [30,P,C], k [30,P,C], neg [30,P,10,C]"""
+    def interframe(self, fv0, negpos=None):
+        """a4 (:381-430) -> packed q [30,P,C], k [30,P,C], neg [30,P,10,C].  negpos: optional pre-drawn device tensor
+        [P,30,10] int32 of ops.pyrandom_interframe positions (lets the caller keep the step free of host work)."""
         B, C, N0 = fv0.shape
         P = B // 2
         dev = fv0.device
         idx, _ = ops.interframe_topk(fv0.detach(), TOP_K)
-        negpos = torch.from_numpy(ops.pyrandom_interframe(P, TOP_K, N0, NEG_N)).to(dev, non_blocking=True)
+        if negpos is None:
+            negpos = torch.from_numpy(ops.pyrandom_interframe(P, TOP_K, N0, NEG_N)).to(dev, non_blocking=True)
         negidx = ops.interframe_negidx(idx, negpos, N0)
         pair = torch.arange(P, device=dev, dtype=torch.int32)[:, None]
         img = torch.cat([(2 * pair).expand(P, TOP_K), (2 * pair + 1).expand(P, TOP_K),
@@ -201,15 +203,17 @@ class grounding_model(nn.Module):
             out.append(m.fused(corr[s], u=u, cc=cc, l2norm=False))
         return out
 
-    def crossmodal(self, fv0, context):
-        """a11 (:625-637, :41-112) -> packed q [N0,B,C], k [N0,B,1,C], neg [N0,B,5,C]"""
+    def crossmodal(self, fv0, context, negidx=None):
+        """a11 (:625-637, :41-112) -> packed q [N0,B,C], k [N0,B,1,C], neg [N0,B,5,C].  negidx: optional pre-drawn device
+        tensor [B,N0,5] int64 of ops.pyrandom_crossmodal."""
         B, C, N0 = fv0.shape
         dev = fv0.device
         vit = ops.rownorm(fv0)                                   # F.normalize over the spatial axis (:629)
         lag = ops.lagnorm(context)                               # [B,T,C]
         fm = self.feature_map[0]
         word, _ = ops.crossmodal_words(lag.detach(), vit.detach(), fm.weight, fm.bias)
-        negidx = torch.from_numpy(ops.pyrandom_crossmodal(B, N0, CROSS_NEG_N)).to(dev, non_blocking=True)
+        if negidx is None:
+            negidx = torch.from_numpy(ops.pyrandom_crossmodal(B, N0, CROSS_NEG_N)).to(dev, non_blocking=True)
         key = ("cm", B, N0, str(dev))
         if key not in self._idx_cache:
             b = torch.arange(B, device=dev, dtype=torch.int32)

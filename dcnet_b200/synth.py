@@ -45,3 +45,21 @@ def make_boxes(pairs, size, gen=None):
     b1 = torch.cat([xy, xy + wh], 1)
     b2 = b1 + (torch.rand(pairs, 4, generator=gen) * 8 - 4)
     return torch.stack([b1, b2], 1).reshape(2 * pairs, 4).clamp(0, size - 1).contiguous()
+
+
+def make_hotpath_batch(pairs, size, gen=None, T=20, C=512):
+    """Synthetic tensors for dcnet_b200.hotpath.HotPath.step (all CPU fp32; see that module for the meaning)."""
+    B = 2 * pairs
+    gs = grids(size)
+    raw = make_raw_fvisu(pairs, size, gen)
+    words = make_words(pairs, T=T, gen=gen)
+    lens = (words != 0).sum(1)
+    unit = lambda t: t / t.norm(dim=1, keepdim=True)
+    flang = unit(torch.randn(pairs, C, generator=gen).abs()).repeat_interleave(2, 0).contiguous()
+    fa = unit(torch.randn(pairs, C, generator=gen).abs()).repeat_interleave(2, 0).contiguous()
+    context = torch.randn(pairs, T, 2 * C, generator=gen).repeat_interleave(2, 0)
+    context = (context * (torch.arange(T)[None, :] < lens[:, None])[:, :, None]).contiguous()    # pad_packed_sequence zeros
+    head = [torch.randn(B, 15, g * g, generator=gen) * 0.5 for g in gs]
+    loc = [torch.rand(B, g * g, generator=gen) for g in gs]
+    dy_head = [torch.randn(B, C, g * g, generator=gen) * 1e-3 for g in gs]
+    return dict(raw=raw, flang=flang, fa=fa, context=context, head=head, loc=loc, dy_head=dy_head, bbox=make_boxes(pairs, size, gen))

@@ -513,3 +513,55 @@ def losses_restated(out, bbox, size):
     total = l_yolo + 100 * l_rank + l_loc + 100 * l_if + l_cm                    # :642
     return dict(loss=total, yolo=l_yolo, rank=l_rank, interframe=l_if, cross=l_cm, loc=l_loc,
                 gi=gi, gj=gj, best_n=best_n)
+
+
+# ----------------------------------------------------------------------------------------------
+# the hot path on its own: neighbours supplied as tensors
+# ----------------------------------------------------------------------------------------------
+def hotpath_restated(net, raw, flang, fa, context, head, loc, dy_head, bbox, size, rng=_pyrandom, backward=True):
+    """Mirror of dcnet_b200.hotpath.HotPath.step for the CPU baseline and the parity tests: a2-a18 of
+    model/DCNet_model.py:356-637 + train_DCNet.py:615-690 with Darknet / text encoder / head / location branch replaced by
+    the given tensors (head[s] [B,15,N_s], loc[s] [B,N_s], dy_head[s] [B,512,N_s] = gradient entering the fusion output)."""
+    training = net.training
+    B = raw[0].shape[0]
+    P = B // 2
+    hw = [(m.shape[2], m.shape[3]) for m in raw]
+    fv = [l2norm_channels(_cbr(net.mapping_visu._modules[str(s)], raw[s].flatten(2), training)) for s in range(3)]
+    C = fv[0].shape[1]
+    f1 = [f.reshape(P, 2, C, -1)[:, 0] for f in fv]
+    f2 = [f.reshape(P, 2, C, -1)[:, 1] for f in fv]
+    q_if, k_if, neg_if, idx_if, _ = interframe_sample(f1[0], f2[0], rng, topk_fn=canonical_topk)
+    corr, sim, neg_sim, y = [], [], [], []
+    for s in range(3):
+        o1, o2 = coattention(f1[s], f2[s], net.temperature)
+        x = interleave_pairs(torch.cat([f1[s], o1], 1), torch.cat([f2[s], o2], 1))
+        c = l2norm_channels(_cbr(net.corr_conv._modules[str(s)][0], x, training))
+        corr.append(c)
+        sm, ng = pix2text(c, fa)
+        sim.append(sm); neg_sim.append(ng)
+        N = c.shape[2]
+        coord = coord_map(hw[s][0], hw[s][1], device=c.device).flatten(1)
+        xin = torch.cat([c, flang[:, :, None].expand(B, C, N), coord[None].expand(B, 8, N)], 1)
+        y.append(_cbr(net.fcn_emb._modules[str(s)][0], xin, training))
+    pred = [modulate_conf(head[s], sim[s], loc[s]) for s in range(3)]
+    fm = net.feature_map[0]
+    vit, lag, M = crossmodal_features(fv[0], context, fm.weight, fm.bias)
+    q_cm, k_cm, neg_cm, word, _ = crossmodal_sample(vit, lag, M, rng)
+    dev = raw[0].device
+    gt, gi, gj, best_n, gtc = build_target(bbox.detach().cpu(), size)
+    gt, gtc = [t.to(dev) for t in gt], [t.to(dev) for t in gtc]
+    g = [size // 32, size // 16, size // 8]
+    pred5 = [p.reshape(B, 3, 5, g[s], g[s]) for s, p in enumerate(pred)]
+    shp = lambda t, s: t.reshape(B, g[s], g[s])
+    comp = dict(yolo=yolo_loss(pred5, gt, gi, gj, best_n),
+                rank=rank_loss([shp(t, s) for s, t in enumerate(sim)], [shp(t, s) for s, t in enumerate(neg_sim)], gtc),
+                loc=loc_loss([shp(t, s) for s, t in enumerate(loc)], gtc),
+                interframe=interframe_contrastive_loss(q_if, k_if, neg_if),
+                cross=crossmodal_contrastive_loss(q_cm, k_cm, neg_cm))
+    loss = comp['yolo'] + 100 * comp['rank'] + comp['loc'] + 100 * comp['interframe'] + comp['cross']
+    boxes = decode_at([p.detach() for p in pred5], gi, gj, best_n, size)
+    iou = bbox_iou(boxes, bbox.detach().cpu().float())
+    if backward:
+        torch.autograd.backward([loss] + y, [None] + list(dy_head))
+    return dict(loss=loss, comp=comp, y=y, iou=iou, boxes=boxes, best_n=best_n, gi=gi, gj=gj, corr=corr, sim=sim, pred=pred,
+                idx_if=idx_if, word=word)
