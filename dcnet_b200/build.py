@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart_static", "-lcuda", "-lpthread", "-ldl", "-lrt"]
+    cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     subprocess.check_call(cmd)
     with open(STAMP, "w") as fh:
         fh.write(dig)

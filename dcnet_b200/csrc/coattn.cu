@@ -62,10 +62,15 @@ extern "C" size_t dcnet_coattn_workspace_bytes(int nprob, int C, int N) {
   return 2 * align256((size_t)nprob * N * N * sizeof(float)) + 256;
 }
 
-extern "C" int dcnet_coattn_fwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob,
-                                float* out, float* lse, int C, int N, float tau, void* workspace, size_t workspace_bytes,
-                                void* stream) {
-  DCNET_CHECK_ARG(frames && qa && kb && oidx && out && lse && nprob >= 0 && C > 0 && N > 0, "coattn_fwd: bad arguments");
+static bool coattn_tc_ok(int precision, int C, int N, const void* a, const void* b, const void* c) {
+  auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  return precision == 1 && N % 4 == 0 && C % 128 == 0 && al(a) && al(b) && al(c);
+}
+
+extern "C" int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                float* out, int n_out, float* lse, int C, int N, float tau, int precision,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  DCNET_CHECK_ARG(frames && qa && kb && oidx && out && lse && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_fwd: bad arguments");
   if (nprob == 0) return 0;
   cudaStream_t st = as_stream(stream);
   if (umma_coattn_supported(C, N))
@@ -73,10 +78,24 @@ extern "C" int dcnet_coattn_fwd(const float* frames, const int* qa, const int* k
   DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(nprob, C, N), "coattn_fwd: workspace too small");
   float* S = (float*)workspace;
   const long long CN = (long long)C * N, NN = (long long)N * N;
+  const long long rows = (long long)nprob * N;
+  if (coattn_tc_ok(precision, C, N, frames, out, S)) {
+    // S' = tau Fa^T Fb : both operands MN-major views of the [C,N] maps
+    UmmaOperand A{frames, C, N, N, CN, F, true}, B{frames, C, N, N, CN, F, true};
+    UmmaEpilogue e{};
+    e.out = S; e.ldo = N; e.so_b = NN; e.alpha = tau; e.idxA = qa; e.idxB = kb;
+    DCNET_TRY(umma_gemm(A, B, nullptr, N, N, C, 0, 0, nprob, e, st));
+    softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(S, lse, rows, N);
+    DCNET_LAUNCH_OK("coattn_fwd.softmax");
+    // O[c,i] = sum_j Fb[c,j] P[i,j] : both K-major
+    UmmaOperand A2{frames, C, N, N, CN, F, false}, B2{S, N, N, N, NN, nprob, false};
+    UmmaEpilogue e2{};
+    e2.out = out; e2.ldo = N; e2.so_b = CN; e2.alpha = 1.f; e2.idxA = kb; e2.idxC = oidx;
+    return umma_gemm(A2, B2, nullptr, C, N, N, 0, 0, nprob, e2, st);
+  }
   // S' = tau Fa^T Fb
   DCNET_TRY(sgemm_launch(frames, frames, S, N, N, C, nprob, 1, 1, N, CN, 0, N, 1, CN, 0, N, 1, NN, qa, kb, nullptr, tau, 0.f,
                          nullptr, 0, 0, st));
-  const long long rows = (long long)nprob * N;
   softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(S, lse, rows, N);
   DCNET_LAUNCH_OK("coattn_fwd.softmax");
   // O[c,i] = sum_j Fb[c,j] P[i,j]
@@ -85,11 +104,11 @@ extern "C" int dcnet_coattn_fwd(const float* frames, const int* qa, const int* k
   return 0;
 }
 
-extern "C" int dcnet_coattn_bwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob,
-                                const float* out, const float* lse, const float* dout, float* dframes,
-                                int C, int N, float tau, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                const float* out, int n_out, const float* lse, const float* dout, float* dframes,
+                                int C, int N, float tau, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   (void)out;
-  DCNET_CHECK_ARG(frames && qa && kb && oidx && lse && dout && dframes && nprob >= 0 && C > 0 && N > 0, "coattn_bwd: bad arguments");
+  DCNET_CHECK_ARG(frames && qa && kb && oidx && lse && dout && dframes && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_bwd: bad arguments");
   if (nprob == 0) return 0;
   DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(nprob, C, N), "coattn_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
@@ -97,18 +116,46 @@ extern "C" int dcnet_coattn_bwd(const float* frames, const int* qa, const int* k
   float* P = (float*)workspace;
   float* dP = (float*)((char*)workspace + align256((size_t)nprob * NN * sizeof(float)));
   const long long rows = (long long)nprob * N;
+  const bool tc = coattn_tc_ok(precision, C, N, frames, dout, dframes) && coattn_tc_ok(precision, C, N, P, dP, P);
+  auto exp_launch = [&]() {
+    long long g = (rows * N + 255) / 256;
+    exp_lse_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, st>>>(P, lse, rows, N);
+  };
+  if (tc) {
+    UmmaOperand Fmn{frames, C, N, N, CN, F, true}, Fk{frames, C, N, N, CN, F, false};
+    UmmaOperand Gmn{dout, C, N, N, CN, n_out, true}, Gk{dout, C, N, N, CN, n_out, false};
+    UmmaOperand Pmn{P, N, N, N, NN, nprob, true};
+    UmmaOperand dSk{dP, N, N, N, NN, nprob, false}, dSmn{dP, N, N, N, NN, nprob, true};
+    UmmaEpilogue e{};
+    // P = exp(tau S - lse)
+    e.out = P; e.ldo = N; e.so_b = NN; e.alpha = tau; e.idxA = qa; e.idxB = kb;
+    DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    exp_launch();
+    DCNET_LAUNCH_OK("coattn_bwd.exp");
+    // dP[i,j] = sum_c dO[c,i] Fb[c,j]
+    e = UmmaEpilogue{}; e.out = dP; e.ldo = N; e.so_b = NN; e.alpha = 1.f; e.idxA = oidx; e.idxB = kb;
+    DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    // dFb[c,j] += sum_i dO[c,i] P[i,j]
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = oidx; e.idxC = kb;
+    DCNET_TRY(umma_gemm(Gk, Pmn, nullptr, C, N, N, 0, 0, nprob, e, st));
+    softmax_bwd_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, dP, rows, N, tau);
+    DCNET_LAUNCH_OK("coattn_bwd.softmax");
+    // dFa[c,i] += sum_j Fb[c,j] dS[i,j]
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = kb; e.idxC = qa;
+    DCNET_TRY(umma_gemm(Fk, dSk, nullptr, C, N, N, 0, 0, nprob, e, st));
+    // dFb[c,j] += sum_i Fa[c,i] dS[i,j]
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = qa; e.idxC = kb;
+    return umma_gemm(Fk, dSmn, nullptr, C, N, N, 0, 0, nprob, e, st);
+  }
   // recompute P = exp(tau S - lse)
   DCNET_TRY(sgemm_launch(frames, frames, P, N, N, C, nprob, 1, 1, N, CN, 0, N, 1, CN, 0, N, 1, NN, qa, kb, nullptr, tau, 0.f,
                          nullptr, 0, 0, st));
-  {
-    long long g = (rows * N + 255) / 256;
-    exp_lse_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, st>>>(P, lse, rows, N);
-    DCNET_LAUNCH_OK("coattn_bwd.exp");
-  }
+  exp_launch();
+  DCNET_LAUNCH_OK("coattn_bwd.exp");
   // dP[i,j] = sum_c dO[c,i] Fb[c,j]
   DCNET_TRY(sgemm_launch(dout, frames, dP, N, N, C, nprob, 1, 1, N, CN, 0, N, 1, CN, 0, N, 1, NN, oidx, kb, nullptr, 1.f, 0.f,
                          nullptr, 0, 0, st));
-  // dFb += dO P   (uses P and dO before dP is overwritten by dS? independent buffers: order free)
+  // dFb += dO P
   DCNET_TRY(sgemm_launch(dout, P, dframes, C, N, N, nprob, 1, N, 1, CN, 0, N, 1, NN, 0, N, 1, CN, oidx, nullptr, kb, 1.f, 0.f,
                          nullptr, 0, 1, st));
   softmax_bwd_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, dP, rows, N, tau);

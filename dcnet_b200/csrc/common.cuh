@@ -77,3 +77,17 @@ int sgemm_launch(const float* A, const float* B, float* C, int M, int N, int K, 
                  long long sCm, long long sCn, long long sCb,
                  const int* idxA, const int* idxB, const int* idxC,
                  float alpha, float beta, const float* colscale, long long sColB, int atomic, cudaStream_t st);
+
+// tcgen05 TF32 GEMM (umma_gemm.cu)
+struct UmmaOperand {
+  const float* ptr; long long rows, cols, ld, batch_stride; int batches;   // batches = 0: not batched
+  bool mn_major;
+};
+struct UmmaEpilogue {
+  float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2; int m_split;
+  float alpha; int atomic; const float* u; int ldu; const float* cc; long long ldcc; float* sum; float* sumsq;
+  const int* idxA; const int* idxB; const int* idxC;
+};
+bool umma_gemm_usable(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int K);
+int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int M, int N, int K, int k_split_elems, int n_split,
+              int batch, const UmmaEpilogue& e, cudaStream_t st);

@@ -5,6 +5,11 @@
 
 namespace {
 
+inline int ew_grid(long long total) {
+  long long g = (total + 255) / 256;
+  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
 // ------------------------------------------------------------------------------------------------------
 // z[b,c,n] = u[b,c] + cc[c,n]   (text + coordinate terms of the split-weight fusion)
 // ------------------------------------------------------------------------------------------------------
@@ -77,6 +82,38 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
       rmean[c] = (1.f - momentum) * rmean[c] + momentum * mu;
       rvar[c] = (1.f - momentum) * rvar[c] + momentum * unb;
     }
+  }
+}
+
+// sum / sum of squares per channel (exact-fp32 path feeding dcnet_bn_finalize); one CTA per channel
+__global__ void __launch_bounds__(256) chan_sums_kernel(const float* __restrict__ z, int B, int C, int N, float* __restrict__ sums) {
+  __shared__ float sh[32];
+  const int c = blockIdx.x;
+  const long long M = (long long)B * N;
+  float s = 0.f, q = 0.f;
+  for (long long i = threadIdx.x; i < M; i += blockDim.x) {
+    const long long b = i / N;
+    const float v = z[(b * C + c) * N + (i - b * N)];
+    s += v;
+    q = fmaf(v, v, q);
+  }
+  s = block_sum(s, sh);
+  q = block_sum(q, sh);
+  if (threadIdx.x == 0) { sums[c] = s; sums[C + c] = q; }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ rmean, float* __restrict__ rvar) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mu = sums[c] / count;
+  const float var = fmaxf(sums[C + c] / count - mu * mu, 0.f);
+  mean[c] = mu;
+  invstd[c] = 1.0f / sqrtf(var + eps);
+  if (rmean) {
+    const float unb = count > 1.f ? var * count / (count - 1.f) : var;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * mu;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * unb;
   }
 }
 
@@ -282,18 +319,29 @@ __global__ void coord_map_kernel(float* __restrict__ coord, int h, int w) {
   coord[7 * hw + i] = 1.f / fw;
 }
 
-inline int ew_grid(long long total) {
-  long long g = (total + 255) / 256;
-  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
-}
-
 }  // namespace
 
+static bool tc_shape_ok(int N, const void* a, const void* b) {
+  return (N % 4 == 0) && (reinterpret_cast<uintptr_t>(a) % 16 == 0) && (!b || reinterpret_cast<uintptr_t>(b) % 16 == 0);
+}
+
 extern "C" int dcnet_conv1x1_fwd(const float* x1, int K1, const float* x2, int K2, const float* W, int ldw,
-                                 const float* u, const float* cc, float* z, int B, int C, int N, void* stream) {
+                                 const float* u, const float* cc, float* z, int B, int C, int N,
+                                 float* stat_sums, int precision, void* stream) {
   DCNET_CHECK_ARG(x1 && W && z && K1 > 0 && B > 0 && C > 0 && N > 0, "conv1x1_fwd: bad arguments");
   DCNET_CHECK_ARG((x2 != nullptr) == (K2 > 0) && ldw >= K1 + K2, "conv1x1_fwd: x2/K2/ldw inconsistent");
   cudaStream_t st = as_stream(stream);
+  const bool tc = precision == 1 && tc_shape_ok(N, x1, x2) && tc_shape_ok(N, z, W) && ldw % 4 == 0 && C % 128 == 0 && K1 % 32 == 0 && K2 % 32 == 0;
+  if (tc) {
+    if (stat_sums) DCNET_CUDA(cudaMemsetAsync(stat_sums, 0, 2 * (size_t)C * sizeof(float), st), "conv1x1_fwd.memset");
+    UmmaOperand A{W, C, K1 + K2, ldw, 0, 0, false};
+    UmmaOperand Bx{x1, K1, N, N, (long long)K1 * N, B, true};
+    UmmaOperand Bx2{x2, K2, N, N, (long long)K2 * N, B, true};
+    UmmaEpilogue e{};
+    e.out = z; e.ldo = N; e.so_b = (long long)C * N; e.alpha = 1.f; e.u = u; e.ldu = C; e.cc = cc; e.ldcc = N;
+    e.sum = stat_sums; e.sumsq = stat_sums ? stat_sums + C : nullptr;
+    return umma_gemm(A, Bx, x2 ? &Bx2 : nullptr, C, N, K1 + K2, K1, 0, B, e, st);
+  }
   float beta = 0.f;
   if (u || cc) {
     init_bias_kernel<<<ew_grid((long long)B * C * N), 256, 0, st>>>(z, u, cc, B, C, N);
@@ -305,13 +353,32 @@ extern "C" int dcnet_conv1x1_fwd(const float* x1, int K1, const float* x2, int K
   if (x2)
     DCNET_TRY(sgemm_launch(W + K1, x2, z, C, N, K2, B, 1, ldw, 1, 0, 0, N, 1, (long long)K2 * N, 0, N, 1, (long long)C * N,
                            nullptr, nullptr, nullptr, 1.f, 1.f, nullptr, 0, 0, st));
+  if (stat_sums) {
+    chan_sums_kernel<<<C, 256, 0, st>>>(z, B, C, N, stat_sums);
+    DCNET_LAUNCH_OK("conv1x1_fwd.sums");
+  }
   return 0;
 }
 
 extern "C" int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, float* dx1, int K1, float* dx2, int K2,
-                                      int B, int C, int N, void* stream) {
+                                      int B, int C, int N, int precision, void* stream) {
   DCNET_CHECK_ARG(dz && W && B > 0 && C > 0 && N > 0 && ldw >= K1 + K2, "conv1x1_bwd_data: bad arguments");
   cudaStream_t st = as_stream(stream);
+  const bool tc = precision == 1 && tc_shape_ok(N, dz, W) && tc_shape_ok(N, dx1, dx2) && ldw % 4 == 0 && C % 32 == 0 && K1 % 128 == 0 &&
+                  K2 % 128 == 0;
+  if (tc && (dx1 || dx2)) {
+    // A = W^T as an MN-major operand: rows = C (reduction), cols = input channel (the M index)
+    const int moff = dx1 ? 0 : K1;
+    const int M = (dx1 ? K1 : 0) + (dx2 ? K2 : 0);
+    UmmaOperand A{W + moff, C, M, ldw, 0, 0, true};
+    UmmaOperand Bz{dz, C, N, N, (long long)C * N, B, true};
+    UmmaEpilogue e{};
+    e.alpha = 1.f;
+    if (dx1) { e.out = dx1; e.ldo = N; e.so_b = (long long)K1 * N; }
+    if (dx1 && dx2) { e.out2 = dx2; e.ldo2 = N; e.so_b2 = (long long)K2 * N; e.m_split = K1; }
+    if (!dx1) { e.out = dx2; e.ldo = N; e.so_b = (long long)K2 * N; }
+    return umma_gemm(A, Bz, nullptr, M, N, C, 0, 0, B, e, st);
+  }
   if (dx1)
     DCNET_TRY(sgemm_launch(W, dz, dx1, K1, N, C, B, 1, 1, ldw, 0, 0, N, 1, (long long)C * N, 0, N, 1, (long long)K1 * N,
                            nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 0, st));
@@ -322,17 +389,27 @@ extern "C" int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, 
 }
 
 extern "C" int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1, const float* x2, int K2,
-                                        float* dW, int ldw, float* du, float* dcc, int B, int C, int N, void* stream) {
+                                        float* dW, int ldw, float* du, float* dcc, int B, int C, int N, int precision, void* stream) {
   DCNET_CHECK_ARG(dz && B > 0 && C > 0 && N > 0 && ldw >= K1 + K2, "conv1x1_bwd_weight: bad arguments");
   cudaStream_t st = as_stream(stream);
   if (dW && x1) {
-    // split the (b,n) reduction over CTAs along b; fp32 atomics into the zeroed columns
+    // the (b,n) reduction is split over CTAs along b; fp32 atomics into the zeroed columns
     DCNET_CUDA(cudaMemset2DAsync(dW, (size_t)ldw * sizeof(float), 0, (size_t)(K1 + K2) * sizeof(float), C, st), "conv1x1_bwd_weight.memset");
-    DCNET_TRY(sgemm_launch(dz, x1, dW, C, K1, N, B, 1, N, 1, (long long)C * N, 0, 1, N, (long long)K1 * N, 0, ldw, 1, 0,
-                           nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 1, st));
-    if (x2)
-      DCNET_TRY(sgemm_launch(dz, x2, dW + K1, C, K2, N, B, 1, N, 1, (long long)C * N, 0, 1, N, (long long)K2 * N, 0, ldw, 1, 0,
+    const bool tc = precision == 1 && tc_shape_ok(N, dz, x1) && tc_shape_ok(N, x2, dW) && C % 128 == 0 && K1 % 128 == 0 && K2 % 128 == 0;
+    if (tc) {
+      UmmaOperand A{dz, C, N, N, (long long)C * N, B, false};
+      UmmaOperand Bx{x1, K1, N, N, (long long)K1 * N, B, false};
+      UmmaOperand Bx2{x2, K2, N, N, (long long)K2 * N, B, false};
+      UmmaEpilogue e{};
+      e.out = dW; e.ldo = ldw; e.so_b = 0; e.alpha = 1.f; e.atomic = 1;
+      DCNET_TRY(umma_gemm(A, Bx, x2 ? &Bx2 : nullptr, C, K1 + K2, N, 0, K1, B, e, st));
+    } else {
+      DCNET_TRY(sgemm_launch(dz, x1, dW, C, K1, N, B, 1, N, 1, (long long)C * N, 0, 1, N, (long long)K1 * N, 0, ldw, 1, 0,
                              nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 1, st));
+      if (x2)
+        DCNET_TRY(sgemm_launch(dz, x2, dW + K1, C, K2, N, B, 1, N, 1, (long long)C * N, 0, 1, N, (long long)K2 * N, 0, ldw, 1, 0,
+                               nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 1, st));
+    }
   }
   if (du) {
     const long long rows = (long long)B * C;
@@ -343,6 +420,15 @@ extern "C" int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1
     batchsum_kernel<<<ew_grid((long long)C * N), 256, 0, st>>>(dz, dcc, B, (long long)C * N);
     DCNET_LAUNCH_OK("conv1x1_bwd_weight.dcc");
   }
+  return 0;
+}
+
+extern "C" int dcnet_bn_finalize(const float* stat_sums, long long count, int C, float eps, float momentum,
+                                 float* mean, float* invstd, float* running_mean, float* running_var, void* stream) {
+  DCNET_CHECK_ARG(stat_sums && mean && invstd && count > 0 && C > 0, "bn_finalize: bad arguments");
+  DCNET_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running_mean/var must both be given");
+  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, as_stream(stream)>>>(stat_sums, (float)count, C, eps, momentum, mean, invstd, running_mean, running_var);
+  DCNET_LAUNCH_OK("bn_finalize");
   return 0;
 }
 

@@ -1,0 +1,247 @@
+// Batched TF32 GEMM on the 5th-generation tensor cores (tcgen05.mma, fp32 accumulators in TMEM) fed by TMA.
+//
+// Operands are the fp32 tensors exactly as the reference lays them out ([.., C, N] with N innermost): TMA brings 128-byte-swizzled
+// tiles into shared memory and the MMA reads them as TF32 (the low 13 mantissa bits are ignored by the hardware), so there is
+// no conversion pass and no extra copy in HBM.  Either operand can be K-major (reduction axis contiguous) or MN-major
+// (output axis contiguous); that covers every contraction of the hot path without a transpose:
+//     conv fwd      z[b]  = W x[b]                A: W      (K-major)   B: x[b]   (MN-major)
+//     conv bwd data dx[b] = W^T dz[b]             A: W^T    (MN-major)  B: dz[b]  (MN-major)
+//     conv bwd wgt  dW   += dz[b] x[b]^T          A: dz[b]  (K-major)   B: x[b]   (K-major)
+//     co-attention  S = Fa^T Fb  (MN,MN);  O = Fb P^T (K,K);  dFb += dO P (K,MN);  dFa += Fb dS^T (K,K);  dFb += Fa dS (K,MN)
+//
+// CTA = one 128 x BN output tile.  Warp roles (192 threads): warps 0-3 epilogue (TMEM -> registers -> global, warp w owns TMEM
+// lanes 32w..32w+31), warp 4 TMA producer (one elected lane), warp 5 TMEM allocator + MMA issuer (one elected lane).
+// A STAGES-deep ring of {A tile, B tile} with full/empty mbarriers decouples TMA from MMA; tcgen05.commit releases a slot.
+#include "common.cuh"
+#include "umma.cuh"
+
+using namespace umma;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;               // tf32 elements per stage along the reduction = one 128-byte swizzle row
+constexpr int A_BYTES = BM * BK * 4; // 16 KiB
+constexpr int BLK_BYTES = 32 * BK * 4;   // one MN-major block: 32 (mn) x BK (k rows) = 4 KiB
+
+struct GemmP {
+  int M_valid, N_valid;     // store predicates
+  int k_iters;              // BK-steps
+  int k_split;              // B MN-major: iterations >= k_split read mapB2 (second K source), 0 = off
+  int n_split;              // B K-major : output columns >= n_split read mapB2 (rows n - n_split), 0 = off
+  int m_split;              // store: rows >= m_split go to out2 (row m - m_split), 0 = off
+  int a_batched, b_batched; // coordinate 2 of the operand = batch index (else 0)
+  const int* idxA; const int* idxB; const int* idxC;   // optional batch indirection (frame / problem indices)
+  float* out; long long ldo, so_b;
+  float* out2; long long ldo2, so_b2;
+  float alpha;
+  int atomic;               // 1: atomicAdd into out (split reductions / shared gradients)
+  const float* u; int ldu;  // + u[b*ldu + m]
+  const float* cc; long long ldcc;   // + cc[m*ldcc + n]
+  float* sum; float* sumsq; // per-row (channel) sums of the stored values and their squares (BatchNorm statistics)
+};
+
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapB2, const GemmP p) {
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, z = blockIdx.z;
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    prefetch_tmap(&mapB2);
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      const int a_b = p.a_batched ? (p.idxA ? p.idxA[z] : z) : 0;
+      const int b_b = p.b_batched ? (p.idxB ? p.idxB[z] : z) : 0;
+      for (int it = 0; it < p.k_iters; it++) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        uint8_t* sA = smem + s * STAGE_BYTES;
+        uint8_t* sB = sA + A_BYTES;
+        if constexpr (A_MN) {
+#pragma unroll
+          for (int j = 0; j < BM / 32; j++) tma_load_3d(sA + j * BLK_BYTES, &mapA, &full[s], m0 + 32 * j, it * BK, a_b);
+        } else {
+          tma_load_3d(sA, &mapA, &full[s], it * BK, m0, a_b);
+        }
+        if constexpr (B_MN) {
+          const bool src2 = p.k_split > 0 && it >= p.k_split;
+          const CUtensorMap* mb = src2 ? &mapB2 : &mapB;
+          const int kc = (src2 ? it - p.k_split : it) * BK;
+#pragma unroll
+          for (int j = 0; j < BN / 32; j++) tma_load_3d(sB + j * BLK_BYTES, mb, &full[s], n0 + 32 * j, kc, b_b);
+        } else {
+          const bool src2 = p.n_split > 0 && n0 >= p.n_split;
+          tma_load_3d(sB, src2 ? &mapB2 : &mapB, &full[s], it * BK, src2 ? n0 - p.n_split : n0, b_b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc(FMT_TF32, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      for (int it = 0; it < p.k_iters; it++) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ks++) {     // one MMA = 8 tf32 along K = 32 bytes
+          // K-major : +32 B inside the 128-B swizzle row; rows 128 B apart, 8-row atoms 1024 B apart
+          // MN-major: +8 k-rows = +1024 B; MN blocks (32 elements) BLK_BYTES apart
+          const uint64_t ad = A_MN ? smem_desc_sw128(sA + ks * 1024, BLK_BYTES, 1024) : smem_desc_sw128(sA + ks * 32, 16, 1024);
+          const uint64_t bd = B_MN ? smem_desc_sw128(sB + ks * 1024, BLK_BYTES, 1024) : smem_desc_sw128(sB + ks * 32, 16, 1024);
+          mma_tf32(tmem_base, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+        }
+        mma_commit(&empty[s]);      // slot reusable once these MMAs have read it
+      }
+      mma_commit(accum);            // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warp w <-> TMEM lanes 32w..32w+31 <-> output rows m0+32w..
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int row = m0 + warp * 32 + lane;
+    const bool row_ok = row < p.M_valid;
+    const int zc = p.idxC ? p.idxC[z] : z;
+    float* orow;
+    if (p.m_split > 0 && m0 >= p.m_split) orow = p.out2 + (long long)zc * p.so_b2 + (long long)(row - p.m_split) * p.ldo2;
+    else orow = p.out + (long long)zc * p.so_b + (long long)row * p.ldo;
+    const float bias = (p.u && row_ok) ? p.u[(long long)z * p.ldu + row] : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (row_ok && nb < p.N_valid) {
+      if (p.cc) {
+        const float* cr = p.cc + (long long)row * p.ldcc + nb;
+#pragma unroll
+        for (int e = 0; e < 32; e++) v[e] = fmaf(p.alpha, v[e], bias + ((nb + e < p.N_valid) ? cr[e] : 0.f));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; e++) v[e] = fmaf(p.alpha, v[e], bias);
+      }
+      if (p.atomic) {
+#pragma unroll
+        for (int e = 0; e < 32; e++)
+          if (nb + e < p.N_valid) atomicAdd(orow + nb + e, v[e]);
+      } else if (nb + 32 <= p.N_valid) {
+        float4* o4 = reinterpret_cast<float4*>(orow + nb);
+#pragma unroll
+        for (int e = 0; e < 8; e++) o4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+#pragma unroll
+        for (int e = 0; e < 32; e++) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
+      } else {
+        for (int e = 0; e < 32 && nb + e < p.N_valid; e++) { orow[nb + e] = v[e]; s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
+      }
+      }
+      __syncwarp();
+    }
+    if (p.sum && row_ok) {
+      atomicAdd(p.sum + row, s1);
+      atomicAdd(p.sumsq + row, s2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, BN);
+}
+
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const GemmP& p, dim3 grid, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_BYTES + BN * BK * 4) + 1024 + 256;
+  auto kern = umma_gemm_kernel<A_MN, B_MN, BN, STAGES>;
+  DCNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "umma_gemm.attr");   // per device
+  kern<<<grid, 192, smem, st>>>(ma, mb, mb2, p);
+  DCNET_LAUNCH_OK("umma_gemm");
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host-side description of one operand: fp32 tensor [batch][rows][cols] (cols contiguous).
+//   K-major  use: rows = the M (or N) index, cols = the reduction index
+//   MN-major use: rows = the reduction index, cols = the M (or N) index
+// ---------------------------------------------------------------------------------------------------------------------
+static bool operand_ok(const UmmaOperand& o) {
+  return o.ptr && (reinterpret_cast<uintptr_t>(o.ptr) % 16 == 0) && (o.ld % 4 == 0) && (o.batch_stride % 4 == 0) && o.rows > 0 && o.cols > 0;
+}
+
+static int make_operand_map(CUtensorMap* m, const UmmaOperand& o, int tile_rows_kmajor) {
+  const uint64_t nb = o.batches > 0 ? (uint64_t)o.batches : 1;
+  const uint64_t bs = o.batches > 0 ? (uint64_t)o.batch_stride : (uint64_t)(o.rows * o.ld);
+  // box: K-major {32 k, tile rows}; MN-major {32 mn, 32 k rows}
+  const int r = make_tmap_f32(m, o.ptr, (uint64_t)o.cols, (uint64_t)o.rows, nb, (uint64_t)o.ld, bs, 32, o.mn_major ? 32u : (uint32_t)tile_rows_kmajor);
+  if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", r, o.rows, o.cols, o.ld);
+  return 0;
+}
+
+bool umma_gemm_usable(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int K) {
+  if (!operand_ok(A) || !operand_ok(B) || (B2 && !operand_ok(*B2))) return false;
+  return K > 0;
+}
+
+// D[z] (M x N) = alpha * A[z] (M x K) B[z] (K x N) (+ second source) ; grid.z = batch
+int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int M, int N, int K, int k_split_elems, int n_split,
+              int batch, const UmmaEpilogue& e, cudaStream_t st) {
+  DCNET_CHECK_ARG(umma_gemm_usable(A, B, B2, K), "umma_gemm: operand not TMA-compatible (16-B aligned base, row pitch multiple of 4 floats)");
+  DCNET_CHECK_ARG(k_split_elems % BK == 0, "umma_gemm: k_split must be a multiple of %d", BK);
+  DCNET_CHECK_ARG(batch >= 1 && batch <= 65535, "umma_gemm: batch %d", batch);
+  const int BN = (N <= 64) ? 64 : 128;
+  CUtensorMap ma, mb, mb2;
+  DCNET_TRY(make_operand_map(&ma, A, BM));
+  DCNET_TRY(make_operand_map(&mb, B, BN));
+  if (B2) DCNET_TRY(make_operand_map(&mb2, *B2, BN)); else mb2 = mb;
+  GemmP p{};
+  p.M_valid = M; p.N_valid = N;
+  p.k_iters = (K + BK - 1) / BK;
+  p.k_split = (B.mn_major && B2) ? k_split_elems / BK : 0;
+  p.n_split = (!B.mn_major && B2) ? n_split : 0;
+  p.m_split = e.m_split;
+  p.a_batched = A.batches > 0; p.b_batched = B.batches > 0;
+  p.idxA = e.idxA; p.idxB = e.idxB; p.idxC = e.idxC;
+  p.out = e.out; p.ldo = e.ldo; p.so_b = e.so_b; p.out2 = e.out2; p.ldo2 = e.ldo2; p.so_b2 = e.so_b2;
+  p.alpha = e.alpha; p.atomic = e.atomic; p.u = e.u; p.ldu = e.ldu; p.cc = e.cc; p.ldcc = e.ldcc; p.sum = e.sum; p.sumsq = e.sumsq;
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
+  const int am = A.mn_major ? 1 : 0, bm = B.mn_major ? 1 : 0;
+#define DISPATCH(AM, BMJ)                                                                   \
+  if (am == AM && bm == BMJ) {                                                              \
+    if (BN == 64) return launch_cfg<AM, BMJ, 64, 4>(ma, mb, mb2, p, grid, st);              \
+    return launch_cfg<AM, BMJ, 128, 3>(ma, mb, mb2, p, grid, st);                           \
+  }
+  DISPATCH(0, 0) DISPATCH(0, 1) DISPATCH(1, 0) DISPATCH(1, 1)
+#undef DISPATCH
+  return dcnet_set_error(-1, "umma_gemm: unreachable");
+}

@@ -143,6 +143,7 @@ class grounding_model(nn.Module):
         self.exact_sampling = True     # reproduce the reference's random.sample stream
         self._idx_cache = {}
         self._capture = None
+        self.precision = ops.TENSOR_TF32   # GEMM-shaped ops on tcgen05 (TF32 operands, fp32 accumulate); ops.EXACT_FP32 = CUDA cores
 
     # ---------------------------------------------------------------------------------------------------------
     def _pair_index(self, B, device):
@@ -153,8 +154,11 @@ class grounding_model(nn.Module):
         return self._idx_cache[key]
 
     def map_visual(self, raw_fvisu):
-        """a2: fvisu[s] = normalize_c(ConvBNReLU_1x1(raw[s]))   (:356-359) -> 3 x [B,C,N_s]"""
-        return [self.mapping_visu._modules[str(s)].fused(raw_fvisu[s].flatten(2), l2norm=True) for s in range(3)]
+        """a2: fvisu[s] = normalize_c(ConvBNReLU_1x1(raw[s]))   (:356-359) -> 3 x [B,C,N_s].
+        Scale 0 runs in exact fp32: the top-30 correspondences (a4) and the arg-max words (a11) are selected from it and
+        index parity with the reference needs fp32 scores (SURVEY section 7 "Index parity"); the other scales use tcgen05."""
+        return [self.mapping_visu._modules[str(s)].fused(raw_fvisu[s].flatten(2), l2norm=True,
+                                                         precision=ops.EXACT_FP32 if s == 0 else self.precision) for s in range(3)]
 
     def interframe(self, fv0, negpos=None):
         """a4 (:381-430) -> packed q [30,P,C], k [30,P,C], neg [30,P,10,C].  negpos: optional pre-drawn device tensor
@@ -183,8 +187,8 @@ class grounding_model(nn.Module):
         qa, kb = self._pair_index(B, fv[0].device)
         corr, sim, neg_sim = [], [], []
         for s in range(3):
-            attn = ops.coattention(fv[s], qa, kb, tau=self.temperature)
-            y, sm, ng = self.corr_conv._modules[str(s)][0].fused(fv[s], x2=attn, fa=fa, l2norm=True)
+            attn = ops.coattention(fv[s], qa, kb, tau=self.temperature, precision=self.precision)
+            y, sm, ng = self.corr_conv._modules[str(s)][0].fused(fv[s], x2=attn, fa=fa, l2norm=True, precision=self.precision)
             corr.append(y); sim.append(sm); neg_sim.append(ng)
         return corr, sim, neg_sim
 
@@ -200,7 +204,7 @@ class grounding_model(nn.Module):
             cc = None
             if self.coordmap:
                 cc = w[:, 2 * C:] @ coords[s]                                    # coord term W_c coord        [C,N]
-            out.append(m.fused(corr[s], u=u, cc=cc, l2norm=False))
+            out.append(m.fused(corr[s], u=u, cc=cc, l2norm=False, precision=self.precision))
         return out
 
     def crossmodal(self, fv0, context, negidx=None):

@@ -173,7 +173,7 @@ class _ConvBNAct(torch.autograd.Function):
     """a1/a2/a6/a8: y = [l2norm_c] act(BN(W[:, :K1] x1 + W[:, K1:K1+K2] x2 + u 1^T + cc)), plus the fused a9 dots."""
 
     @staticmethod
-    def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, running_mean, running_var, training, momentum, eps, slope, l2norm):
+    def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, running_mean, running_var, training, momentum, eps, slope, l2norm, precision):
         x1 = _c(x1, name="x1")
         x2 = _c(x2, name="x2")
         weight = _c(weight, name="weight")
@@ -185,12 +185,18 @@ class _ConvBNAct(torch.autograd.Function):
         dev = x1.device
         st = _st()
         z = torch.empty(B, C, N, device=dev, dtype=F32)
-        _lib.call("dcnet_conv1x1_fwd", _p(x1), K1, _p(x2), K2, _p(weight), ldw, _p(u), _p(cc), _p(z), B, C, N, st)
         mean = torch.empty(C, device=dev, dtype=F32)
         invstd = torch.empty(C, device=dev, dtype=F32)
-        if training:
-            _lib.call("dcnet_bn_stats", _p(z), B, C, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
+        if training and precision == 1:
+            # tensor-core path: BatchNorm sums come out of the GEMM epilogue, z is not re-read
+            sums = torch.empty(2 * C, device=dev, dtype=F32)
+            _lib.call("dcnet_conv1x1_fwd", _p(x1), K1, _p(x2), K2, _p(weight), ldw, _p(u), _p(cc), _p(z), B, C, N, _p(sums), precision, st)
+            _lib.call("dcnet_bn_finalize", _p(sums), B * N, C, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
         else:
+            _lib.call("dcnet_conv1x1_fwd", _p(x1), K1, _p(x2), K2, _p(weight), ldw, _p(u), _p(cc), _p(z), B, C, N, None, precision, st)
+        if training and precision != 1:
+            _lib.call("dcnet_bn_stats", _p(z), B, C, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
+        elif not training:
             _lib.call("dcnet_bn_eval_stats", _p(running_mean), _p(running_var), C, eps, _p(mean), _p(invstd), st)
         y = torch.empty_like(z)
         sim = neg = None
@@ -200,7 +206,7 @@ class _ConvBNAct(torch.autograd.Function):
         _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm), _p(y), _p(fa), _p(sim), _p(neg),
                   B, C, N, st)
         ctx.save_for_backward(x1, x2, weight, gamma, beta, fa, z, mean, invstd)
-        ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None)
+        ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None, precision)
         if fa is None:
             return y
         return y, sim, neg
@@ -208,7 +214,7 @@ class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, dsim=None, dneg=None):
         x1, x2, weight, gamma, beta, fa, z, mean, invstd = ctx.saved_tensors
-        training, slope, l2norm, has_u, has_cc = ctx.cfg
+        training, slope, l2norm, has_u, has_cc, precision = ctx.cfg
         B, K1, N = x1.shape
         K2 = 0 if x2 is None else x2.shape[1]
         C, ldw = weight.shape
@@ -228,7 +234,7 @@ class _ConvBNAct(torch.autograd.Function):
         dx1 = torch.empty_like(x1) if ctx.needs_input_grad[0] else None
         dx2 = torch.empty_like(x2) if (x2 is not None and ctx.needs_input_grad[1]) else None
         if dx1 is not None or dx2 is not None:
-            _lib.call("dcnet_conv1x1_bwd_data", _p(dz), _p(weight), ldw, _p(dx1), K1, _p(dx2), K2, B, C, N, st)
+            _lib.call("dcnet_conv1x1_bwd_data", _p(dz), _p(weight), ldw, _p(dx1), K1, _p(dx2), K2, B, C, N, precision, st)
         dW = du = dcc = None
         need_w = ctx.needs_input_grad[2]
         if need_w:
@@ -239,20 +245,24 @@ class _ConvBNAct(torch.autograd.Function):
             dcc = torch.empty(C, N, device=dev, dtype=F32)
         if need_w or du is not None or dcc is not None:
             _lib.call("dcnet_conv1x1_bwd_weight", _p(dz), _p(x1) if need_w else None, K1, _p(x2) if need_w else None, K2,
-                      _p(dW), ldw, _p(du), _p(dcc), B, C, N, st)
-        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, None, None, None, None, None, None, None)
+                      _p(dW), ldw, _p(du), _p(dcc), B, C, N, precision, st)
+        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, None, None, None, None, None, None, None, None)
+
+
+EXACT_FP32, TENSOR_TF32 = 0, 1
 
 
 def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
-                momentum=0.999, eps=1e-5, slope=0.0, l2norm=False):
-    """x1 [B,K1,N] (+x2 [B,K2,N]); weight [C,ldw].  Returns y [B,C,N] or (y, sim, neg_sim) when fa [B,C] is given."""
+                momentum=0.999, eps=1e-5, slope=0.0, l2norm=False, precision=TENSOR_TF32):
+    """x1 [B,K1,N] (+x2 [B,K2,N]); weight [C,ldw].  Returns y [B,C,N] or (y, sim, neg_sim) when fa [B,C] is given.
+    precision: TENSOR_TF32 = tcgen05 GEMMs (<=1e-3 relative), EXACT_FP32 = CUDA-core fp32 (<=1e-5)."""
     return _ConvBNAct.apply(x1, x2, weight, gamma, beta, u, cc, fa, running_mean, running_var, bool(training), float(momentum),
-                            float(eps), float(slope), bool(l2norm))
+                            float(eps), float(slope), bool(l2norm), int(precision))
 
 
 class _CoAttn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, frames, qa, kb, oidx, n_out, tau):
+    def forward(ctx, frames, qa, kb, oidx, n_out, tau, precision):
         frames = _c(frames, name="frames")
         qa, kb, oidx = (_c(t, torch.int32, "index") for t in (qa, kb, oidx))
         F_, C, N = frames.shape
@@ -262,9 +272,11 @@ class _CoAttn(torch.autograd.Function):
         lse = torch.empty(nprob, N, device=frames.device, dtype=F32)
         nbytes = _lib.lib().dcnet_coattn_workspace_bytes(nprob, C, N)
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
-        _lib.call("dcnet_coattn_fwd", _p(frames), _p(qa), _p(kb), _p(oidx), nprob, _p(out), _p(lse), C, N, tau, _p(ws), nbytes, _st())
+        _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, precision,
+                  _p(ws), nbytes, _st())
         ctx.save_for_backward(frames, qa, kb, oidx, out, lse)
         ctx.tau = tau
+        ctx.precision = precision
         return out
 
     @staticmethod
@@ -276,18 +288,18 @@ class _CoAttn(torch.autograd.Function):
         dframes = torch.zeros_like(frames)
         nbytes = _lib.lib().dcnet_coattn_workspace_bytes(nprob, C, N)
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
-        _lib.call("dcnet_coattn_bwd", _p(frames), _p(qa), _p(kb), _p(oidx), nprob, _p(out), _p(lse), _p(dout), _p(dframes), C, N, ctx.tau,
-                  _p(ws), nbytes, _st())
-        return dframes, None, None, None, None, None
+        _lib.call("dcnet_coattn_bwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout), _p(dframes),
+                  C, N, ctx.tau, ctx.precision, _p(ws), nbytes, _st())
+        return dframes, None, None, None, None, None, None
 
 
-def coattention(frames, qa, kb, oidx=None, n_out=None, tau=10.0):
+def coattention(frames, qa, kb, oidx=None, n_out=None, tau=10.0, precision=1):
     """frames [F,C,N]; problem i: queries frame qa[i] attend to frame kb[i]; result row oidx[i] of out [n_out,C,N]."""
     if oidx is None:
         oidx = torch.arange(qa.numel(), device=qa.device, dtype=torch.int32)
     if n_out is None:
         n_out = qa.numel()
-    return _CoAttn.apply(frames, qa, kb, oidx, int(n_out), float(tau))
+    return _CoAttn.apply(frames, qa, kb, oidx, int(n_out), float(tau), int(precision))
 
 
 class _GatherCols(torch.autograd.Function):

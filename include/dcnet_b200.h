@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCNET_ABI_VERSION 1
+#define DCNET_ABI_VERSION 2
 #define DCNET_API __attribute__((visibility("default")))
 
 /* ---- library ---------------------------------------------------------------------------------------- */
@@ -55,14 +55,24 @@ DCNET_API int dcnet_sgemm(const float* A, const float* B, float* C, int M, int N
  *   W [C, ldw] row-major (ldw >= K1+K2); u [B,C] or NULL (text term W_l flang of the fusion, Appendix A.9);
  *   cc [C,N] or NULL (coordinate term W_c coord); z [B,C,N].                                              */
 DCNET_API int dcnet_conv1x1_fwd(const float* x1, int K1, const float* x2, int K2, const float* W, int ldw,
-                                const float* u, const float* cc, float* z, int B, int C, int N, void* stream);
+                                const float* u, const float* cc, float* z, int B, int C, int N,
+                                float* stat_sums, int precision, void* stream);
+/* precision (all three conv entry points): 0 = exact fp32 on the CUDA cores (used where indices depend on the result:
+ * the scale-0 visual mapping that feeds the top-30 / arg-max selections); 1 = TF32 tcgen05 tensor-core path (fp32 operands
+ * read as TF32 by the MMA, fp32 accumulation in TMEM).  Shapes TMA cannot address (N % 4 != 0) run at precision 0.
+ * stat_sums (optional, [2*C]): receives sum_z[C] and sum_z2[C] over (b,n) for dcnet_bn_finalize -- accumulated in the GEMM
+ * epilogue on the tensor-core path, so z is not re-read for the BatchNorm statistics.                                   */
 /* dx1 = W[:,0:K1]^T dz, dx2 = W[:,K1:]^T dz (either may be NULL) */
 DCNET_API int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, float* dx1, int K1, float* dx2, int K2,
-                                     int B, int C, int N, void* stream);
+                                     int B, int C, int N, int precision, void* stream);
 /* dW[:,0:K1] = sum_b dz[b] x1[b]^T, dW[:,K1:] = sum_b dz[b] x2[b]^T  (overwrites those columns of dW [C,ldw]);
  * du [B,C] = sum_n dz (or NULL); dcc [C,N] = sum_b dz (or NULL)                                           */
 DCNET_API int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1, const float* x2, int K2,
-                                       float* dW, int ldw, float* du, float* dcc, int B, int C, int N, void* stream);
+                                       float* dW, int ldw, float* du, float* dcc, int B, int C, int N, int precision, void* stream);
+
+/* mean/invstd (+ running statistics, momentum, unbiased variance) from the epilogue sums: count = B*N */
+DCNET_API int dcnet_bn_finalize(const float* stat_sums, long long count, int C, float eps, float momentum,
+                                float* mean, float* invstd, float* running_mean, float* running_var, void* stream);
 
 /* BatchNorm statistics of z [B,C,N] over (B,N): mean[C], invstd[C] = 1/sqrt(biased var + eps); when
  * running_mean/var are non-NULL they are updated in place with `momentum` and the UNBIASED variance
@@ -101,13 +111,13 @@ DCNET_API int dcnet_coord_map(float* coord, int h, int w, void* stream);
  * A training pair p is the two problems (2p,2p+1) and (2p+1,2p); the test-time clip path uses the centre
  * direction only.  S / P never leave the chip in the tcgen05 path; workspace is scratch for the rest.     */
 DCNET_API size_t dcnet_coattn_workspace_bytes(int nprob, int C, int N);
-DCNET_API int dcnet_coattn_fwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob,
-                               float* out, float* lse, int C, int N, float tau, void* workspace, size_t workspace_bytes,
-                               void* stream);
+DCNET_API int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                               float* out, int n_out, float* lse, int C, int N, float tau, int precision,
+                               void* workspace, size_t workspace_bytes, void* stream);
 /* dframes [F,C,N] += gradient (caller zeroes); dout/out indexed by oidx like the forward */
-DCNET_API int dcnet_coattn_bwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob,
-                               const float* out, const float* lse, const float* dout, float* dframes,
-                               int C, int N, float tau, void* workspace, size_t workspace_bytes, void* stream);
+DCNET_API int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                               const float* out, int n_out, const float* lse, const float* dout, float* dframes,
+                               int C, int N, float tau, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a4: inter-frame patch correspondence (model/DCNet_model.py:381-430) ------------------------------
  * fv0 [2P,C,N0].  S0[p] = F1^T F2 in exact fp32; idx[p, r] = flat index (row*N0+col) of the r-th largest

@@ -91,6 +91,7 @@ def _cbr_oracle(d, l2, training, dtype=torch.float64):
     return t, outs, (z, mean, var)
 
 
+@pytest.mark.parametrize("precision", [0, 1])
 @pytest.mark.parametrize("B,K1,K2,N,use_u,use_cc,use_fa,l2,training", [
     (4, 1024, 0, 64, False, False, False, True, True),      # mapping_visu scale 0
     (4, 256, 0, 1024, False, False, False, True, True),     # mapping_visu scale 2
@@ -98,20 +99,23 @@ def _cbr_oracle(d, l2, training, dtype=torch.float64):
     (4, 512, 0, 169, True, True, False, False, True),       # fusion: split-weight, odd N (416 scale 0)
     (2, 512, 512, 64, False, False, True, True, False),     # eval mode (running statistics)
 ])
-def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, training):
+def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, training, precision):
+    # precision 0: exact fp32 (CUDA cores), <= 1e-5.  precision 1: TF32 tcgen05 GEMMs with fp32 accumulation, <= 1e-3-class
+    # (BASELINE north_star: "<= 1e-3 relative for bf16-accumulated-in-fp32 GEMMs"; TF32 keeps 3 more mantissa bits than bf16).
+    tol_f, tol_b = (1e-5, 2e-5) if precision == 0 else (2e-3, 4e-3)
     d = _cbr_case(B, K1, K2, N, use_u, use_cc, use_fa, l2, training, seed=10 + N)
     t, outs_ref, (z_ref, mean_ref, var_ref) = _cbr_oracle(d, l2, training)
     c = {k: (v.to(DEV).requires_grad_(k not in ('rm', 'rv')) if v is not None else None) for k, v in d.items()}
     rm0, rv0 = c['rm'].clone(), c['rv'].clone()
     out = ops.conv_bn_act(c['x1'], c['w'], c['gamma'], c['beta'], c['rm'], c['rv'], training, x2=c['x2'], u=c['u'], cc=c['cc'], fa=c['fa'],
-                          l2norm=l2)
+                          l2norm=l2, precision=precision)
     outs = list(out) if isinstance(out, tuple) else [out]
     for o, r in zip(outs, outs_ref):
-        assert rel(o, r) < 1e-5
+        assert rel(o, r) < tol_f, rel(o, r)
     if training:   # running statistics: momentum 0.999, unbiased variance
         n = B * N
-        assert rel(c['rm'], 0.001 * rm0.cpu().double() + 0.999 * mean_ref) < 1e-5
-        assert rel(c['rv'], 0.001 * rv0.cpu().double() + 0.999 * var_ref * n / (n - 1)) < 1e-5
+        assert rel(c['rm'], 0.001 * rm0.cpu().double() + 0.999 * mean_ref) < max(tol_f, 1e-5) * 5
+        assert rel(c['rv'], 0.001 * rv0.cpu().double() + 0.999 * var_ref * n / (n - 1)) < max(tol_f, 1e-5) * 5
     g = gen(99)
     gouts = [torch.randn(o.shape, generator=g) for o in outs_ref]
     torch.autograd.backward(outs_ref, [x.double() for x in gouts])
@@ -124,14 +128,16 @@ def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, t
     K = K1 + K2
     for k in ('x1', 'x2', 'gamma', 'beta', 'u', 'cc', 'fa'):
         if d[k] is not None:
-            assert min(rel(c[k].grad, t[k].grad), rel(c[k].grad, t32[k].grad)) < 2e-5, k
-    assert min(rel(c['w'].grad[:, :K], t['w'].grad[:, :K]), rel(c['w'].grad[:, :K], t32['w'].grad[:, :K])) < 2e-5
+            assert min(rel(c[k].grad, t[k].grad), rel(c[k].grad, t32[k].grad)) < tol_b, (k, rel(c[k].grad, t[k].grad))
+    assert min(rel(c['w'].grad[:, :K], t['w'].grad[:, :K]), rel(c['w'].grad[:, :K], t32['w'].grad[:, :K])) < tol_b
     assert float(c['w'].grad[:, K:].abs().max()) == 0.0 if c['w'].shape[1] > K else True
 
 
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("P,N", [(2, 64), (2, 169), (1, 256)])
-def test_coattention_forward_backward(P, N):
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("P,N", [(2, 64), (2, 169), (1, 256), (1, 676)])
+def test_coattention_forward_backward(P, N, precision):
+    tol_f, tol_b = (1e-5, 2e-5) if precision == 0 else (2e-3, 4e-3)
     g = gen(20 + N)
     C = 512
     fr = torch.nn.functional.normalize(torch.randn(2 * P, C, N, generator=g).abs(), dim=1)
@@ -141,12 +147,14 @@ def test_coattention_forward_backward(P, N):
     ref = O.interleave_pairs(o1, o2)
     x = fr.to(DEV).requires_grad_(True)
     qa = torch.arange(2 * P, device=DEV, dtype=torch.int32)
-    out = ops.coattention(x, qa, qa ^ 1, tau=10.0)
-    assert rel(out, ref) < 1e-5
+    out = ops.coattention(x, qa, qa ^ 1, tau=10.0, precision=precision)
+    print("coattn N=%d precision=%d fwd rel err %.2e" % (N, precision, rel(out, ref)))
+    assert rel(out, ref) < tol_f, rel(out, ref)
     go = torch.randn(ref.shape, generator=g)
     ref.backward(go.double())
     out.backward(go.to(DEV))
-    assert rel(x.grad, ref_in.grad) < 2e-5
+    print("coattn N=%d precision=%d bwd rel err %.2e" % (N, precision, rel(x.grad, ref_in.grad)))
+    assert rel(x.grad, ref_in.grad) < tol_b, rel(x.grad, ref_in.grad)
 
 
 def test_coattention_clip_mode_centre_vs_others():
@@ -158,10 +166,12 @@ def test_coattention_clip_mode_centre_vs_others():
     others = [i for i in range(nf) if i != centre]
     qa = torch.full((len(others),), centre, device=DEV, dtype=torch.int32)
     kb = torch.tensor(others, device=DEV, dtype=torch.int32)
-    out = ops.coattention(fr.to(DEV), qa, kb, tau=10.0)
+    out = ops.coattention(fr.to(DEV), qa, kb, tau=10.0, precision=0)
+    out_tc = ops.coattention(fr.to(DEV), qa, kb, tau=10.0, precision=1)
     for i, o in enumerate(others):
         o1, _ = O.coattention(fr[centre:centre + 1].double(), fr[o:o + 1].double(), 10.0)
         assert rel(out[i], o1[0]) < 1e-5
+        assert rel(out_tc[i], o1[0]) < 2e-3
 
 
 # ------------------------------------------------------------------------------------------------------------------
