@@ -4,6 +4,7 @@
 // layouts documented in cute/atom/mma_traits_sm100.hpp:
 //   K-major : ((8,n),2):((8,SBO),1)   [uint128 units]  rows of 128 B, 8-row atoms SBO apart
 //   MN-major: ((8,n),(8,k)):((1,LBO),(8,SBO))          128 B along MN, MN blocks LBO apart, 8-k-row groups SBO apart
+//   MN-major, 32-bit elements (tf32): SWIZZLE_128B_BASE32B = Swizzle<2,5,2>, ((8,n),(4,k)):((1,LBO),(8,SBO)): 4-k-row groups
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -101,15 +102,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors
-// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor, version 1 (Blackwell).  layout_type: 2 = SWIZZLE_128B (16-byte swizzle atoms),
+// 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only layout UMMA accepts for MN-major 32-bit (tf32) operands,
+// cutlass/gemm/collective/builders/sm100_common.inl:92).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // version
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return smem_desc(saddr, lbo_bytes, sbo_bytes, 2);
 }
 enum : uint32_t { FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2 };
 // instruction descriptor: fp32 accumulate, dense, no negate
@@ -147,7 +153,7 @@ static inline dcnet_encode_tiled_fn dcnet_get_encode_tiled() {
 }
 
 static inline int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                                uint64_t stride2_elems, uint32_t b0, uint32_t b1) {
+                                uint64_t stride2_elems, uint32_t b0, uint32_t b1, bool atom32b = false) {
   dcnet_encode_tiled_fn enc = dcnet_get_encode_tiled();
   if (!enc) return -999;
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -155,7 +161,8 @@ static inline int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t d0, u
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (int)r;
 }

@@ -115,10 +115,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const uint32_t sB = sA + A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ks++) {     // one MMA = 8 tf32 along K = 32 bytes
-          // K-major : +32 B inside the 128-B swizzle row; rows 128 B apart, 8-row atoms 1024 B apart
-          // MN-major: +8 k-rows = +1024 B; MN blocks (32 elements) BLK_BYTES apart
-          const uint64_t ad = A_MN ? smem_desc_sw128(sA + ks * 1024, BLK_BYTES, 1024) : smem_desc_sw128(sA + ks * 32, 16, 1024);
-          const uint64_t bd = B_MN ? smem_desc_sw128(sB + ks * 1024, BLK_BYTES, 1024) : smem_desc_sw128(sB + ks * 32, 16, 1024);
+          // K-major : SWIZZLE_128B; +32 B inside the 128-B swizzle row; rows 128 B apart, 8-row atoms 1024 B apart
+          // MN-major: SWIZZLE_128B_BASE32B (tf32); +8 k-rows = +1024 B; 4-k-row groups 512 B apart (SBO); MN blocks of 32
+          //           elements BLK_BYTES apart (LBO)
+          const uint64_t ad = A_MN ? smem_desc(sA + ks * 1024, BLK_BYTES, 512, 1) : smem_desc(sA + ks * 32, 16, 1024, 2);
+          const uint64_t bd = B_MN ? smem_desc(sB + ks * 1024, BLK_BYTES, 512, 1) : smem_desc(sB + ks * 32, 16, 1024, 2);
           mma_tf32(tmem_base, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
         }
         mma_commit(&empty[s]);      // slot reusable once these MMAs have read it
@@ -203,7 +204,8 @@ static int make_operand_map(CUtensorMap* m, const UmmaOperand& o, int tile_rows_
   const uint64_t nb = o.batches > 0 ? (uint64_t)o.batches : 1;
   const uint64_t bs = o.batches > 0 ? (uint64_t)o.batch_stride : (uint64_t)(o.rows * o.ld);
   // box: K-major {32 k, tile rows}; MN-major {32 mn, 32 k rows}
-  const int r = make_tmap_f32(m, o.ptr, (uint64_t)o.cols, (uint64_t)o.rows, nb, (uint64_t)o.ld, bs, 32, o.mn_major ? 32u : (uint32_t)tile_rows_kmajor);
+  const int r = make_tmap_f32(m, o.ptr, (uint64_t)o.cols, (uint64_t)o.rows, nb, (uint64_t)o.ld, bs, 32, o.mn_major ? 32u : (uint32_t)tile_rows_kmajor,
+                              /*atom32b=*/o.mn_major);
   if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", r, o.rows, o.cols, o.ld);
   return 0;
 }
@@ -244,4 +246,19 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   DISPATCH(0, 0) DISPATCH(0, 1) DISPATCH(1, 0) DISPATCH(1, 1)
 #undef DISPATCH
   return dcnet_set_error(-1, "umma_gemm: unreachable");
+}
+
+
+// C ABI: direct access to the tensor-core GEMM (tests, and callers with their own contractions)
+extern "C" int dcnet_gemm_tf32(const float* A, int a_mn_major, long long lda, long long strideA,
+                               const float* B, int b_mn_major, long long ldb, long long strideB,
+                               float* C, long long ldc, long long strideC, int M, int N, int K, int batch, float alpha, int atomic,
+                               void* stream) {
+  DCNET_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tf32: bad arguments");
+  // K-major operand: [rows = M|N][cols = K]; MN-major operand: [rows = K][cols = M|N]
+  UmmaOperand a{A, a_mn_major ? K : M, a_mn_major ? M : K, lda, strideA, batch, a_mn_major != 0};
+  UmmaOperand b{B, b_mn_major ? K : N, b_mn_major ? N : K, ldb, strideB, batch, b_mn_major != 0};
+  UmmaEpilogue e{};
+  e.out = C; e.ldo = ldc; e.so_b = strideC; e.alpha = alpha; e.atomic = atomic;
+  return umma_gemm(a, b, nullptr, M, N, K, 0, 0, batch, e, as_stream(stream));
 }

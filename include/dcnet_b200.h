@@ -46,6 +46,16 @@ DCNET_API int dcnet_sgemm(const float* A, const float* B, float* C, int M, int N
                           float alpha, float beta, const float* colscale, long long sColscaleB,
                           int atomic, void* stream);
 
+/* ---- batched TF32 tensor-core GEMM (tcgen05.mma, TMA-fed, fp32 accumulation in TMEM) ----------------------------
+ * C[b] (M x N, row pitch ldc) (+)= alpha * A[b] (M x K) * B[b] (K x N).  Operand storage (fp32, innermost axis contiguous):
+ *   a_mn_major = 0: A[b] stored [M][K] (pitch lda)     a_mn_major = 1: stored [K][M]
+ *   b_mn_major = 0: B[b] stored [N][K] (pitch ldb)     b_mn_major = 1: stored [K][N]
+ * Requirements: 16-byte aligned bases, pitches and batch strides multiples of 4 floats.  atomic != 0: atomicAdd into C. */
+DCNET_API int dcnet_gemm_tf32(const float* A, int a_mn_major, long long lda, long long strideA,
+                              const float* B, int b_mn_major, long long ldb, long long strideB,
+                              float* C, long long ldc, long long strideC, int M, int N, int K, int batch, float alpha, int atomic,
+                              void* stream);
+
 /* ---- a1/a2/a6/a8: 1x1 conv (no bias) + BatchNorm + ReLU (+ L2 norm over channels) ---------------------
  * replaces ConvBatchNormReLU (model/darknet.py:118-156) as used by mapping_visu (:356-359), corr_conv
  * (:467-469) and fcn_emb[s][0] (:505), and F.normalize(dim=1).

@@ -53,6 +53,49 @@ def test_sgemm_kbatch_atomic_colscale():
     assert rel(out3, 2 * ref * cs.double()[None]) < 2e-6
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,batch", [(128, 128, 32, 1), (128, 64, 64, 2), (256, 384, 512, 2), (200, 676, 100, 1), (512, 1024, 1032, 1)])
+def test_gemm_tf32_all_operand_majors(a_mn, b_mn, M, N, K, batch):
+    """tcgen05 TF32 GEMM on random +/- data against fp64: any descriptor / swizzle mistake gives O(1) error; correct results
+    sit at the TF32 input-rounding level (~1e-3 of the product of operand norms)."""
+    g = gen(7 + M + N + K)
+    A = torch.randn(batch, M, K, generator=g)
+    B = torch.randn(batch, N, K, generator=g)
+    ref = torch.bmm(A.double(), B.double().transpose(1, 2))
+    Ad = (A.transpose(1, 2).contiguous() if a_mn else A).to(DEV)
+    Bd = (B.transpose(1, 2).contiguous() if b_mn else B).to(DEV)
+    if (Ad.shape[2] % 4) or (Bd.shape[2] % 4):
+        pytest.skip("row pitch not TMA-addressable")
+    C = ops.gemm_tf32(Ad, Bd, a_mn, b_mn, M, N, K)
+    e = rel(C, ref)
+    blk = ((C.double().cpu() - ref)[0].abs()[: (M // 32) * 32, : (N // 32) * 32].reshape(M // 32, 32, N // 32, 32).amax(dim=(1, 3)))
+    print("gemm_tf32 a_mn=%d b_mn=%d M=%d N=%d K=%d rel err %.2e; worst 32x32 blocks:" % (a_mn, b_mn, M, N, K, e), blk.flatten().topk(3).values.tolist())
+    assert e < 2e-3, e
+
+
+def test_conv_linear_backward_forms_tf32():
+    """The two backward contractions of the 1x1 conv are linear (no ReLU kink): TF32 must hold 1e-3-class accuracy."""
+    from dcnet_b200 import _lib
+    g = gen(11)
+    B, C, K1, K2, N = 3, 512, 256, 128, 676
+    dz = torch.randn(B, C, N, generator=g); W = torch.randn(C, K1 + K2 + 8, generator=g)
+    x1 = torch.randn(B, K1, N, generator=g); x2 = torch.randn(B, K2, N, generator=g)
+    d = [t.to(DEV) for t in (dz, W, x1, x2)]
+    dx1 = torch.empty(B, K1, N, device=DEV); dx2 = torch.empty(B, K2, N, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("dcnet_conv1x1_bwd_data", d[0].data_ptr(), d[1].data_ptr(), K1 + K2 + 8, dx1.data_ptr(), K1, dx2.data_ptr(), K2, B, C, N, 1, st)
+    assert rel(dx1, torch.einsum('ck,bcn->bkn', W[:, :K1].double(), dz.double())) < 2e-3
+    assert rel(dx2, torch.einsum('ck,bcn->bkn', W[:, K1:K1 + K2].double(), dz.double())) < 2e-3
+    dW = torch.full((C, K1 + K2 + 8), 7.0, device=DEV)
+    du = torch.empty(B, C, device=DEV); dcc = torch.empty(C, N, device=DEV)
+    _lib.call("dcnet_conv1x1_bwd_weight", d[0].data_ptr(), d[2].data_ptr(), K1, d[3].data_ptr(), K2, dW.data_ptr(), K1 + K2 + 8,
+              du.data_ptr(), dcc.data_ptr(), B, C, N, 1, st)
+    assert rel(dW[:, :K1], torch.einsum('bcn,bkn->ck', dz.double(), x1.double())) < 2e-3
+    assert rel(dW[:, K1:K1 + K2], torch.einsum('bcn,bkn->ck', dz.double(), x2.double())) < 2e-3
+    assert float((dW[:, K1 + K2:] - 7.0).abs().max()) == 0.0          # columns beyond K1+K2 untouched
+    assert rel(du, dz.double().sum(2)) < 1e-5 and rel(dcc, dz.double().sum(0)) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def _cbr_case(B, K1, K2, N, use_u, use_cc, use_fa, l2, training, seed):
     g = gen(seed)
@@ -126,10 +169,27 @@ def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, t
     t32, outs32, _ = _cbr_oracle(d, l2, training, torch.float32)
     torch.autograd.backward(outs32, gouts)
     K = K1 + K2
+    floor = {}
+    if precision == 1:
+        # Reduced-precision forward => ReLU masks differ from the fp64 ones for the fraction f ~ 1e-3 of pre-activations that
+        # lie within TF32 rounding of zero, and a gradient's norm-relative change is ~ sqrt(f) ~ 1-3e-2 whatever the
+        # implementation.  Bar: no worse than 2x PyTorch's own TF32 evaluation (cuBLAS, allow_tf32) of the same graph.
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            dg = {k: (v.to(DEV) if v is not None else None) for k, v in d.items()}
+            tg, outs_g, _ = _cbr_oracle(dg, l2, training, torch.float32)
+            torch.autograd.backward(outs_g, [x.to(DEV) for x in gouts])
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+        floor = {k: rel(tg[k].grad, t[k].grad) for k in ('x1', 'x2', 'gamma', 'beta', 'u', 'cc', 'fa', 'w') if d[k] is not None}
+        print("conv tf32 backward: torch-TF32 floor", {k: "%.1e" % v for k, v in floor.items()})
     for k in ('x1', 'x2', 'gamma', 'beta', 'u', 'cc', 'fa'):
         if d[k] is not None:
-            assert min(rel(c[k].grad, t[k].grad), rel(c[k].grad, t32[k].grad)) < tol_b, (k, rel(c[k].grad, t[k].grad))
-    assert min(rel(c['w'].grad[:, :K], t['w'].grad[:, :K]), rel(c['w'].grad[:, :K], t32['w'].grad[:, :K])) < tol_b
+            e = min(rel(c[k].grad, t[k].grad), rel(c[k].grad, t32[k].grad))
+            assert e < max(tol_b, 2 * floor.get(k, 0.0)), (k, e, floor.get(k))
+    e = min(rel(c['w'].grad[:, :K], t['w'].grad[:, :K]), rel(c['w'].grad[:, :K], t32['w'].grad[:, :K]))
+    assert e < max(tol_b, 2 * floor.get('w', 0.0)), ('w', e, floor.get('w'))
     assert float(c['w'].grad[:, K:].abs().max()) == 0.0 if c['w'].shape[1] > K else True
 
 
