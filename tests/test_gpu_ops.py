@@ -177,7 +177,7 @@ def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, t
         old = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = True
         try:
-            dg = {k: (v.to(DEV) if v is not None else None) for k, v in d.items()}
+            dg = {k: (v.detach().to(DEV) if v is not None else None) for k, v in d.items()}
             tg, outs_g, _ = _cbr_oracle(dg, l2, training, torch.float32)
             torch.autograd.backward(outs_g, [x.to(DEV) for x in gouts])
         finally:
