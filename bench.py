@@ -142,6 +142,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allreduce", action="store_true", help="N>1: skip the data-parallel gradient all-reduce of the hot-path parameters")
+    ap.add_argument("--xgpu-negatives", action="store_true",
+                    help="N>1: BASELINE config 5 -- rank-loss / pixel-to-text negatives from the global batch (NCCL all-gather of text vectors "
+                         "and target cells inside the step; the step then runs eagerly, NCCL is not captured)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
@@ -164,7 +167,10 @@ def main():
     pairs, size = wl["pairs"], wl["size"]
     B = 2 * pairs
     synth.seed_all(13)                       # identical replicas (DDP broadcast equivalent)
-    hp = HotPath(size).to(dev).train()
+    xneg = bool(args.xgpu_negatives and world > 1)
+    hp = HotPath(size, cross_gpu_negatives=xneg).to(dev).train()
+    if xneg:
+        args.no_graph = True
     random.seed(1000 + rank)
     g = torch.Generator().manual_seed(9000 + rank)
 
@@ -338,7 +344,7 @@ def main():
                     config=dict(workload=wl["name"], pairs_per_gpu=pairs, size=size, l2="flushed (256 MiB write) before every timed step",
                                 launch="CUDA graph replay" if graph is not None else "eager",
                                 sampling="exact reference random.sample stream (host C emulation)",
-                                grad_allreduce=bool(world > 1 and not args.no_allreduce)),
+                                grad_allreduce=bool(world > 1 and not args.no_allreduce), cross_gpu_negatives=xneg),
                     clocks=clocks,
                     e2e=dict(value=e2e_val, unit="frame-pairs/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                              ms_per_step=e2e_ms / args.steps, last_loss=loss_val),

@@ -135,7 +135,7 @@ template <int CPT>
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float slope, int l2norm,
-                                                         float* __restrict__ y, const float* __restrict__ fa,
+                                                         float* __restrict__ y, const float* __restrict__ fa, const float* __restrict__ fa_neg,
                                                          float* __restrict__ sim, float* __restrict__ neg_sim, int B, int N) {
   constexpr int C = CPT * 8;
   __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
     s_shift[c] = beta[c] - mean[c] * sc;
     if (fa) {
       s_fa[c] = fa[(long long)b * C + c];
-      s_fr[c] = fa[(long long)(B - 1 - b) * C + c];
+      s_fr[c] = fa_neg ? fa_neg[(long long)b * C + c] : fa[(long long)(B - 1 - b) * C + c];
     }
   }
   __syncthreads();
@@ -201,8 +201,8 @@ template <int CPT>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
     const float* __restrict__ beta, float slope, int l2norm, const float* __restrict__ dy, const float* __restrict__ fa,
-    const float* __restrict__ dsim, const float* __restrict__ dneg, float* __restrict__ dv, float* __restrict__ sum_dv,
-    float* __restrict__ sum_dvz, float* __restrict__ dfa, int B, int N) {
+    const float* __restrict__ fa_neg, const float* __restrict__ dsim, const float* __restrict__ dneg, float* __restrict__ dv,
+    float* __restrict__ sum_dv, float* __restrict__ sum_dvz, float* __restrict__ dfa, float* __restrict__ dfa_neg, int B, int N) {
   constexpr int C = CPT * 8;
   __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
   __shared__ float red[2][8][33];
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     s_shift[c] = beta[c] - mean[c] * sc;
     if (fa) {
       s_fa[c] = fa[(long long)b * C + c];
-      s_fr[c] = fa[(long long)(B - 1 - b) * C + c];
+      s_fr[c] = fa_neg ? fa_neg[(long long)b * C + c] : fa[(long long)(B - 1 - b) * C + c];
     }
   }
   __syncthreads();
@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
       const float f2 = warp_sum(dn * yh);
       if (lane == 0) {
         atomicAdd(dfa + (long long)b * C + c, f1);
-        atomicAdd(dfa + (long long)(B - 1 - b) * C + c, f2);
+        if (fa_neg) { if (dfa_neg) atomicAdd(dfa_neg + (long long)b * C + c, f2); }
+        else atomicAdd(dfa + (long long)(B - 1 - b) * C + c, f2);
       }
     }
   }
@@ -450,7 +451,7 @@ extern "C" int dcnet_bn_eval_stats(const float* running_mean, const float* runni
 }
 
 extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                float slope, int l2norm, float* y, const float* fa, float* sim, float* neg_sim,
+                                float slope, int l2norm, float* y, const float* fa, const float* fa_neg, float* sim, float* neg_sim,
                                 int B, int C, int N, void* stream) {
   DCNET_CHECK_ARG(z && mean && invstd && gamma && beta && y && B > 0 && N > 0, "bn_act_fwd: bad arguments");
   DCNET_CHECK_ARG(C == 512 || C == 256, "bn_act_fwd: C=%d unsupported (512 or 256)", C);
@@ -458,27 +459,27 @@ extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* 
   DCNET_CHECK_ARG(B <= 65535, "bn_act_fwd: B too large");
   dim3 grid(ceil_div(N, 32), B);
   if (C == 512)
-    bn_act_fwd_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, sim, neg_sim, B, N);
+    bn_act_fwd_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
   else
-    bn_act_fwd_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, sim, neg_sim, B, N);
+    bn_act_fwd_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
   DCNET_LAUNCH_OK("bn_act_fwd");
   return 0;
 }
 
 extern "C" int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                       float slope, int l2norm, const float* dy, const float* fa, const float* dsim,
-                                       const float* dneg_sim, float* dv, float* sum_dv, float* sum_dvz, float* dfa,
+                                       float slope, int l2norm, const float* dy, const float* fa, const float* fa_neg, const float* dsim,
+                                       const float* dneg_sim, float* dv, float* sum_dv, float* sum_dvz, float* dfa, float* dfa_neg,
                                        int B, int C, int N, void* stream) {
   DCNET_CHECK_ARG(z && mean && invstd && gamma && beta && dv && sum_dv && sum_dvz && B > 0 && N > 0, "bn_act_bwd_reduce: bad arguments");
   DCNET_CHECK_ARG(dy || fa, "bn_act_bwd_reduce: no incoming gradient");
   DCNET_CHECK_ARG(C == 512 || C == 256, "bn_act_bwd_reduce: C=%d unsupported (512 or 256)", C);
   dim3 grid(ceil_div(N, 32), B);
   if (C == 512)
-    bn_act_bwd_reduce_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, dsim,
-                                                                         dneg_sim, dv, sum_dv, sum_dvz, dfa, B, N);
+    bn_act_bwd_reduce_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, fa_neg, dsim,
+                                                                         dneg_sim, dv, sum_dv, sum_dvz, dfa, dfa_neg, B, N);
   else
-    bn_act_bwd_reduce_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, dsim,
-                                                                         dneg_sim, dv, sum_dv, sum_dvz, dfa, B, N);
+    bn_act_bwd_reduce_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, fa_neg, dsim,
+                                                                         dneg_sim, dv, sum_dv, sum_dvz, dfa, dfa_neg, B, N);
   DCNET_LAUNCH_OK("bn_act_bwd_reduce");
   return 0;
 }

@@ -126,6 +126,7 @@ __global__ void modulate_bwd_kernel(const float* __restrict__ raw, const float* 
 struct LossIn {
   Ptr3 pred, sim, neg, loc;
   const long long* best_n; const long long* gi; const long long* gj; const float* t5;
+  const long long* partner3;   // [3,B] best_n|gi|gj of the rank-loss partner, or NULL = local sample B-1-b
   int B, g0;
   float w_coord, margin;
 };
@@ -184,8 +185,11 @@ __global__ void __launch_bounds__(256) ground_loss_fwd_kernel(LossIn a, float* _
   const float conf = lc - p[4LL * N];
   // rank loss (train_DCNet.py:173-203): partner sample B-1-b supplies the second negative
   const int rb = a.B - 1 - b;
-  const int s2 = (int)(a.best_n[rb] / 3), g2 = a.g0 << s2, N2 = g2 * g2;
-  const int cell2 = (int)(a.gj[rb] * g2 + a.gi[rb]);
+  const long long pbn = a.partner3 ? a.partner3[b] : a.best_n[rb];
+  const long long pgi = a.partner3 ? a.partner3[a.B + b] : a.gi[rb];
+  const long long pgj = a.partner3 ? a.partner3[2 * a.B + b] : a.gj[rb];
+  const int s2 = (int)(pbn / 3), g2 = a.g0 << s2, N2 = g2 * g2;
+  const int cell2 = (int)(pgj * g2 + pgi);
   const float pos = a.sim.p[s][(long long)b * N + cell];
   const float n1 = a.neg.p[s][(long long)b * N + cell];
   const float n2 = a.sim.p[s2][(long long)b * N2 + cell2];
@@ -237,8 +241,11 @@ __global__ void __launch_bounds__(256) ground_loss_bwd_kernel(LossIn a, const fl
   dp[4LL * N] -= g_y;
   dloc.p[s][(long long)b * N + cell] -= g_l;
   const int rb = a.B - 1 - b;
-  const int s2 = (int)(a.best_n[rb] / 3), g2 = a.g0 << s2, N2 = g2 * g2;
-  const int cell2 = (int)(a.gj[rb] * g2 + a.gi[rb]);
+  const long long pbn = a.partner3 ? a.partner3[b] : a.best_n[rb];
+  const long long pgi = a.partner3 ? a.partner3[a.B + b] : a.gi[rb];
+  const long long pgj = a.partner3 ? a.partner3[2 * a.B + b] : a.gj[rb];
+  const int s2 = (int)(pbn / 3), g2 = a.g0 << s2, N2 = g2 * g2;
+  const int cell2 = (int)(pgj * g2 + pgi);
   const float pos = a.sim.p[s][(long long)b * N + cell];
   const float n1 = a.neg.p[s][(long long)b * N + cell];
   const float n2 = a.sim.p[s2][(long long)b * N2 + cell2];
@@ -466,12 +473,13 @@ extern "C" int dcnet_ground_loss_fwd(const float* pred0, const float* pred1, con
                                      const float* neg0, const float* neg1, const float* neg2,
                                      const float* loc0, const float* loc1, const float* loc2,
                                      const long long* best_n, const long long* gi, const long long* gj, const float* t5,
+                                     const long long* partner3,
                                      int B, int g0, float w_coord, float margin, float* losses, float* lse_conf, float* lse_loc,
                                      void* stream) {
   DCNET_CHECK_ARG(pred0 && pred1 && pred2 && sim0 && sim1 && sim2 && neg0 && neg1 && neg2 && loc0 && loc1 && loc2, "ground_loss_fwd: null input");
   DCNET_CHECK_ARG(best_n && gi && gj && t5 && losses && lse_conf && lse_loc && B > 0 && g0 > 0, "ground_loss_fwd: bad arguments");
   cudaStream_t st = as_stream(stream);
-  LossIn a{{{pred0, pred1, pred2}}, {{sim0, sim1, sim2}}, {{neg0, neg1, neg2}}, {{loc0, loc1, loc2}}, best_n, gi, gj, t5, B, g0, w_coord, margin};
+  LossIn a{{{pred0, pred1, pred2}}, {{sim0, sim1, sim2}}, {{neg0, neg1, neg2}}, {{loc0, loc1, loc2}}, best_n, gi, gj, t5, partner3, B, g0, w_coord, margin};
   DCNET_CUDA(cudaMemsetAsync(losses, 0, 3 * sizeof(float), st), "ground_loss_fwd.memset");
   ground_loss_fwd_kernel<<<B, 256, 0, st>>>(a, losses, lse_conf, lse_loc);
   DCNET_LAUNCH_OK("ground_loss_fwd");
@@ -483,6 +491,7 @@ extern "C" int dcnet_ground_loss_bwd(const float* pred0, const float* pred1, con
                                      const float* neg0, const float* neg1, const float* neg2,
                                      const float* loc0, const float* loc1, const float* loc2,
                                      const long long* best_n, const long long* gi, const long long* gj, const float* t5,
+                                     const long long* partner3,
                                      int B, int g0, float w_coord, float margin, const float* lse_conf, const float* lse_loc,
                                      const float* gl,
                                      float* dpred0, float* dpred1, float* dpred2, float* dsim0, float* dsim1, float* dsim2,
@@ -491,7 +500,7 @@ extern "C" int dcnet_ground_loss_bwd(const float* pred0, const float* pred1, con
   DCNET_CHECK_ARG(pred0 && pred1 && pred2 && sim0 && sim1 && sim2 && neg0 && neg1 && neg2 && loc0 && loc1 && loc2, "ground_loss_bwd: null input");
   DCNET_CHECK_ARG(best_n && gi && gj && t5 && lse_conf && lse_loc && gl && B > 0 && g0 > 0, "ground_loss_bwd: bad arguments");
   DCNET_CHECK_ARG(dpred0 && dpred1 && dpred2 && dsim0 && dsim1 && dsim2 && dneg0 && dneg1 && dneg2 && dloc0 && dloc1 && dloc2, "ground_loss_bwd: null output");
-  LossIn a{{{pred0, pred1, pred2}}, {{sim0, sim1, sim2}}, {{neg0, neg1, neg2}}, {{loc0, loc1, loc2}}, best_n, gi, gj, t5, B, g0, w_coord, margin};
+  LossIn a{{{pred0, pred1, pred2}}, {{sim0, sim1, sim2}}, {{neg0, neg1, neg2}}, {{loc0, loc1, loc2}}, best_n, gi, gj, t5, partner3, B, g0, w_coord, margin};
   ground_loss_bwd_kernel<<<B, 256, 0, as_stream(stream)>>>(a, lse_conf, lse_loc, gl, MPtr3{{dpred0, dpred1, dpred2}}, MPtr3{{dsim0, dsim1, dsim2}},
                                                              MPtr3{{dneg0, dneg1, dneg2}}, MPtr3{{dloc0, dloc1, dloc2}});
   DCNET_LAUNCH_OK("ground_loss_bwd");

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import losses as LS
-from . import ops
+from . import ops, parallel
 from .model.DCNet_model import CROSS_NEG_N, NEG_N, TOP_K, grounding_model
 
 
@@ -26,9 +26,12 @@ class _NoBackbone(nn.Module):
 
 
 class HotPath(nn.Module):
-    def __init__(self, size=256, vocab=1000, seed_like_reference=True):
+    def __init__(self, size=256, vocab=1000, cross_gpu_negatives=False):
         super().__init__()
         self.size = size
+        # BASELINE config 5: rank-loss / pixel-to-text negatives taken from the GLOBAL batch (partner Bg-1-g) through an
+        # all-gather of the text vectors and target cells (dcnet_b200/parallel.py); off = the reference's local reversal
+        self.cross_gpu_negatives = cross_gpu_negatives
         # the mirror model supplies the hot-path parameters (same names/shapes/init as the reference)
         self.net = grounding_model(corpus=list(range(vocab)), emb_size=512, visumodel=_NoBackbone(), size=size)
         self.grids = [size // 32, size // 16, size // 8]
@@ -47,13 +50,18 @@ class HotPath(nn.Module):
         hw = [(m.shape[2], m.shape[3]) for m in raw]
         fv = net.map_visual(raw)
         q_if, k_if, neg_if, idx_if, _ = net.interframe(fv[0], negpos)
-        corr, sim, neg_sim = net.correspondence(fv, fa)
+        best_n, gi, gj, t5, _, _ = ops.build_target(bbox, self.size, LS.args.anchor_imsize, LS.anchors_full)
+        fa_neg = partner3 = None
+        if self.cross_gpu_negatives:
+            fa_neg, partner3 = parallel.global_partners(fa, best_n, gi, gj)
+        corr, sim, neg_sim = net.correspondence(fv, fa, fa_neg)
         coords = [ops.coord_map(h, w, fa.device).flatten(1) for (h, w) in hw]
         y = net.fuse(corr, flang, coords)
         oo_obj = [ops.only_obj(head[s], sim[s]) for s in range(3)]
         pred = [ops.modulate_conf(head[s], sim[s], loc[s]) for s in range(3)]
         q_cm, k_cm, neg_cm, word, _ = net.crossmodal(fv[0], context, negidx)
-        loss, comp, cell = LS.fused_losses(pred, sim, neg_sim, loc, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm)
+        loss, comp, cell = LS.fused_losses(pred, sim, neg_sim, loc, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm,
+                                           target=(best_n, gi, gj, t5), partner3=partner3)
         boxes, iou, _, _, _ = LS.decode_boxes(pred, bbox, cell[:3])
         return dict(loss=loss, comp=comp, y=y, iou=iou, boxes=boxes, cell=cell, corr=corr, sim=sim, pred=pred,
                     obj=[o[1] for o in oo_obj], idx_if=idx_if, word=word)

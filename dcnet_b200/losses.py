@@ -150,11 +150,14 @@ def negative_sim_score(flang_attn, corr_feat):
     return [(fa * c[:, :512]).sum(1) for c in corr_feat]
 
 
-def fused_losses(pred_anchor, sim_score, neg_sim_score, loc_score, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm):
+def fused_losses(pred_anchor, sim_score, neg_sim_score, loc_score, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm, target=None, partner3=None):
     """train_DCNet.py:615-642 in one pass: targets + the three grounding losses from one kernel + the two InfoNCE losses.
     Returns (loss, dict of the five components, (best_n, gi, gj, t5))."""
-    best_n, gi, gj, t5, _, _ = ops.build_target(bbox, args.size, args.anchor_imsize, anchors_full, dense=False)
-    g = ops.ground_losses(pred_anchor, sim_score, neg_sim_score, loc_score, best_n, gi, gj, t5)
+    if target is None:
+        best_n, gi, gj, t5, _, _ = ops.build_target(bbox, args.size, args.anchor_imsize, anchors_full, dense=False)
+    else:
+        best_n, gi, gj, t5 = target
+    g = ops.ground_losses(pred_anchor, sim_score, neg_sim_score, loc_score, best_n, gi, gj, t5, partner3=partner3)
     l_if = Interframe_contrastive_loss(q_if, k_if, neg_if)
     l_cm = Crossmodal_constrastive_loss(q_cm, k_cm, neg_cm)
     loss = g[0] + 100 * g[1] + g[2] + 100 * l_if + l_cm

@@ -180,7 +180,7 @@ class grounding_model(nn.Module):
         neg = g[:, 2 * TOP_K:].reshape(P, TOP_K, NEG_N, C).transpose(0, 1)
         return q, k, neg, idx, negidx
 
-    def correspondence(self, fv, fa):
+    def correspondence(self, fv, fa, fa_neg=None):
         """a5 + a6 + a9 (:449-469, :525-535): co-attention both directions, corr_conv on [fvisu | attention] without a
         cat, channel L2 norm, and the pixel-to-text dots fused into the same pass."""
         B = fv[0].shape[0]
@@ -188,7 +188,7 @@ class grounding_model(nn.Module):
         corr, sim, neg_sim = [], [], []
         for s in range(3):
             attn = ops.coattention(fv[s], qa, kb, tau=self.temperature, precision=self.precision)
-            y, sm, ng = self.corr_conv._modules[str(s)][0].fused(fv[s], x2=attn, fa=fa, l2norm=True, precision=self.precision)
+            y, sm, ng = self.corr_conv._modules[str(s)][0].fused(fv[s], x2=attn, fa=fa, l2norm=True, precision=self.precision, fa_neg=fa_neg)
             corr.append(y); sim.append(sm); neg_sim.append(ng)
         return corr, sim, neg_sim
 

@@ -22,13 +22,13 @@ class ConvBatchNormReLU(nn.Sequential):
         elif relu:
             self.add_module("relu", nn.ReLU())
 
-    def fused(self, x1, x2=None, u=None, cc=None, fa=None, l2norm=False, precision=ops.TENSOR_TF32):
+    def fused(self, x1, x2=None, u=None, cc=None, fa=None, l2norm=False, precision=ops.TENSOR_TF32, fa_neg=None):
         """x1 [B,K1,N] (+ x2 [B,K2,N]) through the sm_100a kernels; the weight columns beyond K1+K2 (split-weight fusion)
         are applied by the caller through u / cc."""
         w = self.conv.weight.view(self.conv.weight.shape[0], -1)
         bn = self.bn
         return ops.conv_bn_act(x1, w, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.training, x2=x2, u=u, cc=cc, fa=fa,
-                               momentum=bn.momentum, eps=bn.eps, slope=self.slope, l2norm=l2norm, precision=precision)
+                               momentum=bn.momentum, eps=bn.eps, slope=self.slope, l2norm=l2norm, precision=precision, fa_neg=fa_neg)
 
 
 class YOLOLayer(nn.Module):

@@ -183,11 +183,11 @@ class _ConvBNAct(torch.autograd.Function):
     """a1/a2/a6/a8: y = [l2norm_c] act(BN(W[:, :K1] x1 + W[:, K1:K1+K2] x2 + u 1^T + cc)), plus the fused a9 dots."""
 
     @staticmethod
-    def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, running_mean, running_var, training, momentum, eps, slope, l2norm, precision):
+    def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope, l2norm, precision):
         x1 = _c(x1, name="x1")
         x2 = _c(x2, name="x2")
         weight = _c(weight, name="weight")
-        u, cc, fa = _c(u, name="u"), _c(cc, name="cc"), _c(fa, name="fa")
+        u, cc, fa, fa_neg = _c(u, name="u"), _c(cc, name="cc"), _c(fa, name="fa"), _c(fa_neg, name="fa_neg")
         gamma, beta = _c(gamma, name="gamma"), _c(beta, name="beta")
         B, K1, N = x1.shape
         K2 = 0 if x2 is None else x2.shape[1]
@@ -213,9 +213,9 @@ class _ConvBNAct(torch.autograd.Function):
         if fa is not None:
             sim = torch.empty(B, N, device=dev, dtype=F32)
             neg = torch.empty(B, N, device=dev, dtype=F32)
-        _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm), _p(y), _p(fa), _p(sim), _p(neg),
+        _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm), _p(y), _p(fa), _p(fa_neg), _p(sim), _p(neg),
                   B, C, N, st)
-        ctx.save_for_backward(x1, x2, weight, gamma, beta, fa, z, mean, invstd)
+        ctx.save_for_backward(x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd)
         ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None, precision)
         if fa is None:
             return y
@@ -223,7 +223,7 @@ class _ConvBNAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, dsim=None, dneg=None):
-        x1, x2, weight, gamma, beta, fa, z, mean, invstd = ctx.saved_tensors
+        x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd = ctx.saved_tensors
         training, slope, l2norm, has_u, has_cc, precision = ctx.cfg
         B, K1, N = x1.shape
         K2 = 0 if x2 is None else x2.shape[1]
@@ -236,8 +236,9 @@ class _ConvBNAct(torch.autograd.Function):
         dv = torch.empty_like(z)
         sums = torch.zeros(2, C, device=dev, dtype=F32)
         dfa = torch.zeros(B, C, device=dev, dtype=F32) if (fa is not None and ctx.needs_input_grad[7]) else None
-        _lib.call("dcnet_bn_act_bwd_reduce", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, l2norm, _p(dy), _p(fa), _p(dsim),
-                  _p(dneg), _p(dv), _p(sums[0]), _p(sums[1]), _p(dfa), B, C, N, st)
+        dfa_neg = torch.zeros(B, C, device=dev, dtype=F32) if (fa_neg is not None and ctx.needs_input_grad[8]) else None
+        _lib.call("dcnet_bn_act_bwd_reduce", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, l2norm, _p(dy), _p(fa), _p(fa_neg),
+                  _p(dsim), _p(dneg), _p(dv), _p(sums[0]), _p(sums[1]), _p(dfa), _p(dfa_neg), B, C, N, st)
         _lib.call("dcnet_bn_act_bwd_apply", _p(z), _p(mean), _p(invstd), _p(gamma), _p(dv), _p(sums[0]), _p(sums[1]), int(training), _p(dv),
                   B, C, N, st)
         dz = dv
@@ -256,17 +257,17 @@ class _ConvBNAct(torch.autograd.Function):
         if need_w or du is not None or dcc is not None:
             _lib.call("dcnet_conv1x1_bwd_weight", _p(dz), _p(x1) if need_w else None, K1, _p(x2) if need_w else None, K2,
                       _p(dW), ldw, _p(du), _p(dcc), B, C, N, precision, st)
-        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, None, None, None, None, None, None, None, None)
+        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None)
 
 
 EXACT_FP32, TENSOR_TF32 = 0, 1
 
 
 def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
-                momentum=0.999, eps=1e-5, slope=0.0, l2norm=False, precision=TENSOR_TF32):
+                momentum=0.999, eps=1e-5, slope=0.0, l2norm=False, precision=TENSOR_TF32, fa_neg=None):
     """x1 [B,K1,N] (+x2 [B,K2,N]); weight [C,ldw].  Returns y [B,C,N] or (y, sim, neg_sim) when fa [B,C] is given.
     precision: TENSOR_TF32 = tcgen05 GEMMs (<=1e-3 relative), EXACT_FP32 = CUDA-core fp32 (<=1e-5)."""
-    return _ConvBNAct.apply(x1, x2, weight, gamma, beta, u, cc, fa, running_mean, running_var, bool(training), float(momentum),
+    return _ConvBNAct.apply(x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, bool(training), float(momentum),
                             float(eps), float(slope), bool(l2norm), int(precision))
 
 
@@ -476,16 +477,17 @@ def modulate_conf(raw, sim, loc):
 
 class _GroundLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, best_n, gi, gj, t5, w_coord, margin, *maps):
+    def forward(ctx, best_n, gi, gj, t5, partner3, w_coord, margin, *maps):
         maps = [_c(m, name="map") for m in maps]   # pred0..2, sim0..2, neg0..2, loc0..2
         B = maps[0].shape[0]
         g0 = int(round(maps[3].shape[1] ** 0.5))
         dev = maps[0].device
         losses = torch.empty(3, device=dev, dtype=F32)
         lse = torch.empty(2, B, device=dev, dtype=F32)
-        _lib.call("dcnet_ground_loss_fwd", *[_p(m) for m in maps], _p(best_n), _p(gi), _p(gj), _p(t5), B, g0, w_coord, margin,
+        _lib.call("dcnet_ground_loss_fwd", *[_p(m) for m in maps], _p(best_n), _p(gi), _p(gj), _p(t5), _p(partner3), B, g0, w_coord, margin,
                   _p(losses), _p(lse[0]), _p(lse[1]), _st())
         ctx.save_for_backward(best_n, gi, gj, t5, lse, *maps)
+        ctx.partner3 = partner3
         ctx.cfg = (B, g0, w_coord, margin)
         return losses
 
@@ -496,16 +498,17 @@ class _GroundLoss(torch.autograd.Function):
         B, g0, w_coord, margin = ctx.cfg
         gl = _c(gl, name="grad")
         grads = [torch.empty_like(m) for m in maps]
-        _lib.call("dcnet_ground_loss_bwd", *[_p(m) for m in maps], _p(best_n), _p(gi), _p(gj), _p(t5), B, g0, w_coord, margin,
+        _lib.call("dcnet_ground_loss_bwd", *[_p(m) for m in maps], _p(best_n), _p(gi), _p(gj), _p(t5), _p(ctx.partner3), B, g0, w_coord, margin,
                   _p(lse[0]), _p(lse[1]), _p(gl), *[_p(g) for g in grads], _st())
-        return (None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, *grads)
 
 
-def ground_losses(pred, sim, neg_sim, loc, best_n, gi, gj, t5, w_coord=5.0, margin=0.1):
-    """pred 3 x [B,15,N_s]; sim/neg_sim/loc 3 x [B,N_s] -> tensor [yolo_loss, rank_loss, loc_loss] (train_DCNet.py:45-72,173-220)."""
+def ground_losses(pred, sim, neg_sim, loc, best_n, gi, gj, t5, w_coord=5.0, margin=0.1, partner3=None):
+    """pred 3 x [B,15,N_s]; sim/neg_sim/loc 3 x [B,N_s] -> tensor [yolo_loss, rank_loss, loc_loss] (train_DCNet.py:45-72,173-220).
+    partner3 [3,B] int64 (best_n|gi|gj of each sample's rank-loss partner) overrides the local partner B-1-b (cross-GPU negatives)."""
     flat = [p.reshape(p.shape[0], 15, -1) for p in pred] + [s.reshape(s.shape[0], -1) for s in sim] + \
            [s.reshape(s.shape[0], -1) for s in neg_sim] + [s.reshape(s.shape[0], -1) for s in loc]
-    return _GroundLoss.apply(best_n, gi, gj, t5, float(w_coord), float(margin), *flat)
+    return _GroundLoss.apply(best_n, gi, gj, t5, _c(partner3, torch.long, 'partner3'), float(w_coord), float(margin), *flat)
 
 
 class _IoULoss(torch.autograd.Function):

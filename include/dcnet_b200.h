@@ -96,8 +96,10 @@ DCNET_API int dcnet_bn_eval_stats(const float* running_mean, const float* runnin
  * If fa != NULL (text vectors [B,C], a9): sim[b,n] = <fa[b], y[b,:,n]>, neg_sim[b,n] = <fa[B-1-b], y[b,:,n]>
  * (model/DCNet_model.py:530-535, train_DCNet.py:623-627), fused so corr_feat is read once.               */
 DCNET_API int dcnet_bn_act_fwd(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                               float slope, int l2norm, float* y, const float* fa, float* sim, float* neg_sim,
+                               float slope, int l2norm, float* y, const float* fa, const float* fa_neg, float* sim, float* neg_sim,
                                int B, int C, int N, void* stream);
+/* fa_neg (optional, [B,C]): explicit text vector of each image's negative partner (cross-GPU negatives: the partner of global
+ * sample g is Bg-1-g and may live on another rank); NULL = the reference's local batch reversal fa[B-1-b].                 */
 /* Backward of bn_act_fwd in train mode (batch statistics).  Two launches:
  *   reduce: dv = d(pre-activation) from dy (+ dsim/dneg_sim), written to `dv` [B,C,N]; accumulates
  *           sum_dv[C], sum_dvz[C] (caller zeroes), dfa [B,C] (caller zeroes, may be NULL);
@@ -105,8 +107,8 @@ DCNET_API int dcnet_bn_act_fwd(const float* z, const float* mean, const float* i
  *           dgamma = sum_dvz, dbeta = sum_dv.
  * train == 0 (running statistics): dz = gamma invstd dv.                                                  */
 DCNET_API int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                      float slope, int l2norm, const float* dy, const float* fa, const float* dsim,
-                                      const float* dneg_sim, float* dv, float* sum_dv, float* sum_dvz, float* dfa,
+                                      float slope, int l2norm, const float* dy, const float* fa, const float* fa_neg, const float* dsim,
+                                      const float* dneg_sim, float* dv, float* sum_dv, float* sum_dvz, float* dfa, float* dfa_neg,
                                       int B, int C, int N, void* stream);
 DCNET_API int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const float* invstd, const float* gamma,
                                      const float* dv, const float* sum_dv, const float* sum_dvz, int train,
@@ -190,13 +192,16 @@ DCNET_API int dcnet_ground_loss_fwd(const float* pred0, const float* pred1, cons
                                     const float* neg0, const float* neg1, const float* neg2,
                                     const float* loc0, const float* loc1, const float* loc2,
                                     const long long* best_n, const long long* gi, const long long* gj, const float* t5,
+                                    const long long* partner3,
                                     int B, int g0, float w_coord, float margin, float* losses, float* lse_conf, float* lse_loc,
                                     void* stream);
+/* partner3 (optional, [3,B] = best_n | gi | gj of each sample's rank-loss partner); NULL = local partner B-1-b (:195-196) */
 DCNET_API int dcnet_ground_loss_bwd(const float* pred0, const float* pred1, const float* pred2,
                                     const float* sim0, const float* sim1, const float* sim2,
                                     const float* neg0, const float* neg1, const float* neg2,
                                     const float* loc0, const float* loc1, const float* loc2,
                                     const long long* best_n, const long long* gi, const long long* gj, const float* t5,
+                                    const long long* partner3,
                                     int B, int g0, float w_coord, float margin, const float* lse_conf, const float* lse_loc,
                                     const float* gl,
                                     float* dpred0, float* dpred1, float* dpred2, float* dsim0, float* dsim1, float* dsim2,

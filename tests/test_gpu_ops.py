@@ -458,3 +458,36 @@ def test_empty_inputs_are_noops():
     assert ops.gather_cols(torch.zeros(2, 512, 4, device=DEV), torch.empty(0, device=DEV, dtype=torch.int32),
                            torch.empty(0, device=DEV, dtype=torch.long)).shape == (0, 512)
     assert ops.infonce_rows(torch.empty(0, 512, device=DEV), torch.empty(0, 512, device=DEV), torch.empty(0, 5, 512, device=DEV)).shape == (0,)
+
+
+def test_explicit_negative_partners_equal_local_reversal():
+    """fa_neg / partner3 (cross-GPU negatives) given the local reversal must reproduce the implicit B-1-b path bit for bit,
+    forward and backward -- the multi-rank semantics on top are covered by tests/test_parallel_gloo.py."""
+    g = gen(777)
+    B, C, N, size = 4, 512, 64, 256
+    d = _cbr_case(B, 512, 512, N, False, False, True, True, True, seed=5)
+    outs = []
+    for explicit in (False, True):
+        c = {k: (v.to(DEV).requires_grad_(k not in ('rm', 'rv')) if v is not None else None) for k, v in d.items()}
+        fa_neg = c['fa'].detach().flip(0).clone().requires_grad_(True) if explicit else None
+        y, sim, neg = ops.conv_bn_act(c['x1'], c['w'], c['gamma'], c['beta'], c['rm'], c['rv'], True, x2=c['x2'], fa=c['fa'], l2norm=True,
+                                      precision=0, fa_neg=fa_neg)
+        (sim.sum() + 2 * neg.sum() + y.mean()).backward()
+        dfa = c['fa'].grad.clone()
+        if explicit:
+            dfa = dfa + fa_neg.grad.flip(0)
+        outs.append((sim.detach(), neg.detach(), dfa, c['x1'].grad.clone()))
+    for a, b in zip(*outs):
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+    # rank loss with explicit partner cells
+    gs = [8, 16, 32]
+    bbox = synth.make_boxes(B // 2, size, g)
+    pred = [torch.randn(B, 15, x * x, generator=g).to(DEV) for x in gs]
+    sim = [torch.rand(B, x * x, generator=g).to(DEV).requires_grad_(True) for x in gs]
+    neg = [torch.rand(B, x * x, generator=g).to(DEV) for x in gs]
+    loc = [torch.rand(B, x * x, generator=g).to(DEV) for x in gs]
+    bn, gi, gj, t5, _, _ = ops.build_target(bbox.to(DEV), size, 416, O.ANCHORS_FULL)
+    l0 = ops.ground_losses(pred, sim, neg, loc, bn, gi, gj, t5)
+    p3 = torch.stack([bn, gi, gj]).flip(1).contiguous()
+    l1 = ops.ground_losses(pred, sim, neg, loc, bn, gi, gj, t5, partner3=p3)
+    torch.testing.assert_close(l0, l1, rtol=0, atol=0)
