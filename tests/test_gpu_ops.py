@@ -477,8 +477,8 @@ def test_explicit_negative_partners_equal_local_reversal():
         if explicit:
             dfa = dfa + fa_neg.grad.flip(0)
         outs.append((sim.detach(), neg.detach(), dfa, c['x1'].grad.clone()))
-    for a, b in zip(*outs):
-        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+    for a, b in zip(*outs):        # fp32 atomics: summation order differs between the two paths
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
     # rank loss with explicit partner cells
     gs = [8, 16, 32]
     bbox = synth.make_boxes(B // 2, size, g)
@@ -490,4 +490,4 @@ def test_explicit_negative_partners_equal_local_reversal():
     l0 = ops.ground_losses(pred, sim, neg, loc, bn, gi, gj, t5)
     p3 = torch.stack([bn, gi, gj]).flip(1).contiguous()
     l1 = ops.ground_losses(pred, sim, neg, loc, bn, gi, gj, t5, partner3=p3)
-    torch.testing.assert_close(l0, l1, rtol=0, atol=0)
+    torch.testing.assert_close(l0, l1, rtol=1e-6, atol=1e-7)
