@@ -196,6 +196,30 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
   }
 }
 
+// Sum over the 32 lanes of a warp of a per-lane vector v[0..CPT): recursive halving -- at every step a lane keeps one half of
+// its current values and hands the other half to its partner, so the whole reduction costs CPT-2 shuffles instead of 5*CPT.
+// On return lane L holds in v[0..CPT/32) the totals of original indices  vec_reduce_index(L) + {0 .. CPT/32-1}.
+template <int CPT>
+__device__ __forceinline__ void warp_vec_reduce(float (&v)[CPT], int lane) {
+#pragma unroll
+  for (int h = CPT / 2, bit = 16; bit >= 1; h >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int k = 0; k < h; k++) {
+      const float keep = up ? v[h + k] : v[k];
+      const float send = up ? v[k] : v[h + k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+}
+template <int CPT>
+__device__ __forceinline__ int vec_reduce_index(int lane) {
+  int idx = 0;
+#pragma unroll
+  for (int h = CPT / 2, bit = 16; bit >= 1; h >>= 1, bit >>= 1) idx += ((lane & bit) ? h : 0);
+  return idx;
+}
+
 // backward, phase 1 (see header).  Same tiling; recomputes the forward from z.
 template <int CPT>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
@@ -204,7 +228,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const float* __restrict__ fa_neg, const float* __restrict__ dsim, const float* __restrict__ dneg, float* __restrict__ dv,
     float* __restrict__ sum_dv, float* __restrict__ sum_dvz, float* __restrict__ dfa, float* __restrict__ dfa_neg, int B, int N) {
   constexpr int C = CPT * 8;
-  __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
+  static_assert(CPT == 64 || CPT == 32, "CPT");
+  __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C], s_mean[C], s_istd[C];
   __shared__ float red[2][8][33];
   const int b = blockIdx.y;
   const int pl = threadIdx.x & 31, g = threadIdx.x >> 5;
@@ -213,6 +238,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const float sc = gamma[c] * invstd[c];
     s_scale[c] = sc;
     s_shift[c] = beta[c] - mean[c] * sc;
+    s_mean[c] = mean[c];
+    s_istd[c] = invstd[c];
     if (fa) {
       s_fa[c] = fa[(long long)b * C + c];
       s_fr[c] = fa_neg ? fa_neg[(long long)b * C + c] : fa[(long long)(B - 1 - b) * C + c];
@@ -223,7 +250,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
   const long long base = (long long)b * C * N + n;
   const float ds = (fa && dsim && valid) ? dsim[(long long)b * N + n] : 0.f;
   const float dn = (fa && dneg && valid) ? dneg[(long long)b * N + n] : 0.f;
-  float a[CPT], gr[CPT];
+  float a[CPT], gr[CPT];      // a: pre-activation t, later dpre*zhat;  gr: incoming gradient, later dpre
   float ss = 0.f, dot = 0.f;
 #pragma unroll
   for (int i = 0; i < CPT; i++) {
@@ -231,7 +258,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     float t = valid ? z[base + (long long)c * N] : 0.f;
     t = fmaf(t, s_scale[c], s_shift[c]);
     const float act = t > 0.f ? t : t * slope;
-    a[i] = t;               // keep the pre-activation; act recomputed below
+    a[i] = t;
     ss = fmaf(act, act, ss);
     float gg = (valid && dy) ? dy[base + (long long)c * N] : 0.f;
     if (fa) gg = fmaf(s_fa[c], ds, fmaf(s_fr[c], dn, gg));
@@ -254,33 +281,48 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     dotn = t1 * inv * inv;  // <g, yhat> / nrm, with yhat = act * inv
   }
   const int lane = pl;
+  const int ridx = vec_reduce_index<CPT>(lane);
+  if (fa && dfa) {
+    // d fa[b] += sum_n dsim * yhat ; d fa_partner += sum_n dneg * yhat
+    float f1[CPT], f2[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; i++) {
+      const float t = a[i];
+      const float yh = (t > 0.f ? t : t * slope) * inv;
+      f1[i] = valid ? ds * yh : 0.f;
+      f2[i] = valid ? dn * yh : 0.f;
+    }
+    warp_vec_reduce<CPT>(f1, lane);
+    warp_vec_reduce<CPT>(f2, lane);
+#pragma unroll
+    for (int k = 0; k < CPT / 32; k++) {
+      const int c = g + 8 * (ridx + k);
+      atomicAdd(dfa + (long long)b * C + c, f1[k]);
+      if (fa_neg) { if (dfa_neg) atomicAdd(dfa_neg + (long long)b * C + c, f2[k]); }
+      else atomicAdd(dfa + (long long)(B - 1 - b) * C + c, f2[k]);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < CPT; i++) {
     const int c = g + 8 * i;
     const float t = a[i];
     const float act = t > 0.f ? t : t * slope;
     // d(act): l2norm backward  (g - yhat <g,yhat>) / nrm
-    float da = l2norm ? (gr[i] * inv - act * inv * dotn) : gr[i];
+    const float da = l2norm ? (gr[i] * inv - act * inv * dotn) : gr[i];
     const float dpre = valid ? da * (t > 0.f ? 1.f : slope) : 0.f;
     if (valid) dv[base + (long long)c * N] = dpre;
-    // zhat = (z-mean)*invstd = (t - beta)/gamma  -- recompute from z to stay exact when gamma == 0
-    const float zh = valid ? (z[base + (long long)c * N] - mean[c]) * invstd[c] : 0.f;
-    const float s1 = warp_sum(dpre);
-    const float s2 = warp_sum(dpre * zh);
-    if (lane == 0) {
-      atomicAdd(sum_dv + c, s1);
-      atomicAdd(sum_dvz + c, s2);
-    }
-    if (fa && dfa) {
-      const float yh = act * inv;
-      const float f1 = warp_sum(ds * yh);
-      const float f2 = warp_sum(dn * yh);
-      if (lane == 0) {
-        atomicAdd(dfa + (long long)b * C + c, f1);
-        if (fa_neg) { if (dfa_neg) atomicAdd(dfa_neg + (long long)b * C + c, f2); }
-        else atomicAdd(dfa + (long long)(B - 1 - b) * C + c, f2);
-      }
-    }
+    // zhat = (z - mean) * invstd, from z itself so it stays exact when gamma == 0
+    const float zh = valid ? (z[base + (long long)c * N] - s_mean[c]) * s_istd[c] : 0.f;
+    gr[i] = dpre;
+    a[i] = dpre * zh;
+  }
+  warp_vec_reduce<CPT>(gr, lane);
+  warp_vec_reduce<CPT>(a, lane);
+#pragma unroll
+  for (int k = 0; k < CPT / 32; k++) {
+    const int c = g + 8 * (ridx + k);
+    atomicAdd(sum_dv + c, gr[k]);
+    atomicAdd(sum_dvz + c, a[k]);
   }
 }
 

@@ -63,6 +63,25 @@ __global__ void negidx_kernel(const long long* __restrict__ idx, const int* __re
   negidx[i] = pos + (pos >= col ? 1 : 0);
 }
 
+// cols[p, :] = [ idx//N0 (top_k) | idx%N0 (top_k) | negatives (top_k*neg_n) ]: every gather column of a4 in one launch
+__global__ void interframe_cols_kernel(const long long* __restrict__ idx, const int* __restrict__ negpos, int P, int N0, int top_k, int neg_n,
+                                       long long* __restrict__ cols) {
+  const int per = top_k * (2 + neg_n);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * per) return;
+  const int p = i / per, r = i % per;
+  long long v;
+  if (r < top_k) v = idx[(long long)p * top_k + r] / N0;
+  else if (r < 2 * top_k) v = idx[(long long)p * top_k + (r - top_k)] % N0;
+  else {
+    const int q = r - 2 * top_k;                       // rank * neg_n + j
+    const int col = (int)(idx[(long long)p * top_k + q / neg_n] % N0);
+    const int pos = negpos[(long long)p * top_k * neg_n + q];
+    v = pos + (pos >= col ? 1 : 0);
+  }
+  cols[i] = v;
+}
+
 // out[i,:] = src[img[i], :, col[i]]   one warp per i
 __global__ void gather_cols_kernel(const float* __restrict__ src, const int* __restrict__ img, const long long* __restrict__ col,
                                    int n, float* __restrict__ out, int C, int N) {
@@ -202,6 +221,15 @@ extern "C" int dcnet_interframe_negidx(const long long* idx, const int* negpos, 
   if (total == 0) return 0;
   negidx_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(idx, negpos, total, N0, neg_n, negidx);
   DCNET_LAUNCH_OK("interframe_negidx");
+  return 0;
+}
+
+extern "C" int dcnet_interframe_cols(const long long* idx, const int* negpos, int P, int N0, int top_k, int neg_n, long long* cols, void* stream) {
+  DCNET_CHECK_ARG(idx && negpos && cols && P >= 0 && N0 > 1 && top_k > 0 && neg_n > 0, "interframe_cols: bad arguments");
+  const int total = P * top_k * (2 + neg_n);
+  if (total == 0) return 0;
+  interframe_cols_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(idx, negpos, P, N0, top_k, neg_n, cols);
+  DCNET_LAUNCH_OK("interframe_cols");
   return 0;
 }
 

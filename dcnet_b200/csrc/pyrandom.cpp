@@ -13,40 +13,45 @@
 
 namespace {
 
+// MT19937 on a private copy of the state (no aliasing with the caller's buffer), CPython's genrand_uint32 tempering.
 struct MT {
-  uint32_t* mt;   // 624 words
-  uint32_t* pos;  // index
-  inline uint32_t next() {
+  uint32_t mt[624];
+  uint32_t pos;
+  explicit MT(const uint32_t* st) { std::memcpy(mt, st, sizeof(mt)); pos = st[624]; }
+  void store(uint32_t* st) const { std::memcpy(st, mt, sizeof(mt)); st[624] = pos; }
+  void regen() {
     const uint32_t N = 624, M = 397;
-    if (*pos >= N) {
-      uint32_t kk;
-      for (kk = 0; kk < N - M; kk++) {
-        uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-        mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      }
-      for (; kk < N - 1; kk++) {
-        uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-        mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      }
-      uint32_t y = (mt[N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
-      mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      *pos = 0;
+    uint32_t kk;
+    for (kk = 0; kk < N - M; kk++) {
+      const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+      mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
     }
-    uint32_t y = mt[(*pos)++];
+    for (; kk < N - 1; kk++) {
+      const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+      mt[kk] = mt[kk - (N - M)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    const uint32_t y = (mt[N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+    mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    pos = 0;
+  }
+  inline uint32_t next() {
+    if (__builtin_expect(pos >= 624, 0)) regen();
+    uint32_t y = mt[pos++];
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= (y >> 18);
     return y;
   }
-  // random.Random._randbelow_with_getrandbits(n), n >= 1, n < 2^31
-  inline uint32_t randbelow(uint32_t n) {
-    int k = 32 - __builtin_clz(n);  // n.bit_length()
-    uint32_t r = next() >> (32 - k);
-    while (r >= n) r = next() >> (32 - k);
+  // random.Random._randbelow_with_getrandbits(n), n >= 1; shift = 32 - n.bit_length()
+  inline uint32_t randbelow(uint32_t n, int shift) {
+    uint32_t r = next() >> shift;
+    while (r >= n) r = next() >> shift;
     return r;
   }
 };
+
+inline int bit_shift(uint32_t n) { return 32 - (32 - __builtin_clz(n)); }
 
 inline int set_size_threshold(int k) {
   int setsize = 21;
@@ -59,16 +64,18 @@ inline void sample_positions(MT& g, int n, int k, int setsize, int* pool, int* o
   if (n <= setsize) {
     for (int i = 0; i < n; i++) pool[i] = i;
     for (int i = 0; i < k; i++) {
-      uint32_t j = g.randbelow((uint32_t)(n - i));
+      const uint32_t m = (uint32_t)(n - i);
+      const uint32_t j = g.randbelow(m, bit_shift(m));
       out[i] = pool[j];
       pool[j] = pool[n - i - 1];
     }
   } else {
+    const int sh = bit_shift((uint32_t)n);
     for (int i = 0; i < k; i++) {
       uint32_t j;
       bool dup;
       do {
-        j = g.randbelow((uint32_t)n);
+        j = g.randbelow((uint32_t)n, sh);
         dup = false;
         for (int t = 0; t < i; t++) dup |= (out[t] == (int)j);
       } while (dup);
@@ -81,18 +88,19 @@ inline void sample_positions(MT& g, int n, int k, int setsize, int* pool, int* o
 
 extern "C" int dcnet_pyrandom_interframe(uint32_t* st, int P, int top_k, int N0, int neg_n, int* negpos) {
   if (!st || !negpos || P < 0 || top_k < 0 || neg_n < 0 || N0 - 1 < neg_n) return dcnet_set_error(-1, "pyrandom_interframe: bad arguments");
-  MT g{st, st + 624};
+  MT g(st);
   const int setsize = set_size_threshold(neg_n);
   std::vector<int> pool(N0);
   for (int p = 0; p < P; p++)
     for (int r = 0; r < top_k; r++)
       sample_positions(g, N0 - 1, neg_n, setsize, pool.data(), negpos + ((size_t)p * top_k + r) * neg_n);
+  g.store(st);
   return 0;
 }
 
 extern "C" int dcnet_pyrandom_crossmodal(uint32_t* st, int B, int N0, int neg_n, long long* negidx) {
   if (!st || !negidx || B < 1 || neg_n < 0 || N0 - 1 < neg_n) return dcnet_set_error(-1, "pyrandom_crossmodal: bad arguments");
-  MT g{st, st + 624};
+  MT g(st);
   const int setsize = set_size_threshold(neg_n);
   std::vector<int> pool(N0);
   std::vector<int> tmp(neg_n > 0 ? neg_n : 1);
@@ -108,5 +116,6 @@ extern "C" int dcnet_pyrandom_crossmodal(uint32_t* st, int B, int N0, int neg_n,
         }
       }
     }
+  g.store(st);
   return 0;
 }

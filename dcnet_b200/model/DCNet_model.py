@@ -169,12 +169,16 @@ class grounding_model(nn.Module):
         idx, _ = ops.interframe_topk(fv0.detach(), TOP_K)
         if negpos is None:
             negpos = torch.from_numpy(ops.pyrandom_interframe(P, TOP_K, N0, NEG_N)).to(dev, non_blocking=True)
-        negidx = ops.interframe_negidx(idx, negpos, N0)
-        pair = torch.arange(P, device=dev, dtype=torch.int32)[:, None]
-        img = torch.cat([(2 * pair).expand(P, TOP_K), (2 * pair + 1).expand(P, TOP_K),
-                         (2 * pair + 1).expand(P, TOP_K * NEG_N)], 1).reshape(-1)
-        col = torch.cat([idx // N0, idx % N0, negidx.reshape(P, -1)], 1).reshape(-1)
-        g = ops.gather_cols(fv0, img.contiguous(), col.contiguous()).view(P, TOP_K * (2 + NEG_N), C)
+        cols = ops.interframe_cols(idx, negpos, N0)                  # [P, 30 | 30 | 300]
+        key = ("if", P, str(dev))
+        if key not in self._idx_cache:
+            pair = torch.arange(P, device=dev, dtype=torch.int32)[:, None]
+            self._idx_cache[key] = torch.cat([(2 * pair).expand(P, TOP_K), (2 * pair + 1).expand(P, TOP_K),
+                                              (2 * pair + 1).expand(P, TOP_K * NEG_N)], 1).reshape(-1).contiguous()
+        img = self._idx_cache[key]
+        col = cols.reshape(-1)
+        negidx = cols[:, 2 * TOP_K:].reshape(P, TOP_K, NEG_N)
+        g = ops.gather_cols(fv0, img, col).view(P, TOP_K * (2 + NEG_N), C)
         q = g[:, :TOP_K].transpose(0, 1)
         k = g[:, TOP_K:2 * TOP_K].transpose(0, 1)
         neg = g[:, 2 * TOP_K:].reshape(P, TOP_K, NEG_N, C).transpose(0, 1)
@@ -227,9 +231,12 @@ class grounding_model(nn.Module):
         img_q, col_q, img_n = self._idx_cache[key]
         T = lag.shape[1]
         q = ops.gather_cols(vit, img_q, col_q).view(N0, B, C)
-        widx = (torch.arange(B, device=dev)[:, None] * T + word).t().reshape(-1)              # rows ordered (pixel, image)
+        keyw = ("cmw", B, T, str(dev))
+        if keyw not in self._idx_cache:
+            self._idx_cache[keyw] = (torch.arange(B, device=dev) * T)[:, None]
+        widx = (self._idx_cache[keyw] + word).t().reshape(-1)                                 # rows ordered (pixel, image)
         k = lag.reshape(B * T, C).index_select(0, widx).view(N0, B, 1, C)
-        neg = ops.gather_cols(vit, img_n, negidx.permute(1, 0, 2).reshape(-1).contiguous()).view(N0, B, CROSS_NEG_N, C)
+        neg = ops.gather_cols(vit, img_n, negidx.permute(1, 0, 2).reshape(-1)).view(N0, B, CROSS_NEG_N, C)
         return q, k, neg, word, negidx
 
     def location_branch(self, coords, obj_score, context, embedded, word_id):

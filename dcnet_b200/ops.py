@@ -100,6 +100,15 @@ def interframe_negidx(idx, negpos, N0):
     return out
 
 
+def interframe_cols(idx, negpos, N0):
+    """-> cols [P, top_k*(2+neg_n)] int64: gather columns of q | k | negatives"""
+    P, top_k = idx.shape
+    neg_n = negpos.shape[-1]
+    out = torch.empty(P, top_k * (2 + neg_n), device=idx.device, dtype=torch.long)
+    _lib.call("dcnet_interframe_cols", _p(idx), _p(_c(negpos, torch.int32, "negpos")), P, N0, top_k, neg_n, _p(out), _st())
+    return out
+
+
 def crossmodal_words(lag, vit, fm_w, fm_b):
     lag, vit = _c(lag, name="lag"), _c(vit, name="vit")
     B, T, C = lag.shape

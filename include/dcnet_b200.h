@@ -141,6 +141,10 @@ DCNET_API int dcnet_interframe_topk(const float* fv0, int P, int C, int N0, int 
 DCNET_API int dcnet_interframe_negidx(const long long* idx, const int* negpos, int P, int N0, int top_k, int neg_n,
                                       long long* negidx, void* stream);
 
+/* cols [P, top_k*(2+neg_n)] int64 = [frame-1 column idx//N0 | frame-2 column idx%N0 | negative columns] per pair: the gather
+ * columns of q, k and neg (model/DCNet_model.py:407-420) in one launch.                                                */
+DCNET_API int dcnet_interframe_cols(const long long* idx, const int* negpos, int P, int N0, int top_k, int neg_n, long long* cols, void* stream);
+
 /* ---- generic column gather / scatter-add (a4, a11 gathers and their backward) -------------------------
  * out[i, :] = src[img[i], :, col[i]]   (src [F,C,N]; out [n,C]);  backward: dsrc[img[i], :, col[i]] += dout[i,:] */
 DCNET_API int dcnet_gather_cols(const float* src, const int* img, const long long* col, int n, float* out, int C, int N, void* stream);
