@@ -221,20 +221,22 @@ __device__ __forceinline__ int vec_reduce_index(int lane) {
 }
 
 // backward, phase 1 (see header).  Same tiling; recomputes the forward from z.
-template <int CPT>
-__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
+// G channel groups x 32 positions per CTA (32*G threads); each thread owns CPT = C/G channels of one position.  G = 16 keeps the
+// per-thread arrays at 2 x 32 registers so two 512-thread CTAs fit an SM (the 8-group variant needed 255 registers -> 8 warps/SM).
+template <int CPT, int G>
+__global__ void __launch_bounds__(32 * G) bn_act_bwd_reduce_kernel(
     const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
     const float* __restrict__ beta, float slope, int l2norm, const float* __restrict__ dy, const float* __restrict__ fa,
     const float* __restrict__ fa_neg, const float* __restrict__ dsim, const float* __restrict__ dneg, float* __restrict__ dv,
     float* __restrict__ sum_dv, float* __restrict__ sum_dvz, float* __restrict__ dfa, float* __restrict__ dfa_neg, int B, int N) {
-  constexpr int C = CPT * 8;
-  static_assert(CPT == 64 || CPT == 32, "CPT");
+  constexpr int C = CPT * G;
+  static_assert(CPT % 32 == 0 && CPT <= 64, "CPT");
   __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C], s_mean[C], s_istd[C];
-  __shared__ float red[2][8][33];
+  __shared__ float red[2][G][33];
   const int b = blockIdx.y;
   const int pl = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + pl;
-  for (int c = threadIdx.x; c < C; c += 256) {
+  for (int c = threadIdx.x; c < C; c += 32 * G) {
     const float sc = gamma[c] * invstd[c];
     s_scale[c] = sc;
     s_shift[c] = beta[c] - mean[c] * sc;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
   float ss = 0.f, dot = 0.f;
 #pragma unroll
   for (int i = 0; i < CPT; i++) {
-    const int c = g + 8 * i;
+    const int c = g + G * i;
     float t = valid ? z[base + (long long)c * N] : 0.f;
     t = fmaf(t, s_scale[c], s_shift[c]);
     const float act = t > 0.f ? t : t * slope;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     __syncthreads();
     float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < G; k++) {
       t0 += red[0][k][pl];
       t1 += red[1][k][pl];
     }
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     warp_vec_reduce<CPT>(f2, lane);
 #pragma unroll
     for (int k = 0; k < CPT / 32; k++) {
-      const int c = g + 8 * (ridx + k);
+      const int c = g + G * (ridx + k);
       atomicAdd(dfa + (long long)b * C + c, f1[k]);
       if (fa_neg) { if (dfa_neg) atomicAdd(dfa_neg + (long long)b * C + c, f2[k]); }
       else atomicAdd(dfa + (long long)(B - 1 - b) * C + c, f2[k]);
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
   }
 #pragma unroll
   for (int i = 0; i < CPT; i++) {
-    const int c = g + 8 * i;
+    const int c = g + G * i;
     const float t = a[i];
     const float act = t > 0.f ? t : t * slope;
     // d(act): l2norm backward  (g - yhat <g,yhat>) / nrm
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
   warp_vec_reduce<CPT>(a, lane);
 #pragma unroll
   for (int k = 0; k < CPT / 32; k++) {
-    const int c = g + 8 * (ridx + k);
+    const int c = g + G * (ridx + k);
     atomicAdd(sum_dv + c, gr[k]);
     atomicAdd(sum_dvz + c, a[k]);
   }
@@ -517,11 +519,11 @@ extern "C" int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const 
   DCNET_CHECK_ARG(C == 512 || C == 256, "bn_act_bwd_reduce: C=%d unsupported (512 or 256)", C);
   dim3 grid(ceil_div(N, 32), B);
   if (C == 512)
-    bn_act_bwd_reduce_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, fa_neg, dsim,
-                                                                         dneg_sim, dv, sum_dv, sum_dvz, dfa, dfa_neg, B, N);
+    bn_act_bwd_reduce_kernel<32, 16><<<grid, 512, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, fa_neg, dsim,
+                                                                             dneg_sim, dv, sum_dv, sum_dvz, dfa, dfa_neg, B, N);
   else
-    bn_act_bwd_reduce_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, fa_neg, dsim,
-                                                                         dneg_sim, dv, sum_dv, sum_dvz, dfa, dfa_neg, B, N);
+    bn_act_bwd_reduce_kernel<32, 8><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, fa_neg, dsim,
+                                                                            dneg_sim, dv, sum_dv, sum_dvz, dfa, dfa_neg, B, N);
   DCNET_LAUNCH_OK("bn_act_bwd_reduce");
   return 0;
 }

@@ -221,7 +221,10 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   DCNET_CHECK_ARG(umma_gemm_usable(A, B, B2, K), "umma_gemm: operand not TMA-compatible (16-B aligned base, row pitch multiple of 4 floats)");
   DCNET_CHECK_ARG(k_split_elems % BK == 0, "umma_gemm: k_split must be a multiple of %d", BK);
   DCNET_CHECK_ARG(batch >= 1 && batch <= 65535, "umma_gemm: batch %d", batch);
-  const int BN = (N <= 64) ? 64 : 128;
+  // wide tiles cut the L2->SM operand traffic per FLOP (the kernel is L2-bound at 128x128, profiles/r1b_ncu_full_umma_gemm.txt);
+  // use them once there are enough 128x256 tiles to fill the 148 SMs
+  const long long tiles256 = (long long)ceil_div(N, 256) * ceil_div(M, BM) * batch;
+  const int BN = (N <= 64) ? 64 : ((N >= 256 && tiles256 >= 148) ? 256 : 128);
   CUtensorMap ma, mb, mb2;
   DCNET_TRY(make_operand_map(&ma, A, BM));
   DCNET_TRY(make_operand_map(&mb, B, BN));
@@ -241,6 +244,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
 #define DISPATCH(AM, BMJ)                                                                   \
   if (am == AM && bm == BMJ) {                                                              \
     if (BN == 64) return launch_cfg<AM, BMJ, 64, 4>(ma, mb, mb2, p, grid, st);              \
+    if (BN == 256) return launch_cfg<AM, BMJ, 256, 4>(ma, mb, mb2, p, grid, st);            \
     return launch_cfg<AM, BMJ, 128, 3>(ma, mb, mb2, p, grid, st);                           \
   }
   DISPATCH(0, 0) DISPATCH(0, 1) DISPATCH(1, 0) DISPATCH(1, 1)
