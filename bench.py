@@ -33,6 +33,8 @@ import torch  # noqa: E402
 WORKLOADS = {
     "c2": dict(pairs=8, size=256, name="C2: 8 frame-pairs 256x256 per GPU (32x32 finest map), fwd+bwd of correspondence/fusion/decode path"),
     "c3": dict(pairs=16, size=416, name="C3: 16 frame-pairs 416x416 per GPU (52x52 finest map, 2704x2704 similarity), fwd+bwd"),
+    "c4": dict(pairs=224, size=256, clips=8, frames=8,
+               name="C4: 8 clips x 8 frames 256x256 per GPU, all-pairs inter-frame correspondence (28 unordered = 56 directed pairs per clip), forward"),
 }
 C_EMB = 512
 
@@ -132,6 +134,90 @@ def reference_arm(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_c4(args, wl, rank, world, dev, dist):
+    """BASELINE configs[3]: all ordered frame pairs of every 8-frame clip (generalises model/test_DCNet_model.py:303-332 from
+    centre-vs-others to all pairs): visual mapping of the 64 frames once, then one co-attention problem per directed pair and
+    scale; the maps of a frame are read from HBM/L2 by its 14 problems, never re-mapped.  Forward only, clips shard over GPUs."""
+    from dcnet_b200 import _lib, ops, synth
+    from dcnet_b200.hotpath import HotPath
+    clips, nf, size = wl["clips"], wl["frames"], wl["size"]
+    F_ = clips * nf
+    synth.seed_all(13)
+    hp = HotPath(size).to(dev).eval()
+    g = torch.Generator().manual_seed(7000 + rank)
+    host = [[t.pin_memory() for t in synth.make_raw_fvisu(F_ // 2, size, g)] for _ in range(2)]
+    static = [t.to(dev) for t in host[0]]
+    qa = torch.tensor([c * nf + i for c in range(clips) for i in range(nf) for j in range(nf) if i != j], device=dev, dtype=torch.int32)
+    kb = torch.tensor([c * nf + j for c in range(clips) for i in range(nf) for j in range(nf) if i != j], device=dev, dtype=torch.int32)
+    nprob = qa.numel()
+
+    def run_step():
+        with torch.no_grad():
+            fv = hp.net.map_visual(static)
+            outs = [ops.coattention(fv[s], qa, kb, tau=10.0, precision=hp.net.precision) for s in range(3)]
+            return torch.stack([o.sum() for o in outs])
+
+    n0 = _lib.launch_count(); res = run_step(); launches = _lib.launch_count() - n0
+    for _ in range(2):
+        run_step()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    h_out = torch.empty(3).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.zero_(); run_step()
+    barrier()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        flush.zero_(); a.record(); res = run_step(); b.record()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        for dst, src in zip(static, host[i % 2]):
+            dst.copy_(src, non_blocking=True)
+        res = run_step()
+        h_out.copy_(res, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    pairs = wl["pairs"]
+    if rank == 0:
+        peaks = load_peaks()
+        flops = sum(4.0 * C_EMB * ((size // st) ** 2) ** 2 for st in (32, 16, 8)) * nprob     # 2 GEMMs of 2 N^2 c per directed pair
+        ach = flops / (dev_ms / args.steps * 1e-3) / 1e12
+        h2d = sum(t_.numel() * 4 for t_ in host[0])
+        line = dict(metric="frame_pairs_per_sec", value=world * pairs * args.steps / (dev_ms / 1e3), unit="frame-pairs/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32", data="synthetic",
+                    config=dict(workload=wl["name"], clips_per_gpu=clips, frames=nf, directed_pairs_per_gpu=nprob, size=size,
+                                l2="flushed (256 MiB write) before every timed step", launch="eager"),
+                    clocks=clocks,
+                    e2e=dict(value=world * pairs * args.steps / (e2e_ms / 1e3), unit="frame-pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=12,
+                             ms_per_step=e2e_ms / args.steps),
+                    gpu_launches=int(launches * args.steps), gpu_launches_per_step=int(launches),
+                    roofline=dict(bound="tensor", kernel="visual mapping + all-pairs co-attention forward (whole step)", achieved=ach,
+                                  peak=peaks["tensor_sustained"], unit="TFLOP/s", frac=ach / peaks["tensor_sustained"], traffic=None,
+                                  peak_source=peaks["src"] + " bf16 sustained (kernel timed inside a long step)"),
+                    cpu_baseline=None)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +251,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     pairs, size = wl["pairs"], wl["size"]
+    if args.workload == "c4":
+        return run_c4(args, wl, rank, world, dev, dist)
     B = 2 * pairs
     synth.seed_all(13)                       # identical replicas (DDP broadcast equivalent)
     xneg = bool(args.xgpu_negatives and world > 1)

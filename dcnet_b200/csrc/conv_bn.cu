@@ -346,6 +346,29 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ z, const float
   }
 }
 
+// sim[b,n] = <fa[b], x[b,:,n]>, neg[b,n] = <fa_neg[b] (or fa[B-1-b]), x[b,:,n]>; one thread per (b,n), coalesced along n
+__global__ void pix2text_kernel(const float* __restrict__ x, const float* __restrict__ fa, const float* __restrict__ fa_neg,
+                                float* __restrict__ sim, float* __restrict__ neg, int B, int C, int N) {
+  extern __shared__ float sf[];   // fa[b] | partner
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sf[c] = fa[(long long)b * C + c];
+    sf[C + c] = fa_neg ? fa_neg[(long long)b * C + c] : fa[(long long)(B - 1 - b) * C + c];
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* xp = x + (long long)b * C * N + n;
+  float a = 0.f, d = 0.f;
+  for (int c = 0; c < C; c++) {
+    const float v = xp[(long long)c * N];
+    a = fmaf(v, sf[c], a);
+    d = fmaf(v, sf[C + c], d);
+  }
+  sim[(long long)b * N + n] = a;
+  if (neg) neg[(long long)b * N + n] = d;
+}
+
 __global__ void coord_map_kernel(float* __restrict__ coord, int h, int w) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
@@ -536,6 +559,14 @@ extern "C" int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const f
   bn_act_bwd_apply_kernel<<<ew_grid((long long)B * C * N), 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, dv, sum_dv, sum_dvz,
                                                                                             train, dz, B, C, N);
   DCNET_LAUNCH_OK("bn_act_bwd_apply");
+  return 0;
+}
+
+extern "C" int dcnet_pix2text(const float* x, const float* fa, const float* fa_neg, float* sim, float* neg_sim, int B, int C, int N, void* stream) {
+  DCNET_CHECK_ARG(x && fa && sim && B > 0 && C > 0 && N > 0 && B <= 65535, "pix2text: bad arguments");
+  dim3 grid(ceil_div(N, 128), B);
+  pix2text_kernel<<<grid, 128, 2 * (size_t)C * sizeof(float), as_stream(stream)>>>(x, fa, fa_neg, sim, neg_sim, B, C, N);
+  DCNET_LAUNCH_OK("pix2text");
   return 0;
 }
 

@@ -87,7 +87,7 @@ class PhraseAttention(nn.Module):
 
 class grounding_model(nn.Module):
     def __init__(self, corpus=None, emb_size=256, jemb_drop_out=0.1, bert_model='bert-base-uncased',
-                 coordmap=True, leaky=False, dataset=None, light=False, visumodel=None, size=256):
+                 coordmap=True, leaky=False, dataset=None, light=False, visumodel=None, size=256, _with_feature_map=True):
         """Extra keyword arguments (both optional, defaults = reference behaviour):
         visumodel -- the Darknet backbone instance (reference: Darknet('./model/yolov3.cfg') + yolov3.weights);
                      when None the surrounding checkout's model.darknet.Darknet is imported (drop-in use).
@@ -125,7 +125,8 @@ class grounding_model(nn.Module):
             nn.Linear(emb_size, emb_size), nn.BatchNorm1d(emb_size), nn.ReLU())
         self.corr_conv = nn.Sequential(OrderedDict([
             (str(i), nn.Sequential(ConvBatchNormReLU(emb_size * 2, emb_size, 1, 1, 0, 1, leaky=leaky))) for i in range(3)]))
-        self.feature_map = nn.Sequential(nn.Conv1d(20, 20, stride=1, kernel_size=3, padding=1, bias=True), nn.Softmax(dim=1))
+        if _with_feature_map:      # model/test_DCNet_model.py has no feature_map (and draws no init RNG for it)
+            self.feature_map = nn.Sequential(nn.Conv1d(20, 20, stride=1, kernel_size=3, padding=1, bias=True), nn.Softmax(dim=1))
         embin_size = emb_size * 2 + (8 if coordmap else 0)
         if light:
             self.fcn_emb = nn.Sequential(OrderedDict([

@@ -75,6 +75,15 @@ def gemm_tf32(A, B, a_mn, b_mn, M, N, K, alpha=1.0):
     return C
 
 
+def pix2text(x, fa):
+    """x [B,C,N], fa [B,C] -> sim [B,N]   (forward only; inference / clip path)"""
+    x, fa = _c(x.detach(), name="x"), _c(fa.detach(), name="fa")
+    B, C, N = x.shape
+    sim = torch.empty(B, N, device=x.device, dtype=F32)
+    _lib.call("dcnet_pix2text", _p(x), _p(fa), None, _p(sim), None, B, C, N, _st())
+    return sim
+
+
 def coord_map(h, w, device):
     out = torch.empty(8, h, w, device=device, dtype=F32)
     _lib.call("dcnet_coord_map", _p(out), h, w, _st())

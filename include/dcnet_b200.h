@@ -114,6 +114,10 @@ DCNET_API int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const fl
                                      const float* dv, const float* sum_dv, const float* sum_dvz, int train,
                                      float* dz, int B, int C, int N, void* stream);
 
+/* ---- a9 stand-alone (model/DCNet_model.py:530-535): sim[b,n] = <fa[b], x[b,:,n]>; neg_sim (optional) with fa_neg[b] or fa[B-1-b].
+ * The training path gets these from dcnet_bn_act_fwd's epilogue; the clip path (mean of several corr maps) calls this.  Forward only. */
+DCNET_API int dcnet_pix2text(const float* x, const float* fa, const float* fa_neg, float* sim, float* neg_sim, int B, int C, int N, void* stream);
+
 /* ---- a7: coordinate map (model/DCNet_model.py:23-39), [8,h,w], batch independent ---------------------- */
 DCNET_API int dcnet_coord_map(float* coord, int h, int w, void* stream);
 

@@ -565,3 +565,59 @@ def hotpath_restated(net, raw, flang, fa, context, head, loc, dy_head, bbox, siz
         torch.autograd.backward([loss] + y, [None] + list(dy_head))
     return dict(loss=loss, comp=comp, y=y, iou=iou, boxes=boxes, best_n=best_n, gi=gi, gj=gj, corr=corr, sim=sim, pred=pred,
                 idx_if=idx_if, word=word)
+
+
+# ----------------------------------------------------------------------------------------------
+# test-time multi-frame forward, restated                      model/test_DCNet_model.py:247-483
+# ----------------------------------------------------------------------------------------------
+def forward_test_restated(net, raw_fvisu, word_id, n_frame=5):
+    """raw_fvisu 3 x [b*n_frame,C_s,h,w]; word_id [b,T].  Centre frame vs every other frame (:303-320), corr_conv + L2 norm per
+    partner (:276-280), mean over partners (:324-332), then the same fusion / similarity / location / modulation as the
+    training model with batch b.  Returns dict(outbox, sim_score, loc_score, corr_feat, only_obj, flang_attn)."""
+    training = net.training
+    BF = raw_fvisu[0].shape[0]
+    b = BF // n_frame
+    centre = n_frame // 2
+    hw = [(m.shape[2], m.shape[3]) for m in raw_fvisu]
+    fv = [l2norm_channels(_cbr(net.mapping_visu._modules[str(s)], raw_fvisu[s].flatten(2), training)) for s in range(3)]
+    C = fv[0].shape[1]
+    corr = []
+    for s in range(3):
+        f = fv[s].reshape(b, n_frame, C, -1)
+        f1 = f[:, centre]
+        outs = []
+        for o in range(n_frame):
+            if o == centre:
+                continue
+            o1, _ = coattention(f1, f[:, o], net.temperature)
+            outs.append(l2norm_channels(_cbr(net.corr_conv._modules[str(s)][0], torch.cat([f1, o1], 1), training)))
+        corr.append(torch.stack(outs, 0).mean(0))
+    max_len = int((word_id != 0).sum(1).max().item())
+    word_id = word_id[:, :max_len]
+    raw_flang, context, embedded = net.textmodel(word_id)
+    flang = F.normalize(net.mapping_lang(raw_flang), p=2, dim=1)
+    coords = [coord_map(h, w, device=raw_fvisu[0].device).flatten(1) for (h, w) in hw]
+    outbox = []
+    for s in range(3):
+        N = corr[s].shape[2]
+        x = torch.cat([corr[s], flang[:, :, None].expand(b, C, N), coords[s][None].expand(b, 8, N)], 1)
+        seq = net.fcn_emb._modules[str(s)]
+        y = _cbr(seq[0], x, training).reshape(b, -1, hw[s][0], hw[s][1])
+        for m in list(seq)[1:]:
+            y = m(y)
+        outbox.append(net.fcn_out._modules[str(s)](y).flatten(2))
+    _, fa = net.sub_attn(context, embedded, word_id)
+    fa = F.normalize(fa, p=2, dim=1)
+    sim = [pix2text(corr[s], fa)[0] for s in range(3)]
+    oo = [only_obj(outbox[s]) for s in range(3)]
+    obj = [oo[s] * sim[s] for s in range(3)]
+    locmap = location_branch(net, coords, obj, context, embedded, word_id)
+    loc, st = [], 0
+    for s in range(3):
+        N = corr[s].shape[2]
+        loc.append(locmap[:, st:st + N]); st += N
+    outbox = [modulate_conf(outbox[s], sim[s], loc[s]) for s in range(3)]
+    shp = lambda t, s: t.reshape(t.shape[:-1] + hw[s])
+    return dict(outbox=[shp(outbox[s], s) for s in range(3)], sim_score=[shp(sim[s], s) for s in range(3)],
+                loc_score=[shp(loc[s], s) for s in range(3)], corr_feat=[shp(corr[s], s) for s in range(3)],
+                only_obj=[shp(oo[s], s) for s in range(3)], flang_attn=fa[:, :, None, None])

@@ -224,3 +224,31 @@ def test_against_reference_golden_vectors(precision):
     for i, n in ((0, 'outbox'), (1, 'sim_score'), (3, 'only_obj')):
         for s in range(3):
             assert rel(sub(ev[i][s]), fix['eval'][n][s]) < TF * 2, (n, s)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("n_frame,b", [(5, 2), (8, 1)])
+def test_test_time_clip_model_vs_oracle(n_frame, b, precision):
+    """a20: dcnet_b200.model.test_DCNet_model (centre frame vs the other frames, one co-attention direction per problem) vs the oracle."""
+    from dcnet_b200.model.test_DCNet_model import grounding_model as test_model
+    synth.seed_all(17)
+    net = test_model(corpus=list(range(1000)), emb_size=512, visumodel=StubBackbone(), size=256)
+    net.precision = precision
+    assert not any(k.startswith("feature_map") for k in net.state_dict())
+    g = torch.Generator().manual_seed(70 + n_frame)
+    for m in net.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.running_mean.normal_(0, 0.1, generator=g); m.running_var.uniform_(0.5, 1.5, generator=g)
+    maps = [torch.randn(b * n_frame, c, s, s, generator=g) for c, s in ((1024, 8), (512, 16), (256, 32))]
+    wid = synth.make_words(b, gen=g)[::2].contiguous()
+    cpu_net = copy.deepcopy(net).eval()
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        o = O.forward_test_restated(cpu_net, maps, wid, n_frame)
+        net.visumodel.maps = [m.to(DEV) for m in maps]
+        out = net(torch.zeros(b * n_frame, 1, 1, 1, device=DEV), wid.to(DEV), None, n_frame)
+    tol = 2e-5 if precision == 0 else 3e-3
+    for i, n in enumerate(['outbox', 'sim_score', 'loc_score', 'corr_feat', 'only_obj']):
+        for s in range(3):
+            assert out[i][s].shape == o[n][s].shape
+            assert rel(out[i][s], o[n][s]) < max(tol, 5e-4 if n in ('loc_score', 'outbox') else 0), (n, s, rel(out[i][s], o[n][s]))

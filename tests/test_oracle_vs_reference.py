@@ -142,3 +142,24 @@ def test_eval_decode_matches_reference_logic(ref):
         else: bs = 2
         (bn, gj, gi) = np.where(pred[bs][ii, :, 4].numpy() == max_conf[ii].numpy())
         assert (bs, int(bn[0]), int(gj[0]), int(gi[0])) == (int(S[ii]), int(A[ii]), int(GJ[ii]), int(GI[ii]))
+
+
+@pytest.mark.parametrize("n_frame,b", [(5, 2), (3, 1)])
+def test_test_time_clip_model_matches_reference(ref, n_frame, b):
+    """model/test_DCNet_model.py: forward(image, word_id, word_mask, n_frame) vs the oracle's restatement (eval mode, as test_DCNet.py uses it)."""
+    T, M, MT, _ = ref
+    synth.seed_all(31)
+    net = MT.grounding_model(corpus=list(range(1000)), emb_size=512, coordmap=True).eval()
+    g = torch.Generator().manual_seed(50 + n_frame)
+    for m in net.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.normal_(0, 0.1, generator=g); m.running_var.uniform_(0.5, 1.5, generator=g)
+    maps = [torch.randn(b * n_frame, c, s, s, generator=g) for c, s in ((1024, 8), (512, 16), (256, 32))]
+    wid = synth.make_words(b, gen=g)[::2].contiguous()
+    net.visumodel.set_maps(maps)
+    with torch.no_grad():
+        r = net(torch.zeros(b * n_frame, 1, 1, 1), wid, torch.zeros_like(wid), n_frame)
+        o = O.forward_test_restated(net, maps, wid, n_frame)
+    for i, n in enumerate(['outbox', 'sim_score', 'loc_score', 'corr_feat', 'only_obj']):
+        for s in range(3):
+            torch.testing.assert_close(o[n][s], r[i][s], rtol=2e-5, atol=2e-4 if n == 'loc_score' else 2e-5, msg=lambda m, n=n, s=s: f"{n}[{s}] {m}")
