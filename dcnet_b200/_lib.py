@@ -56,7 +56,7 @@ def lib():
             fn = getattr(L, name)   # AttributeError if the .so does not export a declared symbol
             fn.restype = _ctype(ret)
             fn.argtypes = [_ctype(t) for t, _ in args]
-        if L.dcnet_abi_version() != 2:
+        if L.dcnet_abi_version() != 3:
             raise RuntimeError("dcnet_b200: ABI version mismatch")
         _lib = L
     return _lib

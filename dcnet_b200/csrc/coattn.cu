@@ -5,9 +5,10 @@
 // dcnet_coattn_fwd when the shape is supported.
 #include "common.cuh"
 
-int umma_coattn_fwd(const float* frames, const int* qa, const int* kb, const int* oidx, int nprob, float* out, float* lse,
+int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, float* lse,
                     int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st);  // umma_coattn.cu
 bool umma_coattn_supported(int C, int N);
+size_t umma_coattn_workspace_bytes(int F, int C, int N);
 
 namespace {
 
@@ -29,7 +30,7 @@ __global__ void softmax_rows_kernel(float* __restrict__ S, float* __restrict__ l
   s = warp_sum(s);
   const float inv = 1.f / s;
   for (int j = lane; j < N; j += 32) p[j] *= inv;
-  if (lane == 0) lse[row] = m + logf(s);
+  if (lane == 0 && lse) lse[row] = m + logf(s);
 }
 
 // P = exp(S' - lse[row])
@@ -56,15 +57,16 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
-extern "C" size_t dcnet_coattn_workspace_bytes(int nprob, int C, int N) {
-  (void)C;
-  if (nprob <= 0 || N <= 0) return 256;
-  return 2 * align256((size_t)nprob * N * N * sizeof(float)) + 256;
+extern "C" size_t dcnet_coattn_workspace_bytes(int F, int nprob, int C, int N, int precision) {
+  if (nprob <= 0 || N <= 0 || F <= 0) return 256;
+  const size_t unfused = 2 * align256((size_t)nprob * N * N * sizeof(float)) + 256;   // S / P and dP scratch (backward; unfused forward)
+  const size_t fused = umma_coattn_workspace_bytes(F, C, N);                           // bf16 staging of the maps + column norms
+  return precision == 2 ? (unfused > fused ? unfused : fused) : unfused;
 }
 
 static bool coattn_tc_ok(int precision, int C, int N, const void* a, const void* b, const void* c) {
   auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
-  return precision == 1 && N % 4 == 0 && C % 128 == 0 && al(a) && al(b) && al(c);
+  return precision >= 1 && N % 4 == 0 && C % 128 == 0 && al(a) && al(b) && al(c);
 }
 
 extern "C" int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
@@ -73,9 +75,9 @@ extern "C" int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const
   DCNET_CHECK_ARG(frames && qa && kb && oidx && out && lse && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_fwd: bad arguments");
   if (nprob == 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (umma_coattn_supported(C, N))
-    return umma_coattn_fwd(frames, qa, kb, oidx, nprob, out, lse, C, N, tau, workspace, workspace_bytes, st);
-  DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(nprob, C, N), "coattn_fwd: workspace too small");
+  if (precision == 2 && umma_coattn_supported(C, N))
+    return umma_coattn_fwd(frames, F, qa, kb, oidx, nprob, out, lse, C, N, tau, workspace, workspace_bytes, st);
+  DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(F, nprob, C, N, precision), "coattn_fwd: workspace too small");
   float* S = (float*)workspace;
   const long long CN = (long long)C * N, NN = (long long)N * N;
   const long long rows = (long long)nprob * N;
@@ -110,16 +112,22 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
   (void)out;
   DCNET_CHECK_ARG(frames && qa && kb && oidx && lse && dout && dframes && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_bwd: bad arguments");
   if (nprob == 0) return 0;
-  DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(nprob, C, N), "coattn_bwd: workspace too small");
+  DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(F, nprob, C, N, precision), "coattn_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   const long long CN = (long long)C * N, NN = (long long)N * N;
   float* P = (float*)workspace;
   float* dP = (float*)((char*)workspace + align256((size_t)nprob * NN * sizeof(float)));
   const long long rows = (long long)nprob * N;
   const bool tc = coattn_tc_ok(precision, C, N, frames, dout, dframes) && coattn_tc_ok(precision, C, N, P, dP, P);
+  // precision 2: the forward's lse comes from bf16 logits; P is re-normalised from the logits recomputed here so that its rows
+  // sum to one in this precision (a 5e-4 logit mismatch times tau would otherwise show up as a 5e-3 error in P)
   auto exp_launch = [&]() {
-    long long g = (rows * N + 255) / 256;
-    exp_lse_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, st>>>(P, lse, rows, N);
+    if (precision == 2) {
+      softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, nullptr, rows, N);
+    } else {
+      long long g = (rows * N + 255) / 256;
+      exp_lse_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, st>>>(P, lse, rows, N);
+    }
   };
   if (tc) {
     UmmaOperand Fmn{frames, C, N, N, CN, F, true}, Fk{frames, C, N, N, CN, F, false};

@@ -80,8 +80,9 @@ int sgemm_launch(const float* A, const float* B, float* C, int M, int N, int K, 
 
 // tcgen05 TF32 GEMM (umma_gemm.cu)
 struct UmmaOperand {
-  const float* ptr; long long rows, cols, ld, batch_stride; int batches;   // batches = 0: not batched
+  const float* ptr; long long rows, cols, ld, batch_stride; int batches;   // batches = 0: not batched; ld/stride in elements
   bool mn_major;
+  bool bf16 = false;   // ptr is __nv_bfloat16 data (kind::f16 MMA) instead of fp32 read as TF32
 };
 struct UmmaEpilogue {
   float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2; int m_split;

@@ -1,10 +1,361 @@
-// tcgen05 / TMEM / TMA co-attention forward.  Placeholder selector for the first build step: reports "unsupported"
-// so dcnet_coattn_fwd takes the fp32 composition; replaced by the fused kernel below once it is parity-green.
+// a5 / a20: fused co-attention forward on tcgen05 / TMEM / TMA (model/DCNet_model.py:449-459; model/test_DCNet_model.py:247-274).
+//
+// One problem = one direction: queries = columns of Fa [C,N], keys = values = columns of Fb [C,N] (unit-norm in the model,
+// model/DCNet_model.py:359):   S = Fa^T Fb,  P = softmax_j(tau S),  O = Fb P^T  ([C,N]),  lse[i] = log sum_j exp(tau S[i,j]).
+// The score matrix never leaves the SM: one CTA owns 64 queries and walks the keys in tiles of 128.
+//
+//   transposed formulation (so the output tile is already in the [C,N] layout of the reference and the query tile is the
+//   narrow MMA dimension):
+//     S^T[key, q]   = sum_c Fb[c,key] Fa[c,q]      tcgen05.mma  M=128 (keys)  N=64 (q)  K=C     A: KV tile, MN-major   B: Q tile, MN-major
+//     E^T[key, q]   = exp(tau S^T - shift[q])       8 warps: tcgen05.ld -> ex2 -> bf16 -> swizzled smem (the B operand of the next MMA)
+//     O^T[c, q]    += sum_key Fb[c,key] E^T[key,q]  tcgen05.mma  M=128 (c block) N=64  K=128 (keys)  A: the SAME KV tile, K-major
+//   The KV tile [C x 128 keys] is loaded once by TMA and consumed by both contractions through two descriptor views of the same
+//   128-byte-swizzled bytes.  shift[q] = tau |Fa_q| max_k |Fb_k| >= every logit of the row (Cauchy-Schwarz), so no running
+//   maximum and no rescaling of O is needed: O^T accumulates in TMEM over all key tiles, r[q] = sum_key E^T (of the bf16-rounded
+//   values the MMA sees) is kept in registers, and the epilogue writes O^T / r and lse = shift + log r.
+//   Domain: rows whose true maximum logit lies more than ~80 below the bound underflow (never the case for the unit-norm,
+//   non-negative maps of the model: logits in [0, tau]).
+//
+//   TMEM (512 columns): O^T = C/128 blocks x 64 columns (<= 256), S^T = 64 columns at column 256.
+//   SMEM: Q 64 KiB (resident) + KV tile 128 KiB + E^T 16 KiB = 208 KiB  ->  one CTA per SM.
+//   Warps: 0 = TMA producer, 1 = MMA issuer (one elected thread) + TMEM owner, 2..9 = exp / row-sum / epilogue.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+#include "umma.cuh"
 
-bool umma_coattn_supported(int C, int N) { (void)C; (void)N; return false; }
+using namespace umma;
 
-int umma_coattn_fwd(const float*, const int*, const int*, const int*, int, float*, float*, int, int, float, void*, size_t,
-                    cudaStream_t) {
-  return dcnet_set_error(-2, "umma_coattn_fwd: not built");
+namespace {
+
+constexpr int QT = 64;                  // queries per CTA
+constexpr int KT = 128;                 // keys per tile
+constexpr int CMAX = 512;
+constexpr int CB_BYTES = 128 * 256;     // one 128-channel block of a KV tile: two key halves of [128 c rows x 128 B]
+constexpr int KH_BYTES = 128 * 128;     // one key half (64 keys) of a channel block
+constexpr int Q_BYTES = CMAX * 128;     // [C rows][64 q] bf16
+constexpr int KV_BYTES = (CMAX / 128) * CB_BYTES;
+constexpr int P_BYTES = KT * 128;       // [128 key rows][64 q] bf16
+constexpr int FUSED_SMEM = Q_BYTES + KV_BYTES + P_BYTES + 1024;
+constexpr int NTHREADS = 320;
+constexpr uint32_t S_COL = 256;         // TMEM column of S^T
+
+struct CoP {
+  const int* qa; const int* kb; const int* oidx;
+  float* out; float* lse;
+  const float* normsq;     // [F][N]  squared column norms of the fp32 maps
+  const float* maxnorm;    // [F]     max column norm per frame
+  int N, C, tiles;
+  float scale;             // tau * log2(e)
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const CoP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + Q_BYTES;
+  uint8_t* sP = sKV + KV_BYTES;
+  __shared__ uint64_t bars[12];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_shift[QT], s_inv[QT], s_red[8][32];
+  uint64_t* q_full = &bars[0];
+  uint64_t* kv_full = &bars[1];    // [4]
+  uint64_t* kv_free = &bars[5];    // [4]
+  uint64_t* s_full = &bars[9];
+  uint64_t* p_full = &bars[10];
+  uint64_t* o_full = &bars[11];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.y;
+  const int q0 = blockIdx.x * QT;
+  const int fa = p.qa[z], fb = p.kb[z];
+  const int ncb = p.C >> 7;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int m = 0; m < 4; m++) { mbar_init(&kv_full[m], 1); mbar_init(&kv_free[m], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 8);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&map);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + QT) {
+    const int q = threadIdx.x - 64;
+    const float nq = (q0 + q < p.N) ? sqrtf(p.normsq[(long long)fa * p.N + q0 + q]) : 0.f;
+    s_shift[q] = p.scale * nq * p.maxnorm[fb];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_expect_tx(q_full, (uint32_t)ncb * KH_BYTES);
+      for (int m = 0; m < ncb; m++) tma_load_3d(sQ + m * KH_BYTES, &map, q_full, q0, m * 128, fa);
+      for (int j = 0; j < p.tiles; j++) {
+        for (int m = 0; m < ncb; m++) {
+          if (j > 0) mbar_wait(&kv_free[m], (uint32_t)(j - 1) & 1u);
+          mbar_expect_tx(&kv_full[m], CB_BYTES);
+          tma_load_3d(sKV + m * CB_BYTES, &map, &kv_full[m], j * KT, m * 128, fb);
+          tma_load_3d(sKV + m * CB_BYTES + KH_BYTES, &map, &kv_full[m], j * KT + 64, m * 128, fb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = instr_desc(FMT_BF16, 128, QT, 1, 1);
+      constexpr uint32_t idesc_o = instr_desc(FMT_BF16, 128, QT, 0, 1);
+      // descriptor templates; the 14-bit start-address field (bytes >> 4) is added per MMA
+      const uint64_t kv_mn = smem_desc(smem_u32(sKV), KH_BYTES, 1024, 2);   // MN-major: key halves LBO apart, 8-channel groups SBO apart
+      const uint64_t kv_k = smem_desc(smem_u32(sKV), 16, 1024, 2);          // K-major : rows = channels (128 B), 8-row atoms SBO apart
+      const uint64_t q_mn = smem_desc(smem_u32(sQ), KH_BYTES, 1024, 2);
+      const uint64_t p_mn = smem_desc(smem_u32(sP), KH_BYTES, 1024, 2);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < p.tiles; j++) {
+        const uint32_t ph = (uint32_t)j & 1u;
+        // S^T = KV^T Q over the channels
+        for (int m = 0; m < ncb; m++) {
+          mbar_wait(&kv_full[m], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) {      // 16 channels (16 rows of 128 B) per MMA
+            const uint64_t ad = kv_mn + (uint64_t)((m * CB_BYTES + ks * 2048) >> 4);
+            const uint64_t bd = q_mn + (uint64_t)(((m * 8 + ks) * 2048) >> 4);
+            mma_bf16(tmem + S_COL, ad, bd, idesc_s, (m | ks) != 0 ? 1u : 0u);
+          }
+        }
+        mma_commit(s_full);
+        // O^T += KV E^T over the keys of the tile
+        mbar_wait(p_full, ph);
+        tc_fence_after();
+        for (int m = 0; m < ncb; m++) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) {      // 16 keys (32 B inside the 128-B row; key half = ks / 4) per MMA
+            const uint64_t ad = kv_k + (uint64_t)((m * CB_BYTES + (ks >> 2) * KH_BYTES + (ks & 3) * 32) >> 4);
+            const uint64_t bd = p_mn + (uint64_t)((ks * 2048) >> 4);
+            mma_bf16(tmem + (uint32_t)(m * QT), ad, bd, idesc_o, (j | ks) != 0 ? 1u : 0u);
+          }
+          mma_commit(&kv_free[m]);              // channel block m of this tile may be overwritten
+        }
+      }
+      mma_commit(o_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ exp / row sums / epilogue (8 warps)
+    const int sw = warp - 2;
+    const int qr = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = sw >> 2;                   // which 32 of the 64 query columns
+    const int krow = qr * 32 + lane;            // key row inside the tile == TMEM lane
+    float sh[32], sum[32];
+#pragma unroll
+    for (int e = 0; e < 32; e++) { sh[e] = s_shift[half * 32 + e]; sum[e] = 0.f; }
+    uint8_t* prow = sP + krow * 128;
+    const uint32_t taddr = tmem + ((uint32_t)(qr * 32) << 16) + S_COL + (uint32_t)(half * 32);
+    for (int j = 0; j < p.tiles; j++) {
+      mbar_wait(s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(taddr, v);
+      tmem_ld_wait();
+      const bool valid = j * KT + krow < p.N;
+      uint32_t pk[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const float x0 = valid ? ex2(fmaf(v[e], p.scale, -sh[e])) : 0.f;
+        const float x1 = valid ? ex2(fmaf(v[e + 1], p.scale, -sh[e + 1])) : 0.f;
+        const __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(&b);
+        pk[e >> 1] = u;
+        sum[e] += __uint_as_float(u << 16);
+        sum[e + 1] += __uint_as_float(u & 0xffff0000u);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int chunk = (half * 4 + i) ^ (krow & 7);
+        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // r[q] = sum over the 128 key lanes: transpose-reduce inside the warp (lane l ends with column l), then across the 4 warps
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+      for (int i = 0; i < off; i++) {
+        const bool up = (lane & off) != 0;
+        const float keep = up ? sum[i + off] : sum[i];
+        const float send = up ? sum[i] : sum[i + off];
+        sum[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    s_red[sw][lane] = sum[0];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (sw == 0 || sw == 4) {
+      const int q = half * 32 + lane;
+      const float r = s_red[half * 4][lane] + s_red[half * 4 + 1][lane] + s_red[half * 4 + 2][lane] + s_red[half * 4 + 3][lane];
+      s_inv[q] = 1.f / r;
+      if (q0 + q < p.N) p.lse[(long long)z * p.N + q0 + q] = (s_shift[q] + log2f(r)) * 0.6931471805599453f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float inv[32];
+#pragma unroll
+    for (int e = 0; e < 32; e++) inv[e] = s_inv[half * 32 + e];
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int qb = q0 + half * 32;
+    const bool vec = (p.N & 3) == 0 && qb + 32 <= p.N;
+    for (int m = 0; m < ncb; m++) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(qr * 32) << 16) + (uint32_t)(m * QT + half * 32), v);
+      tmem_ld_wait();
+      float* orow = p.out + ((long long)p.oidx[z] * p.C + (m * 128 + krow)) * p.N + qb;
+      if (vec) {
+        float4* o4 = reinterpret_cast<float4*>(orow);
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+          o4[e] = make_float4(v[4 * e] * inv[4 * e], v[4 * e + 1] * inv[4 * e + 1], v[4 * e + 2] * inv[4 * e + 2], v[4 * e + 3] * inv[4 * e + 3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; e++)
+          if (qb + e < p.N) orow[e] = v[e] * inv[e];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// fp32 [F][C][N] -> bf16 [F][C][ld] (round to nearest even) + squared column norms (atomicAdd over the channel slices).
+// block (32, 8): 32 lanes x VEC consecutive positions, 8 channel rows per step; grid (positions, channel slices, F).
+template <int VEC>
+__global__ void __launch_bounds__(256) cast_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, float* __restrict__ normsq,
+                                                        int C, int N, int ld, int c_per_block) {
+  const int f = blockIdx.z;
+  const int n = (blockIdx.x * 32 + threadIdx.x) * VEC;
+  const int c0 = blockIdx.y * c_per_block;
+  const int c1 = min(C, c0 + c_per_block);
+  __shared__ float part[8][32 * VEC];
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; i++) acc[i] = 0.f;
+  if (n < N) {
+    const float* xp = x + ((long long)f * C) * N + n;
+    __nv_bfloat16* yp = y + ((long long)f * C) * ld + n;
+#pragma unroll 4
+    for (int c = c0 + threadIdx.y; c < c1; c += 8) {
+      if constexpr (VEC == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xp + (long long)c * N);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&lo);
+        u.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(yp + (long long)c * ld) = u;
+        acc[0] = fmaf(v.x, v.x, acc[0]); acc[1] = fmaf(v.y, v.y, acc[1]); acc[2] = fmaf(v.z, v.z, acc[2]); acc[3] = fmaf(v.w, v.w, acc[3]);
+      } else {
+        const float v = xp[(long long)c * N];
+        yp[(long long)c * ld] = __float2bfloat16_rn(v);
+        acc[0] = fmaf(v, v, acc[0]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; i++) part[threadIdx.y][threadIdx.x * VEC + i] = acc[i];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 32 * VEC) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += part[k][t];
+    const int nn = blockIdx.x * 32 * VEC + t;
+    if (nn < N) atomicAdd(normsq + (long long)f * N + nn, s);
+  }
+}
+
+__global__ void maxnorm_kernel(const float* __restrict__ normsq, float* __restrict__ maxnorm, int N) {
+  __shared__ float sh[32];
+  float m = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) m = fmaxf(m, normsq[(long long)blockIdx.x * N + n]);
+  m = block_max(m, sh);
+  if (threadIdx.x == 0) maxnorm[blockIdx.x] = sqrtf(m);
+}
+
+__global__ void cast_flat_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int pitch8(int N) { return (N + 7) & ~7; }
+
+}  // namespace
+
+bool umma_coattn_supported(int C, int N) { return C % 128 == 0 && C >= 128 && C <= CMAX && N >= 1; }
+
+size_t umma_coattn_workspace_bytes(int F, int C, int N) {
+  return align256((size_t)F * C * pitch8(N) * 2) + align256((size_t)F * N * 4 + (size_t)F * 4) + 256;
+}
+
+int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, float* lse,
+                    int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DCNET_CHECK_ARG(umma_coattn_supported(C, N), "coattn_fwd (fused): C must be a multiple of 128, <= 512");
+  DCNET_CHECK_ARG(ws && ws_bytes >= umma_coattn_workspace_bytes(F, C, N), "coattn_fwd (fused): workspace too small");
+  DCNET_CHECK_ARG(reinterpret_cast<uintptr_t>(frames) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(ws) % 256 == 0, "coattn_fwd (fused): pointers must be 16-byte aligned (workspace 256)");
+  DCNET_CHECK_ARG(nprob <= 65535 && F <= 65535, "coattn_fwd (fused): too many problems");
+  const int ld = pitch8(N);
+  __nv_bfloat16* fb16 = reinterpret_cast<__nv_bfloat16*>(ws);
+  float* normsq = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align256((size_t)F * C * ld * 2));
+  float* maxnorm = normsq + (size_t)F * N;
+  DCNET_CUDA(cudaMemsetAsync(normsq, 0, (size_t)F * N * 4, st), "coattn_fwd.memset");
+  const int c_per_block = 128;
+  if (N % 4 == 0) {
+    dim3 g(ceil_div(N, 128), ceil_div(C, c_per_block), F);
+    cast_norm_kernel<4><<<g, dim3(32, 8), 0, st>>>(frames, fb16, normsq, C, N, ld, c_per_block);
+  } else {
+    dim3 g(ceil_div(N, 32), ceil_div(C, c_per_block), F);
+    cast_norm_kernel<1><<<g, dim3(32, 8), 0, st>>>(frames, fb16, normsq, C, N, ld, c_per_block);
+  }
+  DCNET_LAUNCH_OK("coattn_fwd.cast");
+  maxnorm_kernel<<<F, 256, 0, st>>>(normsq, maxnorm, N);
+  DCNET_LAUNCH_OK("coattn_fwd.maxnorm");
+
+  CUtensorMap map;
+  const int r = make_tmap(&map, fb16, 2, (uint64_t)N, (uint64_t)C, (uint64_t)F, (uint64_t)ld, (uint64_t)C * ld, 64, 128);
+  if (r != 0) return dcnet_set_error(-3, "coattn_fwd (fused): cuTensorMapEncodeTiled failed (%d)", r);
+  CoP p{};
+  p.qa = qa; p.kb = kb; p.oidx = oidx; p.out = out; p.lse = lse; p.normsq = normsq; p.maxnorm = maxnorm;
+  p.N = N; p.C = C; p.tiles = ceil_div(N, KT);
+  p.scale = tau * 1.4426950408889634f;
+  DCNET_CUDA(cudaFuncSetAttribute(coattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM), "coattn_fwd.attr");
+  dim3 grid(ceil_div(N, QT), nprob);
+  coattn_fused_kernel<<<grid, NTHREADS, FUSED_SMEM, st>>>(map, p);
+  DCNET_LAUNCH_OK("coattn_fused");
+  return 0;
+}
+
+extern "C" int dcnet_cast_bf16(const float* x, void* y, long long n, void* stream) {
+  DCNET_CHECK_ARG(x && y && n >= 0, "cast_bf16: bad arguments");
+  if (n == 0) return 0;
+  long long g = (n + 255) / 256;
+  cast_flat_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
+  DCNET_LAUNCH_OK("cast_bf16");
+  return 0;
 }

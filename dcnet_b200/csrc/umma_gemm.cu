@@ -20,9 +20,20 @@ using namespace umma;
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 32;               // tf32 elements per stage along the reduction = one 128-byte swizzle row
-constexpr int A_BYTES = BM * BK * 4; // 16 KiB
-constexpr int BLK_BYTES = 32 * BK * 4;   // one MN-major block: 32 (mn) x BK (k rows) = 4 KiB
+constexpr int A_BYTES = BM * 128;    // 16 KiB: 128 rows x one 128-byte swizzle row (32 tf32 or 64 bf16 along the reduction)
+// Element-size dependent geometry (EB = 4: fp32 read as TF32, EB = 2: bf16):
+//   BK       reduction elements per stage = 128 B / EB (32 | 64); one MMA consumes 32 B of K (8 tf32 | 16 bf16) -> 4 MMAs per stage
+//   MN-major operands are stored as blocks of (128 B along MN) x (BK reduction rows): 4 KiB | 8 KiB, LBO = block size.
+//   tf32 MN-major must use SWIZZLE_128B_BASE32B (4-row groups, SBO 512 B); bf16 uses plain SWIZZLE_128B (8-row groups, SBO 1024 B).
+template <int EB> struct Geo {
+  static constexpr int BK = 128 / EB;
+  static constexpr int MN_ELEMS = 128 / EB;            // MN elements per block
+  static constexpr int BLK_BYTES = BK * 128;
+  static constexpr int KSTEP_ROWS = 32 / EB;           // reduction rows per MMA
+  static constexpr uint32_t MN_LAYOUT = (EB == 4) ? 1u : 2u;
+  static constexpr uint32_t MN_SBO = (EB == 4) ? 512u : 1024u;
+  static constexpr uint32_t FMT = (EB == 4) ? FMT_TF32 : FMT_BF16;
+};
 
 struct GemmP {
   int M_valid, N_valid;     // store predicates
@@ -41,11 +52,14 @@ struct GemmP {
   float* sum; float* sumsq; // per-row (channel) sums of the stored values and their squares (BatchNorm statistics)
 };
 
-template <bool A_MN, bool B_MN, int BN, int STAGES>
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapB2, const GemmP p) {
-  constexpr int B_BYTES = BN * BK * 4;
+  using G = Geo<EB>;
+  constexpr int BK = G::BK;
+  constexpr int BLK_BYTES = G::BLK_BYTES;
+  constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,7 +101,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         uint8_t* sB = sA + A_BYTES;
         if constexpr (A_MN) {
 #pragma unroll
-          for (int j = 0; j < BM / 32; j++) tma_load_3d(sA + j * BLK_BYTES, &mapA, &full[s], m0 + 32 * j, it * BK, a_b);
+          for (int j = 0; j < BM / G::MN_ELEMS; j++) tma_load_3d(sA + j * BLK_BYTES, &mapA, &full[s], m0 + G::MN_ELEMS * j, it * BK, a_b);
         } else {
           tma_load_3d(sA, &mapA, &full[s], it * BK, m0, a_b);
         }
@@ -96,7 +110,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const CUtensorMap* mb = src2 ? &mapB2 : &mapB;
           const int kc = (src2 ? it - p.k_split : it) * BK;
 #pragma unroll
-          for (int j = 0; j < BN / 32; j++) tma_load_3d(sB + j * BLK_BYTES, mb, &full[s], n0 + 32 * j, kc, b_b);
+          for (int j = 0; j < BN / G::MN_ELEMS; j++) tma_load_3d(sB + j * BLK_BYTES, mb, &full[s], n0 + G::MN_ELEMS * j, kc, b_b);
         } else {
           const bool src2 = p.n_split > 0 && n0 >= p.n_split;
           tma_load_3d(sB, src2 ? &mapB2 : &mapB, &full[s], it * BK, src2 ? n0 - p.n_split : n0, b_b);
@@ -105,7 +119,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else if (warp == 5) {
     if (elect_one()) {
-      constexpr uint32_t idesc = instr_desc(FMT_TF32, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = instr_desc(G::FMT, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       for (int it = 0; it < p.k_iters; it++) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -114,13 +128,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const uint32_t sA = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sB = sA + A_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ks++) {     // one MMA = 8 tf32 along K = 32 bytes
+        for (int ks = 0; ks < 4; ks++) {          // one MMA = 32 bytes of K (8 tf32 / 16 bf16)
           // K-major : SWIZZLE_128B; +32 B inside the 128-B swizzle row; rows 128 B apart, 8-row atoms 1024 B apart
-          // MN-major: SWIZZLE_128B_BASE32B (tf32); +8 k-rows = +1024 B; 4-k-row groups 512 B apart (SBO); MN blocks of 32
-          //           elements BLK_BYTES apart (LBO)
-          const uint64_t ad = A_MN ? smem_desc(sA + ks * 1024, BLK_BYTES, 512, 1) : smem_desc(sA + ks * 32, 16, 1024, 2);
-          const uint64_t bd = B_MN ? smem_desc(sB + ks * 1024, BLK_BYTES, 512, 1) : smem_desc(sB + ks * 32, 16, 1024, 2);
-          mma_tf32(tmem_base, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+          // MN-major: +KSTEP_ROWS reduction rows = +KSTEP_ROWS*128 B; k-row groups MN_SBO apart; MN blocks BLK_BYTES apart (LBO)
+          constexpr uint32_t kadv = G::KSTEP_ROWS * 128;
+          const uint64_t ad = A_MN ? smem_desc(sA + ks * kadv, BLK_BYTES, G::MN_SBO, G::MN_LAYOUT) : smem_desc(sA + ks * 32, 16, 1024, 2);
+          const uint64_t bd = B_MN ? smem_desc(sB + ks * kadv, BLK_BYTES, G::MN_SBO, G::MN_LAYOUT) : smem_desc(sB + ks * 32, 16, 1024, 2);
+          if constexpr (EB == 4) mma_tf32(tmem_base, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+          else mma_bf16(tmem_base, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
         }
         mma_commit(&empty[s]);      // slot reusable once these MMAs have read it
       }
@@ -179,10 +194,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 5) tmem_dealloc(tmem_base, BN);
 }
 
-template <bool A_MN, bool B_MN, int BN, int STAGES>
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
 int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const GemmP& p, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_BYTES + BN * BK * 4) + 1024 + 256;
-  auto kern = umma_gemm_kernel<A_MN, B_MN, BN, STAGES>;
+  constexpr int smem = STAGES * (A_BYTES + BN * 128) + 1024 + 256;
+  auto kern = umma_gemm_kernel<A_MN, B_MN, BN, STAGES, EB>;
   DCNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "umma_gemm.attr");   // per device
   kern<<<grid, 192, smem, st>>>(ma, mb, mb2, p);
   DCNET_LAUNCH_OK("umma_gemm");
@@ -197,15 +212,17 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
 //   MN-major use: rows = the reduction index, cols = the M (or N) index
 // ---------------------------------------------------------------------------------------------------------------------
 static bool operand_ok(const UmmaOperand& o) {
-  return o.ptr && (reinterpret_cast<uintptr_t>(o.ptr) % 16 == 0) && (o.ld % 4 == 0) && (o.batch_stride % 4 == 0) && o.rows > 0 && o.cols > 0;
+  const int per16 = o.bf16 ? 8 : 4;     // elements per 16 bytes
+  return o.ptr && (reinterpret_cast<uintptr_t>(o.ptr) % 16 == 0) && (o.ld % per16 == 0) && (o.batch_stride % per16 == 0) && o.rows > 0 && o.cols > 0;
 }
 
 static int make_operand_map(CUtensorMap* m, const UmmaOperand& o, int tile_rows_kmajor) {
   const uint64_t nb = o.batches > 0 ? (uint64_t)o.batches : 1;
   const uint64_t bs = o.batches > 0 ? (uint64_t)o.batch_stride : (uint64_t)(o.rows * o.ld);
-  // box: K-major {32 k, tile rows}; MN-major {32 mn, 32 k rows}
-  const int r = make_tmap_f32(m, o.ptr, (uint64_t)o.cols, (uint64_t)o.rows, nb, (uint64_t)o.ld, bs, 32, o.mn_major ? 32u : (uint32_t)tile_rows_kmajor,
-                              /*atom32b=*/o.mn_major);
+  const uint32_t inner = o.bf16 ? 64u : 32u;        // 128 bytes
+  // box: K-major {128 B of k, tile rows}; MN-major {128 B of mn, BK reduction rows}
+  const int r = make_tmap(m, o.ptr, o.bf16 ? 2 : 4, (uint64_t)o.cols, (uint64_t)o.rows, nb, (uint64_t)o.ld, bs, inner,
+                          o.mn_major ? inner : (uint32_t)tile_rows_kmajor, /*atom32b=*/o.mn_major && !o.bf16);
   if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", r, o.rows, o.cols, o.ld);
   return 0;
 }
@@ -219,6 +236,8 @@ bool umma_gemm_usable(const UmmaOperand& A, const UmmaOperand& B, const UmmaOper
 int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int M, int N, int K, int k_split_elems, int n_split,
               int batch, const UmmaEpilogue& e, cudaStream_t st) {
   DCNET_CHECK_ARG(umma_gemm_usable(A, B, B2, K), "umma_gemm: operand not TMA-compatible (16-B aligned base, row pitch multiple of 4 floats)");
+  DCNET_CHECK_ARG(A.bf16 == B.bf16 && (!B2 || B2->bf16 == B.bf16), "umma_gemm: mixed operand element types");
+  const int BK = A.bf16 ? 64 : 32;
   DCNET_CHECK_ARG(k_split_elems % BK == 0, "umma_gemm: k_split must be a multiple of %d", BK);
   DCNET_CHECK_ARG(batch >= 1 && batch <= 65535, "umma_gemm: batch %d", batch);
   // wide tiles cut the L2->SM operand traffic per FLOP (the kernel is L2-bound at 128x128, profiles/r1b_ncu_full_umma_gemm.txt);
@@ -243,9 +262,14 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   const int am = A.mn_major ? 1 : 0, bm = B.mn_major ? 1 : 0;
 #define DISPATCH(AM, BMJ)                                                                   \
   if (am == AM && bm == BMJ) {                                                              \
-    if (BN == 64) return launch_cfg<AM, BMJ, 64, 4>(ma, mb, mb2, p, grid, st);              \
-    if (BN == 256) return launch_cfg<AM, BMJ, 256, 4>(ma, mb, mb2, p, grid, st);            \
-    return launch_cfg<AM, BMJ, 128, 3>(ma, mb, mb2, p, grid, st);                           \
+    if (A.bf16) {                                                                           \
+      if (BN == 64) return launch_cfg<AM, BMJ, 64, 4, 2>(ma, mb, mb2, p, grid, st);         \
+      if (BN == 256) return launch_cfg<AM, BMJ, 256, 4, 2>(ma, mb, mb2, p, grid, st);       \
+      return launch_cfg<AM, BMJ, 128, 3, 2>(ma, mb, mb2, p, grid, st);                      \
+    }                                                                                       \
+    if (BN == 64) return launch_cfg<AM, BMJ, 64, 4, 4>(ma, mb, mb2, p, grid, st);           \
+    if (BN == 256) return launch_cfg<AM, BMJ, 256, 4, 4>(ma, mb, mb2, p, grid, st);         \
+    return launch_cfg<AM, BMJ, 128, 3, 4>(ma, mb, mb2, p, grid, st);                        \
   }
   DISPATCH(0, 0) DISPATCH(0, 1) DISPATCH(1, 0) DISPATCH(1, 1)
 #undef DISPATCH
@@ -260,8 +284,22 @@ extern "C" int dcnet_gemm_tf32(const float* A, int a_mn_major, long long lda, lo
                                void* stream) {
   DCNET_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tf32: bad arguments");
   // K-major operand: [rows = M|N][cols = K]; MN-major operand: [rows = K][cols = M|N]
-  UmmaOperand a{A, a_mn_major ? K : M, a_mn_major ? M : K, lda, strideA, batch, a_mn_major != 0};
-  UmmaOperand b{B, b_mn_major ? K : N, b_mn_major ? N : K, ldb, strideB, batch, b_mn_major != 0};
+  UmmaOperand a{A, a_mn_major ? K : M, a_mn_major ? M : K, lda, strideA, batch, a_mn_major != 0, false};
+  UmmaOperand b{B, b_mn_major ? K : N, b_mn_major ? N : K, ldb, strideB, batch, b_mn_major != 0, false};
+  UmmaEpilogue e{};
+  e.out = C; e.ldo = ldc; e.so_b = strideC; e.alpha = alpha; e.atomic = atomic;
+  return umma_gemm(a, b, nullptr, M, N, K, 0, 0, batch, e, as_stream(stream));
+}
+
+
+// same contraction with bf16 operands (kind::f16, fp32 accumulation); A/B point to __nv_bfloat16 data, pitches in elements
+extern "C" int dcnet_gemm_bf16(const void* A, int a_mn_major, long long lda, long long strideA,
+                               const void* B, int b_mn_major, long long ldb, long long strideB,
+                               float* C, long long ldc, long long strideC, int M, int N, int K, int batch, float alpha, int atomic,
+                               void* stream) {
+  DCNET_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_bf16: bad arguments");
+  UmmaOperand a{(const float*)A, a_mn_major ? K : M, a_mn_major ? M : K, lda, strideA, batch, a_mn_major != 0, true};
+  UmmaOperand b{(const float*)B, b_mn_major ? K : N, b_mn_major ? N : K, ldb, strideB, batch, b_mn_major != 0, true};
   UmmaEpilogue e{};
   e.out = C; e.ldo = ldc; e.so_b = strideC; e.alpha = alpha; e.atomic = atomic;
   return umma_gemm(a, b, nullptr, M, N, K, 0, 0, batch, e, as_stream(stream));

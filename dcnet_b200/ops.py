@@ -75,6 +75,24 @@ def gemm_tf32(A, B, a_mn, b_mn, M, N, K, alpha=1.0):
     return C
 
 
+def cast_bf16(x):
+    """fp32 -> bf16 (round to nearest even) with the library's own kernel"""
+    x = _c(x, name="x")
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.call("dcnet_cast_bf16", _p(x), _p(y), x.numel(), _st())
+    return y
+
+
+def gemm_bf16(A, B, a_mn, b_mn, M, N, K, alpha=1.0):
+    """tcgen05 kind::f16 GEMM on bf16 operands (same operand conventions as gemm_tf32), fp32 result."""
+    A, B = _c(A, torch.bfloat16, "A"), _c(B, torch.bfloat16, "B")
+    batch = A.shape[0]
+    C = torch.empty(batch, M, N, device=A.device, dtype=F32)
+    _lib.call("dcnet_gemm_bf16", _p(A), int(a_mn), A.shape[2], A.shape[1] * A.shape[2], _p(B), int(b_mn), B.shape[2], B.shape[1] * B.shape[2],
+              _p(C), N, M * N, M, N, K, batch, alpha, 0, _st())
+    return C
+
+
 def pix2text(x, fa):
     """x [B,C,N], fa [B,C] -> sim [B,N]   (forward only; inference / clip path)"""
     x, fa = _c(x.detach(), name="x"), _c(fa.detach(), name="fa")
@@ -278,7 +296,7 @@ class _ConvBNAct(torch.autograd.Function):
         return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None)
 
 
-EXACT_FP32, TENSOR_TF32 = 0, 1
+EXACT_FP32, TENSOR_TF32, TENSOR_BF16_FUSED = 0, 1, 2
 
 
 def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
@@ -299,7 +317,7 @@ class _CoAttn(torch.autograd.Function):
         out = torch.empty(n_out, C, N, device=frames.device, dtype=F32) if n_out == nprob else \
             torch.zeros(n_out, C, N, device=frames.device, dtype=F32)
         lse = torch.empty(nprob, N, device=frames.device, dtype=F32)
-        nbytes = _lib.lib().dcnet_coattn_workspace_bytes(nprob, C, N)
+        nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, precision)
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
         _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, precision,
                   _p(ws), nbytes, _st())
@@ -315,7 +333,7 @@ class _CoAttn(torch.autograd.Function):
         nprob = qa.numel()
         dout = _c(dout, name="dout")
         dframes = torch.zeros_like(frames)
-        nbytes = _lib.lib().dcnet_coattn_workspace_bytes(nprob, C, N)
+        nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, ctx.precision)
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
         _lib.call("dcnet_coattn_bwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout), _p(dframes),
                   C, N, ctx.tau, ctx.precision, _p(ws), nbytes, _st())

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCNET_ABI_VERSION 2
+#define DCNET_ABI_VERSION 3
 #define DCNET_API __attribute__((visibility("default")))
 
 /* ---- library ---------------------------------------------------------------------------------------- */
@@ -55,6 +55,14 @@ DCNET_API int dcnet_gemm_tf32(const float* A, int a_mn_major, long long lda, lon
                               const float* B, int b_mn_major, long long ldb, long long strideB,
                               float* C, long long ldc, long long strideC, int M, int N, int K, int batch, float alpha, int atomic,
                               void* stream);
+
+/* same contraction with bf16 operands (tcgen05 kind::f16, fp32 accumulation).  A, B: __nv_bfloat16 data; pitches / strides in
+ * elements, multiples of 8.  dcnet_cast_bf16 converts fp32 -> bf16 with round-to-nearest-even.                            */
+DCNET_API int dcnet_gemm_bf16(const void* A, int a_mn_major, long long lda, long long strideA,
+                              const void* B, int b_mn_major, long long ldb, long long strideB,
+                              float* C, long long ldc, long long strideC, int M, int N, int K, int batch, float alpha, int atomic,
+                              void* stream);
+DCNET_API int dcnet_cast_bf16(const float* x, void* y, long long n, void* stream);
 
 /* ---- a1/a2/a6/a8: 1x1 conv (no bias) + BatchNorm + ReLU (+ L2 norm over channels) ---------------------
  * replaces ConvBatchNormReLU (model/darknet.py:118-156) as used by mapping_visu (:356-359), corr_conv
@@ -125,8 +133,12 @@ DCNET_API int dcnet_coord_map(float* coord, int h, int w, void* stream);
  * One "problem" i is one direction: queries = frame qa[i], keys/values = frame kb[i] of frames [F,C,N]:
  *   S = Fa^T Fb,  P = softmax_j(tau S),  out[oidx[i]] = Fb P^T  ([C,N]),  lse[i][n] = log sum_j exp(tau S[n,j]).
  * A training pair p is the two problems (2p,2p+1) and (2p+1,2p); the test-time clip path uses the centre
- * direction only.  S / P never leave the chip in the tcgen05 path; workspace is scratch for the rest.     */
-DCNET_API size_t dcnet_coattn_workspace_bytes(int nprob, int C, int N);
+ * direction only.  precision: 0 = exact fp32 (CUDA cores), 1 = tcgen05 TF32 GEMMs with S/P in workspace,
+ * 2 = fused tcgen05 kernel (bf16 operands, fp32 accumulation in TMEM): S / P never leave the SM; workspace
+ * holds the bf16 staging of the maps.  The fused forward assumes every logit of a row lies within ~80 of
+ * tau |Fa_q| max_k |Fb_k| (always true for the unit-norm maps of the model, model/DCNet_model.py:359).
+ * The backward of precision 2 is the precision-1 composition.                                            */
+DCNET_API size_t dcnet_coattn_workspace_bytes(int F, int nprob, int C, int N, int precision);
 DCNET_API int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                float* out, int n_out, float* lse, int C, int N, float tau, int precision,
                                void* workspace, size_t workspace_bytes, void* stream);
