@@ -154,7 +154,7 @@ def run_c4(args, wl, rank, world, dev, dist):
     def run_step():
         with torch.no_grad():
             fv = hp.net.map_visual(static)
-            outs = [ops.coattention(fv[s], qa, kb, tau=10.0, precision=hp.net.precision) for s in range(3)]
+            outs = [ops.coattention(fv[s], qa, kb, tau=10.0, precision=hp.net.coattn_precision) for s in range(3)]
             return torch.stack([o.sum() for o in outs])
 
     n0 = _lib.launch_count(); res = run_step(); launches = _lib.launch_count() - n0
@@ -406,21 +406,29 @@ def main():
         fr = torch.nn.functional.normalize(torch.randn(B, C_EMB, N2, device=dev).abs(), dim=1)
         qa = torch.arange(B, device=dev, dtype=torch.int32)
         kb = qa ^ 1
+        # the fused tcgen05 kernel alone (CUDA events on the launching stream), L2 flushed before every launch; the bf16
+        # staging pass (cast + column norms) is timed separately and reported as stage_ms
+        staged = ops.coattn_stage(fr)
+        o_buf = torch.empty(B, C_EMB, N2, device=dev); l_buf = torch.empty(B, N2, device=dev)
         for _ in range(3):
-            ops.coattention(fr, qa, kb, tau=10.0)
+            ops.coattn_fused(staged, fr.shape, qa, kb, tau=10.0, out=o_buf, lse=l_buf)
         reps = 10
-        tt = 0.0
+        tt = ts_ = 0.0
         for _ in range(reps):
             flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); ops.coattention(fr, qa, kb, tau=10.0); b.record()
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record(); staged = ops.coattn_stage(fr); b.record()
+            ops.coattn_fused(staged, fr.shape, qa, kb, tau=10.0, out=o_buf, lse=l_buf); c.record()
             torch.cuda.synchronize()
-            tt += a.elapsed_time(b)
+            ts_ += a.elapsed_time(b); tt += b.elapsed_time(c)
         ms = tt / reps
         flops = 6.0 * C_EMB * N2 * N2 * pairs            # 6*c*N^2 per pair forward (both directions share S)
         ach = flops / (ms * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="coattn_fwd (finest scale, N=%d, %d pairs)" % (N2, pairs), achieved=ach, peak=peaks["tensor_burst"],
-                    unit="TFLOP/s", frac=ach / peaks["tensor_burst"], traffic=None, ms=ms, peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
+        roof = dict(bound="tensor", kernel="coattn_fused_kernel (finest scale, N=%d, %d pairs = %d directed problems, one launch)" % (N2, pairs, B),
+                    achieved=ach, peak=peaks["tensor_burst"], unit="TFLOP/s", frac=ach / peaks["tensor_burst"], traffic=None, ms=ms,
+                    stage_ms=ts_ / reps, executed_tflops=ach * 4.0 / 3.0,
+                    note="algorithmic 6*c*N^2 per pair; the kernel executes 8*c*N^2 (S recomputed per direction)",
+                    peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
         if world == 1 and not args.no_cpu_baseline:
             from oracle import dcnet_oracle as O
             cores = os.cpu_count() or 1

@@ -5,7 +5,7 @@
 // dcnet_coattn_fwd when the shape is supported.
 #include "common.cuh"
 
-int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, float* lse,
+int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, int n_out, float* lse,
                     int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st);  // umma_coattn.cu
 bool umma_coattn_supported(int C, int N);
 size_t umma_coattn_workspace_bytes(int F, int C, int N);
@@ -76,7 +76,7 @@ extern "C" int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const
   if (nprob == 0) return 0;
   cudaStream_t st = as_stream(stream);
   if (precision == 2 && umma_coattn_supported(C, N))
-    return umma_coattn_fwd(frames, F, qa, kb, oidx, nprob, out, lse, C, N, tau, workspace, workspace_bytes, st);
+    return umma_coattn_fwd(frames, F, qa, kb, oidx, nprob, out, n_out, lse, C, N, tau, workspace, workspace_bytes, st);
   DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(F, nprob, C, N, precision), "coattn_fwd: workspace too small");
   float* S = (float*)workspace;
   const long long CN = (long long)C * N, NN = (long long)N * N;

@@ -47,7 +47,13 @@ struct CoP {
   const float* maxnorm;    // [F]     max column norm per frame
   int N, C, tiles;
   float scale;             // tau * log2(e)
+  int tma_store;           // 1: epilogue through swizzled smem + TMA store (needs N % 4 == 0), 0: direct stores
+  int variant;             // experiment switches of the profiling entry point (0 in production)
+  long long* trace;        // optional [CTA][tile][8] clock64 stamps (debug / profiling entry point); nullptr = off
 };
+#define TRACE(slot) do { if (p.trace) p.trace[((long long)(blockIdx.y * gridDim.x + blockIdx.x) * (p.tiles + 1) + j) * 8 + (slot)] = clock64(); } while (0)
+#define TRACE_CTA(slot, val) do { if (p.trace) p.trace[((long long)(blockIdx.y * gridDim.x + blockIdx.x) * (p.tiles + 1) + p.tiles) * 8 + (slot)] = (val); } while (0)
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -56,7 +62,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const CoP p) {
+coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_out, const CoP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -73,6 +79,7 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const CoP p) {
   uint64_t* o_full = &bars[11];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 64) { TRACE_CTA(0, clock64()); TRACE_CTA(4, gtimer()); }
   const int z = blockIdx.y;
   const int q0 = blockIdx.x * QT;
   const int fa = p.qa[z], fb = p.kb[z];
@@ -126,12 +133,14 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const CoP p) {
       const uint64_t q_mn = smem_desc(smem_u32(sQ), KH_BYTES, 1024, 2);
       const uint64_t p_mn = smem_desc(smem_u32(sP), KH_BYTES, 1024, 2);
       mbar_wait(q_full, 0);
+      TRACE_CTA(1, clock64());
       for (int j = 0; j < p.tiles; j++) {
         const uint32_t ph = (uint32_t)j & 1u;
         // S^T = KV^T Q over the channels
         for (int m = 0; m < ncb; m++) {
           mbar_wait(&kv_full[m], ph);
           tc_fence_after();
+          TRACE(m);
 #pragma unroll
           for (int ks = 0; ks < 8; ks++) {      // 16 channels (16 rows of 128 B) per MMA
             const uint64_t ad = kv_mn + (uint64_t)((m * CB_BYTES + ks * 2048) >> 4);
@@ -140,9 +149,11 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const CoP p) {
           }
         }
         mma_commit(s_full);
+        TRACE(4);
         // O^T += KV E^T over the keys of the tile
         mbar_wait(p_full, ph);
         tc_fence_after();
+        TRACE(5);
         for (int m = 0; m < ncb; m++) {
 #pragma unroll
           for (int ks = 0; ks < 8; ks++) {      // 16 keys (32 B inside the 128-B row; key half = ks / 4) per MMA
@@ -169,6 +180,7 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const CoP p) {
     for (int j = 0; j < p.tiles; j++) {
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
+      if (threadIdx.x == 64) TRACE(6);
       float v[32];
       tmem_ld32(taddr, v);
       tmem_ld_wait();
@@ -193,6 +205,7 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const CoP p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (threadIdx.x == 64) TRACE(7);
     }
     // r[q] = sum over the 128 key lanes: transpose-reduce inside the warp (lane l ends with column l), then across the 4 warps
 #pragma unroll
@@ -219,7 +232,30 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const CoP p) {
     for (int e = 0; e < 32; e++) inv[e] = s_inv[half * 32 + e];
     mbar_wait(o_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) TRACE_CTA(2, clock64());
     const int qb = q0 + half * 32;
+    if (p.tma_store) {
+      // O^T / r -> 128-byte-swizzled staging tiles [128 c rows][32 q fp32] in the (now idle) KV buffer -> TMA store; columns
+      // beyond N are clipped by the tensor map
+      for (int m = 0; m < ncb; m++) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(qr * 32) << 16) + (uint32_t)(m * QT + half * 32), v);
+        tmem_ld_wait();
+        uint8_t* srow = sKV + (m * 2 + half) * KH_BYTES + krow * 128;
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+          *reinterpret_cast<float4*>(srow + ((e ^ (krow & 7)) * 16)) =
+              make_float4(v[4 * e] * inv[4 * e], v[4 * e + 1] * inv[4 * e + 1], v[4 * e + 2] * inv[4 * e + 2], v[4 * e + 3] * inv[4 * e + 3]);
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          tma_store_3d(&map_out, sKV + (m * 2) * KH_BYTES, q0, m * 128, p.oidx[z]);
+          tma_store_3d(&map_out, sKV + (m * 2 + 1) * KH_BYTES, q0 + 32, m * 128, p.oidx[z]);
+          tma_store_commit();
+        }
+      }
+      if (threadIdx.x == 64) tma_store_wait_read();
+    } else {
     const bool vec = (p.N & 3) == 0 && qb + 32 <= p.N;
     for (int m = 0; m < ncb; m++) {
       float v[32];
@@ -237,9 +273,15 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const CoP p) {
           if (qb + e < p.N) orow[e] = v[e] * inv[e];
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 64) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    TRACE_CTA(3, clock64()); TRACE_CTA(5, gtimer()); TRACE_CTA(6, (long long)smid);
+  }
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -313,18 +355,18 @@ size_t umma_coattn_workspace_bytes(int F, int C, int N) {
   return align256((size_t)F * C * pitch8(N) * 2) + align256((size_t)F * N * 4 + (size_t)F * 4) + 256;
 }
 
-int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, float* lse,
-                    int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st) {
-  DCNET_CHECK_ARG(umma_coattn_supported(C, N), "coattn_fwd (fused): C must be a multiple of 128, <= 512");
-  DCNET_CHECK_ARG(ws && ws_bytes >= umma_coattn_workspace_bytes(F, C, N), "coattn_fwd (fused): workspace too small");
-  DCNET_CHECK_ARG(reinterpret_cast<uintptr_t>(frames) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
-                  reinterpret_cast<uintptr_t>(ws) % 256 == 0, "coattn_fwd (fused): pointers must be 16-byte aligned (workspace 256)");
-  DCNET_CHECK_ARG(nprob <= 65535 && F <= 65535, "coattn_fwd (fused): too many problems");
+// staging: bf16 copy of the maps (pitch padded to 8 elements for TMA) + squared column norms + per-frame max norm
+int umma_coattn_stage(const float* frames, int F, int C, int N, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DCNET_CHECK_ARG(umma_coattn_supported(C, N), "coattn (fused): C must be a multiple of 128, <= 512");
+  DCNET_CHECK_ARG(frames && ws && ws_bytes >= umma_coattn_workspace_bytes(F, C, N), "coattn (fused): workspace too small");
+  DCNET_CHECK_ARG(reinterpret_cast<uintptr_t>(frames) % 16 == 0 && reinterpret_cast<uintptr_t>(ws) % 256 == 0,
+                  "coattn (fused): frames must be 16-byte aligned, workspace 256");
+  DCNET_CHECK_ARG(F >= 1 && F <= 65535, "coattn (fused): too many frames");
   const int ld = pitch8(N);
   __nv_bfloat16* fb16 = reinterpret_cast<__nv_bfloat16*>(ws);
   float* normsq = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align256((size_t)F * C * ld * 2));
   float* maxnorm = normsq + (size_t)F * N;
-  DCNET_CUDA(cudaMemsetAsync(normsq, 0, (size_t)F * N * 4, st), "coattn_fwd.memset");
+  DCNET_CUDA(cudaMemsetAsync(normsq, 0, (size_t)F * N * 4, st), "coattn_stage.memset");
   const int c_per_block = 128;
   if (N % 4 == 0) {
     dim3 g(ceil_div(N, 128), ceil_div(C, c_per_block), F);
@@ -333,22 +375,72 @@ int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, co
     dim3 g(ceil_div(N, 32), ceil_div(C, c_per_block), F);
     cast_norm_kernel<1><<<g, dim3(32, 8), 0, st>>>(frames, fb16, normsq, C, N, ld, c_per_block);
   }
-  DCNET_LAUNCH_OK("coattn_fwd.cast");
+  DCNET_LAUNCH_OK("coattn_stage.cast");
   maxnorm_kernel<<<F, 256, 0, st>>>(normsq, maxnorm, N);
-  DCNET_LAUNCH_OK("coattn_fwd.maxnorm");
+  DCNET_LAUNCH_OK("coattn_stage.maxnorm");
+  return 0;
+}
 
+// the fused kernel over a staged workspace
+int umma_coattn_run(const void* ws, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, float* lse,
+                    int n_out, int C, int N, float tau, cudaStream_t st, long long* trace = nullptr, int variant = 0) {
+  DCNET_CHECK_ARG(umma_coattn_supported(C, N), "coattn (fused): C must be a multiple of 128, <= 512");
+  DCNET_CHECK_ARG(ws && qa && kb && oidx && out && lse, "coattn (fused): null argument");
+  DCNET_CHECK_ARG(reinterpret_cast<uintptr_t>(out) % 16 == 0 && reinterpret_cast<uintptr_t>(ws) % 256 == 0,
+                  "coattn (fused): out must be 16-byte aligned, workspace 256");
+  DCNET_CHECK_ARG(nprob >= 1 && nprob <= 65535, "coattn (fused): too many problems");
+  const int ld = pitch8(N);
+  const __nv_bfloat16* fb16 = reinterpret_cast<const __nv_bfloat16*>(ws);
+  const float* normsq = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ws) + align256((size_t)F * C * ld * 2));
+  const float* maxnorm = normsq + (size_t)F * N;
   CUtensorMap map;
   const int r = make_tmap(&map, fb16, 2, (uint64_t)N, (uint64_t)C, (uint64_t)F, (uint64_t)ld, (uint64_t)C * ld, 64, 128);
-  if (r != 0) return dcnet_set_error(-3, "coattn_fwd (fused): cuTensorMapEncodeTiled failed (%d)", r);
+  if (r != 0) return dcnet_set_error(-3, "coattn (fused): cuTensorMapEncodeTiled failed (%d)", r);
   CoP p{};
   p.qa = qa; p.kb = kb; p.oidx = oidx; p.out = out; p.lse = lse; p.normsq = normsq; p.maxnorm = maxnorm;
   p.N = N; p.C = C; p.tiles = ceil_div(N, KT);
   p.scale = tau * 1.4426950408889634f;
-  DCNET_CUDA(cudaFuncSetAttribute(coattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM), "coattn_fwd.attr");
+  p.trace = trace;
+  p.variant = variant;
+  p.tma_store = (N % 4 == 0) ? 1 : 0;
+  CUtensorMap map_out = map;   // unused when tma_store == 0
+  if (p.tma_store) {
+    const int ro = make_tmap(&map_out, out, 4, (uint64_t)N, (uint64_t)C, (uint64_t)n_out, (uint64_t)N, (uint64_t)C * N, 32, 128);
+    if (ro != 0) return dcnet_set_error(-3, "coattn (fused): cuTensorMapEncodeTiled(out) failed (%d)", ro);
+  }
+  DCNET_CUDA(cudaFuncSetAttribute(coattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM), "coattn_fused.attr");
   dim3 grid(ceil_div(N, QT), nprob);
-  coattn_fused_kernel<<<grid, NTHREADS, FUSED_SMEM, st>>>(map, p);
+  coattn_fused_kernel<<<grid, NTHREADS, FUSED_SMEM, st>>>(map, map_out, p);
   DCNET_LAUNCH_OK("coattn_fused");
   return 0;
+}
+
+int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, int n_out, float* lse,
+                    int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DCNET_TRY(umma_coattn_stage(frames, F, C, N, ws, ws_bytes, st));
+  return umma_coattn_run(ws, F, qa, kb, oidx, nprob, out, lse, n_out, C, N, tau, st);
+}
+
+extern "C" size_t dcnet_coattn_stage_bytes(int F, int C, int N) { return (F > 0 && C > 0 && N > 0) ? umma_coattn_workspace_bytes(F, C, N) : 256; }
+
+extern "C" int dcnet_coattn_stage(const float* frames, int F, int C, int N, void* staged, size_t staged_bytes, void* stream) {
+  return umma_coattn_stage(frames, F, C, N, staged, staged_bytes, as_stream(stream));
+}
+
+extern "C" int dcnet_coattn_fused_fwd(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                      float* out, int n_out, float* lse, int C, int N, float tau, void* stream) {
+  DCNET_CHECK_ARG(F > 0 && n_out > 0 && nprob >= 0, "coattn_fused_fwd: bad arguments");
+  if (nprob == 0) return 0;
+  return umma_coattn_run(staged, F, qa, kb, oidx, nprob, out, lse, n_out, C, N, tau, as_stream(stream));
+}
+
+// profiling variant: trace [grid CTAs][key tiles][8] receives clock64 stamps of the MMA-issuing thread (0-3: channel block m of
+// the tile landed, 4: S^T issued, 5: E^T ready) and of one exp warp (6: S^T complete, 7: E^T written)
+extern "C" int dcnet_coattn_fused_fwd_trace(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                            float* out, int n_out, float* lse, int C, int N, float tau, long long* trace, int variant,
+                                            void* stream) {
+  DCNET_CHECK_ARG(F > 0 && n_out > 0 && nprob >= 1, "coattn_fused_fwd_trace: bad arguments");
+  return umma_coattn_run(staged, F, qa, kb, oidx, nprob, out, lse, n_out, C, N, tau, as_stream(stream), trace, variant);
 }
 
 extern "C" int dcnet_cast_bf16(const float* x, void* y, long long n, void* stream) {

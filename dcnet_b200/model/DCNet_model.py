@@ -145,8 +145,15 @@ class grounding_model(nn.Module):
         self._idx_cache = {}
         self._capture = None
         self.precision = ops.TENSOR_TF32   # GEMM-shaped ops on tcgen05 (TF32 operands, fp32 accumulate); ops.EXACT_FP32 = CUDA cores
+        self.fused_coattn = True           # co-attention forward: fused tcgen05 kernel (bf16 operands, S/P never leave the SM)
 
     # ---------------------------------------------------------------------------------------------------------
+    @property
+    def coattn_precision(self):
+        if self.precision == ops.EXACT_FP32:
+            return ops.EXACT_FP32
+        return ops.TENSOR_BF16_FUSED if self.fused_coattn else self.precision
+
     def _pair_index(self, B, device):
         key = ("pair", B, str(device))
         if key not in self._idx_cache:
@@ -192,7 +199,7 @@ class grounding_model(nn.Module):
         qa, kb = self._pair_index(B, fv[0].device)
         corr, sim, neg_sim = [], [], []
         for s in range(3):
-            attn = ops.coattention(fv[s], qa, kb, tau=self.temperature, precision=self.precision)
+            attn = ops.coattention(fv[s], qa, kb, tau=self.temperature, precision=self.coattn_precision)
             y, sm, ng = self.corr_conv._modules[str(s)][0].fused(fv[s], x2=attn, fa=fa, l2norm=True, precision=self.precision, fa_neg=fa_neg)
             corr.append(y); sim.append(sm); neg_sim.append(ng)
         return corr, sim, neg_sim

@@ -32,7 +32,7 @@ class grounding_model(_Base):
         K = n_frame - 1
         out = []
         for s in range(3):
-            attn = ops.coattention(fv[s], qa, kb, tau=self.temperature, precision=self.precision)          # [K*b, C, N]
+            attn = ops.coattention(fv[s], qa, kb, tau=self.temperature, precision=self.coattn_precision)          # [K*b, C, N]
             x1 = fv[s].index_select(0, qa_l)                                                                 # centre frames, partner-major
             m = self.corr_conv._modules[str(s)][0]
             if self.training:

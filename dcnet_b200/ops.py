@@ -340,6 +340,31 @@ class _CoAttn(torch.autograd.Function):
         return dframes, None, None, None, None, None, None
 
 
+def coattn_stage(frames):
+    """bf16 staging + column norms of frames [F,C,N] for coattn_fused (forward only)."""
+    frames = _c(frames.detach(), name="frames")
+    F_, C, N = frames.shape
+    nbytes = _lib.lib().dcnet_coattn_stage_bytes(F_, C, N)
+    staged = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
+    _lib.call("dcnet_coattn_stage", _p(frames), F_, C, N, _p(staged), nbytes, _st())
+    return staged
+
+
+def coattn_fused(staged, shape, qa, kb, oidx=None, n_out=None, tau=10.0, out=None, lse=None):
+    """the fused tcgen05 kernel alone over a staged buffer (forward only) -> out [n_out,C,N], lse [nprob,N]"""
+    F_, C, N = shape
+    qa, kb = _c(qa, torch.int32, "index"), _c(kb, torch.int32, "index")
+    nprob = qa.numel()
+    oidx = torch.arange(nprob, device=qa.device, dtype=torch.int32) if oidx is None else _c(oidx, torch.int32, "index")
+    n_out = nprob if n_out is None else n_out
+    if out is None:
+        out = torch.empty(n_out, C, N, device=staged.device, dtype=F32)
+    if lse is None:
+        lse = torch.empty(nprob, N, device=staged.device, dtype=F32)
+    _lib.call("dcnet_coattn_fused_fwd", _p(staged), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, float(tau), _st())
+    return out, lse
+
+
 def coattention(frames, qa, kb, oidx=None, n_out=None, tau=10.0, precision=1):
     """frames [F,C,N]; problem i: queries frame qa[i] attend to frame kb[i]; result row oidx[i] of out [n_out,C,N]."""
     if oidx is None:

@@ -142,6 +142,16 @@ DCNET_API size_t dcnet_coattn_workspace_bytes(int F, int nprob, int C, int N, in
 DCNET_API int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                float* out, int n_out, float* lse, int C, int N, float tau, int precision,
                                void* workspace, size_t workspace_bytes, void* stream);
+/* the two halves of the precision-2 forward, callable separately (the clip path stages a clip once and runs many problems):
+ * dcnet_coattn_stage: staged <- bf16 copy of frames (row pitch padded to 8 elements) + column norms; dcnet_coattn_fused_fwd: the
+ * fused TMA/tcgen05 kernel over a staged buffer (grid = 64-query tiles x problems).  C % 128 == 0, C <= 512.                 */
+DCNET_API size_t dcnet_coattn_stage_bytes(int F, int C, int N);
+DCNET_API int dcnet_coattn_stage(const float* frames, int F, int C, int N, void* staged, size_t staged_bytes, void* stream);
+DCNET_API int dcnet_coattn_fused_fwd(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                     float* out, int n_out, float* lse, int C, int N, float tau, void* stream);
+/* profiling variant: trace [ceil(N/64) * nprob CTAs][ceil(N/128) key tiles + 1][8] int64 receives clock64 stamps (see umma_coattn.cu) */
+DCNET_API int dcnet_coattn_fused_fwd_trace(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                           float* out, int n_out, float* lse, int C, int N, float tau, long long* trace, int variant, void* stream);
 /* dframes [F,C,N] += gradient (caller zeroes); dout/out indexed by oidx like the forward */
 DCNET_API int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                const float* out, int n_out, const float* lse, const float* dout, float* dframes,

@@ -240,6 +240,29 @@ def test_coattention_forward_backward(P, N, precision):
     assert rel(x.grad, ref_in.grad) < tol_b, rel(x.grad, ref_in.grad)
 
 
+@pytest.mark.parametrize("C,N", [(512, 200), (256, 1024), (128, 64), (512, 2704)])
+def test_coattention_fused_staged_problems(C, N):
+    """dcnet_coattn_stage + dcnet_coattn_fused_fwd: one staging of a clip, arbitrary (query frame, key frame, output row) problems,
+    ragged N (last key tile / query tile partly out of range), C < 512; lse against the fp64 log-sum-exp."""
+    g = gen(77 + N)
+    nf = 3
+    fr = torch.nn.functional.normalize(torch.randn(nf, C, N, generator=g).abs(), dim=1)
+    qa = torch.tensor([0, 2, 1, 1], dtype=torch.int32)
+    kb = torch.tensor([1, 0, 1, 2], dtype=torch.int32)
+    oidx = torch.tensor([3, 0, 2, 1], dtype=torch.int32)
+    staged = ops.coattn_stage(fr.to(DEV))
+    out, lse = ops.coattn_fused(staged, fr.shape, qa.to(DEV), kb.to(DEV), oidx.to(DEV), tau=10.0)
+    for i in range(4):
+        S = 10.0 * fr[qa[i]].double().t() @ fr[kb[i]].double()
+        ref = fr[kb[i]].double() @ torch.softmax(S, 1).t()
+        # problem 2 is a frame attending to itself: softmax peaked on one key, so the output is essentially one bf16-rounded
+        # column of Fb and the error is the bf16 operand rounding itself (2^-9 / sqrt(3) = 1.1e-3); distinct frames give 1e-4
+        assert rel(out[oidx[i]], ref) < (1.5e-3 if qa[i] == kb[i] else 1e-3), (i, rel(out[oidx[i]], ref))
+        assert float((lse[i].double().cpu() - torch.logsumexp(S, 1)).abs().max()) < 5e-3
+    print("fused staged C=%d N=%d worst fwd rel err %.2e" % (C, N, max(rel(out[oidx[i]], fr[kb[i]].double() @ torch.softmax(
+        10.0 * fr[qa[i]].double().t() @ fr[kb[i]].double(), 1).t()) for i in range(4))))
+
+
 def test_coattention_clip_mode_centre_vs_others():
     """model/test_DCNet_model.py:303-332: centre frame attends to each other frame (one direction), mean of results."""
     g = gen(31)
