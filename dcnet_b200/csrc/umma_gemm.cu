@@ -194,6 +194,221 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 5) tmem_dealloc(tmem_base, BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (the default): each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... ; two TMEM accumulator
+// stages let the epilogue of tile i run under the main loop of tile i+1; the epilogue leaves through 128-byte-swizzled smem
+// slots and TMA (plain store, or fp32 reduce-add for split reductions / shared gradients) instead of per-thread stores whose
+// lanes hit 32 different rows.  Each epilogue warp owns its 32 rows end to end (2 x 4 KiB slots), so no cross-warp barrier.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Gemm2P {
+  int M_valid, N_valid, k_iters, k_split, n_split, m_split;
+  int a_batched, b_batched, out_batched;
+  const int* idxA; const int* idxB; const int* idxC;
+  int tiles_m, tiles_n, ntiles;
+  float alpha; int atomic;
+  const float* u; int ldu; const float* cc; long long ldcc; float* sum; float* sumsq;
+};
+
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapO,
+                  const __grid_constant__ CUtensorMap mapO2, const Gemm2P p) {
+  using G = Geo<EB>;
+  constexpr int BK = G::BK;
+  constexpr int BLK_BYTES = G::BLK_BYTES;
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int SLOT_BYTES = 32 * 128;           // 32 rows x 32 fp32
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_out = smem + STAGES * STAGE_BYTES;                 // [4 warps][2][SLOT_BYTES]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + 8 * SLOT_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    prefetch_tmap(&mapB2);
+    prefetch_tmap(&mapO);
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per_z = p.tiles_m * p.tiles_n;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      uint32_t itg = 0;
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        const int z = t / per_z, r = t - z * per_z;
+        const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+        const int a_b = p.a_batched ? (p.idxA ? p.idxA[z] : z) : 0;
+        const int b_b = p.b_batched ? (p.idxB ? p.idxB[z] : z) : 0;
+        for (int it = 0; it < p.k_iters; it++, itg++) {
+          const int s = itg % STAGES;
+          const uint32_t ph = (itg / STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          uint8_t* sA = smem + s * STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / G::MN_ELEMS; j++) tma_load_3d(sA + j * BLK_BYTES, &mapA, &full[s], m0 + G::MN_ELEMS * j, it * BK, a_b);
+          } else {
+            tma_load_3d(sA, &mapA, &full[s], it * BK, m0, a_b);
+          }
+          if constexpr (B_MN) {
+            const bool src2 = p.k_split > 0 && it >= p.k_split;
+            const CUtensorMap* mb = src2 ? &mapB2 : &mapB;
+            const int kc = (src2 ? it - p.k_split : it) * BK;
+#pragma unroll
+            for (int j = 0; j < BN / G::MN_ELEMS; j++) tma_load_3d(sB + j * BLK_BYTES, mb, &full[s], n0 + G::MN_ELEMS * j, kc, b_b);
+          } else {
+            const bool src2 = p.n_split > 0 && n0 >= p.n_split;
+            tma_load_3d(sB, src2 ? &mapB2 : &mapB, &full[s], it * BK, src2 ? n0 - p.n_split : n0, b_b);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc(G::FMT, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      uint32_t itg = 0, tl = 0;
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, tl++) {
+        const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
+        mbar_wait(&acc_empty[as], aph ^ 1u);          // the epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + as * BN;
+        for (int it = 0; it < p.k_iters; it++, itg++) {
+          const int s = itg % STAGES;
+          const uint32_t ph = (itg / STAGES) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            constexpr uint32_t kadv = G::KSTEP_ROWS * 128;
+            const uint64_t ad = A_MN ? smem_desc(sA + ks * kadv, BLK_BYTES, G::MN_SBO, G::MN_LAYOUT) : smem_desc(sA + ks * 32, 16, 1024, 2);
+            const uint64_t bd = B_MN ? smem_desc(sB + ks * kadv, BLK_BYTES, G::MN_SBO, G::MN_LAYOUT) : smem_desc(sB + ks * 32, 16, 1024, 2);
+            if constexpr (EB == 4) mma_tf32(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+            else mma_bf16(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+          }
+          mma_commit(&empty[s]);
+        }
+        mma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 0..3: TMEM lanes 32w.. <-> output rows m0 + 32w..
+    uint8_t* slots = stage_out + warp * 2 * SLOT_BYTES;
+    uint32_t tl = 0, chunk = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, tl++) {
+      const int z = t / per_z, r = t - z * per_z;
+      const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+      const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
+      const int row0 = m0 + warp * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < p.M_valid;
+      const int zc = p.out_batched ? (p.idxC ? p.idxC[z] : z) : 0;
+      const bool second = p.m_split > 0 && m0 >= p.m_split;
+      const CUtensorMap* mo = second ? &mapO2 : &mapO;
+      const int orow0 = second ? row0 - p.m_split : row0;
+      const float bias = (p.u && row_ok) ? p.u[(long long)z * p.ldu + row] : 0.f;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++, chunk++) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        const int nb = n0 + c * 32;
+        if (p.cc && row_ok && nb < p.N_valid) {
+          const float* cr = p.cc + (long long)row * p.ldcc + nb;
+          if (nb + 32 <= p.N_valid) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const float4 q = *reinterpret_cast<const float4*>(cr + 4 * e);
+              v[4 * e] = fmaf(p.alpha, v[4 * e], bias + q.x); v[4 * e + 1] = fmaf(p.alpha, v[4 * e + 1], bias + q.y);
+              v[4 * e + 2] = fmaf(p.alpha, v[4 * e + 2], bias + q.z); v[4 * e + 3] = fmaf(p.alpha, v[4 * e + 3], bias + q.w);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e++) v[e] = fmaf(p.alpha, v[e], bias + ((nb + e < p.N_valid) ? cr[e] : 0.f));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e++) v[e] = fmaf(p.alpha, v[e], bias);
+        }
+        if (p.sum && row_ok) {
+          if (nb + 32 <= p.N_valid) {
+#pragma unroll
+            for (int e = 0; e < 32; e++) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e++)
+              if (nb + e < p.N_valid) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
+          }
+        }
+        uint8_t* slot = slots + (chunk & 1u) * SLOT_BYTES;
+        if (lane == 0) tma_store_wait_read1();          // the store that last read this slot (two chunks ago) is done with it
+        __syncwarp();
+        uint8_t* srow = slot + lane * 128;
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+          *reinterpret_cast<float4*>(srow + ((e ^ (lane & 7)) * 16)) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (row0 < p.M_valid && nb < p.N_valid) {       // rows / columns beyond the tensor are clipped by the map
+            if (p.atomic) tma_reduce_add_3d(mo, slot, nb, orow0, zc);
+            else tma_store_3d(mo, slot, nb, orow0, zc);
+          }
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (p.sum && row_ok) {
+        atomicAdd(p.sum + row, s1);
+        atomicAdd(p.sumsq + row, s2);
+      }
+    }
+    if (lane == 0) tma_store_wait_read();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
+int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
+                const Gemm2P& p, int grid, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_BYTES + BN * 128) + 8 * 32 * 128 + 1024 + 256;
+  static_assert(smem <= 232448, "umma_gemm2: shared memory budget");
+  auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB>;
+  DCNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "umma_gemm2.attr");
+  kern<<<grid, 192, smem, st>>>(ma, mb, mb2, mo, mo2, p);
+  DCNET_LAUNCH_OK("umma_gemm2");
+  return 0;
+}
+
 template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
 int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const GemmP& p, dim3 grid, cudaStream_t st) {
   constexpr int smem = STAGES * (A_BYTES + BN * 128) + 1024 + 256;
@@ -211,6 +426,18 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
 //   K-major  use: rows = the M (or N) index, cols = the reduction index
 //   MN-major use: rows = the reduction index, cols = the M (or N) index
 // ---------------------------------------------------------------------------------------------------------------------
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+static bool g_force_v1 = false;   // tests: run the one-tile-per-CTA kernel with direct stores
+extern "C" int dcnet_gemm_select(int variant) { g_force_v1 = (variant == 1); return 0; }
+
 static bool operand_ok(const UmmaOperand& o) {
   const int per16 = o.bf16 ? 8 : 4;     // elements per 16 bytes
   return o.ptr && (reinterpret_cast<uintptr_t>(o.ptr) % 16 == 0) && (o.ld % per16 == 0) && (o.batch_stride % per16 == 0) && o.rows > 0 && o.cols > 0;
@@ -258,8 +485,46 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   p.idxA = e.idxA; p.idxB = e.idxB; p.idxC = e.idxC;
   p.out = e.out; p.ldo = e.ldo; p.so_b = e.so_b; p.out2 = e.out2; p.ldo2 = e.ldo2; p.so_b2 = e.so_b2;
   p.alpha = e.alpha; p.atomic = e.atomic; p.u = e.u; p.ldu = e.ldu; p.cc = e.cc; p.ldcc = e.ldcc; p.sum = e.sum; p.sumsq = e.sumsq;
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
   const int am = A.mn_major ? 1 : 0, bm = B.mn_major ? 1 : 0;
+  // persistent kernel with TMA-store epilogue whenever the output rows are TMA-addressable
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  const bool out_ok = al16(e.out) && e.ldo % 4 == 0 && e.so_b % 4 == 0 &&
+                      (e.m_split == 0 || (e.m_split % BM == 0 && e.out2 && al16(e.out2) && e.ldo2 % 4 == 0 && e.so_b2 % 4 == 0)) &&
+                      (!e.cc || (al16(e.cc) && e.ldcc % 4 == 0)) && !(e.so_b == 0 && batch > 1 && !e.atomic) && !g_force_v1;
+  if (out_ok) {
+    Gemm2P q{};
+    q.M_valid = M; q.N_valid = N; q.k_iters = p.k_iters; q.k_split = p.k_split; q.n_split = p.n_split; q.m_split = p.m_split;
+    q.a_batched = p.a_batched; q.b_batched = p.b_batched; q.out_batched = (e.so_b != 0) ? 1 : 0;
+    q.idxA = e.idxA; q.idxB = e.idxB; q.idxC = e.idxC;
+    q.tiles_m = ceil_div(M, BM); q.tiles_n = ceil_div(N, BN); q.ntiles = q.tiles_m * q.tiles_n * batch;
+    q.alpha = e.alpha; q.atomic = e.atomic; q.u = e.u; q.ldu = e.ldu; q.cc = e.cc; q.ldcc = e.ldcc; q.sum = e.sum; q.sumsq = e.sumsq;
+    const uint64_t nbo = q.out_batched ? 65535u : 1u;
+    const uint64_t rows1 = e.m_split > 0 ? (uint64_t)e.m_split : (uint64_t)M;
+    CUtensorMap mo, mo2;
+    int r = make_tmap(&mo, e.out, 4, (uint64_t)N, rows1, nbo, (uint64_t)e.ldo, q.out_batched ? (uint64_t)e.so_b : rows1 * (uint64_t)e.ldo, 32, 32);
+    if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled(out) failed (%d)", r);
+    mo2 = mo;
+    if (e.m_split > 0) {
+      const uint64_t rows2 = (uint64_t)(M - e.m_split);
+      r = make_tmap(&mo2, e.out2, 4, (uint64_t)N, rows2, nbo, (uint64_t)e.ldo2, q.out_batched ? (uint64_t)e.so_b2 : rows2 * (uint64_t)e.ldo2, 32, 32);
+      if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled(out2) failed (%d)", r);
+    }
+    const int grid2 = q.ntiles < sm_count() ? q.ntiles : sm_count();
+#define DISPATCH2(AM, BMJ)                                                                           \
+    if (am == AM && bm == BMJ) {                                                                     \
+      if (A.bf16) {                                                                                  \
+        if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 2>(ma, mb, mb2, mo, mo2, q, grid2, st);     \
+        if (BN == 256) return launch_cfg2<AM, BMJ, 256, 4, 2>(ma, mb, mb2, mo, mo2, q, grid2, st);   \
+        return launch_cfg2<AM, BMJ, 128, 4, 2>(ma, mb, mb2, mo, mo2, q, grid2, st);                  \
+      }                                                                                              \
+      if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 4>(ma, mb, mb2, mo, mo2, q, grid2, st);       \
+      if (BN == 256) return launch_cfg2<AM, BMJ, 256, 4, 4>(ma, mb, mb2, mo, mo2, q, grid2, st);     \
+      return launch_cfg2<AM, BMJ, 128, 4, 4>(ma, mb, mb2, mo, mo2, q, grid2, st);                    \
+    }
+    DISPATCH2(0, 0) DISPATCH2(0, 1) DISPATCH2(1, 0) DISPATCH2(1, 1)
+#undef DISPATCH2
+  }
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
 #define DISPATCH(AM, BMJ)                                                                   \
   if (am == AM && bm == BMJ) {                                                              \
     if (A.bf16) {                                                                           \

@@ -95,6 +95,21 @@ def test_gemm_bf16_all_operand_majors(a_mn, b_mn, M, N, K, batch):
     assert e < 1e-5, e
 
 
+def test_gemm_one_tile_per_cta_variant_still_agrees():
+    """dcnet_gemm_select(1): the non-persistent kernel with per-thread stores (used when TMA cannot address the output) must give
+    the same numbers as the persistent TMA-store kernel, bit for bit (same MMA order per tile)."""
+    from dcnet_b200 import _lib
+    g = gen(5)
+    A = torch.randn(2, 200, 104, generator=g).to(DEV); B = torch.randn(2, 680, 104, generator=g).to(DEV)
+    c0 = ops.gemm_tf32(A, B, 0, 0, 200, 680, 104)
+    _lib.lib().dcnet_gemm_select(1)
+    try:
+        c1 = ops.gemm_tf32(A, B, 0, 0, 200, 680, 104)
+    finally:
+        _lib.lib().dcnet_gemm_select(0)
+    assert torch.equal(c0, c1)
+
+
 def test_conv_linear_backward_forms_tf32():
     """The two backward contractions of the 1x1 conv are linear (no ReLU kink): TF32 must hold 1e-3-class accuracy."""
     from dcnet_b200 import _lib
@@ -258,7 +273,8 @@ def test_coattention_fused_staged_problems(C, N):
         # problem 2 is a frame attending to itself: softmax peaked on one key, so the output is essentially one bf16-rounded
         # column of Fb and the error is the bf16 operand rounding itself (2^-9 / sqrt(3) = 1.1e-3); distinct frames give 1e-4
         assert rel(out[oidx[i]], ref) < (1.5e-3 if qa[i] == kb[i] else 1e-3), (i, rel(out[oidx[i]], ref))
-        assert float((lse[i].double().cpu() - torch.logsumexp(S, 1)).abs().max()) < 5e-3
+        # logits carry tau x the bf16 rounding of a dot product: 10 x 2^-9 worst case on the self-pair diagonal
+        assert float((lse[i].double().cpu() - torch.logsumexp(S, 1)).abs().max()) < (3e-2 if qa[i] == kb[i] else 5e-3)
     print("fused staged C=%d N=%d worst fwd rel err %.2e" % (C, N, max(rel(out[oidx[i]], fr[kb[i]].double() @ torch.softmax(
         10.0 * fr[qa[i]].double().t() @ fr[kb[i]].double(), 1).t()) for i in range(4))))
 
