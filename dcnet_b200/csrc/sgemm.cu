@@ -16,10 +16,11 @@ struct GemmArgs {
   int atomic;
 };
 
-// BM x BN tile, BK = 8, 256 threads, TM x TN register micro-tile per thread.
-template <int BM, int BN, int TM, int TN>
+// BM x BN tile, 256 threads, TM x TN register micro-tile per thread.  The exact-fp32 problems of the hot path are small and
+// deep (K up to 1024 on a handful of CTAs), i.e. bound by the latency of one global->smem tile per iteration: deep BK tiles
+// (32 for the 64x64 tile, 16 for 128x128) keep 4x / 2x the bytes in flight per iteration and cut the barrier count alike.
+template <int BM, int BN, int TM, int TN, int BK>
 __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
-  constexpr int BK = 8;
   constexpr int NT = 256;
   static_assert((BM / TM) * (BN / TN) == NT, "tile/thread mismatch");
   __shared__ float As[2][BK][BM + 4];
@@ -151,10 +152,10 @@ int sgemm_launch(const float* A, const float* B, float* C, int M, int N, int K, 
   const long long tiles128 = (long long)ceil_div(M, 128) * ceil_div(N, 128) * batch;
   if (M >= 96 && N >= 96 && tiles128 >= 96) {
     dim3 grid(ceil_div(N, 128), ceil_div(M, 128), batch);
-    sgemm_kernel<128, 128, 8, 8><<<grid, 256, 0, st>>>(g);
+    sgemm_kernel<128, 128, 8, 8, 16><<<grid, 256, 0, st>>>(g);
   } else {
     dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch);
-    sgemm_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(g);
+    sgemm_kernel<64, 64, 4, 4, 32><<<grid, 256, 0, st>>>(g);
   }
   DCNET_LAUNCH_OK("sgemm");
   return 0;

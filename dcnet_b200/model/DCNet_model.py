@@ -165,8 +165,9 @@ class grounding_model(nn.Module):
         """a2: fvisu[s] = normalize_c(ConvBNReLU_1x1(raw[s]))   (:356-359) -> 3 x [B,C,N_s].
         Scale 0 runs in exact fp32: the top-30 correspondences (a4) and the arg-max words (a11) are selected from it and
         index parity with the reference needs fp32 scores (SURVEY section 7 "Index parity"); the other scales use tcgen05."""
+        p0 = ops.EXACT_FP32 if self.precision == ops.EXACT_FP32 else ops.EXACT_FWD_TF32_BWD     # gradients select no index
         return [self.mapping_visu._modules[str(s)].fused(raw_fvisu[s].flatten(2), l2norm=True,
-                                                         precision=ops.EXACT_FP32 if s == 0 else self.precision) for s in range(3)]
+                                                         precision=p0 if s == 0 else self.precision) for s in range(3)]
 
     def interframe(self, fv0, negpos=None):
         """a4 (:381-430) -> packed q [30,P,C], k [30,P,C], neg [30,P,10,C].  negpos: optional pre-drawn device tensor

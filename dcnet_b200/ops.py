@@ -233,6 +233,9 @@ class _ConvBNAct(torch.autograd.Function):
         z = torch.empty(B, C, N, device=dev, dtype=F32)
         mean = torch.empty(C, device=dev, dtype=F32)
         invstd = torch.empty(C, device=dev, dtype=F32)
+        ctx_precision = precision
+        if precision == EXACT_FWD_TF32_BWD:
+            precision = EXACT_FP32
         if training and precision == 1:
             # tensor-core path: BatchNorm sums come out of the GEMM epilogue, z is not re-read
             sums = torch.empty(2 * C, device=dev, dtype=F32)
@@ -252,7 +255,7 @@ class _ConvBNAct(torch.autograd.Function):
         _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm), _p(y), _p(fa), _p(fa_neg), _p(sim), _p(neg),
                   B, C, N, st)
         ctx.save_for_backward(x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd)
-        ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None, precision)
+        ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None, ctx_precision)
         if fa is None:
             return y
         return y, sim, neg
@@ -261,6 +264,8 @@ class _ConvBNAct(torch.autograd.Function):
     def backward(ctx, dy, dsim=None, dneg=None):
         x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd = ctx.saved_tensors
         training, slope, l2norm, has_u, has_cc, precision = ctx.cfg
+        if precision == EXACT_FWD_TF32_BWD:
+            precision = TENSOR_TF32      # no index depends on the gradients: the backward contractions run on tcgen05
         B, K1, N = x1.shape
         K2 = 0 if x2 is None else x2.shape[1]
         C, ldw = weight.shape
@@ -296,7 +301,7 @@ class _ConvBNAct(torch.autograd.Function):
         return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None)
 
 
-EXACT_FP32, TENSOR_TF32, TENSOR_BF16_FUSED = 0, 1, 2
+EXACT_FP32, TENSOR_TF32, TENSOR_BF16_FUSED, EXACT_FWD_TF32_BWD = 0, 1, 2, 3
 
 
 def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
