@@ -396,39 +396,54 @@ def main():
     value = world * pairs * args.steps / (dev_ms / 1e3)
     e2e_val = world * pairs * args.steps / (e2e_ms / 1e3)
 
-    # ---- roofline of the dominant kernel: co-attention forward at the finest scale (all pairs of the batch, one launch set)
-    roof = None
+    # ---- roofline.  Dominant kernel by share of the step (profiles/*_step_breakdown.txt): the persistent tcgen05 GEMM
+    # (umma_gemm2_kernel: 1x1 convs fwd/bwd and the five contractions of the co-attention backward).  Timed live, alone, with
+    # CUDA events on the launching stream, L2 flushed before every launch, on its most frequent large instance: the S = Fa^T Fb
+    # recomputation of the co-attention backward at the finest scale (M = N = N2, K = 512, one problem per direction).
+    # roofline_coattn: the fused co-attention forward kernel (north_star item 2), same method.
+    roof = roof_co = None
     cpu_base = None
     if rank == 0:
         from dcnet_b200 import ops
         peaks = load_peaks()
         N2 = (size // 8) ** 2
         fr = torch.nn.functional.normalize(torch.randn(B, C_EMB, N2, device=dev).abs(), dim=1)
+        fr2 = fr.flip(0).contiguous()
         qa = torch.arange(B, device=dev, dtype=torch.int32)
         kb = qa ^ 1
-        # the fused tcgen05 kernel alone (CUDA events on the launching stream), L2 flushed before every launch; the bf16
-        # staging pass (cast + column norms) is timed separately and reported as stage_ms
+
+        def timed(fn, reps=10):
+            for _ in range(3):
+                fn()
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            return tot / reps
+
+        c_buf = torch.empty(B, N2, N2, device=dev)
+        ms_g = timed(lambda: ops.gemm_tf32(fr, fr2, 1, 1, N2, N2, C_EMB, out=c_buf))
+        fl_g = 2.0 * N2 * N2 * C_EMB * B
+        ach_g = fl_g / (ms_g * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="umma_gemm2_kernel (tcgen05 kind::tf32, persistent; S = Fa^T Fb of the co-attention backward, "
+                    "M=N=%d K=%d, %d problems, one launch)" % (N2, C_EMB, B), achieved=ach_g, peak=peaks["tensor_burst"], unit="TFLOP/s",
+                    frac=ach_g / peaks["tensor_burst"], traffic=None, ms=ms_g, dtype="tf32 operands (fp32 in HBM), fp32 accumulate",
+                    note="peak is the measured bf16 figure; the tf32 tensor pipe is nominally half of it",
+                    peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
         staged = ops.coattn_stage(fr)
         o_buf = torch.empty(B, C_EMB, N2, device=dev); l_buf = torch.empty(B, N2, device=dev)
-        for _ in range(3):
-            ops.coattn_fused(staged, fr.shape, qa, kb, tau=10.0, out=o_buf, lse=l_buf)
-        reps = 10
-        tt = ts_ = 0.0
-        for _ in range(reps):
-            flush.zero_()
-            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            a.record(); staged = ops.coattn_stage(fr); b.record()
-            ops.coattn_fused(staged, fr.shape, qa, kb, tau=10.0, out=o_buf, lse=l_buf); c.record()
-            torch.cuda.synchronize()
-            ts_ += a.elapsed_time(b); tt += b.elapsed_time(c)
-        ms = tt / reps
+        ms = timed(lambda: ops.coattn_fused(staged, fr.shape, qa, kb, tau=10.0, out=o_buf, lse=l_buf))
+        ms_stage = timed(lambda: ops.coattn_stage(fr))
         flops = 6.0 * C_EMB * N2 * N2 * pairs            # 6*c*N^2 per pair forward (both directions share S)
         ach = flops / (ms * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="coattn_fused_kernel (finest scale, N=%d, %d pairs = %d directed problems, one launch)" % (N2, pairs, B),
-                    achieved=ach, peak=peaks["tensor_burst"], unit="TFLOP/s", frac=ach / peaks["tensor_burst"], traffic=None, ms=ms,
-                    stage_ms=ts_ / reps, executed_tflops=ach * 4.0 / 3.0,
-                    note="algorithmic 6*c*N^2 per pair; the kernel executes 8*c*N^2 (S recomputed per direction)",
-                    peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
+        roof_co = dict(bound="tensor", kernel="coattn_fused_kernel (finest scale, N=%d, %d pairs = %d directed problems, one launch)" % (N2, pairs, B),
+                       achieved=ach, peak=peaks["tensor_burst"], unit="TFLOP/s", frac=ach / peaks["tensor_burst"], traffic=None, ms=ms,
+                       stage_ms=ms_stage, executed_tflops=ach * 4.0 / 3.0,
+                       note="algorithmic 6*c*N^2 per pair; the kernel executes 8*c*N^2 (S recomputed per direction)",
+                       peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
         if world == 1 and not args.no_cpu_baseline:
             from oracle import dcnet_oracle as O
             cores = os.cpu_count() or 1
@@ -463,7 +478,7 @@ def main():
                     e2e=dict(value=e2e_val, unit="frame-pairs/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                              ms_per_step=e2e_ms / args.steps, last_loss=loss_val),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
-                    roofline=roof, cpu_baseline=cpu_base)
+                    roofline=roof, roofline_coattn=roof_co, cpu_baseline=cpu_base)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

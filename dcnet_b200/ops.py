@@ -65,11 +65,11 @@ def sgemm(A, B, C, M, N, K, batch=1, kbatch=1, sA=(0, 0, 0, 0), sB=(0, 0, 0, 0),
     return C
 
 
-def gemm_tf32(A, B, a_mn, b_mn, M, N, K, alpha=1.0):
+def gemm_tf32(A, B, a_mn, b_mn, M, N, K, alpha=1.0, out=None):
     """direct tensor-core GEMM: A [batch, M, K] (a_mn=0) or [batch, K, M] (a_mn=1); B [batch, N, K] or [batch, K, N]."""
     A, B = _c(A, name="A"), _c(B, name="B")
     batch = A.shape[0]
-    C = torch.empty(batch, M, N, device=A.device, dtype=F32)
+    C = torch.empty(batch, M, N, device=A.device, dtype=F32) if out is None else out
     _lib.call("dcnet_gemm_tf32", _p(A), int(a_mn), A.shape[2], A.shape[1] * A.shape[2], _p(B), int(b_mn), B.shape[2], B.shape[1] * B.shape[2],
               _p(C), N, M * N, M, N, K, batch, alpha, 0, _st())
     return C
