@@ -278,8 +278,7 @@ __global__ void __launch_bounds__(32 * G) bn_act_bwd_reduce_kernel(
       t0 += red[0][k][pl];
       t1 += red[1][k][pl];
     }
-    const float nrm = fmaxf(sqrtf(t0), 1e-12f);
-    inv = 1.f / nrm;
+    inv = rsqrtf(fmaxf(t0, 1e-24f));   // 1 / max(|act|, 1e-12) without the sqrt / divide slow paths (gradient only: 2-ulp MUFU.RSQ)
     dotn = t1 * inv * inv;  // <g, yhat> / nrm, with yhat = act * inv
   }
   const int lane = pl;
@@ -328,21 +327,41 @@ __global__ void __launch_bounds__(32 * G) bn_act_bwd_reduce_kernel(
   }
 }
 
-__global__ void bn_act_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                        const float* __restrict__ gamma, const float* __restrict__ dv,
-                                        const float* __restrict__ sum_dv, const float* __restrict__ sum_dvz, int train,
-                                        float* __restrict__ dz, int B, int C, int N) {
-  const long long total = (long long)B * C * N;
-  const float invM = 1.f / (float)((long long)B * N);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i / N) % C);
-    const float sc = gamma[c] * invstd[c];
-    float d = dv[i];
+// dz = gamma invstd (dv - mean(dv) - zhat mean(dv zhat)).  Rows = (b, c) pairs, VEC consecutive positions per thread; the channel
+// constants are resolved once per thread with 32-bit index arithmetic (no 64-bit division per element).
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ dv, const float* __restrict__ sum_dv,
+                                                               const float* __restrict__ sum_dvz, int train, float* __restrict__ dz,
+                                                               int rows, int C, int N, int tpr, float invM) {
+  const int row = blockIdx.x * (256 / tpr) + threadIdx.x / tpr;
+  const int col = (blockIdx.y * tpr + threadIdx.x % tpr) * VEC;
+  if (row >= rows || col >= N || (int)threadIdx.x >= (256 / tpr) * tpr) return;
+  const int c = row % C;
+  const float is = invstd[c];
+  const float sc = gamma[c] * is;
+  float k0 = 0.f, k1 = 0.f, mu = 0.f;
+  if (train) {
+    mu = mean[c];
+    k0 = sum_dv[c] * invM;
+    k1 = sum_dvz[c] * invM;
+  }
+  const long long off = (long long)row * N + col;
+  if constexpr (VEC == 4) {
+    float4 d = *reinterpret_cast<const float4*>(dv + off);
     if (train) {
-      const float zh = (z[i] - mean[c]) * invstd[c];
-      d = d - sum_dv[c] * invM - zh * sum_dvz[c] * invM;
+      const float4 zz = *reinterpret_cast<const float4*>(z + off);
+      d.x = d.x - k0 - (zz.x - mu) * is * k1;
+      d.y = d.y - k0 - (zz.y - mu) * is * k1;
+      d.z = d.z - k0 - (zz.z - mu) * is * k1;
+      d.w = d.w - k0 - (zz.w - mu) * is * k1;
     }
-    dz[i] = sc * d;
+    *reinterpret_cast<float4*>(dz + off) = make_float4(sc * d.x, sc * d.y, sc * d.z, sc * d.w);
+  } else {
+    float d = dv[off];
+    if (train) d = d - k0 - (z[off] - mu) * is * k1;
+    dz[off] = sc * d;
   }
 }
 
@@ -556,8 +575,19 @@ extern "C" int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const f
                                       float* dz, int B, int C, int N, void* stream) {
   DCNET_CHECK_ARG(z && mean && invstd && gamma && dv && dz && B > 0 && C > 0 && N > 0, "bn_act_bwd_apply: bad arguments");
   DCNET_CHECK_ARG(!train || (sum_dv && sum_dvz), "bn_act_bwd_apply: train mode needs the channel sums");
-  bn_act_bwd_apply_kernel<<<ew_grid((long long)B * C * N), 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, dv, sum_dv, sum_dvz,
-                                                                                            train, dz, B, C, N);
+  const long long rows = (long long)B * C;
+  const float invM = 1.f / (float)((long long)B * N);
+  const bool v4 = N % 4 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0 && reinterpret_cast<uintptr_t>(dv) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(dz) % 16 == 0;
+  const int nv = v4 ? N / 4 : N;
+  const int tpr = nv < 256 ? nv : 256;                  // threads along a row
+  const long long gx = (rows + (256 / tpr) - 1) / (256 / tpr);     // row blocks on grid.x (2^31 limit), column blocks on grid.y
+  DCNET_CHECK_ARG(rows < (1ll << 31) && gx < (1ll << 31), "bn_act_bwd_apply: too many rows");
+  dim3 grid((unsigned)gx, (nv + tpr - 1) / tpr);
+  if (v4)
+    bn_act_bwd_apply_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, dv, sum_dv, sum_dvz, train, dz, (int)rows, C, N, tpr, invM);
+  else
+    bn_act_bwd_apply_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, dv, sum_dv, sum_dvz, train, dz, (int)rows, C, N, tpr, invM);
   DCNET_LAUNCH_OK("bn_act_bwd_apply");
   return 0;
 }
