@@ -201,14 +201,22 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
 // On return lane L holds in v[0..CPT/32) the totals of original indices  vec_reduce_index(L) + {0 .. CPT/32-1}.
 template <int CPT>
 __device__ __forceinline__ void warp_vec_reduce(float (&v)[CPT], int lane) {
+  // CPT >= 32: pure recursive halving.  CPT < 32: halving until one value is left, then plain butterflies for the remaining
+  // lane bits (lanes that differ only in those bits end with the same total).
 #pragma unroll
-  for (int h = CPT / 2, bit = 16; bit >= 1; h >>= 1, bit >>= 1) {
-    const bool up = (lane & bit) != 0;
+  for (int s = 0; s < 5; s++) {
+    const int bit = 16 >> s;
+    const int h = (CPT >> 1) >> s;
+    if (h >= 1) {
+      const bool up = (lane & bit) != 0;
 #pragma unroll
-    for (int k = 0; k < h; k++) {
-      const float keep = up ? v[h + k] : v[k];
-      const float send = up ? v[k] : v[h + k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      for (int k = 0; k < h; k++) {
+        const float keep = up ? v[h + k] : v[k];
+        const float send = up ? v[k] : v[h + k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
     }
   }
 }
@@ -216,9 +224,17 @@ template <int CPT>
 __device__ __forceinline__ int vec_reduce_index(int lane) {
   int idx = 0;
 #pragma unroll
-  for (int h = CPT / 2, bit = 16; bit >= 1; h >>= 1, bit >>= 1) idx += ((lane & bit) ? h : 0);
+  for (int s = 0; s < 5; s++) {
+    const int bit = 16 >> s;
+    const int h = (CPT >> 1) >> s;
+    if (h >= 1) idx += ((lane & bit) ? h : 0);
+  }
   return idx;
 }
+// number of totals a lane holds after warp_vec_reduce, and whether this lane is the one that publishes them
+template <int CPT> struct VecOut { static constexpr int N = CPT >= 32 ? CPT / 32 : 1; };
+template <int CPT>
+__device__ __forceinline__ bool vec_reduce_owner(int lane) { return CPT >= 32 || (lane & (32 / (CPT < 32 ? CPT : 32) - 1)) == 0; }
 
 // backward, phase 1 (see header).  Same tiling; recomputes the forward from z.
 // G channel groups x 32 positions per CTA (32*G threads); each thread owns CPT = C/G channels of one position.  G = 16 keeps the
@@ -230,7 +246,7 @@ __global__ void __launch_bounds__(32 * G) bn_act_bwd_reduce_kernel(
     const float* __restrict__ fa_neg, const float* __restrict__ dsim, const float* __restrict__ dneg, float* __restrict__ dv,
     float* __restrict__ sum_dv, float* __restrict__ sum_dvz, float* __restrict__ dfa, float* __restrict__ dfa_neg, int B, int N) {
   constexpr int C = CPT * G;
-  static_assert(CPT % 32 == 0 && CPT <= 64, "CPT");
+  static_assert(CPT == 16 || CPT == 32 || CPT == 64, "CPT");
   __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C], s_mean[C], s_istd[C];
   __shared__ float red[2][G][33];
   const int b = blockIdx.y;
@@ -283,24 +299,27 @@ __global__ void __launch_bounds__(32 * G) bn_act_bwd_reduce_kernel(
   }
   const int lane = pl;
   const int ridx = vec_reduce_index<CPT>(lane);
+  const bool owner = vec_reduce_owner<CPT>(lane);
   if (fa && dfa) {
-    // d fa[b] += sum_n dsim * yhat ; d fa_partner += sum_n dneg * yhat
-    float f1[CPT], f2[CPT];
+    // d fa[b] += sum_n dsim * yhat ; d fa_partner += sum_n dneg * yhat   (one vector at a time: register pressure)
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+      const float w = which == 0 ? ds : dn;
+      float f[CPT];
 #pragma unroll
-    for (int i = 0; i < CPT; i++) {
-      const float t = a[i];
-      const float yh = (t > 0.f ? t : t * slope) * inv;
-      f1[i] = valid ? ds * yh : 0.f;
-      f2[i] = valid ? dn * yh : 0.f;
-    }
-    warp_vec_reduce<CPT>(f1, lane);
-    warp_vec_reduce<CPT>(f2, lane);
+      for (int i = 0; i < CPT; i++) {
+        const float t = a[i];
+        f[i] = valid ? w * ((t > 0.f ? t : t * slope) * inv) : 0.f;
+      }
+      warp_vec_reduce<CPT>(f, lane);
+      if (owner) {
+        float* dst = which == 0 ? dfa + (long long)b * C
+                                : (fa_neg ? (dfa_neg ? dfa_neg + (long long)b * C : nullptr) : dfa + (long long)(B - 1 - b) * C);
+        if (dst) {
 #pragma unroll
-    for (int k = 0; k < CPT / 32; k++) {
-      const int c = g + G * (ridx + k);
-      atomicAdd(dfa + (long long)b * C + c, f1[k]);
-      if (fa_neg) { if (dfa_neg) atomicAdd(dfa_neg + (long long)b * C + c, f2[k]); }
-      else atomicAdd(dfa + (long long)(B - 1 - b) * C + c, f2[k]);
+          for (int k = 0; k < VecOut<CPT>::N; k++) atomicAdd(dst + g + G * (ridx + k), f[k]);
+        }
+      }
     }
   }
 #pragma unroll
@@ -319,11 +338,13 @@ __global__ void __launch_bounds__(32 * G) bn_act_bwd_reduce_kernel(
   }
   warp_vec_reduce<CPT>(gr, lane);
   warp_vec_reduce<CPT>(a, lane);
+  if (owner) {
 #pragma unroll
-  for (int k = 0; k < CPT / 32; k++) {
-    const int c = g + G * (ridx + k);
-    atomicAdd(sum_dv + c, gr[k]);
-    atomicAdd(sum_dvz + c, a[k]);
+    for (int k = 0; k < VecOut<CPT>::N; k++) {
+      const int c = g + G * (ridx + k);
+      atomicAdd(sum_dv + c, gr[k]);
+      atomicAdd(sum_dvz + c, a[k]);
+    }
   }
 }
 

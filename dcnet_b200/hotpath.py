@@ -20,6 +20,17 @@ from . import ops, parallel
 from .model.DCNet_model import CROSS_NEG_N, NEG_N, TOP_K, grounding_model
 
 
+def _tensors(o):
+    if torch.is_tensor(o):
+        yield o
+    elif isinstance(o, dict):
+        for v in o.values():
+            yield from _tensors(v)
+    elif isinstance(o, (list, tuple)):
+        for v in o:
+            yield from _tensors(v)
+
+
 class _NoBackbone(nn.Module):
     def forward(self, x):
         raise RuntimeError("HotPath has no backbone: feed raw feature maps to step()")
@@ -39,6 +50,36 @@ class HotPath(nn.Module):
                                if n.startswith(("mapping_visu", "corr_conv")) or ".0.conv" in n and n.startswith("fcn_emb")
                                or ".0.bn" in n and n.startswith("fcn_emb")]
 
+    # The three pyramid scales are independent from the Darknet maps up to the losses.  The coarse scales launch 16-128 CTAs per
+    # kernel on a 148-SM part, so each scale's chain (forward, and its backward: autograd replays every node on the stream its
+    # forward ran on) goes to its own CUDA stream; the finest scale stays on the caller's stream.  Fork/join with events, so
+    # the whole step still captures into one CUDA graph.
+    scale_streams = True
+
+    def _run_scales(self, chain):
+        if not self.scale_streams:
+            return [chain(s) for s in range(3)]
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = [torch.cuda.Stream(), torch.cuda.Stream()]
+            # parameters are shared by nothing across scales, but their AccumulateGrad nodes live on the stream of the first
+            # iteration; the engine synchronises the streams itself, the warning about it is noise here
+            if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        outs = [None, None, None]
+        fork = cur.record_event()
+        for s in (0, 1):
+            st = self._side[s]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                outs[s] = chain(s)
+        outs[2] = chain(2)
+        for s in (0, 1):
+            cur.wait_stream(self._side[s])
+            for t in _tensors(outs[s]):
+                t.record_stream(cur)          # produced on a side stream, consumed (and later freed) on the caller's stream
+        return outs
+
     def draw_indices(self, B):
         """host side of the sampling blocks: exact reference RNG stream -> (negpos [P,30,10] int32, negidx [B,N0,5] int64) numpy"""
         N0 = self.grids[0] ** 2
@@ -48,18 +89,33 @@ class HotPath(nn.Module):
         net = self.net
         LS.configure(size=self.size)
         hw = [(m.shape[2], m.shape[3]) for m in raw]
-        fv = net.map_visual(raw)
-        q_if, k_if, neg_if, idx_if, _ = net.interframe(fv[0], negpos)
         best_n, gi, gj, t5, _, _ = ops.build_target(bbox, self.size, LS.args.anchor_imsize, LS.anchors_full)
         fa_neg = partner3 = None
         if self.cross_gpu_negatives:
             fa_neg, partner3 = parallel.global_partners(fa, best_n, gi, gj)
-        corr, sim, neg_sim = net.correspondence(fv, fa, fa_neg)
-        coords = [ops.coord_map(h, w, fa.device).flatten(1) for (h, w) in hw]
-        y = net.fuse(corr, flang, coords)
-        oo_obj = [ops.only_obj(head[s], sim[s]) for s in range(3)]
-        pred = [ops.modulate_conf(head[s], sim[s], loc[s]) for s in range(3)]
-        q_cm, k_cm, neg_cm, word, _ = net.crossmodal(fv[0], context, negidx)
+
+        def chain(s):
+            """everything of one pyramid scale: a2 -> (a4, a11 on the coarsest scale) -> a5/a6/a9 -> a7/a8 -> a10"""
+            o = {}
+            o['fv'] = net.map_visual_scale(raw[s], s)
+            if s == 0:
+                o['if'] = net.interframe(o['fv'], negpos)
+                o['cm'] = net.crossmodal(o['fv'], context, negidx)
+            o['corr'], o['sim'], o['neg_sim'] = net.correspondence_scale(o['fv'], s, fa, fa_neg)
+            coords = ops.coord_map(hw[s][0], hw[s][1], fa.device).flatten(1)
+            o['y'] = net.fuse_scale(o['corr'], s, flang, coords)
+            o['obj'] = ops.only_obj(head[s], o['sim'])
+            o['pred'] = ops.modulate_conf(head[s], o['sim'], loc[s])
+            return o
+
+        sc = self._run_scales(chain)
+        fv = [o['fv'] for o in sc]
+        q_if, k_if, neg_if, idx_if, _ = sc[0]['if']
+        q_cm, k_cm, neg_cm, word, _ = sc[0]['cm']
+        corr, sim, neg_sim = [o['corr'] for o in sc], [o['sim'] for o in sc], [o['neg_sim'] for o in sc]
+        y = [o['y'] for o in sc]
+        oo_obj = [o['obj'] for o in sc]
+        pred = [o['pred'] for o in sc]
         loss, comp, cell = LS.fused_losses(pred, sim, neg_sim, loc, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm,
                                            target=(best_n, gi, gj, t5), partner3=partner3)
         boxes, iou, _, _, _ = LS.decode_boxes(pred, bbox, cell[:3])

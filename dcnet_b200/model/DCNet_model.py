@@ -169,6 +169,23 @@ class grounding_model(nn.Module):
         return [self.mapping_visu._modules[str(s)].fused(raw_fvisu[s].flatten(2), l2norm=True,
                                                          precision=p0 if s == 0 else self.precision) for s in range(3)]
 
+    def map_visual_scale(self, raw_s, s):
+        p0 = ops.EXACT_FP32 if self.precision == ops.EXACT_FP32 else ops.EXACT_FWD_TF32_BWD
+        return self.mapping_visu._modules[str(s)].fused(raw_s.flatten(2), l2norm=True, precision=p0 if s == 0 else self.precision)
+
+    def correspondence_scale(self, fv_s, s, fa, fa_neg=None):
+        qa, kb = self._pair_index(fv_s.shape[0], fv_s.device)
+        attn = ops.coattention(fv_s, qa, kb, tau=self.temperature, precision=self.coattn_precision)
+        return self.corr_conv._modules[str(s)][0].fused(fv_s, x2=attn, fa=fa, l2norm=True, precision=self.precision, fa_neg=fa_neg)
+
+    def fuse_scale(self, corr_s, s, flang, coords_s):
+        C = corr_s.shape[1]
+        m = self.fcn_emb._modules[str(s)][0]
+        w = m.conv.weight.view(m.conv.weight.shape[0], -1)
+        u = F.linear(flang, w[:, C:2 * C])
+        cc = w[:, 2 * C:] @ coords_s if self.coordmap else None
+        return m.fused(corr_s, u=u, cc=cc, l2norm=False, precision=self.precision)
+
     def interframe(self, fv0, negpos=None):
         """a4 (:381-430) -> packed q [30,P,C], k [30,P,C], neg [30,P,10,C].  negpos: optional pre-drawn device tensor
         [P,30,10] int32 of ops.pyrandom_interframe positions (lets the caller keep the step free of host work)."""
