@@ -363,18 +363,46 @@ def main():
 
     pending = [pool.submit(draw, 0)]
 
+    # Input pipeline: the H2D copy of step i+1 (pinned host -> a staging set on a copy stream) runs under the GPU work of step i;
+    # at the start of a step the staged inputs move into the graph's static buffers device-to-device.  Every step's inputs
+    # still cross PCIe inside the timed region; the wall clock sees max(copy, compute) instead of their sum.
+    main_stream = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream()
+    stage = {k: [torch.empty_like(t) for t in static[k]] for k in H2D_KEYS}
+    st_negpos, st_negidx = torch.empty_like(s_negpos), torch.empty_like(s_negidx)
+    ev_staged, ev_consumed = torch.cuda.Event(), torch.cuda.Event()
+
+    def prefetch_maps(i):
+        copy_stream.wait_event(ev_consumed)                # the previous contents of the staging set have been consumed
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            hb = host[i % NB]
+            for k in H2D_KEYS:
+                for dst, src in zip(stage[k], hb[k]):
+                    dst.copy_(src, non_blocking=True)
+
+    def prefetch_indices():
+        slot = pending.pop().result()                      # drawn on the worker thread while the GPU was busy
+        pending.append(pool.submit(draw, slot ^ 1))
+        with torch.cuda.stream(copy_stream):
+            st_negpos.copy_(h_idx[slot][0], non_blocking=True); st_negidx.copy_(h_idx[slot][1], non_blocking=True)
+            ev_staged.record(copy_stream)
+
+    ev_consumed.record(main_stream)
+    prefetch_maps(0); prefetch_indices()
+
     def e2e_step(i):
-        hb = host[i % NB]
+        main_stream.wait_event(ev_staged)
         with torch.no_grad():
             for k in H2D_KEYS:
-                for dst, src in zip(static[k], hb[k]):
+                for dst, src in zip(static[k], stage[k]):
                     dst.copy_(src, non_blocking=True)
-        slot = pending.pop().result()                      # indices of this step (drawn during the previous one)
-        pending.append(pool.submit(draw, slot ^ 1))        # next step's draw overlaps this step's GPU work
-        s_negpos.copy_(h_idx[slot][0], non_blocking=True); s_negidx.copy_(h_idx[slot][1], non_blocking=True)
+            s_negpos.copy_(st_negpos, non_blocking=True); s_negidx.copy_(st_negidx, non_blocking=True)
+        ev_consumed.record(main_stream)
+        prefetch_maps(i + 1)                               # next step's maps cross PCIe under this step's kernels
         do_step()
         h_out.copy_(res, non_blocking=True)
-        torch.cuda.synchronize()
+        prefetch_indices()                                 # next step's indices (host draw finished meanwhile)
+        main_stream.synchronize()
         return float(h_out[0])
 
     for i in range(args.warmup):
@@ -385,6 +413,7 @@ def main():
         loss_val = e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    torch.cuda.synchronize()
     pending.pop().result()
     pool.shutdown()
     clocks = sampler.stop() if rank == 0 else None
@@ -476,7 +505,8 @@ def main():
                                 grad_allreduce=bool(world > 1 and not args.no_allreduce), cross_gpu_negatives=xneg),
                     clocks=clocks,
                     e2e=dict(value=e2e_val, unit="frame-pairs/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
-                             ms_per_step=e2e_ms / args.steps, last_loss=loss_val),
+                             ms_per_step=e2e_ms / args.steps, last_loss=loss_val,
+                             pipeline="H2D of step i+1 (pinned host -> staging set, copy stream) under the kernels of step i; staged -> static inputs device-to-device; loss read back every step"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                     roofline=roof, roofline_coattn=roof_co, cpu_baseline=cpu_base)
         print(json.dumps(line), flush=True)
