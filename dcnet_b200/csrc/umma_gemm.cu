@@ -17,8 +17,35 @@
 
 using namespace umma;
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+static bool g_force_v1 = false;   // tests: run the one-tile-per-CTA kernel with direct stores
+// largest cluster the persistent kernel may use.  Measured on B200 (scripts/prof_gemm.py, M=N=1024 K=512 x16, L2 flushed): no
+// clusters 44.2 us, clusters of 2 44.2 us, clusters of 4 46 us, and the C2 step 1.73 ms vs 1.79 ms -- the kernel is not bound by
+// the L2 -> SM operand traffic that multicast removes, and the cluster lock-step costs a little.  Default: off.
+static int g_cluster_max = 1;
+extern "C" int dcnet_gemm_select(int variant) {
+  g_force_v1 = (variant == 1);
+  g_cluster_max = (variant == 4) ? 4 : ((variant == 3) ? 2 : 1);
+  return 0;
+}
+
+
 namespace {
 
+#ifndef GEMM2_NSLOT
+#define GEMM2_NSLOT 2
+#endif
+#ifndef GEMM2_STAGES256
+#define GEMM2_STAGES256 4
+#endif
 constexpr int BM = 128;
 constexpr int A_BYTES = BM * 128;    // 16 KiB: 128 rows x one 128-byte swizzle row (32 tf32 or 64 bf16 along the reduction)
 // Element-size dependent geometry (EB = 4: fp32 read as TF32, EB = 2: bf16):
@@ -209,7 +236,9 @@ struct Gemm2P {
   const float* u; int ldu; const float* cc; long long ldcc; float* sum; float* sumsq;
 };
 
-template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
+// CS = cluster size: CS CTAs with consecutive M tiles of the same (batch, N tile) share the B tile -- each loads 1/CS of it and
+// multicasts (the kernel is bound by the L2 -> SM operand traffic, profiles/r1i_ncu_full_umma_gemm2.txt).
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapO,
@@ -220,10 +249,11 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int SLOT_BYTES = 32 * 128;           // 32 rows x 32 fp32
+  constexpr int NSLOT = GEMM2_NSLOT;             // staging slots per epilogue warp (TMA stores in flight per warp)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_out = smem + STAGES * STAGE_BYTES;                 // [4 warps][2][SLOT_BYTES]
-  uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + 8 * SLOT_BYTES);
+  uint8_t* stage_out = smem + STAGES * STAGE_BYTES;                 // [4 warps][NSLOT][SLOT_BYTES]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + 4 * NSLOT * SLOT_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
@@ -236,7 +266,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     prefetch_tmap(&mapB);
     prefetch_tmap(&mapB2);
     prefetch_tmap(&mapO);
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CS); }
     for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_barrier_init();
   }
@@ -246,16 +276,23 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();          // every CTA's barriers exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int per_z = p.tiles_m * p.tiles_n;
+  // work item = (batch z, N tile, group of CS consecutive M tiles); the CTAs of a cluster take the M tiles of one group
+  const int mgroups = (p.tiles_m + CS - 1) / CS;
+  const int per_z = mgroups * p.tiles_n;
+  const int ngroups = per_z * (p.ntiles / (p.tiles_m * p.tiles_n));
+  const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int cid = blockIdx.x / CS, ncl = gridDim.x / CS;
+  constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1);
 
   if (warp == 4) {
     if (elect_one()) {
       uint32_t itg = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      for (int t = cid; t < ngroups; t += ncl) {
         const int z = t / per_z, r = t - z * per_z;
-        const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+        const int m0 = ((r / p.tiles_n) * CS + crank) * BM, n0 = (r % p.tiles_n) * BN;
         const int a_b = p.a_batched ? (p.idxA ? p.idxA[z] : z) : 0;
         const int b_b = p.b_batched ? (p.idxB ? p.idxB[z] : z) : 0;
         for (int it = 0; it < p.k_iters; it++, itg++) {
@@ -275,11 +312,24 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const bool src2 = p.k_split > 0 && it >= p.k_split;
             const CUtensorMap* mb = src2 ? &mapB2 : &mapB;
             const int kc = (src2 ? it - p.k_split : it) * BK;
+            constexpr int NBLK = BN / G::MN_ELEMS;
+            if constexpr (CS > 1) {
 #pragma unroll
-            for (int j = 0; j < BN / G::MN_ELEMS; j++) tma_load_3d(sB + j * BLK_BYTES, mb, &full[s], n0 + G::MN_ELEMS * j, kc, b_b);
+              for (int j = 0; j < NBLK / CS; j++) {
+                const int jj = crank * (NBLK / CS) + j;
+                tma_load_3d_mc(sB + jj * BLK_BYTES, mb, &full[s], n0 + G::MN_ELEMS * jj, kc, b_b, cmask);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < NBLK; j++) tma_load_3d(sB + j * BLK_BYTES, mb, &full[s], n0 + G::MN_ELEMS * j, kc, b_b);
+            }
           } else {
             const bool src2 = p.n_split > 0 && n0 >= p.n_split;
-            tma_load_3d(sB, src2 ? &mapB2 : &mapB, &full[s], it * BK, src2 ? n0 - p.n_split : n0, b_b);
+            const int nrow = src2 ? n0 - p.n_split : n0;
+            if constexpr (CS > 1)
+              tma_load_3d_mc(sB + crank * (BN / CS) * 128, src2 ? &mapB2 : &mapB, &full[s], it * BK, nrow + crank * (BN / CS), b_b, cmask);
+            else
+              tma_load_3d(sB, src2 ? &mapB2 : &mapB, &full[s], it * BK, nrow, b_b);
           }
         }
       }
@@ -288,7 +338,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (elect_one()) {
       constexpr uint32_t idesc = instr_desc(G::FMT, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t itg = 0, tl = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, tl++) {
+      for (int t = cid; t < ngroups; t += ncl, tl++) {
         const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
         mbar_wait(&acc_empty[as], aph ^ 1u);          // the epilogue has drained this accumulator stage
         tc_fence_after();
@@ -308,18 +358,19 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             if constexpr (EB == 4) mma_tf32(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
             else mma_bf16(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
           }
-          mma_commit(&empty[s]);
+          if constexpr (CS > 1) mma_commit_mc(&empty[s], cmask);   // the slot is refilled by every CTA of the cluster
+          else mma_commit(&empty[s]);
         }
         mma_commit(&acc_full[as]);
       }
     }
   } else {
     // ---------------- epilogue warps 0..3: TMEM lanes 32w.. <-> output rows m0 + 32w..
-    uint8_t* slots = stage_out + warp * 2 * SLOT_BYTES;
+    uint8_t* slots = stage_out + warp * NSLOT * SLOT_BYTES;
     uint32_t tl = 0, chunk = 0;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, tl++) {
+    for (int t = cid; t < ngroups; t += ncl, tl++) {
       const int z = t / per_z, r = t - z * per_z;
-      const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+      const int m0 = ((r / p.tiles_n) * CS + crank) * BM, n0 = (r % p.tiles_n) * BN;
       const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
@@ -365,8 +416,8 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               if (nb + e < p.N_valid) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
           }
         }
-        uint8_t* slot = slots + (chunk & 1u) * SLOT_BYTES;
-        if (lane == 0) tma_store_wait_read1();          // the store that last read this slot (two chunks ago) is done with it
+        uint8_t* slot = slots + (chunk % NSLOT) * SLOT_BYTES;
+        if (lane == 0) tma_store_wait_read_n<NSLOT - 1>();   // the store that last read this slot (NSLOT chunks ago) is done with it
         __syncwarp();
         uint8_t* srow = slot + lane * 128;
 #pragma unroll
@@ -394,19 +445,53 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 5) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
-int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
-                const Gemm2P& p, int grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_BYTES + BN * 128) + 8 * 32 * 128 + 1024 + 256;
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS>
+int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
+                 const Gemm2P& p, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_BYTES + BN * 128) + 4 * GEMM2_NSLOT * 32 * 128 + 1024 + 256;
   static_assert(smem <= 232448, "umma_gemm2: shared memory budget");
-  auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB>;
+  auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB, CS>;
   DCNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "umma_gemm2.attr");
-  kern<<<grid, 192, smem, st>>>(ma, mb, mb2, mo, mo2, p);
+  const int mgroups = (p.tiles_m + CS - 1) / CS;
+  const int ngroups = mgroups * (p.ntiles / p.tiles_m);
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CS > 1 ? 1 : 0;
+  int ncl = sm_count() / CS;
+  if (CS > 1) {
+    // clusters are placed inside one GPC: ask how many fit (per template instance, cached)
+    static int max_cl = 0;
+    if (!max_cl) {
+      cfg.gridDim = dim3(sm_count() / CS * CS);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_cl = n; else { cudaGetLastError(); max_cl = sm_count() / CS; }
+    }
+    ncl = max_cl;
+  }
+  if (ncl > ngroups) ncl = ngroups;
+  cfg.gridDim = dim3(ncl * CS);
+  DCNET_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mb2, mo, mo2, p), "umma_gemm2.launch");
   DCNET_LAUNCH_OK("umma_gemm2");
   return 0;
+}
+
+// cluster size: the M tiles of a group share B.  4 when M has >= 4 tiles (C = 512 channels, N >= 512 positions), else 2, else 1.
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
+int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
+                const Gemm2P& p, int cs, cudaStream_t st) {
+  if (cs == 4) return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 4>(ma, mb, mb2, mo, mo2, p, st);
+  if (cs == 2) return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 2>(ma, mb, mb2, mo, mo2, p, st);
+  return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 1>(ma, mb, mb2, mo, mo2, p, st);
 }
 
 template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
@@ -426,18 +511,6 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
 //   K-major  use: rows = the M (or N) index, cols = the reduction index
 //   MN-major use: rows = the reduction index, cols = the M (or N) index
 // ---------------------------------------------------------------------------------------------------------------------
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
-static bool g_force_v1 = false;   // tests: run the one-tile-per-CTA kernel with direct stores
-extern "C" int dcnet_gemm_select(int variant) { g_force_v1 = (variant == 1); return 0; }
-
 static bool operand_ok(const UmmaOperand& o) {
   const int per16 = o.bf16 ? 8 : 4;     // elements per 16 bytes
   return o.ptr && (reinterpret_cast<uintptr_t>(o.ptr) % 16 == 0) && (o.ld % per16 == 0) && (o.batch_stride % per16 == 0) && o.rows > 0 && o.cols > 0;
@@ -471,10 +544,22 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   // use them once there are enough 128x256 tiles to fill the 148 SMs
   const long long tiles256 = (long long)ceil_div(N, 256) * ceil_div(M, BM) * batch;
   const int BN = (N <= 64) ? 64 : ((N >= 256 && tiles256 >= 148) ? 256 : 128);
+  // persistent kernel with TMA-store epilogue whenever the output rows are TMA-addressable
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  const bool out_ok = al16(e.out) && e.ldo % 4 == 0 && e.so_b % 4 == 0 &&
+                      (e.m_split == 0 || (e.m_split % BM == 0 && e.out2 && al16(e.out2) && e.ldo2 % 4 == 0 && e.so_b2 % 4 == 0)) &&
+                      (!e.cc || (al16(e.cc) && e.ldcc % 4 == 0)) && !(e.so_b == 0 && batch > 1 && !e.atomic) && !g_force_v1;
+  // cluster size of the persistent kernel: CTAs with consecutive M tiles share (multicast) the B tile
+  const int tiles_m = ceil_div(M, BM);
+  int cs = (!out_ok || g_cluster_max < 2 || tiles_m < 2) ? 1 : ((g_cluster_max >= 4 && tiles_m % 4 == 0) ? 4 : 2);
+  if (B.mn_major) {            // an MN-major B tile is loaded in blocks of 128 B along N: every CTA of the cluster needs >= 1 block
+    const int nblk = BN / (B.bf16 ? 64 : 32);
+    while (cs > 1 && nblk % cs != 0) cs >>= 1;
+  }
   CUtensorMap ma, mb, mb2;
   DCNET_TRY(make_operand_map(&ma, A, BM));
-  DCNET_TRY(make_operand_map(&mb, B, BN));
-  if (B2) DCNET_TRY(make_operand_map(&mb2, *B2, BN)); else mb2 = mb;
+  DCNET_TRY(make_operand_map(&mb, B, BN / cs));
+  if (B2) DCNET_TRY(make_operand_map(&mb2, *B2, BN / cs)); else mb2 = mb;
   GemmP p{};
   p.M_valid = M; p.N_valid = N;
   p.k_iters = (K + BK - 1) / BK;
@@ -486,11 +571,6 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   p.out = e.out; p.ldo = e.ldo; p.so_b = e.so_b; p.out2 = e.out2; p.ldo2 = e.ldo2; p.so_b2 = e.so_b2;
   p.alpha = e.alpha; p.atomic = e.atomic; p.u = e.u; p.ldu = e.ldu; p.cc = e.cc; p.ldcc = e.ldcc; p.sum = e.sum; p.sumsq = e.sumsq;
   const int am = A.mn_major ? 1 : 0, bm = B.mn_major ? 1 : 0;
-  // persistent kernel with TMA-store epilogue whenever the output rows are TMA-addressable
-  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
-  const bool out_ok = al16(e.out) && e.ldo % 4 == 0 && e.so_b % 4 == 0 &&
-                      (e.m_split == 0 || (e.m_split % BM == 0 && e.out2 && al16(e.out2) && e.ldo2 % 4 == 0 && e.so_b2 % 4 == 0)) &&
-                      (!e.cc || (al16(e.cc) && e.ldcc % 4 == 0)) && !(e.so_b == 0 && batch > 1 && !e.atomic) && !g_force_v1;
   if (out_ok) {
     Gemm2P q{};
     q.M_valid = M; q.N_valid = N; q.k_iters = p.k_iters; q.k_split = p.k_split; q.n_split = p.n_split; q.m_split = p.m_split;
@@ -509,17 +589,16 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
       r = make_tmap(&mo2, e.out2, 4, (uint64_t)N, rows2, nbo, (uint64_t)e.ldo2, q.out_batched ? (uint64_t)e.so_b2 : rows2 * (uint64_t)e.ldo2, 32, 32);
       if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled(out2) failed (%d)", r);
     }
-    const int grid2 = q.ntiles < sm_count() ? q.ntiles : sm_count();
-#define DISPATCH2(AM, BMJ)                                                                           \
+    #define DISPATCH2(AM, BMJ)                                                                           \
     if (am == AM && bm == BMJ) {                                                                     \
       if (A.bf16) {                                                                                  \
-        if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 2>(ma, mb, mb2, mo, mo2, q, grid2, st);     \
-        if (BN == 256) return launch_cfg2<AM, BMJ, 256, 4, 2>(ma, mb, mb2, mo, mo2, q, grid2, st);   \
-        return launch_cfg2<AM, BMJ, 128, 4, 2>(ma, mb, mb2, mo, mo2, q, grid2, st);                  \
+        if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 2>(ma, mb, mb2, mo, mo2, q, cs, st);     \
+        if (BN == 256) return launch_cfg2<AM, BMJ, 256, GEMM2_STAGES256, 2>(ma, mb, mb2, mo, mo2, q, cs, st);   \
+        return launch_cfg2<AM, BMJ, 128, 4, 2>(ma, mb, mb2, mo, mo2, q, cs, st);                  \
       }                                                                                              \
-      if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 4>(ma, mb, mb2, mo, mo2, q, grid2, st);       \
-      if (BN == 256) return launch_cfg2<AM, BMJ, 256, 4, 4>(ma, mb, mb2, mo, mo2, q, grid2, st);     \
-      return launch_cfg2<AM, BMJ, 128, 4, 4>(ma, mb, mb2, mo, mo2, q, grid2, st);                    \
+      if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 4>(ma, mb, mb2, mo, mo2, q, cs, st);       \
+      if (BN == 256) return launch_cfg2<AM, BMJ, 256, GEMM2_STAGES256, 4>(ma, mb, mb2, mo, mo2, q, cs, st);     \
+      return launch_cfg2<AM, BMJ, 128, 4, 4>(ma, mb, mb2, mo, mo2, q, cs, st);                    \
     }
     DISPATCH2(0, 0) DISPATCH2(0, 1) DISPATCH2(1, 0) DISPATCH2(1, 1)
 #undef DISPATCH2

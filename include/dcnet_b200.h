@@ -64,8 +64,9 @@ DCNET_API int dcnet_gemm_bf16(const void* A, int a_mn_major, long long lda, long
                               void* stream);
 DCNET_API int dcnet_cast_bf16(const float* x, void* y, long long n, void* stream);
 /* which tensor-core GEMM kernel every entry point of this library uses: 0 (default) = persistent kernel, two TMEM accumulator
- * stages, TMA store / reduce-add epilogue; 1 = one tile per CTA with per-thread stores (kept for outputs TMA cannot address
- * and as a cross-check in the tests).  Process-wide switch, not thread-safe: a test / bring-up knob.                          */
+ * stages, TMA store / reduce-add epilogue; 3 / 4 = the same with thread-block clusters of 2 / 4 CTAs (consecutive M tiles) that
+ * multicast the B tile; 1 = one tile per CTA with per-thread stores (kept for outputs TMA cannot address).  All variants give
+ * identical bits.  Process-wide switch, not thread-safe: a test / bring-up knob.                                              */
 DCNET_API int dcnet_gemm_select(int variant);
 
 /* ---- a1/a2/a6/a8: 1x1 conv (no bias) + BatchNorm + ReLU (+ L2 norm over channels) ---------------------

@@ -95,19 +95,28 @@ def test_gemm_bf16_all_operand_majors(a_mn, b_mn, M, N, K, batch):
     assert e < 1e-5, e
 
 
-def test_gemm_one_tile_per_cta_variant_still_agrees():
-    """dcnet_gemm_select(1): the non-persistent kernel with per-thread stores (used when TMA cannot address the output) must give
-    the same numbers as the persistent TMA-store kernel, bit for bit (same MMA order per tile)."""
+@pytest.mark.parametrize("M,N,K,batch", [(200, 680, 104, 2), (512, 1024, 256, 3), (384, 512, 160, 2), (1024, 256, 64, 1)])
+@pytest.mark.parametrize("b_mn", [0, 1])
+def test_gemm_kernel_variants_agree_bit_for_bit(M, N, K, batch, b_mn):
+    """dcnet_gemm_select: 0 = persistent kernel; 4 / 3 = the same with clusters of up to 4 / 2 CTAs multicasting the B tile
+    (M=512: 4 M tiles -> 4-CTA clusters; M=384: 3 tiles -> 2-CTA clusters with one idle slot; M=200: 2 tiles);
+    1 = one tile per CTA with per-thread stores.  Same MMA order per tile => identical bits."""
     from dcnet_b200 import _lib
-    g = gen(5)
-    A = torch.randn(2, 200, 104, generator=g).to(DEV); B = torch.randn(2, 680, 104, generator=g).to(DEV)
-    c0 = ops.gemm_tf32(A, B, 0, 0, 200, 680, 104)
-    _lib.lib().dcnet_gemm_select(1)
+    g = gen(5 + M)
+    A = torch.randn(batch, M, K, generator=g).to(DEV)
+    B = torch.randn(batch, N, K, generator=g)
+    Bd = (B.transpose(1, 2).contiguous() if b_mn else B).to(DEV)
+    ref = torch.bmm(A.double().cpu(), B.double().transpose(1, 2))
+    outs = []
     try:
-        c1 = ops.gemm_tf32(A, B, 0, 0, 200, 680, 104)
+        for v in (0, 4, 3, 1):
+            _lib.lib().dcnet_gemm_select(v)
+            outs.append(ops.gemm_tf32(A, Bd, 0, b_mn, M, N, K))
     finally:
         _lib.lib().dcnet_gemm_select(0)
-    assert torch.equal(c0, c1)
+    assert rel(outs[0], ref) < 2e-3
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
 
 
 def test_conv_linear_backward_forms_tf32():
