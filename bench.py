@@ -230,7 +230,7 @@ def main():
     ap.add_argument("--no-allreduce", action="store_true", help="N>1: skip the data-parallel gradient all-reduce of the hot-path parameters")
     ap.add_argument("--xgpu-negatives", action="store_true",
                     help="N>1: BASELINE config 5 -- rank-loss / pixel-to-text negatives from the global batch (NCCL all-gather of text vectors "
-                         "and target cells inside the step; the step then runs eagerly, NCCL is not captured)")
+                         "and target cells inside the step, captured into the step's CUDA graph with everything else)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
@@ -257,8 +257,8 @@ def main():
     synth.seed_all(13)                       # identical replicas (DDP broadcast equivalent)
     xneg = bool(args.xgpu_negatives and world > 1)
     hp = HotPath(size, cross_gpu_negatives=xneg).to(dev).train()
-    if xneg:
-        args.no_graph = True
+    if xneg and os.environ.get("DCNET_XNEG_EAGER"):
+        args.no_graph = True                 # bring-up switch: NCCL all-gathers outside any CUDA graph
     random.seed(1000 + rank)
     g = torch.Generator().manual_seed(9000 + rank)
 
@@ -522,6 +522,15 @@ def main():
                     roofline=roof, roofline_coattn=roof_co, cpu_baseline=cpu_base)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # a CUDA graph that holds captured NCCL kernels must be gone before the communicator is torn down
+        graph = None
+        res = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if xneg:
+            sys.stdout.flush()
+            os._exit(0)              # ProcessGroupNCCL teardown after captured collectives can block; nothing is left to flush
         dist.destroy_process_group()
 
 
