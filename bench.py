@@ -430,7 +430,7 @@ def main():
     # CUDA events on the launching stream, L2 flushed before every launch, on its most frequent large instance: the S = Fa^T Fb
     # recomputation of the co-attention backward at the finest scale (M = N = N2, K = 512, one problem per direction).
     # roofline_coattn: the fused co-attention forward kernel (north_star item 2), same method.
-    roof = roof_co = None
+    roof = roof_co = roof_hbm = None
     cpu_base = None
     if rank == 0:
         from dcnet_b200 import ops
@@ -483,7 +483,41 @@ def main():
                        l2="staged operands and outputs rotate over %d sets (%.0f MB)" % (NS2, NS2 * (stg[0].numel() + o_bufs[0].numel() * 4) / 1e6),
                        note="algorithmic 6*c*N^2 per pair; the kernel executes 8*c*N^2 (S recomputed per direction)",
                        peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
-        del frs, c_bufs, stg, o_bufs
+        del c_bufs, stg, o_bufs
+        # ---- HBM-bound kernels of the path against the measured copy bandwidth (north_star: fusion / normalise / decode kernels):
+        # algorithmic bytes = every tensor element read or written once, finest scale, rotating buffer sets
+        from dcnet_b200 import _lib
+        st_ = torch.cuda.current_stream().cuda_stream
+        Pp = lambda t: t.data_ptr()
+        cvec = [torch.rand(C_EMB, device=dev) + 0.5 for _ in range(4)]           # mean, invstd, gamma, beta stand-ins
+        fa_ = torch.nn.functional.normalize(torch.rand(B, C_EMB, device=dev), dim=1)
+        ys = [torch.empty_like(frs[0]) for _ in range(NSET)]
+        dvs = [torch.empty_like(frs[0]) for _ in range(NSET)]
+        sims = [torch.empty(B, N2, device=dev) for _ in range(2)]
+        sums = torch.zeros(2, C_EMB, device=dev); dfa = torch.zeros(B, C_EMB, device=dev)
+        map_bytes = frs[0].numel() * 4
+        hbm = {}
+        t_ = timed_sets([(lambda i=i: _lib.call("dcnet_bn_act_fwd", Pp(frs[i]), Pp(cvec[0]), Pp(cvec[1]), Pp(cvec[2]), Pp(cvec[3]), 0.0, 1, Pp(ys[i]),
+                                                 Pp(fa_), None, Pp(sims[0]), Pp(sims[1]), B, C_EMB, N2, st_)) for i in range(NSET)])
+        hbm["bn_act_fwd_kernel (BN + ReLU + channel L2 norm + pixel-to-text dots: z read once, y written once)"] = (2 * map_bytes, t_)
+        t_ = timed_sets([(lambda i=i: _lib.call("dcnet_bn_act_bwd_reduce", Pp(frs[i]), Pp(cvec[0]), Pp(cvec[1]), Pp(cvec[2]), Pp(cvec[3]), 0.0, 1,
+                                                 Pp(ys[i]), Pp(fa_), None, Pp(sims[0]), Pp(sims[1]), Pp(dvs[i]), Pp(sums[0]), Pp(sums[1]), Pp(dfa), None,
+                                                 B, C_EMB, N2, st_)) for i in range(NSET)])
+        hbm["bn_act_bwd_reduce_kernel (reads z, dy; writes dv; channel sums)"] = (3 * map_bytes, t_)
+        t_ = timed_sets([(lambda i=i: _lib.call("dcnet_bn_act_bwd_apply", Pp(frs[i]), Pp(cvec[0]), Pp(cvec[1]), Pp(cvec[2]), Pp(dvs[i]), Pp(sums[0]),
+                                                 Pp(sums[1]), 1, Pp(dvs[i]), B, C_EMB, N2, st_)) for i in range(NSET)])
+        hbm["bn_act_bwd_apply_kernel (reads z, dv; writes dz)"] = (3 * map_bytes, t_)
+        g2 = size // 8
+        yin = [torch.randn(B, 255, g2, g2, device=dev) for _ in range(NSET)]
+        anc = [(10, 13), (16, 30), (33, 23)]
+        t_ = timed_sets([(lambda i=i: ops.yolo_layer_decode(yin[i], anc, 80, size)) for i in range(NSET)])
+        hbm["yolo_decode_kernel (a19, [B,255,g,g] -> [B,3gg,85])"] = (2 * yin[0].numel() * 4, t_)
+        # what a plain device copy of the same footprint reaches in this harness (torch copy_: read + write of one map)
+        t_copy = timed_sets([(lambda i=i: ys[i].copy_(frs[i])) for i in range(NSET)])
+        copy_gbs = 2 * map_bytes / (t_copy * 1e-3) / 1e9
+        roof_hbm = [dict(bound="hbm", kernel=k, achieved=b_ / (t * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s", frac=b_ / (t * 1e-3) / 1e9 / peaks["hbm"],
+                         ms=t, bytes=b_, traffic=None, copy_same_size_gbs=copy_gbs) for k, (b_, t) in hbm.items()]
+        del frs, ys, dvs, yin
         if world == 1 and not args.no_cpu_baseline:
             from oracle import dcnet_oracle as O
             cores = os.cpu_count() or 1
@@ -519,7 +553,7 @@ def main():
                              ms_per_step=e2e_ms / args.steps, last_loss=loss_val,
                              pipeline="H2D of step i+1 (pinned host -> staging set, copy stream) under the kernels of step i; staged -> static inputs device-to-device; loss read back every step"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
-                    roofline=roof, roofline_coattn=roof_co, cpu_baseline=cpu_base)
+                    roofline=roof, roofline_coattn=roof_co, roofline_hbm=roof_hbm, cpu_baseline=cpu_base)
         print(json.dumps(line), flush=True)
     if world > 1:
         # a CUDA graph that holds captured NCCL kernels must be gone before the communicator is torn down

@@ -3,6 +3,10 @@
 // sim_score products (model/DCNet_model.py:530-535, train_DCNet.py:623-627).
 #include "common.cuh"
 
+#ifndef BNF_CPT
+#define BNF_CPT 32      // channels per thread of bn_act_fwd at C = 512 (32 -> 16 groups, 512-thread CTAs; 64 -> 8 groups)
+#endif
+
 namespace {
 
 inline int ew_grid(long long total) {
@@ -131,19 +135,19 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const floa
 // holds 32 consecutive positions of one channel -> every global access is a full 128-B line.  Each thread keeps
 // its CPT = C/8 channel values of one position in registers, so z is read once and y written once.
 // ------------------------------------------------------------------------------------------------------
-template <int CPT>
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+template <int CPT, int G>
+__global__ void __launch_bounds__(32 * G) bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float slope, int l2norm,
                                                          float* __restrict__ y, const float* __restrict__ fa, const float* __restrict__ fa_neg,
                                                          float* __restrict__ sim, float* __restrict__ neg_sim, int B, int N) {
-  constexpr int C = CPT * 8;
+  constexpr int C = CPT * G;
   __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
-  __shared__ float red[3][8][33];
+  __shared__ float red[3][G][33];
   const int b = blockIdx.y;
   const int pl = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + pl;
-  for (int c = threadIdx.x; c < C; c += 256) {
+  for (int c = threadIdx.x; c < C; c += 32 * G) {
     const float sc = gamma[c] * invstd[c];
     s_scale[c] = sc;
     s_shift[c] = beta[c] - mean[c] * sc;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
   float ss = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
   for (int i = 0; i < CPT; i++) {
-    const int c = g + 8 * i;
+    const int c = g + G * i;
     float a = valid ? zp[(long long)c * N] : 0.f;
     a = fmaf(a, s_scale[c], s_shift[c]);
     a = a > 0.f ? a : a * slope;
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
     __syncthreads();
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < G; k++) {
       t0 += red[0][k][pl];
       t1 += red[1][k][pl];
       t2 += red[2][k][pl];
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
   if (valid) {
     float* yp = y + (long long)b * C * N + n;
 #pragma unroll
-    for (int i = 0; i < CPT; i++) yp[(long long)(g + 8 * i) * N] = v[i] * inv;
+    for (int i = 0; i < CPT; i++) yp[(long long)(g + G * i) * N] = v[i] * inv;
   }
 }
 
@@ -566,9 +570,9 @@ extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* 
   DCNET_CHECK_ARG(B <= 65535, "bn_act_fwd: B too large");
   dim3 grid(ceil_div(N, 32), B);
   if (C == 512)
-    bn_act_fwd_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
+    bn_act_fwd_kernel<BNF_CPT, 512 / BNF_CPT><<<grid, 32 * (512 / BNF_CPT), 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
   else
-    bn_act_fwd_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
+    bn_act_fwd_kernel<32, 8><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
   DCNET_LAUNCH_OK("bn_act_fwd");
   return 0;
 }

@@ -354,31 +354,63 @@ __global__ void bbox_iou_kernel(const float* __restrict__ b1, const float* __res
 // ------------------------------------------------------------------------------------------------------
 constexpr int YMAX_ATTR = 96;
 struct AnchorsA { float w[8], h[8]; };
-__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ x, float* __restrict__ out, int A, int nattr, int g,
+// CTA = 128 cells of one (image, anchor): the [nattr][128] slab is read along the cells (coalesced, float4 when the row pitch
+// allows), transposed through shared memory, and the contiguous [128][nattr] output slab is written linearly with float4.
+// NATTR > 0 fixes the attribute count at compile time (85 for the COCO head) so i / nattr, i % nattr are multiplications.
+constexpr int YCELLS = 128;
+template <int NATTR>
+__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ x, float* __restrict__ out, int A, int nattr_rt, int g,
                                                           float stride, AnchorsA an) {
-  __shared__ float tile[YMAX_ATTR][33];
+  extern __shared__ float ytile[];                    // [nattr][YCELLS + 1]
+  const int nattr = NATTR > 0 ? NATTR : nattr_rt;
+  constexpr int LD = YCELLS + 1;
   const int gg = g * g;
-  const int c0 = blockIdx.x * 32;
+  const int c0 = blockIdx.x * YCELLS;
   const int a = blockIdx.y, b = blockIdx.z;
   const float* xp = x + ((long long)b * A + a) * nattr * gg;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool vec = (gg & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const float aw = an.w[a], ah = an.h[a];
   for (int at = w; at < nattr; at += 8) {
-    const int cell = c0 + lane;
-    float v = 0.f;
-    if (cell < gg) {
-      v = xp[(long long)at * gg + cell];
-      if (at == 0) v = __fmul_rn(__fadd_rn(sigmoidf_(v), (float)(cell % g)), stride);
-      else if (at == 1) v = __fmul_rn(__fadd_rn(sigmoidf_(v), (float)(cell / g)), stride);
-      else if (at == 2) v = __fmul_rn(__fmul_rn(expf(v), an.w[a]), stride);
-      else if (at == 3) v = __fmul_rn(__fmul_rn(expf(v), an.h[a]), stride);
-      else v = sigmoidf_(v);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int cell = c0 + lane * 4;
+    if (vec && cell + 3 < gg) {
+      const float4 q = *reinterpret_cast<const float4*>(xp + (long long)at * gg + cell);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (cell + e < gg) v[e] = xp[(long long)at * gg + cell + e];
     }
-    tile[at][lane] = v;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int ce = cell + e;
+      float r = v[e];
+      if (at == 0) r = __fmul_rn(__fadd_rn(sigmoidf_(r), (float)(ce % g)), stride);
+      else if (at == 1) r = __fmul_rn(__fadd_rn(sigmoidf_(r), (float)(ce / g)), stride);
+      else if (at == 2) r = __fmul_rn(__fmul_rn(expf(r), aw), stride);
+      else if (at == 3) r = __fmul_rn(__fmul_rn(expf(r), ah), stride);
+      else r = sigmoidf_(r);
+      ytile[at * LD + lane * 4 + e] = r;
+    }
   }
   __syncthreads();
-  const int ncell = min(32, gg - c0);
+  const int ncell = min(YCELLS, gg - c0);
+  const int total = ncell * nattr;
   float* op = out + (((long long)b * A + a) * gg + c0) * nattr;
-  for (int i = threadIdx.x; i < ncell * nattr; i += blockDim.x) op[i] = tile[i % nattr][i / nattr];
+  const bool ovec = (reinterpret_cast<uintptr_t>(op) & 15) == 0;
+  for (int i = threadIdx.x * 4; i < total; i += blockDim.x * 4) {
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int ii = min(i + e, total - 1);
+      const int cl = ii / nattr, at = ii - cl * nattr;
+      r[e] = ytile[at * LD + cl];
+    }
+    if (ovec && i + 3 < total) *reinterpret_cast<float4*>(op + i) = make_float4(r[0], r[1], r[2], r[3]);
+    else
+      for (int e = 0; e < 4 && i + e < total; e++) op[i + e] = r[e];
+  }
 }
 
 __global__ void iou_loss_sums_kernel(const float* __restrict__ x, const float* __restrict__ t, long long n, float* __restrict__ acc) {
@@ -538,8 +570,15 @@ extern "C" int dcnet_yolo_layer_decode(const float* x, float* out, int B, int A,
     an.h[a] = (float)((double)h_anchorsAx2[2 * a + 1] / div);
   }
   const float stride = (float)((double)image_dim / (double)g);   // :266
-  dim3 grid(ceil_div(g * g, 32), A, B);
-  yolo_decode_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, out, A, 5 + nc, g, stride, an);
+  dim3 grid(ceil_div(g * g, YCELLS), A, B);
+  const int nattr = 5 + nc;
+  const size_t smem = (size_t)nattr * (YCELLS + 1) * sizeof(float);
+  if (nattr == 85) {
+    yolo_decode_kernel<85><<<grid, 256, smem, as_stream(stream)>>>(x, out, A, nattr, g, stride, an);
+  } else {
+    DCNET_CHECK_ARG(smem <= 48 * 1024, "yolo_layer_decode: %d attributes per anchor exceed the shared-memory tile", nattr);
+    yolo_decode_kernel<0><<<grid, 256, smem, as_stream(stream)>>>(x, out, A, nattr, g, stride, an);
+  }
   DCNET_LAUNCH_OK("yolo_layer_decode");
   return 0;
 }
