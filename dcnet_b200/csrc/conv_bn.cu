@@ -577,6 +577,13 @@ extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* 
   return 0;
 }
 
+int bn_bwd_reduce_staged(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                      int l2norm, const float* dy, const float* fa, const float* fa_neg, const float* dsim, const float* dneg,
+                      float* dv, float* sum_dv, float* sum_dvz, float* dfa, float* dfa_neg, int B, int Cc, int N, cudaStream_t st);
+static bool g_bn_bwd_no_staged = false;
+// test / bring-up knob: 1 = always use the register-staged kernel
+extern "C" int dcnet_bn_bwd_select(int variant) { g_bn_bwd_no_staged = (variant == 1); return 0; }
+
 extern "C" int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                        float slope, int l2norm, const float* dy, const float* fa, const float* fa_neg, const float* dsim,
                                        const float* dneg_sim, float* dv, float* sum_dv, float* sum_dvz, float* dfa, float* dfa_neg,
@@ -584,6 +591,12 @@ extern "C" int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const 
   DCNET_CHECK_ARG(z && mean && invstd && gamma && beta && dv && sum_dv && sum_dvz && B > 0 && N > 0, "bn_act_bwd_reduce: bad arguments");
   DCNET_CHECK_ARG(dy || fa, "bn_act_bwd_reduce: no incoming gradient");
   DCNET_CHECK_ARG(C == 512 || C == 256, "bn_act_bwd_reduce: C=%d unsupported (512 or 256)", C);
+  if (!g_bn_bwd_no_staged) {
+    // persistent smem-staged kernel (bn_bwd_staged.cu) when the maps are TMA-addressable
+    const int r = bn_bwd_reduce_staged(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, fa_neg, dsim, dneg_sim, dv, sum_dv, sum_dvz, dfa,
+                                    dfa_neg, B, C, N, as_stream(stream));
+    if (r != -2147483647) return r;
+  }
   dim3 grid(ceil_div(N, 32), B);
   if (C == 512)
     bn_act_bwd_reduce_kernel<32, 16><<<grid, 512, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, dy, fa, fa_neg, dsim,

@@ -123,6 +123,9 @@ DCNET_API int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const f
                                       float slope, int l2norm, const float* dy, const float* fa, const float* fa_neg, const float* dsim,
                                       const float* dneg_sim, float* dv, float* sum_dv, float* sum_dvz, float* dfa, float* dfa_neg,
                                       int B, int C, int N, void* stream);
+/* 0 (default): dcnet_bn_act_bwd_reduce uses the persistent smem-staged kernel when C == 512 and the maps are 16-byte addressable
+ * (N % 4 == 0, 16-byte aligned); 1: always the register-staged kernel.  Test / bring-up knob, process-wide.                */
+DCNET_API int dcnet_bn_bwd_select(int variant);
 DCNET_API int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const float* invstd, const float* gamma,
                                      const float* dv, const float* sum_dv, const float* sum_dvz, int train,
                                      float* dz, int B, int C, int N, void* stream);

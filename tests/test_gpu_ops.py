@@ -239,6 +239,37 @@ def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, t
     assert float(c['w'].grad[:, K:].abs().max()) == 0.0 if c['w'].shape[1] > K else True
 
 
+@pytest.mark.parametrize("B,N,l2norm,use_fa,use_dy", [(3, 64, 1, 1, 1), (2, 676, 1, 1, 1), (4, 1024, 0, 0, 1), (2, 256, 1, 1, 0), (5, 20, 1, 1, 1)])
+def test_bn_bwd_reduce_staged_kernel_matches_register_kernel(B, N, l2norm, use_fa, use_dy):
+    """dcnet_bn_act_bwd_reduce: the persistent smem-staged kernel (default when C=512, N%4==0) against the register-staged one
+    (dcnet_bn_bwd_select(1)) on the same inputs: dv within fp32 rounding (different summation order of the per-position norms),
+    channel sums / dfa within 1e-5 of their scale; ragged last tile (N=676, N=20 < one tile)."""
+    from dcnet_b200 import _lib
+    g = gen(100 + N)
+    C = 512
+    z = torch.randn(B, C, N, generator=g).to(DEV); dy = torch.randn(B, C, N, generator=g).to(DEV)
+    mean = (torch.randn(C, generator=g) * 0.1).to(DEV); invstd = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV); beta = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    fa = torch.nn.functional.normalize(torch.rand(B, C, generator=g), dim=1).to(DEV)
+    dsim = torch.randn(B, N, generator=g).to(DEV); dneg = torch.randn(B, N, generator=g).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    res = []
+    try:
+        for v in (0, 1):
+            _lib.lib().dcnet_bn_bwd_select(v)
+            dv = torch.full((B, C, N), 7.0, device=DEV); sums = torch.zeros(2, C, device=DEV); dfa = torch.zeros(B, C, device=DEV)
+            _lib.call("dcnet_bn_act_bwd_reduce", z.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 0.0, l2norm,
+                      dy.data_ptr() if use_dy else None, fa.data_ptr() if use_fa else None, None, dsim.data_ptr() if use_fa else None,
+                      dneg.data_ptr() if use_fa else None, dv.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(),
+                      dfa.data_ptr() if use_fa else None, None, B, C, N, st)
+            res.append((dv, sums, dfa))
+    finally:
+        _lib.lib().dcnet_bn_bwd_select(0)
+    (dv0, s0, f0), (dv1, s1, f1) = res
+    assert rel(dv0, dv1) < 1e-6, rel(dv0, dv1)
+    assert rel(s0, s1) < 1e-5 and rel(f0, f1) < 1e-5, (rel(s0, s1), rel(f0, f1))
+
+
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision", [0, 1, 2])
 @pytest.mark.parametrize("P,N", [(2, 64), (2, 169), (1, 256), (1, 676), (1, 1024)])
