@@ -64,19 +64,26 @@ __global__ void negidx_kernel(const long long* __restrict__ idx, const int* __re
 }
 
 // cols[p, :] = [ idx//N0 (top_k) | idx%N0 (top_k) | negatives (top_k*neg_n) ]: every gather column of a4 in one launch
+// rank-major layout: cols = [q: top_k x P | k: top_k x P | neg: top_k x P x neg_n], so the gathered rows are already the packed
+// [rank][pair] tensors the contrastive loss consumes (no transposes / stacks afterwards)
 __global__ void interframe_cols_kernel(const long long* __restrict__ idx, const int* __restrict__ negpos, int P, int N0, int top_k, int neg_n,
                                        long long* __restrict__ cols) {
-  const int per = top_k * (2 + neg_n);
+  const int nq = top_k * P;
+  const int total = nq * (2 + neg_n);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * per) return;
-  const int p = i / per, r = i % per;
+  if (i >= total) return;
   long long v;
-  if (r < top_k) v = idx[(long long)p * top_k + r] / N0;
-  else if (r < 2 * top_k) v = idx[(long long)p * top_k + (r - top_k)] % N0;
-  else {
-    const int q = r - 2 * top_k;                       // rank * neg_n + j
-    const int col = (int)(idx[(long long)p * top_k + q / neg_n] % N0);
-    const int pos = negpos[(long long)p * top_k * neg_n + q];
+  if (i < 2 * nq) {
+    const int j = i < nq ? i : i - nq;                 // rank * P + pair
+    const int r = j / P, p = j - r * P;
+    const long long f = idx[(long long)p * top_k + r];
+    v = i < nq ? f / N0 : f % N0;
+  } else {
+    const int j = i - 2 * nq;                          // (rank * P + pair) * neg_n + t
+    const int t = j % neg_n, rp = j / neg_n;
+    const int r = rp / P, p = rp - r * P;
+    const int col = (int)(idx[(long long)p * top_k + r] % N0);
+    const int pos = negpos[((long long)p * top_k + r) * neg_n + t];
     v = pos + (pos >= col ? 1 : 0);
   }
   cols[i] = v;

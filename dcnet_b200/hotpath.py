@@ -74,11 +74,31 @@ class HotPath(nn.Module):
             with torch.cuda.stream(st):
                 outs[s] = chain(s)
         outs[2] = chain(2)
+        if getattr(self, "_aux_pending", False):
+            for aux in self._aux:
+                cur.wait_stream(aux)
+            self._aux_pending = False
         for s in (0, 1):
             cur.wait_stream(self._side[s])
             for t in _tensors(outs[s]):
                 t.record_stream(cur)          # produced on a side stream, consumed (and later freed) on the caller's stream
         return outs
+
+    def _branch(self, i, fn, *inputs):
+        """fn() on auxiliary stream i, forked from the current one; joined by _run_scales (or immediately without streams)"""
+        if not self.scale_streams:
+            return fn()
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_aux", None) is None:
+            self._aux = [torch.cuda.Stream(), torch.cuda.Stream()]
+        aux = self._aux[i]
+        aux.wait_stream(cur)
+        with torch.cuda.stream(aux):
+            out = fn()
+        for t in inputs:
+            t.record_stream(aux)
+        self._aux_pending = True
+        return out
 
     def draw_indices(self, B):
         """host side of the sampling blocks: exact reference RNG stream -> (negpos [P,30,10] int32, negidx [B,N0,5] int64) numpy"""
@@ -99,8 +119,18 @@ class HotPath(nn.Module):
             o = {}
             o['fv'] = net.map_visual_scale(raw[s], s)
             if s == 0:
-                o['if'] = net.interframe(o['fv'], negpos)
-                o['cm'] = net.crossmodal(o['fv'], context, negidx)
+                # the two sampling blocks and their InfoNCE losses only need fvisu[0]: a branch of their own next to the
+                # co-attention / fusion chain of this scale (forward and, through autograd, backward)
+                # (the host RNG stream is consumed in the reference's order: inter-frame draws, then cross-modal draws)
+                def inter():
+                    r = net.interframe(o['fv'], negpos)
+                    return {'if': r, 'l_if': LS.Interframe_contrastive_loss(*r[:3])}
+
+                def cross():
+                    r = net.crossmodal(o['fv'], context, negidx)
+                    return {'cm': r, 'l_cm': LS.Crossmodal_constrastive_loss(*r[:3])}
+                o.update(self._branch(0, inter, o['fv']))
+                o.update(self._branch(1, cross, o['fv']))
             o['corr'], o['sim'], o['neg_sim'] = net.correspondence_scale(o['fv'], s, fa, fa_neg)
             coords = ops.coord_map(hw[s][0], hw[s][1], fa.device).flatten(1)
             o['y'] = net.fuse_scale(o['corr'], s, flang, coords)
@@ -117,7 +147,7 @@ class HotPath(nn.Module):
         oo_obj = [o['obj'] for o in sc]
         pred = [o['pred'] for o in sc]
         loss, comp, cell = LS.fused_losses(pred, sim, neg_sim, loc, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm,
-                                           target=(best_n, gi, gj, t5), partner3=partner3)
+                                           target=(best_n, gi, gj, t5), partner3=partner3, l_if=sc[0]['l_if'], l_cm=sc[0]['l_cm'])
         boxes, iou, _, _, _ = LS.decode_boxes(pred, bbox, cell[:3])
         return dict(loss=loss, comp=comp, y=y, iou=iou, boxes=boxes, cell=cell, corr=corr, sim=sim, pred=pred,
                     obj=[o[1] for o in oo_obj], idx_if=idx_if, word=word)

@@ -36,6 +36,8 @@ def _as_index(x, device):
 
 
 def _packed(lst, dim_fix=None):
+    if torch.is_tensor(lst):
+        return lst                      # already packed [R, ...] (dcnet_b200.model returns packed tensors)
     p = getattr(lst, "packed", None)
     return p if p is not None else torch.stack(list(lst))
 
@@ -150,7 +152,8 @@ def negative_sim_score(flang_attn, corr_feat):
     return [(fa * c[:, :512]).sum(1) for c in corr_feat]
 
 
-def fused_losses(pred_anchor, sim_score, neg_sim_score, loc_score, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm, target=None, partner3=None):
+def fused_losses(pred_anchor, sim_score, neg_sim_score, loc_score, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm, target=None, partner3=None,
+                 l_if=None, l_cm=None):
     """train_DCNet.py:615-642 in one pass: targets + the three grounding losses from one kernel + the two InfoNCE losses.
     Returns (loss, dict of the five components, (best_n, gi, gj, t5))."""
     if target is None:
@@ -158,8 +161,11 @@ def fused_losses(pred_anchor, sim_score, neg_sim_score, loc_score, bbox, q_if, k
     else:
         best_n, gi, gj, t5 = target
     g = ops.ground_losses(pred_anchor, sim_score, neg_sim_score, loc_score, best_n, gi, gj, t5, partner3=partner3)
-    l_if = Interframe_contrastive_loss(q_if, k_if, neg_if)
-    l_cm = Crossmodal_constrastive_loss(q_cm, k_cm, neg_cm)
+    # l_if / l_cm: the two InfoNCE losses when the caller has already computed them (on another stream, dcnet_b200/hotpath.py)
+    if l_if is None:
+        l_if = Interframe_contrastive_loss(q_if, k_if, neg_if)
+    if l_cm is None:
+        l_cm = Crossmodal_constrastive_loss(q_cm, k_cm, neg_cm)
     loss = g[0] + 100 * g[1] + g[2] + 100 * l_if + l_cm
     return loss, dict(yolo=g[0], rank=g[1], loc=g[2], interframe=l_if, cross=l_cm), (best_n, gi, gj, t5)
 

@@ -195,19 +195,19 @@ class grounding_model(nn.Module):
         idx, _ = ops.interframe_topk(fv0.detach(), TOP_K)
         if negpos is None:
             negpos = torch.from_numpy(ops.pyrandom_interframe(P, TOP_K, N0, NEG_N)).to(dev, non_blocking=True)
-        cols = ops.interframe_cols(idx, negpos, N0)                  # [P, 30 | 30 | 300]
+        cols = ops.interframe_cols(idx, negpos, N0)                  # rank-major: q [30,P] | k [30,P] | neg [30,P,10]
         key = ("if", P, str(dev))
         if key not in self._idx_cache:
-            pair = torch.arange(P, device=dev, dtype=torch.int32)[:, None]
-            self._idx_cache[key] = torch.cat([(2 * pair).expand(P, TOP_K), (2 * pair + 1).expand(P, TOP_K),
-                                              (2 * pair + 1).expand(P, TOP_K * NEG_N)], 1).reshape(-1).contiguous()
+            pair = torch.arange(P, device=dev, dtype=torch.int32)[None, :]
+            self._idx_cache[key] = torch.cat([(2 * pair).expand(TOP_K, P).reshape(-1), (2 * pair + 1).expand(TOP_K, P).reshape(-1),
+                                              (2 * pair + 1)[:, :, None].expand(TOP_K, P, NEG_N).reshape(-1)]).contiguous()
         img = self._idx_cache[key]
-        col = cols.reshape(-1)
-        negidx = cols[:, 2 * TOP_K:].reshape(P, TOP_K, NEG_N)
-        g = ops.gather_cols(fv0, img, col).view(P, TOP_K * (2 + NEG_N), C)
-        q = g[:, :TOP_K].transpose(0, 1)
-        k = g[:, TOP_K:2 * TOP_K].transpose(0, 1)
-        neg = g[:, 2 * TOP_K:].reshape(P, TOP_K, NEG_N, C).transpose(0, 1)
+        nq = TOP_K * P
+        negidx = cols[2 * nq:].view(TOP_K, P, NEG_N).permute(1, 0, 2)
+        g = ops.gather_cols(fv0, img, cols)                          # [30*P*(2+10), C], already in the packed order of the loss
+        q = g[:nq].view(TOP_K, P, C)
+        k = g[nq:2 * nq].view(TOP_K, P, C)
+        neg = g[2 * nq:].view(TOP_K, P, NEG_N, C)
         return q, k, neg, idx, negidx
 
     def correspondence(self, fv, fa, fa_neg=None):

@@ -128,10 +128,10 @@ def interframe_negidx(idx, negpos, N0):
 
 
 def interframe_cols(idx, negpos, N0):
-    """-> cols [P, top_k*(2+neg_n)] int64: gather columns of q | k | negatives"""
+    """-> cols [top_k*P*(2+neg_n)] int64, rank-major: gather columns of q [top_k,P] | k [top_k,P] | negatives [top_k,P,neg_n]"""
     P, top_k = idx.shape
     neg_n = negpos.shape[-1]
-    out = torch.empty(P, top_k * (2 + neg_n), device=idx.device, dtype=torch.long)
+    out = torch.empty(P * top_k * (2 + neg_n), device=idx.device, dtype=torch.long)
     _lib.call("dcnet_interframe_cols", _p(idx), _p(_c(negpos, torch.int32, "negpos")), P, N0, top_k, neg_n, _p(out), _st())
     return out
 

@@ -175,8 +175,9 @@ DCNET_API int dcnet_interframe_topk(const float* fv0, int P, int C, int N0, int 
 DCNET_API int dcnet_interframe_negidx(const long long* idx, const int* negpos, int P, int N0, int top_k, int neg_n,
                                       long long* negidx, void* stream);
 
-/* cols [P, top_k*(2+neg_n)] int64 = [frame-1 column idx//N0 | frame-2 column idx%N0 | negative columns] per pair: the gather
- * columns of q, k and neg (model/DCNet_model.py:407-420) in one launch.                                                */
+/* cols [top_k*P*(2+neg_n)] int64, rank-major: [frame-1 column idx//N0 : top_k x P | frame-2 column idx%N0 : top_k x P |
+ * negative columns : top_k x P x neg_n] -- the gather columns of q, k and neg (model/DCNet_model.py:407-420) in one launch,
+ * ordered so that the gathered rows are the packed [rank][pair] tensors of the contrastive loss.                        */
 DCNET_API int dcnet_interframe_cols(const long long* idx, const int* negpos, int P, int N0, int top_k, int neg_n, long long* cols, void* stream);
 
 /* ---- generic column gather / scatter-add (a4, a11 gathers and their backward) -------------------------
