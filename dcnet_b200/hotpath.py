@@ -114,6 +114,13 @@ class HotPath(nn.Module):
         if self.cross_gpu_negatives:
             fa_neg, partner3 = parallel.global_partners(fa, best_n, gi, gj)
 
+        # text / coordinate terms of the three fusion layers: tiny cuBLAS products that depend on nothing of the chains.  On an
+        # auxiliary stream their backward (weight / text gradients) also stays off the chains' critical path.
+        def fusion_terms():
+            return [net.fuse_terms(s, flang, ops.coord_map(hw[s][0], hw[s][1], fa.device).flatten(1)) for s in range(3)]
+        terms = self._branch(0, fusion_terms, flang)
+        ev_terms = self._aux[0].record_event() if self.scale_streams else None
+
         def chain(s):
             """everything of one pyramid scale: a2 -> (a4, a11 on the coarsest scale) -> a5/a6/a9 -> a7/a8 -> a10"""
             o = {}
@@ -132,8 +139,12 @@ class HotPath(nn.Module):
                 o.update(self._branch(0, inter, o['fv']))
                 o.update(self._branch(1, cross, o['fv']))
             o['corr'], o['sim'], o['neg_sim'] = net.correspondence_scale(o['fv'], s, fa, fa_neg)
-            coords = ops.coord_map(hw[s][0], hw[s][1], fa.device).flatten(1)
-            o['y'] = net.fuse_scale(o['corr'], s, flang, coords)
+            if ev_terms is not None:
+                torch.cuda.current_stream().wait_event(ev_terms)
+                for t in terms[s]:
+                    if t is not None:
+                        t.record_stream(torch.cuda.current_stream())
+            o['y'] = net.fuse_scale(o['corr'], s, flang, None, terms=terms[s])
             o['obj'] = ops.only_obj(head[s], o['sim'])
             o['pred'] = ops.modulate_conf(head[s], o['sim'], loc[s])
             return o

@@ -178,12 +178,17 @@ class grounding_model(nn.Module):
         attn = ops.coattention(fv_s, qa, kb, tau=self.temperature, precision=self.coattn_precision)
         return self.corr_conv._modules[str(s)][0].fused(fv_s, x2=attn, fa=fa, l2norm=True, precision=self.precision, fa_neg=fa_neg)
 
-    def fuse_scale(self, corr_s, s, flang, coords_s):
-        C = corr_s.shape[1]
+    def fuse_terms(self, s, flang, coords_s, C=512):
+        """the text and coordinate terms of the split-weight fusion: u = W_l flang [B,C], cc = W_c coord [C,N]"""
         m = self.fcn_emb._modules[str(s)][0]
         w = m.conv.weight.view(m.conv.weight.shape[0], -1)
         u = F.linear(flang, w[:, C:2 * C])
         cc = w[:, 2 * C:] @ coords_s if self.coordmap else None
+        return u, cc
+
+    def fuse_scale(self, corr_s, s, flang, coords_s, terms=None):
+        m = self.fcn_emb._modules[str(s)][0]
+        u, cc = terms if terms is not None else self.fuse_terms(s, flang, coords_s, corr_s.shape[1])
         return m.fused(corr_s, u=u, cc=cc, l2norm=False, precision=self.precision)
 
     def interframe(self, fv0, negpos=None):
