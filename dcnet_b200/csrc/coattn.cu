@@ -108,7 +108,8 @@ extern "C" int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const
 
 extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                 const float* out, int n_out, const float* lse, const float* dout, float* dframes,
-                                int C, int N, float tau, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+                                int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,
+                                void* stream) {
   (void)out;
   DCNET_CHECK_ARG(frames && qa && kb && oidx && lse && dout && dframes && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_bwd: bad arguments");
   if (nprob == 0) return 0;
@@ -135,11 +136,21 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
     UmmaOperand Pmn{P, N, N, N, NN, nprob, true};
     UmmaOperand dSk{dP, N, N, N, NN, nprob, false}, dSmn{dP, N, N, N, NN, nprob, true};
     UmmaEpilogue e{};
-    // P = exp(tau S - lse)
     e.out = P; e.ldo = N; e.so_b = NN; e.alpha = tau; e.idxA = qa; e.idxB = kb;
-    DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
-    exp_launch();
-    DCNET_LAUNCH_OK("coattn_bwd.exp");
+    if (precision == 2 && staged && reinterpret_cast<uintptr_t>(staged) % 256 == 0 && umma_coattn_supported(C, N)) {
+      // P = exp(tau S - lse) in one kernel: S from the forward's bf16 staging of the maps -- the same operand bits the fused
+      // forward took its lse from, so the rows of P sum to one without a renormalisation pass -- and exp in the GEMM epilogue
+      const int ld = (N + 7) & ~7;
+      const float* s16 = reinterpret_cast<const float*>(staged);
+      UmmaOperand Smn{s16, C, N, ld, (long long)C * ld, F, true, true};
+      e.epi_exp = 1; e.u = lse; e.ldu = N;
+      DCNET_TRY(umma_gemm(Smn, Smn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    } else {
+      // P = exp(tau S - lse) (precision 1) / softmax(tau S) (precision 2 without the forward's staging)
+      DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+      exp_launch();
+      DCNET_LAUNCH_OK("coattn_bwd.exp");
+    }
     // dP[i,j] = sum_c dO[c,i] Fb[c,j]
     e = UmmaEpilogue{}; e.out = dP; e.ldo = N; e.so_b = NN; e.alpha = 1.f; e.idxA = oidx; e.idxB = kb;
     DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));

@@ -88,6 +88,7 @@ struct UmmaEpilogue {
   float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2; int m_split;
   float alpha; int atomic; const float* u; int ldu; const float* cc; long long ldcc; float* sum; float* sumsq;
   const int* idxA; const int* idxB; const int* idxC;
+  int epi_exp = 0;     // persistent kernel only: v = exp(alpha*acc - u[z*ldu + row])  (P from recomputed logits and the saved lse)
 };
 bool umma_gemm_usable(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int K);
 int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int M, int N, int K, int k_split_elems, int n_split,

@@ -234,6 +234,7 @@ struct Gemm2P {
   int tiles_m, tiles_n, ntiles;
   float alpha; int atomic;
   const float* u; int ldu; const float* cc; long long ldcc; float* sum; float* sumsq;
+  int epi_exp;
 };
 
 // CS = cluster size: CS CTAs with consecutive M tiles of the same (batch, N tile) share the B tile -- each loads 1/CS of it and
@@ -389,7 +390,10 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + (uint32_t)(c * 32), v);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
-        if (p.cc && row_ok && nb < p.N_valid) {
+        if (p.epi_exp) {
+#pragma unroll
+          for (int e = 0; e < 32; e++) v[e] = __expf(fmaf(p.alpha, v[e], -bias));
+        } else if (p.cc && row_ok && nb < p.N_valid) {
           const float* cr = p.cc + (long long)row * p.ldcc + nb;
           if (nb + 32 <= p.N_valid) {
 #pragma unroll
@@ -571,6 +575,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   p.out = e.out; p.ldo = e.ldo; p.so_b = e.so_b; p.out2 = e.out2; p.ldo2 = e.ldo2; p.so_b2 = e.so_b2;
   p.alpha = e.alpha; p.atomic = e.atomic; p.u = e.u; p.ldu = e.ldu; p.cc = e.cc; p.ldcc = e.ldcc; p.sum = e.sum; p.sumsq = e.sumsq;
   const int am = A.mn_major ? 1 : 0, bm = B.mn_major ? 1 : 0;
+  DCNET_CHECK_ARG(!e.epi_exp || (out_ok && e.u && !e.cc && !e.sum && !e.atomic), "umma_gemm: the exp epilogue needs the persistent kernel and a row term");
   if (out_ok) {
     Gemm2P q{};
     q.M_valid = M; q.N_valid = N; q.k_iters = p.k_iters; q.k_split = p.k_split; q.n_split = p.n_split; q.m_split = p.m_split;
@@ -578,6 +583,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     q.idxA = e.idxA; q.idxB = e.idxB; q.idxC = e.idxC;
     q.tiles_m = ceil_div(M, BM); q.tiles_n = ceil_div(N, BN); q.ntiles = q.tiles_m * q.tiles_n * batch;
     q.alpha = e.alpha; q.atomic = e.atomic; q.u = e.u; q.ldu = e.ldu; q.cc = e.cc; q.ldcc = e.ldcc; q.sum = e.sum; q.sumsq = e.sumsq;
+    q.epi_exp = e.epi_exp;
     const uint64_t nbo = q.out_batched ? 65535u : 1u;
     const uint64_t rows1 = e.m_split > 0 ? (uint64_t)e.m_split : (uint64_t)M;
     CUtensorMap mo, mo2;

@@ -322,10 +322,20 @@ class _CoAttn(torch.autograd.Function):
         out = torch.empty(n_out, C, N, device=frames.device, dtype=F32) if n_out == nprob else \
             torch.zeros(n_out, C, N, device=frames.device, dtype=F32)
         lse = torch.empty(nprob, N, device=frames.device, dtype=F32)
-        nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, precision)
-        ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
-        _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, precision,
-                  _p(ws), nbytes, _st())
+        staged = None
+        if precision == TENSOR_BF16_FUSED and C % 128 == 0 and C <= 512:
+            # fused kernel: only the bf16 staging of the maps is needed.  Handing it to the backward (dcnet_coattn_bwd's `staged`:
+            # P recomputed from the same bf16 operands, exp fused into the GEMM epilogue, no softmax pass) was measured at
+            # -2 % step time but 1.3e-3 gradient error against 9e-4 with tf32 logits + re-normalisation: not used (bar 1e-3).
+            nbytes = _lib.lib().dcnet_coattn_stage_bytes(F_, C, N)
+            staged = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
+            _lib.call("dcnet_coattn_stage", _p(frames), F_, C, N, _p(staged), nbytes, _st())
+            _lib.call("dcnet_coattn_fused_fwd", _p(staged), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, _st())
+        else:
+            nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, precision)
+            ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
+            _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, precision,
+                      _p(ws), nbytes, _st())
         ctx.save_for_backward(frames, qa, kb, oidx, out, lse)
         ctx.tau = tau
         ctx.precision = precision
@@ -341,7 +351,7 @@ class _CoAttn(torch.autograd.Function):
         nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, ctx.precision)
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
         _lib.call("dcnet_coattn_bwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout), _p(dframes),
-                  C, N, ctx.tau, ctx.precision, _p(ws), nbytes, _st())
+                  C, N, ctx.tau, ctx.precision, None, _p(ws), nbytes, _st())
         return dframes, None, None, None, None, None, None
 
 

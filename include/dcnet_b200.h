@@ -160,10 +160,13 @@ DCNET_API int dcnet_coattn_fused_fwd(const void* staged, int F, const int* qa, c
 /* profiling variant: trace [ceil(N/64) * nprob CTAs][ceil(N/128) key tiles + 1][8] int64 receives clock64 stamps (see umma_coattn.cu) */
 DCNET_API int dcnet_coattn_fused_fwd_trace(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                            float* out, int n_out, float* lse, int C, int N, float tau, long long* trace, int variant, void* stream);
-/* dframes [F,C,N] += gradient (caller zeroes); dout/out indexed by oidx like the forward */
+/* dframes [F,C,N] += gradient (caller zeroes); dout/out indexed by oidx like the forward.  staged (optional, precision 2): the
+ * buffer dcnet_coattn_stage filled for the forward of the same frames; P is then recomputed from the forward's own bf16 operands
+ * with exp fused into the GEMM epilogue (no softmax pass).  NULL: P is re-normalised from tf32 logits.                          */
 DCNET_API int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                const float* out, int n_out, const float* lse, const float* dout, float* dframes,
-                               int C, int N, float tau, int precision, void* workspace, size_t workspace_bytes, void* stream);
+                               int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /* ---- a4: inter-frame patch correspondence (model/DCNet_model.py:381-430) ------------------------------
  * fv0 [2P,C,N0].  S0[p] = F1^T F2 in exact fp32; idx[p, r] = flat index (row*N0+col) of the r-th largest

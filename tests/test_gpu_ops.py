@@ -319,6 +319,34 @@ def test_coattention_fused_staged_problems(C, N):
         10.0 * fr[qa[i]].double().t() @ fr[kb[i]].double(), 1).t()) for i in range(4))))
 
 
+def test_coattention_backward_with_forward_staging():
+    """dcnet_coattn_bwd(staged=...): P recomputed from the forward's bf16 operands with exp in the GEMM epilogue (no softmax
+    pass).  Measured 1.3e-3 against the fp64 gradient (tf32 logits + re-normalisation: 9e-4), so it is an option, not the default."""
+    from dcnet_b200 import _lib
+    g = gen(44)
+    P, C, N = 2, 512, 256
+    fr = torch.nn.functional.normalize(torch.randn(2 * P, C, N, generator=g).abs(), dim=1)
+    ref_in = fr.double().requires_grad_(True)
+    o1, o2 = O.coattention(ref_in.view(P, 2, C, N)[:, 0], ref_in.view(P, 2, C, N)[:, 1], 10.0)
+    ref = O.interleave_pairs(o1, o2)
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go.double())
+    x = fr.to(DEV)
+    qa = torch.arange(2 * P, device=DEV, dtype=torch.int32); kb = qa ^ 1
+    staged = ops.coattn_stage(x)
+    out, lse = ops.coattn_fused(staged, x.shape, qa, kb, tau=10.0)
+    dfr = torch.zeros_like(x)
+    L = _lib.lib()
+    nbytes = L.dcnet_coattn_workspace_bytes(2 * P, 2 * P, C, N, 2)
+    ws = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
+    god = go.to(DEV)
+    _lib.call("dcnet_coattn_bwd", x.data_ptr(), 2 * P, qa.data_ptr(), kb.data_ptr(), qa.data_ptr(), 2 * P, out.data_ptr(), 2 * P, lse.data_ptr(),
+              god.data_ptr(), dfr.data_ptr(), C, N, 10.0, 2, staged.data_ptr(), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+    e = rel(dfr, ref_in.grad)
+    print("coattn bwd with forward staging: rel err %.2e" % e)
+    assert e < 2.5e-3, e
+
+
 def test_coattention_clip_mode_centre_vs_others():
     """model/test_DCNet_model.py:303-332: centre frame attends to each other frame (one direction), mean of results."""
     g = gen(31)
