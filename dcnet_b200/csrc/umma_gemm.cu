@@ -26,6 +26,11 @@ static int sm_count() {
   }
   return n;
 }
+static long long* g_gemm_trace = nullptr;   // profiling: clock stamps of the next persistent GEMM launches
+extern "C" int dcnet_gemm_trace(long long* buf) { g_gemm_trace = buf; return 0; }
+static int g_gemm_tma_store = 1;   // dcnet_gemm_select(5): epilogue through coalesced st.global / red.global.add.v4 instead of TMA store / reduce-add
+static int g_gemm_dbg = 0;
+extern "C" int dcnet_gemm_debug(int v) { g_gemm_dbg = v; return 0; }
 static bool g_force_v1 = false;   // tests: run the one-tile-per-CTA kernel with direct stores
 // largest cluster the persistent kernel may use.  Measured on B200 (scripts/prof_gemm.py, M=N=1024 K=512 x16, L2 flushed): no
 // clusters 44.2 us, clusters of 2 44.2 us, clusters of 4 46 us, and the C2 step 1.73 ms vs 1.79 ms -- the kernel is not bound by
@@ -34,6 +39,7 @@ static int g_cluster_max = 1;
 extern "C" int dcnet_gemm_select(int variant) {
   g_force_v1 = (variant == 1);
   g_cluster_max = (variant == 4) ? 4 : ((variant == 3) ? 2 : 1);
+  g_gemm_tma_store = (variant == 5) ? 0 : 1;
   return 0;
 }
 
@@ -235,7 +241,12 @@ struct Gemm2P {
   float alpha; int atomic;
   const float* u; int ldu; const float* cc; long long ldcc; float* sum; float* sumsq;
   int epi_exp;
+  int direct_store;    // 1: epilogue leaves through coalesced st.global / red.global.add.v4 instead of TMA store / reduce
+  float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2;
+  int dbg;             // profiling experiments: 1 = epilogue skips smem staging and stores, 2 = stages but does not store
+  long long* trace;    // optional [CTA][tile slot < 8][8] clock stamps (profiling entry point dcnet_gemm_tf32_trace); nullptr = off
 };
+#define GTRACE(tl, slot) do { if (p.trace && (tl) < 8) p.trace[((long long)blockIdx.x * 8 + (tl)) * 8 + (slot)] = clock64(); } while (0)
 
 // CS = cluster size: CS CTAs with consecutive M tiles of the same (batch, N tile) share the B tile -- each loads 1/CS of it and
 // multicasts (the kernel is bound by the L2 -> SM operand traffic, profiles/r1i_ncu_full_umma_gemm2.txt).
@@ -341,14 +352,17 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       uint32_t itg = 0, tl = 0;
       for (int t = cid; t < ngroups; t += ncl, tl++) {
         const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
+        GTRACE(tl, 0);
         mbar_wait(&acc_empty[as], aph ^ 1u);          // the epilogue has drained this accumulator stage
         tc_fence_after();
+        GTRACE(tl, 1);
         const uint32_t dcol = tmem_base + as * BN;
         for (int it = 0; it < p.k_iters; it++, itg++) {
           const int s = itg % STAGES;
           const uint32_t ph = (itg / STAGES) & 1u;
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (it == 0) GTRACE(tl, 2);
           const uint32_t sA = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sB = sA + A_BYTES;
 #pragma unroll
@@ -363,6 +377,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           else mma_commit(&empty[s]);
         }
         mma_commit(&acc_full[as]);
+        GTRACE(tl, 3);
       }
     }
   } else {
@@ -375,6 +390,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
+      if (threadIdx.x == 0) GTRACE(tl, 4);
       const int row0 = m0 + warp * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M_valid;
@@ -420,7 +436,44 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               if (nb + e < p.N_valid) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
           }
         }
+        if (p.dbg == 1) continue;
         uint8_t* slot = slots + (chunk % NSLOT) * SLOT_BYTES;
+        if (p.direct_store) {
+          // variant 5: transpose through the warp's swizzled slot, then row-major 16-byte stores (a warp instruction writes
+          // 4 rows x 128 B).  Measured against the TMA-store epilogue on the 128x256x512 tiles of the co-attention backward
+          // (scripts/prof_gemm.py): epilogue 14 k instead of 8.5 k cycles per tile, kernel 65 us instead of 60 us.  Either way the
+          // main loop runs at ~10.3 k cycles per tile without the output stores and ~15 k with them: these GEMMs write 64 MB for
+          // 17 GFLOP and are bound by that traffic, not by the tensor pipe.
+          __syncwarp();                                   // previous chunk's reads of this slot are done
+          uint8_t* srow = slot + lane * 128;
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            *reinterpret_cast<float4*>(srow + ((e ^ (lane & 7)) * 16)) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+          __syncwarp();
+          const int cq = lane & 7, rsub = lane >> 3;
+          const int col = nb + 4 * cq;
+          float* obase = (second ? p.out2 + (long long)zc * p.so_b2 : p.out + (long long)zc * p.so_b);
+          const long long ldo_ = second ? p.ldo2 : p.ldo;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int r = 4 * i + rsub;
+            const float4 q = *reinterpret_cast<const float4*>(slot + r * 128 + ((cq ^ (r & 7)) * 16));
+            if (row0 + r < p.M_valid && col < p.N_valid) {
+              float* dst = obase + (long long)(orow0 + r) * ldo_ + col;
+              if (col + 4 <= p.N_valid) {
+                if (p.atomic) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(q.x), "f"(q.y), "f"(q.z), "f"(q.w) : "memory");
+                else *reinterpret_cast<float4*>(dst) = q;
+              } else {
+                const float qq[4] = {q.x, q.y, q.z, q.w};
+                for (int t = 0; t < 4 && col + t < p.N_valid; t++) {
+                  if (p.atomic) atomicAdd(dst + t, qq[t]);
+                  else dst[t] = qq[t];
+                }
+              }
+            }
+          }
+          continue;
+        }
         if (lane == 0) tma_store_wait_read_n<NSLOT - 1>();   // the store that last read this slot (NSLOT chunks ago) is done with it
         __syncwarp();
         uint8_t* srow = slot + lane * 128;
@@ -430,7 +483,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (row0 < p.M_valid && nb < p.N_valid) {       // rows / columns beyond the tensor are clipped by the map
+          if (p.dbg != 2 && row0 < p.M_valid && nb < p.N_valid) {       // rows / columns beyond the tensor are clipped by the map
             if (p.atomic) tma_reduce_add_3d(mo, slot, nb, orow0, zc);
             else tma_store_3d(mo, slot, nb, orow0, zc);
           }
@@ -439,6 +492,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == 0) GTRACE(tl, 5);
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       if (p.sum && row_ok) {
         atomicAdd(p.sum + row, s1);
@@ -584,6 +638,10 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     q.tiles_m = ceil_div(M, BM); q.tiles_n = ceil_div(N, BN); q.ntiles = q.tiles_m * q.tiles_n * batch;
     q.alpha = e.alpha; q.atomic = e.atomic; q.u = e.u; q.ldu = e.ldu; q.cc = e.cc; q.ldcc = e.ldcc; q.sum = e.sum; q.sumsq = e.sumsq;
     q.epi_exp = e.epi_exp;
+    q.trace = g_gemm_trace;
+    q.dbg = g_gemm_dbg;
+    q.direct_store = g_gemm_tma_store ? 0 : 1;
+    q.out = e.out; q.ldo = e.ldo; q.so_b = e.so_b; q.out2 = e.out2; q.ldo2 = e.ldo2; q.so_b2 = e.so_b2;
     const uint64_t nbo = q.out_batched ? 65535u : 1u;
     const uint64_t rows1 = e.m_split > 0 ? (uint64_t)e.m_split : (uint64_t)M;
     CUtensorMap mo, mo2;

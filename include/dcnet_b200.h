@@ -64,10 +64,17 @@ DCNET_API int dcnet_gemm_bf16(const void* A, int a_mn_major, long long lda, long
                               void* stream);
 DCNET_API int dcnet_cast_bf16(const float* x, void* y, long long n, void* stream);
 /* which tensor-core GEMM kernel every entry point of this library uses: 0 (default) = persistent kernel, two TMEM accumulator
- * stages, TMA store / reduce-add epilogue; 3 / 4 = the same with thread-block clusters of 2 / 4 CTAs (consecutive M tiles) that
- * multicast the B tile; 1 = one tile per CTA with per-thread stores (kept for outputs TMA cannot address).  All variants give
- * identical bits.  Process-wide switch, not thread-safe: a test / bring-up knob.                                              */
+ * stages, epilogue through swizzled smem slots and TMA store / reduce-add; 5 = the same with coalesced 16-byte st.global /
+ * red.global.add.v4.f32 from the slots; 3 / 4 = with thread-block clusters of 2 / 4 CTAs (consecutive M tiles) that multicast
+ * the B tile; 1 = one tile per CTA with per-thread row stores (outputs whose rows are not 16-byte addressable).  All variants give
+ * identical bits for plain stores.  Process-wide switch, not thread-safe: a test / bring-up knob.                              */
 DCNET_API int dcnet_gemm_select(int variant);
+/* profiling: while buf != NULL every persistent GEMM launch writes clock64 stamps to buf [148 CTAs][8 tiles][8]: 0 tile start (MMA
+ * thread), 1 accumulator stage free, 2 first operands landed, 3 last MMA issued, 4 accumulator complete (epilogue), 5 epilogue done */
+DCNET_API int dcnet_gemm_trace(long long* buf);
+/* profiling experiments on the persistent kernel's epilogue: 1 = no staging and no stores, 2 = staging without stores (results are
+ * then wrong by construction); 0 = normal */
+DCNET_API int dcnet_gemm_debug(int v);
 
 /* ---- a1/a2/a6/a8: 1x1 conv (no bias) + BatchNorm + ReLU (+ L2 norm over channels) ---------------------
  * replaces ConvBatchNormReLU (model/darknet.py:118-156) as used by mapping_visu (:356-359), corr_conv

@@ -21,7 +21,7 @@ ms = sorted(tt)[len(tt) // 2]
 print("gemm2 tf32 M=N=%d K=512 batch=%d: median %.4f ms -> %.1f TFLOP/s" % (N, B, ms, 2.0 * N * N * 512 * B / ms / 1e9))
 
 from dcnet_b200 import _lib
-for v, name in ((0, "no clusters"), (3, "clusters<=2"), (4, "clusters<=4"), (1, "one tile per CTA")):
+for v, name in ((0, "TMA stores"), (5, "direct stores"), (3, "clusters<=2"), (1, "one tile per CTA")):
     _lib.lib().dcnet_gemm_select(v)
     for _ in range(20):
         ops.gemm_tf32(fr, fr2, 1, 1, N, N, 512, out=out)
@@ -33,3 +33,27 @@ for v, name in ((0, "no clusters"), (3, "clusters<=2"), (4, "clusters<=4"), (1, 
         torch.cuda.synchronize(); tt.append(a.elapsed_time(b))
     print("  variant %-18s median %.4f ms  min %.4f" % (name, sorted(tt)[5], min(tt)))
 _lib.lib().dcnet_gemm_select(0)
+
+import numpy as np
+tr = torch.zeros(148, 8, 8, dtype=torch.long, device="cuda")
+for (am, bm, M, Nn, K, name, dbg) in ((1, 1, N, N, 512, "S = Fa^T Fb (MN,MN) K=512, TMA stores", 0), (1, 1, N, N, 512, "same, direct stores", -5),
+                                     (1, 1, N, N, 512, "same, epilogue without staging/stores", 1)):
+    _lib.lib().dcnet_gemm_select(5 if dbg == -5 else 0)
+    _lib.lib().dcnet_gemm_debug(max(dbg, 0))
+    A = torch.randn(B, K, M, device="cuda") if am else torch.randn(B, M, K, device="cuda")
+    Bm = torch.randn(B, K, Nn, device="cuda") if bm else torch.randn(B, Nn, K, device="cuda")
+    o = torch.empty(B, M, Nn, device="cuda")
+    for _ in range(3):
+        ops.gemm_tf32(A, Bm, am, bm, M, Nn, K, out=o)
+    flush.zero_(); torch.cuda.synchronize()
+    tr.zero_()
+    _lib.lib().dcnet_gemm_trace(tr.data_ptr())
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); ops.gemm_tf32(A, Bm, am, bm, M, Nn, K, out=o); b.record(); torch.cuda.synchronize()
+    _lib.lib().dcnet_gemm_trace(None)
+    t = tr.cpu().numpy()
+    _lib.lib().dcnet_gemm_debug(0); _lib.lib().dcnet_gemm_select(0)
+    print("%s: %.1f us" % (name, a.elapsed_time(b) * 1e3))
+    for cta in (0, 73, 147):
+        base = t[cta, 0, 0]
+        print("  CTA %3d:" % cta, " | ".join(" ".join("%6d" % (t[cta, j, k] - base) for k in range(6)) for j in range(5) if t[cta, j, 0] > 0))

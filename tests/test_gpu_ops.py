@@ -98,7 +98,7 @@ def test_gemm_bf16_all_operand_majors(a_mn, b_mn, M, N, K, batch):
 @pytest.mark.parametrize("M,N,K,batch", [(200, 680, 104, 2), (512, 1024, 256, 3), (384, 512, 160, 2), (1024, 256, 64, 1)])
 @pytest.mark.parametrize("b_mn", [0, 1])
 def test_gemm_kernel_variants_agree_bit_for_bit(M, N, K, batch, b_mn):
-    """dcnet_gemm_select: 0 = persistent kernel; 4 / 3 = the same with clusters of up to 4 / 2 CTAs multicasting the B tile
+    """dcnet_gemm_select: 0 = persistent kernel, TMA-store epilogue; 5 = coalesced st.global epilogue; 4 / 3 = clusters of up to 4 / 2 CTAs multicasting the B tile
     (M=512: 4 M tiles -> 4-CTA clusters; M=384: 3 tiles -> 2-CTA clusters with one idle slot; M=200: 2 tiles);
     1 = one tile per CTA with per-thread stores.  Same MMA order per tile => identical bits."""
     from dcnet_b200 import _lib
@@ -109,7 +109,7 @@ def test_gemm_kernel_variants_agree_bit_for_bit(M, N, K, batch, b_mn):
     ref = torch.bmm(A.double().cpu(), B.double().transpose(1, 2))
     outs = []
     try:
-        for v in (0, 4, 3, 1):
+        for v in (0, 5, 4, 3, 1):
             _lib.lib().dcnet_gemm_select(v)
             outs.append(ops.gemm_tf32(A, Bd, 0, b_mn, M, N, K))
     finally:
