@@ -29,8 +29,6 @@ static int sm_count() {
 static long long* g_gemm_trace = nullptr;   // profiling: clock stamps of the next persistent GEMM launches
 extern "C" int dcnet_gemm_trace(long long* buf) { g_gemm_trace = buf; return 0; }
 static int g_gemm_tma_store = 1;   // dcnet_gemm_select(5): epilogue through coalesced st.global / red.global.add.v4 instead of TMA store / reduce-add
-static int g_gemm_dbg = 0;
-extern "C" int dcnet_gemm_debug(int v) { g_gemm_dbg = v; return 0; }
 static bool g_force_v1 = false;   // tests: run the one-tile-per-CTA kernel with direct stores
 // largest cluster the persistent kernel may use.  Measured on B200 (scripts/prof_gemm.py, M=N=1024 K=512 x16, L2 flushed): no
 // clusters 44.2 us, clusters of 2 44.2 us, clusters of 4 46 us, and the C2 step 1.73 ms vs 1.79 ms -- the kernel is not bound by
@@ -243,7 +241,6 @@ struct Gemm2P {
   int epi_exp;
   int direct_store;    // 1: epilogue leaves through coalesced st.global / red.global.add.v4 instead of TMA store / reduce
   float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2;
-  int dbg;             // profiling experiments: 1 = epilogue skips smem staging and stores, 2 = stages but does not store
   long long* trace;    // optional [CTA][tile slot < 8][8] clock stamps (profiling entry point dcnet_gemm_tf32_trace); nullptr = off
 };
 #define GTRACE(tl, slot) do { if (p.trace && (tl) < 8) p.trace[((long long)blockIdx.x * 8 + (tl)) * 8 + (slot)] = clock64(); } while (0)
@@ -436,7 +433,6 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               if (nb + e < p.N_valid) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
           }
         }
-        if (p.dbg == 1) continue;
         uint8_t* slot = slots + (chunk % NSLOT) * SLOT_BYTES;
         if (p.direct_store) {
           // variant 5: transpose through the warp's swizzled slot, then row-major 16-byte stores (a warp instruction writes
@@ -483,7 +479,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.dbg != 2 && row0 < p.M_valid && nb < p.N_valid) {       // rows / columns beyond the tensor are clipped by the map
+          if (row0 < p.M_valid && nb < p.N_valid) {       // rows / columns beyond the tensor are clipped by the map
             if (p.atomic) tma_reduce_add_3d(mo, slot, nb, orow0, zc);
             else tma_store_3d(mo, slot, nb, orow0, zc);
           }
@@ -639,7 +635,6 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     q.alpha = e.alpha; q.atomic = e.atomic; q.u = e.u; q.ldu = e.ldu; q.cc = e.cc; q.ldcc = e.ldcc; q.sum = e.sum; q.sumsq = e.sumsq;
     q.epi_exp = e.epi_exp;
     q.trace = g_gemm_trace;
-    q.dbg = g_gemm_dbg;
     q.direct_store = g_gemm_tma_store ? 0 : 1;
     q.out = e.out; q.ldo = e.ldo; q.so_b = e.so_b; q.out2 = e.out2; q.ldo2 = e.ldo2; q.so_b2 = e.so_b2;
     const uint64_t nbo = q.out_batched ? 65535u : 1u;

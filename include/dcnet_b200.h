@@ -72,9 +72,6 @@ DCNET_API int dcnet_gemm_select(int variant);
 /* profiling: while buf != NULL every persistent GEMM launch writes clock64 stamps to buf [148 CTAs][8 tiles][8]: 0 tile start (MMA
  * thread), 1 accumulator stage free, 2 first operands landed, 3 last MMA issued, 4 accumulator complete (epilogue), 5 epilogue done */
 DCNET_API int dcnet_gemm_trace(long long* buf);
-/* profiling experiments on the persistent kernel's epilogue: 1 = no staging and no stores, 2 = staging without stores (results are
- * then wrong by construction); 0 = normal */
-DCNET_API int dcnet_gemm_debug(int v);
 
 /* ---- a1/a2/a6/a8: 1x1 conv (no bias) + BatchNorm + ReLU (+ L2 norm over channels) ---------------------
  * replaces ConvBatchNormReLU (model/darknet.py:118-156) as used by mapping_visu (:356-359), corr_conv

@@ -36,10 +36,8 @@ _lib.lib().dcnet_gemm_select(0)
 
 import numpy as np
 tr = torch.zeros(148, 8, 8, dtype=torch.long, device="cuda")
-for (am, bm, M, Nn, K, name, dbg) in ((1, 1, N, N, 512, "S = Fa^T Fb (MN,MN) K=512, TMA stores", 0), (1, 1, N, N, 512, "same, direct stores", -5),
-                                     (1, 1, N, N, 512, "same, epilogue without staging/stores", 1)):
+for (am, bm, M, Nn, K, name, dbg) in ((1, 1, N, N, 512, "S = Fa^T Fb (MN,MN) K=512, TMA stores", 0), (1, 1, N, N, 512, "same, direct stores", -5)):
     _lib.lib().dcnet_gemm_select(5 if dbg == -5 else 0)
-    _lib.lib().dcnet_gemm_debug(max(dbg, 0))
     A = torch.randn(B, K, M, device="cuda") if am else torch.randn(B, M, K, device="cuda")
     Bm = torch.randn(B, K, Nn, device="cuda") if bm else torch.randn(B, Nn, K, device="cuda")
     o = torch.empty(B, M, Nn, device="cuda")
@@ -52,7 +50,7 @@ for (am, bm, M, Nn, K, name, dbg) in ((1, 1, N, N, 512, "S = Fa^T Fb (MN,MN) K=5
     a.record(); ops.gemm_tf32(A, Bm, am, bm, M, Nn, K, out=o); b.record(); torch.cuda.synchronize()
     _lib.lib().dcnet_gemm_trace(None)
     t = tr.cpu().numpy()
-    _lib.lib().dcnet_gemm_debug(0); _lib.lib().dcnet_gemm_select(0)
+    _lib.lib().dcnet_gemm_select(0)
     print("%s: %.1f us" % (name, a.elapsed_time(b) * 1e3))
     for cta in (0, 73, 147):
         base = t[cta, 0, 0]
