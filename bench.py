@@ -305,12 +305,21 @@ def main():
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     graph = None
+    ar_in_graph = False
+    do_ar = world > 1 and not args.no_allreduce
+    if do_ar:
+        dist.all_reduce(torch.zeros(1, device=dev))          # communicator up before any capture
+        torch.cuda.synchronize()
     if not args.no_graph:
         clear_grads()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             res = run_step()
-    hot_grads = [p.grad for p in hp.hot_parameters if p.grad is not None] if graph is not None else None
+            if do_ar:
+                # data-parallel gradient all-reduce of the hot-path parameters, one flat NCCL collective, captured with the step
+                flat_g = torch.cat([p.grad.reshape(-1) for p in hp.hot_parameters if p.grad is not None])
+                dist.all_reduce(flat_g)
+                ar_in_graph = True
 
     def do_step():
         nonlocal res
@@ -319,9 +328,8 @@ def main():
         else:
             clear_grads()
             res = run_step()
-        if world > 1 and not args.no_allreduce:
-            gs = hot_grads if hot_grads is not None else [p.grad for p in hp.hot_parameters if p.grad is not None]
-            flat = torch.cat([x.reshape(-1) for x in gs])
+        if do_ar and not ar_in_graph:
+            flat = torch.cat([p.grad.reshape(-1) for p in hp.hot_parameters if p.grad is not None])
             dist.all_reduce(flat)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -557,12 +565,13 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         # a CUDA graph that holds captured NCCL kernels must be gone before the communicator is torn down
+        graph_had_nccl = graph is not None and (xneg or ar_in_graph)
         graph = None
         res = None
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-        if xneg:
+        if graph_had_nccl:
             sys.stdout.flush()
             os._exit(0)              # ProcessGroupNCCL teardown after captured collectives can block; nothing is left to flush
         dist.destroy_process_group()
