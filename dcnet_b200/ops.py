@@ -215,8 +215,18 @@ def yolo_layer_decode(x, anchors, num_classes, image_dim):
 # ------------------------------------------------------------------------------------------------------------------
 # differentiable ops
 # ------------------------------------------------------------------------------------------------------------------
+def _pad_n(t, Np):
+    """[.., N] -> [.., Np] zero-padded copy (row pitch a multiple of 16 bytes so TMA can address it)"""
+    return None if t is None else torch.nn.functional.pad(t, (0, Np - t.shape[-1]))
+
+
 class _ConvBNAct(torch.autograd.Function):
-    """a1/a2/a6/a8: y = [l2norm_c] act(BN(W[:, :K1] x1 + W[:, K1:K1+K2] x2 + u 1^T + cc)), plus the fused a9 dots."""
+    """a1/a2/a6/a8: y = [l2norm_c] act(BN(W[:, :K1] x1 + W[:, K1:K1+K2] x2 + u 1^T + cc)), plus the fused a9 dots.
+
+    Maps whose row pitch is not a multiple of 16 bytes (N % 4 != 0: the 13x13 scale of 416x416 inputs) cannot be addressed by
+    TMA.  Their three contractions run on zero-padded copies of the operands (pitch rounded up to 4 positions) so they stay on
+    tcgen05: the padded positions contribute zeros to every reduction over N, the padded output columns are dropped, and the
+    BatchNorm statistics are taken from the unpadded z."""
 
     @staticmethod
     def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope, l2norm, precision):
@@ -236,14 +246,23 @@ class _ConvBNAct(torch.autograd.Function):
         ctx_precision = precision
         if precision == EXACT_FWD_TF32_BWD:
             precision = EXACT_FP32
-        if training and precision == 1:
+        padded = precision == 1 and N % 4 != 0 and K1 % 32 == 0 and K2 % 32 == 0
+        if padded:
+            Np = (N + 3) // 4 * 4
+            zp = torch.empty(B, C, Np, device=dev, dtype=F32)
+            x1p, x2p, ccp = _pad_n(x1, Np), _pad_n(x2, Np), _pad_n(cc, Np)      # named: they must outlive the launch below
+            _lib.call("dcnet_conv1x1_fwd", _p(x1p), K1, _p(x2p), K2, _p(weight), ldw, _p(u), _p(ccp), _p(zp), B, C, Np, None, precision, st)
+            z = zp[..., :N].contiguous()
+            if training:
+                _lib.call("dcnet_bn_stats", _p(z), B, C, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
+        elif training and precision == 1:
             # tensor-core path: BatchNorm sums come out of the GEMM epilogue, z is not re-read
             sums = torch.empty(2 * C, device=dev, dtype=F32)
             _lib.call("dcnet_conv1x1_fwd", _p(x1), K1, _p(x2), K2, _p(weight), ldw, _p(u), _p(cc), _p(z), B, C, N, _p(sums), precision, st)
             _lib.call("dcnet_bn_finalize", _p(sums), B * N, C, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
         else:
             _lib.call("dcnet_conv1x1_fwd", _p(x1), K1, _p(x2), K2, _p(weight), ldw, _p(u), _p(cc), _p(z), B, C, N, None, precision, st)
-        if training and precision != 1:
+        if training and precision != 1 and not padded:
             _lib.call("dcnet_bn_stats", _p(z), B, C, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
         elif not training:
             _lib.call("dcnet_bn_eval_stats", _p(running_mean), _p(running_var), C, eps, _p(mean), _p(invstd), st)
@@ -283,12 +302,35 @@ class _ConvBNAct(torch.autograd.Function):
         _lib.call("dcnet_bn_act_bwd_apply", _p(z), _p(mean), _p(invstd), _p(gamma), _p(dv), _p(sums[0]), _p(sums[1]), int(training), _p(dv),
                   B, C, N, st)
         dz = dv
+        need_w = ctx.needs_input_grad[2]
+        if precision == 1 and N % 4 != 0 and K1 % 128 == 0 and K2 % 128 == 0:
+            # pitch-padded copies (see the class docstring); zero padding leaves every sum over N unchanged
+            Np = (N + 3) // 4 * 4
+            dzp = _pad_n(dz, Np)
+            dx1 = dx2 = None
+            if ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1]):
+                dx1p = torch.empty(B, K1, Np, device=dev, dtype=F32)
+                dx2p = torch.empty(B, K2, Np, device=dev, dtype=F32) if x2 is not None else None
+                _lib.call("dcnet_conv1x1_bwd_data", _p(dzp), _p(weight), ldw, _p(dx1p), K1, _p(dx2p), K2, B, C, Np, precision, st)
+                dx1 = dx1p[..., :N].contiguous() if ctx.needs_input_grad[0] else None
+                dx2 = dx2p[..., :N].contiguous() if (x2 is not None and ctx.needs_input_grad[1]) else None
+            dW = du = dcc = None
+            if need_w:
+                dW = torch.zeros(C, ldw, device=dev, dtype=F32)
+            if has_u and ctx.needs_input_grad[5]:
+                du = torch.empty(B, C, device=dev, dtype=F32)
+            dccp = torch.empty(C, Np, device=dev, dtype=F32) if (has_cc and ctx.needs_input_grad[6]) else None
+            if need_w or du is not None or dccp is not None:
+                x1p = _pad_n(x1, Np) if need_w else None
+                x2p = _pad_n(x2, Np) if (need_w and x2 is not None) else None
+                _lib.call("dcnet_conv1x1_bwd_weight", _p(dzp), _p(x1p), K1, _p(x2p), K2, _p(dW), ldw, _p(du), _p(dccp), B, C, Np, precision, st)
+            dcc = dccp[:, :N].contiguous() if dccp is not None else None
+            return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None)
         dx1 = torch.empty_like(x1) if ctx.needs_input_grad[0] else None
         dx2 = torch.empty_like(x2) if (x2 is not None and ctx.needs_input_grad[1]) else None
         if dx1 is not None or dx2 is not None:
             _lib.call("dcnet_conv1x1_bwd_data", _p(dz), _p(weight), ldw, _p(dx1), K1, _p(dx2), K2, B, C, N, precision, st)
         dW = du = dcc = None
-        need_w = ctx.needs_input_grad[2]
         if need_w:
             dW = torch.zeros(C, ldw, device=dev, dtype=F32)
         if has_u and ctx.needs_input_grad[5]:

@@ -60,7 +60,9 @@ def test_train_forward_losses_gradients_vs_oracle(size, pairs, precision):
     # gradients bounded by the ReLU-mask flips any reduced-precision forward causes (see test_conv_bn_act_forward_backward)
     net = make_net(size)
     net.precision = precision
-    TF, TL, TG = (2e-5, 2e-4, 2e-3) if precision == 0 else (3e-3, 3e-3, 6e-2)
+    # TG at precision 1: 8e-2 -- at 416x416 the 13x13 scale now also runs tf32 contractions (pitch-padded operands) and the worst
+    # library-on-GPU floor of this graph is itself 7.3e-2 (PyTorch's own tf32 evaluation against its fp32 CPU evaluation)
+    TF, TL, TG = (2e-5, 2e-4, 2e-3) if precision == 0 else (3e-3, 3e-3, 8e-2)
     g = torch.Generator().manual_seed(100 + size)
     maps = synth.make_raw_fvisu(pairs, size, g)
     wid = synth.make_words(pairs, gen=g)

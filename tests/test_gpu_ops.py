@@ -239,6 +239,37 @@ def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, t
     assert float(c['w'].grad[:, K:].abs().max()) == 0.0 if c['w'].shape[1] > K else True
 
 
+@pytest.mark.parametrize("use_terms,use_fa", [(False, False), (True, False), (False, True)])
+def test_conv_bn_act_odd_pitch_runs_on_tensor_cores(use_terms, use_fa):
+    """N = 169 (13x13, the coarsest scale of 416x416): the row pitch is not a multiple of 16 bytes, so the three contractions run
+    on zero-padded copies (pitch 172) on tcgen05.  Same numbers as the exact-fp32 path within tf32 rounding, forward and backward."""
+    g = gen(61)
+    B, K1, K2, C, N = 4, 512, 512, 512, 169
+    x1 = torch.randn(B, K1, N, generator=g).to(DEV); x2 = torch.randn(B, K2, N, generator=g).to(DEV)
+    W = (torch.randn(C, K1 + K2 + 8, generator=g) / 32).to(DEV)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV); beta = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    u = (torch.randn(B, C, generator=g) * 0.3).to(DEV); cc = (torch.randn(C, N, generator=g) * 0.3).to(DEV)
+    fa = torch.nn.functional.normalize(torch.rand(B, C, generator=g), dim=1).to(DEV)
+    go = torch.randn(B, C, N, generator=g).to(DEV)
+
+    def run(prec):
+        ins = [t.clone().requires_grad_(True) for t in (x1, x2, W)]
+        rm = torch.zeros(C, device=DEV); rv = torch.ones(C, device=DEV)
+        out = ops.conv_bn_act(ins[0], ins[2], gamma, beta, rm, rv, True, x2=ins[1], u=u if use_terms else None, cc=cc if use_terms else None,
+                              fa=fa if use_fa else None, l2norm=use_fa, precision=prec)
+        if use_fa:
+            torch.autograd.backward(list(out), [go, torch.ones_like(out[1]), torch.ones_like(out[2])])
+            return [out[0].detach(), out[1].detach()] + [t.grad for t in ins] + [rm, rv]
+        out.backward(go)
+        return [out.detach()] + [t.grad for t in ins] + [rm, rv]
+
+    a, b = run(1), run(0)
+    errs = [rel(p, q) for p, q in zip(a, b)]
+    print("odd-pitch conv, tf32 padded vs exact fp32:", ["%.1e" % e for e in errs])
+    nfwd = 2 if use_fa else 1
+    assert max(errs[:nfwd]) < 2e-3 and max(errs) < 3e-2, errs     # gradients: ReLU-mask flips of the tf32 forward (see above)
+
+
 @pytest.mark.parametrize("B,N,l2norm,use_fa,use_dy", [(3, 64, 1, 1, 1), (2, 676, 1, 1, 1), (4, 1024, 0, 0, 1), (2, 256, 1, 1, 0), (5, 20, 1, 1, 1)])
 def test_bn_bwd_reduce_staged_kernel_matches_register_kernel(B, N, l2norm, use_fa, use_dy):
     """dcnet_bn_act_bwd_reduce: the persistent smem-staged kernel (default when C=512, N%4==0) against the register-staged one
