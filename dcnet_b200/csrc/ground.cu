@@ -203,57 +203,61 @@ __global__ void __launch_bounds__(256) ground_loss_fwd_kernel(LossIn a, float* _
   lse_loc[b] = ll;
 }
 
+// grid (B, GL_BWD_SPLIT): the elements of a sample are striped over the CTAs of its row; the handful of special cells (GT cell of
+// the box / confidence / location terms, the two hinge partners) are resolved inline by whichever thread owns them, so no CTA
+// ever touches an element another one writes.
+constexpr int GL_BWD_SPLIT = 8;
 __global__ void __launch_bounds__(256) ground_loss_bwd_kernel(LossIn a, const float* __restrict__ lse_conf, const float* __restrict__ lse_loc,
                                                               const float* __restrict__ gl, MPtr3 dpred, MPtr3 dsim, MPtr3 dneg, MPtr3 dloc) {
   const int b = blockIdx.x;
+  const int t0 = blockIdx.y * blockDim.x + threadIdx.x, tstride = gridDim.y * blockDim.x;
   const float invB = 1.f / (float)a.B;
   const float g_y = gl[0] * invB, g_r = gl[1] * 0.5f * invB, g_l = gl[2] * invB;
   const float lc = lse_conf[b], ll = lse_loc[b];
-  for (int s = 0; s < 3; s++) {
-    const int g = a.g0 << s, N = g * g;
-    const float* p = a.pred.p[s] + (long long)b * 15 * N;
-    float* dp = dpred.p[s] + (long long)b * 15 * N;
-    for (int i = threadIdx.x; i < 15 * N; i += blockDim.x) {
-      const int ch = i / N;
-      dp[i] = (ch % 5 == 4) ? g_y * expf(p[i] - lc) : 0.f;
-    }
-    const float* l = a.loc.p[s] + (long long)b * N;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      dloc.p[s][(long long)b * N + i] = g_l * expf(l[i] - ll);
-      dsim.p[s][(long long)b * N + i] = 0.f;
-      dneg.p[s][(long long)b * N + i] = 0.f;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  const int s = (int)(a.best_n[b] / 3), an = (int)(a.best_n[b] % 3);
-  const int g = a.g0 << s, N = g * g;
-  const int cell = (int)(a.gj[b] * g + a.gi[b]);
-  const float* p = a.pred.p[s] + ((long long)b * 15 + 5 * an) * N + cell;
-  float* dp = dpred.p[s] + ((long long)b * 15 + 5 * an) * N + cell;
-  const float* t = a.t5 + b * 5;
-  const float sx = sigmoidf_(p[0]), sy = sigmoidf_(p[(long long)N]);
-  const float k = 2.f * a.w_coord * g_y;
-  dp[0] = k * (sx - t[0]) * sx * (1.f - sx);
-  dp[(long long)N] = k * (sy - t[1]) * sy * (1.f - sy);
-  dp[2LL * N] = k * (p[2LL * N] - t[2]);
-  dp[3LL * N] = k * (p[3LL * N] - t[3]);
-  dp[4LL * N] -= g_y;
-  dloc.p[s][(long long)b * N + cell] -= g_l;
+  // special cells of this sample
+  const int sg = (int)(a.best_n[b] / 3), an = (int)(a.best_n[b] % 3);
+  const int gg = a.g0 << sg, Ng = gg * gg;
+  const int cellg = (int)(a.gj[b] * gg + a.gi[b]);
   const int rb = a.B - 1 - b;
   const long long pbn = a.partner3 ? a.partner3[b] : a.best_n[rb];
   const long long pgi = a.partner3 ? a.partner3[a.B + b] : a.gi[rb];
   const long long pgj = a.partner3 ? a.partner3[2 * a.B + b] : a.gj[rb];
   const int s2 = (int)(pbn / 3), g2 = a.g0 << s2, N2 = g2 * g2;
   const int cell2 = (int)(pgj * g2 + pgi);
-  const float pos = a.sim.p[s][(long long)b * N + cell];
-  const float n1 = a.neg.p[s][(long long)b * N + cell];
+  const float pos = a.sim.p[sg][(long long)b * Ng + cellg];
+  const float n1 = a.neg.p[sg][(long long)b * Ng + cellg];
   const float n2 = a.sim.p[s2][(long long)b * N2 + cell2];
   const float h1 = (a.margin + n1 - pos >= 0.f) ? g_r : 0.f;   // clamp(min=0) passes the gradient at 0
   const float h2 = (a.margin + n2 - pos >= 0.f) ? g_r : 0.f;
-  dsim.p[s][(long long)b * N + cell] -= (h1 + h2);
-  dsim.p[s2][(long long)b * N2 + cell2] += h2;
-  dneg.p[s][(long long)b * N + cell] += h1;
+  const float* t5 = a.t5 + b * 5;
+  const float kc = 2.f * a.w_coord * g_y;
+  for (int s = 0; s < 3; s++) {
+    const int g = a.g0 << s, N = g * g;
+    const float* p = a.pred.p[s] + (long long)b * 15 * N;
+    float* dp = dpred.p[s] + (long long)b * 15 * N;
+    for (int i = t0; i < 15 * N; i += tstride) {
+      const int ch = i / N, cell = i - ch * N, k5 = ch % 5;
+      float v = (k5 == 4) ? g_y * expf(p[i] - lc) : 0.f;
+      if (s == sg && cell == cellg && ch / 5 == an) {
+        if (k5 == 0 || k5 == 1) {
+          const float sx = sigmoidf_(p[i]);
+          v = kc * (sx - t5[k5]) * sx * (1.f - sx);
+        } else if (k5 == 2 || k5 == 3) {
+          v = kc * (p[i] - t5[k5]);
+        } else {
+          v -= g_y;
+        }
+      }
+      dp[i] = v;
+    }
+    const float* l = a.loc.p[s] + (long long)b * N;
+    for (int i = t0; i < N; i += tstride) {
+      const bool atg = (s == sg && i == cellg);
+      dloc.p[s][(long long)b * N + i] = g_l * expf(l[i] - ll) - (atg ? g_l : 0.f);
+      dsim.p[s][(long long)b * N + i] = (atg ? -(h1 + h2) : 0.f) + ((s == s2 && i == cell2) ? h2 : 0.f);
+      dneg.p[s][(long long)b * N + i] = atg ? h1 : 0.f;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -533,7 +537,7 @@ extern "C" int dcnet_ground_loss_bwd(const float* pred0, const float* pred1, con
   DCNET_CHECK_ARG(best_n && gi && gj && t5 && lse_conf && lse_loc && gl && B > 0 && g0 > 0, "ground_loss_bwd: bad arguments");
   DCNET_CHECK_ARG(dpred0 && dpred1 && dpred2 && dsim0 && dsim1 && dsim2 && dneg0 && dneg1 && dneg2 && dloc0 && dloc1 && dloc2, "ground_loss_bwd: null output");
   LossIn a{{{pred0, pred1, pred2}}, {{sim0, sim1, sim2}}, {{neg0, neg1, neg2}}, {{loc0, loc1, loc2}}, best_n, gi, gj, t5, partner3, B, g0, w_coord, margin};
-  ground_loss_bwd_kernel<<<B, 256, 0, as_stream(stream)>>>(a, lse_conf, lse_loc, gl, MPtr3{{dpred0, dpred1, dpred2}}, MPtr3{{dsim0, dsim1, dsim2}},
+  ground_loss_bwd_kernel<<<dim3(B, GL_BWD_SPLIT), 256, 0, as_stream(stream)>>>(a, lse_conf, lse_loc, gl, MPtr3{{dpred0, dpred1, dpred2}}, MPtr3{{dsim0, dsim1, dsim2}},
                                                              MPtr3{{dneg0, dneg1, dneg2}}, MPtr3{{dloc0, dloc1, dloc2}});
   DCNET_LAUNCH_OK("ground_loss_bwd");
   return 0;
