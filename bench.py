@@ -202,7 +202,7 @@ def run_c4(args, wl, rank, world, dev, dist):
         h2d = sum(t_.numel() * 4 for t_ in host[0])
         line = dict(metric="frame_pairs_per_sec", value=world * pairs * args.steps / (dev_ms / 1e3), unit="frame-pairs/s", n_gpus=world,
                     steps=args.steps, warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32", data="synthetic",
+                    dtype="tf32", data="synthetic",
                     config=dict(workload=wl["name"], clips_per_gpu=clips, frames=nf, directed_pairs_per_gpu=nprob, size=size,
                                 l2="flushed (256 MiB write) before every timed step", launch="eager"),
                     clocks=clocks,
@@ -563,10 +563,12 @@ def main():
 
     if rank == 0:
         line = dict(metric="frame_pairs_per_sec", value=value, unit="frame-pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="tf32", data="synthetic",
                     config=dict(workload=wl["name"], pairs_per_gpu=pairs, size=size, l2="flushed (256 MiB write) before every timed step",
                                 launch="CUDA graph replay" if graph is not None else "eager",
                                 sampling="exact reference random.sample stream (host C emulation)",
+                                arithmetic="fp32 tensors in HBM; contractions on tcgen05 as tf32 x tf32 -> fp32 (bf16 x bf16 -> fp32 in the fused "
+                                           "co-attention forward); index-producing contractions and everything else in fp32",
                                 grad_allreduce=bool(world > 1 and not args.no_allreduce), cross_gpu_negatives=xneg),
                     clocks=clocks,
                     e2e=dict(value=e2e_val, unit="frame-pairs/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
