@@ -105,7 +105,7 @@ class HotPath(nn.Module):
         N0 = self.grids[0] ** 2
         return ops.pyrandom_interframe(B // 2, TOP_K, N0, NEG_N), ops.pyrandom_crossmodal(B, N0, CROSS_NEG_N)
 
-    def forward_losses(self, raw, flang, fa, context, head, loc, bbox, negpos=None, negidx=None):
+    def forward_losses(self, raw, flang, fa, context, head, loc, bbox, negpos=None, negidx=None, decode=True):
         net = self.net
         LS.configure(size=self.size)
         hw = [(m.shape[2], m.shape[3]) for m in raw]
@@ -159,13 +159,28 @@ class HotPath(nn.Module):
         pred = [o['pred'] for o in sc]
         loss, comp, cell = LS.fused_losses(pred, sim, neg_sim, loc, bbox, q_if, k_if, neg_if, q_cm, k_cm, neg_cm,
                                            target=(best_n, gi, gj, t5), partner3=partner3, l_if=sc[0]['l_if'], l_cm=sc[0]['l_cm'])
-        boxes, iou, _, _, _ = LS.decode_boxes(pred, bbox, cell[:3])
-        return dict(loss=loss, comp=comp, y=y, iou=iou, boxes=boxes, cell=cell, corr=corr, sim=sim, pred=pred,
+        boxes = iou = None
+        if decode:
+            boxes, iou, _, _, _ = LS.decode_boxes(pred, bbox, cell[:3])
+        return dict(loss=loss, comp=comp, y=y, iou=iou, boxes=boxes, cell=cell, corr=corr, sim=sim, pred=pred, bbox=bbox,
                     obj=[o[1] for o in oo_obj], idx_if=idx_if, word=word)
 
     def step(self, raw, flang, fa, context, head, loc, dy_head, bbox, negpos=None, negidx=None):
         """forward + backward.  Returns a [6+B] tensor: (loss, yolo, rank, loc, interframe, cross, iou[0..B))."""
-        out = self.forward_losses(raw, flang, fa, context, head, loc, bbox, negpos, negidx)
+        out = self.forward_losses(raw, flang, fa, context, head, loc, bbox, negpos, negidx, decode=False)
+        # train-time decode + IoU (a18, a15) do not feed the backward: they go to an auxiliary stream instead of sitting between
+        # the loss and the first backward kernel on the critical path
+        def dec():
+            with torch.no_grad():
+                return LS.decode_boxes([p.detach() for p in out['pred']], bbox, out['cell'][:3])
+        boxes, iou, _, _, _ = self._branch(1, dec, *out['pred'])
+        out['boxes'], out['iou'] = boxes, iou
         torch.autograd.backward([out['loss']] + list(out['y']), [None] + list(dy_head))
+        if getattr(self, "_aux_pending", False):
+            cur = torch.cuda.current_stream()
+            for aux in self._aux:
+                cur.wait_stream(aux)
+            self._aux_pending = False
+            iou.record_stream(cur)
         c = out['comp']
         return torch.cat([torch.stack([out['loss'], c['yolo'], c['rank'], c['loc'], c['interframe'], c['cross']]).detach(), out['iou']])
