@@ -13,11 +13,11 @@ size_t umma_coattn_workspace_bytes(int F, int C, int N);
 namespace {
 
 // rows of S' = tau*S (already scaled): P = softmax(row), lse = max + log(sum).  One warp per row.
-__global__ void softmax_rows_kernel(float* __restrict__ S, float* __restrict__ lse, long long rows, int N) {
+__global__ void softmax_rows_kernel(float* __restrict__ S, float* __restrict__ lse, long long rows, int N, int ld) {
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  float* p = S + row * N;
+  float* p = S + row * ld;
   float m = -INFINITY;
   for (int j = lane; j < N; j += 32) m = fmaxf(m, p[j]);
   m = warp_max(m);
@@ -41,25 +41,42 @@ __global__ void exp_lse_kernel(float* __restrict__ S, const float* __restrict__ 
 }
 
 // dS = tau * P o (dP - delta 1^T), delta_i = sum_j P_ij dP_ij; in place over dP.  One warp per row.
-__global__ void softmax_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dP, long long rows, int N, float tau) {
+__global__ void softmax_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dP, long long rows, int N, int ld, float tau) {
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* p = P + row * N;
-  float* d = dP + row * N;
+  const float* p = P + row * ld;
+  float* d = dP + row * ld;
   float dl = 0.f;
   for (int j = lane; j < N; j += 32) dl = fmaf(p[j], d[j], dl);
   dl = warp_sum(dl);
   for (int j = lane; j < N; j += 32) d[j] = tau * p[j] * (d[j] - dl);
 }
 
+// dst[r][0..N) = src[(idx ? idx[r / C] : r / C)][r % C][0..N): a copy with the row pitch padded to ld (TMA needs 16-byte pitches)
+__global__ void pad_pitch_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst, long long rows, int C,
+                                 int N, int ld) {
+  const long long total = rows * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / N;
+    const int n = (int)(i - r * N);
+    const long long b = r / C, c = r - b * C;
+    const long long sb = idx ? idx[b] : b;
+    dst[r * ld + n] = src[(sb * C + c) * N + n];
+  }
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int pitch4(int N) { return (N + 3) & ~3; }
 
 }  // namespace
 
 extern "C" size_t dcnet_coattn_workspace_bytes(int F, int nprob, int C, int N, int precision) {
   if (nprob <= 0 || N <= 0 || F <= 0) return 256;
-  const size_t unfused = 2 * align256((size_t)nprob * N * N * sizeof(float)) + 256;   // S / P and dP scratch (backward; unfused forward)
+  size_t unfused = 2 * align256((size_t)nprob * N * N * sizeof(float)) + 256;   // S / P and dP scratch (backward; unfused forward)
+  if (N % 4 != 0 && precision >= 1)    // odd pitch: P / dP with the pitch padded to 4, plus padded copies of the maps and of dout
+    unfused = 2 * align256((size_t)nprob * N * pitch4(N) * sizeof(float)) + align256((size_t)F * C * pitch4(N) * sizeof(float)) +
+              align256((size_t)nprob * C * pitch4(N) * sizeof(float)) + 256;
   const size_t fused = umma_coattn_workspace_bytes(F, C, N);                           // bf16 staging of the maps + column norms
   return precision == 2 ? (unfused > fused ? unfused : fused) : unfused;
 }
@@ -87,7 +104,7 @@ extern "C" int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const
     UmmaEpilogue e{};
     e.out = S; e.ldo = N; e.so_b = NN; e.alpha = tau; e.idxA = qa; e.idxB = kb;
     DCNET_TRY(umma_gemm(A, B, nullptr, N, N, C, 0, 0, nprob, e, st));
-    softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(S, lse, rows, N);
+    softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(S, lse, rows, N, N);
     DCNET_LAUNCH_OK("coattn_fwd.softmax");
     // O[c,i] = sum_j Fb[c,j] P[i,j] : both K-major
     UmmaOperand A2{frames, C, N, N, CN, F, false}, B2{S, N, N, N, NN, nprob, false};
@@ -98,7 +115,7 @@ extern "C" int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const
   // S' = tau Fa^T Fb
   DCNET_TRY(sgemm_launch(frames, frames, S, N, N, C, nprob, 1, 1, N, CN, 0, N, 1, CN, 0, N, 1, NN, qa, kb, nullptr, tau, 0.f,
                          nullptr, 0, 0, st));
-  softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(S, lse, rows, N);
+  softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(S, lse, rows, N, N);
   DCNET_LAUNCH_OK("coattn_fwd.softmax");
   // O[c,i] = sum_j Fb[c,j] P[i,j]
   DCNET_TRY(sgemm_launch(frames, S, out, C, N, N, nprob, 1, N, 1, CN, 0, 1, N, NN, 0, N, 1, CN, kb, nullptr, oidx, 1.f, 0.f,
@@ -116,6 +133,42 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
   DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(F, nprob, C, N, precision), "coattn_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   const long long CN = (long long)C * N, NN = (long long)N * N;
+  if (precision >= 1 && N % 4 != 0 && C % 128 == 0 && reinterpret_cast<uintptr_t>(workspace) % 16 == 0) {
+    // odd row pitch (N = 169 at 416x416): the five contractions still run on tcgen05, on copies of the maps / dout whose pitch is
+    // padded to 4 positions and with P / dP at that pitch; the gradients land in dframes (pitch N) through the per-thread
+    // atomicAdd epilogue of the one-tile-per-CTA kernel
+    const int ld = pitch4(N);
+    const long long NL = (long long)N * ld, CL = (long long)C * ld;
+    char* w = (char*)workspace;
+    float* Pp = (float*)w; w += align256((size_t)nprob * NL * sizeof(float));
+    float* dPp = (float*)w; w += align256((size_t)nprob * NL * sizeof(float));
+    float* Fp = (float*)w; w += align256((size_t)F * CL * sizeof(float));
+    float* Gp = (float*)w;
+    const long long rows_ = (long long)nprob * N;
+    pad_pitch_kernel<<<148 * 8, 256, 0, st>>>(frames, nullptr, Fp, (long long)F * C, C, N, ld);
+    DCNET_LAUNCH_OK("coattn_bwd.pad");
+    pad_pitch_kernel<<<148 * 8, 256, 0, st>>>(dout, oidx, Gp, (long long)nprob * C, C, N, ld);
+    DCNET_LAUNCH_OK("coattn_bwd.pad");
+    UmmaOperand Fmn{Fp, C, N, ld, CL, F, true}, Fk{Fp, C, N, ld, CL, F, false};
+    UmmaOperand Gmn{Gp, C, N, ld, CL, nprob, true}, Gk{Gp, C, N, ld, CL, nprob, false};
+    UmmaOperand Pmn{Pp, N, N, ld, NL, nprob, true};
+    UmmaOperand dSk{dPp, N, N, ld, NL, nprob, false}, dSmn{dPp, N, N, ld, NL, nprob, true};
+    UmmaEpilogue e{};
+    e.out = Pp; e.ldo = ld; e.so_b = NL; e.alpha = tau; e.idxA = qa; e.idxB = kb;
+    DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    softmax_rows_kernel<<<ceil_div(rows_ * 32, 256), 256, 0, st>>>(Pp, nullptr, rows_, N, ld);   // re-normalised from these logits
+    DCNET_LAUNCH_OK("coattn_bwd.softmax");
+    e = UmmaEpilogue{}; e.out = dPp; e.ldo = ld; e.so_b = NL; e.alpha = 1.f; e.idxB = kb;
+    DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxC = kb;
+    DCNET_TRY(umma_gemm(Gk, Pmn, nullptr, C, N, N, 0, 0, nprob, e, st));
+    softmax_bwd_rows_kernel<<<ceil_div(rows_ * 32, 256), 256, 0, st>>>(Pp, dPp, rows_, N, ld, tau);
+    DCNET_LAUNCH_OK("coattn_bwd.softmax");
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = kb; e.idxC = qa;
+    DCNET_TRY(umma_gemm(Fk, dSk, nullptr, C, N, N, 0, 0, nprob, e, st));
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = qa; e.idxC = kb;
+    return umma_gemm(Fk, dSmn, nullptr, C, N, N, 0, 0, nprob, e, st);
+  }
   float* P = (float*)workspace;
   float* dP = (float*)((char*)workspace + align256((size_t)nprob * NN * sizeof(float)));
   const long long rows = (long long)nprob * N;
@@ -124,7 +177,7 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
   // sum to one in this precision (a 5e-4 logit mismatch times tau would otherwise show up as a 5e-3 error in P)
   auto exp_launch = [&]() {
     if (precision == 2) {
-      softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, nullptr, rows, N);
+      softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, nullptr, rows, N, N);
     } else {
       long long g = (rows * N + 255) / 256;
       exp_lse_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, st>>>(P, lse, rows, N);
@@ -157,7 +210,7 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
     // dFb[c,j] += sum_i dO[c,i] P[i,j]
     e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = oidx; e.idxC = kb;
     DCNET_TRY(umma_gemm(Gk, Pmn, nullptr, C, N, N, 0, 0, nprob, e, st));
-    softmax_bwd_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, dP, rows, N, tau);
+    softmax_bwd_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, dP, rows, N, N, tau);
     DCNET_LAUNCH_OK("coattn_bwd.softmax");
     // dFa[c,i] += sum_j Fb[c,j] dS[i,j]
     e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = kb; e.idxC = qa;
@@ -177,7 +230,7 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
   // dFb += dO P
   DCNET_TRY(sgemm_launch(dout, P, dframes, C, N, N, nprob, 1, N, 1, CN, 0, N, 1, NN, 0, N, 1, CN, oidx, nullptr, kb, 1.f, 0.f,
                          nullptr, 0, 1, st));
-  softmax_bwd_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, dP, rows, N, tau);
+  softmax_bwd_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, dP, rows, N, N, tau);
   DCNET_LAUNCH_OK("coattn_bwd.softmax");
   // dFa[c,i] += sum_j Fb[c,j] dS[i,j]
   DCNET_TRY(sgemm_launch(frames, dP, dframes, C, N, N, nprob, 1, N, 1, CN, 0, 1, N, NN, 0, N, 1, CN, kb, nullptr, qa, 1.f, 0.f,
