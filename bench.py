@@ -249,7 +249,19 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed to fd 1 when the communicator comes
+        # up) is sent to stderr by pointing fd 1 at fd 2 until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     pairs, size = wl["pairs"], wl["size"]
     if args.workload == "c4":
         return run_c4(args, wl, rank, world, dev, dist)
