@@ -169,6 +169,18 @@ class grounding_model(nn.Module):
         return [self.mapping_visu._modules[str(s)].fused(raw_fvisu[s].flatten(2), l2norm=True,
                                                          precision=p0 if s == 0 else self.precision) for s in range(3)]
 
+    def _head_layer(self, m, y):
+        """SURVEY 8(f) row 1, first step into the grounding head (model/DCNet_model.py:316-337, :505-506): its 1x1
+        ConvBatchNormReLU layers (fcn_emb[s][2]: 512->512, fcn_out[s][0]: 512->256) run on the same tcgen05 GEMM + fused BN kernels
+        as the rest of the path; the 3x3 conv and the final 1x1 conv with bias stay cuDNN."""
+        if self.head_on_tcgen05 and isinstance(m, ConvBatchNormReLU) and m.conv.kernel_size == (1, 1) and m.conv.out_channels in (256, 512) \
+                and m.conv.in_channels % 128 == 0:
+            B, _, h, w = y.shape
+            return m.fused(y.flatten(2), precision=self.precision).view(B, -1, h, w)
+        return m(y)
+
+    head_on_tcgen05 = True
+
     def map_visual_scale(self, raw_s, s):
         p0 = ops.EXACT_FP32 if self.precision == ops.EXACT_FP32 else ops.EXACT_FWD_TF32_BWD
         return self.mapping_visu._modules[str(s)].fused(raw_s.flatten(2), l2norm=True, precision=p0 if s == 0 else self.precision)
@@ -316,8 +328,10 @@ class grounding_model(nn.Module):
         for s in range(3):
             y = inter[s].view(B, -1, hw[s][0], hw[s][1])
             for m in list(self.fcn_emb._modules[str(s)])[1:]:
-                y = m(y)
-            outbox_raw.append(self.fcn_out._modules[str(s)](y).flatten(2))
+                y = self._head_layer(m, y)
+            for m in self.fcn_out._modules[str(s)]:
+                y = self._head_layer(m, y)
+            outbox_raw.append(y.flatten(2))
 
         oo, obj = zip(*[ops.only_obj(outbox_raw[s], sim[s]) for s in range(3)])
         locmap = self.location_branch(coords, list(obj), context, embedded, word_id)
