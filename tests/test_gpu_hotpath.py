@@ -117,3 +117,30 @@ def test_hotpath_graph_replay_equals_eager():
     torch.testing.assert_close(res, eager, rtol=1e-4, atol=1e-5)
     assert rel(static['raw'][2].grad, eager_graw) < 1e-2
     assert rel(hp.net.corr_conv[2][0].conv.weight.grad, eager_gw) < 1e-2
+
+
+def test_hotpath_streams_do_not_change_the_result():
+    """HotPath.scale_streams: one CUDA stream per pyramid scale plus two auxiliary streams for the sampling blocks, the fusion
+    terms and the decode.  Same kernels on the same data as the single-stream step: losses / IoU to 1e-5, gradients to the
+    atomics' noise (see test_hotpath_graph_replay_equals_eager); the host RNG stream ends in the same state."""
+    size, pairs = 256, 2
+    B = 2 * pairs
+    results = []
+    for streams in (True, False):
+        synth.seed_all(13)
+        hp = HotPath(size).to(DEV).train()
+        hp.scale_streams = streams
+        g = torch.Generator().manual_seed(78)
+        batch = synth.make_hotpath_batch(pairs, size, g)
+        static = _leaves(batch, DEV)
+        random.seed(6)
+        out = hp.step(static['raw'], static['flang'], static['fa'], static['context'], static['head'], static['loc'], static['dy_head'],
+                      static['bbox'])
+        torch.cuda.synchronize()
+        results.append((out.clone(), static['raw'][2].grad.clone(), static['raw'][0].grad.clone(), static['fa'].grad.clone(),
+                        hp.net.fcn_emb[1][0].conv.weight.grad.clone(), random.random()))
+    a, b = results
+    torch.testing.assert_close(a[0], b[0], rtol=1e-4, atol=1e-5)
+    for x, y in zip(a[1:5], b[1:5]):
+        assert rel(x, y) < 1e-2, rel(x, y)
+    assert a[5] == b[5]
