@@ -491,7 +491,8 @@ def main():
         ms_g = timed_sets([(lambda i=i: ops.gemm_tf32(frs[i], frs[(i + 1) % NSET], 1, 1, N2, N2, C_EMB, out=c_bufs[i])) for i in range(NSET)])
         fl_g = 2.0 * N2 * N2 * C_EMB * B
         ach_g = fl_g / (ms_g * 1e-3) / 1e12
-        ncu_traffic = {(256, 8): 87.5e6}.get((size, pairs))     # dram read+write of this launch, profiles/r1i_ncu_full_umma_gemm2.txt
+        ncu_traffic = {(256, 8): 88.2e6}.get((size, pairs))     # dram read+write of this launch, profiles/r1w_ncu_full_umma_gemm2.txt
+        # (67.2 MB read + 21.1 MB written when the profile ends: most of the 64 MB output is still dirty in L2; algorithmic 131 MB)
         roof = dict(bound="tensor", kernel="umma_gemm2_kernel (tcgen05 kind::tf32, persistent; S = Fa^T Fb of the co-attention backward, "
                     "M=N=%d K=%d, %d problems, one launch)" % (N2, C_EMB, B), achieved=ach_g, peak=peaks["tensor_burst"], unit="TFLOP/s",
                     frac=ach_g / peaks["tensor_burst"], traffic=ncu_traffic, ms=ms_g, dtype="tf32 operands (fp32 in HBM), fp32 accumulate",
@@ -511,7 +512,8 @@ def main():
         ach = flops / (ms * 1e-3) / 1e12
         roof_co = dict(bound="tensor", kernel="coattn_fused_kernel (finest scale, N=%d, %d pairs = %d directed problems, one launch)" % (N2, pairs, B),
                        achieved=ach, peak=peaks["tensor_burst"], unit="TFLOP/s", frac=ach / peaks["tensor_burst"],
-                       traffic={(256, 8): 17.7e6}.get((size, pairs)), ms=ms, stage_ms=ms_stage, executed_tflops=ach * 4.0 / 3.0,
+                       traffic={(256, 8): 16.9e6}.get((size, pairs)), ms=ms,   # profiles/r1w_ncu_full_coattn_fused.txt (staged bf16 maps; output in L2)
+                       stage_ms=ms_stage, executed_tflops=ach * 4.0 / 3.0,
                        l2="staged operands and outputs rotate over %d sets (%.0f MB)" % (NS2, NS2 * (stg[0].numel() + o_bufs[0].numel() * 4) / 1e6),
                        note="algorithmic 6*c*N^2 per pair; the kernel executes 8*c*N^2 (S recomputed per direction)",
                        peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
