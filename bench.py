@@ -33,6 +33,8 @@ import torch  # noqa: E402
 WORKLOADS = {
     "c2": dict(pairs=8, size=256, name="C2: 8 frame-pairs 256x256 per GPU (32x32 finest map), fwd+bwd of correspondence/fusion/decode path"),
     "c3": dict(pairs=16, size=416, name="C3: 16 frame-pairs 416x416 per GPU (52x52 finest map, 2704x2704 similarity), fwd+bwd"),
+    "c5": dict(pairs=64, size=416, name="C5: 64 frame-pairs 416x416 per GPU, fwd+bwd (BASELINE configs[4]; add --xgpu-negatives on N > 1 GPUs for the "
+               "NCCL all-gathered cross-GPU contrastive negatives)"),
     "c4": dict(pairs=224, size=256, clips=8, frames=8,
                name="C4: 8 clips x 8 frames 256x256 per GPU, all-pairs inter-frame correspondence (28 unordered = 56 directed pairs per clip), forward"),
 }
