@@ -117,3 +117,22 @@ def test_product_path_refuses_cpu_tensors():
         net(torch.zeros(2, 1, 1, 1), torch.ones(2, 20, dtype=torch.long), None)
     with pytest.raises(RuntimeError, match="CUDA-only"):
         ops.rownorm(torch.zeros(4, 8))
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference`: the reference's CPU path (oracle port) on a bounded sample; exactly one JSON line on stdout with
+    the keys the driver reads (impl, metric, unit, value, cpu_baseline, e2e with zero transfer bytes)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "frame_pairs_per_sec" and d["unit"] == "frame-pairs/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
