@@ -276,23 +276,33 @@ def main():
     random.seed(1000 + rank)
     g = torch.Generator().manual_seed(9000 + rank)
 
-    # ---- host batches (pinned) and static device buffers
-    NB = 2
-    host = []
-    for _ in range(NB):
-        b = synth.make_hotpath_batch(pairs, size, g)
-        flat = dict(raw=b['raw'], flang=[b['flang']], fa=[b['fa']], context=[b['context']], head=b['head'], loc=b['loc'], dy_head=b['dy_head'],
-                    bbox=[b['bbox']])
-        host.append({k: [t.pin_memory() for t in v] for k, v in flat.items()})
-    grad_keys = ('raw', 'flang', 'fa', 'context', 'head', 'loc')
-    static = {k: [t.to(dev).requires_grad_(k in grad_keys) for t in v] for k, v in host[0].items()}
-    np_, ni_ = hp.draw_indices(B)
-    h_negpos, h_negidx = torch.from_numpy(np_).pin_memory(), torch.from_numpy(ni_).pin_memory()
-    s_negpos, s_negidx = h_negpos.to(dev), h_negidx.to(dev)
+    # ---- host batches (pinned) and static device buffers.  Every tensor that crosses PCIe per step (forward inputs of the path,
+    # then the two index tensors) is a view of ONE packed byte buffer per set (synth.PackedSet): a set moves with one copy.
     # dy_head is the gradient the head's backward hands to the fusion output: it is produced on the device in a real step,
     # so it stays resident; every forward input of the path (maps, text vectors, head/location outputs, boxes, indices) is copied.
+    NB = 2
     H2D_KEYS = ('raw', 'flang', 'fa', 'context', 'head', 'loc', 'bbox')
-    h2d_bytes = sum(t.numel() * t.element_size() for k in H2D_KEYS for t in host[0][k]) + h_negpos.numel() * 4 + h_negidx.numel() * 8
+    grad_keys = ('raw', 'flang', 'fa', 'context', 'head', 'loc')
+    batches = []
+    for _ in range(NB):
+        b = synth.make_hotpath_batch(pairs, size, g)
+        batches.append(dict(raw=b['raw'], flang=[b['flang']], fa=[b['fa']], context=[b['context']], head=b['head'], loc=b['loc'],
+                            dy_head=b['dy_head'], bbox=[b['bbox']]))
+    np_, ni_ = hp.draw_indices(B)
+    idx0 = [torch.from_numpy(np_), torch.from_numpy(ni_)]
+    slots = [(k, j) for k in H2D_KEYS for j in range(len(batches[0][k]))]
+    n_maps = len(slots)                                     # views [0, n_maps) = forward inputs, [n_maps, n_maps+2) = negpos, negidx
+    like = [batches[0][k][j] for k, j in slots] + idx0
+    host_sets = [synth.PackedSet(like, pin=True).fill([bt[k][j] for k, j in slots] + idx0) for bt in batches]
+    static_set = synth.PackedSet(like, device=dev)
+    stage_set = synth.PackedSet(like, device=dev)
+    static_set.buf.copy_(host_sets[0].buf); stage_set.buf.copy_(host_sets[0].buf)
+    static = {k: [] for k in H2D_KEYS}
+    for (k, j), v in zip(slots, static_set.views):
+        static[k].append(v.requires_grad_(k in grad_keys))
+    static['dy_head'] = [t.to(dev) for t in batches[0]['dy_head']]
+    s_negpos, s_negidx = static_set.views[n_maps], static_set.views[n_maps + 1]
+    h2d_bytes = static_set.nbytes                          # the bytes of the two copies per step (maps span + index span)
     h_out = torch.empty(6 + B, dtype=torch.float32).pin_memory()
     d2h_bytes = h_out.numel() * 4
 
@@ -376,37 +386,34 @@ def main():
     # while the GPU executes step t; the draw of every timed step is inside the timed region (steady-state pipeline).
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(1)
-    h_idx = [(torch.empty_like(h_negpos).pin_memory(), torch.empty_like(h_negidx).pin_memory()) for _ in range(2)]
+    h_idx = [synth.PackedSet(idx0, pin=True) for _ in range(2)]
 
     def draw(slot):
         npos, nidx = hp.draw_indices(B)
-        h_idx[slot][0].copy_(torch.from_numpy(npos)); h_idx[slot][1].copy_(torch.from_numpy(nidx))
+        h_idx[slot].views[0].copy_(torch.from_numpy(npos)); h_idx[slot].views[1].copy_(torch.from_numpy(nidx))
         return slot
 
     pending = [pool.submit(draw, 0)]
 
     # Input pipeline: the H2D copy of step i+1 (pinned host -> a staging set on a copy stream) runs under the GPU work of step i;
-    # at the start of a step the staged inputs move into the graph's static buffers device-to-device.  Every step's inputs
-    # still cross PCIe inside the timed region; the wall clock sees max(copy, compute) instead of their sum.
+    # at the start of a step the staged set moves into the graph's static buffers device-to-device (one copy).  Every step's
+    # inputs still cross PCIe inside the timed region; the wall clock sees max(copy, compute) instead of their sum.
     main_stream = torch.cuda.current_stream()
     copy_stream = torch.cuda.Stream()
-    stage = {k: [torch.empty_like(t) for t in static[k]] for k in H2D_KEYS}
-    st_negpos, st_negidx = torch.empty_like(s_negpos), torch.empty_like(s_negidx)
     ev_staged, ev_consumed = torch.cuda.Event(), torch.cuda.Event()
+    stage_maps, stage_idx = stage_set.span(0, n_maps), stage_set.span(n_maps, n_maps + 2)
+    assert stage_idx.numel() == h_idx[0].nbytes
 
     def prefetch_maps(i):
         copy_stream.wait_event(ev_consumed)                # the previous contents of the staging set have been consumed
         with torch.cuda.stream(copy_stream), torch.no_grad():
-            hb = host[i % NB]
-            for k in H2D_KEYS:
-                for dst, src in zip(stage[k], hb[k]):
-                    dst.copy_(src, non_blocking=True)
+            stage_maps.copy_(host_sets[i % NB].span(0, n_maps), non_blocking=True)
 
     def prefetch_indices():
         slot = pending.pop().result()                      # drawn on the worker thread while the GPU was busy
         pending.append(pool.submit(draw, slot ^ 1))
-        with torch.cuda.stream(copy_stream):
-            st_negpos.copy_(h_idx[slot][0], non_blocking=True); st_negidx.copy_(h_idx[slot][1], non_blocking=True)
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            stage_idx.copy_(h_idx[slot].buf, non_blocking=True)
             ev_staged.record(copy_stream)
 
     ev_consumed.record(main_stream)
@@ -415,10 +422,7 @@ def main():
     def e2e_step(i):
         main_stream.wait_event(ev_staged)
         with torch.no_grad():
-            for k in H2D_KEYS:
-                for dst, src in zip(static[k], stage[k]):
-                    dst.copy_(src, non_blocking=True)
-            s_negpos.copy_(st_negpos, non_blocking=True); s_negidx.copy_(st_negidx, non_blocking=True)
+            static_set.buf.copy_(stage_set.buf, non_blocking=True)
         ev_consumed.record(main_stream)
         prefetch_maps(i + 1)                               # next step's maps cross PCIe under this step's kernels
         do_step()
@@ -589,7 +593,7 @@ def main():
                     clocks=clocks,
                     e2e=dict(value=e2e_val, unit="frame-pairs/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                              ms_per_step=e2e_ms / args.steps, last_loss=loss_val,
-                             pipeline="H2D of step i+1 (pinned host -> staging set, copy stream) under the kernels of step i; staged -> static inputs device-to-device; every step's loss is copied back, the host reads it one step late"),
+                             pipeline="H2D of step i+1 (pinned host -> staging set, copy stream) under the kernels of step i; staged -> static inputs device-to-device, each set one packed buffer = one copy; every step's loss is copied back, the host reads it one step late"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                     roofline=roof, roofline_coattn=roof_co, roofline_hbm=roof_hbm, cpu_baseline=cpu_base)
         print(json.dumps(line), flush=True)

@@ -63,3 +63,30 @@ def make_hotpath_batch(pairs, size, gen=None, T=20, C=512):
     loc = [torch.rand(B, g * g, generator=gen) for g in gs]
     dy_head = [torch.randn(B, C, g * g, generator=gen) * 1e-3 for g in gs]
     return dict(raw=raw, flang=flang, fa=fa, context=context, head=head, loc=loc, dy_head=dy_head, bbox=make_boxes(pairs, size, gen))
+
+
+class PackedSet:
+    """One step's input tensors laid out back to back in ONE byte buffer (segments aligned to 256 B, so every view keeps the
+    16-byte alignment the TMA descriptors need): a whole input set moves host->device or device->device with a single copy
+    instead of one launch per tensor.  `views[i]` has the shape / dtype of `like[i]`; `span(i0, i1)` is the byte range that
+    holds views i0..i1-1 (for copying a subset, e.g. the maps before the late-drawn indices)."""
+    ALIGN = 256
+
+    def __init__(self, like, device=None, pin=False):
+        self.offsets, n = [], 0
+        for t in like:
+            self.offsets.append(n)
+            n += (t.numel() * t.element_size() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.nbytes = n
+        self.buf = torch.zeros(n, dtype=torch.uint8, device=device, pin_memory=pin)
+        self.views = [self.buf[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape) for o, t in zip(self.offsets, like)]
+
+    def span(self, i0, i1):
+        lo = self.offsets[i0]
+        hi = self.offsets[i1] if i1 < len(self.offsets) else self.nbytes
+        return self.buf[lo:hi]
+
+    def fill(self, tensors):
+        for v, t in zip(self.views, tensors):
+            v.copy_(t)
+        return self

@@ -136,3 +136,31 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_packed_set_views_alias_one_buffer():
+    """bench.py's input sets: tensors of mixed dtype as aligned views of one byte buffer; a copy of the buffer moves them all,
+    and a view can be a gradient-requiring leaf whose storage is refreshed through the buffer."""
+    from dcnet_b200.synth import PackedSet
+    like = [torch.randn(2, 3, 5), torch.arange(7, dtype=torch.int64), torch.arange(9, dtype=torch.int32), torch.randn(4)]
+    a, b = PackedSet(like).fill(like), PackedSet(like)
+    assert a.nbytes % 256 == 0 and all(o % 256 == 0 for o in a.offsets)
+    assert all(v.data_ptr() % 16 == 0 and v.is_contiguous() for v in a.views)
+    b.buf.copy_(a.buf)
+    for v, t in zip(b.views, like):
+        assert v.dtype == t.dtype and v.shape == t.shape and torch.equal(v, t)
+    # a subset span: only the two integer tensors
+    c = PackedSet(like)
+    c.span(1, 3).copy_(a.span(1, 3))
+    assert torch.equal(c.views[1], like[1]) and torch.equal(c.views[2], like[2]) and float(c.views[0].abs().sum()) == 0
+    assert c.span(3, 4).numel() == 256 and c.span(0, 4).numel() == c.nbytes
+    # leaf views: refreshed through the buffer under no_grad, differentiated as usual
+    x = b.views[0].requires_grad_(True)
+    assert x.is_leaf
+    (x * x).sum().backward()
+    assert torch.allclose(x.grad, 2 * like[0])
+    with torch.no_grad():
+        b.buf.zero_()
+    x.grad = None
+    (x + 1).sum().backward()
+    assert float(x.detach().abs().sum()) == 0 and torch.equal(x.grad, torch.ones_like(x))
