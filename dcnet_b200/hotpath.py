@@ -55,13 +55,19 @@ class HotPath(nn.Module):
     # forward ran on) goes to its own CUDA stream; the finest scale stays on the caller's stream.  Fork/join with events, so
     # the whole step still captures into one CUDA graph.
     scale_streams = True
+    # Stream priorities (0 = default, -1 = higher).  The auxiliary branches (fusion text terms, the two sampling + InfoNCE
+    # branches, train-time decode) are short kernels whose results the chains wait for; at default priority their CTAs queue
+    # behind the persistent one-CTA-per-SM GEMMs of the finest scale.  Measured on C2 (profiles/r1z_stream_priorities.txt):
+    # aux -1 -> 1.315 ms against 1.371 ms; raising the coarse-scale streams as well, or instead, gives nothing (1.33-1.36 ms).
+    side_priority = (0, 0)
+    aux_priority = (-1, -1)
 
     def _run_scales(self, chain):
         if not self.scale_streams:
             return [chain(s) for s in range(3)]
         cur = torch.cuda.current_stream()
         if getattr(self, "_side", None) is None:
-            self._side = [torch.cuda.Stream(), torch.cuda.Stream()]
+            self._side = [torch.cuda.Stream(priority=p) for p in self.side_priority]
             # parameters are shared by nothing across scales, but their AccumulateGrad nodes live on the stream of the first
             # iteration; the engine synchronises the streams itself, the warning about it is noise here
             if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
@@ -90,7 +96,7 @@ class HotPath(nn.Module):
             return fn()
         cur = torch.cuda.current_stream()
         if getattr(self, "_aux", None) is None:
-            self._aux = [torch.cuda.Stream(), torch.cuda.Stream()]
+            self._aux = [torch.cuda.Stream(priority=p) for p in self.aux_priority]
         aux = self._aux[i]
         aux.wait_stream(cur)
         with torch.cuda.stream(aux):

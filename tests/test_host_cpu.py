@@ -54,7 +54,7 @@ def test_pyrandom_interframe_matches_cpython(P, K, N0, n):
     assert after == random.random()          # stream left exactly where the reference would leave it
 
 
-@pytest.mark.parametrize("B,N0,n", [(4, 64, 5), (6, 169, 5), (2, 16, 5)])
+@pytest.mark.parametrize("B,N0,n", [(4, 64, 5), (6, 169, 5), (2, 16, 5), (16, 64, 5), (3, 65, 5), (1, 64, 0)])
 def test_pyrandom_crossmodal_matches_cpython(B, N0, n):
     random.seed(7)
     got = ops.pyrandom_crossmodal(B, N0, n)
