@@ -115,6 +115,13 @@ class HotPath(nn.Module):
         net = self.net
         LS.configure(size=self.size)
         hw = [(m.shape[2], m.shape[3]) for m in raw]
+        # `fa` feeds every scale's chain.  As a leaf, its AccumulateGrad node lives on the stream of its first consumer -- the
+        # coarsest scale's side stream -- and autograd queues every scale's contribution on that stream in the order the CPU walks
+        # the graph (finest chain first), so the coarsest chain's own backward sat in the queue behind the finest chain's gradient
+        # (profiles/r1z_timeline_graph_replay.txt: it started 400 us late and ended the step).  A view taken on the caller's stream
+        # moves that accumulation to the caller's stream, where it queues behind the finest chain's own work.
+        if fa.requires_grad:
+            fa = fa.view_as(fa)
         best_n, gi, gj, t5, _, _ = ops.build_target(bbox, self.size, LS.args.anchor_imsize, LS.anchors_full)
         fa_neg = partner3 = None
         if self.cross_gpu_negatives:
