@@ -491,6 +491,32 @@ def main():
     pending.pop().result()
     pool.shutdown()
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("DCNET_E2E_PROBE") and graph is not None:
+        # where the difference between e2e and value sits: wall clock per step of back-to-back replays with pieces of the loop
+        def probe(name, fn, n=200):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            print("probe %-28s %.4f ms/step" % (name, (time.perf_counter() - t1) * 1e3 / n), file=sys.stderr)
+        probe("replay only", graph.replay)
+        probe("replay + D2D", lambda: (static_set.buf.copy_(stage_set.buf, non_blocking=True), graph.replay()))
+        probe("replay + D2H", lambda: (graph.replay(), h_outs[0].copy_(res, non_blocking=True)))
+        probe("replay + D2D + D2H", lambda: (static_set.buf.copy_(stage_set.buf, non_blocking=True), graph.replay(), h_outs[0].copy_(res, non_blocking=True)))
+        def with_h2d():
+            static_set.buf.copy_(stage_set.buf, non_blocking=True)
+            ev_consumed.record(main_stream)
+            copy_stream.wait_event(ev_consumed)
+            with torch.cuda.stream(copy_stream):
+                stage_set.buf.copy_(host_sets[0].buf, non_blocking=True)
+                ev_staged.record(copy_stream)
+            graph.replay()
+            h_outs[0].copy_(res, non_blocking=True)
+            main_stream.wait_event(ev_staged)
+        probe("... + overlapped H2D", with_h2d)
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
