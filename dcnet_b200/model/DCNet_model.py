@@ -282,14 +282,24 @@ class grounding_model(nn.Module):
         neg = ops.gather_cols(vit, img_n, negidx.permute(1, 0, 2).reshape(-1)).view(N0, B, CROSS_NEG_N, C)
         return q, k, neg, word, negidx
 
+    # inference: the [B,SN,SN] relation tensor of the location branch is never built (ops.loc_rank8)
+    rank8_location = True
+
     def location_branch(self, coords, obj_score, context, embedded, word_id):
-        """:556-610, stays PyTorch; written for any number of positions."""
+        """:556-610; written for any number of positions.  Training (batch statistics, gradients) stays PyTorch; at inference on
+        CUDA the relation matrix is kept in its rank-8 form and the branch runs in three kernels of this library."""
         B = obj_score[0].shape[0]
         _, flang_loc = self.loc_attn(context, embedded, word_id)
         flang_loc = F.normalize(flang_loc, p=2, dim=1)
-        coord_map_ = torch.cat([c.t() for c in coords], 0)[None].expand(B, -1, -1)
         obj = F.normalize(torch.cat(obj_score, 1), p=2, dim=1)
         SN = obj.shape[1]
+        if self.rank8_location and not self.training and not torch.is_grad_enabled() and obj.is_cuda:
+            # eval-mode BatchNorm1d(8): the embedding of a position does not depend on the image
+            E = F.normalize(self.loc_embedding(torch.cat([c.t() for c in coords], 0)), p=2, dim=1)
+            lin, bn = self.loc_text_embedding[0], self.loc_text_embedding[1]
+            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            return ops.loc_rank8(E, obj, lin.weight, lin.bias, scale, bn.bias - bn.running_mean * scale, flang_loc)
+        coord_map_ = torch.cat([c.t() for c in coords], 0)[None].expand(B, -1, -1)
         emb = self.loc_embedding(coord_map_.reshape(-1, 8)).reshape(B, SN, -1)
         emb = F.normalize(emb, p=2, dim=2)
         rel = torch.bmm(emb, emb.transpose(1, 2)) * obj[:, None, :]

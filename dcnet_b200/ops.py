@@ -102,6 +102,25 @@ def pix2text(x, fa):
     return sim
 
 
+def loc_rank8(E, obj, W, bias, bn_scale, bn_shift, flang, return_raw=False):
+    """location scores without the [B,SN,SN] relation tensor (forward only; model/DCNet_model.py:556-603).
+    E [SN,8] normalised coordinate embeddings, obj [B,SN] normalised objectness, W [C,SN] / bias [C] the Linear,
+    bn_scale / bn_shift [C] the eval-mode BatchNorm1d affine, flang [B,C] -> score [B,SN] (min-max normalised per image)."""
+    E, obj, W, flang = _c(E.detach(), name="E"), _c(obj.detach(), name="obj"), _c(W.detach(), name="W"), _c(flang.detach(), name="flang")
+    bn_scale, bn_shift = _c(bn_scale.detach(), name="bn_scale"), _c(bn_shift.detach(), name="bn_shift")
+    bias = None if bias is None else _c(bias.detach(), name="bias")
+    B, SN = obj.shape
+    C = W.shape[0]
+    if E.shape != (SN, 8) or W.shape[1] != SN or flang.shape != (B, C):
+        raise ValueError(f"loc_rank8: shapes E {tuple(E.shape)}, obj {tuple(obj.shape)}, W {tuple(W.shape)}, flang {tuple(flang.shape)}")
+    G = torch.empty(B, C, 8, device=obj.device, dtype=F32)
+    raw = torch.empty(B, SN, device=obj.device, dtype=F32)
+    score = torch.empty(B, SN, device=obj.device, dtype=F32)
+    _lib.call("dcnet_loc_rank8_fwd", _p(E), _p(obj), _p(W), SN, _p(bias), _p(bn_scale), _p(bn_shift), _p(flang),
+              _p(G), _p(raw), _p(score), B, SN, C, _st())
+    return (score, raw, G) if return_raw else score
+
+
 def coord_map(h, w, device):
     out = torch.empty(8, h, w, device=device, dtype=F32)
     _lib.call("dcnet_coord_map", _p(out), h, w, _st())

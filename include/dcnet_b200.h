@@ -138,6 +138,16 @@ DCNET_API int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const fl
  * The training path gets these from dcnet_bn_act_fwd's epilogue; the clip path (mean of several corr maps) calls this.  Forward only. */
 DCNET_API int dcnet_pix2text(const float* x, const float* fa, const float* fa_neg, float* sim, float* neg_sim, int B, int C, int N, void* stream);
 
+/* ---- location branch at inference, rank-8 form (model/DCNet_model.py:556-603, model/test_DCNet_model.py same
+ * lines).  Replaces   rel = bmm(E, E^T) * obj[:,None,:]  ->  Linear(SN -> C)  ->  BatchNorm1d (eval)  ->  ReLU  ->  normalize over C
+ * -> dot with the location phrase vector -> min-max over the positions   without the [B,SN,SN] tensor:
+ *   E [SN,8] normalised coordinate embeddings (batch independent), obj [B,SN] L2-normalised objectness, W [C,ldw>=SN] + bias [C]
+ *   (NULL = none) the Linear, bn_scale = gamma / sqrt(running_var + eps), bn_shift = beta - running_mean * bn_scale, flang [B,C].
+ *   Workspaces: G [B,C,8], raw [B,SN] (the scores before min-max).  Output score [B,SN] in [0,1].  C <= 1024.  Forward only. */
+DCNET_API int dcnet_loc_rank8_fwd(const float* E, const float* obj, const float* W, int ldw, const float* bias,
+                                  const float* bn_scale, const float* bn_shift, const float* flang,
+                                  float* G, float* raw, float* score, int B, int SN, int C, void* stream);
+
 /* ---- a7: coordinate map (model/DCNet_model.py:23-39), [8,h,w], batch independent ---------------------- */
 DCNET_API int dcnet_coord_map(float* coord, int h, int w, void* stream);
 

@@ -5,6 +5,7 @@ import random
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from dcnet_b200 import ops, synth
 from oracle import dcnet_oracle as O
@@ -652,3 +653,33 @@ def test_explicit_negative_partners_equal_local_reversal():
     p3 = torch.stack([bn, gi, gj]).flip(1).contiguous()
     l1 = ops.ground_losses(pred, sim, neg, loc, bn, gi, gj, t5, partner3=p3)
     torch.testing.assert_close(l0, l1, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,SN,C", [(2, 1344, 512), (3, 3549, 512), (1, 85, 64), (4, 21, 8)])
+def test_loc_rank8_matches_materialised_relation(B, SN, C):
+    """the location branch at inference without the [B,SN,SN] tensor, against the materialised formula of
+    model/DCNet_model.py:556-603 evaluated in fp64 (fp32 kernel, different summation order: bars 2e-5 on the unit-scale raw scores)."""
+    g = torch.Generator().manual_seed(31 + SN)
+    E = F.normalize(torch.rand(SN, 8, generator=g), dim=1)
+    obj = F.normalize(torch.rand(B, SN, generator=g), dim=1)
+    W = torch.randn(C, SN, generator=g) * (3.0 / SN ** 0.5)
+    bias = torch.randn(C, generator=g) * 0.1
+    scale, shift = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    f = F.normalize(torch.randn(B, C, generator=g), dim=1)
+    d = lambda t: t.double()
+    rel = torch.bmm(d(E)[None].expand(B, -1, -1), d(E).t()[None].expand(B, -1, -1)) * d(obj)[:, None, :]
+    y = torch.relu((rel @ d(W).t() + d(bias)) * d(scale) + d(shift)).permute(0, 2, 1)
+    m = (F.normalize(y, dim=1) * d(f)[:, :, None]).sum(1)
+    mn, mx = m.min(1)[0][:, None], m.max(1)[0][:, None]
+    ref = (m - mn) / (mx - mn + 1e-6)
+    score, raw, G = ops.loc_rank8(*(t.to(DEV) for t in (E, obj, W, bias, scale, shift, f)), return_raw=True)
+    Gref = torch.einsum('cq,bq,qk->bck', d(W), d(obj), d(E))
+    assert float((G.double().cpu() - Gref).abs().max()) < 1e-5 * float(Gref.abs().max()) + 1e-7
+    assert float((raw.double().cpu() - m).abs().max()) < 2e-5
+    spread = float((mx - mn).min())
+    assert float((score.double().cpu() - ref).abs().max()) < 4e-5 / max(spread, 1e-3)
+    assert float(score.min()) >= 0.0 and float(score.max()) <= 1.0
+    # no bias
+    score2 = ops.loc_rank8(E.to(DEV), obj.to(DEV), W.to(DEV), None, scale.to(DEV), (shift + scale * bias).to(DEV), f.to(DEV))
+    assert float((score2 - score).abs().max()) < 1e-5 / max(spread, 1e-3)

@@ -164,3 +164,28 @@ def test_packed_set_views_alias_one_buffer():
     x.grad = None
     (x + 1).sum().backward()
     assert float(x.detach().abs().sum()) == 0 and torch.equal(x.grad, torch.ones_like(x))
+
+
+def test_location_rank8_algebra_matches_materialised_relation():
+    """The identity dcnet_loc_rank8_fwd is built on (model/DCNet_model.py:556-603): Linear(bmm(E, E^T) * obj) = E (E^T diag(obj) W^T),
+    checked in fp64 against the materialised form, through BN (eval), ReLU, channel normalisation, the phrase dot product and min-max."""
+    g = torch.Generator().manual_seed(5)
+    B, SN, C = 3, 85, 32
+    E = torch.nn.functional.normalize(torch.rand(SN, 8, generator=g, dtype=torch.float64), dim=1)
+    obj = torch.nn.functional.normalize(torch.rand(B, SN, generator=g, dtype=torch.float64), dim=1)
+    W = torch.randn(C, SN, generator=g, dtype=torch.float64) / SN ** 0.5
+    bias = torch.randn(C, generator=g, dtype=torch.float64)
+    scale, shift = torch.rand(C, generator=g, dtype=torch.float64) + 0.5, torch.randn(C, generator=g, dtype=torch.float64) * 0.1
+    f = torch.nn.functional.normalize(torch.randn(B, C, generator=g, dtype=torch.float64), dim=1)
+
+    def tail(z):                                            # z [B,SN,C]
+        y = torch.relu(z * scale + shift).permute(0, 2, 1)
+        m = (torch.nn.functional.normalize(y, dim=1) * f[:, :, None]).sum(1)
+        mn, mx = m.min(1)[0][:, None], m.max(1)[0][:, None]
+        return (m - mn) / (mx - mn + 1e-6)
+
+    rel = torch.bmm(E[None].expand(B, -1, -1), E.t()[None].expand(B, -1, -1)) * obj[:, None, :]
+    ref = tail(rel @ W.t() + bias)
+    G = torch.einsum('cq,bq,qk->bck', W, obj, E)
+    got = tail(torch.einsum('bck,pk->bpc', G, E) + bias)
+    assert float((ref - got).abs().max()) < 1e-12
