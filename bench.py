@@ -165,7 +165,6 @@ def run_c4(args, wl, rank, world, dev, dist):
         run_step()
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    h_out = torch.empty(3).pin_memory()
 
     def barrier():
         torch.cuda.synchronize()
@@ -222,8 +221,7 @@ def run_c4(args, wl, rank, world, dev, dist):
     t0 = time.perf_counter()
     for i in range(args.warmup, args.warmup + args.steps):
         e2e_step(i)
-    main_stream.synchronize()
-    res = h_outs[(args.warmup + args.steps - 1) % 2].clone()
+    main_stream.synchronize()                              # the last step's result has reached the host inside the timed region
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
