@@ -189,3 +189,22 @@ def test_location_rank8_algebra_matches_materialised_relation():
     G = torch.einsum('cq,bq,qk->bck', W, obj, E)
     got = tail(torch.einsum('bck,pk->bpc', G, E) + bias)
     assert float((ref - got).abs().max()) < 1e-12
+
+
+def test_location_rank8_batch_statistics_from_moments():
+    """Next step of SURVEY 8f rank 2 (training): BatchNorm1d batch statistics of z[b,p,c] = G[b,c,:].e_p + bias[c] over all (b,p)
+    follow from G and the first / second moments of E (8 and 8x8 numbers) -- no [B,SN,C] pass.  fp64 check of that algebra."""
+    g = torch.Generator().manual_seed(6)
+    B, SN, C = 4, 77, 16
+    E = torch.nn.functional.normalize(torch.rand(SN, 8, generator=g, dtype=torch.float64), dim=1)
+    G = torch.randn(B, C, 8, generator=g, dtype=torch.float64)
+    bias = torch.randn(C, generator=g, dtype=torch.float64)
+    z = torch.einsum('bck,pk->bpc', G, E) + bias
+    mean_ref, var_ref = z.reshape(-1, C).mean(0), z.reshape(-1, C).var(0, unbiased=False)
+    e1 = E.mean(0)                                          # [8]
+    e2 = E.t() @ E / SN                                     # [8,8]
+    mean = bias + (G @ e1).mean(0)
+    second = torch.einsum('bck,kl,bcl->c', G, e2, G) / B + 2 * bias * (G @ e1).mean(0) + bias * bias
+    var = second - mean * mean
+    assert float((mean - mean_ref).abs().max()) < 1e-12
+    assert float((var - var_ref).abs().max()) < 1e-11
