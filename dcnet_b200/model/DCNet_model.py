@@ -284,6 +284,9 @@ class grounding_model(nn.Module):
 
     # inference: the [B,SN,SN] relation tensor of the location branch is never built (ops.loc_rank8)
     rank8_location = True
+    # training: the same identity through torch ops (no [B,SN,SN] tensor, no SN-long GEMM).  Opt-in until it has been through the
+    # GPU gradient tests (checked on CPU in fp64: tests/test_host_cpu.py::test_location_branch_rank8_training_form)
+    rank8_location_train = False
 
     def location_branch(self, coords, obj_score, context, embedded, word_id):
         """:556-610; written for any number of positions.  Training (batch statistics, gradients) stays PyTorch; at inference on
@@ -302,8 +305,18 @@ class grounding_model(nn.Module):
         coord_map_ = torch.cat([c.t() for c in coords], 0)[None].expand(B, -1, -1)
         emb = self.loc_embedding(coord_map_.reshape(-1, 8)).reshape(B, SN, -1)
         emb = F.normalize(emb, p=2, dim=2)
-        rel = torch.bmm(emb, emb.transpose(1, 2)) * obj[:, None, :]
-        rel = self.loc_text_embedding(rel.reshape(-1, SN)).reshape(B, SN, -1).permute(0, 2, 1)
+        if self.rank8_location_train:
+            # same identity with differentiable torch ops: Linear(bmm(E,E^T)*obj) = E (E^T diag(obj) W^T); the modules (and their
+            # batch statistics / running-stat updates) are the reference's, only the [B,SN,SN] tensor and its SN-long GEMM are gone
+            lin = self.loc_text_embedding[0]
+            G = torch.einsum('cq,bq,bqk->bck', lin.weight, obj, emb)
+            z = torch.einsum('bck,bpk->bpc', G, emb) + lin.bias
+            for m in list(self.loc_text_embedding)[1:]:
+                z = m(z.reshape(-1, z.shape[-1]))
+            rel = z.reshape(B, SN, -1).permute(0, 2, 1)
+        else:
+            rel = torch.bmm(emb, emb.transpose(1, 2)) * obj[:, None, :]
+            rel = self.loc_text_embedding(rel.reshape(-1, SN)).reshape(B, SN, -1).permute(0, 2, 1)
         rel = F.normalize(rel, p=2, dim=1)
         m = (rel * flang_loc[:, :, None]).sum(1)
         mn, mx = m.min(1)[0][:, None], m.max(1)[0][:, None]

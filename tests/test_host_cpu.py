@@ -208,3 +208,44 @@ def test_location_rank8_batch_statistics_from_moments():
     var = second - mean * mean
     assert float((mean - mean_ref).abs().max()) < 1e-12
     assert float((var - var_ref).abs().max()) < 1e-11
+
+
+def test_location_branch_rank8_training_form():
+    """grounding_model.location_branch with rank8_location_train: same scores, same parameter / input gradients and the same
+    running-statistics updates as the materialised form of model/DCNet_model.py:556-603 (train mode, fp64, CPU)."""
+    import copy
+    import torch.nn as nn
+    from dcnet_b200.model.DCNet_model import grounding_model
+    torch.manual_seed(3)
+    size = 96                                               # 3*3 + 6*6 + 12*12 = 189 positions
+    net = grounding_model(corpus=list(range(50)), emb_size=512, visumodel=nn.Identity(), size=size).double().train()
+    grids = [size // 32, size // 16, size // 8]
+    B, T = 3, 7
+    g = torch.Generator().manual_seed(4)
+    coords = [torch.rand(8, n * n, generator=g, dtype=torch.float64) for n in grids]
+    context = torch.randn(B, T, 1024, generator=g, dtype=torch.float64)
+    embedded = torch.randn(B, T, net.loc_text_embedding[0].out_features, generator=g, dtype=torch.float64)
+    word_id = torch.randint(1, 50, (B, T), generator=g)
+    word_id[1, 5:] = 0
+    outs = []
+    for flag in (False, True):
+        m = copy.deepcopy(net)
+        m.rank8_location_train = flag
+        obj = [torch.rand(B, n * n, generator=torch.Generator().manual_seed(8 + n), dtype=torch.float64).requires_grad_() for n in grids]
+        ctx = context.clone().requires_grad_()
+        score = m.location_branch(coords, obj, ctx, embedded, word_id)
+        (score * torch.linspace(0.5, 1.5, score.shape[1], dtype=torch.float64)).sum().backward()
+        grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+        stats = {n: b.clone() for n, b in m.named_buffers() if n.startswith(("loc_embedding", "loc_text_embedding"))}
+        outs.append((score.detach(), grads, [o.grad for o in obj], ctx.grad, stats))
+    (s0, g0, o0, c0, st0), (s1, g1, o1, c1, st1) = outs
+    assert s0.shape == (B, sum(n * n for n in grids))
+    assert float((s0 - s1).abs().max()) < 1e-10
+    assert set(g0) == set(g1) and any(k.startswith("loc_text_embedding.0") for k in g0)
+    for k in g0:
+        assert float((g0[k] - g1[k]).abs().max()) < 1e-9 * max(1.0, float(g0[k].abs().max())), k
+    for a, b in zip(o0, o1):
+        assert float((a - b).abs().max()) < 1e-9 * max(1.0, float(a.abs().max()))
+    assert float((c0 - c1).abs().max()) < 1e-9 * max(1.0, float(c0.abs().max()))
+    for k in st0:
+        assert float((st0[k].double() - st1[k].double()).abs().max()) < 1e-10, k
