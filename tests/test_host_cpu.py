@@ -249,3 +249,32 @@ def test_location_branch_rank8_training_form():
     assert float((c0 - c1).abs().max()) < 1e-9 * max(1.0, float(c0.abs().max()))
     for k in st0:
         assert float((st0[k].double() - st1[k].double()).abs().max()) < 1e-10, k
+
+
+def test_pyrandom_crossmodal_block_sampler_randomised():
+    """the block sampler against CPython from arbitrary stream positions (not only a fresh seed): sizes around the set-path /
+    pool-path and bit-length boundaries, pre-advanced states, both compaction paths' shared bookkeeping (prefix counts, exact
+    raw positions after the own-image sample, block refills inside a sample)."""
+    rs = np.random.RandomState(11)
+    for trial in range(40):
+        B = int(rs.randint(1, 9))
+        N0 = int(rs.choice([22, 23, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 169, 255, 256, 257, 676]))
+        seed, adv = int(rs.randint(0, 10 ** 6)), int(rs.randint(0, 700))
+        random.seed(seed)
+        for _ in range(adv):
+            random.getrandbits(32)
+        state = random.getstate()
+        got = ops.pyrandom_crossmodal(B, N0, 5)
+        after = random.getstate()
+        random.setstate(state)
+        ref = np.empty((B, N0, 5), dtype=np.int64)
+        for ii in range(B):
+            for jj in range(N0):
+                for index in range(B):
+                    pool = list(range(N0))
+                    if index == ii:
+                        pool.remove(jj)
+                    last = random.sample(pool, 5)
+                ref[ii, jj] = last
+        assert (ref == got).all(), (trial, B, N0, seed, adv)
+        assert random.getstate() == after, (trial, B, N0, seed, adv)
