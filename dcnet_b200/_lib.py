@@ -7,6 +7,7 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(HERE, "..", "include", "dcnet_b200.h")
 LIB_PATH = os.path.join(HERE, "libdcnet_sm100.so")
+ABI_VERSION = 4
 
 _CTYPES = {
     "int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong, "size_t": ctypes.c_size_t,
@@ -56,7 +57,7 @@ def lib():
             fn = getattr(L, name)   # AttributeError if the .so does not export a declared symbol
             fn.restype = _ctype(ret)
             fn.argtypes = [_ctype(t) for t, _ in args]
-        if L.dcnet_abi_version() != 3:
+        if L.dcnet_abi_version() != ABI_VERSION:
             raise RuntimeError("dcnet_b200: ABI version mismatch")
         _lib = L
     return _lib

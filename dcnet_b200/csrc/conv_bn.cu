@@ -58,10 +58,11 @@ __global__ void batchsum_kernel(const float* __restrict__ dz, float* __restrict_
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ z, int B, int C, int N, float eps, float momentum,
                                                        float* __restrict__ mean, float* __restrict__ invstd,
-                                                       float* __restrict__ rmean, float* __restrict__ rvar) {
+                                                       float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ nbt) {
   __shared__ float sh[32];
   const int c = blockIdx.x;
   const long long M = (long long)B * N;
+  if (nbt && c == 0 && threadIdx.x == 0) *nbt += 1;
   float s = 0.f;
   for (long long i = threadIdx.x; i < M; i += blockDim.x) {
     const long long b = i / N;
@@ -107,9 +108,11 @@ __global__ void __launch_bounds__(256) chan_sums_kernel(const float* __restrict_
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, int C, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ rmean, float* __restrict__ rvar) {
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   long long* __restrict__ nbt) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (nbt && c == 0) *nbt += 1;
   const float mu = sums[c] / count;
   const float var = fmaxf(sums[C + c] / count - mu * mu, 0.f);
   mean[c] = mu;
@@ -536,19 +539,22 @@ extern "C" int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1
 }
 
 extern "C" int dcnet_bn_finalize(const float* stat_sums, long long count, int C, float eps, float momentum,
-                                 float* mean, float* invstd, float* running_mean, float* running_var, void* stream) {
+                                 float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
+                                 void* stream) {
   DCNET_CHECK_ARG(stat_sums && mean && invstd && count > 0 && C > 0, "bn_finalize: bad arguments");
   DCNET_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running_mean/var must both be given");
-  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, as_stream(stream)>>>(stat_sums, (float)count, C, eps, momentum, mean, invstd, running_mean, running_var);
+  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, as_stream(stream)>>>(stat_sums, (float)count, C, eps, momentum, mean, invstd, running_mean, running_var,
+                                                                          num_batches_tracked);
   DCNET_LAUNCH_OK("bn_finalize");
   return 0;
 }
 
 extern "C" int dcnet_bn_stats(const float* z, int B, int C, int N, float eps, float momentum,
-                              float* mean, float* invstd, float* running_mean, float* running_var, void* stream) {
+                              float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
+                              void* stream) {
   DCNET_CHECK_ARG(z && mean && invstd && B > 0 && C > 0 && N > 0, "bn_stats: bad arguments");
   DCNET_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_stats: running_mean/var must both be given");
-  bn_stats_kernel<<<C, 256, 0, as_stream(stream)>>>(z, B, C, N, eps, momentum, mean, invstd, running_mean, running_var);
+  bn_stats_kernel<<<C, 256, 0, as_stream(stream)>>>(z, B, C, N, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked);
   DCNET_LAUNCH_OK("bn_stats");
   return 0;
 }

@@ -137,8 +137,10 @@ extern "C" int dcnet_lagnorm_bwd(const float* lag, const float* nrm, const float
 }
 
 extern "C" int dcnet_crossmodal_words(const float* lag, const float* vit, const float* fm_w, const float* fm_b,
-                                      float* M, long long* word, int B, int T, int C, int N0, void* stream) {
+                                      int fm_cout, int fm_cin, float* M, long long* word, int B, int T, int C, int N0, void* stream) {
   DCNET_CHECK_ARG(lag && vit && fm_w && fm_b && M && word && B > 0 && T > 0 && T <= MAXT && C > 0 && N0 > 0, "crossmodal_words: bad arguments (T<=32)");
+  // the kernel indexes fm_w as [T][T][3]: like the reference's Conv1d(20, 20, 3) (model/DCNet_model.py:288, :635) any other sentence length is an error
+  DCNET_CHECK_ARG(fm_cout == T && fm_cin == T, "crossmodal_words: feature_map is Conv1d(%d -> %d, k=3) but the batch has T=%d words (the reference requires T == in_channels)", fm_cin, fm_cout, T);
   cudaStream_t st = as_stream(stream);
   // M[b] (T x N0) = lag[b] (T x C) . vit[b] (C x N0)
   DCNET_TRY(sgemm_launch(lag, vit, M, T, N0, C, B, 1, C, 1, (long long)T * C, 0, N0, 1, (long long)C * N0, 0, N0, 1, (long long)T * N0,

@@ -44,7 +44,13 @@ __global__ void build_target_kernel(const float* __restrict__ bbox, int B, int s
   const float grid = (float)(size / (32 >> s));
   const float cx = __fmul_rn(ncx, grid), cy = __fmul_rn(ncy, grid);
   const float gw = __fmul_rn(nw, grid), gh = __fmul_rn(nh, grid);
-  const long long gi = (long long)cx, gj = (long long)cy;   // .long() truncates
+  long long gi = (long long)cx, gj = (long long)cy;   // .long() truncates
+  // The reference clamps boxes to [0, size-1] before this point (train_DCNet.py:608), so 0 <= gi, gj < grid there; with an
+  // unclamped box its python indexing raises (or wraps for negatives).  Every consumer of (gi, gj) here indexes device memory
+  // unchecked (ground loss, scatter, decode), so the cell is saturated into the grid instead of being handed on out of range.
+  const long long gmax = (long long)(size / (32 >> s)) - 1;
+  gi = gi < 0 ? 0 : (gi > gmax ? gmax : gi);
+  gj = gj < 0 ? 0 : (gj > gmax ? gmax : gj);
   best_n[b] = bn;
   gi_o[b] = gi;
   gj_o[b] = gj;

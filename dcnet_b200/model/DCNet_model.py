@@ -141,7 +141,9 @@ class grounding_model(nn.Module):
             self.fcn_out = nn.Sequential(OrderedDict([
                 (str(i), nn.Sequential(ConvBatchNormReLU(emb_size, emb_size // 2, 1, 1, 0, 1, leaky=leaky),
                                        nn.Conv2d(emb_size // 2, 3 * 5, kernel_size=1))) for i in range(3)]))
-        self.exact_sampling = True     # reproduce the reference's random.sample stream
+        # reproduce the reference's random.sample stream: training draws its negatives from it, eval
+        # advances it by what the reference's (discarded) eval-mode sampling consumes.  False: eval leaves `random` untouched.
+        self.exact_sampling = True
         self._idx_cache = {}
         self._capture = None
         self.precision = ops.TENSOR_TF32   # GEMM-shaped ops on tcgen05 (TF32 operands, fp32 accumulate); ops.EXACT_FP32 = CUDA cores
@@ -369,6 +371,14 @@ class grounding_model(nn.Module):
         sim_score = [shp(sim[s], s) for s in range(3)]
         loc_score = [shp(loc[s], s) for s in range(3)]
         if not self.training:
+            if self.exact_sampling:
+                # The reference runs both sampling blocks in eval mode too and drops their results (:381-430, :625-637 are
+                # unconditional).  Their only lasting effect is on Python's global `random` stream: advance it
+                # exactly as the reference would (host-only C emulation, no device work), so a run that alternates train and
+                # validation epochs keeps drawing the reference's negatives.  exact_sampling = False skips this.
+                N0 = hw[0][0] * hw[0][1]
+                ops.pyrandom_interframe(B // 2, TOP_K, N0, NEG_N)
+                ops.pyrandom_crossmodal(B, N0, CROSS_NEG_N)
             return outbox, sim_score, loc_score, [shp(o, s) for s, o in enumerate(oo)]
         q_cm, k_cm, neg_cm, _, _ = self.crossmodal(fv[0], context)
         self.last_neg_sim_score = [shp(neg_sim[s], s) for s in range(3)]      # train_DCNet.py:623-627, fused

@@ -27,8 +27,11 @@ class ConvBatchNormReLU(nn.Sequential):
         are applied by the caller through u / cc."""
         w = self.conv.weight.view(self.conv.weight.shape[0], -1)
         bn = self.bn
+        # num_batches_tracked: nn.BatchNorm2d.forward increments it every training step; the statistics kernel does it here so
+        # that state dicts stay interchangeable with a reference-trained checkpoint (no extra launch)
         return ops.conv_bn_act(x1, w, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.training, x2=x2, u=u, cc=cc, fa=fa,
-                               momentum=bn.momentum, eps=bn.eps, slope=self.slope, l2norm=l2norm, precision=precision, fa_neg=fa_neg)
+                               momentum=bn.momentum, eps=bn.eps, slope=self.slope, l2norm=l2norm, precision=precision, fa_neg=fa_neg,
+                               num_batches_tracked=bn.num_batches_tracked)
 
 
 class YOLOLayer(nn.Module):

@@ -159,10 +159,13 @@ def crossmodal_words(lag, vit, fm_w, fm_b):
     lag, vit = _c(lag, name="lag"), _c(vit, name="vit")
     B, T, C = lag.shape
     N0 = vit.shape[2]
+    if tuple(fm_w.shape) != (T, T, 3) or tuple(fm_b.shape) != (T,):
+        raise RuntimeError("dcnet_b200: feature_map weight %s / bias %s do not match the sentence length T=%d (the reference's "
+                           "Conv1d(20,20,3) raises on any other length, model/DCNet_model.py:288)" % (tuple(fm_w.shape), tuple(fm_b.shape), T))
     M = torch.empty(B, T, N0, device=lag.device, dtype=F32)
     word = torch.empty(B, N0, device=lag.device, dtype=torch.long)
     _lib.call("dcnet_crossmodal_words", _p(lag), _p(vit), _p(_c(fm_w.detach(), name="fm_w")), _p(_c(fm_b.detach(), name="fm_b")),
-              _p(M), _p(word), B, T, C, N0, _st())
+              fm_w.shape[0], fm_w.shape[1], _p(M), _p(word), B, T, C, N0, _st())
     return word, M
 
 
@@ -215,6 +218,14 @@ def decode(pred, size, anchor_imsize, anchors_full, best_n=None, gi=None, gj=Non
 
 
 def bbox_iou(b1, b2, x1y1x2y2=True):
+    """utils/utils.py:76-104; like the reference the two box lists broadcast against each other ([1,4] vs [n,4])."""
+    if b1.dim() != 2 or b2.dim() != 2 or b1.shape[1] != 4 or b2.shape[1] != 4:
+        raise ValueError("bbox_iou: boxes must be [n,4], got %s and %s" % (tuple(b1.shape), tuple(b2.shape)))
+    if b1.shape[0] != b2.shape[0]:
+        if b1.shape[0] != 1 and b2.shape[0] != 1:
+            raise ValueError("bbox_iou: %d boxes against %d (row counts must match or one side must be a single box)" % (b1.shape[0], b2.shape[0]))
+        n = max(b1.shape[0], b2.shape[0])
+        b1, b2 = b1.expand(n, 4), b2.expand(n, 4)
     b1, b2 = _c(b1.float(), name="box1"), _c(b2.float(), name="box2")
     out = torch.empty(b1.shape[0], device=b1.device, dtype=F32)
     _lib.call("dcnet_bbox_iou", _p(b1), _p(b2), b1.shape[0], int(bool(x1y1x2y2)), _p(out), _st())
@@ -248,7 +259,7 @@ class _ConvBNAct(torch.autograd.Function):
     BatchNorm statistics are taken from the unpadded z."""
 
     @staticmethod
-    def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope, l2norm, precision):
+    def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope, l2norm, precision, nbt=None):
         x1 = _c(x1, name="x1")
         x2 = _c(x2, name="x2")
         weight = _c(weight, name="weight")
@@ -273,16 +284,16 @@ class _ConvBNAct(torch.autograd.Function):
             _lib.call("dcnet_conv1x1_fwd", _p(x1p), K1, _p(x2p), K2, _p(weight), ldw, _p(u), _p(ccp), _p(zp), B, C, Np, None, precision, st)
             z = zp[..., :N].contiguous()
             if training:
-                _lib.call("dcnet_bn_stats", _p(z), B, C, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
+                _lib.call("dcnet_bn_stats", _p(z), B, C, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), _p(nbt), st)
         elif training and precision == 1:
             # tensor-core path: BatchNorm sums come out of the GEMM epilogue, z is not re-read
             sums = torch.empty(2 * C, device=dev, dtype=F32)
             _lib.call("dcnet_conv1x1_fwd", _p(x1), K1, _p(x2), K2, _p(weight), ldw, _p(u), _p(cc), _p(z), B, C, N, _p(sums), precision, st)
-            _lib.call("dcnet_bn_finalize", _p(sums), B * N, C, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
+            _lib.call("dcnet_bn_finalize", _p(sums), B * N, C, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), _p(nbt), st)
         else:
             _lib.call("dcnet_conv1x1_fwd", _p(x1), K1, _p(x2), K2, _p(weight), ldw, _p(u), _p(cc), _p(z), B, C, N, None, precision, st)
         if training and precision != 1 and not padded:
-            _lib.call("dcnet_bn_stats", _p(z), B, C, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), st)
+            _lib.call("dcnet_bn_stats", _p(z), B, C, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), _p(nbt), st)
         elif not training:
             _lib.call("dcnet_bn_eval_stats", _p(running_mean), _p(running_var), C, eps, _p(mean), _p(invstd), st)
         y = torch.empty_like(z)
@@ -344,7 +355,7 @@ class _ConvBNAct(torch.autograd.Function):
                 x2p = _pad_n(x2, Np) if (need_w and x2 is not None) else None
                 _lib.call("dcnet_conv1x1_bwd_weight", _p(dzp), _p(x1p), K1, _p(x2p), K2, _p(dW), ldw, _p(du), _p(dccp), B, C, Np, precision, st)
             dcc = dccp[:, :N].contiguous() if dccp is not None else None
-            return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None)
+            return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None)
         dx1 = torch.empty_like(x1) if ctx.needs_input_grad[0] else None
         dx2 = torch.empty_like(x2) if (x2 is not None and ctx.needs_input_grad[1]) else None
         if dx1 is not None or dx2 is not None:
@@ -359,18 +370,18 @@ class _ConvBNAct(torch.autograd.Function):
         if need_w or du is not None or dcc is not None:
             _lib.call("dcnet_conv1x1_bwd_weight", _p(dz), _p(x1) if need_w else None, K1, _p(x2) if need_w else None, K2,
                       _p(dW), ldw, _p(du), _p(dcc), B, C, N, precision, st)
-        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None)
+        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None)
 
 
 EXACT_FP32, TENSOR_TF32, TENSOR_BF16_FUSED, EXACT_FWD_TF32_BWD = 0, 1, 2, 3
 
 
 def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
-                momentum=0.999, eps=1e-5, slope=0.0, l2norm=False, precision=TENSOR_TF32, fa_neg=None):
+                momentum=0.999, eps=1e-5, slope=0.0, l2norm=False, precision=TENSOR_TF32, fa_neg=None, num_batches_tracked=None):
     """x1 [B,K1,N] (+x2 [B,K2,N]); weight [C,ldw].  Returns y [B,C,N] or (y, sim, neg_sim) when fa [B,C] is given.
     precision: TENSOR_TF32 = tcgen05 GEMMs (<=1e-3 relative), EXACT_FP32 = CUDA-core fp32 (<=1e-5)."""
     return _ConvBNAct.apply(x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, bool(training), float(momentum),
-                            float(eps), float(slope), bool(l2norm), int(precision))
+                            float(eps), float(slope), bool(l2norm), int(precision), num_batches_tracked if training else None)
 
 
 class _CoAttn(torch.autograd.Function):

@@ -28,5 +28,6 @@ def xywh2xyxy(x):
 
 
 def bbox_iou(box1, box2, x1y1x2y2=True):
-    """IoU of row-aligned boxes [n,4] (clamp(.,0) intersection, +1e-16 in the denominator, no +1 pixel convention)."""
+    """IoU of boxes [n,4] vs [n,4] (or [1,4] broadcast against [n,4], as build_target uses it, train_DCNet.py:303):
+    clamp(.,0) intersection, +1e-16 in the denominator, no +1 pixel convention (utils/utils.py:76-104)."""
     return ops.bbox_iou(box1.cuda() if not box1.is_cuda else box1, box2.cuda() if not box2.is_cuda else box2, x1y1x2y2)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DCNET_ABI_VERSION 3
+#define DCNET_ABI_VERSION 4
 #define DCNET_API __attribute__((visibility("default")))
 
 /* ---- library ---------------------------------------------------------------------------------------- */
@@ -97,15 +97,18 @@ DCNET_API int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, f
 DCNET_API int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1, const float* x2, int K2,
                                        float* dW, int ldw, float* du, float* dcc, int B, int C, int N, int precision, void* stream);
 
-/* mean/invstd (+ running statistics, momentum, unbiased variance) from the epilogue sums: count = B*N */
+/* mean/invstd (+ running statistics, momentum, unbiased variance) from the epilogue sums: count = B*N.
+ * num_batches_tracked (optional, one int64 on the device) is incremented like nn.BatchNorm2d does per training step. */
 DCNET_API int dcnet_bn_finalize(const float* stat_sums, long long count, int C, float eps, float momentum,
-                                float* mean, float* invstd, float* running_mean, float* running_var, void* stream);
+                                float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
+                                void* stream);
 
 /* BatchNorm statistics of z [B,C,N] over (B,N): mean[C], invstd[C] = 1/sqrt(biased var + eps); when
  * running_mean/var are non-NULL they are updated in place with `momentum` and the UNBIASED variance
  * (PyTorch convention; the reference uses momentum 0.999, eps 1e-5, model/darknet.py:145).               */
 DCNET_API int dcnet_bn_stats(const float* z, int B, int C, int N, float eps, float momentum,
-                             float* mean, float* invstd, float* running_mean, float* running_var, void* stream);
+                             float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
+                             void* stream);
 /* eval mode: mean = running_mean, invstd = 1/sqrt(running_var + eps) */
 DCNET_API int dcnet_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
                                   float* mean, float* invstd, void* stream);
@@ -219,9 +222,10 @@ DCNET_API int dcnet_rownorm_bwd(const float* y, const float* nrm, const float* d
 DCNET_API int dcnet_lagnorm_fwd(const float* context, float* lag, float* nrm, int B, int T, int C, void* stream);
 DCNET_API int dcnet_lagnorm_bwd(const float* lag, const float* nrm, const float* dlag, float* dcontext, int B, int T, int C, void* stream);
 /* word[b,n] = argmax_t softmax_t(Conv1d_{T->T,k=3,pad=1}(M)[b,t,n]) (first maximum), M = lag . vit [B,T,N0]
- * computed inside (scratch M [B,T,N0] caller-provided).  fm_w [T,T,3], fm_b [T].                          */
+ * computed inside (scratch M [B,T,N0] caller-provided).  fm_w [fm_cout,fm_cin,3], fm_b [fm_cout]; both must equal T
+ * (the reference's Conv1d(20,20,3) raises on any other sentence length, model/DCNet_model.py:288,:635).          */
 DCNET_API int dcnet_crossmodal_words(const float* lag, const float* vit, const float* fm_w, const float* fm_b,
-                                     float* M, long long* word, int B, int T, int C, int N0, void* stream);
+                                     int fm_cout, int fm_cin, float* M, long long* word, int B, int T, int C, int N0, void* stream);
 
 /* ---- a14: build_target (train_DCNet.py:265-332) -------------------------------------------------------
  * bbox [B,4] xyxy (pixels, already clamped).  Per sample: best_n (0..8, first maximum of the 9 anchor IoUs),

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in protos:
         assert hasattr(L, name), name
-    assert L.dcnet_abi_version() == 3
+    assert L.dcnet_abi_version() == _lib.ABI_VERSION
     assert isinstance(_lib.launch_count(), int)
 
 
