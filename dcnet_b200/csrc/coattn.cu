@@ -66,14 +66,101 @@ __global__ void pad_pitch_kernel(const float* __restrict__ src, const int* __res
   }
 }
 
+// Backward, between the two N x N contractions: for problem z and query i
+//   delta[z,i] = <dO[:,i], O[:,i]>   the softmax-backward row term sum_j P_ij dP_ij, taken from the SAVED output instead of P
+//   r[z,i] <- 1 / r[z,i]             (r = row sums of E = exp(tau S - shift))
+// block (32, 8): 32 lanes x 4 consecutive positions (float4), 8 channel rows per step; grid (N/128, nprob).
+__global__ void __launch_bounds__(256) coattn_delta_kernel(const float* __restrict__ dO, const float* __restrict__ O, const int* __restrict__ oidx,
+                                                           float* __restrict__ r, float* __restrict__ delta, int C, int N) {
+  const int z = blockIdx.y;
+  const int n = (blockIdx.x * 32 + threadIdx.x) * 4;
+  __shared__ float part[8][128];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (n < N) {
+    const long long src = (long long)oidx[z] * C * N + n;
+#pragma unroll 4
+    for (int c = threadIdx.y; c < C; c += 8) {
+      const float4 g = *reinterpret_cast<const float4*>(dO + src + (long long)c * N);
+      const float4 o = *reinterpret_cast<const float4*>(O + src + (long long)c * N);
+      acc[0] = fmaf(g.x, o.x, acc[0]); acc[1] = fmaf(g.y, o.y, acc[1]); acc[2] = fmaf(g.z, o.z, acc[2]); acc[3] = fmaf(g.w, o.w, acc[3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) part[threadIdx.y][threadIdx.x * 4 + i] = acc[i];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += part[k][t];
+    const int nn = blockIdx.x * 128 + t;
+    if (nn < N) {
+      delta[(long long)z * N + nn] = s;
+      r[(long long)z * N + nn] = 1.f / r[(long long)z * N + nn];
+    }
+  }
+}
+
+// After dS' = tau (dP - delta) P has been formed with the delta above.  The saved output comes from the forward's bf16 operands, so
+// delta is off by a relative ~1e-4 against the tf32 P / dP used here; rows of dS' then sum to rho_i = tau (delta_true - delta)_i
+// instead of zero, and because the columns of the maps share a large common component that small row offset would not cancel in
+// Fb dS^T (measured: 6e-3 gradient error at N = 1024 against 9e-4).  rho comes for free as the row sums of the dS' epilogue;
+// dS = dS' - rho_i P_ij exactly, which moves into the [C,N] maps:
+//     dFa[:,i]  = Fb dS'^T[:,i] - rho_i O[:,i]              (O ~ Fb P^T: second-order error now)
+//     dFb      += (dO - rho Fa) P  +  Fa dS'
+// This kernel writes dOs[z][c,i] = (dO[c,i] - rho_i Fa[c,i]) / r_i (rounded to tf32: the A operand of dOs E) and adds -rho_i O[c,i]
+// to dframes[qa[z]].  Same tiling as coattn_delta_kernel.
+__global__ void __launch_bounds__(256) coattn_fix_kernel(const float* __restrict__ dO, const float* __restrict__ O, const float* __restrict__ frames,
+                                                         const int* __restrict__ oidx, const int* __restrict__ qa, const float* __restrict__ inv_r,
+                                                         const float* __restrict__ rho, float* __restrict__ dOs, float* __restrict__ dframes,
+                                                         int C, int N) {
+  const int z = blockIdx.y;
+  const int n = (blockIdx.x * 32 + threadIdx.x) * 4;
+  if (n >= N) return;
+  const long long so = (long long)oidx[z] * C * N + n;
+  const long long sq = (long long)qa[z] * C * N + n;
+  float* dst = dOs + (long long)z * C * N + n;
+  const float4 iv = *reinterpret_cast<const float4*>(inv_r + (long long)z * N + n);
+  const float4 rh = *reinterpret_cast<const float4*>(rho + (long long)z * N + n);
+  auto rn = [](float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); };
+#pragma unroll 4
+  for (int c = threadIdx.y; c < C; c += 8) {
+    const float4 g = *reinterpret_cast<const float4*>(dO + so + (long long)c * N);
+    const float4 o = *reinterpret_cast<const float4*>(O + so + (long long)c * N);
+    const float4 f = *reinterpret_cast<const float4*>(frames + sq + (long long)c * N);
+    *reinterpret_cast<float4*>(dst + (long long)c * N) =
+        make_float4(rn((g.x - rh.x * f.x) * iv.x), rn((g.y - rh.y * f.y) * iv.y), rn((g.z - rh.z * f.z) * iv.z), rn((g.w - rh.w * f.w) * iv.w));
+    float* d = dframes + sq + (long long)c * N;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(-rh.x * o.x), "f"(-rh.y * o.y), "f"(-rh.z * o.z), "f"(-rh.w * o.w) : "memory");
+  }
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int pitch4(int N) { return (N + 3) & ~3; }
 
 }  // namespace
 
+// Backward: the N x N tensors (P, then dP -> dS in place) are produced and consumed chunk by chunk of problems, in ONE reused
+// scratch that is sized to stay resident in the 126 MB L2 (2 x chunk x N^2 fp32 <= g_bwd_l2_budget): the five contractions and
+// the two row kernels of a chunk run back to back, every N^2 line is rewritten while still dirty in L2, so S / P / dP / dS do not
+// travel to HBM and the workspace no longer grows with the number of problems.  A chunk keeps >= one wave of 128x256 tiles.
+static long long g_bwd_l2_budget = 1ll << 62;      // default: one chunk (see profiles/r2b: per-problem chunks starve the [C,N]-output contractions)
+extern "C" int dcnet_coattn_bwd_l2_budget(long long bytes) { g_bwd_l2_budget = bytes > 0 ? bytes : (1ll << 62); return 0; }
+static int coattn_bwd_chunk(int nprob, int N) {
+  const long long per = 2ll * N * N * (long long)sizeof(float);
+  long long c = g_bwd_l2_budget / per;
+  if (c < 1) c = 1;
+  if (c > nprob) c = nprob;
+  return (int)c;
+}
+
 extern "C" size_t dcnet_coattn_workspace_bytes(int F, int nprob, int C, int N, int precision) {
   if (nprob <= 0 || N <= 0 || F <= 0) return 256;
-  size_t unfused = 2 * align256((size_t)nprob * N * N * sizeof(float)) + 256;   // S / P and dP scratch (backward; unfused forward)
+  // S / P and dP scratch: all problems for the unfused forward (precision <= 1), one L2-resident chunk for the backward
+  const int chunk = (precision == 2) ? coattn_bwd_chunk(nprob, N) : nprob;
+  size_t unfused = 2 * align256((size_t)chunk * N * N * sizeof(float)) + 256;
+  if (precision == 2 && N % 4 == 0)    // fused-epilogue backward: dO / r [chunk,C,N] + row sums and delta [chunk,N] each
+    unfused += align256((size_t)chunk * C * N * sizeof(float)) + 3 * align256((size_t)chunk * N * sizeof(float));
   if (N % 4 != 0 && precision >= 1)    // odd pitch: P / dP with the pitch padded to 4, plus padded copies of the maps and of dout
     unfused = 2 * align256((size_t)nprob * N * pitch4(N) * sizeof(float)) + align256((size_t)F * C * pitch4(N) * sizeof(float)) +
               align256((size_t)nprob * C * pitch4(N) * sizeof(float)) + 256;
@@ -127,8 +214,9 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
                                 const float* out, int n_out, const float* lse, const float* dout, float* dframes,
                                 int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,
                                 void* stream) {
-  (void)out;
+  (void)staged;
   DCNET_CHECK_ARG(frames && qa && kb && oidx && lse && dout && dframes && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_bwd: bad arguments");
+  DCNET_CHECK_ARG(out || precision != 2, "coattn_bwd: the saved forward output is needed (delta = <dO, O>)");
   if (nprob == 0) return 0;
   DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(F, nprob, C, N, precision), "coattn_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
@@ -169,10 +257,16 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
     e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = qa; e.idxC = kb;
     return umma_gemm(Fk, dSmn, nullptr, C, N, N, 0, 0, nprob, e, st);
   }
+  const int chunk = (precision == 2) ? coattn_bwd_chunk(nprob, N) : nprob;
   float* P = (float*)workspace;
-  float* dP = (float*)((char*)workspace + align256((size_t)nprob * NN * sizeof(float)));
-  const long long rows = (long long)nprob * N;
+  float* dP = (float*)((char*)workspace + align256((size_t)chunk * NN * sizeof(float)));
   const bool tc = coattn_tc_ok(precision, C, N, frames, dout, dframes) && coattn_tc_ok(precision, C, N, P, dP, P);
+  const int nprob_all = nprob;
+  const int* qa_all = qa; const int* kb_all = kb; const int* oidx_all = oidx; const float* lse_all = lse;
+  for (int p0 = 0; p0 < nprob_all; p0 += chunk) {
+  nprob = (nprob_all - p0 < chunk) ? nprob_all - p0 : chunk;
+  qa = qa_all + p0; kb = kb_all + p0; oidx = oidx_all + p0; lse = lse_all + (long long)p0 * N;
+  const long long rows = (long long)nprob * N;
   // precision 2: the forward's lse comes from bf16 logits; P is re-normalised from the logits recomputed here so that its rows
   // sum to one in this precision (a 5e-4 logit mismatch times tau would otherwise show up as a 5e-3 error in P)
   auto exp_launch = [&]() {
@@ -190,34 +284,58 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
     UmmaOperand dSk{dP, N, N, N, NN, nprob, false}, dSmn{dP, N, N, N, NN, nprob, true};
     UmmaEpilogue e{};
     e.out = P; e.ldo = N; e.so_b = NN; e.alpha = tau; e.idxA = qa; e.idxB = kb;
-    if (precision == 2 && staged && reinterpret_cast<uintptr_t>(staged) % 256 == 0 && umma_coattn_supported(C, N)) {
-      // P = exp(tau S - lse) in one kernel: S from the forward's bf16 staging of the maps -- the same operand bits the fused
-      // forward took its lse from, so the rows of P sum to one without a renormalisation pass -- and exp in the GEMM epilogue
-      const int ld = (N + 7) & ~7;
-      const float* s16 = reinterpret_cast<const float*>(staged);
-      UmmaOperand Smn{s16, C, N, ld, (long long)C * ld, F, true, true};
-      e.epi_exp = 1; e.u = lse; e.ldu = N;
-      DCNET_TRY(umma_gemm(Smn, Smn, nullptr, N, N, C, 0, 0, nprob, e, st));
-    } else {
-      // P = exp(tau S - lse) (precision 1) / softmax(tau S) (precision 2 without the forward's staging)
+    if (precision == 2) {
+      // Fused epilogues: no pass over an N x N tensor outside the five contractions.
+      //   E = exp(tau S - lse_fwd) with row sums r        (epilogue of S = Fa^T Fb; lse_fwd is only a shift: P = E / r exactly sums to 1
+      //                                                     in THIS precision, whatever the forward's bf16 logits gave)
+      //   delta = <dO, O>, r <- 1/r                         (one pass over two [C,N] maps)
+      //   dS' = tau (dP - delta) E / r with row sums rho    (epilogue of dP = dO^T Fb, E tile read back from L2 / HBM)
+      //   dOs = (dO - rho Fa) / r, dFa -= rho O             (first-order repair of delta, see coattn_fix_kernel)
+      //   dFb += dOs E ; dFa += Fb dS'^T ; dFb += Fa dS'   (TMA reduce-add; the reduction split over CTAs when a problem has few tiles)
+      char* w = (char*)dP + align256((size_t)chunk * NN * sizeof(float));
+      float* dOs = (float*)w; w += align256((size_t)chunk * CN * sizeof(float));
+      float* rsum = (float*)w; w += align256((size_t)chunk * N * sizeof(float));
+      float* delta = (float*)w; w += align256((size_t)chunk * N * sizeof(float));
+      float* rho = (float*)w;
+      DCNET_CUDA(cudaMemsetAsync(rsum, 0, (size_t)nprob * N * sizeof(float), st), "coattn_bwd.memset");
+      DCNET_CUDA(cudaMemsetAsync(rho, 0, (size_t)nprob * N * sizeof(float), st), "coattn_bwd.memset");
+      e.epi_exp = 1; e.u = lse; e.ldu = N; e.sum = rsum; e.sum_ldz = N;
       DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
-      exp_launch();
-      DCNET_LAUNCH_OK("coattn_bwd.exp");
+      coattn_delta_kernel<<<dim3(ceil_div(N, 128), nprob), dim3(32, 8), 0, st>>>(dout, out, oidx, rsum, delta, C, N);
+      DCNET_LAUNCH_OK("coattn_bwd.delta");
+      e = UmmaEpilogue{}; e.out = dP; e.ldo = N; e.so_b = NN; e.alpha = tau; e.idxA = oidx; e.idxB = kb;
+      e.epi_exp = 2; e.u = delta; e.u2 = rsum; e.ldu = N; e.cc = P; e.ldcc = N; e.cc_sb = NN; e.sum = rho; e.sum_ldz = N;
+      DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+      coattn_fix_kernel<<<dim3(ceil_div(N, 128), nprob), dim3(32, 8), 0, st>>>(dout, out, frames, oidx, qa, rsum, rho, dOs, dframes, C, N);
+      DCNET_LAUNCH_OK("coattn_bwd.fix");
+      UmmaOperand Gsk{dOs, C, N, N, CN, nprob, false};
+      e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxC = kb; e.k_chunks = -1;
+      DCNET_TRY(umma_gemm(Gsk, Pmn, nullptr, C, N, N, 0, 0, nprob, e, st));
+      e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = kb; e.idxC = qa; e.k_chunks = -1;
+      DCNET_TRY(umma_gemm(Fk, dSk, nullptr, C, N, N, 0, 0, nprob, e, st));
+      e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = qa; e.idxC = kb; e.k_chunks = -1;
+      DCNET_TRY(umma_gemm(Fk, dSmn, nullptr, C, N, N, 0, 0, nprob, e, st));
+      continue;
     }
+    // precision 1: P = exp(tau S - lse) with the (tf32) forward's own lse
+    DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    exp_launch();
+    DCNET_LAUNCH_OK("coattn_bwd.exp");
     // dP[i,j] = sum_c dO[c,i] Fb[c,j]
     e = UmmaEpilogue{}; e.out = dP; e.ldo = N; e.so_b = NN; e.alpha = 1.f; e.idxA = oidx; e.idxB = kb;
     DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
     // dFb[c,j] += sum_i dO[c,i] P[i,j]
-    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = oidx; e.idxC = kb;
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = oidx; e.idxC = kb; e.k_chunks = -1;
     DCNET_TRY(umma_gemm(Gk, Pmn, nullptr, C, N, N, 0, 0, nprob, e, st));
     softmax_bwd_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(P, dP, rows, N, N, tau);
     DCNET_LAUNCH_OK("coattn_bwd.softmax");
     // dFa[c,i] += sum_j Fb[c,j] dS[i,j]
-    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = kb; e.idxC = qa;
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = kb; e.idxC = qa; e.k_chunks = -1;
     DCNET_TRY(umma_gemm(Fk, dSk, nullptr, C, N, N, 0, 0, nprob, e, st));
     // dFb[c,j] += sum_i Fa[c,i] dS[i,j]
-    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = qa; e.idxC = kb;
-    return umma_gemm(Fk, dSmn, nullptr, C, N, N, 0, 0, nprob, e, st);
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = qa; e.idxC = kb; e.k_chunks = -1;
+    DCNET_TRY(umma_gemm(Fk, dSmn, nullptr, C, N, N, 0, 0, nprob, e, st));
+    continue;
   }
   // recompute P = exp(tau S - lse)
   DCNET_TRY(sgemm_launch(frames, frames, P, N, N, C, nprob, 1, 1, N, CN, 0, N, 1, CN, 0, N, 1, NN, qa, kb, nullptr, tau, 0.f,
@@ -238,5 +356,6 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
   // dFb[c,j] += sum_i Fa[c,i] dS[i,j]
   DCNET_TRY(sgemm_launch(frames, dP, dframes, C, N, N, nprob, 1, N, 1, CN, 0, N, 1, NN, 0, N, 1, CN, qa, nullptr, kb, 1.f, 0.f,
                          nullptr, 0, 1, st));
+  }   // chunks
   return 0;
 }

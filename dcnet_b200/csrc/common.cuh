@@ -88,7 +88,15 @@ struct UmmaEpilogue {
   float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2; int m_split;
   float alpha; int atomic; const float* u; int ldu; const float* cc; long long ldcc; float* sum; float* sumsq;
   const int* idxA; const int* idxB; const int* idxC;
-  int epi_exp = 0;     // persistent kernel only: v = exp(alpha*acc - u[z*ldu + row])  (P from recomputed logits and the saved lse)
+  // persistent kernel only (co-attention backward, coattn.cu):
+  //   epi_exp = 1: v = exp(alpha*acc - u[z*ldu + row])                                  E = exp(tau S - shift)
+  //   epi_exp = 2: v = alpha * (acc - u[z*ldu + row]) * u2[z*ldu + row] * cc[z*cc_sb + row*ldcc + col]      dS = tau (dP - delta) E / r
+  //   both round v to the nearest tf32 (what the next MMA reads), and `sum` then receives row sums of exactly those values
+  int epi_exp = 0;
+  const float* u2 = nullptr;     // second per-row term (epi_exp = 2)
+  long long cc_sb = 0;           // batch stride of cc (0: cc is shared by the batch, the conv use)
+  long long sum_ldz = 0;         // sum / sumsq are indexed [z*sum_ldz + row] (0: one vector for the whole batch = BatchNorm statistics)
+  int k_chunks = 1;              // reduce-add outputs (atomic = 1) only: split the reduction over this many work items per output tile
 };
 bool umma_gemm_usable(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int K);
 int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int M, int N, int K, int k_split_elems, int n_split,

@@ -12,6 +12,8 @@
 // CTA = one 128 x BN output tile.  Warp roles (192 threads): warps 0-3 epilogue (TMEM -> registers -> global, warp w owns TMEM
 // lanes 32w..32w+31), warp 4 TMA producer (one elected lane), warp 5 TMEM allocator + MMA issuer (one elected lane).
 // A STAGES-deep ring of {A tile, B tile} with full/empty mbarriers decouples TMA from MMA; tcgen05.commit releases a slot.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -34,10 +36,13 @@ static bool g_force_v1 = false;   // tests: run the one-tile-per-CTA kernel with
 // clusters 44.2 us, clusters of 2 44.2 us, clusters of 4 46 us, and the C2 step 1.73 ms vs 1.79 ms -- the kernel is not bound by
 // the L2 -> SM operand traffic that multicast removes, and the cluster lock-step costs a little.  Default: off.
 static int g_cluster_max = 1;
+// 128x256 tf32 tiles as cta_group::2 pairs (256x256 per cluster); dcnet_gemm_select(6) or DCNET_GEMM_PAIR=0 turns it off
+static int g_pair_mode = []() { const char* v = getenv("DCNET_GEMM_PAIR"); return (v && v[0] == '0') ? 0 : 1; }();
 extern "C" int dcnet_gemm_select(int variant) {
   g_force_v1 = (variant == 1);
   g_cluster_max = (variant == 4) ? 4 : ((variant == 3) ? 2 : 1);
   g_gemm_tma_store = (variant == 5) ? 0 : 1;
+  g_pair_mode = (variant == 6) ? 0 : 1;
   return 0;
 }
 
@@ -49,6 +54,9 @@ namespace {
 #endif
 #ifndef GEMM2_STAGES256
 #define GEMM2_STAGES256 4
+#endif
+#ifndef GEMM2_STAGES_PAIR
+#define GEMM2_STAGES_PAIR 6        // 32 KiB per stage and CTA in pair mode
 #endif
 constexpr int BM = 128;
 constexpr int A_BYTES = BM * 128;    // 16 KiB: 128 rows x one 128-byte swizzle row (32 tf32 or 64 bf16 along the reduction)
@@ -231,6 +239,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // slots and TMA (plain store, or fp32 reduce-add for split reductions / shared gradients) instead of per-thread stores whose
 // lanes hit 32 different rows.  Each epilogue warp owns its 32 rows end to end (2 x 4 KiB slots), so no cross-warp barrier.
 // ---------------------------------------------------------------------------------------------------------------------
+// round to nearest tf32 (10 mantissa bits): the MMA reads fp32 operands by TRUNCATION; values rounded here reach it unchanged, so
+// the rounding error is unbiased and half as large, and sums taken in the epilogue are sums of exactly what the next MMA will see
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 struct Gemm2P {
   int M_valid, N_valid, k_iters, k_split, n_split, m_split;
   int a_batched, b_batched, out_batched;
@@ -239,6 +255,8 @@ struct Gemm2P {
   float alpha; int atomic;
   const float* u; int ldu; const float* cc; long long ldcc; float* sum; float* sumsq;
   int epi_exp;
+  const float* u2; long long cc_sb; long long sum_ldz;
+  int k_chunks, k_per;   // split-K (reduce-add outputs): work item = (tile, chunk); chunk c covers k iterations [c*k_per, min(k_iters, (c+1)*k_per))
   int direct_store;    // 1: epilogue leaves through coalesced st.global / red.global.add.v4 instead of TMA store / reduce
   float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2;
   long long* trace;    // optional [CTA][tile slot < 8][8] clock stamps (profiling entry point dcnet_gemm_tf32_trace); nullptr = off
@@ -247,7 +265,11 @@ struct Gemm2P {
 
 // CS = cluster size: CS CTAs with consecutive M tiles of the same (batch, N tile) share the B tile -- each loads 1/CS of it and
 // multicasts (the kernel is bound by the L2 -> SM operand traffic, profiles/r1i_ncu_full_umma_gemm2.txt).
-template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS>
+// TWO: the CTAs of a cluster of 2 form one cta_group::2 pair: one MMA covers 256 (M) x BN, each CTA's TMEM holds its 128 rows, each
+// CTA loads its own A tile and HALF of the B tile (no multicast: the MMA reads both halves), so a 256 x 256 output tile costs
+// (256 + 256) x K operand elements from L2 instead of 2 x (128 + 256) x K -- the tf32 GEMMs here are bound by that traffic
+// (fp32 operands: 4 bytes per element at half the bf16 MMA rate).  The leader CTA (rank 0) issues every MMA.
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapO,
@@ -255,7 +277,8 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   using G = Geo<EB>;
   constexpr int BK = G::BK;
   constexpr int BLK_BYTES = G::BLK_BYTES;
-  constexpr int B_BYTES = BN * 128;
+  static_assert(!TWO || CS == 2, "a CTA pair is a cluster of 2");
+  constexpr int B_BYTES = (TWO ? BN / 2 : BN) * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int SLOT_BYTES = 32 * 128;           // 32 rows x 32 fp32
   constexpr int NSLOT = GEMM2_NSLOT;             // staging slots per epilogue warp (TMA stores in flight per warp)
@@ -275,13 +298,16 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     prefetch_tmap(&mapB);
     prefetch_tmap(&mapB2);
     prefetch_tmap(&mapO);
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CS); }
-    for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    // pair: a slot is released by ONE commit (multicast to both CTAs); the leader's accumulator stage is free once the epilogue
+    // warps of BOTH CTAs have drained their halves
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], TWO ? 1 : CS); }
+    for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TWO ? 8 : 4); }
     fence_barrier_init();
   }
+  if constexpr (TWO) cluster_sync_all();             // both CTAs are resident before the pair-wide TMEM allocation
   if (warp == 5) {
-    tmem_alloc(tmem_slot, 2 * BN);
-    tmem_relinquish();
+    if constexpr (TWO) { tmem_alloc2(tmem_slot, 2 * BN); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -291,7 +317,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   // work item = (batch z, N tile, group of CS consecutive M tiles); the CTAs of a cluster take the M tiles of one group
   const int mgroups = (p.tiles_m + CS - 1) / CS;
   const int per_z = mgroups * p.tiles_n;
-  const int ngroups = per_z * (p.ntiles / (p.tiles_m * p.tiles_n));
+  const int ngroups = per_z * (p.ntiles / (p.tiles_m * p.tiles_n)) * p.k_chunks;
   const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
   const int cid = blockIdx.x / CS, ncl = gridDim.x / CS;
   constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1);
@@ -300,17 +326,42 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (elect_one()) {
       uint32_t itg = 0;
       for (int t = cid; t < ngroups; t += ncl) {
-        const int z = t / per_z, r = t - z * per_z;
+        const int kch = t % p.k_chunks, tt = t / p.k_chunks;
+        const int z = tt / per_z, r = tt - z * per_z;
         const int m0 = ((r / p.tiles_n) * CS + crank) * BM, n0 = (r % p.tiles_n) * BN;
         const int a_b = p.a_batched ? (p.idxA ? p.idxA[z] : z) : 0;
         const int b_b = p.b_batched ? (p.idxB ? p.idxB[z] : z) : 0;
-        for (int it = 0; it < p.k_iters; it++, itg++) {
+        const int it0 = kch * p.k_per, it1 = min(p.k_iters, it0 + p.k_per);
+        for (int it = it0; it < it1; it++, itg++) {
           const int s = itg % STAGES;
           const uint32_t ph = (itg / STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_expect_tx(&full[s], STAGE_BYTES);
           uint8_t* sA = smem + s * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
+          if constexpr (TWO) {
+            // both CTAs' bytes complete on the leader's barrier; only the leader arms it
+            if (crank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+            if constexpr (A_MN) {
+#pragma unroll
+              for (int j = 0; j < BM / G::MN_ELEMS; j++) tma_load_3d_2cta(sA + j * BLK_BYTES, &mapA, &full[s], m0 + G::MN_ELEMS * j, it * BK, a_b);
+            } else {
+              tma_load_3d_2cta(sA, &mapA, &full[s], it * BK, m0, a_b);
+            }
+            if constexpr (B_MN) {
+              const bool src2 = p.k_split > 0 && it >= p.k_split;
+              const CUtensorMap* mb = src2 ? &mapB2 : &mapB;
+              const int kc = (src2 ? it - p.k_split : it) * BK;
+              constexpr int HB = BN / 2 / G::MN_ELEMS;        // MN blocks of this CTA's half of the B tile
+#pragma unroll
+              for (int j = 0; j < HB; j++) tma_load_3d_2cta(sB + j * BLK_BYTES, mb, &full[s], n0 + G::MN_ELEMS * (crank * HB + j), kc, b_b);
+            } else {
+              const bool src2 = p.n_split > 0 && n0 >= p.n_split;
+              const int nrow = src2 ? n0 - p.n_split : n0;
+              tma_load_3d_2cta(sB, src2 ? &mapB2 : &mapB, &full[s], it * BK, nrow + crank * (BN / 2), b_b);
+            }
+            continue;
+          }
+          mbar_expect_tx(&full[s], STAGE_BYTES);
           if constexpr (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / G::MN_ELEMS; j++) tma_load_3d(sA + j * BLK_BYTES, &mapA, &full[s], m0 + G::MN_ELEMS * j, it * BK, a_b);
@@ -344,8 +395,8 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
   } else if (warp == 5) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = instr_desc(G::FMT, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if ((!TWO || crank == 0) && elect_one()) {
+      constexpr uint32_t idesc = instr_desc(G::FMT, TWO ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t itg = 0, tl = 0;
       for (int t = cid; t < ngroups; t += ncl, tl++) {
         const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
@@ -354,7 +405,9 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tc_fence_after();
         GTRACE(tl, 1);
         const uint32_t dcol = tmem_base + as * BN;
-        for (int it = 0; it < p.k_iters; it++, itg++) {
+        const int kc = t % p.k_chunks;
+        const int nit = min(p.k_iters, (kc + 1) * p.k_per) - kc * p.k_per;
+        for (int it = 0; it < nit; it++, itg++) {
           const int s = itg % STAGES;
           const uint32_t ph = (itg / STAGES) & 1u;
           mbar_wait(&full[s], ph);
@@ -367,13 +420,20 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             constexpr uint32_t kadv = G::KSTEP_ROWS * 128;
             const uint64_t ad = A_MN ? smem_desc(sA + ks * kadv, BLK_BYTES, G::MN_SBO, G::MN_LAYOUT) : smem_desc(sA + ks * 32, 16, 1024, 2);
             const uint64_t bd = B_MN ? smem_desc(sB + ks * kadv, BLK_BYTES, G::MN_SBO, G::MN_LAYOUT) : smem_desc(sB + ks * 32, 16, 1024, 2);
-            if constexpr (EB == 4) mma_tf32(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
-            else mma_bf16(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+            if constexpr (TWO) {
+              if constexpr (EB == 4) mma_tf32_2cta(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+              else mma_bf16_2cta(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+            } else {
+              if constexpr (EB == 4) mma_tf32(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+              else mma_bf16(dcol, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+            }
           }
-          if constexpr (CS > 1) mma_commit_mc(&empty[s], cmask);   // the slot is refilled by every CTA of the cluster
+          if constexpr (TWO) mma_commit_2cta(&empty[s], cmask);    // both CTAs' producers refill their part of the slot
+          else if constexpr (CS > 1) mma_commit_mc(&empty[s], cmask);   // the slot is refilled by every CTA of the cluster
           else mma_commit(&empty[s]);
         }
-        mma_commit(&acc_full[as]);
+        if constexpr (TWO) mma_commit_2cta(&acc_full[as], cmask);  // each CTA's epilogue drains its own 128 rows
+        else mma_commit(&acc_full[as]);
         GTRACE(tl, 3);
       }
     }
@@ -382,7 +442,8 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     uint8_t* slots = stage_out + warp * NSLOT * SLOT_BYTES;
     uint32_t tl = 0, chunk = 0;
     for (int t = cid; t < ngroups; t += ncl, tl++) {
-      const int z = t / per_z, r = t - z * per_z;
+      const int kc = t % p.k_chunks, tt = t / p.k_chunks;
+      const int z = tt / per_z, r = tt - z * per_z;
       const int m0 = ((r / p.tiles_n) * CS + crank) * BM, n0 = (r % p.tiles_n) * BN;
       const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
       mbar_wait(&acc_full[as], aph);
@@ -395,7 +456,9 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const bool second = p.m_split > 0 && m0 >= p.m_split;
       const CUtensorMap* mo = second ? &mapO2 : &mapO;
       const int orow0 = second ? row0 - p.m_split : row0;
-      const float bias = (p.u && row_ok) ? p.u[(long long)z * p.ldu + row] : 0.f;
+      // the bias / coordinate terms belong to the whole reduction: with split-K only chunk 0 adds them
+      const float bias = (p.u && row_ok && kc == 0) ? p.u[(long long)z * p.ldu + row] : 0.f;
+      const float rowmul = (p.epi_exp == 2 && row_ok) ? p.alpha * p.u2[(long long)z * p.ldu + row] : 0.f;
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++, chunk++) {
@@ -403,10 +466,26 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + (uint32_t)(c * 32), v);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
-        if (p.epi_exp) {
+        if (p.epi_exp == 1) {
 #pragma unroll
-          for (int e = 0; e < 32; e++) v[e] = __expf(fmaf(p.alpha, v[e], -bias));
-        } else if (p.cc && row_ok && nb < p.N_valid) {
+          for (int e = 0; e < 32; e++) v[e] = tf32_rn(__expf(fmaf(p.alpha, v[e], -bias)));
+        } else if (p.epi_exp == 2) {
+          // dS = tau (dP - delta) E / r : E tile from global (row-contiguous 128 B per thread), per-row delta (bias) and tau / r (rowmul)
+          if (row_ok && nb < p.N_valid) {
+            const float* er = p.cc + (long long)z * p.cc_sb + (long long)row * p.ldcc + nb;
+            if (nb + 32 <= p.N_valid) {
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                const float4 q = *reinterpret_cast<const float4*>(er + 4 * e);
+                v[4 * e] = tf32_rn((v[4 * e] - bias) * rowmul * q.x); v[4 * e + 1] = tf32_rn((v[4 * e + 1] - bias) * rowmul * q.y);
+                v[4 * e + 2] = tf32_rn((v[4 * e + 2] - bias) * rowmul * q.z); v[4 * e + 3] = tf32_rn((v[4 * e + 3] - bias) * rowmul * q.w);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; e++) v[e] = (nb + e < p.N_valid) ? tf32_rn((v[e] - bias) * rowmul * er[e]) : 0.f;
+            }
+          }
+        } else if (p.cc && row_ok && nb < p.N_valid && kc == 0) {
           const float* cr = p.cc + (long long)row * p.ldcc + nb;
           if (nb + 32 <= p.N_valid) {
 #pragma unroll
@@ -489,10 +568,13 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (threadIdx.x == 0) GTRACE(tl, 5);
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_remote(&acc_empty[as], 0);   // the leader's MMA thread waits for both halves
+        else mbar_arrive(&acc_empty[as]);
+      }
       if (p.sum && row_ok) {
-        atomicAdd(p.sum + row, s1);
-        atomicAdd(p.sumsq + row, s2);
+        atomicAdd(p.sum + (long long)z * p.sum_ldz + row, s1);
+        if (p.sumsq) atomicAdd(p.sumsq + (long long)z * p.sum_ldz + row, s2);
       }
     }
     if (lane == 0) tma_store_wait_read();
@@ -500,18 +582,21 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if constexpr (CS > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / arrive on its barriers
-  if (warp == 5) tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 5) {
+    if constexpr (TWO) tmem_dealloc2(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
+  }
 }
 
-template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS>
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO = false>
 int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
                  const Gemm2P& p, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_BYTES + BN * 128) + 4 * GEMM2_NSLOT * 32 * 128 + 1024 + 256;
+  constexpr int smem = STAGES * (A_BYTES + (TWO ? BN / 2 : BN) * 128) + 4 * GEMM2_NSLOT * 32 * 128 + 1024 + 256;
   static_assert(smem <= 232448, "umma_gemm2: shared memory budget");
-  auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB, CS>;
+  auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB, CS, TWO>;
   DCNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "umma_gemm2.attr");
   const int mgroups = (p.tiles_m + CS - 1) / CS;
-  const int ngroups = mgroups * (p.ntiles / p.tiles_m);
+  const int ngroups = mgroups * (p.ntiles / p.tiles_m) * p.k_chunks;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = smem;
@@ -543,6 +628,9 @@ int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap
 template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
 int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
                 const Gemm2P& p, int cs, cudaStream_t st) {
+  if constexpr (BN == 256 && EB == 4) {
+    if (cs == -2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR, EB, 2, true>(ma, mb, mb2, mo, mo2, p, st);
+  }
   if (cs == 4) return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 4>(ma, mb, mb2, mo, mo2, p, st);
   if (cs == 2) return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 2>(ma, mb, mb2, mo, mo2, p, st);
   return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 1>(ma, mb, mb2, mo, mo2, p, st);
@@ -597,7 +685,10 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   // wide tiles cut the L2->SM operand traffic per FLOP (the kernel is L2-bound at 128x128, profiles/r1b_ncu_full_umma_gemm.txt);
   // use them once there are enough 128x256 tiles to fill the 148 SMs
   const long long tiles256 = (long long)ceil_div(N, 256) * ceil_div(M, BM) * batch;
-  const int BN = (N <= 64) ? 64 : ((N >= 256 && tiles256 >= 148) ? 256 : 128);
+  // k_chunks < 0 (auto split-K, reduce-add outputs): the wide tile is kept even when there are fewer than 148 of them -- the
+  // reduction is then split so that every SM still gets work (long-K contractions onto a [C,N] map: 44 tiles per problem at N=2704)
+  const bool auto_split = e.k_chunks < 0 && e.atomic;
+  const int BN = (N <= 64) ? 64 : ((N >= 256 && (tiles256 >= 148 || auto_split)) ? 256 : 128);
   // persistent kernel with TMA-store epilogue whenever the output rows are TMA-addressable
   auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
   const bool out_ok = al16(e.out) && e.ldo % 4 == 0 && e.so_b % 4 == 0 &&
@@ -610,10 +701,14 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     const int nblk = BN / (B.bf16 ? 64 : 32);
     while (cs > 1 && nblk % cs != 0) cs >>= 1;
   }
+  // CTA pairs (cta_group::2) for the wide tf32 tiles: halves the B traffic per output tile
+  const bool pair = out_ok && g_pair_mode && BN == 256 && !A.bf16 && tiles_m >= 2;
+  if (pair) cs = 2;
   CUtensorMap ma, mb, mb2;
   DCNET_TRY(make_operand_map(&ma, A, BM));
   DCNET_TRY(make_operand_map(&mb, B, BN / cs));
   if (B2) DCNET_TRY(make_operand_map(&mb2, *B2, BN / cs)); else mb2 = mb;
+  if (pair) cs = -2;
   GemmP p{};
   p.M_valid = M; p.N_valid = N;
   p.k_iters = (K + BK - 1) / BK;
@@ -625,7 +720,11 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   p.out = e.out; p.ldo = e.ldo; p.so_b = e.so_b; p.out2 = e.out2; p.ldo2 = e.ldo2; p.so_b2 = e.so_b2;
   p.alpha = e.alpha; p.atomic = e.atomic; p.u = e.u; p.ldu = e.ldu; p.cc = e.cc; p.ldcc = e.ldcc; p.sum = e.sum; p.sumsq = e.sumsq;
   const int am = A.mn_major ? 1 : 0, bm = B.mn_major ? 1 : 0;
-  DCNET_CHECK_ARG(!e.epi_exp || (out_ok && e.u && !e.cc && !e.sum && !e.atomic), "umma_gemm: the exp epilogue needs the persistent kernel and a row term");
+  DCNET_CHECK_ARG(e.epi_exp != 1 || (out_ok && e.u && !e.cc && !e.atomic), "umma_gemm: the exp epilogue needs the persistent kernel and a row term");
+  DCNET_CHECK_ARG(e.epi_exp != 2 || (out_ok && e.u && e.u2 && e.cc && !e.atomic), "umma_gemm: the dS epilogue needs the persistent kernel, two row terms and the E tile");
+  DCNET_CHECK_ARG(e.k_chunks <= 1 || (out_ok && e.atomic && !e.sum && !e.epi_exp), "umma_gemm: split-K needs a reduce-add output on the persistent kernel");
+  DCNET_CHECK_ARG(!(B.mn_major && B2) || e.k_chunks == 1 || e.k_chunks == 0, "umma_gemm: split-K with a second K source is not supported");
+  DCNET_CHECK_ARG(out_ok || (e.sum_ldz == 0 && e.cc_sb == 0), "umma_gemm: batched sums / cc need the persistent kernel");
   if (out_ok) {
     Gemm2P q{};
     q.M_valid = M; q.N_valid = N; q.k_iters = p.k_iters; q.k_split = p.k_split; q.n_split = p.n_split; q.m_split = p.m_split;
@@ -633,7 +732,16 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     q.idxA = e.idxA; q.idxB = e.idxB; q.idxC = e.idxC;
     q.tiles_m = ceil_div(M, BM); q.tiles_n = ceil_div(N, BN); q.ntiles = q.tiles_m * q.tiles_n * batch;
     q.alpha = e.alpha; q.atomic = e.atomic; q.u = e.u; q.ldu = e.ldu; q.cc = e.cc; q.ldcc = e.ldcc; q.sum = e.sum; q.sumsq = e.sumsq;
-    q.epi_exp = e.epi_exp;
+    q.epi_exp = e.epi_exp; q.u2 = e.u2; q.cc_sb = e.cc_sb; q.sum_ldz = e.sum_ldz;
+    int want_chunks = e.k_chunks;
+    if (auto_split) {
+      const long long tiles = (long long)q.ntiles;
+      want_chunks = tiles >= 2 * sm_count() ? 1 : (int)((2 * sm_count() + tiles - 1) / tiles);
+      if (want_chunks > q.k_iters / 8) want_chunks = q.k_iters / 8;       // keep >= 8 k-steps (256 tf32 / 512 bf16 reduction elements) per item
+    }
+    q.k_chunks = want_chunks > 1 ? (want_chunks < q.k_iters ? want_chunks : q.k_iters) : 1;
+    q.k_per = (q.k_iters + q.k_chunks - 1) / q.k_chunks;
+    q.k_chunks = (q.k_iters + q.k_per - 1) / q.k_per;        // no empty chunk
     q.trace = g_gemm_trace;
     q.direct_store = g_gemm_tma_store ? 0 : 1;
     q.out = e.out; q.ldo = e.ldo; q.so_b = e.so_b; q.out2 = e.out2; q.ldo2 = e.ldo2; q.so_b2 = e.so_b2;

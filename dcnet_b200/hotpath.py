@@ -31,6 +31,15 @@ def _tensors(o):
             yield from _tensors(v)
 
 
+def all_ordered_pairs(clips, n_frame, device):
+    """BASELINE configs[3]: every ordered pair (i, j), i != j, of the n_frame frames of each clip -> (qa, kb) int32 problem lists
+    for ops.coattention (queries frame qa attend to frame kb).  Generalises model/test_DCNet_model.py:303-332 (centre frame vs
+    the others) to all pairs; frames are numbered clip-major."""
+    qa = [c * n_frame + i for c in range(clips) for i in range(n_frame) for j in range(n_frame) if i != j]
+    kb = [c * n_frame + j for c in range(clips) for i in range(n_frame) for j in range(n_frame) if i != j]
+    return (torch.tensor(qa, device=device, dtype=torch.int32), torch.tensor(kb, device=device, dtype=torch.int32))
+
+
 class _NoBackbone(nn.Module):
     def forward(self, x):
         raise RuntimeError("HotPath has no backbone: feed raw feature maps to step()")
@@ -176,10 +185,11 @@ class HotPath(nn.Module):
         if decode:
             boxes, iou, _, _, _ = LS.decode_boxes(pred, bbox, cell[:3])
         return dict(loss=loss, comp=comp, y=y, iou=iou, boxes=boxes, cell=cell, corr=corr, sim=sim, pred=pred, bbox=bbox,
-                    obj=[o[1] for o in oo_obj], idx_if=idx_if, word=word)
+                    obj=[o[1] for o in oo_obj], idx_if=idx_if, word=word, fv=fv)
 
-    def step(self, raw, flang, fa, context, head, loc, dy_head, bbox, negpos=None, negidx=None):
-        """forward + backward.  Returns a [6+B] tensor: (loss, yolo, rank, loc, interframe, cross, iou[0..B))."""
+    def step(self, raw, flang, fa, context, head, loc, dy_head, bbox, negpos=None, negidx=None, return_internals=False):
+        """forward + backward.  Returns a [6+B] tensor: (loss, yolo, rank, loc, interframe, cross, iou[0..B));
+        with return_internals also the dict of forward_losses (tests: activation patterns, indices)."""
         out = self.forward_losses(raw, flang, fa, context, head, loc, bbox, negpos, negidx, decode=False)
         # train-time decode + IoU (a18, a15) do not feed the backward: they go to an auxiliary stream instead of sitting between
         # the loss and the first backward kernel on the critical path
@@ -196,4 +206,5 @@ class HotPath(nn.Module):
             self._aux_pending = False
             iou.record_stream(cur)
         c = out['comp']
-        return torch.cat([torch.stack([out['loss'], c['yolo'], c['rank'], c['loc'], c['interframe'], c['cross']]).detach(), out['iou']])
+        vec = torch.cat([torch.stack([out['loss'], c['yolo'], c['rank'], c['loc'], c['interframe'], c['cross']]).detach(), out['iou']])
+        return (vec, out) if return_internals else vec

@@ -152,6 +152,8 @@ class grounding_model(nn.Module):
     # ---------------------------------------------------------------------------------------------------------
     @property
     def coattn_precision(self):
+        if getattr(self, "coattn_precision_override", None) is not None:      # experiments / diagnostics
+            return self.coattn_precision_override
         if self.precision == ops.EXACT_FP32:
             return ops.EXACT_FP32
         return ops.TENSOR_BF16_FUSED if self.fused_coattn else self.precision

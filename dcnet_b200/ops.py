@@ -395,6 +395,10 @@ class _CoAttn(torch.autograd.Function):
             torch.zeros(n_out, C, N, device=frames.device, dtype=F32)
         lse = torch.empty(nprob, N, device=frames.device, dtype=F32)
         staged = None
+        ctx.precision = precision
+        if precision == EXACT_FWD_TF32_BWD:
+            precision = EXACT_FP32           # exact fp32 forward (lse included); the backward contractions run as tf32 on tcgen05
+            ctx.precision = TENSOR_TF32
         if precision == TENSOR_BF16_FUSED and C % 128 == 0 and C <= 512:
             # fused kernel: only the bf16 staging of the maps is needed.  Handing it to the backward (dcnet_coattn_bwd's `staged`:
             # P recomputed from the same bf16 operands, exp fused into the GEMM epilogue, no softmax pass) was measured at
@@ -410,7 +414,6 @@ class _CoAttn(torch.autograd.Function):
                       _p(ws), nbytes, _st())
         ctx.save_for_backward(frames, qa, kb, oidx, out, lse)
         ctx.tau = tau
-        ctx.precision = precision
         return out
 
     @staticmethod

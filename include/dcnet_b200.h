@@ -184,6 +184,9 @@ DCNET_API int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const 
                                const float* out, int n_out, const float* lse, const float* dout, float* dframes,
                                int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,
                                void* stream);
+/* The backward keeps its N x N scratch (P, dP -> dS) resident in L2 by working through the problems in chunks whose scratch
+ * fits `bytes` (default 64 MiB of the 126 MB L2; <= 0 = unlimited = one chunk); dcnet_coattn_workspace_bytes follows it. */
+DCNET_API int dcnet_coattn_bwd_l2_budget(long long bytes);
 
 /* ---- a4: inter-frame patch correspondence (model/DCNet_model.py:381-430) ------------------------------
  * fv0 [2P,C,N0].  S0[p] = F1^T F2 in exact fp32; idx[p, r] = flat index (row*N0+col) of the r-th largest

@@ -41,10 +41,12 @@ ANCHORS_FULL = [(373.0, 326.0), (156.0, 198.0), (116.0, 90.0), (59.0, 119.0), (6
 # a1  ConvBatchNormReLU (1x1)                                  model/darknet.py:118-156
 # ----------------------------------------------------------------------------------------------
 def conv1x1_bn_relu(x, weight, gamma, beta, running_mean=None, running_var=None, training=True,
-                    leaky=False, update_running=False):
+                    leaky=False, update_running=False, relu_mask=None):
     """x [B,K,N] (flattened NCHW), weight [C,K].  Train mode: batch statistics over (B,N), biased
     variance for the normalisation; running stats (momentum 0.999, unbiased var) updated in place
-    when update_running.  Returns y [B,C,N]."""
+    when update_running.  Returns y [B,C,N].
+    relu_mask (test aid, bool [B,C,N]): use this activation pattern instead of (y > 0) -- lets a test compare gradients
+    at the SAME ReLU pattern as the implementation under test (the derivative of the function it actually evaluated)."""
     z = torch.einsum('ck,bkn->bcn', weight, x)
     if training:
         mean = z.mean(dim=(0, 2))
@@ -57,6 +59,9 @@ def conv1x1_bn_relu(x, weight, gamma, beta, running_mean=None, running_var=None,
     else:
         mean, var = running_mean, running_var
     y = (z - mean[None, :, None]) / torch.sqrt(var[None, :, None] + BN_EPS) * gamma[None, :, None] + beta[None, :, None]
+    if relu_mask is not None:
+        assert not leaky
+        return y * relu_mask.to(y.dtype)
     return F.leaky_relu(y, 0.1) if leaky else F.relu(y)
 
 
@@ -143,10 +148,11 @@ def interleave_pairs(a1, a2):
 # ----------------------------------------------------------------------------------------------
 # a9  pixel-to-text similarity                                 model/DCNet_model.py:525-535, train_DCNet.py:623-627
 # ----------------------------------------------------------------------------------------------
-def pix2text(corr, flang_attn):
-    """corr [B,C,N], flang_attn [B,C] -> (sim [B,N], neg_sim [B,N]); neg uses the batch-reversed text."""
+def pix2text(corr, flang_attn, fa_partner=None):
+    """corr [B,C,N], flang_attn [B,C] -> (sim [B,N], neg_sim [B,N]); neg uses the batch-reversed text (train_DCNet.py:623-627),
+    or the given partner text vectors [B,C] (global-batch reversal of BASELINE config 5: the partner lives on another rank)."""
     sim = (flang_attn[:, :, None] * corr).sum(1)
-    neg = (flang_attn.flip(0)[:, :, None] * corr).sum(1)
+    neg = ((flang_attn.flip(0) if fa_partner is None else fa_partner)[:, :, None] * corr).sum(1)
     return sim, neg
 
 
@@ -295,14 +301,17 @@ def yolo_loss(pred, gt, gi, gj, best_n, w_coord=5.0):
     return l_box * w_coord + F.cross_entropy(pc, gc.max(1)[1])
 
 
-def rank_loss(sim, neg_sim, gt_center, margin=0.1):
+def rank_loss(sim, neg_sim, gt_center, margin=0.1, gt_center_partner=None):
+    """train_DCNet.py:173-203.  gt_center_partner: dense centre targets of each sample's partner when the partner is not the
+    local reversal B-1-b (cross-GPU negatives: the same formula on the concatenated batch)."""
     B = sim[0].shape[0]
     pos = torch.cat([s.reshape(B, -1) for s in sim], 1)
     neg = torch.cat([s.reshape(B, -1) for s in neg_sim], 1)
     gc = torch.cat([g[:, 4].reshape(B, -1) for g in gt_center], 1)
     p = (pos * gc).sum(-1)
     n1 = (neg * gc).sum(-1)
-    n2 = (pos * gc.flip(0)).sum(-1)
+    gp = gc.flip(0) if gt_center_partner is None else torch.cat([g[:, 4].reshape(B, -1) for g in gt_center_partner], 1)
+    n2 = (pos * gp).sum(-1)
     return (torch.clamp(margin + n1 - p, 0) + torch.clamp(margin + n2 - p, 0)).sum() / (B * 2)
 
 
@@ -428,11 +437,11 @@ def location_branch(net, coords, obj_score, context, embedded, word_id):
 # ----------------------------------------------------------------------------------------------
 # whole forward, restated                                      model/DCNet_model.py:340-650
 # ----------------------------------------------------------------------------------------------
-def _cbr(mod, x, training):
+def _cbr(mod, x, training, relu_mask=None):
     """Apply a reference-style ConvBatchNormReLU module `mod` (has .conv.weight and .bn.*) as a 1x1 op on [B,K,N]."""
     w = mod.conv.weight.reshape(mod.conv.weight.shape[0], -1)
     return conv1x1_bn_relu(x, w, mod.bn.weight, mod.bn.bias, mod.bn.running_mean, mod.bn.running_var,
-                           training=training, update_running=False)
+                           training=training, update_running=False, relu_mask=relu_mask)
 
 
 def forward_restated(net, raw_fvisu, word_id, rng=_pyrandom, topk_fn=None, return_internals=False):
@@ -518,15 +527,21 @@ def losses_restated(out, bbox, size):
 # ----------------------------------------------------------------------------------------------
 # the hot path on its own: neighbours supplied as tensors
 # ----------------------------------------------------------------------------------------------
-def hotpath_restated(net, raw, flang, fa, context, head, loc, dy_head, bbox, size, rng=_pyrandom, backward=True):
+def hotpath_restated(net, raw, flang, fa, context, head, loc, dy_head, bbox, size, rng=_pyrandom, backward=True, relu_masks=None,
+                     fa_partner=None, bbox_partner=None):
     """Mirror of dcnet_b200.hotpath.HotPath.step for the CPU baseline and the parity tests: a2-a18 of
     model/DCNet_model.py:356-637 + train_DCNet.py:615-690 with Darknet / text encoder / head / location branch replaced by
-    the given tensors (head[s] [B,15,N_s], loc[s] [B,N_s], dy_head[s] [B,512,N_s] = gradient entering the fusion output)."""
+    the given tensors (head[s] [B,15,N_s], loc[s] [B,N_s], dy_head[s] [B,512,N_s] = gradient entering the fusion output).
+    relu_masks (test aid): dict(map=3x, corr=3x, fuse=3x bool [B,512,N_s]) pins the ReLU pattern of the three 1x1 layers.
+    fa_partner [B,512] / bbox_partner [B,4]: text vector and box of each sample's rank-loss partner when it is not the local
+    reversal B-1-b -- the slice a rank sees of the reference loss on the concatenated global batch (BASELINE config 5)."""
     training = net.training
+    rm = relu_masks or {}
+    mk = lambda k, s: rm[k][s] if k in rm else None
     B = raw[0].shape[0]
     P = B // 2
     hw = [(m.shape[2], m.shape[3]) for m in raw]
-    fv = [l2norm_channels(_cbr(net.mapping_visu._modules[str(s)], raw[s].flatten(2), training)) for s in range(3)]
+    fv = [l2norm_channels(_cbr(net.mapping_visu._modules[str(s)], raw[s].flatten(2), training, mk('map', s))) for s in range(3)]
     C = fv[0].shape[1]
     f1 = [f.reshape(P, 2, C, -1)[:, 0] for f in fv]
     f2 = [f.reshape(P, 2, C, -1)[:, 1] for f in fv]
@@ -535,14 +550,14 @@ def hotpath_restated(net, raw, flang, fa, context, head, loc, dy_head, bbox, siz
     for s in range(3):
         o1, o2 = coattention(f1[s], f2[s], net.temperature)
         x = interleave_pairs(torch.cat([f1[s], o1], 1), torch.cat([f2[s], o2], 1))
-        c = l2norm_channels(_cbr(net.corr_conv._modules[str(s)][0], x, training))
+        c = l2norm_channels(_cbr(net.corr_conv._modules[str(s)][0], x, training, mk('corr', s)))
         corr.append(c)
-        sm, ng = pix2text(c, fa)
+        sm, ng = pix2text(c, fa, fa_partner)
         sim.append(sm); neg_sim.append(ng)
         N = c.shape[2]
         coord = coord_map(hw[s][0], hw[s][1], device=c.device).flatten(1)
         xin = torch.cat([c, flang[:, :, None].expand(B, C, N), coord[None].expand(B, 8, N)], 1)
-        y.append(_cbr(net.fcn_emb._modules[str(s)][0], xin, training))
+        y.append(_cbr(net.fcn_emb._modules[str(s)][0], xin, training, mk('fuse', s)))
     pred = [modulate_conf(head[s], sim[s], loc[s]) for s in range(3)]
     fm = net.feature_map[0]
     vit, lag, M = crossmodal_features(fv[0], context, fm.weight, fm.bias)
@@ -553,8 +568,12 @@ def hotpath_restated(net, raw, flang, fa, context, head, loc, dy_head, bbox, siz
     g = [size // 32, size // 16, size // 8]
     pred5 = [p.reshape(B, 3, 5, g[s], g[s]) for s, p in enumerate(pred)]
     shp = lambda t, s: t.reshape(B, g[s], g[s])
+    gtc_partner = None
+    if bbox_partner is not None:
+        gtc_partner = [t.to(dev) for t in build_target(bbox_partner.detach().cpu(), size)[4]]
     comp = dict(yolo=yolo_loss(pred5, gt, gi, gj, best_n),
-                rank=rank_loss([shp(t, s) for s, t in enumerate(sim)], [shp(t, s) for s, t in enumerate(neg_sim)], gtc),
+                rank=rank_loss([shp(t, s) for s, t in enumerate(sim)], [shp(t, s) for s, t in enumerate(neg_sim)], gtc,
+                               gt_center_partner=gtc_partner),
                 loc=loc_loss([shp(t, s) for s, t in enumerate(loc)], gtc),
                 interframe=interframe_contrastive_loss(q_if, k_if, neg_if),
                 cross=crossmodal_contrastive_loss(q_cm, k_cm, neg_cm))

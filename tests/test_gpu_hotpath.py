@@ -1,6 +1,7 @@
 """-m gpu: the hot path on its own (what bench.py times) against the CPU oracle: losses, decode, and every gradient that
 leaves the path (to the backbone, the text encoder, the head, the location branch) or lands on a hot-path parameter."""
 import copy
+import os
 import random
 
 import pytest
@@ -144,3 +145,100 @@ def test_hotpath_streams_do_not_change_the_result():
     for x, y in zip(a[1:5], b[1:5]):
         assert rel(x, y) < 1e-2, rel(x, y)
     assert a[5] == b[5]
+
+
+def _grad_errors(c, r, pc, pr):
+    errs = {}
+    for k in ('flang', 'fa', 'context'):
+        errs[k] = rel(c[k].grad, r[k].grad)
+    for k in ('raw', 'head', 'loc'):
+        for s in range(3):
+            errs["%s[%d]" % (k, s)] = rel(c[k][s].grad, r[k][s].grad)
+    for k, v in pr.items():
+        if v.grad is not None:
+            errs[k] = rel(pc[k].grad, v.grad)
+    return errs
+
+
+# bars of the benchmark-shape test (measured values in DESIGN.md section 2)
+TL_BENCH, TG_NOISE, TG_PINNED = 3e-3, 6e-2, 5e-3
+
+
+@pytest.mark.parametrize("size,pairs", [(256, 8), (416, 16)])
+def test_hotpath_step_at_benchmark_shapes_vs_oracle(size, pairs):
+    """BASELINE configs[1] (8 pairs at 256x256) and configs[2] (16 pairs at 416x416) -- the shapes bench.py times -- in the
+    benchmarked mode (tf32 tcgen05 contractions, fused bf16 co-attention forward).  Losses, IoU and every integer output against
+    the CPU oracle; gradients twice: against the oracle as is (bar = the ReLU-pattern noise any reduced-precision forward has,
+    see DESIGN.md section 2), and against the oracle evaluated AT THE PRODUCT'S ReLU PATTERNS, i.e. as the derivative of the
+    function the product actually computed (tight bar: what is left is operand rounding of the tf32 contractions)."""
+    synth.seed_all(13)
+    hp = HotPath(size)
+    g = torch.Generator().manual_seed(900 + size + pairs)
+    batch = synth.make_hotpath_batch(pairs, size, g)
+    cpu = copy.deepcopy(hp.net).train()
+    cpu2 = copy.deepcopy(hp.net).train()
+    hp = hp.to(DEV).train()
+    torch.set_num_threads(os.cpu_count() or 1)
+    r = _leaves(batch, "cpu")
+    random.seed(33)
+    o = O.hotpath_restated(cpu, r['raw'], r['flang'], r['fa'], r['context'], r['head'], r['loc'], r['dy_head'], r['bbox'], size)
+    c = _leaves(batch, DEV)
+    random.seed(33)
+    out, it = hp.step(c['raw'], c['flang'], c['fa'], c['context'], c['head'], c['loc'], c['dy_head'], c['bbox'], return_internals=True)
+    want = torch.stack([o['loss'], o['comp']['yolo'], o['comp']['rank'], o['comp']['loc'], o['comp']['interframe'], o['comp']['cross']])
+    for i in range(6):
+        assert abs(float(out[i]) - float(want[i])) < TL_BENCH * max(1.0, abs(float(want[i]))), (i, float(out[i]), float(want[i]))
+    torch.testing.assert_close(out[6:].cpu(), o['iou'], rtol=TL_BENCH, atol=1e-5)
+    # integer outputs: target cells exact; top-30 flat indices and arg-max words exact except fp32 near-ties (gaps < 1e-6 between
+    # consecutive candidates exist in these maps, SURVEY section 7 "Index parity"): at most 1 % may differ
+    bn, gi, gj = it['cell'][:3]
+    assert torch.equal(bn.cpu(), o['best_n']) and torch.equal(gi.cpu(), o['gi']) and torch.equal(gj.cpu(), o['gj'])
+    assert (it['idx_if'].cpu() == o['idx_if']).float().mean() >= 0.99
+    assert (it['word'].cpu() == o['word']).float().mean() >= 0.99
+    pc, pr = dict(hp.net.named_parameters()), dict(cpu.named_parameters())
+    errs = _grad_errors(c, r, pc, pr)
+    assert len(errs) == 12 + 27
+    bad = {k: e for k, e in errs.items() if e > TG_NOISE}
+    assert not bad, bad
+    # the same comparison at the product's activation patterns
+    masks = dict(map=[(t.detach() > 0).cpu() for t in it['fv']], corr=[(t.detach() > 0).cpu() for t in it['corr']],
+                 fuse=[(t.detach() > 0).cpu() for t in it['y']])
+    r2 = _leaves(batch, "cpu")
+    random.seed(33)
+    O.hotpath_restated(cpu2, r2['raw'], r2['flang'], r2['fa'], r2['context'], r2['head'], r2['loc'], r2['dy_head'], r2['bbox'], size,
+                       relu_masks=masks)
+    errs2 = _grad_errors(c, r2, pc, dict(cpu2.named_parameters()))
+    print("benchmark shape %dx%d, %d pairs: worst gradient error %.2e as is, %.2e at the product's ReLU patterns" % (
+        size, size, pairs, max(errs.values()), max(errs2.values())))
+    bad = {k: e for k, e in errs2.items() if e > TG_PINNED}
+    assert not bad, bad
+
+
+def test_c4_all_ordered_pairs_vs_oracle_loop():
+    """BASELINE configs[3] (what bench.py --workload c4 times): visual mapping of every frame once, then one co-attention problem
+    per ordered frame pair of each clip and scale, against a plain loop of the oracle's co-attention block."""
+    from dcnet_b200 import ops
+    from dcnet_b200.hotpath import all_ordered_pairs
+    clips, nf, size = 2, 8, 256
+    F_ = clips * nf
+    synth.seed_all(13)
+    hp = HotPath(size)
+    g = torch.Generator().manual_seed(44)
+    for m in hp.net.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.normal_(0, 0.1, generator=g); m.running_var.uniform_(0.5, 1.5, generator=g)
+    maps = synth.make_raw_fvisu(F_ // 2, size, g)
+    cpu = copy.deepcopy(hp.net).eval()
+    hp = hp.to(DEV).eval()
+    qa, kb = all_ordered_pairs(clips, nf, DEV)
+    assert qa.numel() == clips * nf * (nf - 1)
+    with torch.no_grad():
+        fv = hp.net.map_visual([m.to(DEV) for m in maps])
+        outs = [ops.coattention(fv[s], qa, kb, tau=10.0, precision=hp.net.coattn_precision) for s in range(3)]
+        for s in range(3):
+            f = O.l2norm_channels(O._cbr(cpu.mapping_visu._modules[str(s)], maps[s].flatten(2), False))
+            worst = 0.0
+            for p_, (i, j) in enumerate(zip(qa.tolist(), kb.tolist())):
+                o1, _ = O.coattention(f[i][None], f[j][None], 10.0)          # queries of frame i attend to frame j
+                worst = max(worst, rel(outs[s][p_], o1[0]))
+            assert worst < 1e-3, (s, worst)
