@@ -577,7 +577,8 @@ def measure_hotpath(key, steps, warmup, rank, world, local, dev, dist, xneg=Fals
 # ----------------------------------------------------------------------------------------------------------------------
 # DRAM traffic per launch of the two tensor-core kernels, from `ncu --set full` captures of the same instances
 # (dram__bytes_read.sum + dram__bytes_write.sum); (size, pairs) -> (bytes, source file)
-NCU_TRAFFIC_GEMM = {(256, 8): (88.2e6, "profiles/r1w_ncu_full_umma_gemm2.txt")}
+NCU_TRAFFIC_GEMM = {}
+NCU_TRAFFIC_GEMM_S = {(256, 8): (88.2e6, "profiles/r1w_ncu_full_umma_gemm2.txt")}
 NCU_TRAFFIC_COATTN = {(256, 8): (16.9e6, "profiles/r1w_ncu_full_coattn_fused.txt")}
 
 
@@ -606,23 +607,35 @@ def kernel_rooflines(key, dev):
 
     NSET = 5 if size <= 256 else 3
     frs = [torch.nn.functional.normalize(torch.randn(B, C_EMB, N2, device=dev).abs(), dim=1) for _ in range(NSET)]
-    # the dominant kernel family of the step is the persistent tcgen05 GEMM; its most frequent large instance is S = Fa^T Fb of the
-    # co-attention backward at the finest scale (M = N = N2, K = 512), launched per L2-resident chunk of problems
-    nchunk = max(1, min(B, (64 << 20) // (2 * N2 * N2 * 4)))
-    c_bufs = [torch.empty(nchunk, N2, N2, device=dev) for _ in range(NSET)]
-    set_bytes_g = 2 * nchunk * C_EMB * N2 * 4 + c_bufs[0].numel() * 4
-    ms_g = timed_sets([(lambda i=i: ops.gemm_tf32(frs[i][:nchunk], frs[(i + 1) % NSET][:nchunk], 1, 1, N2, N2, C_EMB, out=c_bufs[i])) for i in range(NSET)])
-    fl_g = 2.0 * N2 * N2 * C_EMB * nchunk
+    # The dominant kernel family of the step is the persistent tcgen05 tf32 GEMM (cta_group::2 pairs, 256x256 per cluster).  Its two
+    # large instance types at the finest scale, each timed alone on all problems of the batch (= how the step launches them):
+    #   roofline        : a [C,N]-output contraction of the co-attention backward (dFa += Fb dS^T: M=512, N=K=N2), three per scale --
+    #                     the largest share of the step
+    #   roofline_gemm_s : S = Fa^T Fb (M=N=N2, K=512) with the exp / row-sum epilogue's plain sibling, two per scale (S and dP)
+    nprob = B
+    c_bufs = [torch.empty(nprob, N2, N2, device=dev) for _ in range(NSET)]
+    set_bytes_g = 2 * nprob * C_EMB * N2 * 4 + c_bufs[0].numel() * 4
+    ms_s = timed_sets([(lambda i=i: ops.gemm_tf32(frs[i], frs[(i + 1) % NSET], 1, 1, N2, N2, C_EMB, out=c_bufs[i])) for i in range(NSET)])
+    fl_s = 2.0 * N2 * N2 * C_EMB * nprob
+    ach_s = fl_s / (ms_s * 1e-3) / 1e12
+    d_bufs = [torch.zeros(nprob, C_EMB, N2, device=dev) for _ in range(NSET)]
+    ms_g = timed_sets([(lambda i=i: ops.gemm_tf32(frs[i], c_bufs[i], 0, 0, C_EMB, N2, N2, out=d_bufs[i], atomic=1)) for i in range(NSET)])
+    fl_g = 2.0 * C_EMB * N2 * N2 * nprob
     ach_g = fl_g / (ms_g * 1e-3) / 1e12
     tr = NCU_TRAFFIC_GEMM.get((size, pairs))
-    roof = dict(bound="tensor", kernel="umma_gemm2_kernel (tcgen05 kind::tf32, persistent; S = Fa^T Fb of the co-attention backward, "
-                "M=N=%d K=%d, %d problems, one launch)" % (N2, C_EMB, nchunk), achieved=ach_g, peak=peaks["tensor_burst"], unit="TFLOP/s",
-                frac=ach_g / peaks["tensor_burst"], traffic=tr[0] if tr else None,
-                traffic_source=(tr[1] + ": dram__bytes_read.sum + dram__bytes_write.sum") if tr else None, ms=ms_g,
-                dtype="tf32 operands (fp32 in HBM), fp32 accumulate", frac_of_tf32_pipe=2.0 * ach_g / peaks["tensor_burst"],
-                l2="operands and outputs rotate over %d sets, %.0f MB in total (> 126 MB L2)" % (NSET, NSET * set_bytes_g / 1e6),
-                note="peak is the measured bf16 figure; the tf32 tensor pipe is nominally half of it (frac_of_tf32_pipe)",
-                peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
+    common = dict(bound="tensor", peak=peaks["tensor_burst"], unit="TFLOP/s", dtype="tf32 operands (fp32 in HBM), fp32 accumulate",
+                  l2="operands and outputs rotate over %d sets, %.0f MB in total (> 126 MB L2)" % (NSET, NSET * set_bytes_g / 1e6),
+                  note="peak is the measured bf16 figure; the tf32 tensor pipe is nominally half of it (frac_of_tf32_pipe)",
+                  peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
+    roof = dict(kernel="umma_gemm2_kernel (tcgen05 kind::tf32, cta_group::2 pairs, persistent, TMA reduce-add epilogue; dFa += Fb dS^T of the "
+                "co-attention backward, M=%d N=K=%d, %d problems, one launch)" % (C_EMB, N2, nprob), achieved=ach_g, frac=ach_g / peaks["tensor_burst"],
+                frac_of_tf32_pipe=2.0 * ach_g / peaks["tensor_burst"], ms=ms_g, traffic=tr[0] if tr else None,
+                traffic_source=(tr[1] + ": dram__bytes_read.sum + dram__bytes_write.sum") if tr else None, **common)
+    tr = NCU_TRAFFIC_GEMM_S.get((size, pairs))
+    roof_s = dict(kernel="umma_gemm2_kernel (same kernel; S = Fa^T Fb of the co-attention backward, M=N=%d K=%d, %d problems, one launch)" % (N2, C_EMB, nprob),
+                  achieved=ach_s, frac=ach_s / peaks["tensor_burst"], frac_of_tf32_pipe=2.0 * ach_s / peaks["tensor_burst"], ms=ms_s,
+                  traffic=tr[0] if tr else None, traffic_source=(tr[1] + ": dram__bytes_read.sum + dram__bytes_write.sum") if tr else None, **common)
+    del d_bufs
     del c_bufs
     qa = torch.arange(B, device=dev, dtype=torch.int32)
     kb = qa ^ 1
@@ -681,7 +694,7 @@ def kernel_rooflines(key, dev):
     del frs, ys, dvs, yin
     gc.collect()
     torch.cuda.empty_cache()
-    return roof, roof_co, roof_hbm
+    return roof, roof_s, roof_co, roof_hbm
 
 
 def step_flops(key):
@@ -764,10 +777,10 @@ def main():
                                                                      h2d_bytes_per_step=e["e2e"]["h2d_bytes_per_step"]),
                                               grad_allreduce=e["grad_allreduce"], cross_gpu_negatives=e["cross_gpu_negatives"])
 
-    roof = roof_co = roof_hbm = cpu_base = gpu_base = None
+    roof = roof_s = roof_co = roof_hbm = cpu_base = gpu_base = None
     if rank == 0:
         if not args.no_rooflines:
-            roof, roof_co, roof_hbm = kernel_rooflines(key, dev)
+            roof, roof_s, roof_co, roof_hbm = kernel_rooflines(key, dev)
         if world == 1 and not args.no_cpu_baseline:
             gpu_base = pytorch_gpu_baseline(key, dev)
             cpu_base = cpu_baseline(key)
@@ -783,7 +796,7 @@ def main():
                                  step_gemm_tflops=step_tf, step_gemm_frac_of_sustained=step_tf / peaks["tensor_sustained"]),
                     clocks=m["clocks"], e2e=m["e2e"],
                     gpu_launches=int(m["launches_per_step"] * args.steps), gpu_launches_per_step=m["launches_per_step"],
-                    roofline=roof, roofline_coattn=roof_co, roofline_hbm=roof_hbm, cpu_baseline=cpu_base, pytorch_gpu_baseline=gpu_base,
+                    roofline=roof, roofline_gemm_s=roof_s, roofline_coattn=roof_co, roofline_hbm=roof_hbm, cpu_baseline=cpu_base, pytorch_gpu_baseline=gpu_base,
                     extra=extra or None)
         print(json.dumps(line), flush=True)
     if world > 1:

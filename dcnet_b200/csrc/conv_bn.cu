@@ -416,6 +416,60 @@ __global__ void pix2text_kernel(const float* __restrict__ x, const float* __rest
   if (neg) neg[(long long)b * N + n] = d;
 }
 
+// u[b,c] = sum_k W[c, col_l + k] flang[b,k]: one warp per output channel keeps its weight row in registers (KT = Ct/32 values per lane)
+// and walks the batch; flang (B x Ct floats) is read through L1/L2 by every warp.  A [B,C] result with B ~ 32: a GEMM tile grid would
+// be 8 CTAs deep in a 512-long reduction (measured 50-75 us for the SIMT GEMM against a few us here).
+template <int KT>
+__global__ void __launch_bounds__(256) text_term_kernel(const float* __restrict__ W, int ldw, const float* __restrict__ flang,
+                                                        float* __restrict__ u, int B, int C) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  float w[KT];
+#pragma unroll
+  for (int i = 0; i < KT; i++) w[i] = W[(long long)c * ldw + lane + 32 * i];
+  for (int b = 0; b < B; b++) {
+    const float* f = flang + (long long)b * (32 * KT) + lane;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < KT; i++) acc = fmaf(w[i], f[32 * i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) u[(long long)b * C + c] = acc;
+  }
+}
+
+// dflang[b,k] = sum_c du[b,c] W[c, col_l + k]: one thread per (b,k), coalesced along k, du[b,:] broadcast
+__global__ void __launch_bounds__(256) text_grad_kernel(const float* __restrict__ W, int ldw, const float* __restrict__ du,
+                                                        float* __restrict__ dflang, int C, int Ct) {
+  const int k = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (k >= Ct) return;
+  const float* d = du + (long long)b * C;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int c = 0; c < C; c++) acc = fmaf(d[c], W[(long long)c * ldw + k], acc);
+  dflang[(long long)b * Ct + k] = acc;
+}
+
+// dWc[c,j] = sum_n dcc[c,n] coord[j,n], j < 8: one warp per channel row, coalesced along n (a [512,8] result over a long reduction:
+// a GEMM tile would leave all but 8 CTAs idle)
+__global__ void __launch_bounds__(256) coord_wgrad_kernel(const float* __restrict__ dcc, const float* __restrict__ coord, float* __restrict__ dW,
+                                                          int ldw, int C, int N) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int n = lane; n < N; n += 32) {
+    const float d = dcc[(long long)c * N + n];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = fmaf(d, coord[(long long)j * N + n], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const float v = warp_sum(acc[j]);
+    if (lane == 0) dW[(long long)c * ldw + j] = v;
+  }
+}
+
 __global__ void coord_map_kernel(float* __restrict__ coord, int h, int w) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
@@ -534,6 +588,52 @@ extern "C" int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1
   if (dcc) {
     batchsum_kernel<<<ew_grid((long long)C * N), 256, 0, st>>>(dz, dcc, B, (long long)C * N);
     DCNET_LAUNCH_OK("conv1x1_bwd_weight.dcc");
+  }
+  return 0;
+}
+
+// a8, the text and coordinate terms of the split-weight fusion (model/DCNet_model.py:489-505 concatenates
+// [corr_feat | flang tiled over h x w | coord] before the fusing 1x1 conv): with W = [W_v | W_l | W_c],
+//   u[b,c]  = sum_k W_l[c,k] flang[b,k]      (a [B,C] bias per image instead of a [B,512,h,w] tile)
+//   cc[c,n] = sum_j W_c[c,j] coord[j,n]      (a [C,N] map shared by the batch instead of a [B,8,h,w] tensor)
+// W_l = W[:, col_l : col_l+Ct], W_c = W[:, col_c : col_c+8] inside the [C, ldw] weight.  Exact fp32 (CUDA cores): the products are tiny.
+extern "C" int dcnet_fuse_terms_fwd(const float* W, int ldw, int col_l, int Ct, int col_c, const float* flang, const float* coord,
+                                    float* u, float* cc, int B, int C, int N, void* stream) {
+  DCNET_CHECK_ARG(W && flang && u && B > 0 && C > 0 && Ct > 0 && col_l >= 0 && col_l + Ct <= ldw, "fuse_terms_fwd: bad arguments");
+  DCNET_CHECK_ARG((coord != nullptr) == (cc != nullptr) && (!coord || (N > 0 && col_c >= 0 && col_c + 8 <= ldw)), "fuse_terms_fwd: coord/cc inconsistent");
+  cudaStream_t st = as_stream(stream);
+  if (Ct == 512) {
+    text_term_kernel<16><<<ceil_div(C, 8), 256, 0, st>>>(W + col_l, ldw, flang, u, B, C);
+    DCNET_LAUNCH_OK("fuse_terms_fwd.text");
+  } else {
+    DCNET_TRY(sgemm_launch(flang, W + col_l, u, B, C, Ct, 1, 1, Ct, 1, 0, 0, 1, ldw, 0, 0, C, 1, 0, nullptr, nullptr, nullptr, 1.f, 0.f,
+                           nullptr, 0, 0, st));
+  }
+  if (coord)
+    DCNET_TRY(sgemm_launch(W + col_c, coord, cc, C, N, 8, 1, 1, ldw, 1, 0, 0, N, 1, 0, 0, N, 1, 0, nullptr, nullptr, nullptr, 1.f, 0.f,
+                           nullptr, 0, 0, st));
+  return 0;
+}
+
+// backward of the above from du [B,C] (= sum_n dz) and dcc [C,N] (= sum_b dz): dflang [B,Ct] (or NULL), and the text / coordinate
+// columns of dW [C,ldw] (overwritten; dW NULL = no weight gradient).
+extern "C" int dcnet_fuse_terms_bwd(const float* W, int ldw, int col_l, int Ct, int col_c, const float* flang, const float* coord,
+                                    const float* du, const float* dcc, float* dflang, float* dW, int B, int C, int N, void* stream) {
+  DCNET_CHECK_ARG(W && flang && du && B > 0 && C > 0 && Ct > 0 && col_l >= 0 && col_l + Ct <= ldw, "fuse_terms_bwd: bad arguments");
+  DCNET_CHECK_ARG((coord != nullptr) == (dcc != nullptr) && (!coord || (N > 0 && col_c >= 0 && col_c + 8 <= ldw)), "fuse_terms_bwd: coord/dcc inconsistent");
+  cudaStream_t st = as_stream(stream);
+  if (dflang) {
+    DCNET_CHECK_ARG(B <= 65535, "fuse_terms_bwd: B too large");
+    text_grad_kernel<<<dim3(ceil_div(Ct, 256), B), 256, 0, st>>>(W + col_l, ldw, du, dflang, C, Ct);
+    DCNET_LAUNCH_OK("fuse_terms_bwd.text");
+  }
+  if (dW) {
+    DCNET_TRY(sgemm_launch(du, flang, dW + col_l, C, Ct, B, 1, 1, 1, C, 0, 0, Ct, 1, 0, 0, ldw, 1, 0, nullptr, nullptr, nullptr, 1.f, 0.f,
+                           nullptr, 0, 0, st));
+    if (coord) {
+      coord_wgrad_kernel<<<ceil_div(C, 8), 256, 0, st>>>(dcc, coord, dW + col_c, ldw, C, N);
+      DCNET_LAUNCH_OK("fuse_terms_bwd.coord");
+    }
   }
   return 0;
 }

@@ -341,6 +341,163 @@ __global__ void __launch_bounds__(256) decode_kernel(Ptr3 pred, int B, int g0, A
     iou[b] = iou_xyxy(bx1, by1, bx2, by2, target[b * 4 + 0], target[b * 4 + 1], target[b * 4 + 2], target[b * 4 + 3]);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// 8f-3: test-time cache writer (test_DCNet.py:546-654, get_topk_pred_bbox :657-701) -- per image the top-k confidence
+// cells over all scales / anchors, their decoded boxes mapped back to the un-letterboxed image, and the 512-d
+// correspondence feature of each cell.  One CTA per image.
+//   ranking : torch.topk over the concatenated [3 N0 | 3 N1 | 3 N2] confidences (order anchor, gj, gi inside a scale); ties go to
+//             the lower flat index.
+//   cell    : the reference takes the SCALE from the flat index and then searches that scale for the FIRST cell whose confidence
+//             equals the value (np.where(pred_conf == max_conf)[0], :682) -- with duplicated values both ranks report the first
+//             cell; reproduced.
+//   box     : (sigmoid(tx)+gi, sigmoid(ty)+gj, exp(tw) aw, exp(th) ah) * stride -> xyxy -> ((x - dw)/ratio, (y - dh)/ratio)
+//             -> x1,y1 >= 0, x2 <= img_w, y2 <= img_h (:693-696)
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) topk_boxes_kernel(Ptr3 pred, Ptr3 feat, int B, int g0, int C, int k, Anchors9 an,
+                                                         const float* __restrict__ meta /* [B,5]: ratio, dw, dh, img_w, img_h */,
+                                                         float* __restrict__ boxes, float* __restrict__ scores, long long* __restrict__ cells,
+                                                         float* __restrict__ feats) {
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  __shared__ float s_bv;
+  __shared__ int s_bi, s_first;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int n0 = 3 * g0 * g0, n1 = 12 * g0 * g0;
+  float pv = INFINITY;     // previously selected (value, flat index): the next one is the largest element strictly after it
+  int pi = -1;
+  for (int r = 0; r < k; r++) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff, off = 0;
+    for (int sc = 0; sc < 3; sc++) {
+      const int g = g0 << sc, N = g * g;
+      const float* p = pred.p[sc] + (long long)b * 15 * N;
+      for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) {
+        const float v = p[(long long)(5 * (i / N) + 4) * N + i % N];
+        const int fi = off + i;
+        const bool after = v < pv || (v == pv && fi > pi);
+        if (after && (v > bv || (v == bv && fi < bi))) { bv = v; bi = fi; }
+      }
+      off += 3 * N;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_v[w] = bv; s_i[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+      bv = lane < nw ? s_v[lane] : -INFINITY;
+      bi = lane < nw ? s_i[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { s_bv = bv; s_bi = bi; s_first = 0x7fffffff; }
+    }
+    __syncthreads();
+    pv = s_bv; pi = s_bi;
+    const int s = pi < n0 ? 0 : (pi < n0 + n1 ? 1 : 2);
+    const int g = g0 << s, N = g * g;
+    // first cell of that scale holding the same confidence
+    {
+      const float* p = pred.p[s] + (long long)b * 15 * N;
+      int first = 0x7fffffff;
+      for (int i = threadIdx.x; i < 3 * N; i += blockDim.x)
+        if (p[(long long)(5 * (i / N) + 4) * N + i % N] == pv) { first = i; break; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+      if (lane == 0 && first != 0x7fffffff) atomicMin(&s_first, first);
+    }
+    __syncthreads();
+    const int fi = s_first;
+    const int a = fi / N, gj = (fi % N) / g, gi = fi % g;
+    const long long o = (long long)b * k + r;
+    // the cell's feature column
+    const float* f = feat.p[s] + (long long)b * C * N + gj * g + gi;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) feats[o * C + c] = f[(long long)c * N];
+    if (threadIdx.x == 0) {
+      const float stride = (float)(32 >> s);
+      const float* p = pred.p[s] + ((long long)b * 15 + 5 * a) * N + gj * g + gi;
+      const float x = __fmul_rn(__fadd_rn(sigmoidf_(p[0]), (float)gi), stride);
+      const float y = __fmul_rn(__fadd_rn(sigmoidf_(p[(long long)N]), (float)gj), stride);
+      const float bw = __fmul_rn(__fmul_rn(expf(p[2LL * N]), an.w[3 * s + a]), stride);
+      const float bh = __fmul_rn(__fmul_rn(expf(p[3LL * N]), an.h[3 * s + a]), stride);
+      const float ratio = meta[b * 5 + 0], dw = meta[b * 5 + 1], dh = meta[b * 5 + 2], iw = meta[b * 5 + 3], ih = meta[b * 5 + 4];
+      float x1 = __fdiv_rn(__fsub_rn(__fsub_rn(x, __fdiv_rn(bw, 2.f)), dw), ratio), y1 = __fdiv_rn(__fsub_rn(__fsub_rn(y, __fdiv_rn(bh, 2.f)), dh), ratio);
+      float x2 = __fdiv_rn(__fsub_rn(__fadd_rn(x, __fdiv_rn(bw, 2.f)), dw), ratio), y2 = __fdiv_rn(__fsub_rn(__fadd_rn(y, __fdiv_rn(bh, 2.f)), dh), ratio);
+      boxes[o * 4 + 0] = fmaxf(x1, 0.f); boxes[o * 4 + 1] = fmaxf(y1, 0.f);
+      boxes[o * 4 + 2] = fminf(x2, iw); boxes[o * 4 + 3] = fminf(y2, ih);
+      scores[o] = pv;
+      cells[o * 4 + 0] = s; cells[o * 4 + 1] = a; cells[o * 4 + 2] = gj; cells[o * 4 + 3] = gi;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 8f-3: post_processing.py:205-270 -- re-scoring of the centre frame's top-k boxes against the cached top-k of R reference
+// frames: sim[i,j,r] = <centre_i, ref_{j,r}>; per (i,r) the best matching reference box (first maximum over j) and its
+// score; weights = softmax_r(max sim) with invalid frames zeroed AFTER the softmax (:265-268); fused[i] = sum_r w score;
+// best = first arg-max of fused.  One CTA; k, R <= 16.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) post_rescore_kernel(const float* __restrict__ centre /* [k,C] */, const float* __restrict__ ref /* [k,R,C] */,
+                                                           const float* __restrict__ ref_score /* [k,R] */, const int* __restrict__ invalid /* [R] or null */,
+                                                           int k, int R, int C, float* __restrict__ fused, long long* __restrict__ best,
+                                                           long long* __restrict__ match /* [k,R] or null */) {
+  __shared__ float s_sim[16 * 16 * 16];
+  __shared__ float s_w[16 * 16], s_sc[16 * 16], s_f[16];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int t = w; t < k * k * R; t += nw) {            // t = (i, j, r): one warp per dot product
+    const int i = t / (k * R), j = (t / R) % k, r = t % R;
+    const float* a = centre + (long long)i * C;
+    const float* b = ref + ((long long)j * R + r) * C;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(a[c], b[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s_sim[t] = acc;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < k * R; t += blockDim.x) {
+    const int i = t / R, r = t % R;
+    float bv = -INFINITY;
+    int bj = 0;
+    for (int j = 0; j < k; j++) {
+      const float v = s_sim[(i * k + j) * R + r];
+      if (v > bv) { bv = v; bj = j; }
+    }
+    s_w[t] = bv;
+    s_sc[t] = ref_score[bj * R + r];
+    if (match) match[t] = bj;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < k) {
+    const int i = threadIdx.x;
+    float m = -INFINITY;
+    for (int r = 0; r < R; r++) m = fmaxf(m, s_w[i * R + r]);
+    float z = 0.f;
+    for (int r = 0; r < R; r++) z += expf(s_w[i * R + r] - m);
+    float f = 0.f;
+    for (int r = 0; r < R; r++) {
+      const float wgt = (invalid && invalid[r]) ? 0.f : expf(s_w[i * R + r] - m) / z;
+      f = fmaf(wgt, s_sc[i * R + r], f);
+    }
+    s_f[i] = f;
+    fused[i] = f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bi = 0;
+    for (int i = 1; i < k; i++)
+      if (s_f[i] > s_f[bi]) bi = i;
+    *best = bi;
+  }
+}
+
 __global__ void bbox_iou_kernel(const float* __restrict__ b1, const float* __restrict__ b2, int n, int xyxy, float* __restrict__ iou) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -558,6 +715,28 @@ extern "C" int dcnet_decode(const float* pred0, const float* pred1, const float*
   const Anchors9 an = scale_anchors9(h_anchors9x2, size, anchor_imsize);
   decode_kernel<<<B, 256, 0, as_stream(stream)>>>(Ptr3{{pred0, pred1, pred2}}, B, g0, an, mode, best_n, gi, gj, boxes, target, iou);
   DCNET_LAUNCH_OK("decode");
+  return 0;
+}
+
+extern "C" int dcnet_topk_boxes(const float* pred0, const float* pred1, const float* pred2,
+                                const float* feat0, const float* feat1, const float* feat2, int B, int g0, int size, int C, int k,
+                                float anchor_imsize, const float* h_anchors9x2, const float* meta,
+                                float* boxes, float* scores, long long* cells, float* feats, void* stream) {
+  DCNET_CHECK_ARG(pred0 && pred1 && pred2 && feat0 && feat1 && feat2 && h_anchors9x2 && meta && boxes && scores && cells && feats,
+                  "topk_boxes: null argument");
+  DCNET_CHECK_ARG(B > 0 && B <= 65535 && C > 0 && g0 == size / 32 && k >= 1 && k <= 63 * g0 * g0, "topk_boxes: bad sizes (k <= 3 sum N)");
+  const Anchors9 an = scale_anchors9(h_anchors9x2, size, anchor_imsize);
+  topk_boxes_kernel<<<B, 256, 0, as_stream(stream)>>>(Ptr3{{pred0, pred1, pred2}}, Ptr3{{feat0, feat1, feat2}}, B, g0, C, k, an, meta, boxes,
+                                                      scores, cells, feats);
+  DCNET_LAUNCH_OK("topk_boxes");
+  return 0;
+}
+
+extern "C" int dcnet_post_rescore(const float* centre, const float* ref, const float* ref_score, const int* invalid, int k, int R, int C,
+                                  float* fused, long long* best, long long* match, void* stream) {
+  DCNET_CHECK_ARG(centre && ref && ref_score && fused && best && k >= 1 && k <= 16 && R >= 1 && R <= 16 && C > 0, "post_rescore: bad arguments (k, R <= 16)");
+  post_rescore_kernel<<<1, 256, 0, as_stream(stream)>>>(centre, ref, ref_score, invalid, k, R, C, fused, best, match);
+  DCNET_LAUNCH_OK("post_rescore");
   return 0;
 }
 

@@ -446,9 +446,6 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int z = tt / per_z, r = tt - z * per_z;
       const int m0 = ((r / p.tiles_n) * CS + crank) * BM, n0 = (r % p.tiles_n) * BN;
       const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
-      mbar_wait(&acc_full[as], aph);
-      tc_fence_after();
-      if (threadIdx.x == 0) GTRACE(tl, 4);
       const int row0 = m0 + warp * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M_valid;
@@ -460,8 +457,26 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const float bias = (p.u && row_ok && kc == 0) ? p.u[(long long)z * p.ldu + row] : 0.f;
       const float rowmul = (p.epi_exp == 2 && row_ok) ? p.alpha * p.u2[(long long)z * p.ldu + row] : 0.f;
       float s1 = 0.f, s2 = 0.f;
+      // dS epilogue: the E chunk of a thread's row (128 contiguous bytes) is fetched ONE CHUNK AHEAD -- the first one before the
+      // accumulator is even complete -- so its L2 / HBM latency hides under the TMEM load, the arithmetic and the store of the
+      // previous chunk (profiles/r2i: with the load inside the chunk this GEMM took 824 us against 525 us for its exp sibling)
+      float4 ecur[8];
+      const float* erow = (p.epi_exp == 2 && row_ok) ? p.cc + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
+      auto load_e = [&](int c, float4 (&dst)[8]) {
+        const int nb_ = n0 + c * 32;
+        if (erow && nb_ + 32 <= p.N_valid) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) dst[e] = __ldg(reinterpret_cast<const float4*>(erow + nb_ + 4 * e));
+        }
+      };
+      if (p.epi_exp == 2) load_e(0, ecur);
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
+      if (threadIdx.x == 0) GTRACE(tl, 4);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++, chunk++) {
+        float4 enext[8];
+        if (p.epi_exp == 2 && c + 1 < BN / 32) load_e(c + 1, enext);
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + (uint32_t)(c * 32), v);
         tmem_ld_wait();
@@ -472,19 +487,21 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         } else if (p.epi_exp == 2) {
           // dS = tau (dP - delta) E / r : E tile from global (row-contiguous 128 B per thread), per-row delta (bias) and tau / r (rowmul)
           if (row_ok && nb < p.N_valid) {
-            const float* er = p.cc + (long long)z * p.cc_sb + (long long)row * p.ldcc + nb;
             if (nb + 32 <= p.N_valid) {
 #pragma unroll
               for (int e = 0; e < 8; e++) {
-                const float4 q = *reinterpret_cast<const float4*>(er + 4 * e);
+                const float4 q = ecur[e];
                 v[4 * e] = tf32_rn((v[4 * e] - bias) * rowmul * q.x); v[4 * e + 1] = tf32_rn((v[4 * e + 1] - bias) * rowmul * q.y);
                 v[4 * e + 2] = tf32_rn((v[4 * e + 2] - bias) * rowmul * q.z); v[4 * e + 3] = tf32_rn((v[4 * e + 3] - bias) * rowmul * q.w);
               }
             } else {
+              const float* er = erow + nb;      // ragged last chunk of the row: element by element
 #pragma unroll
               for (int e = 0; e < 32; e++) v[e] = (nb + e < p.N_valid) ? tf32_rn((v[e] - bias) * rowmul * er[e]) : 0.f;
             }
           }
+#pragma unroll
+          for (int e = 0; e < 8; e++) ecur[e] = enext[e];
         } else if (p.cc && row_ok && nb < p.N_valid && kc == 0) {
           const float* cr = p.cc + (long long)row * p.ldcc + nb;
           if (nb + 32 <= p.N_valid) {
@@ -799,6 +816,7 @@ extern "C" int dcnet_gemm_tf32(const float* A, int a_mn_major, long long lda, lo
   UmmaOperand b{B, b_mn_major ? K : N, b_mn_major ? N : K, ldb, strideB, batch, b_mn_major != 0, false};
   UmmaEpilogue e{};
   e.out = C; e.ldo = ldc; e.so_b = strideC; e.alpha = alpha; e.atomic = atomic;
+  if (atomic) e.k_chunks = -1;     // reduce-add output: split the reduction when the tiles do not fill the SMs
   return umma_gemm(a, b, nullptr, M, N, K, 0, 0, batch, e, as_stream(stream));
 }
 

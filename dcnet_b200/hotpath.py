@@ -70,6 +70,7 @@ class HotPath(nn.Module):
     # aux -1 -> 1.315 ms against 1.371 ms; raising the coarse-scale streams as well, or instead, gives nothing (1.33-1.36 ms).
     side_priority = (0, 0)
     aux_priority = (-1, -1)
+    terms_on_aux = True
 
     def _run_scales(self, chain):
         if not self.scale_streams:
@@ -83,12 +84,14 @@ class HotPath(nn.Module):
                 torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         outs = [None, None, None]
         fork = cur.record_event()
-        for s in (0, 1):
+        # the finest scale's chain is the critical path of the step: issue it first so that its kernels are first in line for the
+        # SMs (profiles/r2i_timeline_c3.txt: issued last, its first GEMM waited 300 us behind the coarsest scale's exact-fp32 conv)
+        outs[2] = chain(2)
+        for s in (1, 0):
             st = self._side[s]
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 outs[s] = chain(s)
-        outs[2] = chain(2)
         if getattr(self, "_aux_pending", False):
             for aux in self._aux:
                 cur.wait_stream(aux)
@@ -131,17 +134,22 @@ class HotPath(nn.Module):
         # moves that accumulation to the caller's stream, where it queues behind the finest chain's own work.
         if fa.requires_grad:
             fa = fa.view_as(fa)
+        if flang.requires_grad:
+            flang = flang.view_as(flang)       # same for the sentence vector: every scale's fusion layer consumes it
         best_n, gi, gj, t5, _, _ = ops.build_target(bbox, self.size, LS.args.anchor_imsize, LS.anchors_full)
         fa_neg = partner3 = None
         if self.cross_gpu_negatives:
             fa_neg, partner3 = parallel.global_partners(fa, best_n, gi, gj)
 
-        # text / coordinate terms of the three fusion layers: tiny cuBLAS products that depend on nothing of the chains.  On an
-        # auxiliary stream their backward (weight / text gradients) also stays off the chains' critical path.
-        def fusion_terms():
-            return [net.fuse_terms(s, flang, ops.coord_map(hw[s][0], hw[s][1], fa.device).flatten(1)) for s in range(3)]
-        terms = self._branch(0, fusion_terms, flang)
-        ev_terms = self._aux[0].record_event() if self.scale_streams else None
+        coords = [ops.coord_map(hw[s][0], hw[s][1], fa.device).flatten(1) for s in range(3)]
+        # text / coordinate terms of the three fusion layers (a8): small kernels that depend on nothing of the chains.  Issued up
+        # front on an auxiliary stream, their backward (weight / text gradients) also stays off the chains' critical path -- that
+        # matters at 256x256 where a chain is a sequence of 10-40 us kernels; terms_on_aux = False computes them inside the fusion
+        # layer's own node instead (no extra weight-gradient add).
+        terms, ev_terms = [None, None, None], None
+        if self.terms_on_aux:
+            terms = self._branch(0, lambda: [net.fuse_terms(s, flang, coords[s]) for s in range(3)], flang)
+            ev_terms = self._aux[0].record_event() if self.scale_streams else None
 
         def chain(s):
             """everything of one pyramid scale: a2 -> (a4, a11 on the coarsest scale) -> a5/a6/a9 -> a7/a8 -> a10"""
@@ -166,7 +174,7 @@ class HotPath(nn.Module):
                 for t in terms[s]:
                     if t is not None:
                         t.record_stream(torch.cuda.current_stream())
-            o['y'] = net.fuse_scale(o['corr'], s, flang, None, terms=terms[s])
+            o['y'] = net.fuse_scale(o['corr'], s, flang, coords[s], terms=terms[s])
             o['obj'] = ops.only_obj(head[s], o['sim'])
             o['pred'] = ops.modulate_conf(head[s], o['sim'], loc[s])
             return o

@@ -194,18 +194,21 @@ class grounding_model(nn.Module):
         attn = ops.coattention(fv_s, qa, kb, tau=self.temperature, precision=self.coattn_precision)
         return self.corr_conv._modules[str(s)][0].fused(fv_s, x2=attn, fa=fa, l2norm=True, precision=self.precision, fa_neg=fa_neg)
 
-    def fuse_terms(self, s, flang, coords_s, C=512):
-        """the text and coordinate terms of the split-weight fusion: u = W_l flang [B,C], cc = W_c coord [C,N]"""
+    def fuse_terms(self, s, flang, coords_s, kv=512):
+        """the text / coordinate terms of scale s on their own (ops.fuse_terms): for callers that issue them ahead of the chain"""
         m = self.fcn_emb._modules[str(s)][0]
         w = m.conv.weight.view(m.conv.weight.shape[0], -1)
-        u = F.linear(flang, w[:, C:2 * C])
-        cc = w[:, 2 * C:] @ coords_s if self.coordmap else None
-        return u, cc
+        r = ops.fuse_terms(w, flang, coords_s if self.coordmap else None, kv)
+        return r if self.coordmap else (r, None)
 
     def fuse_scale(self, corr_s, s, flang, coords_s, terms=None):
+        """a7 + a8 for one scale (:489-505): split-weight form of cat([corr, flang_tile, coord]) -> 1x1 conv + BN + ReLU (SURVEY
+        Appendix A.9).  The text / coordinate terms W_l flang, W_c coord and their gradients run on this library's kernels
+        (dcnet_fuse_terms_*), the visual term on the tcgen05 GEMM whose epilogue adds them."""
         m = self.fcn_emb._modules[str(s)][0]
-        u, cc = terms if terms is not None else self.fuse_terms(s, flang, coords_s, corr_s.shape[1])
-        return m.fused(corr_s, u=u, cc=cc, l2norm=False, precision=self.precision)
+        if terms is not None:
+            return m.fused(corr_s, u=terms[0], cc=terms[1], l2norm=False, precision=self.precision)
+        return m.fused(corr_s, l2norm=False, precision=self.precision, flang=flang, coords=coords_s if self.coordmap else None)
 
     def interframe(self, fv0, negpos=None):
         """a4 (:381-430) -> packed q [30,P,C], k [30,P,C], neg [30,P,10,C].  negpos: optional pre-drawn device tensor
@@ -244,19 +247,8 @@ class grounding_model(nn.Module):
         return corr, sim, neg_sim
 
     def fuse(self, corr, flang, coords):
-        """a7 + a8 (:489-505): split-weight form of cat([corr, flang_tile, coord]) -> 1x1 conv.
-        coords: 3 x [8,N_s] from ops.coord_map."""
-        out = []
-        C = corr[0].shape[1]
-        for s in range(3):
-            m = self.fcn_emb._modules[str(s)][0]
-            w = m.conv.weight.view(m.conv.weight.shape[0], -1)
-            u = F.linear(flang, w[:, C:2 * C])                                   # text term  W_l flang        [B,C]
-            cc = None
-            if self.coordmap:
-                cc = w[:, 2 * C:] @ coords[s]                                    # coord term W_c coord        [C,N]
-            out.append(m.fused(corr[s], u=u, cc=cc, l2norm=False, precision=self.precision))
-        return out
+        """a7 + a8 (:489-505) for the three scales.  coords: 3 x [8,N_s] from ops.coord_map."""
+        return [self.fuse_scale(corr[s], s, flang, coords[s]) for s in range(3)]
 
     def crossmodal(self, fv0, context, negidx=None):
         """a11 (:625-637, :41-112) -> packed q [N0,B,C], k [N0,B,1,C], neg [N0,B,5,C].  negidx: optional pre-drawn device

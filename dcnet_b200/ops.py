@@ -65,13 +65,14 @@ def sgemm(A, B, C, M, N, K, batch=1, kbatch=1, sA=(0, 0, 0, 0), sB=(0, 0, 0, 0),
     return C
 
 
-def gemm_tf32(A, B, a_mn, b_mn, M, N, K, alpha=1.0, out=None):
-    """direct tensor-core GEMM: A [batch, M, K] (a_mn=0) or [batch, K, M] (a_mn=1); B [batch, N, K] or [batch, K, N]."""
+def gemm_tf32(A, B, a_mn, b_mn, M, N, K, alpha=1.0, out=None, atomic=0):
+    """direct tensor-core GEMM: A [batch, M, K] (a_mn=0) or [batch, K, M] (a_mn=1); B [batch, N, K] or [batch, K, N].
+    atomic=1: the result is ADDED to `out` (TMA reduce-add epilogue, reduction split over CTAs when there are few tiles)."""
     A, B = _c(A, name="A"), _c(B, name="B")
     batch = A.shape[0]
     C = torch.empty(batch, M, N, device=A.device, dtype=F32) if out is None else out
     _lib.call("dcnet_gemm_tf32", _p(A), int(a_mn), A.shape[2], A.shape[1] * A.shape[2], _p(B), int(b_mn), B.shape[2], B.shape[1] * B.shape[2],
-              _p(C), N, M * N, M, N, K, batch, alpha, 0, _st())
+              _p(C), N, M * N, M, N, K, batch, alpha, int(atomic), _st())
     return C
 
 
@@ -232,6 +233,38 @@ def bbox_iou(b1, b2, x1y1x2y2=True):
     return out
 
 
+def topk_boxes(pred, feat, k, meta, size, anchor_imsize, anchors_full):
+    """8f-3 (test_DCNet.py:593-645, :657-701).  pred 3 x [B,15,N_s] (or [B,3,5,g,g]), feat 3 x [B,C,N_s] (corr_feat), meta [B,5] =
+    (ratio, dw, dh, img_w, img_h).  -> boxes [B,k,4] (original image, clamped), scores [B,k], cells [B,k,4] int64 = (scale, anchor,
+    gj, gi), feats [B,k,C]."""
+    pred = [_c(p.detach().reshape(p.shape[0], 15, -1), name="pred") for p in pred]
+    feat = [_c(f.detach().reshape(f.shape[0], f.shape[1], -1), name="feat") for f in feat]
+    meta = _c(meta.detach().float(), name="meta")
+    B, C = feat[0].shape[0], feat[0].shape[1]
+    dev = pred[0].device
+    boxes = torch.empty(B, k, 4, device=dev, dtype=F32)
+    scores = torch.empty(B, k, device=dev, dtype=F32)
+    cells = torch.empty(B, k, 4, device=dev, dtype=torch.long)
+    feats = torch.empty(B, k, C, device=dev, dtype=F32)
+    an = _anchors_arr(anchors_full)
+    _lib.call("dcnet_topk_boxes", *[_p(p) for p in pred], *[_p(f) for f in feat], B, int(size) // 32, int(size), C, int(k), float(anchor_imsize),
+              an.ctypes.data, _p(meta), _p(boxes), _p(scores), _p(cells), _p(feats), _st())
+    return boxes, scores, cells, feats
+
+
+def post_rescore(centre, ref, ref_score, invalid=None):
+    """8f-3 (post_processing.py:239-274).  centre [k,C], ref [k,R,C], ref_score [k,R], invalid [R] int32 (or None)
+    -> fused [k], best [1] int64, match [k,R] int64."""
+    centre, ref, ref_score = _c(centre.detach(), name="centre"), _c(ref.detach(), name="ref"), _c(ref_score.detach().float(), name="ref_score")
+    k, R, C = ref.shape
+    invalid = _c(invalid, torch.int32, "invalid") if invalid is not None else None
+    fused = torch.empty(k, device=ref.device, dtype=F32)
+    best = torch.empty(1, device=ref.device, dtype=torch.long)
+    match = torch.empty(k, R, device=ref.device, dtype=torch.long)
+    _lib.call("dcnet_post_rescore", _p(centre), _p(ref), _p(ref_score), _p(invalid), k, R, C, _p(fused), _p(best), _p(match), _st())
+    return fused, best, match
+
+
 def yolo_layer_decode(x, anchors, num_classes, image_dim):
     x = _c(x, name="x")
     B, _, g, _ = x.shape
@@ -259,7 +292,8 @@ class _ConvBNAct(torch.autograd.Function):
     BatchNorm statistics are taken from the unpadded z."""
 
     @staticmethod
-    def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope, l2norm, precision, nbt=None):
+    def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope, l2norm, precision, nbt=None,
+                flang=None, coords=None):
         x1 = _c(x1, name="x1")
         x2 = _c(x2, name="x2")
         weight = _c(weight, name="weight")
@@ -270,6 +304,19 @@ class _ConvBNAct(torch.autograd.Function):
         C, ldw = weight.shape
         dev = x1.device
         st = _st()
+        flang, coords = _c(flang, name="flang"), _c(coords, name="coords")
+        if flang is not None:
+            # a8: the text / coordinate columns of the weight act on flang [B,Ct] and coords [8,N] (split-weight form of the
+            # reference's cat([corr_feat, flang tile, coord]) -> 1x1 conv): u and cc come from this library's own kernels
+            if u is not None or cc is not None:
+                raise ValueError("conv_bn_act: give either (u, cc) or (flang, coords)")
+            Ct = flang.shape[1]
+            if ldw != K1 + K2 + Ct + (8 if coords is not None else 0) or (coords is not None and tuple(coords.shape) != (8, N)):
+                raise ValueError("conv_bn_act: weight [%d,%d] does not split into %d + %d visual, %d text%s columns" % (
+                    C, ldw, K1, K2, Ct, ", 8 coordinate" if coords is not None else ""))
+            u = torch.empty(B, C, device=dev, dtype=F32)
+            cc = torch.empty(C, N, device=dev, dtype=F32) if coords is not None else None
+            _lib.call("dcnet_fuse_terms_fwd", _p(weight), ldw, K1 + K2, Ct, K1 + K2 + Ct, _p(flang), _p(coords), _p(u), _p(cc), B, C, N, st)
         z = torch.empty(B, C, N, device=dev, dtype=F32)
         mean = torch.empty(C, device=dev, dtype=F32)
         invstd = torch.empty(C, device=dev, dtype=F32)
@@ -303,7 +350,7 @@ class _ConvBNAct(torch.autograd.Function):
             neg = torch.empty(B, N, device=dev, dtype=F32)
         _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm), _p(y), _p(fa), _p(fa_neg), _p(sim), _p(neg),
                   B, C, N, st)
-        ctx.save_for_backward(x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd)
+        ctx.save_for_backward(x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd, flang, coords)
         ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None, ctx_precision)
         if fa is None:
             return y
@@ -311,8 +358,9 @@ class _ConvBNAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, dsim=None, dneg=None):
-        x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd = ctx.saved_tensors
+        x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd, flang, coords = ctx.saved_tensors
         training, slope, l2norm, has_u, has_cc, precision = ctx.cfg
+        terms = flang is not None          # u / cc were derived from (flang, coords) inside forward
         if precision == EXACT_FWD_TF32_BWD:
             precision = TENSOR_TF32      # no index depends on the gradients: the backward contractions run on tcgen05
         B, K1, N = x1.shape
@@ -324,9 +372,13 @@ class _ConvBNAct(torch.autograd.Function):
         dsim = _c(dsim, name="dsim") if fa is not None else None
         dneg = _c(dneg, name="dneg") if fa is not None else None
         dv = torch.empty_like(z)
-        sums = torch.zeros(2, C, device=dev, dtype=F32)
-        dfa = torch.zeros(B, C, device=dev, dtype=F32) if (fa is not None and ctx.needs_input_grad[7]) else None
-        dfa_neg = torch.zeros(B, C, device=dev, dtype=F32) if (fa_neg is not None and ctx.needs_input_grad[8]) else None
+        # every accumulator the reduce kernel adds into with atomics, zeroed by ONE fill
+        want_dfa = fa is not None and ctx.needs_input_grad[7]
+        want_dfa_neg = fa_neg is not None and ctx.needs_input_grad[8]
+        acc = torch.zeros(2 * C + (B * C if want_dfa else 0) + (B * C if want_dfa_neg else 0), device=dev, dtype=F32)
+        sums = acc[:2 * C].view(2, C)
+        dfa = acc[2 * C:2 * C + B * C].view(B, C) if want_dfa else None
+        dfa_neg = acc[acc.numel() - B * C:].view(B, C) if want_dfa_neg else None
         _lib.call("dcnet_bn_act_bwd_reduce", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, l2norm, _p(dy), _p(fa), _p(fa_neg),
                   _p(dsim), _p(dneg), _p(dv), _p(sums[0]), _p(sums[1]), _p(dfa), _p(dfa_neg), B, C, N, st)
         _lib.call("dcnet_bn_act_bwd_apply", _p(z), _p(mean), _p(invstd), _p(gamma), _p(dv), _p(sums[0]), _p(sums[1]), int(training), _p(dv),
@@ -345,43 +397,103 @@ class _ConvBNAct(torch.autograd.Function):
                 dx1 = dx1p[..., :N].contiguous() if ctx.needs_input_grad[0] else None
                 dx2 = dx2p[..., :N].contiguous() if (x2 is not None and ctx.needs_input_grad[1]) else None
             dW = du = dcc = None
-            if need_w:
-                dW = torch.zeros(C, ldw, device=dev, dtype=F32)
-            if has_u and ctx.needs_input_grad[5]:
+            covered = (K1 + K2 == ldw) or (terms and (coords is not None or K1 + K2 + flang.shape[1] == ldw))
+            if need_w:        # the kernels overwrite every column they own: a fill only when some columns are nobody's
+                dW = (torch.empty if covered else torch.zeros)(C, ldw, device=dev, dtype=F32)
+            if has_u and (terms or ctx.needs_input_grad[5]):
                 du = torch.empty(B, C, device=dev, dtype=F32)
-            dccp = torch.empty(C, Np, device=dev, dtype=F32) if (has_cc and ctx.needs_input_grad[6]) else None
+            dccp = torch.empty(C, Np, device=dev, dtype=F32) if (has_cc and (terms or ctx.needs_input_grad[6])) else None
             if need_w or du is not None or dccp is not None:
                 x1p = _pad_n(x1, Np) if need_w else None
                 x2p = _pad_n(x2, Np) if (need_w and x2 is not None) else None
                 _lib.call("dcnet_conv1x1_bwd_weight", _p(dzp), _p(x1p), K1, _p(x2p), K2, _p(dW), ldw, _p(du), _p(dccp), B, C, Np, precision, st)
             dcc = dccp[:, :N].contiguous() if dccp is not None else None
-            return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None)
+            return _ConvBNAct._finish(ctx, dx1, dx2, dW, sums, du, dcc, dfa, dfa_neg, weight, flang, coords, K1 + K2, B, C, N, st)
         dx1 = torch.empty_like(x1) if ctx.needs_input_grad[0] else None
         dx2 = torch.empty_like(x2) if (x2 is not None and ctx.needs_input_grad[1]) else None
         if dx1 is not None or dx2 is not None:
             _lib.call("dcnet_conv1x1_bwd_data", _p(dz), _p(weight), ldw, _p(dx1), K1, _p(dx2), K2, B, C, N, precision, st)
         dW = du = dcc = None
+        covered = (K1 + K2 == ldw) or (terms and (coords is not None or K1 + K2 + flang.shape[1] == ldw))
         if need_w:
-            dW = torch.zeros(C, ldw, device=dev, dtype=F32)
-        if has_u and ctx.needs_input_grad[5]:
+            dW = (torch.empty if covered else torch.zeros)(C, ldw, device=dev, dtype=F32)
+        if has_u and (terms or ctx.needs_input_grad[5]):
             du = torch.empty(B, C, device=dev, dtype=F32)
-        if has_cc and ctx.needs_input_grad[6]:
+        if has_cc and (terms or ctx.needs_input_grad[6]):
             dcc = torch.empty(C, N, device=dev, dtype=F32)
         if need_w or du is not None or dcc is not None:
             _lib.call("dcnet_conv1x1_bwd_weight", _p(dz), _p(x1) if need_w else None, K1, _p(x2) if need_w else None, K2,
                       _p(dW), ldw, _p(du), _p(dcc), B, C, N, precision, st)
-        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None)
+        return _ConvBNAct._finish(ctx, dx1, dx2, dW, sums, du, dcc, dfa, dfa_neg, weight, flang, coords, K1 + K2, B, C, N, st)
+
+    @staticmethod
+    def _finish(ctx, dx1, dx2, dW, sums, du, dcc, dfa, dfa_neg, weight, flang, coords, kv, B, C, N, st):
+        """gradients in the order of forward's inputs; with (flang, coords) the text / coordinate columns of dW and dflang"""
+        dflang = None
+        if flang is not None:
+            Ct = flang.shape[1]
+            dflang = torch.empty_like(flang) if ctx.needs_input_grad[18] else None
+            if dflang is not None or dW is not None:
+                _lib.call("dcnet_fuse_terms_bwd", _p(weight), weight.shape[1], kv, Ct, kv + Ct, _p(flang), _p(coords), _p(du), _p(dcc),
+                          _p(dflang), _p(dW), B, C, N, st)
+            du = dcc = None
+        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, dflang, None)
 
 
 EXACT_FP32, TENSOR_TF32, TENSOR_BF16_FUSED, EXACT_FWD_TF32_BWD = 0, 1, 2, 3
+FUSED_MIN_N = 128      # the fused bf16 co-attention forward is used from this many positions on (below: exact fp32, tiny)
 
 
 def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
-                momentum=0.999, eps=1e-5, slope=0.0, l2norm=False, precision=TENSOR_TF32, fa_neg=None, num_batches_tracked=None):
+                momentum=0.999, eps=1e-5, slope=0.0, l2norm=False, precision=TENSOR_TF32, fa_neg=None, num_batches_tracked=None,
+                flang=None, coords=None):
     """x1 [B,K1,N] (+x2 [B,K2,N]); weight [C,ldw].  Returns y [B,C,N] or (y, sim, neg_sim) when fa [B,C] is given.
-    precision: TENSOR_TF32 = tcgen05 GEMMs (<=1e-3 relative), EXACT_FP32 = CUDA-core fp32 (<=1e-5)."""
+    precision: TENSOR_TF32 = tcgen05 GEMMs (<=1e-3 relative), EXACT_FP32 = CUDA-core fp32 (<=1e-5).
+    (u [B,C], cc [C,N]): extra terms added to the conv output; or (flang [B,Ct], coords [8,N]): the fusion's text / coordinate
+    inputs, whose weight columns follow the visual ones in `weight` (a8) -- u and cc are then computed and back-propagated here."""
     return _ConvBNAct.apply(x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, bool(training), float(momentum),
-                            float(eps), float(slope), bool(l2norm), int(precision), num_batches_tracked if training else None)
+                            float(eps), float(slope), bool(l2norm), int(precision), num_batches_tracked if training else None,
+                            flang, coords)
+
+
+class _FuseTerms(torch.autograd.Function):
+    """a8 as a node of its own: (u, cc) = (W_l flang, W_c coords) and their backward through dcnet_fuse_terms_*.  conv_bn_act does the
+    same inline when it is given (flang, coords); this form lets a caller issue the terms early / on another stream (HotPath)."""
+
+    @staticmethod
+    def forward(ctx, weight, flang, coords, kv):
+        weight, flang, coords = _c(weight, name="weight"), _c(flang, name="flang"), _c(coords, name="coords")
+        C, ldw = weight.shape
+        B, Ct = flang.shape
+        N = coords.shape[1] if coords is not None else 1
+        u = torch.empty(B, C, device=flang.device, dtype=F32)
+        cc = torch.empty(C, N, device=flang.device, dtype=F32) if coords is not None else None
+        _lib.call("dcnet_fuse_terms_fwd", _p(weight), ldw, kv, Ct, kv + Ct, _p(flang), _p(coords), _p(u), _p(cc), B, C, N, _st())
+        ctx.save_for_backward(weight, flang, coords)
+        ctx.kv = kv
+        return (u, cc) if cc is not None else u
+
+    @staticmethod
+    def backward(ctx, du, dcc=None):
+        weight, flang, coords = ctx.saved_tensors
+        C, ldw = weight.shape
+        B, Ct = flang.shape
+        N = coords.shape[1] if coords is not None else 1
+        du = _c(du, name="du")
+        dcc = _c(dcc, name="dcc") if coords is not None else None
+        dflang = torch.empty_like(flang) if ctx.needs_input_grad[1] else None
+        dW = None
+        if ctx.needs_input_grad[0]:
+            # only the text / coordinate columns are this node's; the visual columns arrive from the conv node and autograd adds
+            dW = torch.zeros(C, ldw, device=flang.device, dtype=F32)
+        _lib.call("dcnet_fuse_terms_bwd", _p(weight), ldw, ctx.kv, Ct, ctx.kv + Ct, _p(flang), _p(coords), _p(du), _p(dcc), _p(dflang), _p(dW),
+                  B, C, N, _st())
+        return dW, dflang, None, None
+
+
+def fuse_terms(weight, flang, coords, kv):
+    """weight [C,ldw] = [W_v (kv columns) | W_l | W_c]; -> (u [B,C], cc [C,N]) (cc omitted when coords is None)"""
+    return _FuseTerms.apply(weight, flang, coords, int(kv))
 
 
 class _CoAttn(torch.autograd.Function):
@@ -399,6 +511,11 @@ class _CoAttn(torch.autograd.Function):
         if precision == EXACT_FWD_TF32_BWD:
             precision = EXACT_FP32           # exact fp32 forward (lse included); the backward contractions run as tf32 on tcgen05
             ctx.precision = TENSOR_TF32
+        if precision == TENSOR_BF16_FUSED and N < FUSED_MIN_N:
+            # short key axes: with few keys the rounding of bf16 (and tf32) operands does not average out -- 1.6e-3 (1.15e-3) on the
+            # worst of 112 problems at N = 64, bar 1e-3 -- and the contraction is tiny: exact fp32 forward; the backward is the
+            # precision-2 one either way (it recomputes its own tf32 logits and uses the saved lse only as a shift)
+            precision = EXACT_FP32
         if precision == TENSOR_BF16_FUSED and C % 128 == 0 and C <= 512:
             # fused kernel: only the bf16 staging of the maps is needed.  Handing it to the backward (dcnet_coattn_bwd's `staged`:
             # P recomputed from the same bf16 operands, exp fused into the GEMM epilogue, no softmax pass) was measured at

@@ -97,6 +97,18 @@ DCNET_API int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, f
 DCNET_API int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1, const float* x2, int K2,
                                        float* dW, int ldw, float* du, float* dcc, int B, int C, int N, int precision, void* stream);
 
+/* ---- a8: text / coordinate terms of the split-weight fusion (model/DCNet_model.py:489-505; ancestor
+ * model/grounding_model_semantic_attn.py:266-281).  W [C,ldw] = [W_v | W_l | W_c]: u [B,C] = flang [B,Ct] W_l^T with
+ * W_l = W[:, col_l:col_l+Ct]; cc [C,N] = W_c coord with W_c = W[:, col_c:col_c+8], coord [8,N] (dcnet_coord_map).  coord / cc may be
+ * NULL (coordmap=False).  u and cc are what dcnet_conv1x1_fwd adds in its epilogue, so the [B,1032,h,w] concatenation of the
+ * reference is never built.                                                                                               */
+DCNET_API int dcnet_fuse_terms_fwd(const float* W, int ldw, int col_l, int Ct, int col_c, const float* flang, const float* coord,
+                                   float* u, float* cc, int B, int C, int N, void* stream);
+/* backward from du [B,C] / dcc [C,N] (dcnet_conv1x1_bwd_weight): dflang [B,Ct] (or NULL) and the text / coordinate columns of
+ * dW [C,ldw] (overwritten; NULL = no weight gradient)                                                                     */
+DCNET_API int dcnet_fuse_terms_bwd(const float* W, int ldw, int col_l, int Ct, int col_c, const float* flang, const float* coord,
+                                   const float* du, const float* dcc, float* dflang, float* dW, int B, int C, int N, void* stream);
+
 /* mean/invstd (+ running statistics, momentum, unbiased variance) from the epilogue sums: count = B*N.
  * num_batches_tracked (optional, one int64 on the device) is incremented like nn.BatchNorm2d does per training step. */
 DCNET_API int dcnet_bn_finalize(const float* stat_sums, long long count, int C, float eps, float momentum,
@@ -270,6 +282,22 @@ DCNET_API int dcnet_ground_loss_bwd(const float* pred0, const float* pred1, cons
                                     float* dpred0, float* dpred1, float* dpred2, float* dsim0, float* dsim1, float* dsim2,
                                     float* dneg0, float* dneg1, float* dneg2, float* dloc0, float* dloc1, float* dloc2,
                                     void* stream);
+
+/* ---- 8f-3: test-time cache writer (test_DCNet.py:546-654, get_topk_pred_bbox :657-701) -----------------------------
+ * pred0..2 [B,15,N_s] (modulated confidences at channels 5a+4), feat0..2 [B,C,N_s] (corr_feat), meta [B,5] = (ratio, dw, dh,
+ * img_w, img_h) of the letterbox (test_DCNet.py:615-627).  Per image the k best (scale, anchor, cell) by confidence (ties ->
+ * lower flat index; the cell is the FIRST of its scale with that confidence, :682): boxes [B,k,4] xyxy in the original image
+ * (clamped like :693-696), scores [B,k], cells [B,k,4] = (scale, anchor, gj, gi), feats [B,k,C].                          */
+DCNET_API int dcnet_topk_boxes(const float* pred0, const float* pred1, const float* pred2,
+                               const float* feat0, const float* feat1, const float* feat2, int B, int g0, int size, int C, int k,
+                               float anchor_imsize, const float* h_anchors9x2, const float* meta,
+                               float* boxes, float* scores, long long* cells, float* feats, void* stream);
+/* ---- 8f-3: post_processing.py:205-270.  centre [k,C]; ref [k,R,C] / ref_score [k,R] = cached features / scores of the top-k boxes
+ * of R reference frames; invalid [R] (or NULL) marks frames whose cache was missing (:234-236, zeroed after the softmax :267).
+ * fused [k] = sum_r softmax_r(max_j <centre_i, ref_jr>) * score of the arg-max box; best = first arg-max of fused;
+ * match [k,R] (or NULL) the matched reference box per (i,r).  k, R <= 16.                                                  */
+DCNET_API int dcnet_post_rescore(const float* centre, const float* ref, const float* ref_score, const int* invalid, int k, int R, int C,
+                                 float* fused, long long* best, long long* match, void* stream);
 
 /* ---- a18: decode (train_DCNet.py:656-690 at the GT cell; :766-816 arg-max) + a15 bbox_iou ---------------
  * mode 0: decode at the given (best_n, gi, gj); mode 1: arg-max over the 3*SN conf logits (first maximum in

@@ -640,3 +640,75 @@ def forward_test_restated(net, raw_fvisu, word_id, n_frame=5):
     return dict(outbox=[shp(outbox[s], s) for s in range(3)], sim_score=[shp(sim[s], s) for s in range(3)],
                 loc_score=[shp(loc[s], s) for s in range(3)], corr_feat=[shp(corr[s], s) for s in range(3)],
                 only_obj=[shp(oo[s], s) for s in range(3)], flang_attn=fa[:, :, None, None])
+
+
+# ----------------------------------------------------------------------------------------------
+# 8f-3  test-time cache writer and offline re-scoring      test_DCNet.py:546-701, post_processing.py:205-270
+# ----------------------------------------------------------------------------------------------
+def letterbox_image_size(ratio, dw, dh, size):
+    """(img_w, img_h) of the un-letterboxed image the boxes are clamped to: the crop [top:bottom, left:right] of the size x size
+    input resized by 1/ratio, with python's round() exactly as test_DCNet.py:617-624."""
+    top, bottom = round(float(dh) - 0.1), size - round(float(dh) + 0.1)
+    left, right = round(float(dw) - 0.1), size - round(float(dw) + 0.1)
+    ratio = float(ratio)
+    return round((right - left) / ratio), round((bottom - top) / ratio)
+
+
+def topk_pred_boxes(pred5, fvisu, topk, ratio, dw, dh, size, anchor_imsize=416, anchors_full=ANCHORS_FULL):
+    """One image (batch 1, as test_DCNet.py:save_cache runs).  pred5: 3 x [1,3,5,g,g]; fvisu: 3 x [1,C,g,g].
+    Returns (boxes [k,1,4], scores list of k floats, cells list of (scale, anchor, gj, gi), feats [k,1,C]) following
+    test_DCNet.py:593-645 and get_topk_pred_bbox :657-701: torch.topk over the concatenated confidences; the scale from the flat
+    index (:662-667); the cell = first position of that scale equal to the value (np.where(...)[0], :682-683); box decode, un-letterbox
+    and clamp (:688-696).  Top-k ties are canonicalised to the lower flat index (PyTorch leaves the order unspecified)."""
+    conf = [p[:, :, 4].contiguous().view(1, -1) for p in pred5]                        # :595-597
+    flat = torch.cat(conf, 1)[0]
+    order = sorted(range(flat.numel()), key=lambda i: (-float(flat[i]), i))[:topk]     # topk(k) with ties -> lower index
+    img_w, img_h = letterbox_image_size(ratio, dw, dh, size)
+    g0 = size // 32
+    boxes, scores, cells, feats = [], [], [], []
+    for loc in order:
+        v = flat[loc]
+        s = 0 if loc < 3 * g0 ** 2 else (1 if loc < 3 * g0 ** 2 + 3 * (2 * g0) ** 2 else 2)     # :662-667
+        grid, stride = size // (32 // (2 ** s)), 32 // (2 ** s)
+        sa = scaled_anchors(s, size, anchor_imsize, anchors_full)
+        pc = conf[s].view(3, grid, grid).numpy()
+        a_, gj_, gi_ = np.where(pc == v.numpy())                                        # :682
+        a, gi, gj = int(a_[0]), int(gi_[0]), int(gj_[0])
+        p = pred5[s][0, a, :, gj, gi]
+        b = torch.zeros(1, 4)
+        b[0, 0] = torch.sigmoid(p[0]) + gi                                              # :688-692
+        b[0, 1] = torch.sigmoid(p[1]) + gj
+        b[0, 2] = torch.exp(p[2]) * sa[a][0]
+        b[0, 3] = torch.exp(p[3]) * sa[a][1]
+        b[0, :] = b[0, :] * stride
+        b = xywh2xyxy(b)
+        b[:, 0], b[:, 2] = (b[:, 0] - dw) / ratio, (b[:, 2] - dw) / ratio                # :695-696
+        b[:, 1], b[:, 3] = (b[:, 1] - dh) / ratio, (b[:, 3] - dh) / ratio
+        b[:, :2] = torch.clamp(b[:, :2], min=0)                                          # :697-698
+        b[:, 2] = torch.clamp(b[:, 2], max=img_w)
+        b[:, 3] = torch.clamp(b[:, 3], max=img_h)
+        boxes.append(b); scores.append(float(v)); cells.append((s, a, gj, gi))
+        feats.append(fvisu[s][:, :, gj, gi])                                             # :645  [1,C]
+    return torch.stack(boxes), scores, cells, torch.stack(feats)
+
+
+def post_rescore(centre_feat, ref_feats, ref_scores, invalid=()):
+    """post_processing.py:239-274.  centre_feat [k,1,C]; ref_feats: R x [k,1,C]; ref_scores: R x [k]; invalid: frame indices whose cache
+    was missing.  Returns (fused [k], best index, matched reference box [k,R])."""
+    k = centre_feat.shape[0]
+    R = len(ref_feats)
+    refer = torch.cat(ref_feats, dim=1)                                                  # :239  [k,R,C]
+    centre = centre_feat.unsqueeze(1)
+    scores = torch.stack([torch.as_tensor(s, dtype=torch.float) for s in ref_scores]).permute(1, 0)     # :241  [k,R]
+    C = refer.shape[2]
+    refer = refer.view(-1, C).permute(1, 0)                                              # :245-246  [C, k*R]
+    centre = centre.view(-1, C)
+    sim = torch.bmm(centre.unsqueeze(0), refer.unsqueeze(0)).reshape(k, k, R)            # :249-251
+    best_sim, idx = sim.max(dim=1)                                                       # :252
+    ref_score = scores.gather(0, idx)                                                    # :254
+    w = F.softmax(best_sim, dim=1)                                                       # :257
+    if len(invalid) > 0:
+        w[:, list(invalid)] = 0                                                          # :259-260
+    fused = torch.sum(w * ref_score, dim=1)                                              # :262
+    (where,) = np.where(fused.numpy() == fused.max().numpy())                            # :265
+    return fused, int(where[0]), idx

@@ -1,0 +1,30 @@
+"""step time of C2 / C3 (CUDA-graph replay, L2 flushed) under switches of the step's composition"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from dcnet_b200 import ops, _lib
+from dcnet_b200.hotpath import HotPath
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+key = sys.argv[1] if len(sys.argv) > 1 else "c2"
+
+
+def run(name):
+    m = bench.measure_hotpath(key, 20, 3, 0, 1, 0, dev, None)
+    print("%-50s %.4f ms/step  e2e %.4f  launches %d" % (name, m["ms_per_step"], m["e2e"]["ms_per_step"], m["launches_per_step"]), flush=True)
+
+
+run("default")
+HotPath.terms_on_aux = False
+run("fusion terms inline")
+HotPath.terms_on_aux = True
+ops.FUSED_MIN_N = 0
+run("fused bf16 co-attention forward at every N")
+ops.FUSED_MIN_N = 256
+_lib.lib().dcnet_gemm_select(6)
+run("no CTA pairs")
+_lib.lib().dcnet_gemm_select(0)
+_lib.lib().dcnet_coattn_bwd_l2_budget(64 << 20)
+run("co-attention backward in L2-resident chunks (64 MiB)")
+_lib.lib().dcnet_coattn_bwd_l2_budget(0)

@@ -5,7 +5,8 @@ import torch, random
 from dcnet_b200 import synth
 from dcnet_b200.hotpath import HotPath
 dev = torch.device("cuda")
-pairs, size = 8, 256
+pairs, size = (int(sys.argv[2]) if len(sys.argv) > 2 else 8), (int(sys.argv[1]) if len(sys.argv) > 1 else 256)
+tag = sys.argv[3] if len(sys.argv) > 3 else "timeline"
 B = 2 * pairs
 synth.seed_all(13)
 hp = HotPath(size).to(dev).train()
@@ -37,8 +38,8 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     graph.replay(); torch.cuda.synchronize()
     graph.replay(); torch.cuda.synchronize()
-prof.export_chrome_trace("gpurun_out/timeline.json")
-ev = json.load(open("gpurun_out/timeline.json"))["traceEvents"]
+prof.export_chrome_trace("/tmp/timeline.json")
+ev = json.load(open("/tmp/timeline.json"))["traceEvents"]
 ks = [e for e in ev if e.get("cat") == "kernel"]
 ks.sort(key=lambda e: e["ts"])
 # second replay only
@@ -49,6 +50,6 @@ print("kernels in one replay: %d, span %.1f us" % (len(ks), t1 - t0))
 per = collections.defaultdict(float)
 for e in ks: per[e["args"].get("stream")] += e["dur"]
 for s, d in per.items(): print("  stream %s busy %.1f us" % (s, d))
-with open("gpurun_out/timeline.txt", "w") as f:
+with open("gpurun_out/%s.txt" % tag, "w") as f:
     for e in ks:
         f.write("%9.1f %8.1f s%-3s %s\n" % (e["ts"] - t0, e["dur"], e["args"].get("stream"), e["name"][:90]))

@@ -683,3 +683,43 @@ def test_loc_rank8_matches_materialised_relation(B, SN, C):
     # no bias
     score2 = ops.loc_rank8(E.to(DEV), obj.to(DEV), W.to(DEV), None, scale.to(DEV), (shift + scale * bias).to(DEV), f.to(DEV))
     assert float((score2 - score).abs().max()) < 1e-5 / max(spread, 1e-3)
+
+
+@pytest.mark.parametrize("precision,N", [(0, 256), (1, 256), (0, 169)])
+def test_fusion_layer_with_text_and_coordinate_terms(precision, N):
+    """a8 (model/DCNet_model.py:489-505): cat([corr_feat, flang tile, coord]) -> 1x1 conv + BN + ReLU in its split-weight form, the text /
+    coordinate terms and their gradients on the library's own kernels (dcnet_fuse_terms_fwd/bwd), against the dense form in fp64."""
+    B, C, Ct = 4, 512, 512
+    g = gen(300 + N)
+    h = int(round(N ** 0.5))
+    x = torch.randn(B, C, N, generator=g)
+    flang = torch.nn.functional.normalize(torch.randn(B, Ct, generator=g).abs(), dim=1)
+    w = torch.randn(C, C + Ct + 8, generator=g) / 30
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    coord = O.coord_map(h, h).flatten(1)
+    gy = torch.randn(B, C, N, generator=g)
+
+    def dense(dt):
+        t = dict(x=x.clone().to(dt).requires_grad_(True), flang=flang.clone().to(dt).requires_grad_(True), w=w.clone().to(dt).requires_grad_(True),
+                 gamma=gamma.clone().to(dt).requires_grad_(True), beta=beta.clone().to(dt).requires_grad_(True))
+        xin = torch.cat([t['x'], t['flang'][:, :, None].expand(B, Ct, N), coord.to(dt)[None].expand(B, 8, N)], 1)
+        y = O.conv1x1_bn_relu(xin, t['w'], t['gamma'], t['beta'], training=True)
+        y.backward(gy.to(dt))
+        return t, y
+    t64, y64 = dense(torch.float64)
+    t32, y32 = dense(torch.float32)
+    c = dict(x=x.to(DEV).requires_grad_(True), flang=flang.to(DEV).requires_grad_(True), w=w.to(DEV).requires_grad_(True),
+             gamma=gamma.to(DEV).requires_grad_(True), beta=beta.to(DEV).requires_grad_(True))
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    y = ops.conv_bn_act(c['x'], c['w'], c['gamma'], c['beta'], rm, rv, True, flang=c['flang'], coords=ops.coord_map(h, h, DEV).flatten(1),
+                        precision=precision)
+    tol_f, tol_b = (1e-5, 1e-4) if precision == 0 else (2e-3, 3e-2)      # tf32: ReLU-pattern noise, see test_conv_bn_act_forward_backward
+    assert rel(y, y64) < tol_f, rel(y, y64)
+    y.backward(gy.to(DEV))
+    for k in ('x', 'flang', 'w', 'gamma', 'beta'):
+        e = min(rel(c[k].grad, t64[k].grad), rel(c[k].grad, t32[k].grad))
+        assert e < tol_b, (k, e)
+    # the text and coordinate columns of the weight gradient on their own (they are written by dcnet_fuse_terms_bwd)
+    for lo, hi in ((C, C + Ct), (C + Ct, C + Ct + 8)):
+        e = min(rel(c['w'].grad[:, lo:hi], t64['w'].grad[:, lo:hi]), rel(c['w'].grad[:, lo:hi], t32['w'].grad[:, lo:hi]))
+        assert e < tol_b, (lo, hi, e)

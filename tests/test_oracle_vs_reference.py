@@ -163,3 +163,38 @@ def test_test_time_clip_model_matches_reference(ref, n_frame, b):
     for i, n in enumerate(['outbox', 'sim_score', 'loc_score', 'corr_feat', 'only_obj']):
         for s in range(3):
             torch.testing.assert_close(o[n][s], r[i][s], rtol=2e-5, atol=2e-4 if n == 'loc_score' else 2e-5, msg=lambda m, n=n, s=s: f"{n}[{s}] {m}")
+
+
+def test_topk_pred_boxes_matches_reference_get_topk_pred_bbox(ref):
+    """8f-3: the oracle's cache-writer restatement against the reference's own get_topk_pred_bbox (test_DCNet.py:657-701) called on
+    the same confidences, including a duplicated maximum (the reference reports the FIRST cell of the scale for both ranks)."""
+    import os
+    import sys
+    import types
+    cwd = os.getcwd()
+    os.chdir(ref_loader.REF_ROOT)
+    try:
+        import test_DCNet as TD
+    finally:
+        os.chdir(cwd)
+    size = 256
+    TD.args = types.SimpleNamespace(size=size, anchor_imsize=416)
+    TD.anchors_full = list(ref_loader.ANCHORS_FULL)
+    g = torch.Generator().manual_seed(5)
+    pred5 = [torch.randn(1, 3, 5, s, s, generator=g) for s in (8, 16, 32)]
+    pred5[1][0, 2, 4, 3, 5] = 9.0
+    pred5[1][0, 0, 4, 7, 1] = 9.0                       # duplicated top confidence inside scale 1
+    fv = [torch.randn(1, 512, s, s, generator=g) for s in (8, 16, 32)]
+    ratio, dw, dh = 0.8, torch.tensor([10.0]), torch.tensor([20.0])
+    k = 5
+    iw, ih = O.letterbox_image_size(ratio, dw, dh, size)
+    img_np = torch.zeros(1, 3, ih, iw)
+    boxes, scores, cells, feats = O.topk_pred_boxes(pred5, fv, k, ratio, dw, dh, size)
+    conf = [p[:, :, 4].contiguous().view(1, -1) for p in pred5]
+    mc, ml = torch.topk(torch.cat(conf, 1), k=k, dim=1)
+    for ii in range(k):
+        rb, rs, rscale, rn, rgj, rgi = TD.get_topk_pred_bbox(conf, None, None, mc[:, ii], ml[:, ii], pred5, ratio, dw, dh, img_np)
+        assert torch.equal(rb, boxes[ii]), (ii, rb, boxes[ii])
+        assert float(rs) == scores[ii] and (rscale, rn, rgj, rgi) == cells[ii]
+        assert torch.equal(fv[rscale][:, :, rgj, rgi], feats[ii])
+    assert cells[0] == cells[1] == (1, 0, 7, 1)          # the duplicate: both ranks report the first cell (anchor 0 before anchor 2)
