@@ -74,12 +74,15 @@ __global__ void __launch_bounds__(256) coattn_delta_kernel(const float* __restri
                                                            float* __restrict__ r, float* __restrict__ delta, int C, int N) {
   const int z = blockIdx.y;
   const int n = (blockIdx.x * 32 + threadIdx.x) * 4;
+  // gridDim.z channel slices per (position block, problem): small maps (N = 1024: 8 x 16 blocks) would leave most SMs idle;
+  // delta is zero-filled by the caller and the slices add into it
+  const int cper = (C + gridDim.z - 1) / gridDim.z, c0 = blockIdx.z * cper, c1 = min(C, c0 + cper);
   __shared__ float part[8][128];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (n < N) {
     const long long src = (long long)oidx[z] * C * N + n;
 #pragma unroll 4
-    for (int c = threadIdx.y; c < C; c += 8) {
+    for (int c = c0 + threadIdx.y; c < c1; c += 8) {
       const float4 g = *reinterpret_cast<const float4*>(dO + src + (long long)c * N);
       const float4 o = *reinterpret_cast<const float4*>(O + src + (long long)c * N);
       acc[0] = fmaf(g.x, o.x, acc[0]); acc[1] = fmaf(g.y, o.y, acc[1]); acc[2] = fmaf(g.z, o.z, acc[2]); acc[3] = fmaf(g.w, o.w, acc[3]);
@@ -95,8 +98,8 @@ __global__ void __launch_bounds__(256) coattn_delta_kernel(const float* __restri
     for (int k = 0; k < 8; k++) s += part[k][t];
     const int nn = blockIdx.x * 128 + t;
     if (nn < N) {
-      delta[(long long)z * N + nn] = s;
-      r[(long long)z * N + nn] = 1.f / r[(long long)z * N + nn];
+      atomicAdd(delta + (long long)z * N + nn, s);
+      if (blockIdx.z == 0) r[(long long)z * N + nn] = 1.f / r[(long long)z * N + nn];      // nobody reads r before the next kernel
     }
   }
 }
@@ -123,8 +126,9 @@ __global__ void __launch_bounds__(256) coattn_fix_kernel(const float* __restrict
   const float4 iv = *reinterpret_cast<const float4*>(inv_r + (long long)z * N + n);
   const float4 rh = *reinterpret_cast<const float4*>(rho + (long long)z * N + n);
   auto rn = [](float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); };
+  const int cper = (C + gridDim.z - 1) / gridDim.z, c0 = blockIdx.z * cper, c1 = min(C, c0 + cper);
 #pragma unroll 4
-  for (int c = threadIdx.y; c < C; c += 8) {
+  for (int c = c0 + threadIdx.y; c < c1; c += 8) {
     const float4 g = *reinterpret_cast<const float4*>(dO + so + (long long)c * N);
     const float4 o = *reinterpret_cast<const float4*>(O + so + (long long)c * N);
     const float4 f = *reinterpret_cast<const float4*>(frames + sq + (long long)c * N);
@@ -297,16 +301,18 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
       float* rsum = (float*)w; w += align256((size_t)chunk * N * sizeof(float));
       float* delta = (float*)w; w += align256((size_t)chunk * N * sizeof(float));
       float* rho = (float*)w;
-      DCNET_CUDA(cudaMemsetAsync(rsum, 0, (size_t)nprob * N * sizeof(float), st), "coattn_bwd.memset");
-      DCNET_CUDA(cudaMemsetAsync(rho, 0, (size_t)nprob * N * sizeof(float), st), "coattn_bwd.memset");
+      // rsum | delta | rho are contiguous: one fill for the three accumulators
+      DCNET_CUDA(cudaMemsetAsync(rsum, 0, (size_t)((char*)rho - (char*)rsum) + (size_t)nprob * N * sizeof(float), st), "coattn_bwd.memset");
+      const int mblk = ceil_div(N, 128) * nprob;
+      const int zsl = mblk >= 592 ? 1 : (592 / mblk > 8 ? 8 : 592 / mblk);     // >= 4 blocks per SM
       e.epi_exp = 1; e.u = lse; e.ldu = N; e.sum = rsum; e.sum_ldz = N;
       DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
-      coattn_delta_kernel<<<dim3(ceil_div(N, 128), nprob), dim3(32, 8), 0, st>>>(dout, out, oidx, rsum, delta, C, N);
+      coattn_delta_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, oidx, rsum, delta, C, N);
       DCNET_LAUNCH_OK("coattn_bwd.delta");
       e = UmmaEpilogue{}; e.out = dP; e.ldo = N; e.so_b = NN; e.alpha = tau; e.idxA = oidx; e.idxB = kb;
       e.epi_exp = 2; e.u = delta; e.u2 = rsum; e.ldu = N; e.cc = P; e.ldcc = N; e.cc_sb = NN; e.sum = rho; e.sum_ldz = N;
       DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
-      coattn_fix_kernel<<<dim3(ceil_div(N, 128), nprob), dim3(32, 8), 0, st>>>(dout, out, frames, oidx, qa, rsum, rho, dOs, dframes, C, N);
+      coattn_fix_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, frames, oidx, qa, rsum, rho, dOs, dframes, C, N);
       DCNET_LAUNCH_OK("coattn_bwd.fix");
       UmmaOperand Gsk{dOs, C, N, N, CN, nprob, false};
       e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxC = kb; e.k_chunks = -1;

@@ -87,6 +87,22 @@ __global__ void only_obj_kernel(const float* __restrict__ raw, const float* __re
   if (obj) obj[i] = __fmul_rn(m, sim[i]);
 }
 
+// backward of only_obj / obj_score: d raw[b, 5a+4, n] = (d only_obj + d obj * sim) / 3 for the three anchors (every other channel 0),
+// d sim = d obj * only_obj
+__global__ void only_obj_bwd_kernel(const float* __restrict__ doo, const float* __restrict__ dobj, const float* __restrict__ sim,
+                                    const float* __restrict__ oo, float* __restrict__ draw, float* __restrict__ dsim, int B, int N) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const long long b = i / N;
+  const int n = (int)(i % N);
+  const float go = doo ? doo[i] : 0.f, gb = dobj ? dobj[i] : 0.f;
+  const float d = __fdiv_rn(fmaf(gb, sim[i], go), 3.f);
+  float* r = draw + b * 15 * N + n;
+#pragma unroll
+  for (int k = 0; k < 15; k++) r[(long long)k * N] = (k % 5 == 4) ? d : 0.f;
+  dsim[i] = gb * oo[i];
+}
+
 __global__ void modulate_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ sim, const float* __restrict__ loc,
                                     float* __restrict__ out, int B, int N) {
   const long long total = (long long)B * 15 * N;
@@ -595,8 +611,9 @@ __global__ void iou_loss_sums_kernel(const float* __restrict__ x, const float* _
 
 // d/dx of (-I/U) * gscale
 __global__ void iou_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, long long n, const float* __restrict__ acc,
-                                    float gscale, float* __restrict__ dx) {
+                                    const float* __restrict__ g, float gscale, float* __restrict__ dx) {
   const float I = acc[0], U = acc[1];
+  if (g) gscale *= g[0];          // upstream gradient read on the device: no host synchronisation, capturable in a CUDA graph
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float s = sigmoidf_(x[i]), tt = t[i];
     const float dI = tt, dU = 1.f - tt;
@@ -649,6 +666,14 @@ extern "C" int dcnet_only_obj(const float* raw, const float* sim, float* only_ob
   DCNET_CHECK_ARG(raw && (only_obj || obj) && (!obj || sim) && B > 0 && N > 0, "only_obj: bad arguments");
   only_obj_kernel<<<ceil_div((long long)B * N, 256), 256, 0, as_stream(stream)>>>(raw, sim, only_obj, obj, B, N);
   DCNET_LAUNCH_OK("only_obj");
+  return 0;
+}
+
+extern "C" int dcnet_only_obj_bwd(const float* d_only_obj, const float* d_obj, const float* sim, const float* only_obj, float* draw, float* dsim,
+                                  int B, int N, void* stream) {
+  DCNET_CHECK_ARG((d_only_obj || d_obj) && sim && only_obj && draw && dsim && B > 0 && N > 0, "only_obj_bwd: bad arguments");
+  only_obj_bwd_kernel<<<ceil_div((long long)B * N, 256), 256, 0, as_stream(stream)>>>(d_only_obj, d_obj, sim, only_obj, draw, dsim, B, N);
+  DCNET_LAUNCH_OK("only_obj_bwd");
   return 0;
 }
 
@@ -780,10 +805,11 @@ extern "C" int dcnet_iou_loss_sums(const float* x, const float* t, long long n, 
   return 0;
 }
 
-extern "C" int dcnet_iou_loss_bwd(const float* x, const float* t, long long n, const float* acc2, float gscale, float* dx, void* stream) {
+extern "C" int dcnet_iou_loss_bwd(const float* x, const float* t, long long n, const float* acc2, const float* g, float gscale, float* dx,
+                                  void* stream) {
   DCNET_CHECK_ARG(x && t && acc2 && dx && n >= 0, "iou_loss_bwd: bad arguments");
   if (n == 0) return 0;
-  iou_loss_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, t, n, acc2, gscale, dx);
+  iou_loss_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, t, n, acc2, g, gscale, dx);
   DCNET_LAUNCH_OK("iou_loss_bwd");
   return 0;
 }

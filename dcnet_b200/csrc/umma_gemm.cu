@@ -56,7 +56,7 @@ namespace {
 #define GEMM2_STAGES256 4
 #endif
 #ifndef GEMM2_STAGES_PAIR
-#define GEMM2_STAGES_PAIR 6        // 32 KiB per stage and CTA in pair mode
+#define GEMM2_STAGES_PAIR 6        // 32 KiB per stage and CTA in pair mode (+ 32 KiB output slots; one stage less with the 32 KiB E slots)
 #endif
 constexpr int BM = 128;
 constexpr int A_BYTES = BM * 128;    // 16 KiB: 128 rows x one 128-byte swizzle row (32 tf32 or 64 bf16 along the reduction)
@@ -269,7 +269,8 @@ struct Gemm2P {
 // CTA loads its own A tile and HALF of the B tile (no multicast: the MMA reads both halves), so a 256 x 256 output tile costs
 // (256 + 256) x K operand elements from L2 instead of 2 x (128 + 256) x K -- the tf32 GEMMs here are bound by that traffic
 // (fp32 operands: 4 bytes per element at half the bf16 MMA rate).  The leader CTA (rank 0) issues every MMA.
-template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO>
+// ESLOT (pair mode, dS epilogue only): per-warp landing slots for the E tile (one pipeline stage less)
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO, bool ESLOT = false>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapO,
@@ -285,11 +286,16 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_out = smem + STAGES * STAGE_BYTES;                 // [4 warps][NSLOT][SLOT_BYTES]
-  uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + 4 * NSLOT * SLOT_BYTES);
+  // pair mode only: [4 warps][2][SLOT_BYTES] landing slots for the E tile of the dS epilogue (TMA, same 128-byte-swizzled 32x32 boxes)
+  static_assert(!ESLOT || TWO, "E landing slots exist in pair mode only");
+  constexpr int E_BYTES = ESLOT ? 4 * 2 * SLOT_BYTES : 0;
+  uint8_t* stage_e = stage_out + 4 * NSLOT * SLOT_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_e + E_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* e_full = acc_empty + 2;        // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -302,6 +308,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // warps of BOTH CTAs have drained their halves
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], TWO ? 1 : CS); }
     for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TWO ? 8 : 4); }
+    for (int s = 0; s < 8; s++) mbar_init(&e_full[s], 1);
     fence_barrier_init();
   }
   if constexpr (TWO) cluster_sync_all();             // both CTAs are resident before the pair-wide TMEM allocation
@@ -440,7 +447,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   } else {
     // ---------------- epilogue warps 0..3: TMEM lanes 32w.. <-> output rows m0 + 32w..
     uint8_t* slots = stage_out + warp * NSLOT * SLOT_BYTES;
-    uint32_t tl = 0, chunk = 0;
+    uint32_t tl = 0, chunk = 0, echunk = 0;
     for (int t = cid; t < ngroups; t += ncl, tl++) {
       const int kc = t % p.k_chunks, tt = t / p.k_chunks;
       const int z = tt / per_z, r = tt - z * per_z;
@@ -460,8 +467,16 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       // dS epilogue: the E chunk of a thread's row (128 contiguous bytes) is fetched ONE CHUNK AHEAD -- the first one before the
       // accumulator is even complete -- so its L2 / HBM latency hides under the TMEM load, the arithmetic and the store of the
       // previous chunk (profiles/r2i: with the load inside the chunk this GEMM took 824 us against 525 us for its exp sibling)
+      // dS epilogue: the 32x32 E block of a chunk.  A thread needs ITS row (128 contiguous bytes): read directly that is 32 cache lines
+      // per warp instruction, and the epilogue became L1-wavefront bound (profiles/r2i, r2j: 825 us against 476 us for the exp
+      // sibling, with or without prefetching).  Pair mode: TMA brings the block into a per-warp swizzled slot one chunk ahead (the
+      // first one before the accumulator is complete) and each thread reads its row from shared memory; columns / rows beyond the
+      // tensor arrive as zeros.  mapO2 is the E tensor in that mode (m_split is never used together with this epilogue).
+      const bool e_tma = ESLOT && p.epi_exp == 2;
+      uint8_t* eslots = stage_e + warp * 2 * SLOT_BYTES;
+      uint64_t* ebar = e_full + warp * 2;
       float4 ecur[8];
-      const float* erow = (p.epi_exp == 2 && row_ok) ? p.cc + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
+      const float* erow = (p.epi_exp == 2 && row_ok && !e_tma) ? p.cc + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
       auto load_e = [&](int c, float4 (&dst)[8]) {
         const int nb_ = n0 + c * 32;
         if (erow && nb_ + 32 <= p.N_valid) {
@@ -469,14 +484,21 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           for (int e = 0; e < 8; e++) dst[e] = __ldg(reinterpret_cast<const float4*>(erow + nb_ + 4 * e));
         }
       };
-      if (p.epi_exp == 2) load_e(0, ecur);
+      auto tma_e = [&](int c) {          // lane 0: E block of chunk c -> slot (echunk + c) & 1
+        const uint32_t k = echunk + (uint32_t)c;
+        mbar_expect_tx(&ebar[k & 1u], SLOT_BYTES);
+        tma_load_3d(eslots + (k & 1u) * SLOT_BYTES, &mapO2, &ebar[k & 1u], n0 + c * 32, row0, z);
+      };
+      if (e_tma) { if (lane == 0) tma_e(0); }
+      else if (p.epi_exp == 2) load_e(0, ecur);
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
       if (threadIdx.x == 0) GTRACE(tl, 4);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++, chunk++) {
         float4 enext[8];
-        if (p.epi_exp == 2 && c + 1 < BN / 32) load_e(c + 1, enext);
+        if (e_tma) { if (lane == 0 && c + 1 < BN / 32) tma_e(c + 1); }
+        else if (p.epi_exp == 2 && c + 1 < BN / 32) load_e(c + 1, enext);
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + (uint32_t)(c * 32), v);
         tmem_ld_wait();
@@ -484,8 +506,19 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (p.epi_exp == 1) {
 #pragma unroll
           for (int e = 0; e < 32; e++) v[e] = tf32_rn(__expf(fmaf(p.alpha, v[e], -bias)));
+        } else if (e_tma) {
+          // dS = tau (dP - delta) E / r : per-row delta (bias) and tau / r (rowmul)
+          const uint32_t k = echunk + (uint32_t)c;
+          mbar_wait(&ebar[k & 1u], (k >> 1) & 1u);
+          const uint8_t* er = eslots + (k & 1u) * SLOT_BYTES + lane * 128;
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const float4 q = *reinterpret_cast<const float4*>(er + ((e ^ (lane & 7)) * 16));
+            v[4 * e] = tf32_rn((v[4 * e] - bias) * rowmul * q.x); v[4 * e + 1] = tf32_rn((v[4 * e + 1] - bias) * rowmul * q.y);
+            v[4 * e + 2] = tf32_rn((v[4 * e + 2] - bias) * rowmul * q.z); v[4 * e + 3] = tf32_rn((v[4 * e + 3] - bias) * rowmul * q.w);
+          }
         } else if (p.epi_exp == 2) {
-          // dS = tau (dP - delta) E / r : E tile from global (row-contiguous 128 B per thread), per-row delta (bias) and tau / r (rowmul)
+          // same from global memory (single-CTA tiles: no room for the landing slots)
           if (row_ok && nb < p.N_valid) {
             if (nb + 32 <= p.N_valid) {
 #pragma unroll
@@ -582,6 +615,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           tma_store_commit();
         }
       }
+      if (e_tma) echunk += BN / 32;
       tc_fence_before();
       __syncwarp();
       if (threadIdx.x == 0) GTRACE(tl, 5);
@@ -605,12 +639,12 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
 }
 
-template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO = false>
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO = false, bool ESLOT = false>
 int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
                  const Gemm2P& p, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_BYTES + (TWO ? BN / 2 : BN) * 128) + 4 * GEMM2_NSLOT * 32 * 128 + 1024 + 256;
+  constexpr int smem = STAGES * (A_BYTES + (TWO ? BN / 2 : BN) * 128) + 4 * GEMM2_NSLOT * 32 * 128 + (ESLOT ? 4 * 2 * 32 * 128 : 0) + 1024 + 256;
   static_assert(smem <= 232448, "umma_gemm2: shared memory budget");
-  auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB, CS, TWO>;
+  auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB, CS, TWO, ESLOT>;
   DCNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "umma_gemm2.attr");
   const int mgroups = (p.tiles_m + CS - 1) / CS;
   const int ngroups = mgroups * (p.ntiles / p.tiles_m) * p.k_chunks;
@@ -646,6 +680,9 @@ template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
 int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
                 const Gemm2P& p, int cs, cudaStream_t st) {
   if constexpr (BN == 256 && EB == 4) {
+    if constexpr (A_MN && B_MN) {      // the dS epilogue belongs to dP = dO^T Fb: both operands MN-major
+      if (cs == -2 && p.epi_exp == 2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR - 1, EB, 2, true, true>(ma, mb, mb2, mo, mo2, p, st);
+    }
     if (cs == -2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR, EB, 2, true>(ma, mb, mb2, mo, mo2, p, st);
   }
   if (cs == 4) return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 4>(ma, mb, mb2, mo, mo2, p, st);
@@ -768,6 +805,11 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     int r = make_tmap(&mo, e.out, 4, (uint64_t)N, rows1, nbo, (uint64_t)e.ldo, q.out_batched ? (uint64_t)e.so_b : rows1 * (uint64_t)e.ldo, 32, 32);
     if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled(out) failed (%d)", r);
     mo2 = mo;
+    if (e.epi_exp == 2) {
+      DCNET_CHECK_ARG(e.m_split == 0 && al16(e.cc) && e.ldcc % 4 == 0 && e.cc_sb % 4 == 0, "umma_gemm: dS epilogue: E must be TMA-addressable, no m_split");
+      r = make_tmap(&mo2, e.cc, 4, (uint64_t)N, (uint64_t)M, e.cc_sb ? 65535u : 1u, (uint64_t)e.ldcc, e.cc_sb ? (uint64_t)e.cc_sb : (uint64_t)M * e.ldcc, 32, 32);
+      if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled(E) failed (%d)", r);
+    }
     if (e.m_split > 0) {
       const uint64_t rows2 = (uint64_t)(M - e.m_split);
       r = make_tmap(&mo2, e.out2, 4, (uint64_t)N, rows2, nbo, (uint64_t)e.ldo2, q.out_batched ? (uint64_t)e.so_b2 : rows2 * (uint64_t)e.ldo2, 32, 32);

@@ -71,6 +71,7 @@ class HotPath(nn.Module):
     side_priority = (0, 0)
     aux_priority = (-1, -1)
     terms_on_aux = True
+    finest_first = False     # measured: 7.96 ms against 7.85 ms (C3), 1.475 against 1.439 (C2), profiles/r2l_variants.txt
 
     def _run_scales(self, chain):
         if not self.scale_streams:
@@ -84,14 +85,14 @@ class HotPath(nn.Module):
                 torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         outs = [None, None, None]
         fork = cur.record_event()
-        # the finest scale's chain is the critical path of the step: issue it first so that its kernels are first in line for the
-        # SMs (profiles/r2i_timeline_c3.txt: issued last, its first GEMM waited 300 us behind the coarsest scale's exact-fp32 conv)
-        outs[2] = chain(2)
-        for s in (1, 0):
+        for s in (0, 1):
             st = self._side[s]
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 outs[s] = chain(s)
+        # (issuing the finest chain first was measured and changes nothing, profiles/r2j_timeline_c3.txt: its first GEMM then shares
+        # the SMs with the coarsest scale's exact-fp32 conv instead of waiting behind it)
+        outs[2] = chain(2)
         if getattr(self, "_aux_pending", False):
             for aux in self._aux:
                 cur.wait_stream(aux)
@@ -151,10 +152,16 @@ class HotPath(nn.Module):
             terms = self._branch(0, lambda: [net.fuse_terms(s, flang, coords[s]) for s in range(3)], flang)
             ev_terms = self._aux[0].record_event() if self.scale_streams else None
 
+        # The finest scale's chain is the critical path of the step; the coarsest scale opens with an exact-fp32 CUDA-core conv whose
+        # 256 CTAs hold the SMs for ~350 us at 416x416 (profiles/r2k_timeline_c3.txt: the finest scale's first tcgen05 GEMM waited
+        # behind it).  The finest visual mapping is therefore issued BEFORE the fork: the other chains start once it is done and
+        # have ~1 ms of slack to the end of the forward anyway.
+        fv_first = net.map_visual_scale(raw[2], 2) if self.finest_first else None
+
         def chain(s):
             """everything of one pyramid scale: a2 -> (a4, a11 on the coarsest scale) -> a5/a6/a9 -> a7/a8 -> a10"""
             o = {}
-            o['fv'] = net.map_visual_scale(raw[s], s)
+            o['fv'] = fv_first if (s == 2 and fv_first is not None) else net.map_visual_scale(raw[s], s)
             if s == 0:
                 # the two sampling blocks and their InfoNCE losses only need fvisu[0]: a branch of their own next to the
                 # co-attention / fusion chain of this scale (forward and, through autograd, backward)

@@ -707,10 +707,12 @@ class _OnlyObj(torch.autograd.Function):
     def backward(ctx, doo, dobj):
         sim, oo = ctx.saved_tensors
         B, N = sim.shape
-        d = (doo + dobj * sim) / 3.0
-        draw = torch.zeros(B, 3, 5, N, device=sim.device, dtype=F32)
-        draw[:, :, 4] = d[:, None]
-        return draw.view(B, 15, N), dobj * oo
+        doo = _c(doo, name="d only_obj") if doo is not None else None
+        dobj = _c(dobj, name="d obj_score") if dobj is not None else None
+        draw = torch.empty(B, 15, N, device=sim.device, dtype=F32)
+        dsim = torch.empty_like(sim)
+        _lib.call("dcnet_only_obj_bwd", _p(doo), _p(dobj), _p(sim), _p(oo), _p(draw), _p(dsim), B, N, _st())
+        return draw, dsim
 
 
 def only_obj(raw, sim):
@@ -793,7 +795,7 @@ class _IoULoss(torch.autograd.Function):
     def backward(ctx, g):
         x, t, acc = ctx.saved_tensors
         dx = torch.empty_like(x)
-        _lib.call("dcnet_iou_loss_bwd", _p(x), _p(t), x.numel(), _p(acc), float(g.item()) * ctx.scale, _p(dx), _st())
+        _lib.call("dcnet_iou_loss_bwd", _p(x), _p(t), x.numel(), _p(acc), _p(_c(g.reshape(1).float(), name="grad")), ctx.scale, _p(dx), _st())
         return dx, None, None
 
 

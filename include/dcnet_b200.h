@@ -253,6 +253,10 @@ DCNET_API int dcnet_build_target(const float* bbox, int B, int size, float ancho
 /* ---- a10: objectness / confidence modulation (model/DCNet_model.py:545-552, :612-621) -------------------
  * raw [B,15,N] -> only_obj [B,N] = mean_a raw[b,5a+4,n]; obj [B,N] = only_obj*sim;  (either out may be NULL)  */
 DCNET_API int dcnet_only_obj(const float* raw, const float* sim, float* only_obj, float* obj, int B, int N, void* stream);
+/* backward of dcnet_only_obj: draw [B,15,N] (confidence channels 5a+4 = (d_only_obj + d_obj sim)/3, the rest 0), dsim = d_obj only_obj;
+ * either incoming gradient may be NULL                                                                     */
+DCNET_API int dcnet_only_obj_bwd(const float* d_only_obj, const float* d_obj, const float* sim, const float* only_obj, float* draw, float* dsim,
+                                 int B, int N, void* stream);
 /* out = raw with channels 5a+4 multiplied by sim*loc */
 DCNET_API int dcnet_modulate_conf_fwd(const float* raw, const float* sim, const float* loc, float* out, int B, int N, void* stream);
 DCNET_API int dcnet_modulate_conf_bwd(const float* raw, const float* sim, const float* loc, const float* dout,
@@ -316,7 +320,9 @@ DCNET_API int dcnet_yolo_layer_decode(const float* x, float* out, int B, int A, 
 
 /* ---- a21: IoULoss (utils/losses.py:26-34): acc[0] += sum(sig(x) t), acc[1] += sum(sig(x)+t-sig(x) t) -- */
 DCNET_API int dcnet_iou_loss_sums(const float* x, const float* t, long long n, float* acc2, void* stream);
-DCNET_API int dcnet_iou_loss_bwd(const float* x, const float* t, long long n, const float* acc2, float gscale, float* dx, void* stream);
+/* dx = g[0] * gscale * d(-I/U)/dx; g (device scalar, may be NULL = 1) is the upstream gradient: read on the device, no host sync */
+DCNET_API int dcnet_iou_loss_bwd(const float* x, const float* t, long long n, const float* acc2, const float* g, float gscale, float* dx,
+                                 void* stream);
 
 /* ---- host: exact emulation of CPython's random.sample() stream (model/DCNet_model.py:87, :413) --------
  * state625: the 625 uint32 words of random.getstate()[1] (624 MT19937 words + position), updated in place so

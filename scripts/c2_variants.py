@@ -16,6 +16,9 @@ def run(name):
 
 
 run("default")
+HotPath.finest_first = False
+run("finest mapping inside its chain (after the fork)")
+HotPath.finest_first = True
 HotPath.terms_on_aux = False
 run("fusion terms inline")
 HotPath.terms_on_aux = True
@@ -25,6 +28,3 @@ ops.FUSED_MIN_N = 256
 _lib.lib().dcnet_gemm_select(6)
 run("no CTA pairs")
 _lib.lib().dcnet_gemm_select(0)
-_lib.lib().dcnet_coattn_bwd_l2_budget(64 << 20)
-run("co-attention backward in L2-resident chunks (64 MiB)")
-_lib.lib().dcnet_coattn_bwd_l2_budget(0)

@@ -266,3 +266,52 @@ def test_test_time_clip_model_vs_oracle(n_frame, b, precision):
         for s in range(3):
             assert out[i][s].shape == o[n][s].shape
             assert rel(out[i][s], o[n][s]) < max(tol, 5e-4 if n in ('loc_score', 'outbox') else 0), (n, s, rel(out[i][s], o[n][s]))
+
+
+@pytest.mark.parametrize("size", [256, 416])
+def test_location_branch_rank8_training_form_on_gpu(size):
+    """SURVEY 8(f) row 2, training: the location branch in its rank-8 form (no [B,SN,SN] relation tensor: 1.6 GB for 32 images at
+    416x416, no SN-long GEMM) against the materialised form of model/DCNet_model.py:556-603 on the GPU in fp32 -- scores, input and
+    parameter gradients, running statistics."""
+    synth.seed_all(5)
+    net = grounding_model(corpus=list(range(100)), emb_size=512, visumodel=StubBackbone(), size=size).to(DEV).train()
+    grids = [size // 32, size // 16, size // 8]
+    B, T = 4, 9
+    g = torch.Generator().manual_seed(6)
+    from dcnet_b200 import ops
+    coords = [ops.coord_map(n, n, DEV).flatten(1) for n in grids]
+    context = torch.randn(B, T, 1024, generator=g).to(DEV)
+    embedded = torch.randn(B, T, net.loc_text_embedding[0].out_features, generator=g).to(DEV)
+    word_id = torch.randint(1, 100, (B, T), generator=g).to(DEV)
+    word_id[1, 5:] = 0
+    outs = []
+    for flag in (False, True):
+        m = copy.deepcopy(net)
+        m.rank8_location_train = flag
+        obj = [torch.rand(B, n * n, generator=torch.Generator().manual_seed(8 + n)).to(DEV).requires_grad_() for n in grids]
+        ctx = context.clone().requires_grad_()
+        score = m.location_branch(coords, obj, ctx, embedded, word_id)
+        (score * torch.linspace(0.5, 1.5, score.shape[1], device=DEV)).sum().backward()
+        grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+        stats = {n: b.clone() for n, b in m.named_buffers() if n.startswith(("loc_embedding", "loc_text_embedding")) and b.dtype.is_floating_point}
+        outs.append((score.detach(), grads, [o.grad for o in obj], ctx.grad, stats))
+    (s0, g0, o0, c0, st0), (s1, g1, o1, c1, st1) = outs
+    assert rel(s1, s0) < 2e-5, rel(s1, s0)
+    assert set(g0) == set(g1)
+    # biases in front of a BatchNorm (loc_embedding.0, loc_text_embedding.0) and the softmax-shift bias loc_attn.fc.bias have an
+    # analytically zero gradient: both forms only produce round-off there
+    ZERO = ("loc_embedding.0.bias", "loc_text_embedding.0.bias", "loc_attn.fc.bias")
+    errs = {k: rel(g1[k], g0[k]) for k in g0 if k not in ZERO}
+    errs.update({"obj[%d]" % i: rel(a, b) for i, (a, b) in enumerate(zip(o1, o0))})
+    errs["context"] = rel(c1, c0)
+    print("rank-8 location training form at %d: worst gradient difference to the materialised form %.2e (%s)" % (
+        size, max(errs.values()), max(errs, key=errs.get)))
+    scale = max(float(v.norm()) for v in g0.values())
+    for k in ZERO:
+        assert float(g1[k].norm()) < 1e-3 * scale and float(g0[k].norm()) < 1e-3 * scale, k
+    # fp32, min-max normalised scores, two orders of summation: 5e-3; the BatchNorm1d(8) bias of loc_embedding is an ill-conditioned
+    # sum (4-8 % between the two orders, 1e-9 in fp64)
+    bad = {k: e for k, e in errs.items() if e > (0.15 if k.startswith("loc_embedding.1") else 5e-3)}
+    assert not bad, bad
+    for k in st0:
+        assert rel(st1[k], st0[k]) < 1e-4, k
