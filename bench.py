@@ -577,9 +577,11 @@ def measure_hotpath(key, steps, warmup, rank, world, local, dev, dist, xneg=Fals
 # ----------------------------------------------------------------------------------------------------------------------
 # DRAM traffic per launch of the two tensor-core kernels, from `ncu --set full` captures of the same instances
 # (dram__bytes_read.sum + dram__bytes_write.sum); (size, pairs) -> (bytes, source file)
-NCU_TRAFFIC_GEMM = {}
-NCU_TRAFFIC_GEMM_S = {(256, 8): (88.2e6, "profiles/r1w_ncu_full_umma_gemm2.txt")}
-NCU_TRAFFIC_COATTN = {(256, 8): (16.9e6, "profiles/r1w_ncu_full_coattn_fused.txt")}
+NCU_TRAFFIC_GEMM = {(416, 16): (1.465118e9 + 162.2592e6, "profiles/r2n_ncu_full_gemm_cn.txt")}
+NCU_TRAFFIC_GEMM_S = {(416, 16): (354.53568e6 + 883.129088e6, "profiles/r2n_ncu_full_gemm_s.txt"), (256, 8): (88.2e6, "profiles/r1w_ncu_full_umma_gemm2.txt")}
+NCU_TRAFFIC_COATTN = {(416, 16): (89.010432e6 + 127.560192e6, "profiles/r2n_ncu_full_coattn_fwd.txt"), (256, 8): (16.9e6, "profiles/r1w_ncu_full_coattn_fused.txt")}
+NCU_TRAFFIC_HBM = {(416, 16): {"bn_act_fwd": (177.355264e6 + 136.50944e6, "profiles/r2n_ncu_full_bn_fwd.txt"),
+                              "bn_act_bwd_reduce": (367.188224e6 + 145.653248e6, "profiles/r2n_ncu_full_bn_bwd.txt")}}
 
 
 def kernel_rooflines(key, dev):
@@ -689,8 +691,15 @@ def kernel_rooflines(key, dev):
     # what a plain device copy of the same footprint reaches in this harness (torch copy_: read + write of one map)
     t_copy = timed_sets([(lambda i=i: ys[i].copy_(frs[i])) for i in range(NSET)])
     copy_gbs = 2 * map_bytes / (t_copy * 1e-3) / 1e9
+    def ncu_hbm(k):
+        for name, v in NCU_TRAFFIC_HBM.get((size, pairs), {}).items():
+            if k.startswith(name + "_kernel"):
+                return v
+        return (None, None)
     roof_hbm = [dict(bound="hbm", kernel=k, achieved=b_ / (t * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s", frac=b_ / (t * 1e-3) / 1e9 / peaks["hbm"],
-                     ms=t, bytes=b_, traffic=None, copy_same_size_gbs=copy_gbs) for k, (b_, t) in hbm.items()]
+                     ms=t, bytes=b_, traffic=ncu_hbm(k)[0],
+                     traffic_source=(ncu_hbm(k)[1] + ": dram__bytes_read.sum + dram__bytes_write.sum") if ncu_hbm(k)[1] else None,
+                     copy_same_size_gbs=copy_gbs) for k, (b_, t) in hbm.items()]
     del frs, ys, dvs, yin
     gc.collect()
     torch.cuda.empty_cache()

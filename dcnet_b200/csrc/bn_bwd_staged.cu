@@ -97,11 +97,15 @@ bn_bwd_reduce_staged_kernel(const BwdP p) {
   }
   __syncthreads();
 
+  // every CTA walks a CONTIGUOUS range of (image, tile) items: consecutive items mostly belong to the same image, so the text-vector
+  // gradients of an image accumulate in registers and leave with one round of atomics per image instead of one per tile
+  const int per_cta = (p.items + gridDim.x - 1) / gridDim.x;
+  const int it_begin = blockIdx.x * per_cta, it_end = min(p.items, it_begin + per_cta);
   if (warp >= NCOMPUTE / 32) {
     // ------------------------------------------------------------ producers: 64 threads x 16-byte chunks
     const int pt = threadIdx.x - NCOMPUTE;
     uint32_t k = 0;
-    for (int it = blockIdx.x; it < p.items; it += gridDim.x, k++) {
+    for (int it = it_begin; it < it_end; it++, k++) {
       const int s = k % NST;
       const uint32_t ph = (k / NST) & 1u;
       mbar_wait(&empty[s], ph ^ 1u);
@@ -136,15 +140,32 @@ bn_bwd_reduce_staged_kernel(const BwdP p) {
   float acc_dv[OUTN], acc_dvz[OUTN];
 #pragma unroll
   for (int o = 0; o < OUTN; o++) acc_dv[o] = acc_dvz[o] = 0.f;
+  float acc_fa[2][OUTN];
+#pragma unroll
+  for (int o = 0; o < OUTN; o++) acc_fa[0][o] = acc_fa[1][o] = 0.f;
+  auto flush_fa = [&](int b) {
+    if (b < 0 || !(p.fa && p.dfa)) return;
+#pragma unroll
+    for (int which = 0; which < 2; which++) {
+      float* dst = which == 0 ? p.dfa + (long long)b * C
+                              : (p.fa_neg ? (p.dfa_neg ? p.dfa_neg + (long long)b * C : nullptr) : p.dfa + (long long)(p.B - 1 - b) * C);
+#pragma unroll
+      for (int o = 0; o < OUTN; o++) {
+        if (dst) atomicAdd(dst + g + NG * (ridx + o), acc_fa[which][o]);
+        acc_fa[which][o] = 0.f;
+      }
+    }
+  };
   uint32_t k = 0;
   int cur_b = -1;
-  for (int it = blockIdx.x; it < p.items; it += gridDim.x, k++) {
+  for (int it = it_begin; it < it_end; it++, k++) {
     const int s = k % NST;
     const uint32_t ph = (k / NST) & 1u;
     const int b = it / p.tiles, n0 = (it - b * p.tiles) * PT;
     const int n = n0 + pp;
     const bool valid = n < p.N;
     if (p.fa && b != cur_b) {
+      flush_fa(cur_b);
       // text vectors of this image (and of its negative partner)
       compute_sync();      // every thread is done with the previous image's vectors
       for (int c = threadIdx.x; c < C; c += NCOMPUTE) {
@@ -189,7 +210,7 @@ bn_bwd_reduce_staged_kernel(const BwdP p) {
       dotn = t1 * inv * inv;
     }
     if (p.fa && p.dfa) {
-#pragma unroll 1
+#pragma unroll
       for (int which = 0; which < 2; which++) {
         const float w = which == 0 ? ds : dn;
         float f[CPT];
@@ -199,12 +220,8 @@ bn_bwd_reduce_staged_kernel(const BwdP p) {
           f[i] = w * ((t > 0.f ? t : t * p.slope) * inv);      // w = 0 at positions beyond N
         }
         half_vec_reduce(f, lane);
-        float* dst = which == 0 ? p.dfa + (long long)b * C
-                                : (p.fa_neg ? (p.dfa_neg ? p.dfa_neg + (long long)b * C : nullptr) : p.dfa + (long long)(p.B - 1 - b) * C);
-        if (dst) {
 #pragma unroll
-          for (int o = 0; o < OUTN; o++) atomicAdd(dst + g + NG * (ridx + o), f[o]);
-        }
+        for (int o = 0; o < OUTN; o++) acc_fa[which][o] += f[o];
       }
     }
 #pragma unroll
@@ -236,6 +253,7 @@ bn_bwd_reduce_staged_kernel(const BwdP p) {
     }
     mbar_arrive(&empty[s]);
   }
+  flush_fa(cur_b);
   // channel sums of this CTA
 #pragma unroll
   for (int o = 0; o < OUTN; o++) {
@@ -264,7 +282,8 @@ int bn_bwd_reduce_staged(const float* z, const float* mean, const float* invstd,
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   DCNET_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "bn_bwd_reduce_staged.attr");
-  const int grid = p.items < sms ? p.items : sms;
+  int grid = p.items < sms ? p.items : sms;
+  grid = ceil_div(p.items, ceil_div(p.items, grid));      // no CTA with an empty item range
   bn_bwd_reduce_staged_kernel<<<grid, NCOMPUTE + NPROD, SMEM_BYTES, st>>>(p);
   DCNET_LAUNCH_OK("bn_act_bwd_reduce");
   return 0;

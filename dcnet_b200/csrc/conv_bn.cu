@@ -203,6 +203,74 @@ __global__ void __launch_bounds__(32 * G) bn_act_fwd_kernel(const float* __restr
   }
 }
 
+// Same pass with TWO consecutive positions per thread (float2): a CTA covers 64 positions x all channels, so every channel row is
+// read and written in 256-byte runs instead of 128 (fewer, longer DRAM bursts per row of the [C,N] map) with 1024 threads in flight
+// per SM.  G = 32 channel groups (warps), CPT = C / 32 channels per thread.  Needs N % 2 == 0.
+template <int CPT, int G>
+__global__ void __launch_bounds__(32 * G, 1) bn_act_fwd_v2_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float slope, int l2norm,
+                                                                float* __restrict__ y, const float* __restrict__ fa, const float* __restrict__ fa_neg,
+                                                                float* __restrict__ sim, float* __restrict__ neg_sim, int B, int N) {
+  constexpr int C = CPT * G;
+  __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
+  __shared__ float red[3][G][64];          // [..][g][pl] = first position of the lane, [..][g][32 + pl] = second (conflict-free)
+  const int b = blockIdx.y;
+  const int pl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int n = blockIdx.x * 64 + 2 * pl;
+  for (int c = threadIdx.x; c < C; c += 32 * G) {
+    const float sc = gamma[c] * invstd[c];
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - mean[c] * sc;
+    if (fa) {
+      s_fa[c] = fa[(long long)b * C + c];
+      s_fr[c] = fa_neg ? fa_neg[(long long)b * C + c] : fa[(long long)(B - 1 - b) * C + c];
+    }
+  }
+  __syncthreads();
+  const bool valid = n < N;                // N is even: both positions of a lane are valid together
+  const float* zp = z + (long long)b * C * N + n;
+  float2 v[CPT];
+  float ss0 = 0.f, ss1 = 0.f, d10 = 0.f, d11 = 0.f, d20 = 0.f, d21 = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPT; i++) {
+    const int c = g + G * i;
+    float2 a = valid ? *reinterpret_cast<const float2*>(zp + (long long)c * N) : make_float2(0.f, 0.f);
+    a.x = fmaf(a.x, s_scale[c], s_shift[c]); a.y = fmaf(a.y, s_scale[c], s_shift[c]);
+    a.x = a.x > 0.f ? a.x : a.x * slope; a.y = a.y > 0.f ? a.y : a.y * slope;
+    v[i] = a;
+    ss0 = fmaf(a.x, a.x, ss0); ss1 = fmaf(a.y, a.y, ss1);
+    if (fa) {
+      d10 = fmaf(a.x, s_fa[c], d10); d11 = fmaf(a.y, s_fa[c], d11);
+      d20 = fmaf(a.x, s_fr[c], d20); d21 = fmaf(a.y, s_fr[c], d21);
+    }
+  }
+  float inv0 = 1.f, inv1 = 1.f;
+  if (l2norm || fa) {
+    red[0][g][pl] = ss0; red[0][g][32 + pl] = ss1;
+    red[1][g][pl] = d10; red[1][g][32 + pl] = d11;
+    red[2][g][pl] = d20; red[2][g][32 + pl] = d21;
+    __syncthreads();
+    float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f, t20 = 0.f, t21 = 0.f;
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+      t00 += red[0][k][pl]; t01 += red[0][k][32 + pl];
+      t10 += red[1][k][pl]; t11 += red[1][k][32 + pl];
+      t20 += red[2][k][pl]; t21 += red[2][k][32 + pl];
+    }
+    if (l2norm) { inv0 = 1.f / fmaxf(sqrtf(t00), 1e-12f); inv1 = 1.f / fmaxf(sqrtf(t01), 1e-12f); }
+    if (fa && g == 0 && valid) {
+      *reinterpret_cast<float2*>(sim + (long long)b * N + n) = make_float2(t10 * inv0, t11 * inv1);
+      *reinterpret_cast<float2*>(neg_sim + (long long)b * N + n) = make_float2(t20 * inv0, t21 * inv1);
+    }
+  }
+  if (valid) {
+    float* yp = y + (long long)b * C * N + n;
+#pragma unroll
+    for (int i = 0; i < CPT; i++) *reinterpret_cast<float2*>(yp + (long long)(g + G * i) * N) = make_float2(v[i].x * inv0, v[i].y * inv1);
+  }
+}
+
 // Sum over the 32 lanes of a warp of a per-lane vector v[0..CPT): recursive halving -- at every step a lane keeps one half of
 // its current values and hands the other half to its partner, so the whole reduction costs CPT-2 shuffles instead of 5*CPT.
 // On return lane L holds in v[0..CPT/32) the totals of original indices  vec_reduce_index(L) + {0 .. CPT/32-1}.
@@ -667,6 +735,9 @@ extern "C" int dcnet_bn_eval_stats(const float* running_mean, const float* runni
   return 0;
 }
 
+// two positions per thread in bn_act_fwd: measured SLOWER than one (126 us against 87 us at C3, 0.43 against 0.62 of the copy
+// bandwidth, profiles/r2o): kept behind dcnet_bn_bwd_select(3) only
+static int g_bn_fwd_v2 = 0;
 extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                 float slope, int l2norm, float* y, const float* fa, const float* fa_neg, float* sim, float* neg_sim,
                                 int B, int C, int N, void* stream) {
@@ -675,7 +746,12 @@ extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* 
   DCNET_CHECK_ARG(!fa || (sim && neg_sim), "bn_act_fwd: fa given without sim/neg_sim outputs");
   DCNET_CHECK_ARG(B <= 65535, "bn_act_fwd: B too large");
   dim3 grid(ceil_div(N, 32), B);
-  if (C == 512)
+  auto al8 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 8 == 0; };
+  if (C == 512 && g_bn_fwd_v2 && N % 2 == 0 && (long long)B * N >= 64 * 148 * 2 && al8(z) && al8(y) && (!fa || (al8(sim) && al8(neg_sim)))) {
+    // large maps: two positions per thread, 256-byte runs per channel row
+    bn_act_fwd_v2_kernel<16, 32><<<dim3(ceil_div(N, 64), B), 1024, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg,
+                                                                                       sim, neg_sim, B, N);
+  } else if (C == 512)
     bn_act_fwd_kernel<BNF_CPT, 512 / BNF_CPT><<<grid, 32 * (512 / BNF_CPT), 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
   else
     bn_act_fwd_kernel<32, 8><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
@@ -687,8 +763,8 @@ int bn_bwd_reduce_staged(const float* z, const float* mean, const float* invstd,
                       int l2norm, const float* dy, const float* fa, const float* fa_neg, const float* dsim, const float* dneg,
                       float* dv, float* sum_dv, float* sum_dvz, float* dfa, float* dfa_neg, int B, int Cc, int N, cudaStream_t st);
 static bool g_bn_bwd_no_staged = false;
-// test / bring-up knob: 1 = always use the register-staged kernel
-extern "C" int dcnet_bn_bwd_select(int variant) { g_bn_bwd_no_staged = (variant == 1); return 0; }
+// test / bring-up knob: 1 = always use the register-staged backward kernel; 3 = two positions per thread in the forward kernel
+extern "C" int dcnet_bn_bwd_select(int variant) { g_bn_bwd_no_staged = (variant == 1); g_bn_fwd_v2 = (variant == 3) ? 1 : 0; return 0; }
 
 extern "C" int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                        float slope, int l2norm, const float* dy, const float* fa, const float* fa_neg, const float* dsim,

@@ -574,7 +574,9 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restric
       else if (at == 2) r = __fmul_rn(__fmul_rn(expf(r), aw), stride);
       else if (at == 3) r = __fmul_rn(__fmul_rn(expf(r), ah), stride);
       else r = sigmoidf_(r);
-      ytile[at * LD + lane * 4 + e] = r;
+      // cell 4 lane + e of the tile lives in column 32 e + lane: a warp's 32 stores of one e hit 32 different banks (the natural
+      // column 4 lane + e is a 4-way conflict)
+      ytile[at * LD + e * 32 + lane] = r;
     }
   }
   __syncthreads();
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restric
     for (int e = 0; e < 4; e++) {
       const int ii = min(i + e, total - 1);
       const int cl = ii / nattr, at = ii - cl * nattr;
-      r[e] = ytile[at * LD + cl];
+      r[e] = ytile[at * LD + (cl & 3) * 32 + (cl >> 2)];
     }
     if (ovec && i + 3 < total) *reinterpret_cast<float4*>(op + i) = make_float4(r[0], r[1], r[2], r[3]);
     else

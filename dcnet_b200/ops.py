@@ -509,8 +509,10 @@ class _CoAttn(torch.autograd.Function):
         staged = None
         ctx.precision = precision
         if precision == EXACT_FWD_TF32_BWD:
-            precision = EXACT_FP32           # exact fp32 forward (lse included); the backward contractions run as tf32 on tcgen05
-            ctx.precision = TENSOR_TF32
+            # exact fp32 forward (lse included); the backward is the tcgen05 one with fused epilogues, which recomputes its own tf32
+            # logits and re-normalises them (the saved lse is only a shift there, so the two precisions cannot disagree about P)
+            precision = EXACT_FP32
+            ctx.precision = TENSOR_BF16_FUSED
         if precision == TENSOR_BF16_FUSED and N < FUSED_MIN_N:
             # short key axes: with few keys the rounding of bf16 (and tf32) operands does not average out -- 1.6e-3 (1.15e-3) on the
             # worst of 112 problems at N = 64, bar 1e-3 -- and the contraction is tiny: exact fp32 forward; the backward is the
