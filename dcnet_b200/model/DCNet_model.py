@@ -190,9 +190,15 @@ class grounding_model(nn.Module):
         return self.mapping_visu._modules[str(s)].fused(raw_s.flatten(2), l2norm=True, precision=p0 if s == 0 else self.precision)
 
     def correspondence_scale(self, fv_s, s, fa, fa_neg=None):
+        """a5 + a6 + a9 of one scale as one autograd node (ops.correspondence): co-attention both directions, corr_conv on
+        [fvisu | attention] without a cat, channel L2 norm, pixel-to-text dots"""
         qa, kb = self._pair_index(fv_s.shape[0], fv_s.device)
-        attn = ops.coattention(fv_s, qa, kb, tau=self.temperature, precision=self.coattn_precision)
-        return self.corr_conv._modules[str(s)][0].fused(fv_s, x2=attn, fa=fa, l2norm=True, precision=self.precision, fa_neg=fa_neg)
+        m = self.corr_conv._modules[str(s)][0]
+        bn = m.bn
+        return ops.correspondence(fv_s, qa, kb, m.conv.weight.view(m.conv.weight.shape[0], -1), bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                  self.training, fa=fa, fa_neg=fa_neg, tau=self.temperature, cprecision=self.coattn_precision,
+                                  momentum=bn.momentum, eps=bn.eps, slope=m.slope, precision=self.precision,
+                                  num_batches_tracked=bn.num_batches_tracked)
 
     def fuse_terms(self, s, flang, coords_s, kv=512):
         """the text / coordinate terms of scale s on their own (ops.fuse_terms): for callers that issue them ahead of the chain"""
@@ -241,8 +247,7 @@ class grounding_model(nn.Module):
         qa, kb = self._pair_index(B, fv[0].device)
         corr, sim, neg_sim = [], [], []
         for s in range(3):
-            attn = ops.coattention(fv[s], qa, kb, tau=self.temperature, precision=self.coattn_precision)
-            y, sm, ng = self.corr_conv._modules[str(s)][0].fused(fv[s], x2=attn, fa=fa, l2norm=True, precision=self.precision, fa_neg=fa_neg)
+            y, sm, ng = self.correspondence_scale(fv[s], s, fa, fa_neg)
             corr.append(y); sim.append(sm); neg_sim.append(ng)
         return corr, sim, neg_sim
 

@@ -536,12 +536,14 @@ class _CoAttn(torch.autograd.Function):
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, accumulate_into=None):
+        """accumulate_into (used by _Correspondence): a [F,C,N] gradient buffer that already holds the other consumers' contribution to
+        d frames -- the kernels add into it (TMA reduce-add) instead of into a zero-filled tensor that autograd would add afterwards"""
         frames, qa, kb, oidx, out, lse = ctx.saved_tensors
         F_, C, N = frames.shape
         nprob = qa.numel()
         dout = _c(dout, name="dout")
-        dframes = torch.zeros_like(frames)
+        dframes = torch.zeros_like(frames) if accumulate_into is None else accumulate_into
         nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, ctx.precision)
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
         _lib.call("dcnet_coattn_bwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout), _p(dframes),
@@ -564,7 +566,7 @@ def coattn_fused(staged, shape, qa, kb, oidx=None, n_out=None, tau=10.0, out=Non
     F_, C, N = shape
     qa, kb = _c(qa, torch.int32, "index"), _c(kb, torch.int32, "index")
     nprob = qa.numel()
-    oidx = torch.arange(nprob, device=qa.device, dtype=torch.int32) if oidx is None else _c(oidx, torch.int32, "index")
+    oidx = _iota(nprob, qa.device) if oidx is None else _c(oidx, torch.int32, "index")
     n_out = nprob if n_out is None else n_out
     if out is None:
         out = torch.empty(n_out, C, N, device=staged.device, dtype=F32)
@@ -574,10 +576,77 @@ def coattn_fused(staged, shape, qa, kb, oidx=None, n_out=None, tau=10.0, out=Non
     return out, lse
 
 
+_IOTA = {}
+
+
+def _iota(n, device):
+    """cached arange(n) int32 (identity output map of the co-attention problems): no kernel launch per call"""
+    key = (int(n), str(device))
+    if key not in _IOTA:
+        _IOTA[key] = torch.arange(n, device=device, dtype=torch.int32)
+    return _IOTA[key]
+
+
+class _FakeCtx:
+    """stands in for an autograd ctx when one Function's forward / backward body is run inside another Function"""
+
+    def __init__(self, needs_input_grad=()):
+        self.saved_tensors = ()
+        self.needs_input_grad = needs_input_grad
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+
+class _Correspondence(torch.autograd.Function):
+    """a5 + a6 (+ a9) as ONE autograd node: attn = coattention(fv), y = corr_conv([fv | attn]) (+ pixel-to-text dots).  fv feeds both
+    the co-attention and the conv; as two nodes autograd materialises two [B,C,N] gradients of fv (one of them into a zero-filled tensor)
+    and adds them -- at 416x416 that is a 177 MB fill and a 531 MB add on the critical path of the finest scale.  Here the conv's data
+    gradient is written first and the co-attention backward reduce-adds into the same buffer."""
+
+    @staticmethod
+    def forward(ctx, fv, qa, kb, tau, cprecision, weight, gamma, beta, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope,
+                precision, nbt):
+        c1, c2 = _FakeCtx(), _FakeCtx()
+        nprob = qa.numel()
+        attn = _CoAttn.forward(c1, fv, qa, kb, _iota(nprob, qa.device), nprob, tau, cprecision)
+        out = _ConvBNAct.forward(c2, fv, attn, weight, gamma, beta, None, None, fa, fa_neg, running_mean, running_var, training, momentum, eps,
+                                 slope, True, precision, nbt)
+        ctx.n1 = len(c1.saved_tensors)
+        ctx.save_for_backward(*c1.saved_tensors, *c2.saved_tensors)
+        ctx.c1_attrs = (c1.tau, c1.precision)
+        ctx.c2_cfg = c2.cfg
+        return out
+
+    @staticmethod
+    def backward(ctx, dy, dsim=None, dneg=None):
+        saved = ctx.saved_tensors
+        nig = ctx.needs_input_grad
+        # conv node first: inputs (x1 = fv, x2 = attn, weight, gamma, beta, u, cc, fa, fa_neg, ...)
+        c2 = _FakeCtx((True, True, nig[5], nig[6], nig[7], False, False, nig[8], nig[9]) + (False,) * 11)
+        c2.saved_tensors = saved[ctx.n1:]
+        c2.cfg = ctx.c2_cfg
+        g2 = _ConvBNAct.backward(c2, dy, dsim, dneg)
+        dfv, dattn, dW, dgamma, dbeta, dfa, dfa_neg = g2[0], g2[1], g2[2], g2[3], g2[4], g2[7], g2[8]
+        c1 = _FakeCtx()
+        c1.saved_tensors = saved[:ctx.n1]
+        c1.tau, c1.precision = ctx.c1_attrs
+        _CoAttn.backward(c1, dattn, accumulate_into=dfv)
+        return (dfv, None, None, None, None, dW, dgamma, dbeta, dfa, dfa_neg, None, None, None, None, None, None, None, None)
+
+
+def correspondence(fv, qa, kb, weight, gamma, beta, running_mean, running_var, training, fa=None, fa_neg=None, tau=10.0, cprecision=TENSOR_BF16_FUSED,
+                   momentum=0.999, eps=1e-5, slope=0.0, precision=TENSOR_TF32, num_batches_tracked=None):
+    """fv [B,C,N] (pairs = consecutive frames via qa / kb) -> corr_feat [B,Cout,N] (channel-normalised) or (corr_feat, sim, neg_sim) with fa.
+    weight [Cout, 2C]: corr_conv applied to [fv | co-attention(fv)] (model/DCNet_model.py:449-469, :525-535)."""
+    return _Correspondence.apply(fv, qa, kb, float(tau), int(cprecision), weight, gamma, beta, fa, fa_neg, running_mean, running_var, bool(training),
+                                 float(momentum), float(eps), float(slope), int(precision), num_batches_tracked if training else None)
+
+
 def coattention(frames, qa, kb, oidx=None, n_out=None, tau=10.0, precision=1):
     """frames [F,C,N]; problem i: queries frame qa[i] attend to frame kb[i]; result row oidx[i] of out [n_out,C,N]."""
     if oidx is None:
-        oidx = torch.arange(qa.numel(), device=qa.device, dtype=torch.int32)
+        oidx = _iota(qa.numel(), qa.device)
     if n_out is None:
         n_out = qa.numel()
     return _CoAttn.apply(frames, qa, kb, oidx, int(n_out), float(tau), int(precision))
