@@ -6,7 +6,7 @@
 #include "common.cuh"
 
 int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, int n_out, float* lse,
-                    int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st);  // umma_coattn.cu
+                    int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st, int round_out);  // umma_coattn.cu
 bool umma_coattn_supported(int C, int N);
 size_t umma_coattn_workspace_bytes(int F, int C, int N);
 
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) coattn_fix_kernel(const float* __restrict
   float* dst = dOs + (long long)z * C * N + n;
   const float4 iv = *reinterpret_cast<const float4*>(inv_r + (long long)z * N + n);
   const float4 rh = *reinterpret_cast<const float4*>(rho + (long long)z * N + n);
-  auto rn = [](float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); };
+  auto rn = [](float x) { return tf32_rn(x); };
   const int cper = (C + gridDim.z - 1) / gridDim.z, c0 = blockIdx.z * cper, c1 = min(C, c0 + cper);
 #pragma unroll 4
   for (int c = c0 + threadIdx.y; c < c1; c += 8) {
@@ -183,8 +183,17 @@ extern "C" int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const
   DCNET_CHECK_ARG(frames && qa && kb && oidx && out && lse && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_fwd: bad arguments");
   if (nprob == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  if (precision & DCNET_RN_TF32) {
+    // the attention maps feed a tf32 contraction (corr_conv): round them once here.  The fused kernel does it in its epilogue;
+    // the other forms (small maps) get a pass over `out` -- rows no problem writes (n_out > nprob) are zero either way
+    precision &= ~DCNET_RN_TF32;
+    if (precision == 2 && umma_coattn_supported(C, N))
+      return umma_coattn_fwd(frames, F, qa, kb, oidx, nprob, out, n_out, lse, C, N, tau, workspace, workspace_bytes, st, 1);
+    DCNET_TRY(dcnet_coattn_fwd(frames, F, qa, kb, oidx, nprob, out, n_out, lse, C, N, tau, precision, workspace, workspace_bytes, stream));
+    return dcnet_round_tf32(out, out, (long long)n_out * C * N, stream);
+  }
   if (precision == 2 && umma_coattn_supported(C, N))
-    return umma_coattn_fwd(frames, F, qa, kb, oidx, nprob, out, n_out, lse, C, N, tau, workspace, workspace_bytes, st);
+    return umma_coattn_fwd(frames, F, qa, kb, oidx, nprob, out, n_out, lse, C, N, tau, workspace, workspace_bytes, st, 0);
   DCNET_CHECK_ARG(workspace && workspace_bytes >= dcnet_coattn_workspace_bytes(F, nprob, C, N, precision), "coattn_fwd: workspace too small");
   float* S = (float*)workspace;
   const long long CN = (long long)C * N, NN = (long long)N * N;

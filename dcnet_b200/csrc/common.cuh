@@ -68,6 +68,15 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
   return r;
 }
 
+// round to nearest tf32 (10 mantissa bits).  tcgen05.mma.kind::tf32 reads fp32 operands by TRUNCATION (a relative bias of about
+// -2^-12 per operand that adds up along a chain of contractions); a value rounded here reaches the MMA unchanged, so the rounding error
+// is unbiased and half as large.  Producers that hand a tensor to a tf32 contraction round it when DCNET_RN_TF32 is set.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // internal launcher of the generic fp32 GEMM (sgemm.cu)

@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(32 * G) bn_act_fwd_kernel(const float* __restr
   constexpr int C = CPT * G;
   __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
   __shared__ float red[3][G][33];
+  const bool rn = (l2norm & DCNET_RN_TF32) != 0;      // y leaves rounded to the nearest tf32 (it feeds a tf32 contraction)
+  l2norm &= 1;
   const int b = blockIdx.y;
   const int pl = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + pl;
@@ -199,75 +201,7 @@ __global__ void __launch_bounds__(32 * G) bn_act_fwd_kernel(const float* __restr
   if (valid) {
     float* yp = y + (long long)b * C * N + n;
 #pragma unroll
-    for (int i = 0; i < CPT; i++) yp[(long long)(g + G * i) * N] = v[i] * inv;
-  }
-}
-
-// Same pass with TWO consecutive positions per thread (float2): a CTA covers 64 positions x all channels, so every channel row is
-// read and written in 256-byte runs instead of 128 (fewer, longer DRAM bursts per row of the [C,N] map) with 1024 threads in flight
-// per SM.  G = 32 channel groups (warps), CPT = C / 32 channels per thread.  Needs N % 2 == 0.
-template <int CPT, int G>
-__global__ void __launch_bounds__(32 * G, 1) bn_act_fwd_v2_kernel(const float* __restrict__ z, const float* __restrict__ mean,
-                                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta, float slope, int l2norm,
-                                                                float* __restrict__ y, const float* __restrict__ fa, const float* __restrict__ fa_neg,
-                                                                float* __restrict__ sim, float* __restrict__ neg_sim, int B, int N) {
-  constexpr int C = CPT * G;
-  __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
-  __shared__ float red[3][G][64];          // [..][g][pl] = first position of the lane, [..][g][32 + pl] = second (conflict-free)
-  const int b = blockIdx.y;
-  const int pl = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int n = blockIdx.x * 64 + 2 * pl;
-  for (int c = threadIdx.x; c < C; c += 32 * G) {
-    const float sc = gamma[c] * invstd[c];
-    s_scale[c] = sc;
-    s_shift[c] = beta[c] - mean[c] * sc;
-    if (fa) {
-      s_fa[c] = fa[(long long)b * C + c];
-      s_fr[c] = fa_neg ? fa_neg[(long long)b * C + c] : fa[(long long)(B - 1 - b) * C + c];
-    }
-  }
-  __syncthreads();
-  const bool valid = n < N;                // N is even: both positions of a lane are valid together
-  const float* zp = z + (long long)b * C * N + n;
-  float2 v[CPT];
-  float ss0 = 0.f, ss1 = 0.f, d10 = 0.f, d11 = 0.f, d20 = 0.f, d21 = 0.f;
-#pragma unroll
-  for (int i = 0; i < CPT; i++) {
-    const int c = g + G * i;
-    float2 a = valid ? *reinterpret_cast<const float2*>(zp + (long long)c * N) : make_float2(0.f, 0.f);
-    a.x = fmaf(a.x, s_scale[c], s_shift[c]); a.y = fmaf(a.y, s_scale[c], s_shift[c]);
-    a.x = a.x > 0.f ? a.x : a.x * slope; a.y = a.y > 0.f ? a.y : a.y * slope;
-    v[i] = a;
-    ss0 = fmaf(a.x, a.x, ss0); ss1 = fmaf(a.y, a.y, ss1);
-    if (fa) {
-      d10 = fmaf(a.x, s_fa[c], d10); d11 = fmaf(a.y, s_fa[c], d11);
-      d20 = fmaf(a.x, s_fr[c], d20); d21 = fmaf(a.y, s_fr[c], d21);
-    }
-  }
-  float inv0 = 1.f, inv1 = 1.f;
-  if (l2norm || fa) {
-    red[0][g][pl] = ss0; red[0][g][32 + pl] = ss1;
-    red[1][g][pl] = d10; red[1][g][32 + pl] = d11;
-    red[2][g][pl] = d20; red[2][g][32 + pl] = d21;
-    __syncthreads();
-    float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f, t20 = 0.f, t21 = 0.f;
-#pragma unroll
-    for (int k = 0; k < G; k++) {
-      t00 += red[0][k][pl]; t01 += red[0][k][32 + pl];
-      t10 += red[1][k][pl]; t11 += red[1][k][32 + pl];
-      t20 += red[2][k][pl]; t21 += red[2][k][32 + pl];
-    }
-    if (l2norm) { inv0 = 1.f / fmaxf(sqrtf(t00), 1e-12f); inv1 = 1.f / fmaxf(sqrtf(t01), 1e-12f); }
-    if (fa && g == 0 && valid) {
-      *reinterpret_cast<float2*>(sim + (long long)b * N + n) = make_float2(t10 * inv0, t11 * inv1);
-      *reinterpret_cast<float2*>(neg_sim + (long long)b * N + n) = make_float2(t20 * inv0, t21 * inv1);
-    }
-  }
-  if (valid) {
-    float* yp = y + (long long)b * C * N + n;
-#pragma unroll
-    for (int i = 0; i < CPT; i++) *reinterpret_cast<float2*>(yp + (long long)(g + G * i) * N) = make_float2(v[i].x * inv0, v[i].y * inv1);
+    for (int i = 0; i < CPT; i++) yp[(long long)(g + G * i) * N] = rn ? tf32_rn(v[i] * inv) : v[i] * inv;
   }
 }
 
@@ -434,6 +368,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const float* __re
   const int row = blockIdx.x * (256 / tpr) + threadIdx.x / tpr;
   const int col = (blockIdx.y * tpr + threadIdx.x % tpr) * VEC;
   if (row >= rows || col >= N || (int)threadIdx.x >= (256 / tpr) * tpr) return;
+  const bool rn = (train & DCNET_RN_TF32) != 0;       // dz feeds the two tf32 contractions of the conv backward and nothing else
+  train &= 1;
   const int c = row % C;
   const float is = invstd[c];
   const float sc = gamma[c] * is;
@@ -453,11 +389,13 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const float* __re
       d.z = d.z - k0 - (zz.z - mu) * is * k1;
       d.w = d.w - k0 - (zz.w - mu) * is * k1;
     }
-    *reinterpret_cast<float4*>(dz + off) = make_float4(sc * d.x, sc * d.y, sc * d.z, sc * d.w);
+    float4 o = make_float4(sc * d.x, sc * d.y, sc * d.z, sc * d.w);
+    if (rn) o = make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w));
+    *reinterpret_cast<float4*>(dz + off) = o;
   } else {
     float d = dv[off];
     if (train) d = d - k0 - (z[off] - mu) * is * k1;
-    dz[off] = sc * d;
+    dz[off] = rn ? tf32_rn(sc * d) : sc * d;
   }
 }
 
@@ -735,9 +673,7 @@ extern "C" int dcnet_bn_eval_stats(const float* running_mean, const float* runni
   return 0;
 }
 
-// two positions per thread in bn_act_fwd: measured SLOWER than one (126 us against 87 us at C3, 0.43 against 0.62 of the copy
-// bandwidth, profiles/r2o): kept behind dcnet_bn_bwd_select(3) only
-static int g_bn_fwd_v2 = 0;
+// (two positions per thread in bn_act_fwd was measured SLOWER than one: 126 us against 87 us at C3, profiles/r2o; removed)
 extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                 float slope, int l2norm, float* y, const float* fa, const float* fa_neg, float* sim, float* neg_sim,
                                 int B, int C, int N, void* stream) {
@@ -746,12 +682,7 @@ extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* 
   DCNET_CHECK_ARG(!fa || (sim && neg_sim), "bn_act_fwd: fa given without sim/neg_sim outputs");
   DCNET_CHECK_ARG(B <= 65535, "bn_act_fwd: B too large");
   dim3 grid(ceil_div(N, 32), B);
-  auto al8 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 8 == 0; };
-  if (C == 512 && g_bn_fwd_v2 && N % 2 == 0 && (long long)B * N >= 64 * 148 * 2 && al8(z) && al8(y) && (!fa || (al8(sim) && al8(neg_sim)))) {
-    // large maps: two positions per thread, 256-byte runs per channel row
-    bn_act_fwd_v2_kernel<16, 32><<<dim3(ceil_div(N, 64), B), 1024, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg,
-                                                                                       sim, neg_sim, B, N);
-  } else if (C == 512)
+  if (C == 512)
     bn_act_fwd_kernel<BNF_CPT, 512 / BNF_CPT><<<grid, 32 * (512 / BNF_CPT), 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
   else
     bn_act_fwd_kernel<32, 8><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
@@ -763,8 +694,8 @@ int bn_bwd_reduce_staged(const float* z, const float* mean, const float* invstd,
                       int l2norm, const float* dy, const float* fa, const float* fa_neg, const float* dsim, const float* dneg,
                       float* dv, float* sum_dv, float* sum_dvz, float* dfa, float* dfa_neg, int B, int Cc, int N, cudaStream_t st);
 static bool g_bn_bwd_no_staged = false;
-// test / bring-up knob: 1 = always use the register-staged backward kernel; 3 = two positions per thread in the forward kernel
-extern "C" int dcnet_bn_bwd_select(int variant) { g_bn_bwd_no_staged = (variant == 1); g_bn_fwd_v2 = (variant == 3) ? 1 : 0; return 0; }
+// test / bring-up knob: 1 = always use the register-staged backward kernel
+extern "C" int dcnet_bn_bwd_select(int variant) { g_bn_bwd_no_staged = (variant == 1); return 0; }
 
 extern "C" int dcnet_bn_act_bwd_reduce(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                        float slope, int l2norm, const float* dy, const float* fa, const float* fa_neg, const float* dsim,
@@ -794,7 +725,7 @@ extern "C" int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const f
                                       const float* dv, const float* sum_dv, const float* sum_dvz, int train,
                                       float* dz, int B, int C, int N, void* stream) {
   DCNET_CHECK_ARG(z && mean && invstd && gamma && dv && dz && B > 0 && C > 0 && N > 0, "bn_act_bwd_apply: bad arguments");
-  DCNET_CHECK_ARG(!train || (sum_dv && sum_dvz), "bn_act_bwd_apply: train mode needs the channel sums");
+  DCNET_CHECK_ARG(!(train & 1) || (sum_dv && sum_dvz), "bn_act_bwd_apply: train mode needs the channel sums");
   const long long rows = (long long)B * C;
   const float invM = 1.f / (float)((long long)B * N);
   const bool v4 = N % 4 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0 && reinterpret_cast<uintptr_t>(dv) % 16 == 0 &&
@@ -809,6 +740,26 @@ extern "C" int dcnet_bn_act_bwd_apply(const float* z, const float* mean, const f
   else
     bn_act_bwd_apply_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, dv, sum_dv, sum_dvz, train, dz, (int)rows, C, N, tpr, invM);
   DCNET_LAUNCH_OK("bn_act_bwd_apply");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n4) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+  }
+  if (i == 0)
+    for (long long k = n4 * 4; k < n; k++) y[k] = tf32_rn(x[k]);
+}
+
+extern "C" int dcnet_round_tf32(const float* x, float* y, long long n, void* stream) {
+  DCNET_CHECK_ARG(x && y && n > 0, "round_tf32: bad arguments");
+  const bool v4 = reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0;
+  const long long n4 = v4 ? n / 4 : 0;
+  DCNET_CHECK_ARG(v4 || n < 4096, "round_tf32: unaligned buffers");
+  round_tf32_kernel<<<(unsigned)((n4 > 0 ? n4 + 255 : 256) / 256), 256, 0, as_stream(stream)>>>(x, y, n4, n);
+  DCNET_LAUNCH_OK("round_tf32");
   return 0;
 }
 

@@ -7,19 +7,23 @@
 //   transposed formulation (so the output tile is already in the [C,N] layout of the reference and the query tile is the
 //   narrow MMA dimension):
 //     S^T[key, q]   = sum_c Fb[c,key] Fa[c,q]      tcgen05.mma  M=128 (keys)  N=64 (q)  K=C     A: KV tile, MN-major   B: Q tile, MN-major
-//     E^T[key, q]   = exp(tau S^T - shift[q])       8 warps: tcgen05.ld -> ex2 -> bf16 -> swizzled smem (the B operand of the next MMA)
+//     E^T[key, q]   = exp(tau S^T - shift[q])       8 warps: tcgen05.ld -> ex2 -> fp16 -> swizzled smem (the B operand of the next MMA)
 //     O^T[c, q]    += sum_key Fb[c,key] E^T[key,q]  tcgen05.mma  M=128 (c block) N=64  K=128 (keys)  A: the SAME KV tile, K-major
 //   The KV tile [C x 128 keys] is loaded once by TMA and consumed by both contractions through two descriptor views of the same
 //   128-byte-swizzled bytes.  shift[q] = tau |Fa_q| max_k |Fb_k| >= every logit of the row (Cauchy-Schwarz), so no running
-//   maximum and no rescaling of O is needed: O^T accumulates in TMEM over all key tiles, r[q] = sum_key E^T (of the bf16-rounded
+//   maximum and no rescaling of O is needed: O^T accumulates in TMEM over all key tiles, r[q] = sum_key E^T (of the fp16-rounded
 //   values the MMA sees) is kept in registers, and the epilogue writes O^T / r and lse = shift + log r.
-//   Domain: rows whose true maximum logit lies more than ~80 below the bound underflow (never the case for the unit-norm,
-//   non-negative maps of the model: logits in [0, tau]).
+//   Operands are fp16 (kind::f16), not bf16: 11 significant bits like tf32 (a tf32-rounded map converts exactly above 6e-5), same
+//   MMA rate as bf16 -- the forward is then as accurate as the tf32 composition (1e-4 against 3e-4, and the gradients of the path
+//   against the oracle 7e-4 against 1.3e-3).  The maps are unit-norm (|values| <= 1); E carries a factor 2^E_EXP that cancels in O / r.
+//   Domain: |frames| < 65504, and rows whose true maximum logit lies more than ~10 below the bound lose weights to fp16's
+//   subnormal range (never the case for the unit-norm, non-negative maps of the model: logits in [0, tau], tau = 10).
 //
 //   TMEM (512 columns): O^T = C/128 blocks x 64 columns (<= 256), S^T = 64 columns at column 256.
 //   SMEM: Q 64 KiB (resident) + KV tile 128 KiB + E^T 16 KiB = 208 KiB  ->  one CTA per SM.
 //   Warps: 0 = TMA producer, 1 = MMA issuer (one elected thread) + TMEM owner, 2..9 = exp / row-sum / epilogue.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -33,9 +37,10 @@ constexpr int KT = 128;                 // keys per tile
 constexpr int CMAX = 512;
 constexpr int CB_BYTES = 128 * 256;     // one 128-channel block of a KV tile: two key halves of [128 c rows x 128 B]
 constexpr int KH_BYTES = 128 * 128;     // one key half (64 keys) of a channel block
-constexpr int Q_BYTES = CMAX * 128;     // [C rows][64 q] bf16
+constexpr int Q_BYTES = CMAX * 128;     // [C rows][64 q] fp16
 constexpr int KV_BYTES = (CMAX / 128) * CB_BYTES;
-constexpr int P_BYTES = KT * 128;       // [128 key rows][64 q] bf16
+constexpr int P_BYTES = KT * 128;       // [128 key rows][64 q] fp16
+constexpr int E_EXP = 4;
 constexpr int FUSED_SMEM = Q_BYTES + KV_BYTES + P_BYTES + 1024;
 constexpr int NTHREADS = 320;
 constexpr uint32_t S_COL = 256;         // TMEM column of S^T
@@ -48,6 +53,7 @@ struct CoP {
   int N, C, tiles;
   float scale;             // tau * log2(e)
   int tma_store;           // 1: epilogue through swizzled smem + TMA store (needs N % 4 == 0), 0: direct stores
+  int round_out;           // 1: O leaves rounded to the nearest tf32 (DCNET_RN_TF32: it is the operand of a tf32 contraction)
   int variant;             // experiment switches of the profiling entry point (0 in production)
   long long* trace;        // optional [CTA][tile][8] clock64 stamps (debug / profiling entry point); nullptr = off
 };
@@ -101,7 +107,9 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
   if (threadIdx.x >= 64 && threadIdx.x < 64 + QT) {
     const int q = threadIdx.x - 64;
     const float nq = (q0 + q < p.N) ? sqrtf(p.normsq[(long long)fa * p.N + q0 + q]) : 0.f;
-    s_shift[q] = p.scale * nq * p.maxnorm[fb];
+    // E = 2^(logit - shift + E_EXP) <= 2^E_EXP: the common factor cancels in O / r and keeps weights down to 2^-(14 + E_EXP) of the
+    // largest possible one in fp16's normal range (full 11-bit precision)
+    s_shift[q] = p.scale * nq * p.maxnorm[fb] - (float)E_EXP;
   }
   tc_fence_before();
   __syncthreads();
@@ -125,8 +133,8 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc_s = instr_desc(FMT_BF16, 128, QT, 1, 1);
-      constexpr uint32_t idesc_o = instr_desc(FMT_BF16, 128, QT, 0, 1);
+      constexpr uint32_t idesc_s = instr_desc(FMT_F16, 128, QT, 1, 1);
+      constexpr uint32_t idesc_o = instr_desc(FMT_F16, 128, QT, 0, 1);
       // descriptor templates; the 14-bit start-address field (bytes >> 4) is added per MMA
       const uint64_t kv_mn = smem_desc(smem_u32(sKV), KH_BYTES, 1024, 2);   // MN-major: key halves LBO apart, 8-channel groups SBO apart
       const uint64_t kv_k = smem_desc(smem_u32(sKV), 16, 1024, 2);          // K-major : rows = channels (128 B), 8-row atoms SBO apart
@@ -190,11 +198,11 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
       for (int e = 0; e < 32; e += 2) {
         const float x0 = valid ? ex2(fmaf(v[e], p.scale, -sh[e])) : 0.f;
         const float x1 = valid ? ex2(fmaf(v[e + 1], p.scale, -sh[e + 1])) : 0.f;
-        const __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
-        const uint32_t u = *reinterpret_cast<const uint32_t*>(&b);
-        pk[e >> 1] = u;
-        sum[e] += __uint_as_float(u << 16);
-        sum[e + 1] += __uint_as_float(u & 0xffff0000u);
+        const __half2 b = __floats2half2_rn(x0, x1);
+        pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&b);
+        const float2 bf = __half22float2(b);        // the row sum is the sum of exactly the weights the MMA reads
+        sum[e] += bf.x;
+        sum[e + 1] += bf.y;
       }
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -241,11 +249,13 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(qr * 32) << 16) + (uint32_t)(m * QT + half * 32), v);
         tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e++) v[e] = p.round_out ? tf32_rn(v[e] * inv[e]) : v[e] * inv[e];
         uint8_t* srow = sKV + (m * 2 + half) * KH_BYTES + krow * 128;
 #pragma unroll
         for (int e = 0; e < 8; e++)
           *reinterpret_cast<float4*>(srow + ((e ^ (krow & 7)) * 16)) =
-              make_float4(v[4 * e] * inv[4 * e], v[4 * e + 1] * inv[4 * e + 1], v[4 * e + 2] * inv[4 * e + 2], v[4 * e + 3] * inv[4 * e + 3]);
+              make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
         fence_proxy_async();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 64) {
@@ -262,15 +272,16 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
       tmem_ld32(tmem + ((uint32_t)(qr * 32) << 16) + (uint32_t)(m * QT + half * 32), v);
       tmem_ld_wait();
       float* orow = p.out + ((long long)p.oidx[z] * p.C + (m * 128 + krow)) * p.N + qb;
+#pragma unroll
+      for (int e = 0; e < 32; e++) v[e] = p.round_out ? tf32_rn(v[e] * inv[e]) : v[e] * inv[e];
       if (vec) {
         float4* o4 = reinterpret_cast<float4*>(orow);
 #pragma unroll
-        for (int e = 0; e < 8; e++)
-          o4[e] = make_float4(v[4 * e] * inv[4 * e], v[4 * e + 1] * inv[4 * e + 1], v[4 * e + 2] * inv[4 * e + 2], v[4 * e + 3] * inv[4 * e + 3]);
+        for (int e = 0; e < 8; e++) o4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
       } else {
 #pragma unroll
         for (int e = 0; e < 32; e++)
-          if (qb + e < p.N) orow[e] = v[e] * inv[e];
+          if (qb + e < p.N) orow[e] = v[e];
       }
     }
     }
@@ -285,10 +296,10 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// fp32 [F][C][N] -> bf16 [F][C][ld] (round to nearest even) + squared column norms (atomicAdd over the channel slices).
+// fp32 [F][C][N] -> fp16 [F][C][ld] (round to nearest even) + squared column norms (atomicAdd over the channel slices).
 // block (32, 8): 32 lanes x VEC consecutive positions, 8 channel rows per step; grid (positions, channel slices, F).
 template <int VEC>
-__global__ void __launch_bounds__(256) cast_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, float* __restrict__ normsq,
+__global__ void __launch_bounds__(256) cast_norm_kernel(const float* __restrict__ x, __half* __restrict__ y, float* __restrict__ normsq,
                                                         int C, int N, int ld, int c_per_block) {
   const int f = blockIdx.z;
   const int n = (blockIdx.x * 32 + threadIdx.x) * VEC;
@@ -300,12 +311,12 @@ __global__ void __launch_bounds__(256) cast_norm_kernel(const float* __restrict_
   for (int i = 0; i < VEC; i++) acc[i] = 0.f;
   if (n < N) {
     const float* xp = x + ((long long)f * C) * N + n;
-    __nv_bfloat16* yp = y + ((long long)f * C) * ld + n;
+    __half* yp = y + ((long long)f * C) * ld + n;
 #pragma unroll 4
     for (int c = c0 + threadIdx.y; c < c1; c += 8) {
       if constexpr (VEC == 4) {
         const float4 v = *reinterpret_cast<const float4*>(xp + (long long)c * N);
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
         uint2 u;
         u.x = *reinterpret_cast<const uint32_t*>(&lo);
         u.y = *reinterpret_cast<const uint32_t*>(&hi);
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(256) cast_norm_kernel(const float* __restrict_
         acc[0] = fmaf(v.x, v.x, acc[0]); acc[1] = fmaf(v.y, v.y, acc[1]); acc[2] = fmaf(v.z, v.z, acc[2]); acc[3] = fmaf(v.w, v.w, acc[3]);
       } else {
         const float v = xp[(long long)c * N];
-        yp[(long long)c * ld] = __float2bfloat16_rn(v);
+        yp[(long long)c * ld] = __float2half_rn(v);
         acc[0] = fmaf(v, v, acc[0]);
       }
     }
@@ -355,7 +366,7 @@ size_t umma_coattn_workspace_bytes(int F, int C, int N) {
   return align256((size_t)F * C * pitch8(N) * 2) + align256((size_t)F * N * 4 + (size_t)F * 4) + 256;
 }
 
-// staging: bf16 copy of the maps (pitch padded to 8 elements for TMA) + squared column norms + per-frame max norm
+// staging: fp16 copy of the maps (pitch padded to 8 elements for TMA) + squared column norms + per-frame max norm
 int umma_coattn_stage(const float* frames, int F, int C, int N, void* ws, size_t ws_bytes, cudaStream_t st) {
   DCNET_CHECK_ARG(umma_coattn_supported(C, N), "coattn (fused): C must be a multiple of 128, <= 512");
   DCNET_CHECK_ARG(frames && ws && ws_bytes >= umma_coattn_workspace_bytes(F, C, N), "coattn (fused): workspace too small");
@@ -363,7 +374,7 @@ int umma_coattn_stage(const float* frames, int F, int C, int N, void* ws, size_t
                   "coattn (fused): frames must be 16-byte aligned, workspace 256");
   DCNET_CHECK_ARG(F >= 1 && F <= 65535, "coattn (fused): too many frames");
   const int ld = pitch8(N);
-  __nv_bfloat16* fb16 = reinterpret_cast<__nv_bfloat16*>(ws);
+  __half* fb16 = reinterpret_cast<__half*>(ws);
   float* normsq = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align256((size_t)F * C * ld * 2));
   float* maxnorm = normsq + (size_t)F * N;
   DCNET_CUDA(cudaMemsetAsync(normsq, 0, (size_t)F * N * 4, st), "coattn_stage.memset");
@@ -383,14 +394,14 @@ int umma_coattn_stage(const float* frames, int F, int C, int N, void* ws, size_t
 
 // the fused kernel over a staged workspace
 int umma_coattn_run(const void* ws, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, float* lse,
-                    int n_out, int C, int N, float tau, cudaStream_t st, long long* trace = nullptr, int variant = 0) {
+                    int n_out, int C, int N, float tau, cudaStream_t st, long long* trace = nullptr, int variant = 0, int round_out = 0) {
   DCNET_CHECK_ARG(umma_coattn_supported(C, N), "coattn (fused): C must be a multiple of 128, <= 512");
   DCNET_CHECK_ARG(ws && qa && kb && oidx && out && lse, "coattn (fused): null argument");
   DCNET_CHECK_ARG(reinterpret_cast<uintptr_t>(out) % 16 == 0 && reinterpret_cast<uintptr_t>(ws) % 256 == 0,
                   "coattn (fused): out must be 16-byte aligned, workspace 256");
   DCNET_CHECK_ARG(nprob >= 1 && nprob <= 65535, "coattn (fused): too many problems");
   const int ld = pitch8(N);
-  const __nv_bfloat16* fb16 = reinterpret_cast<const __nv_bfloat16*>(ws);
+  const __half* fb16 = reinterpret_cast<const __half*>(ws);
   const float* normsq = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ws) + align256((size_t)F * C * ld * 2));
   const float* maxnorm = normsq + (size_t)F * N;
   CUtensorMap map;
@@ -403,6 +414,7 @@ int umma_coattn_run(const void* ws, int F, const int* qa, const int* kb, const i
   p.trace = trace;
   p.variant = variant;
   p.tma_store = (N % 4 == 0) ? 1 : 0;
+  p.round_out = round_out;
   CUtensorMap map_out = map;   // unused when tma_store == 0
   if (p.tma_store) {
     const int ro = make_tmap(&map_out, out, 4, (uint64_t)N, (uint64_t)C, (uint64_t)n_out, (uint64_t)N, (uint64_t)C * N, 32, 128);
@@ -416,9 +428,9 @@ int umma_coattn_run(const void* ws, int F, const int* qa, const int* kb, const i
 }
 
 int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, int n_out, float* lse,
-                    int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    int C, int N, float tau, void* ws, size_t ws_bytes, cudaStream_t st, int round_out) {
   DCNET_TRY(umma_coattn_stage(frames, F, C, N, ws, ws_bytes, st));
-  return umma_coattn_run(ws, F, qa, kb, oidx, nprob, out, lse, n_out, C, N, tau, st);
+  return umma_coattn_run(ws, F, qa, kb, oidx, nprob, out, lse, n_out, C, N, tau, st, nullptr, 0, round_out);
 }
 
 extern "C" size_t dcnet_coattn_stage_bytes(int F, int C, int N) { return (F > 0 && C > 0 && N > 0) ? umma_coattn_workspace_bytes(F, C, N) : 256; }

@@ -239,14 +239,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // slots and TMA (plain store, or fp32 reduce-add for split reductions / shared gradients) instead of per-thread stores whose
 // lanes hit 32 different rows.  Each epilogue warp owns its 32 rows end to end (2 x 4 KiB slots), so no cross-warp barrier.
 // ---------------------------------------------------------------------------------------------------------------------
-// round to nearest tf32 (10 mantissa bits): the MMA reads fp32 operands by TRUNCATION; values rounded here reach it unchanged, so
-// the rounding error is unbiased and half as large, and sums taken in the epilogue are sums of exactly what the next MMA will see
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-
 struct Gemm2P {
   int M_valid, N_valid, k_iters, k_split, n_split, m_split;
   int a_batched, b_batched, out_batched;

@@ -169,9 +169,7 @@ class grounding_model(nn.Module):
         """a2: fvisu[s] = normalize_c(ConvBNReLU_1x1(raw[s]))   (:356-359) -> 3 x [B,C,N_s].
         Scale 0 runs in exact fp32: the top-30 correspondences (a4) and the arg-max words (a11) are selected from it and
         index parity with the reference needs fp32 scores (SURVEY section 7 "Index parity"); the other scales use tcgen05."""
-        p0 = ops.EXACT_FP32 if self.precision == ops.EXACT_FP32 else ops.EXACT_FWD_TF32_BWD     # gradients select no index
-        return [self.mapping_visu._modules[str(s)].fused(raw_fvisu[s].flatten(2), l2norm=True,
-                                                         precision=p0 if s == 0 else self.precision) for s in range(3)]
+        return [self.map_visual_scale(raw_fvisu[s], s) for s in range(3)]
 
     def _head_layer(self, m, y):
         """SURVEY 8(f) row 1, first step into the grounding head (model/DCNet_model.py:316-337, :505-506): its 1x1
@@ -186,8 +184,11 @@ class grounding_model(nn.Module):
     head_on_tcgen05 = True
 
     def map_visual_scale(self, raw_s, s):
-        p0 = ops.EXACT_FP32 if self.precision == ops.EXACT_FP32 else ops.EXACT_FWD_TF32_BWD
-        return self.mapping_visu._modules[str(s)].fused(raw_s.flatten(2), l2norm=True, precision=p0 if s == 0 else self.precision)
+        p0 = ops.EXACT_FP32 if self.precision == ops.EXACT_FP32 else ops.EXACT_FWD_TF32_BWD     # gradients select no index
+        # the maps of scales 1, 2 only feed tf32 contractions (corr_conv, co-attention backward): they leave rounded to tf32;
+        # scale 0 stays exact fp32 (the index selections read it) and is rounded where the contractions start (correspondence_scale)
+        return self.mapping_visu._modules[str(s)].fused(raw_s.flatten(2), l2norm=True, precision=p0 if s == 0 else self.precision,
+                                                        round_out=s > 0)
 
     def correspondence_scale(self, fv_s, s, fa, fa_neg=None):
         """a5 + a6 + a9 of one scale as one autograd node (ops.correspondence): co-attention both directions, corr_conv on
@@ -198,7 +199,7 @@ class grounding_model(nn.Module):
         return ops.correspondence(fv_s, qa, kb, m.conv.weight.view(m.conv.weight.shape[0], -1), bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                   self.training, fa=fa, fa_neg=fa_neg, tau=self.temperature, cprecision=self.coattn_precision,
                                   momentum=bn.momentum, eps=bn.eps, slope=m.slope, precision=self.precision,
-                                  num_batches_tracked=bn.num_batches_tracked)
+                                  num_batches_tracked=bn.num_batches_tracked, round_in=(s == 0), round_out=True)
 
     def fuse_terms(self, s, flang, coords_s, kv=512):
         """the text / coordinate terms of scale s on their own (ops.fuse_terms): for callers that issue them ahead of the chain"""
@@ -213,8 +214,8 @@ class grounding_model(nn.Module):
         (dcnet_fuse_terms_*), the visual term on the tcgen05 GEMM whose epilogue adds them."""
         m = self.fcn_emb._modules[str(s)][0]
         if terms is not None:
-            return m.fused(corr_s, u=terms[0], cc=terms[1], l2norm=False, precision=self.precision)
-        return m.fused(corr_s, l2norm=False, precision=self.precision, flang=flang, coords=coords_s if self.coordmap else None)
+            return m.fused(corr_s, u=terms[0], cc=terms[1], l2norm=False, precision=self.precision, round_in=False)
+        return m.fused(corr_s, l2norm=False, precision=self.precision, flang=flang, coords=coords_s if self.coordmap else None, round_in=False)
 
     def interframe(self, fv0, negpos=None):
         """a4 (:381-430) -> packed q [30,P,C], k [30,P,C], neg [30,P,10,C].  negpos: optional pre-drawn device tensor

@@ -76,6 +76,21 @@ def gemm_tf32(A, B, a_mn, b_mn, M, N, K, alpha=1.0, out=None, atomic=0):
     return C
 
 
+# Operands of the tf32 contractions are rounded to the nearest tf32 where they are produced (include/dcnet_b200.h, DCNET_RN_TF32): the
+# MMA truncates, and the truncation bias adds up along the ~10 chained contractions of the backward.  False = the round-1 behaviour
+# (diagnostics only).
+RN_TF32 = True
+_RN_FLAG = 0x100
+
+
+def round_tf32(x, out=None):
+    """x rounded to the nearest tf32 value (fp32 storage); a tensor the library did not produce itself (weights, Darknet maps)"""
+    x = _c(x.detach(), name="x")
+    y = torch.empty_like(x) if out is None else out
+    _lib.call("dcnet_round_tf32", _p(x), _p(y), x.numel(), _st())
+    return y
+
+
 def cast_bf16(x):
     """fp32 -> bf16 (round to nearest even) with the library's own kernel"""
     x = _c(x, name="x")
@@ -293,7 +308,9 @@ class _ConvBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope, l2norm, precision, nbt=None,
-                flang=None, coords=None):
+                flang=None, coords=None, round_in=True, round_out=False):
+        """round_in: x1 / x2 are not tf32-rounded yet (a producer of this library that was told to round hands them over rounded:
+        round_in=False); round_out: y feeds another tf32 contraction, round it on the way out (see RN_TF32)."""
         x1 = _c(x1, name="x1")
         x2 = _c(x2, name="x2")
         weight = _c(weight, name="weight")
@@ -323,6 +340,16 @@ class _ConvBNAct(torch.autograd.Function):
         ctx_precision = precision
         if precision == EXACT_FWD_TF32_BWD:
             precision = EXACT_FP32
+        wq, rounded = weight, False
+        if RN_TF32 and precision == TENSOR_TF32:
+            wq = round_tf32(weight)
+            if round_in:
+                x1 = round_tf32(x1)
+                x2 = round_tf32(x2) if x2 is not None else None
+            rounded = True
+        elif not round_in:
+            rounded = True
+        weight_full, weight = weight, wq          # the contractions read wq; the fp32 text / coordinate kernels the parameter itself
         padded = precision == 1 and N % 4 != 0 and K1 % 32 == 0 and K2 % 32 == 0
         if padded:
             Np = (N + 3) // 4 * 4
@@ -348,21 +375,28 @@ class _ConvBNAct(torch.autograd.Function):
         if fa is not None:
             sim = torch.empty(B, N, device=dev, dtype=F32)
             neg = torch.empty(B, N, device=dev, dtype=F32)
-        _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm), _p(y), _p(fa), _p(fa_neg), _p(sim), _p(neg),
-                  B, C, N, st)
-        ctx.save_for_backward(x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd, flang, coords)
-        ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None, ctx_precision)
+        rn_out = _RN_FLAG if (RN_TF32 and round_out and ctx_precision == TENSOR_TF32) else 0
+        _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm) | rn_out, _p(y), _p(fa), _p(fa_neg), _p(sim),
+                  _p(neg), B, C, N, st)
+        ctx.save_for_backward(x1, x2, weight_full, gamma, beta, fa, fa_neg, z, mean, invstd, flang, coords, wq)
+        ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None, ctx_precision, rounded)
         if fa is None:
             return y
         return y, sim, neg
 
     @staticmethod
     def backward(ctx, dy, dsim=None, dneg=None):
-        x1, x2, weight, gamma, beta, fa, fa_neg, z, mean, invstd, flang, coords = ctx.saved_tensors
-        training, slope, l2norm, has_u, has_cc, precision = ctx.cfg
+        x1, x2, weight_full, gamma, beta, fa, fa_neg, z, mean, invstd, flang, coords, weight = ctx.saved_tensors
+        training, slope, l2norm, has_u, has_cc, precision, rounded = ctx.cfg
         terms = flang is not None          # u / cc were derived from (flang, coords) inside forward
         if precision == EXACT_FWD_TF32_BWD:
             precision = TENSOR_TF32      # no index depends on the gradients: the backward contractions run on tcgen05
+        rn = RN_TF32 and precision == TENSOR_TF32
+        if rn and weight is weight_full:
+            weight = round_tf32(weight_full)        # exact-fp32 forward: the backward's operands are rounded here
+        if rn and not rounded and ctx.needs_input_grad[2]:
+            x1 = round_tf32(x1)
+            x2 = round_tf32(x2) if x2 is not None else None
         B, K1, N = x1.shape
         K2 = 0 if x2 is None else x2.shape[1]
         C, ldw = weight.shape
@@ -381,8 +415,8 @@ class _ConvBNAct(torch.autograd.Function):
         dfa_neg = acc[acc.numel() - B * C:].view(B, C) if want_dfa_neg else None
         _lib.call("dcnet_bn_act_bwd_reduce", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, l2norm, _p(dy), _p(fa), _p(fa_neg),
                   _p(dsim), _p(dneg), _p(dv), _p(sums[0]), _p(sums[1]), _p(dfa), _p(dfa_neg), B, C, N, st)
-        _lib.call("dcnet_bn_act_bwd_apply", _p(z), _p(mean), _p(invstd), _p(gamma), _p(dv), _p(sums[0]), _p(sums[1]), int(training), _p(dv),
-                  B, C, N, st)
+        _lib.call("dcnet_bn_act_bwd_apply", _p(z), _p(mean), _p(invstd), _p(gamma), _p(dv), _p(sums[0]), _p(sums[1]),
+                  int(training) | (_RN_FLAG if rn else 0), _p(dv), B, C, N, st)
         dz = dv
         need_w = ctx.needs_input_grad[2]
         if precision == 1 and N % 4 != 0 and K1 % 128 == 0 and K2 % 128 == 0:
@@ -408,7 +442,7 @@ class _ConvBNAct(torch.autograd.Function):
                 x2p = _pad_n(x2, Np) if (need_w and x2 is not None) else None
                 _lib.call("dcnet_conv1x1_bwd_weight", _p(dzp), _p(x1p), K1, _p(x2p), K2, _p(dW), ldw, _p(du), _p(dccp), B, C, Np, precision, st)
             dcc = dccp[:, :N].contiguous() if dccp is not None else None
-            return _ConvBNAct._finish(ctx, dx1, dx2, dW, sums, du, dcc, dfa, dfa_neg, weight, flang, coords, K1 + K2, B, C, N, st)
+            return _ConvBNAct._finish(ctx, dx1, dx2, dW, sums, du, dcc, dfa, dfa_neg, weight_full, flang, coords, K1 + K2, B, C, N, st)
         dx1 = torch.empty_like(x1) if ctx.needs_input_grad[0] else None
         dx2 = torch.empty_like(x2) if (x2 is not None and ctx.needs_input_grad[1]) else None
         if dx1 is not None or dx2 is not None:
@@ -424,7 +458,7 @@ class _ConvBNAct(torch.autograd.Function):
         if need_w or du is not None or dcc is not None:
             _lib.call("dcnet_conv1x1_bwd_weight", _p(dz), _p(x1) if need_w else None, K1, _p(x2) if need_w else None, K2,
                       _p(dW), ldw, _p(du), _p(dcc), B, C, N, precision, st)
-        return _ConvBNAct._finish(ctx, dx1, dx2, dW, sums, du, dcc, dfa, dfa_neg, weight, flang, coords, K1 + K2, B, C, N, st)
+        return _ConvBNAct._finish(ctx, dx1, dx2, dW, sums, du, dcc, dfa, dfa_neg, weight_full, flang, coords, K1 + K2, B, C, N, st)
 
     @staticmethod
     def _finish(ctx, dx1, dx2, dW, sums, du, dcc, dfa, dfa_neg, weight, flang, coords, kv, B, C, N, st):
@@ -437,7 +471,7 @@ class _ConvBNAct(torch.autograd.Function):
                 _lib.call("dcnet_fuse_terms_bwd", _p(weight), weight.shape[1], kv, Ct, kv + Ct, _p(flang), _p(coords), _p(du), _p(dcc),
                           _p(dflang), _p(dW), B, C, N, st)
             du = dcc = None
-        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, dflang, None)
+        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, dflang, None, None, None)
 
 
 EXACT_FP32, TENSOR_TF32, TENSOR_BF16_FUSED, EXACT_FWD_TF32_BWD = 0, 1, 2, 3
@@ -446,14 +480,16 @@ FUSED_MIN_N = 128      # the fused bf16 co-attention forward is used from this m
 
 def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
                 momentum=0.999, eps=1e-5, slope=0.0, l2norm=False, precision=TENSOR_TF32, fa_neg=None, num_batches_tracked=None,
-                flang=None, coords=None):
+                flang=None, coords=None, round_in=True, round_out=False):
     """x1 [B,K1,N] (+x2 [B,K2,N]); weight [C,ldw].  Returns y [B,C,N] or (y, sim, neg_sim) when fa [B,C] is given.
     precision: TENSOR_TF32 = tcgen05 GEMMs (<=1e-3 relative), EXACT_FP32 = CUDA-core fp32 (<=1e-5).
     (u [B,C], cc [C,N]): extra terms added to the conv output; or (flang [B,Ct], coords [8,N]): the fusion's text / coordinate
-    inputs, whose weight columns follow the visual ones in `weight` (a8) -- u and cc are then computed and back-propagated here."""
+    inputs, whose weight columns follow the visual ones in `weight` (a8) -- u and cc are then computed and back-propagated here.
+    round_in / round_out: tf32 rounding of the operands / of y (RN_TF32): pass round_in=False for inputs a kernel of this library
+    already rounded (round_out=True of the producing layer), round_out=True when y feeds another tf32 contraction."""
     return _ConvBNAct.apply(x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, bool(training), float(momentum),
                             float(eps), float(slope), bool(l2norm), int(precision), num_batches_tracked if training else None,
-                            flang, coords)
+                            flang, coords, bool(round_in), bool(round_out))
 
 
 class _FuseTerms(torch.autograd.Function):
@@ -498,7 +534,8 @@ def fuse_terms(weight, flang, coords, kv):
 
 class _CoAttn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, frames, qa, kb, oidx, n_out, tau, precision):
+    def forward(ctx, frames, qa, kb, oidx, n_out, tau, precision, round_out=False):
+        """round_out: the attention maps feed a tf32 contraction (corr_conv): they leave rounded to the nearest tf32 (RN_TF32)"""
         frames = _c(frames, name="frames")
         qa, kb, oidx = (_c(t, torch.int32, "index") for t in (qa, kb, oidx))
         F_, C, N = frames.shape
@@ -508,6 +545,7 @@ class _CoAttn(torch.autograd.Function):
         lse = torch.empty(nprob, N, device=frames.device, dtype=F32)
         staged = None
         ctx.precision = precision
+        rn_out = _RN_FLAG if (RN_TF32 and round_out) else 0
         if precision == EXACT_FWD_TF32_BWD:
             # exact fp32 forward (lse included); the backward is the tcgen05 one with fused epilogues, which recomputes its own tf32
             # logits and re-normalises them (the saved lse is only a shift there, so the two precisions cannot disagree about P)
@@ -524,12 +562,13 @@ class _CoAttn(torch.autograd.Function):
             # -2 % step time but 1.3e-3 gradient error against 9e-4 with tf32 logits + re-normalisation: not used (bar 1e-3).
             nbytes = _lib.lib().dcnet_coattn_stage_bytes(F_, C, N)
             staged = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
-            _lib.call("dcnet_coattn_stage", _p(frames), F_, C, N, _p(staged), nbytes, _st())
-            _lib.call("dcnet_coattn_fused_fwd", _p(staged), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, _st())
+            # staging + fused kernel (dcnet_coattn_fwd at precision 2 needs only the staging bytes)
+            _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau,
+                      TENSOR_BF16_FUSED | rn_out, _p(staged), nbytes, _st())
         else:
             nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, precision)
             ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
-            _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, precision,
+            _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, precision | rn_out,
                       _p(ws), nbytes, _st())
         ctx.save_for_backward(frames, qa, kb, oidx, out, lse)
         ctx.tau = tau
@@ -548,7 +587,7 @@ class _CoAttn(torch.autograd.Function):
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
         _lib.call("dcnet_coattn_bwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout), _p(dframes),
                   C, N, ctx.tau, ctx.precision, None, _p(ws), nbytes, _st())
-        return dframes, None, None, None, None, None, None
+        return dframes, None, None, None, None, None, None, None
 
 
 def coattn_stage(frames):
@@ -606,12 +645,17 @@ class _Correspondence(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, fv, qa, kb, tau, cprecision, weight, gamma, beta, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope,
-                precision, nbt):
+                precision, nbt, round_in, round_out):
         c1, c2 = _FakeCtx(), _FakeCtx()
         nprob = qa.numel()
-        attn = _CoAttn.forward(c1, fv, qa, kb, _iota(nprob, qa.device), nprob, tau, cprecision)
+        rn = RN_TF32 and precision == TENSOR_TF32
+        if rn and round_in:
+            # fv arrives unrounded (the scale-0 maps are exact fp32 for the index selections): every contraction below -- corr_conv,
+            # and the five of the co-attention backward -- reads one rounded copy; the gradient is that of the identity
+            fv = round_tf32(_c(fv, name="fv"))
+        attn = _CoAttn.forward(c1, fv, qa, kb, _iota(nprob, qa.device), nprob, tau, cprecision, rn)
         out = _ConvBNAct.forward(c2, fv, attn, weight, gamma, beta, None, None, fa, fa_neg, running_mean, running_var, training, momentum, eps,
-                                 slope, True, precision, nbt)
+                                 slope, True, precision, nbt, None, None, False, round_out)
         ctx.n1 = len(c1.saved_tensors)
         ctx.save_for_backward(*c1.saved_tensors, *c2.saved_tensors)
         ctx.c1_attrs = (c1.tau, c1.precision)
@@ -623,7 +667,7 @@ class _Correspondence(torch.autograd.Function):
         saved = ctx.saved_tensors
         nig = ctx.needs_input_grad
         # conv node first: inputs (x1 = fv, x2 = attn, weight, gamma, beta, u, cc, fa, fa_neg, ...)
-        c2 = _FakeCtx((True, True, nig[5], nig[6], nig[7], False, False, nig[8], nig[9]) + (False,) * 11)
+        c2 = _FakeCtx((True, True, nig[5], nig[6], nig[7], False, False, nig[8], nig[9]) + (False,) * 13)
         c2.saved_tensors = saved[ctx.n1:]
         c2.cfg = ctx.c2_cfg
         g2 = _ConvBNAct.backward(c2, dy, dsim, dneg)
@@ -632,15 +676,16 @@ class _Correspondence(torch.autograd.Function):
         c1.saved_tensors = saved[:ctx.n1]
         c1.tau, c1.precision = ctx.c1_attrs
         _CoAttn.backward(c1, dattn, accumulate_into=dfv)
-        return (dfv, None, None, None, None, dW, dgamma, dbeta, dfa, dfa_neg, None, None, None, None, None, None, None, None)
+        return (dfv, None, None, None, None, dW, dgamma, dbeta, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, None)
 
 
 def correspondence(fv, qa, kb, weight, gamma, beta, running_mean, running_var, training, fa=None, fa_neg=None, tau=10.0, cprecision=TENSOR_BF16_FUSED,
-                   momentum=0.999, eps=1e-5, slope=0.0, precision=TENSOR_TF32, num_batches_tracked=None):
+                   momentum=0.999, eps=1e-5, slope=0.0, precision=TENSOR_TF32, num_batches_tracked=None, round_in=True, round_out=False):
     """fv [B,C,N] (pairs = consecutive frames via qa / kb) -> corr_feat [B,Cout,N] (channel-normalised) or (corr_feat, sim, neg_sim) with fa.
     weight [Cout, 2C]: corr_conv applied to [fv | co-attention(fv)] (model/DCNet_model.py:449-469, :525-535)."""
     return _Correspondence.apply(fv, qa, kb, float(tau), int(cprecision), weight, gamma, beta, fa, fa_neg, running_mean, running_var, bool(training),
-                                 float(momentum), float(eps), float(slope), int(precision), num_batches_tracked if training else None)
+                                 float(momentum), float(eps), float(slope), int(precision), num_batches_tracked if training else None,
+                                 bool(round_in), bool(round_out))
 
 
 def coattention(frames, qa, kb, oidx=None, n_out=None, tau=10.0, precision=1):

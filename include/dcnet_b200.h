@@ -73,6 +73,15 @@ DCNET_API int dcnet_gemm_select(int variant);
  * thread), 1 accumulator stage free, 2 first operands landed, 3 last MMA issued, 4 accumulator complete (epilogue), 5 epilogue done */
 DCNET_API int dcnet_gemm_trace(long long* buf);
 
+/* ---- operand rounding for the tf32 contractions.  tcgen05.mma.kind::tf32 reads fp32 operands by truncating them to 10 mantissa
+ * bits: a relative bias of about -2^-12 per operand, which adds up along a chain of contractions (the backward of the path is ~10
+ * of them: 5.7e-3 after 8 layers against 8e-4 with rounded operands).  A value already rounded to the nearest tf32 passes the MMA
+ * unchanged.  DCNET_RN_TF32, or-ed into the flag argument named at each entry point, makes a producer round what it hands to a tf32
+ * contraction (dcnet_bn_act_fwd: `l2norm`; dcnet_bn_act_bwd_apply: `train`; dcnet_coattn_fwd: `precision`); dcnet_round_tf32 rounds
+ * a tensor the library did not produce (weights, the Darknet maps).  y may alias x.                                              */
+#define DCNET_RN_TF32 0x100
+DCNET_API int dcnet_round_tf32(const float* x, float* y, long long n, void* stream);
+
 /* ---- a1/a2/a6/a8: 1x1 conv (no bias) + BatchNorm + ReLU (+ L2 norm over channels) ---------------------
  * replaces ConvBatchNormReLU (model/darknet.py:118-156) as used by mapping_visu (:356-359), corr_conv
  * (:467-469) and fcn_emb[s][0] (:505), and F.normalize(dim=1).

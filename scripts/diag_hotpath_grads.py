@@ -6,6 +6,9 @@ import torch
 from dcnet_b200 import synth
 from dcnet_b200.hotpath import HotPath
 from oracle import dcnet_oracle as O
+from dcnet_b200 import ops
+ops.RN_TF32 = os.environ.get("DCNET_RN", "1") != "0"      # 0: operands truncated by the MMA (round 1 behaviour)
+print("RN_TF32 =", ops.RN_TF32)
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 2
