@@ -180,8 +180,8 @@ DCNET_API int dcnet_coord_map(float* coord, int h, int w, void* stream);
  *   S = Fa^T Fb,  P = softmax_j(tau S),  out[oidx[i]] = Fb P^T  ([C,N]),  lse[i][n] = log sum_j exp(tau S[n,j]).
  * A training pair p is the two problems (2p,2p+1) and (2p+1,2p); the test-time clip path uses the centre
  * direction only.  precision: 0 = exact fp32 (CUDA cores), 1 = tcgen05 TF32 GEMMs with S/P in workspace,
- * 2 = fused tcgen05 kernel (bf16 operands, fp32 accumulation in TMEM): S / P never leave the SM; workspace
- * holds the bf16 staging of the maps.  The fused forward assumes every logit of a row lies within ~80 of
+ * 2 = fused tcgen05 kernel (fp16 operands -- 11 significant bits like tf32 --, fp32 accumulation in TMEM): S / P never leave
+ * the SM; workspace holds the fp16 staging of the maps (|values| < 65504; the model's maps are unit-norm).  The fused forward assumes every logit of a row lies within ~80 of
  * tau |Fa_q| max_k |Fb_k| (always true for the unit-norm maps of the model, model/DCNet_model.py:359).
  * The backward of precision 2 is the precision-1 composition.                                            */
 DCNET_API size_t dcnet_coattn_workspace_bytes(int F, int nprob, int C, int N, int precision);
@@ -189,7 +189,7 @@ DCNET_API int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const 
                                float* out, int n_out, float* lse, int C, int N, float tau, int precision,
                                void* workspace, size_t workspace_bytes, void* stream);
 /* the two halves of the precision-2 forward, callable separately (the clip path stages a clip once and runs many problems):
- * dcnet_coattn_stage: staged <- bf16 copy of frames (row pitch padded to 8 elements) + column norms; dcnet_coattn_fused_fwd: the
+ * dcnet_coattn_stage: staged <- fp16 copy of frames (row pitch padded to 8 elements) + column norms; dcnet_coattn_fused_fwd: the
  * fused TMA/tcgen05 kernel over a staged buffer (grid = 64-query tiles x problems).  C % 128 == 0, C <= 512.                 */
 DCNET_API size_t dcnet_coattn_stage_bytes(int F, int C, int N);
 DCNET_API int dcnet_coattn_stage(const float* frames, int F, int C, int N, void* staged, size_t staged_bytes, void* stream);
@@ -198,9 +198,9 @@ DCNET_API int dcnet_coattn_fused_fwd(const void* staged, int F, const int* qa, c
 /* profiling variant: trace [ceil(N/64) * nprob CTAs][ceil(N/128) key tiles + 1][8] int64 receives clock64 stamps (see umma_coattn.cu) */
 DCNET_API int dcnet_coattn_fused_fwd_trace(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                            float* out, int n_out, float* lse, int C, int N, float tau, long long* trace, int variant, void* stream);
-/* dframes [F,C,N] += gradient (caller zeroes); dout/out indexed by oidx like the forward.  staged (optional, precision 2): the
- * buffer dcnet_coattn_stage filled for the forward of the same frames; P is then recomputed from the forward's own bf16 operands
- * with exp fused into the GEMM epilogue (no softmax pass).  NULL: P is re-normalised from tf32 logits.                          */
+/* dframes [F,C,N] += gradient (caller zeroes, or hands over a buffer that already holds another consumer's gradient of the
+ * frames); dout/out indexed by oidx like the forward.  P is re-normalised from tf32 logits recomputed here (the forward's lse is
+ * only a shift).  staged: reserved, pass NULL (round 1 could recompute P from the forward's staging: 1.3e-3 against 5e-4).   */
 DCNET_API int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                const float* out, int n_out, const float* lse, const float* dout, float* dframes,
                                int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,

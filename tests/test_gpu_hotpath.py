@@ -161,13 +161,13 @@ def _grad_errors(c, r, pc, pr):
 
 
 # bars of the benchmark-shape test (measured values in DESIGN.md section 2)
-TL_BENCH, TG_NOISE, TG_PINNED = 3e-3, 6e-2, 5e-3
+TL_BENCH, TG_NOISE, TG_PINNED = 1e-3, 6e-2, 1e-3
 
 
 @pytest.mark.parametrize("size,pairs", [(256, 8), (416, 16)])
 def test_hotpath_step_at_benchmark_shapes_vs_oracle(size, pairs):
     """BASELINE configs[1] (8 pairs at 256x256) and configs[2] (16 pairs at 416x416) -- the shapes bench.py times -- in the
-    benchmarked mode (tf32 tcgen05 contractions, fused bf16 co-attention forward).  Losses, IoU and every integer output against
+    benchmarked mode (tf32 tcgen05 contractions on rounded operands, fused fp16 co-attention forward).  Losses, IoU and every integer output against
     the CPU oracle; gradients twice: against the oracle as is (bar = the ReLU-pattern noise any reduced-precision forward has,
     see DESIGN.md section 2), and against the oracle evaluated AT THE PRODUCT'S ReLU PATTERNS, i.e. as the derivative of the
     function the product actually computed (tight bar: what is left is operand rounding of the tf32 contractions)."""
@@ -245,6 +245,5 @@ def test_c4_all_ordered_pairs_vs_oracle_loop():
             worst = max(rel(outs[s][p_], want[p_]) for p_ in range(qa.numel()))
             print("C4 all ordered pairs, scale %d (N=%d): rel err %.2e over the batch, %.2e on the worst problem" % (
                 s, f.shape[2], rel(outs[s], want), worst))
-            # bf16 operands at tau = 10: 1e-3 over the batch; a single problem of these eval-mode maps (peaky: few active channels,
-            # little averaging over the channel sum) may reach 1.5e-3
-            assert rel(outs[s], want) < 1e-3 and worst < 2e-3, (s, rel(outs[s], want), worst)
+            # fp16 operands at tau = 10 (bf16 gave 7e-4 over the batch and 1.5e-3 on the worst problem of these peaky eval-mode maps)
+            assert rel(outs[s], want) < 3e-4 and worst < 5e-4, (s, rel(outs[s], want), worst)

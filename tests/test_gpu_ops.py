@@ -71,7 +71,7 @@ def test_gemm_tf32_all_operand_majors(a_mn, b_mn, M, N, K, batch):
     e = rel(C, ref)
     blk = ((C.double().cpu() - ref)[0].abs()[: (M // 32) * 32, : (N // 32) * 32].reshape(M // 32, 32, N // 32, 32).amax(dim=(1, 3)))
     print("gemm_tf32 a_mn=%d b_mn=%d M=%d N=%d K=%d rel err %.2e; worst 32x32 blocks:" % (a_mn, b_mn, M, N, K, e), blk.flatten().topk(3).values.tolist())
-    assert e < 2e-3, e
+    assert e < 1e-3, e
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
@@ -115,7 +115,7 @@ def test_gemm_kernel_variants_agree_bit_for_bit(M, N, K, batch, b_mn):
             outs.append(ops.gemm_tf32(A, Bd, 0, b_mn, M, N, K))
     finally:
         _lib.lib().dcnet_gemm_select(0)
-    assert rel(outs[0], ref) < 2e-3
+    assert rel(outs[0], ref) < 1e-3
     for o in outs[1:]:
         assert torch.equal(outs[0], o)
 
@@ -131,14 +131,14 @@ def test_conv_linear_backward_forms_tf32():
     dx1 = torch.empty(B, K1, N, device=DEV); dx2 = torch.empty(B, K2, N, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
     _lib.call("dcnet_conv1x1_bwd_data", d[0].data_ptr(), d[1].data_ptr(), K1 + K2 + 8, dx1.data_ptr(), K1, dx2.data_ptr(), K2, B, C, N, 1, st)
-    assert rel(dx1, torch.einsum('ck,bcn->bkn', W[:, :K1].double(), dz.double())) < 2e-3
-    assert rel(dx2, torch.einsum('ck,bcn->bkn', W[:, K1:K1 + K2].double(), dz.double())) < 2e-3
+    assert rel(dx1, torch.einsum('ck,bcn->bkn', W[:, :K1].double(), dz.double())) < 1e-3
+    assert rel(dx2, torch.einsum('ck,bcn->bkn', W[:, K1:K1 + K2].double(), dz.double())) < 1e-3
     dW = torch.full((C, K1 + K2 + 8), 7.0, device=DEV)
     du = torch.empty(B, C, device=DEV); dcc = torch.empty(C, N, device=DEV)
     _lib.call("dcnet_conv1x1_bwd_weight", d[0].data_ptr(), d[2].data_ptr(), K1, d[3].data_ptr(), K2, dW.data_ptr(), K1 + K2 + 8,
               du.data_ptr(), dcc.data_ptr(), B, C, N, 1, st)
-    assert rel(dW[:, :K1], torch.einsum('bcn,bkn->ck', dz.double(), x1.double())) < 2e-3
-    assert rel(dW[:, K1:K1 + K2], torch.einsum('bcn,bkn->ck', dz.double(), x2.double())) < 2e-3
+    assert rel(dW[:, :K1], torch.einsum('bcn,bkn->ck', dz.double(), x1.double())) < 1e-3
+    assert rel(dW[:, K1:K1 + K2], torch.einsum('bcn,bkn->ck', dz.double(), x2.double())) < 1e-3
     assert float((dW[:, K1 + K2:] - 7.0).abs().max()) == 0.0          # columns beyond K1+K2 untouched
     assert rel(du, dz.double().sum(2)) < 1e-5 and rel(dcc, dz.double().sum(0)) < 1e-5
 
@@ -192,7 +192,7 @@ def _cbr_oracle(d, l2, training, dtype=torch.float64):
 def test_conv_bn_act_forward_backward(B, K1, K2, N, use_u, use_cc, use_fa, l2, training, precision):
     # precision 0: exact fp32 (CUDA cores), <= 1e-5.  precision 1: TF32 tcgen05 GEMMs with fp32 accumulation, <= 1e-3-class
     # (BASELINE north_star: "<= 1e-3 relative for bf16-accumulated-in-fp32 GEMMs"; TF32 keeps 3 more mantissa bits than bf16).
-    tol_f, tol_b = (1e-5, 2e-5) if precision == 0 else (2e-3, 4e-3)
+    tol_f, tol_b = (1e-5, 2e-5) if precision == 0 else (1e-3, 4e-3)
     d = _cbr_case(B, K1, K2, N, use_u, use_cc, use_fa, l2, training, seed=10 + N)
     t, outs_ref, (z_ref, mean_ref, var_ref) = _cbr_oracle(d, l2, training)
     c = {k: (v.to(DEV).requires_grad_(k not in ('rm', 'rv')) if v is not None else None) for k, v in d.items()}
@@ -268,7 +268,7 @@ def test_conv_bn_act_odd_pitch_runs_on_tensor_cores(use_terms, use_fa):
     errs = [rel(p, q) for p, q in zip(a, b)]
     print("odd-pitch conv, tf32 padded vs exact fp32:", ["%.1e" % e for e in errs])
     nfwd = 2 if use_fa else 1
-    assert max(errs[:nfwd]) < 2e-3 and max(errs) < 3e-2, errs     # gradients: ReLU-mask flips of the tf32 forward (see above)
+    assert max(errs[:nfwd]) < 1e-3 and max(errs) < 3e-2, errs     # gradients: ReLU-mask flips of the tf32 forward (see above)
 
 
 @pytest.mark.parametrize("B,N,l2norm,use_fa,use_dy", [(3, 64, 1, 1, 1), (2, 676, 1, 1, 1), (4, 1024, 0, 0, 1), (2, 256, 1, 1, 0), (5, 20, 1, 1, 1)])
@@ -306,8 +306,9 @@ def test_bn_bwd_reduce_staged_kernel_matches_register_kernel(B, N, l2norm, use_f
 @pytest.mark.parametrize("precision", [0, 1, 2])
 @pytest.mark.parametrize("P,N", [(2, 64), (2, 169), (1, 256), (1, 676), (1, 1024)])
 def test_coattention_forward_backward(P, N, precision):
-    # precision 2 = fused tcgen05 kernel, bf16 operands: north_star bar 1e-3 relative for the forward
-    tol_f, tol_b = {0: (1e-5, 2e-5), 1: (2e-3, 4e-3), 2: (1e-3, 4e-3)}[precision]
+    # precision 1 = tf32 tcgen05 composition, 2 = fused tcgen05 kernel on fp16 operands (backward: the tf32 contractions with fused
+    # epilogues): north_star bar 1e-3 relative, forward and backward (no ReLU in this block, so the gradient has no pattern noise)
+    tol_f, tol_b = {0: (1e-5, 2e-5), 1: (1e-3, 1e-3), 2: (5e-4, 1e-3)}[precision]
     g = gen(20 + N)
     C = 512
     fr = torch.nn.functional.normalize(torch.randn(2 * P, C, N, generator=g).abs(), dim=1)
@@ -342,41 +343,13 @@ def test_coattention_fused_staged_problems(C, N):
     for i in range(4):
         S = 10.0 * fr[qa[i]].double().t() @ fr[kb[i]].double()
         ref = fr[kb[i]].double() @ torch.softmax(S, 1).t()
-        # problem 2 is a frame attending to itself: softmax peaked on one key, so the output is essentially one bf16-rounded
-        # column of Fb and the error is the bf16 operand rounding itself (2^-9 / sqrt(3) = 1.1e-3); distinct frames give 1e-4
-        assert rel(out[oidx[i]], ref) < (1.5e-3 if qa[i] == kb[i] else 1e-3), (i, rel(out[oidx[i]], ref))
-        # logits carry tau x the bf16 rounding of a dot product: 10 x 2^-9 worst case on the self-pair diagonal
-        assert float((lse[i].double().cpu() - torch.logsumexp(S, 1)).abs().max()) < (3e-2 if qa[i] == kb[i] else 5e-3)
+        # problem 2 is a frame attending to itself: softmax peaked on one key, so the output is essentially one fp16-rounded
+        # column of Fb and the error is the operand rounding itself (2^-12 / sqrt(3) = 1.4e-4); distinct frames average it out
+        assert rel(out[oidx[i]], ref) < (3e-4 if qa[i] == kb[i] else 2e-4), (i, rel(out[oidx[i]], ref))
+        # logits carry tau x the fp16 rounding of a dot product: 10 x 2^-12 worst case on the self-pair diagonal
+        assert float((lse[i].double().cpu() - torch.logsumexp(S, 1)).abs().max()) < (4e-3 if qa[i] == kb[i] else 1e-3)
     print("fused staged C=%d N=%d worst fwd rel err %.2e" % (C, N, max(rel(out[oidx[i]], fr[kb[i]].double() @ torch.softmax(
         10.0 * fr[qa[i]].double().t() @ fr[kb[i]].double(), 1).t()) for i in range(4))))
-
-
-def test_coattention_backward_with_forward_staging():
-    """dcnet_coattn_bwd(staged=...): P recomputed from the forward's bf16 operands with exp in the GEMM epilogue (no softmax
-    pass).  Measured 1.3e-3 against the fp64 gradient (tf32 logits + re-normalisation: 9e-4), so it is an option, not the default."""
-    from dcnet_b200 import _lib
-    g = gen(44)
-    P, C, N = 2, 512, 256
-    fr = torch.nn.functional.normalize(torch.randn(2 * P, C, N, generator=g).abs(), dim=1)
-    ref_in = fr.double().requires_grad_(True)
-    o1, o2 = O.coattention(ref_in.view(P, 2, C, N)[:, 0], ref_in.view(P, 2, C, N)[:, 1], 10.0)
-    ref = O.interleave_pairs(o1, o2)
-    go = torch.randn(ref.shape, generator=g)
-    ref.backward(go.double())
-    x = fr.to(DEV)
-    qa = torch.arange(2 * P, device=DEV, dtype=torch.int32); kb = qa ^ 1
-    staged = ops.coattn_stage(x)
-    out, lse = ops.coattn_fused(staged, x.shape, qa, kb, tau=10.0)
-    dfr = torch.zeros_like(x)
-    L = _lib.lib()
-    nbytes = L.dcnet_coattn_workspace_bytes(2 * P, 2 * P, C, N, 2)
-    ws = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
-    god = go.to(DEV)
-    _lib.call("dcnet_coattn_bwd", x.data_ptr(), 2 * P, qa.data_ptr(), kb.data_ptr(), qa.data_ptr(), 2 * P, out.data_ptr(), 2 * P, lse.data_ptr(),
-              god.data_ptr(), dfr.data_ptr(), C, N, 10.0, 2, staged.data_ptr(), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
-    e = rel(dfr, ref_in.grad)
-    print("coattn bwd with forward staging: rel err %.2e" % e)
-    assert e < 2.5e-3, e
 
 
 def test_coattention_clip_mode_centre_vs_others():
@@ -393,7 +366,7 @@ def test_coattention_clip_mode_centre_vs_others():
     for i, o in enumerate(others):
         o1, _ = O.coattention(fr[centre:centre + 1].double(), fr[o:o + 1].double(), 10.0)
         assert rel(out[i], o1[0]) < 1e-5
-        assert rel(out_tc[i], o1[0]) < 2e-3
+        assert rel(out_tc[i], o1[0]) < 1e-3
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -713,7 +686,7 @@ def test_fusion_layer_with_text_and_coordinate_terms(precision, N):
     rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
     y = ops.conv_bn_act(c['x'], c['w'], c['gamma'], c['beta'], rm, rv, True, flang=c['flang'], coords=ops.coord_map(h, h, DEV).flatten(1),
                         precision=precision)
-    tol_f, tol_b = (1e-5, 1e-4) if precision == 0 else (2e-3, 3e-2)      # tf32: ReLU-pattern noise, see test_conv_bn_act_forward_backward
+    tol_f, tol_b = (1e-5, 1e-4) if precision == 0 else (1e-3, 3e-2)      # tf32: ReLU-pattern noise, see test_conv_bn_act_forward_backward
     assert rel(y, y64) < tol_f, rel(y, y64)
     y.backward(gy.to(DEV))
     for k in ('x', 'flang', 'w', 'gamma', 'beta'):
