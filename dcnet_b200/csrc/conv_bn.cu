@@ -1,6 +1,8 @@
 // a1/a2/a6/a8: 1x1 conv + BatchNorm + ReLU (+ L2 norm over channels, + pixel-to-text dots), forward and backward.
 // Replaces ConvBatchNormReLU (model/darknet.py:118-156) + F.normalize(dim=1) (model/DCNet_model.py:359,469) and the
 // sim_score products (model/DCNet_model.py:530-535, train_DCNet.py:623-627).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 #ifndef BNF_CPT
@@ -143,7 +145,9 @@ __global__ void __launch_bounds__(32 * G) bn_act_fwd_kernel(const float* __restr
                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float slope, int l2norm,
                                                          float* __restrict__ y, const float* __restrict__ fa, const float* __restrict__ fa_neg,
-                                                         float* __restrict__ sim, float* __restrict__ neg_sim, int B, int N) {
+                                                         float* __restrict__ sim, float* __restrict__ neg_sim, int B, int N,
+                                                         __half* __restrict__ st16, int ld16, float* __restrict__ st_normsq,
+                                                         unsigned int* __restrict__ st_maxnorm) {
   constexpr int C = CPT * G;
   __shared__ float s_scale[C], s_shift[C], s_fa[C], s_fr[C];
   __shared__ float red[3][G][33];
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(32 * G) bn_act_fwd_kernel(const float* __restr
     }
   }
   float inv = 1.f;
-  if (l2norm || fa) {
+  if (l2norm || fa || st16) {
     red[0][g][pl] = ss;
     red[1][g][pl] = d1;
     red[2][g][pl] = d2;
@@ -197,11 +201,28 @@ __global__ void __launch_bounds__(32 * G) bn_act_fwd_kernel(const float* __restr
       sim[(long long)b * N + n] = t1 * inv;
       neg_sim[(long long)b * N + n] = t2 * inv;
     }
+    if (st16 && g == 0) {
+      // the co-attention staging of this map (umma_coattn.cu): squared column norms and the largest norm of the frame
+      const float nsq = valid ? t0 * inv * inv : 0.f;
+      if (valid) st_normsq[(long long)b * N + n] = nsq;
+      const float mx = warp_max(nsq);
+      if (pl == 0) atomicMax(st_maxnorm + b, __float_as_uint(sqrtf(mx)));      // non-negative floats order like their bit patterns
+    }
   }
   if (valid) {
     float* yp = y + (long long)b * C * N + n;
 #pragma unroll
-    for (int i = 0; i < CPT; i++) yp[(long long)(g + G * i) * N] = rn ? tf32_rn(v[i] * inv) : v[i] * inv;
+    for (int i = 0; i < CPT; i++) {
+      const float o = rn ? tf32_rn(v[i] * inv) : v[i] * inv;
+      yp[(long long)(g + G * i) * N] = o;
+      v[i] = o;
+    }
+    if (st16) {
+      // fp16 copy for the fused co-attention forward: a tf32-rounded value converts exactly (both keep 11 significant bits)
+      __half* sp = st16 + (long long)b * C * ld16 + n;
+#pragma unroll
+      for (int i = 0; i < CPT; i++) sp[(long long)(g + G * i) * ld16] = __float2half_rn(v[i]);
+    }
   }
 }
 
@@ -674,18 +695,34 @@ extern "C" int dcnet_bn_eval_stats(const float* running_mean, const float* runni
 }
 
 // (two positions per thread in bn_act_fwd was measured SLOWER than one: 126 us against 87 us at C3, profiles/r2o; removed)
+int umma_coattn_stage_layout(void* ws, size_t ws_bytes, int F, int C, int N, void** fp16_maps, int* ld, float** normsq, float** maxnorm);
+
 extern "C" int dcnet_bn_act_fwd(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                 float slope, int l2norm, float* y, const float* fa, const float* fa_neg, float* sim, float* neg_sim,
                                 int B, int C, int N, void* stream) {
+  return dcnet_bn_act_fwd_staged(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, C, N, nullptr, 0, stream);
+}
+
+extern "C" int dcnet_bn_act_fwd_staged(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                       float slope, int l2norm, float* y, const float* fa, const float* fa_neg, float* sim, float* neg_sim,
+                                       int B, int C, int N, void* staged, size_t staged_bytes, void* stream) {
   DCNET_CHECK_ARG(z && mean && invstd && gamma && beta && y && B > 0 && N > 0, "bn_act_fwd: bad arguments");
+  __half* st16 = nullptr; int ld16 = 0; float* st_normsq = nullptr; float* st_maxnorm = nullptr;
+  if (staged) {
+    void* maps;
+    DCNET_TRY(umma_coattn_stage_layout(staged, staged_bytes, B, C, N, &maps, &ld16, &st_normsq, &st_maxnorm));
+    st16 = reinterpret_cast<__half*>(maps);
+    DCNET_CUDA(cudaMemsetAsync(st_maxnorm, 0, (size_t)B * sizeof(float), as_stream(stream)), "bn_act_fwd.memset");
+  }
+  unsigned int* st_mx = reinterpret_cast<unsigned int*>(st_maxnorm);
   DCNET_CHECK_ARG(C == 512 || C == 256, "bn_act_fwd: C=%d unsupported (512 or 256)", C);
   DCNET_CHECK_ARG(!fa || (sim && neg_sim), "bn_act_fwd: fa given without sim/neg_sim outputs");
   DCNET_CHECK_ARG(B <= 65535, "bn_act_fwd: B too large");
   dim3 grid(ceil_div(N, 32), B);
   if (C == 512)
-    bn_act_fwd_kernel<BNF_CPT, 512 / BNF_CPT><<<grid, 32 * (512 / BNF_CPT), 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
+    bn_act_fwd_kernel<BNF_CPT, 512 / BNF_CPT><<<grid, 32 * (512 / BNF_CPT), 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N, st16, ld16, st_normsq, st_mx);
   else
-    bn_act_fwd_kernel<32, 8><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N);
+    bn_act_fwd_kernel<32, 8><<<grid, 256, 0, as_stream(stream)>>>(z, mean, invstd, gamma, beta, slope, l2norm, y, fa, fa_neg, sim, neg_sim, B, N, st16, ld16, st_normsq, st_mx);
   DCNET_LAUNCH_OK("bn_act_fwd");
   return 0;
 }

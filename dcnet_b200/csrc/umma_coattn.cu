@@ -366,6 +366,18 @@ size_t umma_coattn_workspace_bytes(int F, int C, int N) {
   return align256((size_t)F * C * pitch8(N) * 2) + align256((size_t)F * N * 4 + (size_t)F * 4) + 256;
 }
 
+// where the three parts of a staging buffer live (used by the producers that fill it themselves: dcnet_bn_act_fwd_staged)
+int umma_coattn_stage_layout(void* ws, size_t ws_bytes, int F, int C, int N, void** fp16_maps, int* ld, float** normsq, float** maxnorm) {
+  DCNET_CHECK_ARG(umma_coattn_supported(C, N), "coattn (fused): C must be a multiple of 128, <= 512");
+  DCNET_CHECK_ARG(ws && ws_bytes >= umma_coattn_workspace_bytes(F, C, N), "coattn (fused): staging buffer too small");
+  DCNET_CHECK_ARG(reinterpret_cast<uintptr_t>(ws) % 256 == 0, "coattn (fused): staging buffer must be 256-byte aligned");
+  *ld = pitch8(N);
+  *fp16_maps = ws;
+  *normsq = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align256((size_t)F * C * *ld * 2));
+  *maxnorm = *normsq + (size_t)F * N;
+  return 0;
+}
+
 // staging: fp16 copy of the maps (pitch padded to 8 elements for TMA) + squared column norms + per-frame max norm
 int umma_coattn_stage(const float* frames, int F, int C, int N, void* ws, size_t ws_bytes, cudaStream_t st) {
   DCNET_CHECK_ARG(umma_coattn_supported(C, N), "coattn (fused): C must be a multiple of 128, <= 512");
@@ -440,10 +452,11 @@ extern "C" int dcnet_coattn_stage(const float* frames, int F, int C, int N, void
 }
 
 extern "C" int dcnet_coattn_fused_fwd(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
-                                      float* out, int n_out, float* lse, int C, int N, float tau, void* stream) {
+                                      float* out, int n_out, float* lse, int C, int N, float tau, int flags, void* stream) {
   DCNET_CHECK_ARG(F > 0 && n_out > 0 && nprob >= 0, "coattn_fused_fwd: bad arguments");
   if (nprob == 0) return 0;
-  return umma_coattn_run(staged, F, qa, kb, oidx, nprob, out, lse, n_out, C, N, tau, as_stream(stream));
+  return umma_coattn_run(staged, F, qa, kb, oidx, nprob, out, lse, n_out, C, N, tau, as_stream(stream), nullptr, 0,
+                         (flags & DCNET_RN_TF32) ? 1 : 0);
 }
 
 // profiling variant: trace [grid CTAs][key tiles][8] receives clock64 stamps of the MMA-issuing thread (0-3: channel block m of

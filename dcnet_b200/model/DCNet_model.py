@@ -187,8 +187,19 @@ class grounding_model(nn.Module):
         p0 = ops.EXACT_FP32 if self.precision == ops.EXACT_FP32 else ops.EXACT_FWD_TF32_BWD     # gradients select no index
         # the maps of scales 1, 2 only feed tf32 contractions (corr_conv, co-attention backward): they leave rounded to tf32;
         # scale 0 stays exact fp32 (the index selections read it) and is rounded where the contractions start (correspondence_scale)
-        return self.mapping_visu._modules[str(s)].fused(raw_s.flatten(2), l2norm=True, precision=p0 if s == 0 else self.precision,
-                                                        round_out=s > 0)
+        m = self.mapping_visu._modules[str(s)]
+        N = raw_s.shape[2] * raw_s.shape[3]
+        # ... and the same kernel writes the fused co-attention's staging (fp16 copy + column norms) from its registers
+        stage = (s > 0 and self.precision == ops.TENSOR_TF32 and self.coattn_precision == ops.TENSOR_BF16_FUSED and N >= ops.FUSED_MIN_N
+                 and m.conv.out_channels % 128 == 0 and m.conv.out_channels <= 512)
+        # (the Darknet map itself is read truncated: a pass over it would cost more than the layer's BN kernel, and a uniform
+        # relative bias of z is removed by the BatchNorm that follows; the weight gradient carries it once, ~2e-4)
+        out = m.fused(raw_s.flatten(2), l2norm=True, precision=p0 if s == 0 else self.precision, round_in=False, round_out=s > 0,
+                      stage_out=stage)
+        if stage:
+            out, staged = out
+            out._dcnet_staged = staged       # travels with the map to correspondence_scale (same tensor object)
+        return out
 
     def correspondence_scale(self, fv_s, s, fa, fa_neg=None):
         """a5 + a6 + a9 of one scale as one autograd node (ops.correspondence): co-attention both directions, corr_conv on
@@ -199,7 +210,8 @@ class grounding_model(nn.Module):
         return ops.correspondence(fv_s, qa, kb, m.conv.weight.view(m.conv.weight.shape[0], -1), bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                   self.training, fa=fa, fa_neg=fa_neg, tau=self.temperature, cprecision=self.coattn_precision,
                                   momentum=bn.momentum, eps=bn.eps, slope=m.slope, precision=self.precision,
-                                  num_batches_tracked=bn.num_batches_tracked, round_in=(s == 0), round_out=True)
+                                  num_batches_tracked=bn.num_batches_tracked, round_in=(s == 0), round_out=True,
+                                  staged=getattr(fv_s, "_dcnet_staged", None))
 
     def fuse_terms(self, s, flang, coords_s, kv=512):
         """the text / coordinate terms of scale s on their own (ops.fuse_terms): for callers that issue them ahead of the chain"""

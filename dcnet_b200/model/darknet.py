@@ -23,7 +23,7 @@ class ConvBatchNormReLU(nn.Sequential):
             self.add_module("relu", nn.ReLU())
 
     def fused(self, x1, x2=None, u=None, cc=None, fa=None, l2norm=False, precision=ops.TENSOR_TF32, fa_neg=None, flang=None, coords=None,
-              round_in=True, round_out=False):
+              round_in=True, round_out=False, stage_out=False):
         """x1 [B,K1,N] (+ x2 [B,K2,N]) through the sm_100a kernels; the weight columns beyond K1+K2 (split-weight fusion) act
         on (flang [B,Ct], coords [8,N]) -- or the caller applies them itself and passes the results as u / cc."""
         w = self.conv.weight.view(self.conv.weight.shape[0], -1)
@@ -32,7 +32,8 @@ class ConvBatchNormReLU(nn.Sequential):
         # that state dicts stay interchangeable with a reference-trained checkpoint (no extra launch)
         return ops.conv_bn_act(x1, w, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.training, x2=x2, u=u, cc=cc, fa=fa,
                                momentum=bn.momentum, eps=bn.eps, slope=self.slope, l2norm=l2norm, precision=precision, fa_neg=fa_neg,
-                               num_batches_tracked=bn.num_batches_tracked, flang=flang, coords=coords, round_in=round_in, round_out=round_out)
+                               num_batches_tracked=bn.num_batches_tracked, flang=flang, coords=coords, round_in=round_in, round_out=round_out,
+                               stage_out=stage_out)
 
 
 class YOLOLayer(nn.Module):

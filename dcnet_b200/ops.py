@@ -308,8 +308,10 @@ class _ConvBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope, l2norm, precision, nbt=None,
-                flang=None, coords=None, round_in=True, round_out=False):
-        """round_in: x1 / x2 are not tf32-rounded yet (a producer of this library that was told to round hands them over rounded:
+                flang=None, coords=None, round_in=True, round_out=False, stage_out=False):
+        """stage_out: also return the co-attention staging of y (fp16 copy + column norms, dcnet_bn_act_fwd_staged) as a last,
+        non-differentiable output -- the fused co-attention forward of the next block then starts without a pass over y.
+        round_in: x1 / x2 are not tf32-rounded yet (a producer of this library that was told to round hands them over rounded:
         round_in=False); round_out: y feeds another tf32 contraction, round it on the way out (see RN_TF32)."""
         x1 = _c(x1, name="x1")
         x2 = _c(x2, name="x2")
@@ -376,16 +378,23 @@ class _ConvBNAct(torch.autograd.Function):
             sim = torch.empty(B, N, device=dev, dtype=F32)
             neg = torch.empty(B, N, device=dev, dtype=F32)
         rn_out = _RN_FLAG if (RN_TF32 and round_out and ctx_precision == TENSOR_TF32) else 0
-        _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm) | rn_out, _p(y), _p(fa), _p(fa_neg), _p(sim),
-                  _p(neg), B, C, N, st)
+        staged, nst = None, 0
+        if stage_out:
+            nst = _lib.lib().dcnet_coattn_stage_bytes(B, C, N)
+            staged = torch.empty(nst, device=dev, dtype=torch.uint8)
+        _lib.call("dcnet_bn_act_fwd_staged", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, int(l2norm) | rn_out, _p(y), _p(fa), _p(fa_neg),
+                  _p(sim), _p(neg), B, C, N, _p(staged), nst, st)
         ctx.save_for_backward(x1, x2, weight_full, gamma, beta, fa, fa_neg, z, mean, invstd, flang, coords, wq)
         ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None, ctx_precision, rounded)
-        if fa is None:
-            return y
-        return y, sim, neg
+        outs = (y,) if fa is None else (y, sim, neg)
+        if stage_out:
+            ctx.mark_non_differentiable(staged)
+            outs = outs + (staged,)
+        return outs[0] if len(outs) == 1 else outs
 
     @staticmethod
-    def backward(ctx, dy, dsim=None, dneg=None):
+    def backward(ctx, dy, *more):
+        dsim, dneg = (more[0], more[1]) if len(more) >= 2 else (None, None)
         x1, x2, weight_full, gamma, beta, fa, fa_neg, z, mean, invstd, flang, coords, weight = ctx.saved_tensors
         training, slope, l2norm, has_u, has_cc, precision, rounded = ctx.cfg
         terms = flang is not None          # u / cc were derived from (flang, coords) inside forward
@@ -471,7 +480,7 @@ class _ConvBNAct(torch.autograd.Function):
                 _lib.call("dcnet_fuse_terms_bwd", _p(weight), weight.shape[1], kv, Ct, kv + Ct, _p(flang), _p(coords), _p(du), _p(dcc),
                           _p(dflang), _p(dW), B, C, N, st)
             du = dcc = None
-        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, dflang, None, None, None)
+        return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, dflang, None, None, None, None)
 
 
 EXACT_FP32, TENSOR_TF32, TENSOR_BF16_FUSED, EXACT_FWD_TF32_BWD = 0, 1, 2, 3
@@ -480,16 +489,17 @@ FUSED_MIN_N = 128      # the fused bf16 co-attention forward is used from this m
 
 def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
                 momentum=0.999, eps=1e-5, slope=0.0, l2norm=False, precision=TENSOR_TF32, fa_neg=None, num_batches_tracked=None,
-                flang=None, coords=None, round_in=True, round_out=False):
+                flang=None, coords=None, round_in=True, round_out=False, stage_out=False):
     """x1 [B,K1,N] (+x2 [B,K2,N]); weight [C,ldw].  Returns y [B,C,N] or (y, sim, neg_sim) when fa [B,C] is given.
     precision: TENSOR_TF32 = tcgen05 GEMMs (<=1e-3 relative), EXACT_FP32 = CUDA-core fp32 (<=1e-5).
     (u [B,C], cc [C,N]): extra terms added to the conv output; or (flang [B,Ct], coords [8,N]): the fusion's text / coordinate
     inputs, whose weight columns follow the visual ones in `weight` (a8) -- u and cc are then computed and back-propagated here.
     round_in / round_out: tf32 rounding of the operands / of y (RN_TF32): pass round_in=False for inputs a kernel of this library
-    already rounded (round_out=True of the producing layer), round_out=True when y feeds another tf32 contraction."""
+    already rounded (round_out=True of the producing layer), round_out=True when y feeds another tf32 contraction.
+    stage_out: a last output `staged` (uint8 buffer) = the fused co-attention's staging of y, for correspondence(staged=)."""
     return _ConvBNAct.apply(x1, x2, weight, gamma, beta, u, cc, fa, fa_neg, running_mean, running_var, bool(training), float(momentum),
                             float(eps), float(slope), bool(l2norm), int(precision), num_batches_tracked if training else None,
-                            flang, coords, bool(round_in), bool(round_out))
+                            flang, coords, bool(round_in), bool(round_out), bool(stage_out))
 
 
 class _FuseTerms(torch.autograd.Function):
@@ -534,8 +544,9 @@ def fuse_terms(weight, flang, coords, kv):
 
 class _CoAttn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, frames, qa, kb, oidx, n_out, tau, precision, round_out=False):
-        """round_out: the attention maps feed a tf32 contraction (corr_conv): they leave rounded to the nearest tf32 (RN_TF32)"""
+    def forward(ctx, frames, qa, kb, oidx, n_out, tau, precision, round_out=False, prestaged=None):
+        """round_out: the attention maps feed a tf32 contraction (corr_conv): they leave rounded to the nearest tf32 (RN_TF32);
+        prestaged: the staging of `frames` its producer already wrote (conv_bn_act(stage_out=True)) -- precision 2 only"""
         frames = _c(frames, name="frames")
         qa, kb, oidx = (_c(t, torch.int32, "index") for t in (qa, kb, oidx))
         F_, C, N = frames.shape
@@ -561,10 +572,15 @@ class _CoAttn(torch.autograd.Function):
             # P recomputed from the same bf16 operands, exp fused into the GEMM epilogue, no softmax pass) was measured at
             # -2 % step time but 1.3e-3 gradient error against 9e-4 with tf32 logits + re-normalisation: not used (bar 1e-3).
             nbytes = _lib.lib().dcnet_coattn_stage_bytes(F_, C, N)
-            staged = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
-            # staging + fused kernel (dcnet_coattn_fwd at precision 2 needs only the staging bytes)
-            _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau,
-                      TENSOR_BF16_FUSED | rn_out, _p(staged), nbytes, _st())
+            if prestaged is not None:
+                if prestaged.numel() < nbytes or prestaged.dtype != torch.uint8:
+                    raise ValueError("coattention: prestaged buffer does not belong to frames of shape %s" % (tuple(frames.shape),))
+                _lib.call("dcnet_coattn_fused_fwd", _p(prestaged), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, rn_out, _st())
+            else:
+                staged = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
+                # staging + fused kernel (dcnet_coattn_fwd at precision 2 needs only the staging bytes)
+                _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau,
+                          TENSOR_BF16_FUSED | rn_out, _p(staged), nbytes, _st())
         else:
             nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, precision)
             ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
@@ -587,7 +603,7 @@ class _CoAttn(torch.autograd.Function):
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
         _lib.call("dcnet_coattn_bwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout), _p(dframes),
                   C, N, ctx.tau, ctx.precision, None, _p(ws), nbytes, _st())
-        return dframes, None, None, None, None, None, None, None
+        return dframes, None, None, None, None, None, None, None, None
 
 
 def coattn_stage(frames):
@@ -611,7 +627,7 @@ def coattn_fused(staged, shape, qa, kb, oidx=None, n_out=None, tau=10.0, out=Non
         out = torch.empty(n_out, C, N, device=staged.device, dtype=F32)
     if lse is None:
         lse = torch.empty(nprob, N, device=staged.device, dtype=F32)
-    _lib.call("dcnet_coattn_fused_fwd", _p(staged), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, float(tau), _st())
+    _lib.call("dcnet_coattn_fused_fwd", _p(staged), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, float(tau), 0, _st())
     return out, lse
 
 
@@ -645,7 +661,7 @@ class _Correspondence(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, fv, qa, kb, tau, cprecision, weight, gamma, beta, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope,
-                precision, nbt, round_in, round_out):
+                precision, nbt, round_in, round_out, staged):
         c1, c2 = _FakeCtx(), _FakeCtx()
         nprob = qa.numel()
         rn = RN_TF32 and precision == TENSOR_TF32
@@ -653,9 +669,10 @@ class _Correspondence(torch.autograd.Function):
             # fv arrives unrounded (the scale-0 maps are exact fp32 for the index selections): every contraction below -- corr_conv,
             # and the five of the co-attention backward -- reads one rounded copy; the gradient is that of the identity
             fv = round_tf32(_c(fv, name="fv"))
-        attn = _CoAttn.forward(c1, fv, qa, kb, _iota(nprob, qa.device), nprob, tau, cprecision, rn)
+            staged = None
+        attn = _CoAttn.forward(c1, fv, qa, kb, _iota(nprob, qa.device), nprob, tau, cprecision, rn, staged)
         out = _ConvBNAct.forward(c2, fv, attn, weight, gamma, beta, None, None, fa, fa_neg, running_mean, running_var, training, momentum, eps,
-                                 slope, True, precision, nbt, None, None, False, round_out)
+                                 slope, True, precision, nbt, None, None, False, round_out, False)
         ctx.n1 = len(c1.saved_tensors)
         ctx.save_for_backward(*c1.saved_tensors, *c2.saved_tensors)
         ctx.c1_attrs = (c1.tau, c1.precision)
@@ -667,7 +684,7 @@ class _Correspondence(torch.autograd.Function):
         saved = ctx.saved_tensors
         nig = ctx.needs_input_grad
         # conv node first: inputs (x1 = fv, x2 = attn, weight, gamma, beta, u, cc, fa, fa_neg, ...)
-        c2 = _FakeCtx((True, True, nig[5], nig[6], nig[7], False, False, nig[8], nig[9]) + (False,) * 13)
+        c2 = _FakeCtx((True, True, nig[5], nig[6], nig[7], False, False, nig[8], nig[9]) + (False,) * 14)
         c2.saved_tensors = saved[ctx.n1:]
         c2.cfg = ctx.c2_cfg
         g2 = _ConvBNAct.backward(c2, dy, dsim, dneg)
@@ -676,16 +693,18 @@ class _Correspondence(torch.autograd.Function):
         c1.saved_tensors = saved[:ctx.n1]
         c1.tau, c1.precision = ctx.c1_attrs
         _CoAttn.backward(c1, dattn, accumulate_into=dfv)
-        return (dfv, None, None, None, None, dW, dgamma, dbeta, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, None)
+        return (dfv, None, None, None, None, dW, dgamma, dbeta, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def correspondence(fv, qa, kb, weight, gamma, beta, running_mean, running_var, training, fa=None, fa_neg=None, tau=10.0, cprecision=TENSOR_BF16_FUSED,
-                   momentum=0.999, eps=1e-5, slope=0.0, precision=TENSOR_TF32, num_batches_tracked=None, round_in=True, round_out=False):
+                   momentum=0.999, eps=1e-5, slope=0.0, precision=TENSOR_TF32, num_batches_tracked=None, round_in=True, round_out=False,
+                   staged=None):
     """fv [B,C,N] (pairs = consecutive frames via qa / kb) -> corr_feat [B,Cout,N] (channel-normalised) or (corr_feat, sim, neg_sim) with fa.
-    weight [Cout, 2C]: corr_conv applied to [fv | co-attention(fv)] (model/DCNet_model.py:449-469, :525-535)."""
+    weight [Cout, 2C]: corr_conv applied to [fv | co-attention(fv)] (model/DCNet_model.py:449-469, :525-535).
+    staged: the co-attention staging of fv written by its producer (conv_bn_act(stage_out=True)); None = staged here."""
     return _Correspondence.apply(fv, qa, kb, float(tau), int(cprecision), weight, gamma, beta, fa, fa_neg, running_mean, running_var, bool(training),
                                  float(momentum), float(eps), float(slope), int(precision), num_batches_tracked if training else None,
-                                 bool(round_in), bool(round_out))
+                                 bool(round_in), bool(round_out), staged)
 
 
 def coattention(frames, qa, kb, oidx=None, n_out=None, tau=10.0, precision=1):

@@ -139,6 +139,12 @@ DCNET_API int dcnet_bn_eval_stats(const float* running_mean, const float* runnin
 DCNET_API int dcnet_bn_act_fwd(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                float slope, int l2norm, float* y, const float* fa, const float* fa_neg, float* sim, float* neg_sim,
                                int B, int C, int N, void* stream);
+/* same, and fills `staged` (dcnet_coattn_stage_bytes(B, C, N) bytes, 256-byte aligned) with what dcnet_coattn_stage would make of y
+ * -- fp16 copy, column norms, largest norm per frame -- so the fused co-attention forward starts from the producer's registers
+ * instead of re-reading the map (staged = NULL: plain dcnet_bn_act_fwd).  Follow with dcnet_coattn_fused_fwd.                     */
+DCNET_API int dcnet_bn_act_fwd_staged(const float* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                      float slope, int l2norm, float* y, const float* fa, const float* fa_neg, float* sim, float* neg_sim,
+                                      int B, int C, int N, void* staged, size_t staged_bytes, void* stream);
 /* fa_neg (optional, [B,C]): explicit text vector of each image's negative partner (cross-GPU negatives: the partner of global
  * sample g is Bg-1-g and may live on another rank); NULL = the reference's local batch reversal fa[B-1-b].                 */
 /* Backward of bn_act_fwd in train mode (batch statistics).  Two launches:
@@ -194,7 +200,8 @@ DCNET_API int dcnet_coattn_fwd(const float* frames, int F, const int* qa, const 
 DCNET_API size_t dcnet_coattn_stage_bytes(int F, int C, int N);
 DCNET_API int dcnet_coattn_stage(const float* frames, int F, int C, int N, void* staged, size_t staged_bytes, void* stream);
 DCNET_API int dcnet_coattn_fused_fwd(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
-                                     float* out, int n_out, float* lse, int C, int N, float tau, void* stream);
+                                     float* out, int n_out, float* lse, int C, int N, float tau, int flags, void* stream);
+/* flags: 0 or DCNET_RN_TF32 (out leaves rounded to the nearest tf32) */
 /* profiling variant: trace [ceil(N/64) * nprob CTAs][ceil(N/128) key tiles + 1][8] int64 receives clock64 stamps (see umma_coattn.cu) */
 DCNET_API int dcnet_coattn_fused_fwd_trace(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                            float* out, int n_out, float* lse, int C, int N, float tau, long long* trace, int variant, void* stream);
