@@ -106,6 +106,9 @@ struct UmmaEpilogue {
   long long cc_sb = 0;           // batch stride of cc (0: cc is shared by the batch, the conv use)
   long long sum_ldz = 0;         // sum / sumsq are indexed [z*sum_ldz + row] (0: one vector for the whole batch = BatchNorm statistics)
   int k_chunks = 1;              // reduce-add outputs (atomic = 1) only: split the reduction over this many work items per output tile
+  // 3x3 convolution as an implicit GEMM (conv3x3.cu; see Gemm2P in umma_gemm.cu): B, B2, B3 = the map shifted by dx = -1, 0, +1
+  const UmmaOperand* B3 = nullptr;
+  int tap_kper = 0, tap_w = 0, tap_flip = 0, tap_n = 0;
 };
 bool umma_gemm_usable(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int K);
 int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2, int M, int N, int K, int k_split_elems, int n_split,

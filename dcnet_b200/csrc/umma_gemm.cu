@@ -249,6 +249,13 @@ struct Gemm2P {
   int epi_exp;
   const float* u2; long long cc_sb; long long sum_ldz;
   int k_chunks, k_per;   // split-K (reduce-add outputs): work item = (tile, chunk); chunk c covers k iterations [c*k_per, min(k_iters, (c+1)*k_per))
+  // 3x3 convolution as an implicit GEMM over three column-shifted copies of the map (B = x(dx=-1), B2 = x, B3 = x(dx=+1); conv3x3.cu):
+  //   tap_kper > 0 (B MN-major; forward / data gradient): k iteration `it` belongs to tap t = it / tap_kper = (dy+1)*3 + (dx+1); A tile
+  //     from "batch" t of A (the weight is stored [tap][Cout][Cin]); B tile from copy dx at positions shifted by dy * tap_w (TMA
+  //     zero-fills rows above / below the image); tap_flip: the B side uses tap 8 - t (transposed convolution of the data gradient)
+  //   tap_n > 0 (B K-major; weight gradient): output column block n0 belongs to tap t = n0 / tap_n; B rows from copy dx, reduction
+  //     coordinate (positions) shifted by dy * tap_w
+  int tap_kper, tap_w, tap_flip, tap_n;
   int direct_store;    // 1: epilogue leaves through coalesced st.global / red.global.add.v4 instead of TMA store / reduce
   float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2;
   long long* trace;    // optional [CTA][tile slot < 8][8] clock stamps (profiling entry point dcnet_gemm_tf32_trace); nullptr = off
@@ -265,8 +272,8 @@ struct Gemm2P {
 template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO, bool ESLOT = false>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                  const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapO,
-                  const __grid_constant__ CUtensorMap mapO2, const Gemm2P p) {
+                  const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapB3,
+                  const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2, const Gemm2P p) {
   using G = Geo<EB>;
   constexpr int BK = G::BK;
   constexpr int BLK_BYTES = G::BLK_BYTES;
@@ -295,6 +302,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
     prefetch_tmap(&mapB2);
+    prefetch_tmap(&mapB3);
     prefetch_tmap(&mapO);
     // pair: a slot is released by ONE commit (multicast to both CTAs); the leader's accumulator stage is free once the epilogue
     // warps of BOTH CTAs have drained their halves
@@ -337,58 +345,74 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t* sA = smem + s * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
+          // where this k step's tiles come from
+          int a_k = it * BK, a_z = a_b, b_k = it * BK, b_n = n0;
+          const CUtensorMap* mb = &mapB;
+          if constexpr (B_MN) {
+            if (p.tap_kper > 0) {
+              const int tap = it / p.tap_kper, tb = p.tap_flip ? 8 - tap : tap;
+              a_k = b_k = (it - tap * p.tap_kper) * BK;
+              a_z = tap;
+              const int dxi = tb % 3;
+              mb = dxi == 0 ? &mapB : (dxi == 1 ? &mapB2 : &mapB3);
+              b_n = n0 + (tb / 3 - 1) * p.tap_w;
+            } else if (p.k_split > 0 && it >= p.k_split) {
+              mb = &mapB2;
+              b_k = (it - p.k_split) * BK;
+            }
+          } else {
+            if (p.tap_n > 0) {
+              const int tap = n0 / p.tap_n, dxi = tap % 3;
+              mb = dxi == 0 ? &mapB : (dxi == 1 ? &mapB2 : &mapB3);
+              b_n = n0 - tap * p.tap_n;
+              b_k = it * BK + (tap / 3 - 1) * p.tap_w;
+            } else if (p.n_split > 0 && n0 >= p.n_split) {
+              mb = &mapB2;
+              b_n = n0 - p.n_split;
+            }
+          }
           if constexpr (TWO) {
             // both CTAs' bytes complete on the leader's barrier; only the leader arms it
             if (crank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
             if constexpr (A_MN) {
 #pragma unroll
-              for (int j = 0; j < BM / G::MN_ELEMS; j++) tma_load_3d_2cta(sA + j * BLK_BYTES, &mapA, &full[s], m0 + G::MN_ELEMS * j, it * BK, a_b);
+              for (int j = 0; j < BM / G::MN_ELEMS; j++) tma_load_3d_2cta(sA + j * BLK_BYTES, &mapA, &full[s], m0 + G::MN_ELEMS * j, a_k, a_z);
             } else {
-              tma_load_3d_2cta(sA, &mapA, &full[s], it * BK, m0, a_b);
+              tma_load_3d_2cta(sA, &mapA, &full[s], a_k, m0, a_z);
             }
             if constexpr (B_MN) {
-              const bool src2 = p.k_split > 0 && it >= p.k_split;
-              const CUtensorMap* mb = src2 ? &mapB2 : &mapB;
-              const int kc = (src2 ? it - p.k_split : it) * BK;
               constexpr int HB = BN / 2 / G::MN_ELEMS;        // MN blocks of this CTA's half of the B tile
 #pragma unroll
-              for (int j = 0; j < HB; j++) tma_load_3d_2cta(sB + j * BLK_BYTES, mb, &full[s], n0 + G::MN_ELEMS * (crank * HB + j), kc, b_b);
+              for (int j = 0; j < HB; j++) tma_load_3d_2cta(sB + j * BLK_BYTES, mb, &full[s], b_n + G::MN_ELEMS * (crank * HB + j), b_k, b_b);
             } else {
-              const bool src2 = p.n_split > 0 && n0 >= p.n_split;
-              const int nrow = src2 ? n0 - p.n_split : n0;
-              tma_load_3d_2cta(sB, src2 ? &mapB2 : &mapB, &full[s], it * BK, nrow + crank * (BN / 2), b_b);
+              tma_load_3d_2cta(sB, mb, &full[s], b_k, b_n + crank * (BN / 2), b_b);
             }
             continue;
           }
           mbar_expect_tx(&full[s], STAGE_BYTES);
           if constexpr (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / G::MN_ELEMS; j++) tma_load_3d(sA + j * BLK_BYTES, &mapA, &full[s], m0 + G::MN_ELEMS * j, it * BK, a_b);
+            for (int j = 0; j < BM / G::MN_ELEMS; j++) tma_load_3d(sA + j * BLK_BYTES, &mapA, &full[s], m0 + G::MN_ELEMS * j, a_k, a_z);
           } else {
-            tma_load_3d(sA, &mapA, &full[s], it * BK, m0, a_b);
+            tma_load_3d(sA, &mapA, &full[s], a_k, m0, a_z);
           }
           if constexpr (B_MN) {
-            const bool src2 = p.k_split > 0 && it >= p.k_split;
-            const CUtensorMap* mb = src2 ? &mapB2 : &mapB;
-            const int kc = (src2 ? it - p.k_split : it) * BK;
             constexpr int NBLK = BN / G::MN_ELEMS;
             if constexpr (CS > 1) {
 #pragma unroll
               for (int j = 0; j < NBLK / CS; j++) {
                 const int jj = crank * (NBLK / CS) + j;
-                tma_load_3d_mc(sB + jj * BLK_BYTES, mb, &full[s], n0 + G::MN_ELEMS * jj, kc, b_b, cmask);
+                tma_load_3d_mc(sB + jj * BLK_BYTES, mb, &full[s], b_n + G::MN_ELEMS * jj, b_k, b_b, cmask);
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < NBLK; j++) tma_load_3d(sB + j * BLK_BYTES, mb, &full[s], n0 + G::MN_ELEMS * j, kc, b_b);
+              for (int j = 0; j < NBLK; j++) tma_load_3d(sB + j * BLK_BYTES, mb, &full[s], b_n + G::MN_ELEMS * j, b_k, b_b);
             }
           } else {
-            const bool src2 = p.n_split > 0 && n0 >= p.n_split;
-            const int nrow = src2 ? n0 - p.n_split : n0;
             if constexpr (CS > 1)
-              tma_load_3d_mc(sB + crank * (BN / CS) * 128, src2 ? &mapB2 : &mapB, &full[s], it * BK, nrow + crank * (BN / CS), b_b, cmask);
+              tma_load_3d_mc(sB + crank * (BN / CS) * 128, mb, &full[s], b_k, b_n + crank * (BN / CS), b_b, cmask);
             else
-              tma_load_3d(sB, src2 ? &mapB2 : &mapB, &full[s], it * BK, nrow, b_b);
+              tma_load_3d(sB, mb, &full[s], b_k, b_n, b_b);
           }
         }
       }
@@ -632,8 +656,8 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 }
 
 template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO = false, bool ESLOT = false>
-int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
-                 const Gemm2P& p, cudaStream_t st) {
+int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mb3, const CUtensorMap& mo,
+                 const CUtensorMap& mo2, const Gemm2P& p, cudaStream_t st) {
   constexpr int smem = STAGES * (A_BYTES + (TWO ? BN / 2 : BN) * 128) + 4 * GEMM2_NSLOT * 32 * 128 + (ESLOT ? 4 * 2 * 32 * 128 : 0) + 1024 + 256;
   static_assert(smem <= 232448, "umma_gemm2: shared memory budget");
   auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB, CS, TWO, ESLOT>;
@@ -662,24 +686,24 @@ int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap
   }
   if (ncl > ngroups) ncl = ngroups;
   cfg.gridDim = dim3(ncl * CS);
-  DCNET_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mb2, mo, mo2, p), "umma_gemm2.launch");
+  DCNET_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mb2, mb3, mo, mo2, p), "umma_gemm2.launch");
   DCNET_LAUNCH_OK("umma_gemm2");
   return 0;
 }
 
 // cluster size: the M tiles of a group share B.  4 when M has >= 4 tiles (C = 512 channels, N >= 512 positions), else 2, else 1.
 template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
-int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mo, const CUtensorMap& mo2,
-                const Gemm2P& p, int cs, cudaStream_t st) {
+int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mb3, const CUtensorMap& mo,
+                const CUtensorMap& mo2, const Gemm2P& p, int cs, cudaStream_t st) {
   if constexpr (BN == 256 && EB == 4) {
     if constexpr (A_MN && B_MN) {      // the dS epilogue belongs to dP = dO^T Fb: both operands MN-major
-      if (cs == -2 && p.epi_exp == 2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR - 1, EB, 2, true, true>(ma, mb, mb2, mo, mo2, p, st);
+      if (cs == -2 && p.epi_exp == 2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR - 1, EB, 2, true, true>(ma, mb, mb2, mb3, mo, mo2, p, st);
     }
-    if (cs == -2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR, EB, 2, true>(ma, mb, mb2, mo, mo2, p, st);
+    if (cs == -2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR, EB, 2, true>(ma, mb, mb2, mb3, mo, mo2, p, st);
   }
-  if (cs == 4) return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 4>(ma, mb, mb2, mo, mo2, p, st);
-  if (cs == 2) return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 2>(ma, mb, mb2, mo, mo2, p, st);
-  return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 1>(ma, mb, mb2, mo, mo2, p, st);
+  if (cs == 4) return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 4>(ma, mb, mb2, mb3, mo, mo2, p, st);
+  if (cs == 2) return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 2>(ma, mb, mb2, mb3, mo, mo2, p, st);
+  return launch_cfg2c<A_MN, B_MN, BN, STAGES, EB, 1>(ma, mb, mb2, mb3, mo, mo2, p, st);
 }
 
 template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
@@ -750,16 +774,21 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   // CTA pairs (cta_group::2) for the wide tf32 tiles: halves the B traffic per output tile
   const bool pair = out_ok && g_pair_mode && BN == 256 && !A.bf16 && tiles_m >= 2;
   if (pair) cs = 2;
-  CUtensorMap ma, mb, mb2;
+  CUtensorMap ma, mb, mb2, mb3;
   DCNET_TRY(make_operand_map(&ma, A, BM));
   DCNET_TRY(make_operand_map(&mb, B, BN / cs));
   if (B2) DCNET_TRY(make_operand_map(&mb2, *B2, BN / cs)); else mb2 = mb;
+  if (e.B3) DCNET_TRY(make_operand_map(&mb3, *e.B3, BN / cs)); else mb3 = mb;
+  const bool taps = e.tap_kper > 0 || e.tap_n > 0;
+  DCNET_CHECK_ARG(!taps || (out_ok && B2 && e.B3 && !A.bf16 && (e.tap_kper == 0) != (e.tap_n == 0)), "umma_gemm: tap mode needs three B sources and the persistent kernel");
+  DCNET_CHECK_ARG(e.tap_kper == 0 || (B.mn_major && K == 9 * e.tap_kper * BK), "umma_gemm: tap_kper: B must be MN-major and K = 9 taps");
+  DCNET_CHECK_ARG(e.tap_n == 0 || (!B.mn_major && e.tap_n % BN == 0 && N == 9 * e.tap_n), "umma_gemm: tap_n: B must be K-major, N = 9 taps of whole tiles");
   if (pair) cs = -2;
   GemmP p{};
   p.M_valid = M; p.N_valid = N;
   p.k_iters = (K + BK - 1) / BK;
-  p.k_split = (B.mn_major && B2) ? k_split_elems / BK : 0;
-  p.n_split = (!B.mn_major && B2) ? n_split : 0;
+  p.k_split = (B.mn_major && B2 && !taps) ? k_split_elems / BK : 0;
+  p.n_split = (!B.mn_major && B2 && !taps) ? n_split : 0;
   p.m_split = e.m_split;
   p.a_batched = A.batches > 0; p.b_batched = B.batches > 0;
   p.idxA = e.idxA; p.idxB = e.idxB; p.idxC = e.idxC;
@@ -779,6 +808,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     q.tiles_m = ceil_div(M, BM); q.tiles_n = ceil_div(N, BN); q.ntiles = q.tiles_m * q.tiles_n * batch;
     q.alpha = e.alpha; q.atomic = e.atomic; q.u = e.u; q.ldu = e.ldu; q.cc = e.cc; q.ldcc = e.ldcc; q.sum = e.sum; q.sumsq = e.sumsq;
     q.epi_exp = e.epi_exp; q.u2 = e.u2; q.cc_sb = e.cc_sb; q.sum_ldz = e.sum_ldz;
+    q.tap_kper = e.tap_kper; q.tap_w = e.tap_w; q.tap_flip = e.tap_flip; q.tap_n = e.tap_n;
     int want_chunks = e.k_chunks;
     if (auto_split) {
       const long long tiles = (long long)q.ntiles;
@@ -810,13 +840,13 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     #define DISPATCH2(AM, BMJ)                                                                           \
     if (am == AM && bm == BMJ) {                                                                     \
       if (A.bf16) {                                                                                  \
-        if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 2>(ma, mb, mb2, mo, mo2, q, cs, st);     \
-        if (BN == 256) return launch_cfg2<AM, BMJ, 256, GEMM2_STAGES256, 2>(ma, mb, mb2, mo, mo2, q, cs, st);   \
-        return launch_cfg2<AM, BMJ, 128, 4, 2>(ma, mb, mb2, mo, mo2, q, cs, st);                  \
+        if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 2>(ma, mb, mb2, mb3, mo, mo2, q, cs, st);     \
+        if (BN == 256) return launch_cfg2<AM, BMJ, 256, GEMM2_STAGES256, 2>(ma, mb, mb2, mb3, mo, mo2, q, cs, st);   \
+        return launch_cfg2<AM, BMJ, 128, 4, 2>(ma, mb, mb2, mb3, mo, mo2, q, cs, st);                  \
       }                                                                                              \
-      if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 4>(ma, mb, mb2, mo, mo2, q, cs, st);       \
-      if (BN == 256) return launch_cfg2<AM, BMJ, 256, GEMM2_STAGES256, 4>(ma, mb, mb2, mo, mo2, q, cs, st);     \
-      return launch_cfg2<AM, BMJ, 128, 4, 4>(ma, mb, mb2, mo, mo2, q, cs, st);                    \
+      if (BN == 64) return launch_cfg2<AM, BMJ, 64, 4, 4>(ma, mb, mb2, mb3, mo, mo2, q, cs, st);       \
+      if (BN == 256) return launch_cfg2<AM, BMJ, 256, GEMM2_STAGES256, 4>(ma, mb, mb2, mb3, mo, mo2, q, cs, st);     \
+      return launch_cfg2<AM, BMJ, 128, 4, 4>(ma, mb, mb2, mb3, mo, mo2, q, cs, st);                    \
     }
     DISPATCH2(0, 0) DISPATCH2(0, 1) DISPATCH2(1, 0) DISPATCH2(1, 1)
 #undef DISPATCH2

@@ -172,13 +172,30 @@ class grounding_model(nn.Module):
         return [self.map_visual_scale(raw_fvisu[s], s) for s in range(3)]
 
     def _head_layer(self, m, y):
-        """SURVEY 8(f) row 1, first step into the grounding head (model/DCNet_model.py:316-337, :505-506): its 1x1
-        ConvBatchNormReLU layers (fcn_emb[s][2]: 512->512, fcn_out[s][0]: 512->256) run on the same tcgen05 GEMM + fused BN kernels
-        as the rest of the path; the 3x3 conv and the final 1x1 conv with bias stay cuDNN."""
-        if self.head_on_tcgen05 and isinstance(m, ConvBatchNormReLU) and m.conv.kernel_size == (1, 1) and m.conv.out_channels in (256, 512) \
-                and m.conv.in_channels % 128 == 0:
-            B, _, h, w = y.shape
-            return m.fused(y.flatten(2), precision=self.precision).view(B, -1, h, w)
+        """SURVEY 8(f) row 1, the grounding head (model/DCNet_model.py:316-337, :505-506) on this library's kernels: the 3x3
+        ConvBatchNormReLU (fcn_emb[s][1]) as an implicit GEMM on tcgen05 (ops.conv3x3_bn_act), the 1x1 ConvBatchNormReLU layers
+        (fcn_emb[s][2]: 512->512, fcn_out[s][0]: 512->256) on the tcgen05 GEMM + fused BN kernels of the rest of the path, the final
+        Conv2d(256, 15, 1) with bias as an exact-fp32 pass (ops.conv1x1_bias).  Shapes the 3x3 kernel cannot address (13x13 maps:
+        169 positions, row pitch not a multiple of 16 bytes) and the exact-fp32 mode keep the library convolution."""
+        B, _, h, w = y.shape
+        if not self.head_on_tcgen05 or not y.is_cuda:
+            return m(y)
+        tf32 = self.precision == ops.TENSOR_TF32
+        if isinstance(m, ConvBatchNormReLU) and m.conv.kernel_size == (1, 1) and m.conv.out_channels in (256, 512) and m.conv.in_channels % 128 == 0:
+            # inputs rounded by the producing layer of this head, outputs rounded for the next one
+            out = m.fused(y.flatten(2), precision=self.precision, round_in=not getattr(y, "_dcnet_rounded", False), round_out=tf32).view(B, -1, h, w)
+            out._dcnet_rounded = tf32
+            return out
+        if tf32 and isinstance(m, ConvBatchNormReLU) and m.conv.kernel_size == (3, 3) and m.conv.stride == (1, 1) and m.conv.padding == (1, 1) \
+                and m.conv.dilation == (1, 1) and ops.conv3x3_supported(m.conv.in_channels, m.conv.out_channels, h, w):
+            bn = m.bn
+            out = ops.conv3x3_bn_act(y.flatten(2), m.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.training, h, w,
+                                     momentum=bn.momentum, eps=bn.eps, slope=m.slope, num_batches_tracked=bn.num_batches_tracked,
+                                     round_out=True).view(B, -1, h, w)
+            out._dcnet_rounded = True
+            return out
+        if isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1) and m.bias is not None:
+            return ops.conv1x1_bias(y.flatten(2), m.weight.view(m.out_channels, -1), m.bias).view(B, -1, h, w)
         return m(y)
 
     head_on_tcgen05 = True

@@ -502,6 +502,123 @@ def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2
                             flang, coords, bool(round_in), bool(round_out), bool(stage_out))
 
 
+class _Conv3x3BNAct(torch.autograd.Function):
+    """ConvBatchNormReLU(C, C, 3, 1, 1) of the grounding head (model/DCNet_model.py:316-337) on this library's
+    kernels: implicit-GEMM 3x3 convolution on tcgen05 (csrc/conv3x3.cu: three column-shifted copies of the map, the nine taps inside the
+    K loop, rows off the image zero-filled by TMA), BatchNorm statistics from its epilogue, the BN / activation kernels of the 1x1 layers."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, training, momentum, eps, slope, nbt, h, w, round_out):
+        x = _c(x, name="x")
+        weight, gamma, beta = _c(weight, name="weight"), _c(gamma, name="gamma"), _c(beta, name="beta")
+        B, Cin, N = x.shape
+        Cout = weight.shape[0]
+        if N != h * w or tuple(weight.shape) != (Cout, Cin, 3, 3):
+            raise ValueError("conv3x3_bn_act: x %s, weight %s, h*w = %d" % (tuple(x.shape), tuple(weight.shape), h * w))
+        if not _lib.lib().dcnet_conv3x3_supported(Cin, Cout, h, w):
+            raise RuntimeError("conv3x3_bn_act: shape (Cin=%d, Cout=%d, %dx%d) is not supported by the tcgen05 kernel" % (Cin, Cout, h, w))
+        dev, st = x.device, _st()
+        rn = _RN_FLAG if RN_TF32 else 0
+        wq = torch.empty(9, Cout, Cin, device=dev, dtype=F32)
+        _lib.call("dcnet_conv3x3_pack_weight", _p(weight), _p(wq), Cout, Cin, rn, st)
+        xm, xp, x0 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        _lib.call("dcnet_conv3x3_shift", _p(x), _p(xm), _p(xp), _p(x0), B * Cin * h, w, rn, st)
+        z = torch.empty(B, Cout, N, device=dev, dtype=F32)
+        mean = torch.empty(Cout, device=dev, dtype=F32)
+        invstd = torch.empty(Cout, device=dev, dtype=F32)
+        if training:
+            sums = torch.empty(2 * Cout, device=dev, dtype=F32)
+            _lib.call("dcnet_conv3x3_fwd", _p(xm), _p(x0), _p(xp), _p(wq), _p(z), B, Cin, Cout, h, w, _p(sums), st)
+            _lib.call("dcnet_bn_finalize", _p(sums), B * N, Cout, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), _p(nbt), st)
+        else:
+            _lib.call("dcnet_conv3x3_fwd", _p(xm), _p(x0), _p(xp), _p(wq), _p(z), B, Cin, Cout, h, w, None, st)
+            _lib.call("dcnet_bn_eval_stats", _p(running_mean), _p(running_var), Cout, eps, _p(mean), _p(invstd), st)
+        y = torch.empty_like(z)
+        _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, (_RN_FLAG if (RN_TF32 and round_out) else 0), _p(y),
+                  None, None, None, None, B, Cout, N, st)
+        ctx.save_for_backward(xm, x0, xp, wq, gamma, beta, z, mean, invstd)
+        ctx.cfg = (training, slope, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xm, x0, xp, wq, gamma, beta, z, mean, invstd = ctx.saved_tensors
+        training, slope, h, w = ctx.cfg
+        B, Cin, N = x0.shape
+        Cout = wq.shape[1]
+        dev, st = x0.device, _st()
+        dy = _c(dy, name="dy")
+        rn = _RN_FLAG if RN_TF32 else 0
+        dv = torch.empty_like(z)
+        sums = torch.zeros(2, Cout, device=dev, dtype=F32)
+        _lib.call("dcnet_bn_act_bwd_reduce", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, 0, _p(dy), None, None, None, None, _p(dv),
+                  _p(sums[0]), _p(sums[1]), None, None, B, Cout, N, st)
+        _lib.call("dcnet_bn_act_bwd_apply", _p(z), _p(mean), _p(invstd), _p(gamma), _p(dv), _p(sums[0]), _p(sums[1]), int(training) | rn, _p(dv),
+                  B, Cout, N, st)
+        dz = dv
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            dzm, dzp = torch.empty_like(dz), torch.empty_like(dz)
+            _lib.call("dcnet_conv3x3_shift", _p(dz), _p(dzm), _p(dzp), None, B * Cout * h, w, 0, st)     # dz is rounded already
+            dx = torch.empty_like(x0)
+            _lib.call("dcnet_conv3x3_bwd_data", _p(dzm), _p(dz), _p(dzp), _p(wq), _p(dx), B, Cin, Cout, h, w, st)
+        if ctx.needs_input_grad[1]:
+            dWp = torch.empty(Cout, 9, Cin, device=dev, dtype=F32)
+            dW = torch.empty(Cout, Cin, 3, 3, device=dev, dtype=F32)
+            _lib.call("dcnet_conv3x3_bwd_weight", _p(dz), _p(xm), _p(x0), _p(xp), _p(dWp), _p(dW), B, Cin, Cout, h, w, st)
+        return dx, dW, sums[1], sums[0], None, None, None, None, None, None, None, None, None, None
+
+
+def conv3x3_supported(Cin, Cout, h, w):
+    return bool(_lib.lib().dcnet_conv3x3_supported(int(Cin), int(Cout), int(h), int(w)))
+
+
+def conv3x3_bn_act(x, weight, gamma, beta, running_mean, running_var, training, h, w, momentum=0.999, eps=1e-5, slope=0.0,
+                   num_batches_tracked=None, round_out=False):
+    """x [B,Cin,h*w], weight [Cout,Cin,3,3] (stride 1, padding 1, no bias) -> act(BN(conv3x3(x))) [B,Cout,h*w]; tcgen05 tf32."""
+    return _Conv3x3BNAct.apply(x, weight, gamma, beta, running_mean, running_var, bool(training), float(momentum), float(eps), float(slope),
+                               num_batches_tracked if training else None, int(h), int(w), bool(round_out))
+
+
+class _Conv1x1Bias(torch.autograd.Function):
+    """fcn_out[s][-1] = nn.Conv2d(256, 15, 1) with bias (model/DCNet_model.py:329-337): 15 output channels -- a memory-bound pass over
+    the 256-channel map, exact fp32 on the CUDA cores (dcnet_conv1x1_* at precision 0); the bias enters as the per-image term u."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, weight, bias = _c(x, name="x"), _c(weight, name="weight"), _c(bias, name="bias")
+        B, K, N = x.shape
+        C = weight.shape[0]
+        u = bias[None, :].expand(B, C).contiguous()
+        z = torch.empty(B, C, N, device=x.device, dtype=F32)
+        _lib.call("dcnet_conv1x1_fwd", _p(x), K, None, 0, _p(weight), K, _p(u), None, _p(z), B, C, N, None, EXACT_FP32, _st())
+        ctx.save_for_backward(x, weight)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, weight = ctx.saved_tensors
+        B, K, N = x.shape
+        C = weight.shape[0]
+        dz = _c(dz, name="dz")
+        st = _st()
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.call("dcnet_conv1x1_bwd_data", _p(dz), _p(weight), K, _p(dx), K, None, 0, B, C, N, EXACT_FP32, st)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dW = torch.empty(C, K, device=x.device, dtype=F32)
+            du = torch.empty(B, C, device=x.device, dtype=F32)
+            _lib.call("dcnet_conv1x1_bwd_weight", _p(dz), _p(x), K, None, 0, _p(dW), K, _p(du), None, B, C, N, EXACT_FP32, st)
+            db = du.sum(0)
+        return dx, dW, db
+
+
+def conv1x1_bias(x, weight, bias):
+    """x [B,K,N], weight [C,K], bias [C] -> [B,C,N]"""
+    return _Conv1x1Bias.apply(x, weight, bias)
+
+
 class _FuseTerms(torch.autograd.Function):
     """a8 as a node of its own: (u, cc) = (W_l flang, W_c coords) and their backward through dcnet_fuse_terms_*.  conv_bn_act does the
     same inline when it is given (flang, coords); this form lets a caller issue the terms early / on another stream (HotPath)."""

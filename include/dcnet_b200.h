@@ -106,6 +106,26 @@ DCNET_API int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, f
 DCNET_API int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1, const float* x2, int K2,
                                        float* dW, int ldw, float* du, float* dcc, int B, int C, int N, int precision, void* stream);
 
+/* ---- 8(f) row 1: the grounding head's 3x3 convolution (fcn_emb[s][1] = ConvBatchNormReLU(C, C, 3, 1, 1), model/DCNet_model.py:316-337,
+ * :505-506; ConvBatchNormReLU model/darknet.py:118-156) as an implicit GEMM on tcgen05 (csrc/conv3x3.cu).  Maps are [B, C, N = h*w].
+ *   dcnet_conv3x3_shift:       x_m[p] = x[p-1], x_p[p] = x[p+1] inside each image row of w positions (zero at the border column); x_0
+ *                              (optional) = copy of x; flags = DCNET_RN_TF32 rounds all outputs.  rows = B*C*h.
+ *   dcnet_conv3x3_pack_weight: W [Cout,Cin,3,3] -> Wq [9,Cout,Cin] (flags = DCNET_RN_TF32: rounded)
+ *   dcnet_conv3x3_fwd:         z [B,Cout,N] = conv3x3(x) (stride 1, zero padding 1, no bias); stat_sums like dcnet_conv1x1_fwd
+ *   dcnet_conv3x3_bwd_data:    dx [B,Cin,N] from the three shifted copies of dz [B,Cout,N]
+ *   dcnet_conv3x3_bwd_weight:  dW [Cout,Cin,3,3] (overwritten); dWp [Cout,9,Cin] is scratch
+ * Needs Cin, Cout multiples of 256 and w % 4 == 0 (a TMA box shifted by one image row must start 16-byte aligned):
+ * dcnet_conv3x3_supported; other shapes stay with the caller's library convolution.                                              */
+DCNET_API int dcnet_conv3x3_supported(int Cin, int Cout, int h, int w);
+DCNET_API int dcnet_conv3x3_shift(const float* x, float* x_m, float* x_p, float* x_0, long long rows, int w, int flags, void* stream);
+DCNET_API int dcnet_conv3x3_pack_weight(const float* W, float* Wq, int Cout, int Cin, int flags, void* stream);
+DCNET_API int dcnet_conv3x3_fwd(const float* x_m, const float* x_0, const float* x_p, const float* Wq, float* z,
+                                int B, int Cin, int Cout, int h, int w, float* stat_sums, void* stream);
+DCNET_API int dcnet_conv3x3_bwd_data(const float* dz_m, const float* dz_0, const float* dz_p, const float* Wq, float* dx,
+                                     int B, int Cin, int Cout, int h, int w, void* stream);
+DCNET_API int dcnet_conv3x3_bwd_weight(const float* dz, const float* x_m, const float* x_0, const float* x_p, float* dWp, float* dW,
+                                       int B, int Cin, int Cout, int h, int w, void* stream);
+
 /* ---- a8: text / coordinate terms of the split-weight fusion (model/DCNet_model.py:489-505; ancestor
  * model/grounding_model_semantic_attn.py:266-281).  W [C,ldw] = [W_v | W_l | W_c]: u [B,C] = flang [B,Ct] W_l^T with
  * W_l = W[:, col_l:col_l+Ct]; cc [C,N] = W_c coord with W_c = W[:, col_c:col_c+8], coord [8,N] (dcnet_coord_map).  coord / cc may be

@@ -696,3 +696,107 @@ def test_fusion_layer_with_text_and_coordinate_terms(precision, N):
     for lo, hi in ((C, C + Ct), (C + Ct, C + Ct + 8)):
         e = min(rel(c['w'].grad[:, lo:hi], t64['w'].grad[:, lo:hi]), rel(c['w'].grad[:, lo:hi], t32['w'].grad[:, lo:hi]))
         assert e < tol_b, (lo, hi, e)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the grounding head's 3x3 ConvBatchNormReLU and final 1x1 conv with bias on this library's kernels
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,h,w", [(2, 512, 8, 8), (3, 512, 16, 16), (2, 256, 32, 32), (1, 512, 52, 52), (2, 512, 6, 12), (1, 256, 20, 8)])
+def test_conv3x3_contractions_vs_conv2d(B, C, h, w):
+    """the three contractions of csrc/conv3x3.cu on their own (linear, no activation): forward against F.conv2d(padding=1), data
+    gradient against conv_transpose2d, weight gradient against the autograd of conv2d -- all in fp64 on the same tf32-rounded
+    operands (what the kernels are handed by their producers), bar 5e-5 (exact tf32 products, the tensor core's fp32 accumulation over 4608 terms: measured 1e-5) and 1e-3
+    against the unrounded fp64 result."""
+    from dcnet_b200 import _lib
+    g = gen(300 + h * w)
+    N = h * w
+    x = torch.randn(B, C, N, generator=g).to(DEV)
+    W = (torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(DEV)
+    dz = torch.randn(B, C, N, generator=g).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    RN = 0x100
+    wq = torch.empty(9, C, C, device=DEV)
+    _lib.call("dcnet_conv3x3_pack_weight", W.data_ptr(), wq.data_ptr(), C, C, RN, st)
+    xm, x0, xp = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    _lib.call("dcnet_conv3x3_shift", x.data_ptr(), xm.data_ptr(), xp.data_ptr(), x0.data_ptr(), B * C * h, w, RN, st)
+    # the shifted copies themselves
+    x4 = x0.view(B, C, h, w)
+    assert torch.equal(xm.view(B, C, h, w)[..., 1:], x4[..., :-1]) and float(xm.view(B, C, h, w)[..., 0].abs().max()) == 0.0
+    assert torch.equal(xp.view(B, C, h, w)[..., :-1], x4[..., 1:]) and float(xp.view(B, C, h, w)[..., -1].abs().max()) == 0.0
+    assert rel(x0, x) < 3e-4 and torch.equal(wq.permute(1, 2, 0).reshape(C, C, 3, 3), ops.round_tf32(W))
+    z = torch.empty(B, C, N, device=DEV)
+    sums = torch.empty(2 * C, device=DEV)
+    _lib.call("dcnet_conv3x3_fwd", xm.data_ptr(), x0.data_ptr(), xp.data_ptr(), wq.data_ptr(), z.data_ptr(), B, C, C, h, w, sums.data_ptr(), st)
+    Wr = ops.round_tf32(W).double().cpu().requires_grad_(True)
+    xr = x0.double().cpu().view(B, C, h, w).requires_grad_(True)
+    zr = torch.nn.functional.conv2d(xr, Wr, padding=1)
+    e_f = rel(z.view(B, C, h, w), zr)
+    e_f_exact = rel(z.view(B, C, h, w), torch.nn.functional.conv2d(x.double().cpu().view(B, C, h, w), W.double().cpu(), padding=1))
+    assert rel(sums[:C], zr.sum((0, 2, 3))) < 1e-4 and rel(sums[C:], (zr * zr).sum((0, 2, 3))) < 1e-4
+    dzr = ops.round_tf32(dz)
+    zr.backward(dzr.double().cpu().view(B, C, h, w))
+    dzm, dzp = torch.empty_like(dz), torch.empty_like(dz)
+    _lib.call("dcnet_conv3x3_shift", dzr.data_ptr(), dzm.data_ptr(), dzp.data_ptr(), None, B * C * h, w, 0, st)
+    dx = torch.empty_like(x)
+    _lib.call("dcnet_conv3x3_bwd_data", dzm.data_ptr(), dzr.data_ptr(), dzp.data_ptr(), wq.data_ptr(), dx.data_ptr(), B, C, C, h, w, st)
+    dWp = torch.empty(C, 9, C, device=DEV)
+    dW = torch.empty(C, C, 3, 3, device=DEV)
+    _lib.call("dcnet_conv3x3_bwd_weight", dzr.data_ptr(), xm.data_ptr(), x0.data_ptr(), xp.data_ptr(), dWp.data_ptr(), dW.data_ptr(), B, C, C, h, w, st)
+    e_dx, e_dw = rel(dx.view(B, C, h, w), xr.grad), rel(dW, Wr.grad)
+    print("conv3x3 %dx%d C=%d B=%d: fwd %.1e (vs unrounded fp64 %.1e), dx %.1e, dW %.1e" % (h, w, C, B, e_f, e_f_exact, e_dx, e_dw))
+    assert e_f < 5e-5 and e_dx < 5e-5 and e_dw < 5e-5 and e_f_exact < 1e-3, (e_f, e_f_exact, e_dx, e_dw)
+
+
+@pytest.mark.parametrize("B,h,w,training", [(2, 16, 16, True), (1, 52, 52, True), (3, 8, 8, False)])
+def test_conv3x3_bn_act_forward_backward(B, h, w, training):
+    """ops.conv3x3_bn_act = ConvBatchNormReLU(512, 512, 3, 1, 1) (model/darknet.py:118-156) against plain PyTorch in fp64: outputs and
+    running statistics 1e-3; gradients at the product's own ReLU pattern (the derivative of the function it evaluated) 1e-3."""
+    g = gen(310 + h)
+    C, N = 512, h * w
+    x = torch.randn(B, C, N, generator=g)
+    W = torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    rm0, rv0 = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    go = torch.randn(B, C, N, generator=g)
+    c = [t.to(DEV).requires_grad_(True) for t in (x, W, gamma, beta)]
+    rm, rv = rm0.to(DEV), rv0.to(DEV)
+    nbt = torch.zeros((), dtype=torch.long, device=DEV)
+    y = ops.conv3x3_bn_act(c[0], c[1], c[2], c[3], rm, rv, training, h, w, num_batches_tracked=nbt)
+    y.backward(go.to(DEV))
+    r = [t.double().requires_grad_(True) for t in (x, W, gamma, beta)]
+    z = torch.nn.functional.conv2d(r[0].view(B, C, h, w), r[1], padding=1)
+    rmr, rvr = rm0.double().clone(), rv0.double().clone()
+    zn = torch.nn.functional.batch_norm(z, rmr, rvr, r[2], r[3], training, 0.999, 1e-5)
+    yr = torch.relu(zn).view(B, C, N)
+    assert rel(y, yr) < 1e-3, rel(y, yr)
+    if training:
+        assert rel(rm, rmr) < 1e-3 and rel(rv, rvr) < 1e-3 and int(nbt) == 1
+    mask = (y.detach() > 0).cpu()
+    (zn.view(B, C, N) * mask).backward(go.double())
+    errs = [rel(a.grad, b.grad) for a, b in zip(c, r)]
+    print("conv3x3_bn_act %dx%d train=%s: fwd %.1e, grads (x, W, gamma, beta) %s" % (h, w, training, rel(y, yr), ["%.1e" % e for e in errs]))
+    assert max(errs) < 1e-3, errs
+
+
+def test_conv3x3_refuses_unaligned_rows():
+    assert not ops.conv3x3_supported(512, 512, 26, 26) and not ops.conv3x3_supported(512, 512, 13, 13) and ops.conv3x3_supported(512, 512, 52, 52)
+    x = torch.zeros(1, 512, 676, device=DEV); W = torch.zeros(512, 512, 3, 3, device=DEV); v = torch.ones(512, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.conv3x3_bn_act(x, W, v, v, v.clone(), v.clone(), True, 26, 26)
+
+
+def test_conv1x1_bias_head_output_layer():
+    """fcn_out[s][1] = nn.Conv2d(256, 15, 1) with bias (model/DCNet_model.py:329-337): exact fp32"""
+    g = gen(320)
+    B, K, C, N = 3, 256, 15, 676
+    x, W, b = torch.randn(B, K, N, generator=g), torch.randn(C, K, generator=g) / 16, torch.randn(C, generator=g)
+    go = torch.randn(B, C, N, generator=g)
+    c = [t.to(DEV).requires_grad_(True) for t in (x, W, b)]
+    out = ops.conv1x1_bias(*c)
+    out.backward(go.to(DEV))
+    r = [t.double().requires_grad_(True) for t in (x, W, b)]
+    ref = torch.einsum('ck,bkn->bcn', r[1], r[0]) + r[2][None, :, None]
+    ref.backward(go.double())
+    assert rel(out, ref) < 1e-5
+    for a, b_ in zip(c, r):
+        assert rel(a.grad, b_.grad) < 2e-5, rel(a.grad, b_.grad)
