@@ -315,16 +315,17 @@ class grounding_model(nn.Module):
 
     # inference: the [B,SN,SN] relation tensor of the location branch is never built (ops.loc_rank8)
     rank8_location = True
-    # training: the same identity through differentiable torch ops -- no [B,SN,SN] tensor (1.6 GB for 32 images at 416x416), no
-    # SN-long GEMM.  Equal to the materialised form in fp64 on CPU (tests/test_host_cpu.py::test_location_branch_rank8_training_form);
-    # in fp32 on the GPU scores and running statistics agree to 2e-5 and all gradients to 5e-3 except the BatchNorm1d(8) bias of
-    # loc_embedding, an ill-conditioned sum whose two orders of evaluation differ by 4-8 % (tests/test_gpu_model.py::
-    # test_location_branch_rank8_training_form_on_gpu).  Opt-in for that reason: the default keeps the reference's evaluation order.
-    rank8_location_train = False
+    # training: the same identity with batch statistics and the backward on this library's kernels (ops.loc_rank8_train: no [B,SN,SN]
+    # tensor -- 1.6 GB for 32 images at 416x416 --, no [B*SN,C] activations).  The embedding of a position is the same for every image
+    # (same coordinates; BatchNorm1d(8) batch statistics over B copies of the same rows), so the kernels take E = emb[0]: parameter
+    # gradients of loc_embedding are sums over the images and do not change (tests/test_gpu_model.py).
+    # "torch": the identity through differentiable torch ops (round 1); False: the reference's materialised evaluation.
+    rank8_location_train = "kernels"
 
     def location_branch(self, coords, obj_score, context, embedded, word_id):
-        """:556-610; written for any number of positions.  Training (batch statistics, gradients) stays PyTorch; at inference on
-        CUDA the relation matrix is kept in its rank-8 form and the branch runs in three kernels of this library."""
+        """:556-610; written for any number of positions.  On CUDA the relation matrix is kept in its rank-8 form: three kernels of
+        this library at inference, dcnet_loc_rank8_train_fwd / _bwd in training; the tiny coordinate embedding (Linear(8,8) +
+        BatchNorm1d(8) + ReLU on the [B*SN, 8] coordinate rows, exactly the reference's evaluation) and the phrase attention stay torch."""
         B = obj_score[0].shape[0]
         _, flang_loc = self.loc_attn(context, embedded, word_id)
         flang_loc = F.normalize(flang_loc, p=2, dim=1)
@@ -339,6 +340,12 @@ class grounding_model(nn.Module):
         coord_map_ = torch.cat([c.t() for c in coords], 0)[None].expand(B, -1, -1)
         emb = self.loc_embedding(coord_map_.reshape(-1, 8)).reshape(B, SN, -1)
         emb = F.normalize(emb, p=2, dim=2)
+        lt = self.loc_text_embedding
+        if self.rank8_location_train == "kernels" and self.training and obj.is_cuda and isinstance(lt[1], nn.BatchNorm1d) \
+                and isinstance(lt[2], nn.ReLU) and lt[1].momentum is not None and lt[0].out_features % 32 == 0:
+            lin, bn = lt[0], lt[1]
+            return ops.loc_rank8_train(emb[0], obj, lin.weight, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                       bn.num_batches_tracked, bn.momentum, bn.eps, flang_loc)
         if self.rank8_location_train:
             # same identity with differentiable torch ops: Linear(bmm(E,E^T)*obj) = E (E^T diag(obj) W^T); the modules (and their
             # batch statistics / running-stat updates) are the reference's, only the [B,SN,SN] tensor and its SN-long GEMM are gone

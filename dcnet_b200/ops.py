@@ -137,6 +137,55 @@ def loc_rank8(E, obj, W, bias, bn_scale, bn_shift, flang, return_raw=False):
     return (score, raw, G) if return_raw else score
 
 
+class _LocRank8Train(torch.autograd.Function):
+    """SURVEY 8(f) row 2, training: the location branch (model/DCNet_model.py:556-603) in its rank-8 form on this library's kernels --
+    Linear(SN -> C) on bmm(E, E^T) * obj, BatchNorm1d with BATCH statistics (running statistics updated like nn.BatchNorm1d), ReLU,
+    channel norm, dot with the phrase vector, per-image min-max -- and its backward (dcnet_loc_rank8_train_fwd / _bwd).  Neither the
+    [B,SN,SN] relation tensor nor the [B*SN,C] activations exist."""
+
+    @staticmethod
+    def forward(ctx, E, obj, W, bias, gamma, beta, running_mean, running_var, nbt, momentum, eps, flang):
+        E, obj, W, flang = _c(E, name="E"), _c(obj, name="obj"), _c(W, name="W"), _c(flang, name="flang")
+        gamma, beta = _c(gamma, name="gamma"), _c(beta, name="beta")
+        bias = None if bias is None else _c(bias, name="bias")
+        B, SN = obj.shape
+        C = W.shape[0]
+        if E.shape != (SN, 8) or W.shape[1] != SN or flang.shape != (B, C) or C % 32 != 0:
+            raise ValueError(f"loc_rank8_train: shapes E {tuple(E.shape)}, obj {tuple(obj.shape)}, W {tuple(W.shape)}, flang {tuple(flang.shape)}")
+        dev = obj.device
+        G = torch.empty(B, C, 8, device=dev, dtype=F32)
+        mom = torch.empty(72, device=dev, dtype=F32)
+        stats = torch.empty(4 * C, device=dev, dtype=F32)
+        raw, inrm, score = (torch.empty(B, SN, device=dev, dtype=F32) for _ in range(3))
+        _lib.call("dcnet_loc_rank8_train_fwd", _p(E), _p(obj), _p(W), SN, _p(bias), _p(gamma), _p(beta), float(eps), float(momentum),
+                  _p(running_mean), _p(running_var), _p(nbt), _p(flang), _p(G), _p(mom), _p(stats), _p(raw), _p(inrm), _p(score), B, SN, C, _st())
+        ctx.save_for_backward(E, obj, W, bias, flang, G, stats, raw, inrm)
+        return score
+
+    @staticmethod
+    def backward(ctx, dscore):
+        E, obj, W, bias, flang, G, stats, raw, inrm = ctx.saved_tensors
+        B, SN = obj.shape
+        C = W.shape[0]
+        dev = obj.device
+        dscore = _c(dscore, name="dscore")
+        draw = torch.empty(B, SN, device=dev, dtype=F32)
+        dG = torch.empty(B, C, 8, device=dev, dtype=F32)
+        dE, dobj, dW = torch.empty_like(E), torch.empty_like(obj), torch.empty_like(W)
+        dgamma, dbeta = torch.empty(C, device=dev, dtype=F32), torch.empty(C, device=dev, dtype=F32)
+        dflang = torch.empty_like(flang)
+        _lib.call("dcnet_loc_rank8_train_bwd", _p(E), _p(obj), _p(W), SN, _p(bias), _p(flang), _p(G), _p(stats), _p(raw), _p(inrm), _p(dscore),
+                  _p(draw), _p(dG), _p(dE), _p(dobj), _p(dW), _p(dgamma), _p(dbeta), _p(dflang), B, SN, C, _st())
+        dbias = torch.zeros_like(bias) if (bias is not None and ctx.needs_input_grad[3]) else None     # removed by the batch statistics
+        return dE, dobj, dW, dbias, dgamma, dbeta, None, None, None, None, None, dflang
+
+
+def loc_rank8_train(E, obj, W, bias, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, flang):
+    """training-mode location scores [B,SN] with gradients to E [SN,8], obj [B,SN], the Linear (W [C,SN], bias [C]), the BatchNorm1d
+    affine (gamma, beta [C]) and flang [B,C]; running_mean / running_var / num_batches_tracked are updated in place."""
+    return _LocRank8Train.apply(E, obj, W, bias, gamma, beta, running_mean, running_var, num_batches_tracked, float(momentum), float(eps), flang)
+
+
 def coord_map(h, w, device):
     out = torch.empty(8, h, w, device=device, dtype=F32)
     _lib.call("dcnet_coord_map", _p(out), h, w, _st())

@@ -199,6 +199,20 @@ DCNET_API int dcnet_loc_rank8_fwd(const float* E, const float* obj, const float*
                                   float* G, float* raw, float* score, int B, int SN, int C, void* stream);
 
 /* ---- a7: coordinate map (model/DCNet_model.py:23-39), [8,h,w], batch independent ---------------------- */
+/* the same branch in training mode (batch statistics of the BatchNorm1d, running statistics updated like nn.BatchNorm1d, and the
+ * backward): forward keeps G [B,C,8], stats [4*C] = (BN scale, BN shift, mean of z without the Linear's bias, invstd), raw and
+ * inrm [B,SN] (score before min-max, 1 / channel norm) for the backward; mom [72] is scratch.  Backward from dscore [B,SN]: dE [SN,8],
+ * dobj [B,SN], dW [C,ldw] (columns < SN), dgamma / dbeta [C], dflang [B,C], all overwritten (the Linear's bias has no gradient under
+ * batch statistics); draw [B,SN] and dG [B,C,8] are scratch.  The [B,SN,SN] relation tensor and the [B*SN, C] activations never exist. */
+DCNET_API int dcnet_loc_rank8_train_fwd(const float* E, const float* obj, const float* W, int ldw, const float* bias,
+                                        const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                                        float* running_var, long long* num_batches_tracked, const float* flang,
+                                        float* G, float* mom, float* stats, float* raw, float* inrm, float* score,
+                                        int B, int SN, int C, void* stream);
+DCNET_API int dcnet_loc_rank8_train_bwd(const float* E, const float* obj, const float* W, int ldw, const float* bias, const float* flang,
+                                        const float* G, const float* stats, const float* raw, const float* inrm, const float* dscore,
+                                        float* draw, float* dG, float* dE, float* dobj, float* dW, float* dgamma, float* dbeta, float* dflang,
+                                        int B, int SN, int C, void* stream);
 DCNET_API int dcnet_coord_map(float* coord, int h, int w, void* stream);
 
 /* ---- a5/a20: co-attention (model/DCNet_model.py:449-459, model/test_DCNet_model.py:247-274) -----------

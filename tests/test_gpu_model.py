@@ -148,6 +148,12 @@ def test_train_forward_losses_gradients_vs_oracle(size, pairs, precision):
             continue
         if float(v.grad.norm()) < 1e-12:
             continue
+        if k == "loc_embedding.1.bias":
+            # the BatchNorm1d(8) bias of the coordinate embedding: a sum over B*SN rows that cancels to ~1e-3 of its terms.  The fp32
+            # materialised evaluation (this oracle, and PyTorch on the GPU in the same order: the "floor") is itself 4-8 % off its
+            # fp64 value at 416x416; the location kernels are held to the fp64 evaluation instead (4e-5,
+            # test_location_branch_training_kernels_vs_materialised_fp64)
+            continue
         report[k] = (rel(pc[k].grad, v.grad), rel(pg[k].grad, v.grad))
     # precision 1: "floor" is ONE sample (PyTorch's TF32 evaluation) of the chaotic ReLU-mask-flip noise and the product's
     # forward (TF32 convs + bf16 fused co-attention, each MORE accurate than TF32 co-attention) is another sample of it:
@@ -287,7 +293,7 @@ def test_location_branch_rank8_training_form_on_gpu(size):
     outs = []
     for flag in (False, True):
         m = copy.deepcopy(net)
-        m.rank8_location_train = flag
+        m.rank8_location_train = "torch" if flag else False
         obj = [torch.rand(B, n * n, generator=torch.Generator().manual_seed(8 + n)).to(DEV).requires_grad_() for n in grids]
         ctx = context.clone().requires_grad_()
         score = m.location_branch(coords, obj, ctx, embedded, word_id)
@@ -315,3 +321,57 @@ def test_location_branch_rank8_training_form_on_gpu(size):
     assert not bad, bad
     for k in st0:
         assert rel(st1[k], st0[k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("size,B", [(256, 4), (256, 16), (416, 3)])
+def test_location_branch_training_kernels_vs_materialised_fp64(size, B):
+    """SURVEY 8(f) row 2, training: grounding_model.location_branch on dcnet_loc_rank8_train_fwd / _bwd (rank-8 form, batch statistics,
+    backward: no [B,SN,SN] tensor, no [B*SN,C] activations) against the reference's materialised evaluation (model/DCNet_model.py:556-603)
+    of the same module in fp64: scores, running statistics, gradients of every parameter and input."""
+    synth.seed_all(5)
+    net = grounding_model(corpus=list(range(100)), emb_size=512, visumodel=StubBackbone(), size=size).to(DEV).train()
+    grids = [size // 32, size // 16, size // 8]
+    T = 9
+    g = torch.Generator().manual_seed(6)
+    from dcnet_b200 import ops
+    coords = [ops.coord_map(n, n, DEV).flatten(1) for n in grids]
+    context = torch.randn(B, T, 1024, generator=g).to(DEV)
+    embedded = torch.randn(B, T, net.loc_text_embedding[0].out_features, generator=g).to(DEV)
+    word_id = torch.randint(1, 100, (B, T), generator=g).to(DEV)
+    word_id[1, 5:] = 0
+    wts = torch.linspace(0.5, 1.5, sum(n * n for n in grids), device=DEV)
+    outs = []
+    for mode in ("fp64", "kernels"):
+        m = copy.deepcopy(net)
+        m.rank8_location_train = False if mode == "fp64" else "kernels"
+        dt = torch.float64 if mode == "fp64" else torch.float32
+        m = m.to(dt)
+        obj = [torch.rand(B, n * n, generator=torch.Generator().manual_seed(8 + n)).to(DEV).to(dt).requires_grad_() for n in grids]
+        ctx = context.to(dt).requires_grad_()
+        score = m.location_branch([c.to(dt) for c in coords], obj, ctx, embedded.to(dt), word_id)
+        (score * wts.to(dt)).sum().backward()
+        grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+        stats = {n: b.clone() for n, b in m.named_buffers() if n.startswith(("loc_embedding", "loc_text_embedding"))}
+        outs.append((score.detach(), grads, [o.grad for o in obj], ctx.grad, stats))
+    (s0, g0, o0, c0, st0), (s1, g1, o1, c1, st1) = outs
+    assert rel(s1, s0) < 2e-5, rel(s1, s0)
+    assert set(g0) == set(g1)
+    # biases in front of a BatchNorm and the softmax-shift bias of the phrase attention have an analytically zero gradient
+    ZERO = ("loc_embedding.0.bias", "loc_text_embedding.0.bias", "loc_attn.fc.bias")
+    errs = {k: rel(g1[k], g0[k]) for k in g0 if k not in ZERO}
+    errs.update({"obj[%d]" % i: rel(a, b) for i, (a, b) in enumerate(zip(o1, o0))})
+    errs["context"] = rel(c1, c0)
+    print("location branch, training kernels at %d, B=%d: scores %.1e, worst gradient error against fp64 %.2e (%s)" % (
+        size, B, rel(s1, s0), max(errs.values()), max(errs, key=errs.get)))
+    scale = max(float(v.norm()) for v in g0.values())
+    for k in ZERO:
+        assert float(g1[k].norm()) < 1e-3 * scale, k
+    # fp32 against fp64 through a min-max normalisation: measured 4e-6 (256x256) and 4e-5 (416x416) -- including the BatchNorm1d(8) bias
+    # of loc_embedding, an ill-conditioned sum on which PyTorch's two fp32 evaluation orders differ by 4-8 % (torch-form test above)
+    bad = {k: e for k, e in errs.items() if e > 2e-4}
+    assert not bad, bad
+    for k in st0:
+        if st0[k].dtype.is_floating_point:
+            assert rel(st1[k], st0[k]) < 1e-4, (k, rel(st1[k], st0[k]))
+        else:
+            assert int(st1[k]) == int(st0[k]), k
