@@ -3,6 +3,8 @@
 // This file holds the fp32 composition used for exactness checks and as the backward of round 1: the score matrix
 // lives in caller-provided scratch.  The tcgen05 path (umma_coattn.cu) keeps S/P in TMEM/SMEM and is selected by
 // dcnet_coattn_fwd when the shape is supported.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 int umma_coattn_fwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, int n_out, float* lse,
@@ -139,7 +141,111 @@ __global__ void __launch_bounds__(256) coattn_fix_kernel(const float* __restrict
   }
 }
 
+// ---- fp16 pipeline of the backward.  fp16 keeps 11 significant bits like tf32, so a contraction on fp16 operands is as accurate as the
+// tf32 one AS LONG AS the operands stay in fp16's normal range (6e-5 .. 65504) -- at twice the MMA rate and half the operand bytes
+// (E and dS' are N x N).  The maps are unit-norm (the forward's own fp16 staging is reused); E carries a factor 2^8 that cancels
+// against its row sums; everything that scales with the incoming gradient (dO, dS', dOs) is multiplied by a per-problem power of two
+// s_z that brings max |dO| to [4, 8), and the three reduce-add contractions undo it through alpha_z = 1 / s_z.
+constexpr float E_SHIFT = 5.545177444479562f;      // 8 ln 2
+
+// mx[z] = max |dO[oidx[z]]| as the bit pattern of a non-negative float (caller zeroes)
+__global__ void __launch_bounds__(256) coattn_absmax_kernel(const float* __restrict__ dO, const int* __restrict__ oidx, unsigned int* __restrict__ mx,
+                                                            long long CN4) {
+  const int z = blockIdx.y;
+  const float4* src = reinterpret_cast<const float4*>(dO) + (long long)oidx[z] * CN4;
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < CN4; i += (long long)gridDim.x * 256) {
+    const float4 v = src[i];
+    m = fmaxf(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))), m);
+  }
+  __shared__ float sh[32];
+  m = block_max(m, sh);
+  if (threadIdx.x == 0) atomicMax(mx + z, __float_as_uint(m));
+}
+
+// the power of two that brings a maximum of m into [4, 8)
+__device__ __forceinline__ float coattn_scale(unsigned int mbits) {
+  const float m = __uint_as_float(mbits);
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e;
+  frexpf(m, &e);                   // m = f * 2^e, f in [0.5, 1)
+  return ldexpf(1.f, 3 - e);
+}
+
+// coattn_delta_kernel of the fp16 pipeline: delta <- s <dO, O> (the row term in the scaled units of dP), r <- 1 / r, and the scaled fp16
+// copy dO16[z][c][n] = fp16(s dO) (pitch ldh); block (0, z, 0) also publishes alpha_z[z] = 1 / s.
+__global__ void __launch_bounds__(256) coattn_delta16_kernel(const float* __restrict__ dO, const float* __restrict__ O, const int* __restrict__ oidx,
+                                                             const unsigned int* __restrict__ mx, float* __restrict__ r, float* __restrict__ delta,
+                                                             __half* __restrict__ dO16, float* __restrict__ alpha_z, int C, int N, int ldh) {
+  const int z = blockIdx.y;
+  const int n = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const float s = coattn_scale(mx[z]);
+  if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0) alpha_z[z] = 1.f / s;
+  const int cper = (C + gridDim.z - 1) / gridDim.z, c0 = blockIdx.z * cper, c1 = min(C, c0 + cper);
+  __shared__ float part[8][128];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (n < N) {
+    const long long src = (long long)oidx[z] * C * N + n;
+    __half* dst = dO16 + (long long)z * C * ldh + n;
+#pragma unroll 4
+    for (int c = c0 + threadIdx.y; c < c1; c += 8) {
+      const float4 g = *reinterpret_cast<const float4*>(dO + src + (long long)c * N);
+      const float4 o = *reinterpret_cast<const float4*>(O + src + (long long)c * N);
+      acc[0] = fmaf(g.x, o.x, acc[0]); acc[1] = fmaf(g.y, o.y, acc[1]); acc[2] = fmaf(g.z, o.z, acc[2]); acc[3] = fmaf(g.w, o.w, acc[3]);
+      const __half2 lo = __floats2half2_rn(g.x * s, g.y * s), hi = __floats2half2_rn(g.z * s, g.w * s);
+      *reinterpret_cast<uint2*>(dst + (long long)c * ldh) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) part[threadIdx.y][threadIdx.x * 4 + i] = acc[i];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += part[k][t];
+    const int nn = blockIdx.x * 128 + t;
+    if (nn < N) {
+      atomicAdd(delta + (long long)z * N + nn, sum * s);
+      if (blockIdx.z == 0) r[(long long)z * N + nn] = 1.f / r[(long long)z * N + nn];
+    }
+  }
+}
+
+// coattn_fix_kernel of the fp16 pipeline: rho arrives scaled by s (row sums of s dS'), the maps Fa come from the fp16 staging (pitch ldh):
+//   dOs16[z][c,i] = fp16( (s dO[c,i] - rho_i Fa[c,i]) / r_i ),     dframes[qa[z]][c,i] -= (rho_i / s) O[c,i]
+__global__ void __launch_bounds__(256) coattn_fix16_kernel(const float* __restrict__ dO, const float* __restrict__ O, const __half* __restrict__ F16,
+                                                           const int* __restrict__ oidx, const int* __restrict__ qa, const float* __restrict__ inv_r,
+                                                           const float* __restrict__ rho, const unsigned int* __restrict__ mx,
+                                                           __half* __restrict__ dOs16, float* __restrict__ dframes, int C, int N, int ldh) {
+  const int z = blockIdx.y;
+  const int n = (blockIdx.x * 32 + threadIdx.x) * 4;
+  if (n >= N) return;
+  const float s = coattn_scale(mx[z]), is = 1.f / s;
+  const long long so = (long long)oidx[z] * C * N + n;
+  const long long sq = (long long)qa[z] * C * N + n;
+  const __half* fq = F16 + (long long)qa[z] * C * ldh + n;
+  __half* dst = dOs16 + (long long)z * C * ldh + n;
+  const float4 iv = *reinterpret_cast<const float4*>(inv_r + (long long)z * N + n);
+  const float4 rh = *reinterpret_cast<const float4*>(rho + (long long)z * N + n);
+  const int cper = (C + gridDim.z - 1) / gridDim.z, c0 = blockIdx.z * cper, c1 = min(C, c0 + cper);
+#pragma unroll 4
+  for (int c = c0 + threadIdx.y; c < c1; c += 8) {
+    const float4 g = *reinterpret_cast<const float4*>(dO + so + (long long)c * N);
+    const float4 o = *reinterpret_cast<const float4*>(O + so + (long long)c * N);
+    const uint2 fu = *reinterpret_cast<const uint2*>(fq + (long long)c * ldh);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&fu.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&fu.y));
+    const __half2 lo = __floats2half2_rn((g.x * s - rh.x * f0.x) * iv.x, (g.y * s - rh.y * f0.y) * iv.y);
+    const __half2 hi = __floats2half2_rn((g.z * s - rh.z * f1.x) * iv.z, (g.w * s - rh.w * f1.y) * iv.w);
+    *reinterpret_cast<uint2*>(dst + (long long)c * ldh) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    float* d = dframes + sq + (long long)c * N;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(-rh.x * is * o.x), "f"(-rh.y * is * o.y), "f"(-rh.z * is * o.z),
+                 "f"(-rh.w * is * o.w) : "memory");
+  }
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int pitch8h(int N) { return (N + 7) & ~7; }
 inline int pitch4(int N) { return (N + 3) & ~3; }
 
 }  // namespace
@@ -150,6 +256,10 @@ inline int pitch4(int N) { return (N + 3) & ~3; }
 // travel to HBM and the workspace no longer grows with the number of problems.  A chunk keeps >= one wave of 128x256 tiles.
 static long long g_bwd_l2_budget = 1ll << 62;      // default: one chunk (see profiles/r2b: per-problem chunks starve the [C,N]-output contractions)
 extern "C" int dcnet_coattn_bwd_l2_budget(long long bytes) { g_bwd_l2_budget = bytes > 0 ? bytes : (1ll << 62); return 0; }
+// 1 (default): dcnet_coattn_bwd at precision 2 runs its contractions on fp16 operands when the caller hands over the forward's staging;
+// 0: always the tf32 contractions (bring-up / comparison knob, process-wide)
+static int g_bwd_fp16 = 1;
+extern "C" int dcnet_coattn_bwd_fp16(int on) { g_bwd_fp16 = on ? 1 : 0; return 0; }
 static int coattn_bwd_chunk(int nprob, int N) {
   const long long per = 2ll * N * N * (long long)sizeof(float);
   long long c = g_bwd_l2_budget / per;
@@ -168,7 +278,13 @@ extern "C" size_t dcnet_coattn_workspace_bytes(int F, int nprob, int C, int N, i
   if (N % 4 != 0 && precision >= 1)    // odd pitch: P / dP with the pitch padded to 4, plus padded copies of the maps and of dout
     unfused = 2 * align256((size_t)nprob * N * pitch4(N) * sizeof(float)) + align256((size_t)F * C * pitch4(N) * sizeof(float)) +
               align256((size_t)nprob * C * pitch4(N) * sizeof(float)) + 256;
-  const size_t fused = umma_coattn_workspace_bytes(F, C, N);                           // bf16 staging of the maps + column norms
+  if (precision == 2 && N % 4 == 0) {  // fp16 pipeline (dcnet_coattn_bwd with the forward's staging): E16, dS16 [chunk,N,ldh], dO16, dOs16 [chunk,C,ldh]
+    const size_t ldh = (size_t)((N + 7) & ~7);
+    const size_t h16 = 2 * align256((size_t)chunk * N * ldh * 2) + 2 * align256((size_t)chunk * C * ldh * 2) +
+                       3 * align256((size_t)chunk * N * sizeof(float)) + 2 * align256((size_t)chunk * sizeof(float)) + 256;
+    if (h16 > unfused) unfused = h16;
+  }
+  const size_t fused = umma_coattn_workspace_bytes(F, C, N);                           // fp16 staging of the maps + column norms
   return precision == 2 ? (unfused > fused ? unfused : fused) : unfused;
 }
 
@@ -227,7 +343,6 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
                                 const float* out, int n_out, const float* lse, const float* dout, float* dframes,
                                 int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,
                                 void* stream) {
-  (void)staged;
   DCNET_CHECK_ARG(frames && qa && kb && oidx && lse && dout && dframes && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_bwd: bad arguments");
   DCNET_CHECK_ARG(out || precision != 2, "coattn_bwd: the saved forward output is needed (delta = <dO, O>)");
   if (nprob == 0) return 0;
@@ -268,6 +383,57 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
     e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = kb; e.idxC = qa;
     DCNET_TRY(umma_gemm(Fk, dSk, nullptr, C, N, N, 0, 0, nprob, e, st));
     e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.atomic = 1; e.idxA = qa; e.idxC = kb;
+    return umma_gemm(Fk, dSmn, nullptr, C, N, N, 0, 0, nprob, e, st);
+  }
+  if (precision == 2 && staged && g_bwd_fp16 && N % 4 == 0 && C % 128 == 0 && N >= 64 && coattn_tc_ok(precision, C, N, frames, dout, dframes) &&
+      reinterpret_cast<uintptr_t>(workspace) % 256 == 0 && reinterpret_cast<uintptr_t>(staged) % 256 == 0) {
+    // ---- fp16 pipeline (see above): the five contractions on kind::f16 with operands that carry tf32's precision
+    const int ldh = pitch8h(N);
+    const long long NLh = (long long)N * ldh, CLh = (long long)C * ldh;
+    const __half* F16 = reinterpret_cast<const __half*>(staged);            // [F][C][ldh]: the forward's staging (same pitch rule)
+    char* w = (char*)workspace;
+    __half* E16 = (__half*)w; w += align256((size_t)nprob * NLh * 2);
+    __half* dS16 = (__half*)w; w += align256((size_t)nprob * NLh * 2);
+    __half* dO16 = (__half*)w; w += align256((size_t)nprob * CLh * 2);
+    __half* dOs16 = (__half*)w; w += align256((size_t)nprob * CLh * 2);
+    float* rsum = (float*)w; w += align256((size_t)nprob * N * sizeof(float));
+    float* delta = (float*)w; w += align256((size_t)nprob * N * sizeof(float));
+    float* rho = (float*)w; w += align256((size_t)nprob * N * sizeof(float));
+    unsigned int* mx = (unsigned int*)w; w += align256((size_t)nprob * sizeof(float));
+    float* alpha_z = (float*)w;
+    DCNET_CUDA(cudaMemsetAsync(rsum, 0, (size_t)((char*)alpha_z - (char*)rsum), st), "coattn_bwd.memset");
+    auto H = [](const __half* p_, long long rows, long long cols, long long ld, long long bs, int nb, bool mn) {
+      UmmaOperand o{reinterpret_cast<const float*>(p_), rows, cols, ld, bs, nb, mn};
+      o.bf16 = true; o.f16 = true;
+      return o;
+    };
+    const UmmaOperand Fmn = H(F16, C, N, ldh, CLh, F, true), Fk = H(F16, C, N, ldh, CLh, F, false);
+    const UmmaOperand Gmn = H(dO16, C, N, ldh, CLh, nprob, true), Gsk = H(dOs16, C, N, ldh, CLh, nprob, false);
+    const UmmaOperand Emn = H(E16, N, N, ldh, NLh, nprob, true);
+    const UmmaOperand dSk = H(dS16, N, N, ldh, NLh, nprob, false), dSmn = H(dS16, N, N, ldh, NLh, nprob, true);
+    const int mblk = ceil_div(N, 128) * nprob;
+    const int zsl = mblk >= 592 ? 1 : (592 / mblk > 8 ? 8 : 592 / mblk);
+    coattn_absmax_kernel<<<dim3(8, nprob), 256, 0, st>>>(dout, oidx, mx, CN / 4);
+    DCNET_LAUNCH_OK("coattn_bwd.absmax");
+    // E' = 2^8 exp(tau S - lse_fwd) (fp16) with row sums r'
+    UmmaEpilogue e{};
+    e.out = reinterpret_cast<float*>(E16); e.out_f16 = 1; e.ldo = ldh; e.so_b = NLh; e.alpha = tau; e.idxA = qa; e.idxB = kb;
+    e.epi_exp = 1; e.u = lse; e.ldu = N; e.exp_shift = E_SHIFT; e.sum = rsum; e.sum_ldz = N;
+    DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    coattn_delta16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, oidx, mx, rsum, delta, dO16, alpha_z, C, N, ldh);
+    DCNET_LAUNCH_OK("coattn_bwd.delta16");
+    // s dS' = tau (s dP - s delta) E' / r' (fp16) with row sums s rho
+    e = UmmaEpilogue{};
+    e.out = reinterpret_cast<float*>(dS16); e.out_f16 = 1; e.ldo = ldh; e.so_b = NLh; e.alpha = tau; e.idxB = kb;
+    e.epi_exp = 2; e.u = delta; e.u2 = rsum; e.ldu = N; e.cc = reinterpret_cast<const float*>(E16); e.ldcc = ldh; e.cc_sb = NLh; e.sum = rho; e.sum_ldz = N;
+    DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    coattn_fix16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, F16, oidx, qa, rsum, rho, mx, dOs16, dframes, C, N, ldh);
+    DCNET_LAUNCH_OK("coattn_bwd.fix16");
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.alpha_z = alpha_z; e.atomic = 1; e.idxC = kb; e.k_chunks = -1;
+    DCNET_TRY(umma_gemm(Gsk, Emn, nullptr, C, N, N, 0, 0, nprob, e, st));
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.alpha_z = alpha_z; e.atomic = 1; e.idxA = kb; e.idxC = qa; e.k_chunks = -1;
+    DCNET_TRY(umma_gemm(Fk, dSk, nullptr, C, N, N, 0, 0, nprob, e, st));
+    e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.alpha_z = alpha_z; e.atomic = 1; e.idxA = qa; e.idxC = kb; e.k_chunks = -1;
     return umma_gemm(Fk, dSmn, nullptr, C, N, N, 0, 0, nprob, e, st);
   }
   const int chunk = (precision == 2) ? coattn_bwd_chunk(nprob, N) : nprob;

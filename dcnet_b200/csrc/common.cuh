@@ -91,7 +91,8 @@ int sgemm_launch(const float* A, const float* B, float* C, int M, int N, int K, 
 struct UmmaOperand {
   const float* ptr; long long rows, cols, ld, batch_stride; int batches;   // batches = 0: not batched; ld/stride in elements
   bool mn_major;
-  bool bf16 = false;   // ptr is __nv_bfloat16 data (kind::f16 MMA) instead of fp32 read as TF32
+  bool bf16 = false;   // ptr is 2-byte data (kind::f16 MMA) instead of fp32 read as TF32: __nv_bfloat16 ...
+  bool f16 = false;    // ... or, with bf16 = true as well, __half (11 significant bits like tf32, at twice the tf32 MMA rate)
 };
 struct UmmaEpilogue {
   float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2; int m_split;
@@ -106,6 +107,12 @@ struct UmmaEpilogue {
   long long cc_sb = 0;           // batch stride of cc (0: cc is shared by the batch, the conv use)
   long long sum_ldz = 0;         // sum / sumsq are indexed [z*sum_ldz + row] (0: one vector for the whole batch = BatchNorm statistics)
   int k_chunks = 1;              // reduce-add outputs (atomic = 1) only: split the reduction over this many work items per output tile
+  // fp16 pipeline of the co-attention backward (coattn.cu): out (and the E tile `cc` of the dS epilogue) are __half tensors -- ldo /
+  // ldcc / so_b / cc_sb in elements, multiples of 8 --, epi_exp values are rounded to fp16 instead of tf32; exp_shift is added to the
+  // exponent of epi_exp = 1; alpha_z[z] (optional) multiplies alpha per batch item (undoes a per-problem operand scale)
+  int out_f16 = 0;
+  float exp_shift = 0.f;
+  const float* alpha_z = nullptr;
   // 3x3 convolution as an implicit GEMM (conv3x3.cu; see Gemm2P in umma_gemm.cu): B, B2, B3 = the map shifted by dx = -1, 0, +1
   const UmmaOperand* B3 = nullptr;
   int tap_kper = 0, tap_w = 0, tap_flip = 0, tap_n = 0;

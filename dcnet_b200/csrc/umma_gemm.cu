@@ -14,6 +14,8 @@
 // A STAGES-deep ring of {A tile, B tile} with full/empty mbarriers decouples TMA from MMA; tcgen05.commit releases a slot.
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -256,6 +258,9 @@ struct Gemm2P {
   //   tap_n > 0 (B K-major; weight gradient): output column block n0 belongs to tap t = n0 / tap_n; B rows from copy dx, reduction
   //     coordinate (positions) shifted by dy * tap_w
   int tap_kper, tap_w, tap_flip, tap_n;
+  int f16;             // 2-byte operands are __half (FMT_F16) instead of __nv_bfloat16
+  int out_f16;         // out / the E tile are __half tensors: two 32-column chunks share one 128-byte slot row, values rounded to fp16
+  float exp_shift; const float* alpha_z;
   int direct_store;    // 1: epilogue leaves through coalesced st.global / red.global.add.v4 instead of TMA store / reduce
   float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2;
   long long* trace;    // optional [CTA][tile slot < 8][8] clock stamps (profiling entry point dcnet_gemm_tf32_trace); nullptr = off
@@ -419,7 +424,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   } else if (warp == 5) {
     if ((!TWO || crank == 0) && elect_one()) {
-      constexpr uint32_t idesc = instr_desc(G::FMT, TWO ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint32_t idesc = instr_desc((EB == 2 && p.f16) ? (uint32_t)FMT_F16 : G::FMT, TWO ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t itg = 0, tl = 0;
       for (int t = cid; t < ngroups; t += ncl, tl++) {
         const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
@@ -479,6 +484,10 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       // the bias / coordinate terms belong to the whole reduction: with split-K only chunk 0 adds them
       const float bias = (p.u && row_ok && kc == 0) ? p.u[(long long)z * p.ldu + row] : 0.f;
       const float rowmul = (p.epi_exp == 2 && row_ok) ? p.alpha * p.u2[(long long)z * p.ldu + row] : 0.f;
+      const float alpha = p.alpha_z ? p.alpha * p.alpha_z[z] : p.alpha;
+      const bool h16 = p.out_f16 != 0;
+      // the value the next MMA will read: rounded to tf32, or to fp16 when the output is stored as fp16
+      auto rnd = [h16](float x) { return h16 ? __half2float(__float2half_rn(x)) : tf32_rn(x); };
       float s1 = 0.f, s2 = 0.f;
       // dS epilogue: the E chunk of a thread's row (128 contiguous bytes) is fetched ONE CHUNK AHEAD -- the first one before the
       // accumulator is even complete -- so its L2 / HBM latency hides under the TMEM load, the arithmetic and the store of the
@@ -493,15 +502,29 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       uint64_t* ebar = e_full + warp * 2;
       float4 ecur[8];
       const float* erow = (p.epi_exp == 2 && row_ok && !e_tma) ? p.cc + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
+      const __half* erow_h = (p.epi_exp == 2 && row_ok && !e_tma && h16)
+                                 ? reinterpret_cast<const __half*>(p.cc) + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
       auto load_e = [&](int c, float4 (&dst)[8]) {
         const int nb_ = n0 + c * 32;
-        if (erow && nb_ + 32 <= p.N_valid) {
+        if (erow_h) {
+          if (nb_ + 32 <= p.N_valid) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(erow_h + nb_ + 8 * e));
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+              const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
+              dst[2 * e] = make_float4(a.x, a.y, b.x, b.y);
+              dst[2 * e + 1] = make_float4(c2.x, c2.y, d.x, d.y);
+            }
+          }
+        } else if (erow && nb_ + 32 <= p.N_valid) {
 #pragma unroll
           for (int e = 0; e < 8; e++) dst[e] = __ldg(reinterpret_cast<const float4*>(erow + nb_ + 4 * e));
         }
       };
+      // fp32 E: one 32 x 32 block per chunk; fp16 E: one 32 x 64 block per PAIR of chunks (same 4 KiB slot, same swizzle)
       auto tma_e = [&](int c) {          // lane 0: E block of chunk c -> slot (echunk + c) & 1
-        const uint32_t k = echunk + (uint32_t)c;
+        const uint32_t k = echunk + (uint32_t)(h16 ? c >> 1 : c);
         mbar_expect_tx(&ebar[k & 1u], SLOT_BYTES);
         tma_load_3d(eslots + (k & 1u) * SLOT_BYTES, &mapO2, &ebar[k & 1u], n0 + c * 32, row0, z);
       };
@@ -513,15 +536,32 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++, chunk++) {
         float4 enext[8];
-        if (e_tma) { if (lane == 0 && c + 1 < BN / 32) tma_e(c + 1); }
-        else if (p.epi_exp == 2 && c + 1 < BN / 32) load_e(c + 1, enext);
+        if (e_tma) {
+          if (h16) { if (lane == 0 && (c & 1) == 0 && c + 2 < BN / 32) tma_e(c + 2); }
+          else if (lane == 0 && c + 1 < BN / 32) tma_e(c + 1);
+        } else if (p.epi_exp == 2 && c + 1 < BN / 32) load_e(c + 1, enext);
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + (uint32_t)(c * 32), v);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
         if (p.epi_exp == 1) {
 #pragma unroll
-          for (int e = 0; e < 32; e++) v[e] = tf32_rn(__expf(fmaf(p.alpha, v[e], -bias)));
+          for (int e = 0; e < 32; e++) v[e] = rnd(__expf(fmaf(p.alpha, v[e], p.exp_shift - bias)));
+        } else if (e_tma && h16) {
+          // dS = tau (dP - delta) E / r with the fp16 E block of this chunk pair: this chunk's half of the thread's 128-byte row
+          const uint32_t k = echunk + (uint32_t)(c >> 1);
+          mbar_wait(&ebar[k & 1u], (k >> 1) & 1u);
+          const uint8_t* er = eslots + (k & 1u) * SLOT_BYTES + lane * 128;
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const uint4 q = *reinterpret_cast<const uint4*>(er + ((((c & 1) * 4 + e) ^ (lane & 7)) * 16));
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+            const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
+            v[8 * e] = rnd((v[8 * e] - bias) * rowmul * a.x); v[8 * e + 1] = rnd((v[8 * e + 1] - bias) * rowmul * a.y);
+            v[8 * e + 2] = rnd((v[8 * e + 2] - bias) * rowmul * b.x); v[8 * e + 3] = rnd((v[8 * e + 3] - bias) * rowmul * b.y);
+            v[8 * e + 4] = rnd((v[8 * e + 4] - bias) * rowmul * c2.x); v[8 * e + 5] = rnd((v[8 * e + 5] - bias) * rowmul * c2.y);
+            v[8 * e + 6] = rnd((v[8 * e + 6] - bias) * rowmul * d.x); v[8 * e + 7] = rnd((v[8 * e + 7] - bias) * rowmul * d.y);
+          }
         } else if (e_tma) {
           // dS = tau (dP - delta) E / r : per-row delta (bias) and tau / r (rowmul)
           const uint32_t k = echunk + (uint32_t)c;
@@ -540,13 +580,16 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 8; e++) {
                 const float4 q = ecur[e];
-                v[4 * e] = tf32_rn((v[4 * e] - bias) * rowmul * q.x); v[4 * e + 1] = tf32_rn((v[4 * e + 1] - bias) * rowmul * q.y);
-                v[4 * e + 2] = tf32_rn((v[4 * e + 2] - bias) * rowmul * q.z); v[4 * e + 3] = tf32_rn((v[4 * e + 3] - bias) * rowmul * q.w);
+                v[4 * e] = rnd((v[4 * e] - bias) * rowmul * q.x); v[4 * e + 1] = rnd((v[4 * e + 1] - bias) * rowmul * q.y);
+                v[4 * e + 2] = rnd((v[4 * e + 2] - bias) * rowmul * q.z); v[4 * e + 3] = rnd((v[4 * e + 3] - bias) * rowmul * q.w);
               }
             } else {
-              const float* er = erow + nb;      // ragged last chunk of the row: element by element
+              // ragged last chunk of the row: element by element
 #pragma unroll
-              for (int e = 0; e < 32; e++) v[e] = (nb + e < p.N_valid) ? tf32_rn((v[e] - bias) * rowmul * er[e]) : 0.f;
+              for (int e = 0; e < 32; e++) {
+                const float ev = (nb + e < p.N_valid) ? (erow_h ? __half2float(erow_h[nb + e]) : erow[nb + e]) : 0.f;
+                v[e] = (nb + e < p.N_valid) ? rnd((v[e] - bias) * rowmul * ev) : 0.f;
+              }
             }
           }
 #pragma unroll
@@ -557,16 +600,16 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 8; e++) {
               const float4 q = *reinterpret_cast<const float4*>(cr + 4 * e);
-              v[4 * e] = fmaf(p.alpha, v[4 * e], bias + q.x); v[4 * e + 1] = fmaf(p.alpha, v[4 * e + 1], bias + q.y);
-              v[4 * e + 2] = fmaf(p.alpha, v[4 * e + 2], bias + q.z); v[4 * e + 3] = fmaf(p.alpha, v[4 * e + 3], bias + q.w);
+              v[4 * e] = fmaf(alpha, v[4 * e], bias + q.x); v[4 * e + 1] = fmaf(alpha, v[4 * e + 1], bias + q.y);
+              v[4 * e + 2] = fmaf(alpha, v[4 * e + 2], bias + q.z); v[4 * e + 3] = fmaf(alpha, v[4 * e + 3], bias + q.w);
             }
           } else {
 #pragma unroll
-            for (int e = 0; e < 32; e++) v[e] = fmaf(p.alpha, v[e], bias + ((nb + e < p.N_valid) ? cr[e] : 0.f));
+            for (int e = 0; e < 32; e++) v[e] = fmaf(alpha, v[e], bias + ((nb + e < p.N_valid) ? cr[e] : 0.f));
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; e++) v[e] = fmaf(p.alpha, v[e], bias);
+          for (int e = 0; e < 32; e++) v[e] = fmaf(alpha, v[e], bias);
         }
         if (p.sum && row_ok) {
           if (nb + 32 <= p.N_valid) {
@@ -577,6 +620,33 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             for (int e = 0; e < 32; e++)
               if (nb + e < p.N_valid) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
           }
+        }
+        if (h16) {
+          // fp16 output: the chunks 2j and 2j+1 fill the two halves of one 128-byte slot row (64 fp16), one TMA store per pair.  BN / 32
+          // is even, so the parity of the running chunk counter is the parity of c
+          uint8_t* slot16 = slots + ((chunk >> 1) % NSLOT) * SLOT_BYTES;
+          if ((c & 1) == 0) {
+            if (lane == 0) tma_store_wait_read_n<NSLOT - 1>();
+            __syncwarp();
+          }
+          uint8_t* srow16 = slot16 + lane * 128;
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const __half2 h0 = __floats2half2_rn(v[8 * e], v[8 * e + 1]), h1 = __floats2half2_rn(v[8 * e + 2], v[8 * e + 3]);
+            const __half2 h2 = __floats2half2_rn(v[8 * e + 4], v[8 * e + 5]), h3 = __floats2half2_rn(v[8 * e + 6], v[8 * e + 7]);
+            *reinterpret_cast<uint4*>(srow16 + ((((c & 1) * 4 + e) ^ (lane & 7)) * 16)) =
+                make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                           *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          }
+          if (c & 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (row0 < p.M_valid && nb - 32 < p.N_valid) tma_store_3d(mo, slot16, nb - 32, orow0, zc);
+              tma_store_commit();
+            }
+          }
+          continue;
         }
         uint8_t* slot = slots + (chunk % NSLOT) * SLOT_BYTES;
         if (p.direct_store) {
@@ -631,7 +701,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           tma_store_commit();
         }
       }
-      if (e_tma) echunk += BN / 32;
+      if (e_tma) echunk += h16 ? BN / 64 : BN / 32;
       tc_fence_before();
       __syncwarp();
       if (threadIdx.x == 0) GTRACE(tl, 5);
@@ -695,7 +765,7 @@ int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap
 template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
 int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mb3, const CUtensorMap& mo,
                 const CUtensorMap& mo2, const Gemm2P& p, int cs, cudaStream_t st) {
-  if constexpr (BN == 256 && EB == 4) {
+  if constexpr (BN == 256) {
     if constexpr (A_MN && B_MN) {      // the dS epilogue belongs to dP = dO^T Fb: both operands MN-major
       if (cs == -2 && p.epi_exp == 2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR - 1, EB, 2, true, true>(ma, mb, mb2, mb3, mo, mo2, p, st);
     }
@@ -749,6 +819,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
               int batch, const UmmaEpilogue& e, cudaStream_t st) {
   DCNET_CHECK_ARG(umma_gemm_usable(A, B, B2, K), "umma_gemm: operand not TMA-compatible (16-B aligned base, row pitch multiple of 4 floats)");
   DCNET_CHECK_ARG(A.bf16 == B.bf16 && (!B2 || B2->bf16 == B.bf16), "umma_gemm: mixed operand element types");
+  DCNET_CHECK_ARG(A.f16 == B.f16 && (!A.f16 || A.bf16), "umma_gemm: fp16 operands: both, and flagged as 2-byte");
   const int BK = A.bf16 ? 64 : 32;
   DCNET_CHECK_ARG(k_split_elems % BK == 0, "umma_gemm: k_split must be a multiple of %d", BK);
   DCNET_CHECK_ARG(batch >= 1 && batch <= 65535, "umma_gemm: batch %d", batch);
@@ -761,9 +832,12 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   const int BN = (N <= 64) ? 64 : ((N >= 256 && (tiles256 >= 148 || auto_split)) ? 256 : 128);
   // persistent kernel with TMA-store epilogue whenever the output rows are TMA-addressable
   auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
-  const bool out_ok = al16(e.out) && e.ldo % 4 == 0 && e.so_b % 4 == 0 &&
+  const int oal = e.out_f16 ? 8 : 4;        // elements per 16 bytes of the output
+  DCNET_CHECK_ARG(!e.out_f16 || (!e.atomic && e.m_split == 0 && !(e.cc && e.epi_exp != 2)), "umma_gemm: fp16 output: plain store, no m_split, no cc term");
+  const bool out_ok = al16(e.out) && e.ldo % oal == 0 && e.so_b % oal == 0 &&
                       (e.m_split == 0 || (e.m_split % BM == 0 && e.out2 && al16(e.out2) && e.ldo2 % 4 == 0 && e.so_b2 % 4 == 0)) &&
-                      (!e.cc || (al16(e.cc) && e.ldcc % 4 == 0)) && !(e.so_b == 0 && batch > 1 && !e.atomic) && !g_force_v1;
+                      (!e.cc || (al16(e.cc) && e.ldcc % oal == 0)) && !(e.so_b == 0 && batch > 1 && !e.atomic) && !g_force_v1;
+  DCNET_CHECK_ARG(out_ok || (!e.out_f16 && !e.alpha_z && e.exp_shift == 0.f), "umma_gemm: fp16 output / alpha_z / exp_shift need the persistent kernel");
   // cluster size of the persistent kernel: CTAs with consecutive M tiles share (multicast) the B tile
   const int tiles_m = ceil_div(M, BM);
   int cs = (!out_ok || g_cluster_max < 2 || tiles_m < 2) ? 1 : ((g_cluster_max >= 4 && tiles_m % 4 == 0) ? 4 : 2);
@@ -772,7 +846,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     while (cs > 1 && nblk % cs != 0) cs >>= 1;
   }
   // CTA pairs (cta_group::2) for the wide tf32 tiles: halves the B traffic per output tile
-  const bool pair = out_ok && g_pair_mode && BN == 256 && !A.bf16 && tiles_m >= 2;
+  const bool pair = out_ok && g_pair_mode && BN == 256 && tiles_m >= 2;
   if (pair) cs = 2;
   CUtensorMap ma, mb, mb2, mb3;
   DCNET_TRY(make_operand_map(&ma, A, BM));
@@ -809,6 +883,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     q.alpha = e.alpha; q.atomic = e.atomic; q.u = e.u; q.ldu = e.ldu; q.cc = e.cc; q.ldcc = e.ldcc; q.sum = e.sum; q.sumsq = e.sumsq;
     q.epi_exp = e.epi_exp; q.u2 = e.u2; q.cc_sb = e.cc_sb; q.sum_ldz = e.sum_ldz;
     q.tap_kper = e.tap_kper; q.tap_w = e.tap_w; q.tap_flip = e.tap_flip; q.tap_n = e.tap_n;
+    q.f16 = A.f16 ? 1 : 0; q.out_f16 = e.out_f16; q.exp_shift = e.exp_shift; q.alpha_z = e.alpha_z;
     int want_chunks = e.k_chunks;
     if (auto_split) {
       const long long tiles = (long long)q.ntiles;
@@ -824,12 +899,15 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     const uint64_t nbo = q.out_batched ? 65535u : 1u;
     const uint64_t rows1 = e.m_split > 0 ? (uint64_t)e.m_split : (uint64_t)M;
     CUtensorMap mo, mo2;
-    int r = make_tmap(&mo, e.out, 4, (uint64_t)N, rows1, nbo, (uint64_t)e.ldo, q.out_batched ? (uint64_t)e.so_b : rows1 * (uint64_t)e.ldo, 32, 32);
+    // fp16 output: 32 rows x 64 fp16 per store (the same 128-byte slot rows)
+    const int oeb = e.out_f16 ? 2 : 4;
+    const uint32_t obox = e.out_f16 ? 64u : 32u;
+    int r = make_tmap(&mo, e.out, oeb, (uint64_t)N, rows1, nbo, (uint64_t)e.ldo, q.out_batched ? (uint64_t)e.so_b : rows1 * (uint64_t)e.ldo, obox, 32);
     if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled(out) failed (%d)", r);
     mo2 = mo;
     if (e.epi_exp == 2) {
-      DCNET_CHECK_ARG(e.m_split == 0 && al16(e.cc) && e.ldcc % 4 == 0 && e.cc_sb % 4 == 0, "umma_gemm: dS epilogue: E must be TMA-addressable, no m_split");
-      r = make_tmap(&mo2, e.cc, 4, (uint64_t)N, (uint64_t)M, e.cc_sb ? 65535u : 1u, (uint64_t)e.ldcc, e.cc_sb ? (uint64_t)e.cc_sb : (uint64_t)M * e.ldcc, 32, 32);
+      DCNET_CHECK_ARG(e.m_split == 0 && al16(e.cc) && e.ldcc % oal == 0 && e.cc_sb % oal == 0, "umma_gemm: dS epilogue: E must be TMA-addressable, no m_split");
+      r = make_tmap(&mo2, e.cc, oeb, (uint64_t)N, (uint64_t)M, e.cc_sb ? 65535u : 1u, (uint64_t)e.ldcc, e.cc_sb ? (uint64_t)e.cc_sb : (uint64_t)M * e.ldcc, obox, 32);
       if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled(E) failed (%d)", r);
     }
     if (e.m_split > 0) {

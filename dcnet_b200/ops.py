@@ -81,6 +81,9 @@ def gemm_tf32(A, B, a_mn, b_mn, M, N, K, alpha=1.0, out=None, atomic=0):
 # (diagnostics only).
 RN_TF32 = True
 _RN_FLAG = 0x100
+# co-attention backward on fp16 operands (kind::f16 at twice the tf32 rate, the same 11 significant bits; include/dcnet_b200.h,
+# dcnet_coattn_bwd `staged`).  False = the tf32 contractions (comparison).
+BWD_FP16 = True
 
 
 def round_tf32(x, out=None):
@@ -742,6 +745,7 @@ class _CoAttn(torch.autograd.Function):
                 if prestaged.numel() < nbytes or prestaged.dtype != torch.uint8:
                     raise ValueError("coattention: prestaged buffer does not belong to frames of shape %s" % (tuple(frames.shape),))
                 _lib.call("dcnet_coattn_fused_fwd", _p(prestaged), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, rn_out, _st())
+                staged = prestaged
             else:
                 staged = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
                 # staging + fused kernel (dcnet_coattn_fwd at precision 2 needs only the staging bytes)
@@ -752,7 +756,8 @@ class _CoAttn(torch.autograd.Function):
             ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
             _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, precision | rn_out,
                       _p(ws), nbytes, _st())
-        ctx.save_for_backward(frames, qa, kb, oidx, out, lse)
+        # the fp16 staging goes to the backward: its five contractions then run on fp16 operands (tf32's precision at twice the rate)
+        ctx.save_for_backward(frames, qa, kb, oidx, out, lse, staged if BWD_FP16 else None)
         ctx.tau = tau
         return out
 
@@ -760,7 +765,7 @@ class _CoAttn(torch.autograd.Function):
     def backward(ctx, dout, accumulate_into=None):
         """accumulate_into (used by _Correspondence): a [F,C,N] gradient buffer that already holds the other consumers' contribution to
         d frames -- the kernels add into it (TMA reduce-add) instead of into a zero-filled tensor that autograd would add afterwards"""
-        frames, qa, kb, oidx, out, lse = ctx.saved_tensors
+        frames, qa, kb, oidx, out, lse, staged = ctx.saved_tensors
         F_, C, N = frames.shape
         nprob = qa.numel()
         dout = _c(dout, name="dout")
@@ -768,7 +773,7 @@ class _CoAttn(torch.autograd.Function):
         nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, ctx.precision)
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
         _lib.call("dcnet_coattn_bwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout), _p(dframes),
-                  C, N, ctx.tau, ctx.precision, None, _p(ws), nbytes, _st())
+                  C, N, ctx.tau, ctx.precision, _p(staged), _p(ws), nbytes, _st())
         return dframes, None, None, None, None, None, None, None, None
 
 

@@ -241,7 +241,10 @@ DCNET_API int dcnet_coattn_fused_fwd_trace(const void* staged, int F, const int*
                                            float* out, int n_out, float* lse, int C, int N, float tau, long long* trace, int variant, void* stream);
 /* dframes [F,C,N] += gradient (caller zeroes, or hands over a buffer that already holds another consumer's gradient of the
  * frames); dout/out indexed by oidx like the forward.  P is re-normalised from tf32 logits recomputed here (the forward's lse is
- * only a shift).  staged: reserved, pass NULL (round 1 could recompute P from the forward's staging: 1.3e-3 against 5e-4).   */
+ * only a shift).  staged (optional, precision 2): the fp16 staging of `frames` the forward used (dcnet_coattn_stage /
+ * dcnet_bn_act_fwd_staged).  With it the five contractions run on fp16 operands -- kind::f16: the 11 significant bits of tf32 at twice
+ * the MMA rate and half the bytes for the two N x N tensors; everything that scales with dout carries a per-problem power of two
+ * that keeps it in fp16's normal range --; NULL: tf32 contractions on the fp32 maps.                                           */
 DCNET_API int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                const float* out, int n_out, const float* lse, const float* dout, float* dframes,
                                int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,
@@ -249,6 +252,8 @@ DCNET_API int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const 
 /* The backward keeps its N x N scratch (P, dP -> dS) resident in L2 by working through the problems in chunks whose scratch
  * fits `bytes` (default 64 MiB of the 126 MB L2; <= 0 = unlimited = one chunk); dcnet_coattn_workspace_bytes follows it. */
 DCNET_API int dcnet_coattn_bwd_l2_budget(long long bytes);
+/* 1 (default): the fp16 pipeline is used whenever `staged` is given; 0: always tf32 (comparison knob, process-wide) */
+DCNET_API int dcnet_coattn_bwd_fp16(int on);
 
 /* ---- a4: inter-frame patch correspondence (model/DCNet_model.py:381-430) ------------------------------
  * fv0 [2P,C,N0].  S0[p] = F1^T F2 in exact fp32; idx[p, r] = flat index (row*N0+col) of the r-th largest

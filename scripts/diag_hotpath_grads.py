@@ -8,7 +8,8 @@ from dcnet_b200.hotpath import HotPath
 from oracle import dcnet_oracle as O
 from dcnet_b200 import ops
 ops.RN_TF32 = os.environ.get("DCNET_RN", "1") != "0"      # 0: operands truncated by the MMA (round 1 behaviour)
-print("RN_TF32 =", ops.RN_TF32)
+ops.BWD_FP16 = os.environ.get("DCNET_BWD_FP16", "1") != "0"
+print("RN_TF32 =", ops.RN_TF32, "BWD_FP16 =", ops.BWD_FP16)
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 2
