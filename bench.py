@@ -323,7 +323,7 @@ def run_c4(args, wl, rank, world, dev, dist):
         cfg.update(clips_per_gpu=clips, frames=nf, directed_pairs_per_gpu=nprob)
         line = dict(metric="frame_pairs_per_sec", value=world * pairs * args.steps / (dev_ms / 1e3), unit="frame-pairs/s", n_gpus=world,
                     steps=args.steps, warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="tf32", data="synthetic", config=cfg, details=dict(launch="eager"),
+                    dtype="tf32/fp16 operands, fp32 accumulate", data="synthetic", config=cfg, details=dict(launch="eager"),
                     clocks=clocks,
                     e2e=dict(value=world * pairs * args.steps / (e2e_ms / 1e3), unit="frame-pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=12,
                              ms_per_step=e2e_ms / args.steps,
@@ -577,8 +577,8 @@ def measure_hotpath(key, steps, warmup, rank, world, local, dev, dist, xneg=Fals
 # ----------------------------------------------------------------------------------------------------------------------
 # DRAM traffic per launch of the two tensor-core kernels, from `ncu --set full` captures of the same instances
 # (dram__bytes_read.sum + dram__bytes_write.sum); (size, pairs) -> (bytes, source file)
-NCU_TRAFFIC_GEMM = {(416, 16): (1.465118e9 + 162.2592e6, "profiles/r2n_ncu_full_gemm_cn.txt")}
-NCU_TRAFFIC_GEMM_S = {(416, 16): (354.53568e6 + 883.129088e6, "profiles/r2n_ncu_full_gemm_s.txt"), (256, 8): (88.2e6, "profiles/r1w_ncu_full_umma_gemm2.txt")}
+NCU_TRAFFIC_GEMM = {(416, 16): (788.396544e6 + 154.899968e6, "profiles/r3b_ncu_full_gemm_cn_f16.txt")}
+NCU_TRAFFIC_GEMM_S = {(416, 16): (177.33888e6 + 881.462784e6, "profiles/r3b_ncu_full_gemm_s_f16.txt")}
 NCU_TRAFFIC_COATTN = {(416, 16): (89.010432e6 + 127.560192e6, "profiles/r2n_ncu_full_coattn_fwd.txt"), (256, 8): (16.9e6, "profiles/r1w_ncu_full_coattn_fused.txt")}
 NCU_TRAFFIC_HBM = {(416, 16): {"bn_act_fwd": (177.355264e6 + 136.50944e6, "profiles/r2n_ncu_full_bn_fwd.txt"),
                               "bn_act_bwd_reduce": (367.188224e6 + 145.653248e6, "profiles/r2n_ncu_full_bn_bwd.txt")}}
@@ -609,34 +609,54 @@ def kernel_rooflines(key, dev):
 
     NSET = 5 if size <= 256 else 3
     frs = [torch.nn.functional.normalize(torch.randn(B, C_EMB, N2, device=dev).abs(), dim=1) for _ in range(NSET)]
-    # The dominant kernel family of the step is the persistent tcgen05 tf32 GEMM (cta_group::2 pairs, 256x256 per cluster).  Its two
-    # large instance types at the finest scale, each timed alone on all problems of the batch (= how the step launches them):
-    #   roofline        : a [C,N]-output contraction of the co-attention backward (dFa += Fb dS^T: M=512, N=K=N2), three per scale --
-    #                     the largest share of the step
-    #   roofline_gemm_s : S = Fa^T Fb (M=N=N2, K=512) with the exp / row-sum epilogue's plain sibling, two per scale (S and dP)
+    # The dominant kernel family of the step is the persistent tcgen05 GEMM (cta_group::2 pairs, 256x256 per cluster); its largest
+    # instances are the five contractions of the co-attention backward at the finest scale, which run on fp16 operands (kind::f16: the
+    # 11 significant bits of tf32 at twice its MMA rate).  Two instance types, each timed alone on all problems of the batch (= how the
+    # step launches them):
+    #   roofline        : a [C,N]-output contraction (dFa += Fb dS^T: M=512, N=K=N2, reduce-add epilogue), three per scale -- the largest
+    #                     share of the step
+    #   roofline_gemm_s : S = Fa^T Fb (M=N=N2, K=512), the plain-epilogue sibling of the two N x N-output contractions (S / exp, dP / dS)
     nprob = B
+    ld8 = (N2 + 7) // 8 * 8
+    f16s = [torch.zeros(B, C_EMB, ld8, device=dev, dtype=torch.float16) for _ in range(NSET)]
+    for i in range(NSET):
+        f16s[i][:, :, :N2] = ops.cast_f16(frs[i])
+    s16 = [torch.zeros(nprob, N2, ld8, device=dev, dtype=torch.float16) for _ in range(NSET)]
+    for t in s16:
+        t[:, :, :N2].normal_()
     c_bufs = [torch.empty(nprob, N2, N2, device=dev) for _ in range(NSET)]
-    set_bytes_g = 2 * nprob * C_EMB * N2 * 4 + c_bufs[0].numel() * 4
-    ms_s = timed_sets([(lambda i=i: ops.gemm_tf32(frs[i], frs[(i + 1) % NSET], 1, 1, N2, N2, C_EMB, out=c_bufs[i])) for i in range(NSET)])
+    set_bytes_g = 2 * nprob * C_EMB * ld8 * 2 + s16[0].numel() * 2 + nprob * C_EMB * N2 * 4
+    st0 = torch.cuda.current_stream().cuda_stream
+
+    def gemm16(Aop, a_mn, lda, sA, Bop, b_mn, ldb, sB, out, ldc, sC, M, N, K, atomic):
+        _lib.call("dcnet_gemm_f16", Aop.data_ptr(), a_mn, lda, sA, Bop.data_ptr(), b_mn, ldb, sB, out.data_ptr(), ldc, sC, M, N, K, nprob, 1.0, atomic, st0)
+
+    ms_s = timed_sets([(lambda i=i: gemm16(f16s[i], 1, ld8, C_EMB * ld8, f16s[(i + 1) % NSET], 1, ld8, C_EMB * ld8, c_bufs[i], N2, N2 * N2,
+                                            N2, N2, C_EMB, 0)) for i in range(NSET)])
     fl_s = 2.0 * N2 * N2 * C_EMB * nprob
     ach_s = fl_s / (ms_s * 1e-3) / 1e12
     d_bufs = [torch.zeros(nprob, C_EMB, N2, device=dev) for _ in range(NSET)]
-    ms_g = timed_sets([(lambda i=i: ops.gemm_tf32(frs[i], c_bufs[i], 0, 0, C_EMB, N2, N2, out=d_bufs[i], atomic=1)) for i in range(NSET)])
+    ms_g = timed_sets([(lambda i=i: gemm16(f16s[i], 0, ld8, C_EMB * ld8, s16[i], 0, ld8, N2 * ld8, d_bufs[i], N2, C_EMB * N2,
+                                            C_EMB, N2, N2, 1)) for i in range(NSET)])
     fl_g = 2.0 * C_EMB * N2 * N2 * nprob
     ach_g = fl_g / (ms_g * 1e-3) / 1e12
+    # algorithmic bytes of one launch: A and B read once, the fp32 output read and written once (reduce-add)
+    alg_g = nprob * (C_EMB * N2 * 2 + N2 * N2 * 2 + 2 * C_EMB * N2 * 4)
     tr = NCU_TRAFFIC_GEMM.get((size, pairs))
-    common = dict(bound="tensor", peak=peaks["tensor_burst"], unit="TFLOP/s", dtype="tf32 operands (fp32 in HBM), fp32 accumulate",
+    common = dict(bound="tensor", peak=peaks["tensor_burst"], unit="TFLOP/s", dtype="fp16 operands (kind::f16), fp32 accumulate",
                   l2="operands and outputs rotate over %d sets, %.0f MB in total (> 126 MB L2)" % (NSET, NSET * set_bytes_g / 1e6),
-                  note="peak is the measured bf16 figure; the tf32 tensor pipe is nominally half of it (frac_of_tf32_pipe)",
+                  note="peak is the measured bf16 figure (fp16 and bf16 share the kind::f16 MMA rate)",
                   peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
-    roof = dict(kernel="umma_gemm2_kernel (tcgen05 kind::tf32, cta_group::2 pairs, persistent, TMA reduce-add epilogue; dFa += Fb dS^T of the "
-                "co-attention backward, M=%d N=K=%d, %d problems, one launch)" % (C_EMB, N2, nprob), achieved=ach_g, frac=ach_g / peaks["tensor_burst"],
-                frac_of_tf32_pipe=2.0 * ach_g / peaks["tensor_burst"], ms=ms_g, traffic=tr[0] if tr else None,
+    roof = dict(kernel="umma_gemm2_kernel (tcgen05 kind::f16, cta_group::2 pairs, persistent, TMA reduce-add epilogue; dFa += Fb dS^T of the "
+                "co-attention backward on fp16 operands, M=%d N=K=%d, %d problems, one launch)" % (C_EMB, N2, nprob), achieved=ach_g,
+                frac=ach_g / peaks["tensor_burst"], ms=ms_g, algorithmic_bytes=alg_g, traffic=tr[0] if tr else None,
                 traffic_source=(tr[1] + ": dram__bytes_read.sum + dram__bytes_write.sum") if tr else None, **common)
     tr = NCU_TRAFFIC_GEMM_S.get((size, pairs))
-    roof_s = dict(kernel="umma_gemm2_kernel (same kernel; S = Fa^T Fb of the co-attention backward, M=N=%d K=%d, %d problems, one launch)" % (N2, C_EMB, nprob),
-                  achieved=ach_s, frac=ach_s / peaks["tensor_burst"], frac_of_tf32_pipe=2.0 * ach_s / peaks["tensor_burst"], ms=ms_s,
+    roof_s = dict(kernel="umma_gemm2_kernel (same kernel; S = Fa^T Fb of the co-attention backward on fp16 operands, fp32 output, M=N=%d K=%d, "
+                  "%d problems, one launch)" % (N2, C_EMB, nprob),
+                  achieved=ach_s, frac=ach_s / peaks["tensor_burst"], ms=ms_s,
                   traffic=tr[0] if tr else None, traffic_source=(tr[1] + ": dram__bytes_read.sum + dram__bytes_write.sum") if tr else None, **common)
+    del f16s, s16
     del d_bufs
     del c_bufs
     qa = torch.arange(B, device=dev, dtype=torch.int32)
@@ -796,11 +816,13 @@ def main():
         peaks = load_peaks()
         step_tf = step_flops(key) / (m["ms_per_step"] * 1e-3) / 1e12
         line = dict(metric="frame_pairs_per_sec", value=m["value"], unit="frame-pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=m["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="tf32", data="synthetic",
+                    ms_per_step=m["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="tf32/fp16 operands, fp32 accumulate", data="synthetic",
                     config=config_of(key),
                     details=dict(launch=m["launch"],
-                                 arithmetic="fp32 tensors in HBM; contractions on tcgen05 as tf32 x tf32 -> fp32 (bf16 x bf16 -> fp32 in the fused "
-                                            "co-attention forward); index-producing contractions and everything else in fp32",
+                                 arithmetic="fp32 tensors in HBM; 1x1-conv contractions on tcgen05 as tf32 x tf32 -> fp32 on operands rounded to the "
+                                            "nearest tf32 by their producers; co-attention forward and backward on fp16 x fp16 -> fp32 (kind::f16: the "
+                                            "11 significant bits of tf32, gradient-side operands scaled per problem into fp16's range); "
+                                            "index-producing contractions and everything else in fp32",
                                  grad_allreduce=m["grad_allreduce"], cross_gpu_negatives=m["cross_gpu_negatives"],
                                  step_gemm_tflops=step_tf, step_gemm_frac_of_sustained=step_tf / peaks["tensor_sustained"]),
                     clocks=m["clocks"], e2e=m["e2e"],

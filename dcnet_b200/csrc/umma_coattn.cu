@@ -355,6 +355,11 @@ __global__ void cast_flat_kernel(const float* __restrict__ x, __nv_bfloat16* __r
     y[i] = __float2bfloat16_rn(x[i]);
 }
 
+__global__ void cast_flat_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2half_rn(x[i]);
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int pitch8(int N) { return (N + 7) & ~7; }
 
@@ -474,5 +479,14 @@ extern "C" int dcnet_cast_bf16(const float* x, void* y, long long n, void* strea
   long long g = (n + 255) / 256;
   cast_flat_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
   DCNET_LAUNCH_OK("cast_bf16");
+  return 0;
+}
+
+extern "C" int dcnet_cast_f16(const float* x, void* y, long long n, void* stream) {
+  DCNET_CHECK_ARG(x && y && n >= 0, "cast_f16: bad arguments");
+  if (n == 0) return 0;
+  long long g = (n + 255) / 256;
+  cast_flat_f16_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__half*>(y), n);
+  DCNET_LAUNCH_OK("cast_f16");
   return 0;
 }

@@ -241,6 +241,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // slots and TMA (plain store, or fp32 reduce-add for split reductions / shared gradients) instead of per-thread stores whose
 // lanes hit 32 different rows.  Each epilogue warp owns its 32 rows end to end (2 x 4 KiB slots), so no cross-warp barrier.
 // ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct Gemm2P {
   int M_valid, N_valid, k_iters, k_split, n_split, m_split;
   int a_batched, b_batched, out_batched;
@@ -485,9 +491,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const float bias = (p.u && row_ok && kc == 0) ? p.u[(long long)z * p.ldu + row] : 0.f;
       const float rowmul = (p.epi_exp == 2 && row_ok) ? p.alpha * p.u2[(long long)z * p.ldu + row] : 0.f;
       const float alpha = p.alpha_z ? p.alpha * p.alpha_z[z] : p.alpha;
-      const bool h16 = p.out_f16 != 0;
-      // the value the next MMA will read: rounded to tf32, or to fp16 when the output is stored as fp16
-      auto rnd = [h16](float x) { return h16 ? __half2float(__float2half_rn(x)) : tf32_rn(x); };
+      const bool h16 = p.out_f16 != 0;       // fp16 pipeline of the co-attention backward: its own chunk code below
       float s1 = 0.f, s2 = 0.f;
       // dS epilogue: the E chunk of a thread's row (128 contiguous bytes) is fetched ONE CHUNK AHEAD -- the first one before the
       // accumulator is even complete -- so its L2 / HBM latency hides under the TMEM load, the arithmetic and the store of the
@@ -501,23 +505,12 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       uint8_t* eslots = stage_e + warp * 2 * SLOT_BYTES;
       uint64_t* ebar = e_full + warp * 2;
       float4 ecur[8];
-      const float* erow = (p.epi_exp == 2 && row_ok && !e_tma) ? p.cc + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
+      const float* erow = (p.epi_exp == 2 && row_ok && !e_tma && !h16) ? p.cc + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
       const __half* erow_h = (p.epi_exp == 2 && row_ok && !e_tma && h16)
                                  ? reinterpret_cast<const __half*>(p.cc) + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
       auto load_e = [&](int c, float4 (&dst)[8]) {
         const int nb_ = n0 + c * 32;
-        if (erow_h) {
-          if (nb_ + 32 <= p.N_valid) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(erow_h + nb_ + 8 * e));
-              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-              const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
-              dst[2 * e] = make_float4(a.x, a.y, b.x, b.y);
-              dst[2 * e + 1] = make_float4(c2.x, c2.y, d.x, d.y);
-            }
-          }
-        } else if (erow && nb_ + 32 <= p.N_valid) {
+        if (erow && nb_ + 32 <= p.N_valid) {
 #pragma unroll
           for (int e = 0; e < 8; e++) dst[e] = __ldg(reinterpret_cast<const float4*>(erow + nb_ + 4 * e));
         }
@@ -529,7 +522,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tma_load_3d(eslots + (k & 1u) * SLOT_BYTES, &mapO2, &ebar[k & 1u], n0 + c * 32, row0, z);
       };
       if (e_tma) { if (lane == 0) tma_e(0); }
-      else if (p.epi_exp == 2) load_e(0, ecur);
+      else if (p.epi_exp == 2 && !h16) load_e(0, ecur);
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
       if (threadIdx.x == 0) GTRACE(tl, 4);
@@ -539,29 +532,89 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (e_tma) {
           if (h16) { if (lane == 0 && (c & 1) == 0 && c + 2 < BN / 32) tma_e(c + 2); }
           else if (lane == 0 && c + 1 < BN / 32) tma_e(c + 1);
-        } else if (p.epi_exp == 2 && c + 1 < BN / 32) load_e(c + 1, enext);
+        } else if (p.epi_exp == 2 && !h16 && c + 1 < BN / 32) load_e(c + 1, enext);
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + (uint32_t)(c * 32), v);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
+        if (h16) {
+          // ---- fp16 pipeline (co-attention backward, epi_exp 1 / 2): the chunk's 32 values are produced, rounded to fp16, summed (the
+          // row sum is the sum of exactly the values the next MMA reads) and packed in ONE pass -- ~5 instructions per element; the
+          // epilogue warp is the bottleneck of these N x N-output contractions (one warp per SM sub-partition).  Chunks 2j and 2j+1
+          // fill the two halves of one 128-byte slot row (64 fp16), one TMA store per pair; BN / 32 is even, so the parity of the
+          // running chunk counter is the parity of c.
+          uint32_t pk[16];
+          float rs = 0.f;
+          const bool full = nb + 32 <= p.N_valid;
+          if (p.epi_exp == 1) {
+            const float a2 = p.alpha * 1.4426950408889634f, c2 = (p.exp_shift - bias) * 1.4426950408889634f;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+              float x0 = ex2_approx(fmaf(v[2 * e], a2, c2)), x1 = ex2_approx(fmaf(v[2 * e + 1], a2, c2));
+              if (!full) { if (nb + 2 * e >= p.N_valid) x0 = 0.f; if (nb + 2 * e + 1 >= p.N_valid) x1 = 0.f; }
+              const __half2 hh = __floats2half2_rn(x0, x1);
+              pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              const float2 f = __half22float2(hh);
+              rs += f.x; rs += f.y;
+            }
+          } else {
+            // dS = tau (dP - delta) E / r : per-row delta (bias) and tau / r (rowmul); E tile: this chunk's half of the 128-byte row
+            uint32_t eh[16];
+            if (e_tma) {
+              const uint32_t k = echunk + (uint32_t)(c >> 1);
+              mbar_wait(&ebar[k & 1u], (k >> 1) & 1u);
+              const uint8_t* er = eslots + (k & 1u) * SLOT_BYTES + lane * 128;
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const uint4 q = *reinterpret_cast<const uint4*>(er + ((((c & 1) * 4 + e) ^ (lane & 7)) * 16));
+                eh[4 * e] = q.x; eh[4 * e + 1] = q.y; eh[4 * e + 2] = q.z; eh[4 * e + 3] = q.w;
+              }
+            } else if (erow_h && full) {
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(erow_h + nb + 8 * e));
+                eh[4 * e] = q.x; eh[4 * e + 1] = q.y; eh[4 * e + 2] = q.z; eh[4 * e + 3] = q.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; e++) {
+                const __half2 hh = __halves2half2((erow_h && nb + 2 * e < p.N_valid) ? erow_h[nb + 2 * e] : __float2half(0.f),
+                                                  (erow_h && nb + 2 * e + 1 < p.N_valid) ? erow_h[nb + 2 * e + 1] : __float2half(0.f));
+                eh[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+              const float2 ev = __half22float2(*reinterpret_cast<const __half2*>(&eh[e]));
+              const __half2 hh = __floats2half2_rn((v[2 * e] - bias) * (rowmul * ev.x), (v[2 * e + 1] - bias) * (rowmul * ev.y));
+              pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              const float2 f = __half22float2(hh);
+              rs += f.x; rs += f.y;
+            }
+          }
+          if (p.sum && row_ok) s1 += rs;
+          uint8_t* slot16 = slots + ((chunk >> 1) % NSLOT) * SLOT_BYTES;
+          if ((c & 1) == 0) {
+            if (lane == 0) tma_store_wait_read_n<NSLOT - 1>();
+            __syncwarp();
+          }
+          uint8_t* srow16 = slot16 + lane * 128;
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            *reinterpret_cast<uint4*>(srow16 + ((((c & 1) * 4 + e) ^ (lane & 7)) * 16)) = make_uint4(pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
+          if (c & 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (row0 < p.M_valid && nb - 32 < p.N_valid) tma_store_3d(mo, slot16, nb - 32, orow0, zc);
+              tma_store_commit();
+            }
+          }
+          continue;
+        }
         if (p.epi_exp == 1) {
 #pragma unroll
-          for (int e = 0; e < 32; e++) v[e] = rnd(__expf(fmaf(p.alpha, v[e], p.exp_shift - bias)));
-        } else if (e_tma && h16) {
-          // dS = tau (dP - delta) E / r with the fp16 E block of this chunk pair: this chunk's half of the thread's 128-byte row
-          const uint32_t k = echunk + (uint32_t)(c >> 1);
-          mbar_wait(&ebar[k & 1u], (k >> 1) & 1u);
-          const uint8_t* er = eslots + (k & 1u) * SLOT_BYTES + lane * 128;
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const uint4 q = *reinterpret_cast<const uint4*>(er + ((((c & 1) * 4 + e) ^ (lane & 7)) * 16));
-            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-            const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
-            v[8 * e] = rnd((v[8 * e] - bias) * rowmul * a.x); v[8 * e + 1] = rnd((v[8 * e + 1] - bias) * rowmul * a.y);
-            v[8 * e + 2] = rnd((v[8 * e + 2] - bias) * rowmul * b.x); v[8 * e + 3] = rnd((v[8 * e + 3] - bias) * rowmul * b.y);
-            v[8 * e + 4] = rnd((v[8 * e + 4] - bias) * rowmul * c2.x); v[8 * e + 5] = rnd((v[8 * e + 5] - bias) * rowmul * c2.y);
-            v[8 * e + 6] = rnd((v[8 * e + 6] - bias) * rowmul * d.x); v[8 * e + 7] = rnd((v[8 * e + 7] - bias) * rowmul * d.y);
-          }
+          for (int e = 0; e < 32; e++) v[e] = tf32_rn(__expf(fmaf(p.alpha, v[e], p.exp_shift - bias)));
         } else if (e_tma) {
           // dS = tau (dP - delta) E / r : per-row delta (bias) and tau / r (rowmul)
           const uint32_t k = echunk + (uint32_t)c;
@@ -580,16 +633,13 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 8; e++) {
                 const float4 q = ecur[e];
-                v[4 * e] = rnd((v[4 * e] - bias) * rowmul * q.x); v[4 * e + 1] = rnd((v[4 * e + 1] - bias) * rowmul * q.y);
-                v[4 * e + 2] = rnd((v[4 * e + 2] - bias) * rowmul * q.z); v[4 * e + 3] = rnd((v[4 * e + 3] - bias) * rowmul * q.w);
+                v[4 * e] = tf32_rn((v[4 * e] - bias) * rowmul * q.x); v[4 * e + 1] = tf32_rn((v[4 * e + 1] - bias) * rowmul * q.y);
+                v[4 * e + 2] = tf32_rn((v[4 * e + 2] - bias) * rowmul * q.z); v[4 * e + 3] = tf32_rn((v[4 * e + 3] - bias) * rowmul * q.w);
               }
             } else {
-              // ragged last chunk of the row: element by element
+              const float* er = erow + nb;      // ragged last chunk of the row: element by element
 #pragma unroll
-              for (int e = 0; e < 32; e++) {
-                const float ev = (nb + e < p.N_valid) ? (erow_h ? __half2float(erow_h[nb + e]) : erow[nb + e]) : 0.f;
-                v[e] = (nb + e < p.N_valid) ? rnd((v[e] - bias) * rowmul * ev) : 0.f;
-              }
+              for (int e = 0; e < 32; e++) v[e] = (nb + e < p.N_valid) ? tf32_rn((v[e] - bias) * rowmul * er[e]) : 0.f;
             }
           }
 #pragma unroll
@@ -620,33 +670,6 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             for (int e = 0; e < 32; e++)
               if (nb + e < p.N_valid) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
           }
-        }
-        if (h16) {
-          // fp16 output: the chunks 2j and 2j+1 fill the two halves of one 128-byte slot row (64 fp16), one TMA store per pair.  BN / 32
-          // is even, so the parity of the running chunk counter is the parity of c
-          uint8_t* slot16 = slots + ((chunk >> 1) % NSLOT) * SLOT_BYTES;
-          if ((c & 1) == 0) {
-            if (lane == 0) tma_store_wait_read_n<NSLOT - 1>();
-            __syncwarp();
-          }
-          uint8_t* srow16 = slot16 + lane * 128;
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const __half2 h0 = __floats2half2_rn(v[8 * e], v[8 * e + 1]), h1 = __floats2half2_rn(v[8 * e + 2], v[8 * e + 3]);
-            const __half2 h2 = __floats2half2_rn(v[8 * e + 4], v[8 * e + 5]), h3 = __floats2half2_rn(v[8 * e + 6], v[8 * e + 7]);
-            *reinterpret_cast<uint4*>(srow16 + ((((c & 1) * 4 + e) ^ (lane & 7)) * 16)) =
-                make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                           *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
-          }
-          if (c & 1) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              if (row0 < p.M_valid && nb - 32 < p.N_valid) tma_store_3d(mo, slot16, nb - 32, orow0, zc);
-              tma_store_commit();
-            }
-          }
-          continue;
         }
         uint8_t* slot = slots + (chunk % NSLOT) * SLOT_BYTES;
         if (p.direct_store) {
@@ -833,7 +856,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
   // persistent kernel with TMA-store epilogue whenever the output rows are TMA-addressable
   auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
   const int oal = e.out_f16 ? 8 : 4;        // elements per 16 bytes of the output
-  DCNET_CHECK_ARG(!e.out_f16 || (!e.atomic && e.m_split == 0 && !(e.cc && e.epi_exp != 2)), "umma_gemm: fp16 output: plain store, no m_split, no cc term");
+  DCNET_CHECK_ARG(!e.out_f16 || (!e.atomic && e.m_split == 0 && (e.epi_exp == 1 || e.epi_exp == 2)), "umma_gemm: fp16 output belongs to the exp / dS epilogues (plain store, no m_split)");
   const bool out_ok = al16(e.out) && e.ldo % oal == 0 && e.so_b % oal == 0 &&
                       (e.m_split == 0 || (e.m_split % BM == 0 && e.out2 && al16(e.out2) && e.ldo2 % 4 == 0 && e.so_b2 % 4 == 0)) &&
                       (!e.cc || (al16(e.cc) && e.ldcc % oal == 0)) && !(e.so_b == 0 && batch > 1 && !e.atomic) && !g_force_v1;
@@ -973,5 +996,21 @@ extern "C" int dcnet_gemm_bf16(const void* A, int a_mn_major, long long lda, lon
   UmmaOperand b{(const float*)B, b_mn_major ? K : N, b_mn_major ? N : K, ldb, strideB, batch, b_mn_major != 0, true};
   UmmaEpilogue e{};
   e.out = C; e.ldo = ldc; e.so_b = strideC; e.alpha = alpha; e.atomic = atomic;
+  return umma_gemm(a, b, nullptr, M, N, K, 0, 0, batch, e, as_stream(stream));
+}
+
+
+// same contraction with fp16 operands (kind::f16, fp32 accumulation): __half data, pitches in elements.  fp16 keeps the 11 significant
+// bits of tf32, so for operands inside its normal range this is the tf32 contraction at twice the MMA rate (co-attention backward)
+extern "C" int dcnet_gemm_f16(const void* A, int a_mn_major, long long lda, long long strideA,
+                              const void* B, int b_mn_major, long long ldb, long long strideB,
+                              float* C, long long ldc, long long strideC, int M, int N, int K, int batch, float alpha, int atomic,
+                              void* stream) {
+  DCNET_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_f16: bad arguments");
+  UmmaOperand a{(const float*)A, a_mn_major ? K : M, a_mn_major ? M : K, lda, strideA, batch, a_mn_major != 0, true, true};
+  UmmaOperand b{(const float*)B, b_mn_major ? K : N, b_mn_major ? N : K, ldb, strideB, batch, b_mn_major != 0, true, true};
+  UmmaEpilogue e{};
+  e.out = C; e.ldo = ldc; e.so_b = strideC; e.alpha = alpha; e.atomic = atomic;
+  if (atomic) e.k_chunks = -1;
   return umma_gemm(a, b, nullptr, M, N, K, 0, 0, batch, e, as_stream(stream));
 }

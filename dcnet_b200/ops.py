@@ -112,6 +112,24 @@ def gemm_bf16(A, B, a_mn, b_mn, M, N, K, alpha=1.0):
     return C
 
 
+def cast_f16(x):
+    """fp32 -> fp16 (round to nearest even) with the library's own kernel"""
+    x = _c(x, name="x")
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    _lib.call("dcnet_cast_f16", _p(x), _p(y), x.numel(), _st())
+    return y
+
+
+def gemm_f16(A, B, a_mn, b_mn, M, N, K, alpha=1.0, out=None, atomic=0):
+    """tcgen05 kind::f16 GEMM on fp16 operands (same operand conventions as gemm_tf32), fp32 result; atomic=1 adds into `out`."""
+    A, B = _c(A, torch.float16, "A"), _c(B, torch.float16, "B")
+    batch = A.shape[0]
+    C = torch.empty(batch, M, N, device=A.device, dtype=F32) if out is None else out
+    _lib.call("dcnet_gemm_f16", _p(A), int(a_mn), A.shape[2], A.shape[1] * A.shape[2], _p(B), int(b_mn), B.shape[2], B.shape[1] * B.shape[2],
+              _p(C), N, M * N, M, N, K, batch, alpha, int(atomic), _st())
+    return C
+
+
 def pix2text(x, fa):
     """x [B,C,N], fa [B,C] -> sim [B,N]   (forward only; inference / clip path)"""
     x, fa = _c(x.detach(), name="x"), _c(fa.detach(), name="fa")

@@ -63,6 +63,14 @@ DCNET_API int dcnet_gemm_bf16(const void* A, int a_mn_major, long long lda, long
                               float* C, long long ldc, long long strideC, int M, int N, int K, int batch, float alpha, int atomic,
                               void* stream);
 DCNET_API int dcnet_cast_bf16(const float* x, void* y, long long n, void* stream);
+/* and with fp16 operands (__half; dcnet_cast_f16 rounds to nearest even): the 11 significant bits of tf32 at twice its MMA rate, for
+ * operands inside fp16's normal range.  This is what the co-attention backward runs on (dcnet_coattn_bwd with `staged`).  atomic = 1:
+ * reduce-add into C, the reduction split over CTAs when the tiles do not fill the SMs.                                          */
+DCNET_API int dcnet_gemm_f16(const void* A, int a_mn_major, long long lda, long long strideA,
+                             const void* B, int b_mn_major, long long ldb, long long strideB,
+                             float* C, long long ldc, long long strideC, int M, int N, int K, int batch, float alpha, int atomic,
+                             void* stream);
+DCNET_API int dcnet_cast_f16(const float* x, void* y, long long n, void* stream);
 /* which tensor-core GEMM kernel every entry point of this library uses: 0 (default) = persistent kernel, two TMEM accumulator
  * stages, epilogue through swizzled smem slots and TMA store / reduce-add; 5 = the same with coalesced 16-byte st.global /
  * red.global.add.v4.f32 from the slots; 3 / 4 = with thread-block clusters of 2 / 4 CTAs (consecutive M tiles) that multicast

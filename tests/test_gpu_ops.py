@@ -96,6 +96,34 @@ def test_gemm_bf16_all_operand_majors(a_mn, b_mn, M, N, K, batch):
     assert e < 1e-5, e
 
 
+@pytest.mark.parametrize("a_mn,b_mn,M,N,K,batch,atomic", [(0, 0, 512, 2704, 2704, 2, 1), (0, 1, 512, 1024, 1024, 3, 1), (1, 1, 1024, 1024, 512, 2, 0),
+                                                       (1, 1, 256, 256, 512, 4, 0), (0, 0, 512, 680, 672, 2, 1), (1, 0, 384, 512, 128, 1, 0)])
+def test_gemm_f16_operands(a_mn, b_mn, M, N, K, batch, atomic):
+    """tcgen05 kind::f16 on fp16 operands (what the co-attention backward runs on): single-CTA tiles and cta_group::2 pairs, plain store
+    and reduce-add (split reduction), against fp64 on the same fp16-rounded operands -- and, since fp16 and tf32 keep the same 11
+    significant bits, the same numbers as the tf32 GEMM on those operands up to the accumulation order."""
+    g = gen(19 + M + N + K)
+    A = torch.randn(batch, M, K, generator=g)
+    B = torch.randn(batch, N, K, generator=g)
+    Ad = ops.cast_f16((A.transpose(1, 2).contiguous() if a_mn else A).to(DEV))
+    Bd = ops.cast_f16((B.transpose(1, 2).contiguous() if b_mn else B).to(DEV))
+    assert torch.equal(Ad.cpu(), (A.transpose(1, 2).contiguous() if a_mn else A).to(torch.float16))      # RNE cast
+    Ar = (Ad.transpose(1, 2) if a_mn else Ad).double().cpu()
+    Br = (Bd.transpose(1, 2) if b_mn else Bd).double().cpu()
+    ref = torch.bmm(Ar, Br.transpose(1, 2))
+    if atomic:
+        base = torch.randn(batch, M, N, generator=g)
+        C = ops.gemm_f16(Ad, Bd, a_mn, b_mn, M, N, K, alpha=0.5, out=base.to(DEV).clone(), atomic=1)
+        ref = base.double() + 0.5 * ref
+    else:
+        C = ops.gemm_f16(Ad, Bd, a_mn, b_mn, M, N, K)
+    e = rel(C, ref)
+    Ct = ops.gemm_tf32(Ad.float(), Bd.float(), a_mn, b_mn, M, N, K)
+    e2 = rel(ops.gemm_f16(Ad, Bd, a_mn, b_mn, M, N, K), Ct)
+    print("gemm_f16 a_mn=%d b_mn=%d M=%d N=%d K=%d atomic=%d: rel err %.2e vs fp64, %.2e vs the tf32 GEMM on the same values" % (a_mn, b_mn, M, N, K, atomic, e, e2))
+    assert e < 2e-5 and e2 < 2e-5, (e, e2)
+
+
 @pytest.mark.parametrize("M,N,K,batch", [(200, 680, 104, 2), (512, 1024, 256, 3), (384, 512, 160, 2), (1024, 256, 64, 1)])
 @pytest.mark.parametrize("b_mn", [0, 1])
 def test_gemm_kernel_variants_agree_bit_for_bit(M, N, K, batch, b_mn):
