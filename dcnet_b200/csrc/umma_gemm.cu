@@ -544,18 +544,29 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           // fill the two halves of one 128-byte slot row (64 fp16), one TMA store per pair; BN / 32 is even, so the parity of the
           // running chunk counter is the parity of c.
           uint32_t pk[16];
-          float rs = 0.f;
+          float rs = 0.f, rs2 = 0.f;
           const bool full = nb + 32 <= p.N_valid;
           if (p.epi_exp == 1) {
             const float a2 = p.alpha * 1.4426950408889634f, c2 = (p.exp_shift - bias) * 1.4426950408889634f;
+            if (full) {          // (a separate copy: the column masks of the ragged chunk cost 3 predicated instructions per element)
 #pragma unroll
-            for (int e = 0; e < 16; e++) {
-              float x0 = ex2_approx(fmaf(v[2 * e], a2, c2)), x1 = ex2_approx(fmaf(v[2 * e + 1], a2, c2));
-              if (!full) { if (nb + 2 * e >= p.N_valid) x0 = 0.f; if (nb + 2 * e + 1 >= p.N_valid) x1 = 0.f; }
-              const __half2 hh = __floats2half2_rn(x0, x1);
-              pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
-              const float2 f = __half22float2(hh);
-              rs += f.x; rs += f.y;
+              for (int e = 0; e < 16; e++) {
+                const __half2 hh = __floats2half2_rn(ex2_approx(fmaf(v[2 * e], a2, c2)), ex2_approx(fmaf(v[2 * e + 1], a2, c2)));
+                pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                const float2 f = __half22float2(hh);
+                rs += f.x; rs2 += f.y;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; e++) {
+                float x0 = ex2_approx(fmaf(v[2 * e], a2, c2)), x1 = ex2_approx(fmaf(v[2 * e + 1], a2, c2));
+                if (nb + 2 * e >= p.N_valid) x0 = 0.f;
+                if (nb + 2 * e + 1 >= p.N_valid) x1 = 0.f;
+                const __half2 hh = __floats2half2_rn(x0, x1);
+                pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                const float2 f = __half22float2(hh);
+                rs += f.x; rs += f.y;
+              }
             }
           } else {
             // dS = tau (dP - delta) E / r : per-row delta (bias) and tau / r (rowmul); E tile: this chunk's half of the 128-byte row
@@ -589,10 +600,10 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               const __half2 hh = __floats2half2_rn((v[2 * e] - bias) * (rowmul * ev.x), (v[2 * e + 1] - bias) * (rowmul * ev.y));
               pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
               const float2 f = __half22float2(hh);
-              rs += f.x; rs += f.y;
+              rs += f.x; rs2 += f.y;
             }
           }
-          if (p.sum && row_ok) s1 += rs;
+          if (p.sum && row_ok) s1 += rs + rs2;
           uint8_t* slot16 = slots + ((chunk >> 1) % NSLOT) * SLOT_BYTES;
           if ((c & 1) == 0) {
             if (lane == 0) tma_store_wait_read_n<NSLOT - 1>();

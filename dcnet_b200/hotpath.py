@@ -71,6 +71,8 @@ class HotPath(nn.Module):
     side_priority = (0, 0)
     aux_priority = (-1, -1)
     terms_on_aux = True
+    # the finest scale's chain (the critical path of the step) on a stream of its own priority; None = the caller's stream (priority 0)
+    finest_priority = None
     finest_first = False     # measured: 7.96 ms against 7.85 ms (C3), 1.475 against 1.439 (C2), profiles/r2l_variants.txt
 
     def _run_scales(self, chain):
@@ -92,7 +94,17 @@ class HotPath(nn.Module):
                 outs[s] = chain(s)
         # (issuing the finest chain first was measured and changes nothing, profiles/r2j_timeline_c3.txt: its first GEMM then shares
         # the SMs with the coarsest scale's exact-fp32 conv instead of waiting behind it)
-        outs[2] = chain(2)
+        if self.finest_priority is None:
+            outs[2] = chain(2)
+        else:
+            if getattr(self, "_fine", None) is None:
+                self._fine = torch.cuda.Stream(priority=self.finest_priority)
+            self._fine.wait_event(fork)
+            with torch.cuda.stream(self._fine):
+                outs[2] = chain(2)
+            cur.wait_stream(self._fine)
+            for t in _tensors(outs[2]):
+                t.record_stream(cur)
         if getattr(self, "_aux_pending", False):
             for aux in self._aux:
                 cur.wait_stream(aux)

@@ -458,13 +458,18 @@ class _ConvBNAct(torch.autograd.Function):
         ctx.cfg = (training, slope, int(l2norm), u is not None, cc is not None, ctx_precision, rounded)
         outs = (y,) if fa is None else (y, sim, neg)
         if stage_out:
+            # the staging buffer is an output without a gradient; autograd must not materialise a zero tensor of its size for it
+            # (88 MB at 416x416: a 35 us fill on the critical path, profiles/r3a_timeline_c3.txt)
             ctx.mark_non_differentiable(staged)
+            ctx.set_materialize_grads(False)
             outs = outs + (staged,)
         return outs[0] if len(outs) == 1 else outs
 
     @staticmethod
     def backward(ctx, dy, *more):
         dsim, dneg = (more[0], more[1]) if len(more) >= 2 else (None, None)
+        if dy is None and not any(g is not None for g in more):
+            return (None,) * 23
         x1, x2, weight_full, gamma, beta, fa, fa_neg, z, mean, invstd, flang, coords, weight = ctx.saved_tensors
         training, slope, l2norm, has_u, has_cc, precision, rounded = ctx.cfg
         terms = flang is not None          # u / cc were derived from (flang, coords) inside forward
@@ -481,9 +486,14 @@ class _ConvBNAct(torch.autograd.Function):
         C, ldw = weight.shape
         dev = x1.device
         st = _st()
+        if dy is None:                       # set_materialize_grads(False): an unused output arrives as None
+            dy = torch.zeros_like(z)
         dy = _c(dy, name="dy")
-        dsim = _c(dsim, name="dsim") if fa is not None else None
-        dneg = _c(dneg, name="dneg") if fa is not None else None
+        if fa is not None:
+            dsim = torch.zeros(B, N, device=dev, dtype=F32) if dsim is None else _c(dsim, name="dsim")
+            dneg = torch.zeros(B, N, device=dev, dtype=F32) if dneg is None else _c(dneg, name="dneg")
+        else:
+            dsim = dneg = None
         dv = torch.empty_like(z)
         # every accumulator the reduce kernel adds into with atomics, zeroed by ONE fill
         want_dfa = fa is not None and ctx.needs_input_grad[7]
