@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libdcnet_sm100.so")
 ABI_VERSION = 4
 
 _CTYPES = {
-    "int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong, "size_t": ctypes.c_size_t,
+    "int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong, "size_t": ctypes.c_size_t, "unsigned int": ctypes.c_uint,
     "void": None,
 }
 

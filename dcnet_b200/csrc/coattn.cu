@@ -175,11 +175,12 @@ __device__ __forceinline__ float coattn_scale(unsigned int mbits) {
 // coattn_delta_kernel of the fp16 pipeline: delta <- s <dO, O> (the row term in the scaled units of dP), r <- 1 / r, and the scaled fp16
 // copy dO16[z][c][n] = fp16(s dO) (pitch ldh); block (0, z, 0) also publishes alpha_z[z] = 1 / s.
 __global__ void __launch_bounds__(256) coattn_delta16_kernel(const float* __restrict__ dO, const float* __restrict__ O, const int* __restrict__ oidx,
-                                                             const unsigned int* __restrict__ mx, float* __restrict__ r, float* __restrict__ delta,
-                                                             __half* __restrict__ dO16, float* __restrict__ alpha_z, int C, int N, int ldh) {
+                                                             const unsigned int* __restrict__ mx, int mx_by_oidx, float* __restrict__ r,
+                                                             float* __restrict__ delta, __half* __restrict__ dO16, float* __restrict__ alpha_z,
+                                                             int C, int N, int ldh) {
   const int z = blockIdx.y;
   const int n = (blockIdx.x * 32 + threadIdx.x) * 4;
-  const float s = coattn_scale(mx[z]);
+  const float s = coattn_scale(mx[mx_by_oidx ? oidx[z] : z]);
   if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0) alpha_z[z] = 1.f / s;
   const int cper = (C + gridDim.z - 1) / gridDim.z, c0 = blockIdx.z * cper, c1 = min(C, c0 + cper);
   __shared__ float part[8][128];
@@ -216,12 +217,12 @@ __global__ void __launch_bounds__(256) coattn_delta16_kernel(const float* __rest
 //   dOs16[z][c,i] = fp16( (s dO[c,i] - rho_i Fa[c,i]) / r_i ),     dframes[qa[z]][c,i] -= (rho_i / s) O[c,i]
 __global__ void __launch_bounds__(256) coattn_fix16_kernel(const float* __restrict__ dO, const float* __restrict__ O, const __half* __restrict__ F16,
                                                            const int* __restrict__ oidx, const int* __restrict__ qa, const float* __restrict__ inv_r,
-                                                           const float* __restrict__ rho, const unsigned int* __restrict__ mx,
+                                                           const float* __restrict__ rho, const unsigned int* __restrict__ mx, int mx_by_oidx,
                                                            __half* __restrict__ dOs16, float* __restrict__ dframes, int C, int N, int ldh) {
   const int z = blockIdx.y;
   const int n = (blockIdx.x * 32 + threadIdx.x) * 4;
   if (n >= N) return;
-  const float s = coattn_scale(mx[z]), is = 1.f / s;
+  const float s = coattn_scale(mx[mx_by_oidx ? oidx[z] : z]), is = 1.f / s;
   const long long so = (long long)oidx[z] * C * N + n;
   const long long sq = (long long)qa[z] * C * N + n;
   const __half* fq = F16 + (long long)qa[z] * C * ldh + n;
@@ -343,6 +344,14 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
                                 const float* out, int n_out, const float* lse, const float* dout, float* dframes,
                                 int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,
                                 void* stream) {
+  return dcnet_coattn_bwd_ex(frames, F, qa, kb, oidx, nprob, out, n_out, lse, dout, nullptr, dframes, C, N, tau, precision, staged, workspace,
+                             workspace_bytes, stream);
+}
+
+extern "C" int dcnet_coattn_bwd_ex(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                   const float* out, int n_out, const float* lse, const float* dout, const unsigned int* dout_absmax,
+                                   float* dframes, int C, int N, float tau, int precision, const void* staged, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   DCNET_CHECK_ARG(frames && qa && kb && oidx && lse && dout && dframes && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_bwd: bad arguments");
   DCNET_CHECK_ARG(out || precision != 2, "coattn_bwd: the saved forward output is needed (delta = <dO, O>)");
   if (nprob == 0) return 0;
@@ -413,21 +422,27 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
     const UmmaOperand dSk = H(dS16, N, N, ldh, NLh, nprob, false), dSmn = H(dS16, N, N, ldh, NLh, nprob, true);
     const int mblk = ceil_div(N, 128) * nprob;
     const int zsl = mblk >= 592 ? 1 : (592 / mblk > 8 ? 8 : 592 / mblk);
-    coattn_absmax_kernel<<<dim3(8, nprob), 256, 0, st>>>(dout, oidx, mx, CN / 4);
-    DCNET_LAUNCH_OK("coattn_bwd.absmax");
+    const unsigned int* mxp = mx;
+    const int mx_by_oidx = dout_absmax ? 1 : 0;
+    if (dout_absmax) {
+      mxp = dout_absmax;            // max |dout[row]| per output row, left by the GEMM that produced dout (dcnet_conv1x1_bwd_data_absmax)
+    } else {
+      coattn_absmax_kernel<<<dim3(8, nprob), 256, 0, st>>>(dout, oidx, mx, CN / 4);
+      DCNET_LAUNCH_OK("coattn_bwd.absmax");
+    }
     // E' = 2^8 exp(tau S - lse_fwd) (fp16) with row sums r'
     UmmaEpilogue e{};
     e.out = reinterpret_cast<float*>(E16); e.out_f16 = 1; e.ldo = ldh; e.so_b = NLh; e.alpha = tau; e.idxA = qa; e.idxB = kb;
     e.epi_exp = 1; e.u = lse; e.ldu = N; e.exp_shift = E_SHIFT; e.sum = rsum; e.sum_ldz = N;
     DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
-    coattn_delta16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, oidx, mx, rsum, delta, dO16, alpha_z, C, N, ldh);
+    coattn_delta16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, oidx, mxp, mx_by_oidx, rsum, delta, dO16, alpha_z, C, N, ldh);
     DCNET_LAUNCH_OK("coattn_bwd.delta16");
     // s dS' = tau (s dP - s delta) E' / r' (fp16) with row sums s rho
     e = UmmaEpilogue{};
     e.out = reinterpret_cast<float*>(dS16); e.out_f16 = 1; e.ldo = ldh; e.so_b = NLh; e.alpha = tau; e.idxB = kb;
     e.epi_exp = 2; e.u = delta; e.u2 = rsum; e.ldu = N; e.cc = reinterpret_cast<const float*>(E16); e.ldcc = ldh; e.cc_sb = NLh; e.sum = rho; e.sum_ldz = N;
     DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
-    coattn_fix16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, F16, oidx, qa, rsum, rho, mx, dOs16, dframes, C, N, ldh);
+    coattn_fix16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, F16, oidx, qa, rsum, rho, mxp, mx_by_oidx, dOs16, dframes, C, N, ldh);
     DCNET_LAUNCH_OK("coattn_bwd.fix16");
     e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.alpha_z = alpha_z; e.atomic = 1; e.idxC = kb; e.k_chunks = -1;
     DCNET_TRY(umma_gemm(Gsk, Emn, nullptr, C, N, N, 0, 0, nprob, e, st));

@@ -113,6 +113,9 @@ struct UmmaEpilogue {
   int out_f16 = 0;
   float exp_shift = 0.f;
   const float* alpha_z = nullptr;
+  // plain epilogue with m_split: absmax2[z] = max |out2[z]| as the bit pattern of a non-negative float (caller zeroes) -- the
+  // per-problem scale of the co-attention backward's fp16 pipeline comes out of the GEMM that produces its dO
+  unsigned int* absmax2 = nullptr;
   // 3x3 convolution as an implicit GEMM (conv3x3.cu; see Gemm2P in umma_gemm.cu): B, B2, B3 = the map shifted by dx = -1, 0, +1
   const UmmaOperand* B3 = nullptr;
   int tap_kper = 0, tap_w = 0, tap_flip = 0, tap_n = 0;

@@ -558,6 +558,11 @@ extern "C" int dcnet_conv1x1_fwd(const float* x1, int K1, const float* x2, int K
 
 extern "C" int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, float* dx1, int K1, float* dx2, int K2,
                                       int B, int C, int N, int precision, void* stream) {
+  return dcnet_conv1x1_bwd_data_absmax(dz, W, ldw, dx1, K1, dx2, K2, B, C, N, precision, nullptr, stream);
+}
+
+extern "C" int dcnet_conv1x1_bwd_data_absmax(const float* dz, const float* W, int ldw, float* dx1, int K1, float* dx2, int K2,
+                                             int B, int C, int N, int precision, unsigned int* dx2_absmax, void* stream) {
   DCNET_CHECK_ARG(dz && W && B > 0 && C > 0 && N > 0 && ldw >= K1 + K2, "conv1x1_bwd_data: bad arguments");
   cudaStream_t st = as_stream(stream);
   const bool tc = precision == 1 && tc_shape_ok(N, dz, W) && tc_shape_ok(N, dx1, dx2) && ldw % 4 == 0 && C % 32 == 0 && K1 % 128 == 0 &&
@@ -573,8 +578,14 @@ extern "C" int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, 
     if (dx1) { e.out = dx1; e.ldo = N; e.so_b = (long long)K1 * N; }
     if (dx1 && dx2) { e.out2 = dx2; e.ldo2 = N; e.so_b2 = (long long)K2 * N; e.m_split = K1; }
     if (!dx1) { e.out = dx2; e.ldo = N; e.so_b = (long long)K2 * N; }
+    if (dx2_absmax) {
+      DCNET_CHECK_ARG(dx1 && dx2, "conv1x1_bwd_data: dx2_absmax needs both outputs");
+      DCNET_CUDA(cudaMemsetAsync(dx2_absmax, 0, (size_t)B * sizeof(unsigned int), st), "conv1x1_bwd_data.memset");
+      e.absmax2 = dx2_absmax;
+    }
     return umma_gemm(A, Bz, nullptr, M, N, C, 0, 0, B, e, st);
   }
+  DCNET_CHECK_ARG(!dx2_absmax, "conv1x1_bwd_data: dx2_absmax is produced by the tensor-core path only");
   if (dx1)
     DCNET_TRY(sgemm_launch(W, dz, dx1, K1, N, C, B, 1, 1, ldw, 0, 0, N, 1, (long long)C * N, 0, N, 1, (long long)K1 * N,
                            nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 0, st));

@@ -267,6 +267,7 @@ struct Gemm2P {
   int f16;             // 2-byte operands are __half (FMT_F16) instead of __nv_bfloat16
   int out_f16;         // out / the E tile are __half tensors: two 32-column chunks share one 128-byte slot row, values rounded to fp16
   float exp_shift; const float* alpha_z;
+  unsigned int* absmax2;
   int direct_store;    // 1: epilogue leaves through coalesced st.global / red.global.add.v4 instead of TMA store / reduce
   float* out; long long ldo, so_b; float* out2; long long ldo2, so_b2;
   long long* trace;    // optional [CTA][tile slot < 8][8] clock stamps (profiling entry point dcnet_gemm_tf32_trace); nullptr = off
@@ -492,7 +493,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const float rowmul = (p.epi_exp == 2 && row_ok) ? p.alpha * p.u2[(long long)z * p.ldu + row] : 0.f;
       const float alpha = p.alpha_z ? p.alpha * p.alpha_z[z] : p.alpha;
       const bool h16 = p.out_f16 != 0;       // fp16 pipeline of the co-attention backward: its own chunk code below
-      float s1 = 0.f, s2 = 0.f;
+      float s1 = 0.f, s2 = 0.f, amax = 0.f;
       // dS epilogue: the E chunk of a thread's row (128 contiguous bytes) is fetched ONE CHUNK AHEAD -- the first one before the
       // accumulator is even complete -- so its L2 / HBM latency hides under the TMEM load, the arithmetic and the store of the
       // previous chunk (profiles/r2i: with the load inside the chunk this GEMM took 824 us against 525 us for its exp sibling)
@@ -671,6 +672,10 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         } else {
 #pragma unroll
           for (int e = 0; e < 32; e++) v[e] = fmaf(alpha, v[e], bias);
+          if (p.absmax2 && second) {      // rows / columns beyond the tensor come from zero-filled operands: they contribute 0
+#pragma unroll
+            for (int e = 0; e < 32; e++) amax = fmaxf(amax, fabsf(v[e]));
+          }
         }
         if (p.sum && row_ok) {
           if (nb + 32 <= p.N_valid) {
@@ -736,6 +741,10 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
       }
       if (e_tma) echunk += h16 ? BN / 64 : BN / 32;
+      if (p.absmax2 && second) {
+        amax = warp_max(amax);
+        if (lane == 0) atomicMax(p.absmax2 + z, __float_as_uint(amax));
+      }
       tc_fence_before();
       __syncwarp();
       if (threadIdx.x == 0) GTRACE(tl, 5);
@@ -872,6 +881,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
                       (e.m_split == 0 || (e.m_split % BM == 0 && e.out2 && al16(e.out2) && e.ldo2 % 4 == 0 && e.so_b2 % 4 == 0)) &&
                       (!e.cc || (al16(e.cc) && e.ldcc % oal == 0)) && !(e.so_b == 0 && batch > 1 && !e.atomic) && !g_force_v1;
   DCNET_CHECK_ARG(out_ok || (!e.out_f16 && !e.alpha_z && e.exp_shift == 0.f), "umma_gemm: fp16 output / alpha_z / exp_shift need the persistent kernel");
+  DCNET_CHECK_ARG(!e.absmax2 || (out_ok && e.m_split > 0 && !e.cc && !e.epi_exp && !e.atomic), "umma_gemm: absmax2 belongs to the plain two-output epilogue of the persistent kernel");
   // cluster size of the persistent kernel: CTAs with consecutive M tiles share (multicast) the B tile
   const int tiles_m = ceil_div(M, BM);
   int cs = (!out_ok || g_cluster_max < 2 || tiles_m < 2) ? 1 : ((g_cluster_max >= 4 && tiles_m % 4 == 0) ? 4 : 2);
@@ -918,6 +928,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     q.epi_exp = e.epi_exp; q.u2 = e.u2; q.cc_sb = e.cc_sb; q.sum_ldz = e.sum_ldz;
     q.tap_kper = e.tap_kper; q.tap_w = e.tap_w; q.tap_flip = e.tap_flip; q.tap_n = e.tap_n;
     q.f16 = A.f16 ? 1 : 0; q.out_f16 = e.out_f16; q.exp_shift = e.exp_shift; q.alpha_z = e.alpha_z;
+    q.absmax2 = e.absmax2;
     int want_chunks = e.k_chunks;
     if (auto_split) {
       const long long tiles = (long long)q.ntiles;

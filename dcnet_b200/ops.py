@@ -535,7 +535,12 @@ class _ConvBNAct(torch.autograd.Function):
         dx1 = torch.empty_like(x1) if ctx.needs_input_grad[0] else None
         dx2 = torch.empty_like(x2) if (x2 is not None and ctx.needs_input_grad[1]) else None
         if dx1 is not None or dx2 is not None:
-            _lib.call("dcnet_conv1x1_bwd_data", _p(dz), _p(weight), ldw, _p(dx1), K1, _p(dx2), K2, B, C, N, precision, st)
+            mx = None
+            if getattr(ctx, "want_dx2_absmax", False) and dx1 is not None and dx2 is not None and precision == TENSOR_TF32:
+                # corr_conv inside _Correspondence: max |dx2[b]| out of the GEMM's epilogue (the co-attention backward's fp16 scale)
+                mx = torch.empty(B, device=dev, dtype=torch.int32)
+                ctx.dx2_absmax = mx
+            _lib.call("dcnet_conv1x1_bwd_data_absmax", _p(dz), _p(weight), ldw, _p(dx1), K1, _p(dx2), K2, B, C, N, precision, _p(mx), st)
         dW = du = dcc = None
         covered = (K1 + K2 == ldw) or (terms and (coords is not None or K1 + K2 + flang.shape[1] == ldw))
         if need_w:
@@ -790,7 +795,7 @@ class _CoAttn(torch.autograd.Function):
         return out
 
     @staticmethod
-    def backward(ctx, dout, accumulate_into=None):
+    def backward(ctx, dout, accumulate_into=None, dout_absmax=None):
         """accumulate_into (used by _Correspondence): a [F,C,N] gradient buffer that already holds the other consumers' contribution to
         d frames -- the kernels add into it (TMA reduce-add) instead of into a zero-filled tensor that autograd would add afterwards"""
         frames, qa, kb, oidx, out, lse, staged = ctx.saved_tensors
@@ -800,8 +805,8 @@ class _CoAttn(torch.autograd.Function):
         dframes = torch.zeros_like(frames) if accumulate_into is None else accumulate_into
         nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, ctx.precision)
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
-        _lib.call("dcnet_coattn_bwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout), _p(dframes),
-                  C, N, ctx.tau, ctx.precision, _p(staged), _p(ws), nbytes, _st())
+        _lib.call("dcnet_coattn_bwd_ex", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout),
+                  _p(dout_absmax) if staged is not None else None, _p(dframes), C, N, ctx.tau, ctx.precision, _p(staged), _p(ws), nbytes, _st())
         return dframes, None, None, None, None, None, None, None, None
 
 
@@ -886,12 +891,13 @@ class _Correspondence(torch.autograd.Function):
         c2 = _FakeCtx((True, True, nig[5], nig[6], nig[7], False, False, nig[8], nig[9]) + (False,) * 14)
         c2.saved_tensors = saved[ctx.n1:]
         c2.cfg = ctx.c2_cfg
+        c2.want_dx2_absmax = BWD_FP16
         g2 = _ConvBNAct.backward(c2, dy, dsim, dneg)
         dfv, dattn, dW, dgamma, dbeta, dfa, dfa_neg = g2[0], g2[1], g2[2], g2[3], g2[4], g2[7], g2[8]
         c1 = _FakeCtx()
         c1.saved_tensors = saved[:ctx.n1]
         c1.tau, c1.precision = ctx.c1_attrs
-        _CoAttn.backward(c1, dattn, accumulate_into=dfv)
+        _CoAttn.backward(c1, dattn, accumulate_into=dfv, dout_absmax=getattr(c2, "dx2_absmax", None))
         return (dfv, None, None, None, None, dW, dgamma, dbeta, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, None, None)
 
 

@@ -109,6 +109,10 @@ DCNET_API int dcnet_conv1x1_fwd(const float* x1, int K1, const float* x2, int K2
 /* dx1 = W[:,0:K1]^T dz, dx2 = W[:,K1:]^T dz (either may be NULL) */
 DCNET_API int dcnet_conv1x1_bwd_data(const float* dz, const float* W, int ldw, float* dx1, int K1, float* dx2, int K2,
                                      int B, int C, int N, int precision, void* stream);
+/* same; dx2_absmax [B] (optional, tensor-core path with both outputs) receives max |dx2[b]| as the bit pattern of a non-negative float,
+ * out of the GEMM's epilogue: corr_conv's dx2 is the co-attention's dout, whose per-problem scale dcnet_coattn_bwd_ex then needs no pass for */
+DCNET_API int dcnet_conv1x1_bwd_data_absmax(const float* dz, const float* W, int ldw, float* dx1, int K1, float* dx2, int K2,
+                                            int B, int C, int N, int precision, unsigned int* dx2_absmax, void* stream);
 /* dW[:,0:K1] = sum_b dz[b] x1[b]^T, dW[:,K1:] = sum_b dz[b] x2[b]^T  (overwrites those columns of dW [C,ldw]);
  * du [B,C] = sum_n dz (or NULL); dcc [C,N] = sum_b dz (or NULL)                                           */
 DCNET_API int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1, const float* x2, int K2,
@@ -257,6 +261,12 @@ DCNET_API int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const 
                                const float* out, int n_out, const float* lse, const float* dout, float* dframes,
                                int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,
                                void* stream);
+/* same with dout_absmax [n_out] (optional): max |dout[row]| per output row as float bit patterns (dcnet_conv1x1_bwd_data_absmax); the
+ * fp16 pipeline then skips its own pass over dout */
+DCNET_API int dcnet_coattn_bwd_ex(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                  const float* out, int n_out, const float* lse, const float* dout, const unsigned int* dout_absmax,
+                                  float* dframes, int C, int N, float tau, int precision, const void* staged, void* workspace,
+                                  size_t workspace_bytes, void* stream);
 /* The backward keeps its N x N scratch (P, dP -> dS) resident in L2 by working through the problems in chunks whose scratch
  * fits `bytes` (default 64 MiB of the 126 MB L2; <= 0 = unlimited = one chunk); dcnet_coattn_workspace_bytes follows it. */
 DCNET_API int dcnet_coattn_bwd_l2_budget(long long bytes);
