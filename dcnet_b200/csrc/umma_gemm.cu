@@ -40,7 +40,10 @@ static bool g_force_v1 = false;   // tests: run the one-tile-per-CTA kernel with
 static int g_cluster_max = 1;
 // 128x256 tf32 tiles as cta_group::2 pairs (256x256 per cluster); dcnet_gemm_select(6) or DCNET_GEMM_PAIR=0 turns it off
 static int g_pair_mode = []() { const char* v = getenv("DCNET_GEMM_PAIR"); return (v && v[0] == '0') ? 0 : 1; }();
+// fp16 exp / dS epilogues with 8 epilogue warps (two per SM sub-partition); dcnet_gemm_select(7) keeps 4
+static int g_epi_warps8 = 1;
 extern "C" int dcnet_gemm_select(int variant) {
+  g_epi_warps8 = (variant == 7) ? 0 : 1;
   g_force_v1 = (variant == 1);
   g_cluster_max = (variant == 4) ? 4 : ((variant == 3) ? 2 : 1);
   g_gemm_tma_store = (variant == 5) ? 0 : 1;
@@ -281,8 +284,11 @@ struct Gemm2P {
 // (256 + 256) x K operand elements from L2 instead of 2 x (128 + 256) x K -- the tf32 GEMMs here are bound by that traffic
 // (fp32 operands: 4 bytes per element at half the bf16 MMA rate).  The leader CTA (rank 0) issues every MMA.
 // ESLOT (pair mode, dS epilogue only): per-warp landing slots for the E tile (one pipeline stage less)
-template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO, bool ESLOT = false>
-__global__ void __launch_bounds__(192, 1)
+// EW: epilogue warps, 4 or 8.  tcgen05.ld ties a warp to the TMEM lane quarter (warp % 4), so with 8 the warps w and w + 4 share 32 rows
+// and split the columns (chunk pairs alternate between them): two epilogue warps per SM sub-partition hide each other's TMEM / barrier /
+// store latencies.  Used by the fp16 exp / dS epilogues, which are bound by the epilogue (K = 512: 4 k MMA cycles per tile).
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO, bool ESLOT = false, int EW = 4>
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
 umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapB3,
                   const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2, const Gemm2P p) {
@@ -293,24 +299,25 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   constexpr int B_BYTES = (TWO ? BN / 2 : BN) * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int SLOT_BYTES = 32 * 128;           // 32 rows x 32 fp32
-  constexpr int NSLOT = GEMM2_NSLOT;             // staging slots per epilogue warp (TMA stores in flight per warp)
+  constexpr int NSLOT = EW == 8 ? 1 : GEMM2_NSLOT;   // staging slots per epilogue warp (TMA stores in flight per warp)
+  static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_out = smem + STAGES * STAGE_BYTES;                 // [4 warps][NSLOT][SLOT_BYTES]
   // pair mode only: [4 warps][2][SLOT_BYTES] landing slots for the E tile of the dS epilogue (TMA, same 128-byte-swizzled 32x32 boxes)
   static_assert(!ESLOT || TWO, "E landing slots exist in pair mode only");
-  constexpr int E_BYTES = ESLOT ? 4 * 2 * SLOT_BYTES : 0;
-  uint8_t* stage_e = stage_out + 4 * NSLOT * SLOT_BYTES;
+  constexpr int E_BYTES = ESLOT ? EW * 2 * SLOT_BYTES : 0;
+  uint8_t* stage_e = stage_out + EW * NSLOT * SLOT_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(stage_e + E_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
   uint64_t* e_full = acc_empty + 2;        // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_full + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_full + 2 * EW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == EW && lane == 0) {
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
     prefetch_tmap(&mapB2);
@@ -319,12 +326,12 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // pair: a slot is released by ONE commit (multicast to both CTAs); the leader's accumulator stage is free once the epilogue
     // warps of BOTH CTAs have drained their halves
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], TWO ? 1 : CS); }
-    for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TWO ? 8 : 4); }
-    for (int s = 0; s < 8; s++) mbar_init(&e_full[s], 1);
+    for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TWO ? 2 * EW : EW); }
+    for (int s = 0; s < 2 * EW; s++) mbar_init(&e_full[s], 1);
     fence_barrier_init();
   }
   if constexpr (TWO) cluster_sync_all();             // both CTAs are resident before the pair-wide TMEM allocation
-  if (warp == 5) {
+  if (warp == EW + 1) {
     if constexpr (TWO) { tmem_alloc2(tmem_slot, 2 * BN); tmem_relinquish2(); }
     else { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
   }
@@ -341,7 +348,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int cid = blockIdx.x / CS, ncl = gridDim.x / CS;
   constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1);
 
-  if (warp == 4) {
+  if (warp == EW) {
     if (elect_one()) {
       uint32_t itg = 0;
       for (int t = cid; t < ngroups; t += ncl) {
@@ -429,7 +436,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EW + 1) {
     if ((!TWO || crank == 0) && elect_one()) {
       const uint32_t idesc = instr_desc((EB == 2 && p.f16) ? (uint32_t)FMT_F16 : G::FMT, TWO ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t itg = 0, tl = 0;
@@ -475,13 +482,15 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   } else {
     // ---------------- epilogue warps 0..3: TMEM lanes 32w.. <-> output rows m0 + 32w..
     uint8_t* slots = stage_out + warp * NSLOT * SLOT_BYTES;
+    const int q4 = warp & 3;            // TMEM lane quarter = 32-row block of the tile
+    const int chalf = warp >> 2;        // EW == 8: which chunk pairs of a tile are this warp's (pair index parity)
     uint32_t tl = 0, chunk = 0, echunk = 0;
     for (int t = cid; t < ngroups; t += ncl, tl++) {
       const int kc = t % p.k_chunks, tt = t / p.k_chunks;
       const int z = tt / per_z, r = tt - z * per_z;
       const int m0 = ((r / p.tiles_n) * CS + crank) * BM, n0 = (r % p.tiles_n) * BN;
       const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
-      const int row0 = m0 + warp * 32;
+      const int row0 = m0 + q4 * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M_valid;
       const int zc = p.out_batched ? (p.idxC ? p.idxC[z] : z) : 0;
@@ -518,11 +527,11 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       };
       // fp32 E: one 32 x 32 block per chunk; fp16 E: one 32 x 64 block per PAIR of chunks (same 4 KiB slot, same swizzle)
       auto tma_e = [&](int c) {          // lane 0: E block of chunk c -> slot (echunk + c) & 1
-        const uint32_t k = echunk + (uint32_t)(h16 ? c >> 1 : c);
+        const uint32_t k = echunk + (uint32_t)(h16 ? (EW == 8 ? c >> 2 : c >> 1) : c);
         mbar_expect_tx(&ebar[k & 1u], SLOT_BYTES);
         tma_load_3d(eslots + (k & 1u) * SLOT_BYTES, &mapO2, &ebar[k & 1u], n0 + c * 32, row0, z);
       };
-      if (e_tma) { if (lane == 0) tma_e(0); }
+      if (e_tma) { if (lane == 0) tma_e(EW == 8 ? 2 * chalf : 0); }
       else if (p.epi_exp == 2 && !h16) load_e(0, ecur);
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
@@ -530,12 +539,15 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++, chunk++) {
         float4 enext[8];
+        const bool mine = EW == 4 || ((c >> 1) & 1) == chalf;
         if (e_tma) {
-          if (h16) { if (lane == 0 && (c & 1) == 0 && c + 2 < BN / 32) tma_e(c + 2); }
+          constexpr int estep = EW == 8 ? 4 : 2;      // chunks to this warp's next pair
+          if (h16) { if (lane == 0 && (c & 1) == 0 && mine && c + estep < BN / 32) tma_e(c + estep); }
           else if (lane == 0 && c + 1 < BN / 32) tma_e(c + 1);
         } else if (p.epi_exp == 2 && !h16 && c + 1 < BN / 32) load_e(c + 1, enext);
+        if (!mine) continue;
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + (uint32_t)(c * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + as * BN + (uint32_t)(c * 32), v);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
         if (h16) {
@@ -573,7 +585,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             // dS = tau (dP - delta) E / r : per-row delta (bias) and tau / r (rowmul); E tile: this chunk's half of the 128-byte row
             uint32_t eh[16];
             if (e_tma) {
-              const uint32_t k = echunk + (uint32_t)(c >> 1);
+              const uint32_t k = echunk + (uint32_t)(EW == 8 ? c >> 2 : c >> 1);
               mbar_wait(&ebar[k & 1u], (k >> 1) & 1u);
               const uint8_t* er = eslots + (k & 1u) * SLOT_BYTES + lane * 128;
 #pragma unroll
@@ -740,7 +752,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           tma_store_commit();
         }
       }
-      if (e_tma) echunk += h16 ? BN / 64 : BN / 32;
+      if (e_tma) echunk += h16 ? BN / 64 / (EW / 4) : BN / 32;
       if (p.absmax2 && second) {
         amax = warp_max(amax);
         if (lane == 0) atomicMax(p.absmax2 + z, __float_as_uint(amax));
@@ -762,23 +774,24 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if constexpr (CS > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / arrive on its barriers
-  if (warp == 5) {
+  if (warp == EW + 1) {
     if constexpr (TWO) tmem_dealloc2(tmem_base, 2 * BN);
     else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
-template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO = false, bool ESLOT = false>
+template <bool A_MN, bool B_MN, int BN, int STAGES, int EB, int CS, bool TWO = false, bool ESLOT = false, int EW = 4>
 int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mb3, const CUtensorMap& mo,
                  const CUtensorMap& mo2, const Gemm2P& p, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_BYTES + (TWO ? BN / 2 : BN) * 128) + 4 * GEMM2_NSLOT * 32 * 128 + (ESLOT ? 4 * 2 * 32 * 128 : 0) + 1024 + 256;
+  constexpr int smem = STAGES * (A_BYTES + (TWO ? BN / 2 : BN) * 128) + EW * (EW == 8 ? 1 : GEMM2_NSLOT) * 32 * 128 +
+                       (ESLOT ? EW * 2 * 32 * 128 : 0) + 1024 + 256;
   static_assert(smem <= 232448, "umma_gemm2: shared memory budget");
-  auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB, CS, TWO, ESLOT>;
+  auto kern = umma_gemm2_kernel<A_MN, B_MN, BN, STAGES, EB, CS, TWO, ESLOT, EW>;
   DCNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "umma_gemm2.attr");
   const int mgroups = (p.tiles_m + CS - 1) / CS;
   const int ngroups = mgroups * (p.ntiles / p.tiles_m) * p.k_chunks;
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3((EW + 2) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -808,6 +821,13 @@ int launch_cfg2c(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap
 template <bool A_MN, bool B_MN, int BN, int STAGES, int EB>
 int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mb3, const CUtensorMap& mo,
                 const CUtensorMap& mo2, const Gemm2P& p, int cs, cudaStream_t st) {
+  if constexpr (BN == 256 && EB == 2 && A_MN && B_MN) {
+    // fp16 exp / dS epilogues of the co-attention backward (S = Fa^T Fb, dP = dO^T Fb: both operands MN-major): 8 epilogue warps
+    if (cs == -2 && p.out_f16 && g_epi_warps8) {
+      if (p.epi_exp == 2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR - 2, EB, 2, true, true, 8>(ma, mb, mb2, mb3, mo, mo2, p, st);
+      return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR, EB, 2, true, false, 8>(ma, mb, mb2, mb3, mo, mo2, p, st);
+    }
+  }
   if constexpr (BN == 256) {
     if constexpr (A_MN && B_MN) {      // the dS epilogue belongs to dP = dO^T Fb: both operands MN-major
       if (cs == -2 && p.epi_exp == 2) return launch_cfg2c<A_MN, B_MN, BN, GEMM2_STAGES_PAIR - 1, EB, 2, true, true>(ma, mb, mb2, mb3, mo, mo2, p, st);

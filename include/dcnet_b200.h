@@ -75,7 +75,8 @@ DCNET_API int dcnet_cast_f16(const float* x, void* y, long long n, void* stream)
  * stages, epilogue through swizzled smem slots and TMA store / reduce-add; 5 = the same with coalesced 16-byte st.global /
  * red.global.add.v4.f32 from the slots; 3 / 4 = with thread-block clusters of 2 / 4 CTAs (consecutive M tiles) that multicast
  * the B tile; 1 = one tile per CTA with per-thread row stores (outputs whose rows are not 16-byte addressable).  All variants give
- * identical bits for plain stores.  Process-wide switch, not thread-safe: a test / bring-up knob.                              */
+ * identical bits for plain stores.  6 = no cta_group::2 pairs; 7 = 4 instead of 8 epilogue warps in the fp16 exp / dS epilogues of the
+ * co-attention backward.  Process-wide switch, not thread-safe: a test / bring-up knob.                                          */
 DCNET_API int dcnet_gemm_select(int variant);
 /* profiling: while buf != NULL every persistent GEMM launch writes clock64 stamps to buf [148 CTAs][8 tiles][8]: 0 tile start (MMA
  * thread), 1 accumulator stage free, 2 first operands landed, 3 last MMA issued, 4 accumulator complete (epilogue), 5 epilogue done */

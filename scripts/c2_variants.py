@@ -16,16 +16,9 @@ def run(name):
 
 
 run("default")
-HotPath.finest_priority = -1
-HotPath.aux_priority = (-2, -2)
-run("finest chain on a priority -1 stream, aux -2, coarse scales 0")
-HotPath.finest_priority = -2
-HotPath.aux_priority = (-3, -3)
-HotPath.side_priority = (-1, 0)
-run("finest -2, aux -3, middle scale -1, coarsest 0")
-HotPath.finest_priority = None
-HotPath.aux_priority = (-1, -1)
-HotPath.side_priority = (0, 0)
+_lib.lib().dcnet_gemm_select(7)
+run("4 epilogue warps in the fp16 exp / dS epilogues")
+_lib.lib().dcnet_gemm_select(0)
 ops.BWD_FP16 = False
 run("co-attention backward on tf32 operands (round-2a)")
 ops.BWD_FP16 = True
