@@ -828,3 +828,81 @@ def test_conv1x1_bias_head_output_layer():
     assert rel(out, ref) < 1e-5
     for a, b_ in zip(c, r):
         assert rel(a.grad, b_.grad) < 2e-5, rel(a.grad, b_.grad)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# operand rounding (DCNET_RN_TF32) and the per-problem gradient scale of the fp16 co-attention backward
+# ------------------------------------------------------------------------------------------------------------------
+def _is_tf32(t):
+    return bool(((t.contiguous().view(torch.int32) & 0x1FFF) == 0).all())
+
+
+def test_producers_round_to_nearest_tf32():
+    """DCNET_RN_TF32: what a producer hands to a tf32 contraction has its 13 low mantissa bits clear (the MMA's truncation is then
+    exact) and lies within half a tf32 ulp (2^-11 relative) of the unrounded result: dcnet_round_tf32, bn_act_fwd (round_out), the
+    co-attention forward (round_out), and the gradient dz that bn_act_bwd_apply hands to the conv backward (seen through dx)."""
+    g = gen(400)
+    x = torch.randn(3, 777, generator=g).to(DEV)
+    r = ops.round_tf32(x)
+    assert _is_tf32(r) and float(((r - x).abs() / x.abs()).max()) <= 2.0 ** -11 + 1e-9
+    # ties away from zero (cvt.rna): 1 + 2^-11 -> 1 + 2^-10
+    t = torch.tensor([1.0 + 2.0 ** -11, -(1.0 + 2.0 ** -11), 1.0 + 2.0 ** -12], device=DEV)
+    assert ops.round_tf32(t).tolist() == [1.0 + 2.0 ** -10, -(1.0 + 2.0 ** -10), 1.0]
+    B, K, C, N = 2, 256, 512, 256
+    x1 = torch.randn(B, K, N, generator=g).to(DEV)
+    W = (torch.randn(C, K, generator=g) / 16).to(DEV)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(DEV), (torch.randn(C, generator=g) * 0.1).to(DEV)
+    outs = {}
+    for flag in (False, True):
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        outs[flag] = ops.conv_bn_act(x1, W, gamma, beta, rm, rv, True, l2norm=True, round_out=flag)
+    assert _is_tf32(outs[True]) and not _is_tf32(outs[False])
+    assert rel(outs[True], outs[False]) < 2.0 ** -11
+    fr = torch.nn.functional.normalize(torch.randn(4, 512, 256, generator=g).abs(), dim=1).to(DEV)
+    qa = torch.arange(4, device=DEV, dtype=torch.int32)
+    from dcnet_b200.ops import _CoAttn
+    a = _CoAttn.apply(fr, qa, qa ^ 1, qa, 4, 10.0, 2, True)
+    b = _CoAttn.apply(fr, qa, qa ^ 1, qa, 4, 10.0, 2, False)
+    assert _is_tf32(a) and not _is_tf32(b) and rel(a, b) < 2.0 ** -11
+
+
+def test_conv_bwd_data_absmax_from_the_gemm_epilogue():
+    """dcnet_conv1x1_bwd_data_absmax: max |dx2[b]| per image out of the data-gradient GEMM's epilogue == the maximum of the tensor it wrote"""
+    from dcnet_b200 import _lib
+    g = gen(401)
+    B, K1, K2, C, N = 5, 512, 512, 512, 676
+    dz = (torch.randn(B, C, N, generator=g) * torch.logspace(-6, 2, B)[:, None, None]).to(DEV)       # images on very different scales
+    W = (torch.randn(C, K1 + K2, generator=g) / 32).to(DEV)
+    dx1, dx2 = torch.empty(B, K1, N, device=DEV), torch.empty(B, K2, N, device=DEV)
+    mx = torch.full((B,), -1, device=DEV, dtype=torch.int32)
+    _lib.call("dcnet_conv1x1_bwd_data_absmax", dz.data_ptr(), W.data_ptr(), K1 + K2, dx1.data_ptr(), K1, dx2.data_ptr(), K2, B, C, N, 1,
+              mx.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(mx.view(torch.float32), dx2.abs().amax(dim=(1, 2)))
+    assert rel(dx2, torch.einsum('ck,bcn->bkn', W[:, K1:].double().cpu(), dz.double().cpu())) < 1e-3
+
+
+@pytest.mark.parametrize("scale", [1e-7, 1e-3, 1.0, 3e4])
+def test_coattention_backward_fp16_pipeline_is_scale_free(scale):
+    """the fp16 pipeline multiplies everything that follows the incoming gradient by a per-problem power of two: gradients 1e-7 or 3e4
+    in magnitude (far outside fp16's range unscaled), and problems of very different magnitude in one batch, give the same relative
+    error as gradients of order one; equal to the tf32 pipeline's numbers to rounding."""
+    g = gen(402)
+    P, C, N = 2, 512, 256
+    fr = torch.nn.functional.normalize(torch.randn(2 * P, C, N, generator=g).abs(), dim=1)
+    go = torch.randn(2 * P, C, N, generator=g) * scale
+    go[1] *= 1e-3                                                # one problem a thousand times smaller than its neighbours
+    ref_in = fr.double().requires_grad_(True)
+    o1, o2 = O.coattention(ref_in.view(P, 2, C, N)[:, 0], ref_in.view(P, 2, C, N)[:, 1], 10.0)
+    O.interleave_pairs(o1, o2).backward(go.double())
+    qa = torch.arange(2 * P, device=DEV, dtype=torch.int32)
+    errs = {}
+    for fp16 in (True, False):
+        ops.BWD_FP16 = fp16
+        try:
+            x = fr.to(DEV).requires_grad_(True)
+            ops.coattention(x, qa, qa ^ 1, tau=10.0, precision=2).backward(go.to(DEV))
+        finally:
+            ops.BWD_FP16 = True
+        errs[fp16] = max(rel(x.grad[i], ref_in.grad[i]) for i in range(2 * P))      # per frame: the small problem counts on its own
+    print("coattn bwd at gradient scale %.0e: worst per-frame rel err fp16 %.2e, tf32 %.2e" % (scale, errs[True], errs[False]))
+    assert errs[True] < 1e-3 and errs[True] < 1.5 * errs[False] + 1e-4, errs
