@@ -12,26 +12,41 @@
 //   data gradient  dx = sum_t  Wq[t]^T . shift_-dy(dz_-dx)           K = 9*Cout   same Wq read MN-major, B side uses tap 8 - t
 //   weight grad.   dWp[co][t][ci] = sum_{b,p} dz[b,co,p] x_dx[b,ci,p+dy*w]        N = 9*Cin, tap = output column block, K = positions
 // The start of a TMA box must be 16-byte aligned, so the row shift needs w % 4 == 0 (8, 16, 32 at 256x256 -- the only size the reference
-// itself runs, model/DCNet_model.py:584 --, 52 at 416x416; the 13- and 26-wide maps of 416x416 keep the library convolution).
+// itself runs, model/DCNet_model.py:584 --, 52 at 416x416).  Other widths (13, 26 at 416x416) run at a padded width wp = 16, 28: the
+// shifted copies are written at pitch wp with zero pad columns (dcnet_conv3x3_shift_padded), the contractions see an h x wp image whose
+// pad columns act as the border, and the pad columns of the result are dropped (dcnet_conv3x3_unpad).
 // Wq is the weight permuted to [tap][Cout][Cin] (and rounded to tf32) once per step; dWp is permuted back to [Cout][Cin][3][3].
 // BatchNorm statistics come out of the forward's epilogue like in the 1x1 layers.
 #include "common.cuh"
 
 namespace {
 
-// rows = (b, c, y); one thread per element of a row chunk
+// rows = (b, c, y); one thread per element of an OUTPUT row of pitch wp >= w (the pad columns w .. wp-1 are written as zeros)
 __global__ void __launch_bounds__(256) conv3x3_shift_kernel(const float* __restrict__ x, float* __restrict__ xm, float* __restrict__ xp,
-                                                            float* __restrict__ x0, long long total, int w, int rn) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+                                                            float* __restrict__ x0, long long total, int w, int wp, int rn) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;       // index into the padded outputs
   if (i >= total) return;
-  const int col = (int)(i % w);
-  float v = x[i];
-  float l = col > 0 ? x[i - 1] : 0.f;          // x(dx=-1)[p] = x[p-1]
-  float r = col < w - 1 ? x[i + 1] : 0.f;      // x(dx=+1)[p] = x[p+1]
-  if (rn) { v = tf32_rn(v); l = tf32_rn(l); r = tf32_rn(r); }
+  const long long row = i / wp;
+  const int col = (int)(i - row * wp);
+  float v = 0.f, l = 0.f, r = 0.f;
+  if (col < w) {
+    const float* xr = x + row * w;
+    v = xr[col];
+    l = col > 0 ? xr[col - 1] : 0.f;          // x(dx=-1)[p] = x[p-1]
+    r = col < w - 1 ? xr[col + 1] : 0.f;      // x(dx=+1)[p] = x[p+1]
+    if (rn) { v = tf32_rn(v); l = tf32_rn(l); r = tf32_rn(r); }
+  }
   xm[i] = l;
   xp[i] = r;
   if (x0) x0[i] = v;
+}
+
+// [rows][wp] -> [rows][w]
+__global__ void __launch_bounds__(256) conv3x3_unpad_kernel(const float* __restrict__ zp, float* __restrict__ z, long long total, int w, int wp) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;       // index into the unpadded output
+  if (i >= total) return;
+  const long long row = i / w;
+  z[i] = zp[row * wp + (i - row * w)];
 }
 
 // W [Cout][Cin][9] -> Wq [9][Cout][Cin]
@@ -70,10 +85,26 @@ extern "C" int dcnet_conv3x3_supported(int Cin, int Cout, int h, int w) {
 }
 
 extern "C" int dcnet_conv3x3_shift(const float* x, float* x_m, float* x_p, float* x_0, long long rows, int w, int flags, void* stream) {
-  DCNET_CHECK_ARG(x && x_m && x_p && rows > 0 && w >= 2, "conv3x3_shift: bad arguments");
-  const long long total = rows * w;
-  conv3x3_shift_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(x, x_m, x_p, x_0, total, w, (flags & DCNET_RN_TF32) ? 1 : 0);
+  return dcnet_conv3x3_shift_padded(x, x_m, x_p, x_0, rows, w, w, flags, stream);
+}
+
+// the same with the outputs at row pitch wp >= w (pad columns zero): maps whose width is not a multiple of 4 run the implicit GEMM at a
+// padded width -- every row shift is then 16-byte aligned for TMA, the zero pad columns play the part of the image border, and the
+// results at the pad columns are dropped (dcnet_conv3x3_unpad).  x_0 is required when wp != w.
+extern "C" int dcnet_conv3x3_shift_padded(const float* x, float* x_m, float* x_p, float* x_0, long long rows, int w, int wp, int flags,
+                                          void* stream) {
+  DCNET_CHECK_ARG(x && x_m && x_p && rows > 0 && w >= 2 && wp >= w && (wp == w || x_0), "conv3x3_shift: bad arguments");
+  const long long total = rows * wp;
+  conv3x3_shift_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(x, x_m, x_p, x_0, total, w, wp, (flags & DCNET_RN_TF32) ? 1 : 0);
   DCNET_LAUNCH_OK("conv3x3_shift");
+  return 0;
+}
+
+extern "C" int dcnet_conv3x3_unpad(const float* zp, float* z, long long rows, int w, int wp, void* stream) {
+  DCNET_CHECK_ARG(zp && z && rows > 0 && w >= 1 && wp >= w, "conv3x3_unpad: bad arguments");
+  const long long total = rows * w;
+  conv3x3_unpad_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(zp, z, total, w, wp);
+  DCNET_LAUNCH_OK("conv3x3_unpad");
   return 0;
 }
 

@@ -590,7 +590,8 @@ def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2
 class _Conv3x3BNAct(torch.autograd.Function):
     """ConvBatchNormReLU(C, C, 3, 1, 1) of the grounding head (model/DCNet_model.py:316-337) on this library's
     kernels: implicit-GEMM 3x3 convolution on tcgen05 (csrc/conv3x3.cu: three column-shifted copies of the map, the nine taps inside the
-    K loop, rows off the image zero-filled by TMA), BatchNorm statistics from its epilogue, the BN / activation kernels of the 1x1 layers."""
+    K loop, rows off the image zero-filled by TMA), BatchNorm statistics from its epilogue, the BN / activation kernels of the 1x1 layers.
+    Widths that are not a multiple of 4 (13, 26 at 416x416) run at a padded width (zero pad columns = the image border)."""
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, running_mean, running_var, training, momentum, eps, slope, nbt, h, w, round_out):
@@ -600,38 +601,48 @@ class _Conv3x3BNAct(torch.autograd.Function):
         Cout = weight.shape[0]
         if N != h * w or tuple(weight.shape) != (Cout, Cin, 3, 3):
             raise ValueError("conv3x3_bn_act: x %s, weight %s, h*w = %d" % (tuple(x.shape), tuple(weight.shape), h * w))
-        if not _lib.lib().dcnet_conv3x3_supported(Cin, Cout, h, w):
+        wp = (w + 3) // 4 * 4
+        if not _lib.lib().dcnet_conv3x3_supported(Cin, Cout, h, wp):
             raise RuntimeError("conv3x3_bn_act: shape (Cin=%d, Cout=%d, %dx%d) is not supported by the tcgen05 kernel" % (Cin, Cout, h, w))
         dev, st = x.device, _st()
         rn = _RN_FLAG if RN_TF32 else 0
         wq = torch.empty(9, Cout, Cin, device=dev, dtype=F32)
         _lib.call("dcnet_conv3x3_pack_weight", _p(weight), _p(wq), Cout, Cin, rn, st)
-        xm, xp, x0 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
-        _lib.call("dcnet_conv3x3_shift", _p(x), _p(xm), _p(xp), _p(x0), B * Cin * h, w, rn, st)
-        z = torch.empty(B, Cout, N, device=dev, dtype=F32)
+        Np = h * wp
+        xm, xp, x0 = (torch.empty(B, Cin, Np, device=dev, dtype=F32) for _ in range(3))
+        _lib.call("dcnet_conv3x3_shift_padded", _p(x), _p(xm), _p(xp), _p(x0), B * Cin * h, w, wp, rn, st)
         mean = torch.empty(Cout, device=dev, dtype=F32)
         invstd = torch.empty(Cout, device=dev, dtype=F32)
-        if training:
-            sums = torch.empty(2 * Cout, device=dev, dtype=F32)
+        if wp == w:
+            z = torch.empty(B, Cout, N, device=dev, dtype=F32)
+            sums = torch.empty(2 * Cout, device=dev, dtype=F32) if training else None
             _lib.call("dcnet_conv3x3_fwd", _p(xm), _p(x0), _p(xp), _p(wq), _p(z), B, Cin, Cout, h, w, _p(sums), st)
-            _lib.call("dcnet_bn_finalize", _p(sums), B * N, Cout, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), _p(nbt), st)
+            if training:
+                _lib.call("dcnet_bn_finalize", _p(sums), B * N, Cout, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), _p(nbt), st)
         else:
-            _lib.call("dcnet_conv3x3_fwd", _p(xm), _p(x0), _p(xp), _p(wq), _p(z), B, Cin, Cout, h, w, None, st)
+            zp = torch.empty(B, Cout, Np, device=dev, dtype=F32)
+            _lib.call("dcnet_conv3x3_fwd", _p(xm), _p(x0), _p(xp), _p(wq), _p(zp), B, Cin, Cout, h, wp, None, st)
+            z = torch.empty(B, Cout, N, device=dev, dtype=F32)
+            _lib.call("dcnet_conv3x3_unpad", _p(zp), _p(z), B * Cout * h, w, wp, st)
+            if training:
+                _lib.call("dcnet_bn_stats", _p(z), B, Cout, N, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var), _p(nbt), st)
+        if not training:
             _lib.call("dcnet_bn_eval_stats", _p(running_mean), _p(running_var), Cout, eps, _p(mean), _p(invstd), st)
         y = torch.empty_like(z)
         _lib.call("dcnet_bn_act_fwd", _p(z), _p(mean), _p(invstd), _p(gamma), _p(beta), slope, (_RN_FLAG if (RN_TF32 and round_out) else 0), _p(y),
                   None, None, None, None, B, Cout, N, st)
         ctx.save_for_backward(xm, x0, xp, wq, gamma, beta, z, mean, invstd)
-        ctx.cfg = (training, slope, h, w)
+        ctx.cfg = (training, slope, h, w, wp)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xm, x0, xp, wq, gamma, beta, z, mean, invstd = ctx.saved_tensors
-        training, slope, h, w = ctx.cfg
-        B, Cin, N = x0.shape
-        Cout = wq.shape[1]
-        dev, st = x0.device, _st()
+        training, slope, h, w, wp = ctx.cfg
+        B, Cout, N = z.shape
+        Cin = wq.shape[2]
+        Np = h * wp
+        dev, st = z.device, _st()
         dy = _c(dy, name="dy")
         rn = _RN_FLAG if RN_TF32 else 0
         dv = torch.empty_like(z)
@@ -642,20 +653,31 @@ class _Conv3x3BNAct(torch.autograd.Function):
                   B, Cout, N, st)
         dz = dv
         dx = dW = None
-        if ctx.needs_input_grad[0]:
-            dzm, dzp = torch.empty_like(dz), torch.empty_like(dz)
-            _lib.call("dcnet_conv3x3_shift", _p(dz), _p(dzm), _p(dzp), None, B * Cout * h, w, 0, st)     # dz is rounded already
-            dx = torch.empty_like(x0)
-            _lib.call("dcnet_conv3x3_bwd_data", _p(dzm), _p(dz), _p(dzp), _p(wq), _p(dx), B, Cin, Cout, h, w, st)
-        if ctx.needs_input_grad[1]:
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dz0 = dz
+        if need_x or wp != w:
+            dzm, dzp = (torch.empty(B, Cout, Np, device=dev, dtype=F32) for _ in range(2))
+            dz0 = dz if wp == w else torch.empty(B, Cout, Np, device=dev, dtype=F32)
+            _lib.call("dcnet_conv3x3_shift_padded", _p(dz), _p(dzm), _p(dzp), _p(dz0) if wp != w else None, B * Cout * h, w, wp, 0, st)   # dz is rounded already
+        if need_x:
+            if wp == w:
+                dx = torch.empty(B, Cin, N, device=dev, dtype=F32)
+                _lib.call("dcnet_conv3x3_bwd_data", _p(dzm), _p(dz0), _p(dzp), _p(wq), _p(dx), B, Cin, Cout, h, w, st)
+            else:
+                dxp = torch.empty(B, Cin, Np, device=dev, dtype=F32)
+                _lib.call("dcnet_conv3x3_bwd_data", _p(dzm), _p(dz0), _p(dzp), _p(wq), _p(dxp), B, Cin, Cout, h, wp, st)
+                dx = torch.empty(B, Cin, N, device=dev, dtype=F32)
+                _lib.call("dcnet_conv3x3_unpad", _p(dxp), _p(dx), B * Cin * h, w, wp, st)
+        if need_w:
             dWp = torch.empty(Cout, 9, Cin, device=dev, dtype=F32)
             dW = torch.empty(Cout, Cin, 3, 3, device=dev, dtype=F32)
-            _lib.call("dcnet_conv3x3_bwd_weight", _p(dz), _p(xm), _p(x0), _p(xp), _p(dWp), _p(dW), B, Cin, Cout, h, w, st)
+            _lib.call("dcnet_conv3x3_bwd_weight", _p(dz0), _p(xm), _p(x0), _p(xp), _p(dWp), _p(dW), B, Cin, Cout, h, wp, st)
         return dx, dW, sums[1], sums[0], None, None, None, None, None, None, None, None, None, None
 
 
 def conv3x3_supported(Cin, Cout, h, w):
-    return bool(_lib.lib().dcnet_conv3x3_supported(int(Cin), int(Cout), int(h), int(w)))
+    """shapes ops.conv3x3_bn_act runs (any width: widths that are not a multiple of 4 run at the next multiple)"""
+    return bool(_lib.lib().dcnet_conv3x3_supported(int(Cin), int(Cout), int(h), (int(w) + 3) // 4 * 4))
 
 
 def conv3x3_bn_act(x, weight, gamma, beta, running_mean, running_var, training, h, w, momentum=0.999, eps=1e-5, slope=0.0,

@@ -127,10 +127,15 @@ DCNET_API int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1,
  *   dcnet_conv3x3_fwd:         z [B,Cout,N] = conv3x3(x) (stride 1, zero padding 1, no bias); stat_sums like dcnet_conv1x1_fwd
  *   dcnet_conv3x3_bwd_data:    dx [B,Cin,N] from the three shifted copies of dz [B,Cout,N]
  *   dcnet_conv3x3_bwd_weight:  dW [Cout,Cin,3,3] (overwritten); dWp [Cout,9,Cin] is scratch
- * Needs Cin, Cout multiples of 256 and w % 4 == 0 (a TMA box shifted by one image row must start 16-byte aligned):
- * dcnet_conv3x3_supported; other shapes stay with the caller's library convolution.                                              */
+ * Needs Cin, Cout multiples of 256 and w % 4 == 0 (a TMA box shifted by one image row must start 16-byte aligned:
+ * dcnet_conv3x3_supported).  Other widths run at a padded width wp (multiple of 4): dcnet_conv3x3_shift_padded writes the copies at
+ * row pitch wp with zero pad columns, the three contractions are called with (h, wp), dcnet_conv3x3_unpad drops the pad columns of
+ * z / dx (stat_sums = NULL there: the BatchNorm statistics come from the unpadded z).                                             */
 DCNET_API int dcnet_conv3x3_supported(int Cin, int Cout, int h, int w);
 DCNET_API int dcnet_conv3x3_shift(const float* x, float* x_m, float* x_p, float* x_0, long long rows, int w, int flags, void* stream);
+DCNET_API int dcnet_conv3x3_shift_padded(const float* x, float* x_m, float* x_p, float* x_0, long long rows, int w, int wp, int flags,
+                                         void* stream);
+DCNET_API int dcnet_conv3x3_unpad(const float* zp, float* z, long long rows, int w, int wp, void* stream);
 DCNET_API int dcnet_conv3x3_pack_weight(const float* W, float* Wq, int Cout, int Cin, int flags, void* stream);
 DCNET_API int dcnet_conv3x3_fwd(const float* x_m, const float* x_0, const float* x_p, const float* Wq, float* z,
                                 int B, int Cin, int Cout, int h, int w, float* stat_sums, void* stream);

@@ -775,7 +775,7 @@ def test_conv3x3_contractions_vs_conv2d(B, C, h, w):
     assert e_f < 5e-5 and e_dx < 5e-5 and e_dw < 5e-5 and e_f_exact < 1e-3, (e_f, e_f_exact, e_dx, e_dw)
 
 
-@pytest.mark.parametrize("B,h,w,training", [(2, 16, 16, True), (1, 52, 52, True), (3, 8, 8, False)])
+@pytest.mark.parametrize("B,h,w,training", [(2, 16, 16, True), (1, 52, 52, True), (3, 8, 8, False), (2, 26, 26, True), (3, 13, 13, True), (2, 13, 13, False)])
 def test_conv3x3_bn_act_forward_backward(B, h, w, training):
     """ops.conv3x3_bn_act = ConvBatchNormReLU(512, 512, 3, 1, 1) (model/darknet.py:118-156) against plain PyTorch in fp64: outputs and
     running statistics 1e-3; gradients at the product's own ReLU pattern (the derivative of the function it evaluated) 1e-3."""
@@ -806,11 +806,14 @@ def test_conv3x3_bn_act_forward_backward(B, h, w, training):
     assert max(errs) < 1e-3, errs
 
 
-def test_conv3x3_refuses_unaligned_rows():
-    assert not ops.conv3x3_supported(512, 512, 26, 26) and not ops.conv3x3_supported(512, 512, 13, 13) and ops.conv3x3_supported(512, 512, 52, 52)
-    x = torch.zeros(1, 512, 676, device=DEV); W = torch.zeros(512, 512, 3, 3, device=DEV); v = torch.ones(512, device=DEV)
-    with pytest.raises(RuntimeError):
-        ops.conv3x3_bn_act(x, W, v, v, v.clone(), v.clone(), True, 26, 26)
+def test_conv3x3_alignment_rule_of_the_c_entry_points():
+    """the contractions themselves need w % 4 == 0 (a TMA box shifted by one image row must start 16-byte aligned); ops.conv3x3_bn_act
+    runs other widths at the next multiple of 4 (13 -> 16, 26 -> 28: test_conv3x3_bn_act_forward_backward)"""
+    from dcnet_b200 import _lib
+    L = _lib.lib()
+    assert not L.dcnet_conv3x3_supported(512, 512, 26, 26) and not L.dcnet_conv3x3_supported(512, 512, 13, 13)
+    assert L.dcnet_conv3x3_supported(512, 512, 52, 52) and L.dcnet_conv3x3_supported(512, 512, 26, 28)
+    assert ops.conv3x3_supported(512, 512, 26, 26) and ops.conv3x3_supported(512, 512, 13, 13) and not ops.conv3x3_supported(100, 512, 8, 8)
 
 
 def test_conv1x1_bias_head_output_layer():
