@@ -726,6 +726,48 @@ def kernel_rooflines(key, dev):
     return roof, roof_s, roof_co, roof_hbm
 
 
+_FULL_AFFINITY = None
+
+
+def pin_to_gpu_numa_node(local):
+    """The end-to-end loop streams every step's inputs from pinned host memory (165 MB per step and GPU at C3: ~25 GB/s per rank, ~200 GB/s
+    on 8 GPUs).  Pinned pages are placed on the NUMA node of the thread that first touches them, so each rank binds itself to the CPU
+    cores next to its GPU BEFORE it allocates anything: the copies then never cross the socket interconnect.  Best effort (NVML's ideal
+    CPU affinity; falls back to sysfs); returns a short description for the JSON line, or None."""
+    global _FULL_AFFINITY
+    try:
+        _FULL_AFFINITY = os.sched_getaffinity(0)
+        before = len(_FULL_AFFINITY)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            how = "nvmlDeviceSetCpuAffinity"
+        except Exception:
+            bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+            if bus is None:
+                return None
+            path = "/sys/bus/pci/devices/0000:%02x:00.0/numa_node" % bus
+            node = int(open(path).read())
+            if node < 0:
+                return None
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if not cpus:
+                return None
+            os.sched_setaffinity(0, cpus)
+            how = "sysfs numa_node %d" % node
+        return "%s: %d of %d cores" % (how, len(os.sched_getaffinity(0)), before)
+    except Exception:
+        return None
+
+
 def step_flops(key):
     """algorithmic GEMM FLOPs of one step per GPU: co-attention 18 c sum N^2 + 1x1 convs 3 x 2 K c sum N per image"""
     wl = WORKLOADS[key]
@@ -766,6 +808,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed to fd 1 when the communicator comes
@@ -812,6 +855,8 @@ def main():
             roof, roof_s, roof_co, roof_hbm = kernel_rooflines(key, dev)
         if world == 1 and not args.no_cpu_baseline:
             gpu_base = pytorch_gpu_baseline(key, dev)
+            if _FULL_AFFINITY:
+                os.sched_setaffinity(0, _FULL_AFFINITY)      # the CPU arm uses every core the process was given, not one NUMA node
             cpu_base = cpu_baseline(key)
         peaks = load_peaks()
         step_tf = step_flops(key) / (m["ms_per_step"] * 1e-3) / 1e12
@@ -825,7 +870,7 @@ def main():
                                             "index-producing contractions and everything else in fp32",
                                  grad_allreduce=m["grad_allreduce"], cross_gpu_negatives=m["cross_gpu_negatives"],
                                  step_gemm_tflops=step_tf, step_gemm_frac_of_sustained=step_tf / peaks["tensor_sustained"]),
-                    clocks=m["clocks"], e2e=m["e2e"],
+                    clocks=m["clocks"], e2e=m["e2e"], host_affinity=numa,
                     gpu_launches=int(m["launches_per_step"] * args.steps), gpu_launches_per_step=m["launches_per_step"],
                     roofline=roof, roofline_gemm_s=roof_s, roofline_coattn=roof_co, roofline_hbm=roof_hbm, cpu_baseline=cpu_base, pytorch_gpu_baseline=gpu_base,
                     extra=extra or None)
