@@ -260,7 +260,8 @@ extern "C" int dcnet_coattn_bwd_l2_budget(long long bytes) { g_bwd_l2_budget = b
 // 1 (default): dcnet_coattn_bwd at precision 2 runs its contractions on fp16 operands when the caller hands over the forward's staging;
 // 0: always the tf32 contractions (bring-up / comparison knob, process-wide)
 static int g_bwd_fp16 = 1;
-extern "C" int dcnet_coattn_bwd_fp16(int on) { g_bwd_fp16 = on ? 1 : 0; return 0; }
+static int g_bwd_stop = 0;         // profiling: on > 1 stops the fp16 pipeline after its (on - 1)-th contraction (dcnet_gemm_trace then holds that launch)
+extern "C" int dcnet_coattn_bwd_fp16(int on) { g_bwd_fp16 = on ? 1 : 0; g_bwd_stop = on > 1 ? on - 1 : 0; return 0; }
 static int coattn_bwd_chunk(int nprob, int N) {
   const long long per = 2ll * N * N * (long long)sizeof(float);
   long long c = g_bwd_l2_budget / per;
@@ -435,6 +436,7 @@ extern "C" int dcnet_coattn_bwd_ex(const float* frames, int F, const int* qa, co
     e.out = reinterpret_cast<float*>(E16); e.out_f16 = 1; e.ldo = ldh; e.so_b = NLh; e.alpha = tau; e.idxA = qa; e.idxB = kb;
     e.epi_exp = 1; e.u = lse; e.ldu = N; e.exp_shift = E_SHIFT; e.sum = rsum; e.sum_ldz = N;
     DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    if (g_bwd_stop == 1) return 0;
     coattn_delta16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, oidx, mxp, mx_by_oidx, rsum, delta, dO16, alpha_z, C, N, ldh);
     DCNET_LAUNCH_OK("coattn_bwd.delta16");
     // s dS' = tau (s dP - s delta) E' / r' (fp16) with row sums s rho
@@ -442,10 +444,12 @@ extern "C" int dcnet_coattn_bwd_ex(const float* frames, int F, const int* qa, co
     e.out = reinterpret_cast<float*>(dS16); e.out_f16 = 1; e.ldo = ldh; e.so_b = NLh; e.alpha = tau; e.idxB = kb;
     e.epi_exp = 2; e.u = delta; e.u2 = rsum; e.ldu = N; e.cc = reinterpret_cast<const float*>(E16); e.ldcc = ldh; e.cc_sb = NLh; e.sum = rho; e.sum_ldz = N;
     DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    if (g_bwd_stop == 2) return 0;
     coattn_fix16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, F16, oidx, qa, rsum, rho, mxp, mx_by_oidx, dOs16, dframes, C, N, ldh);
     DCNET_LAUNCH_OK("coattn_bwd.fix16");
     e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.alpha_z = alpha_z; e.atomic = 1; e.idxC = kb; e.k_chunks = -1;
     DCNET_TRY(umma_gemm(Gsk, Emn, nullptr, C, N, N, 0, 0, nprob, e, st));
+    if (g_bwd_stop == 3) return 0;
     e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.alpha_z = alpha_z; e.atomic = 1; e.idxA = kb; e.idxC = qa; e.k_chunks = -1;
     DCNET_TRY(umma_gemm(Fk, dSk, nullptr, C, N, N, 0, 0, nprob, e, st));
     e = UmmaEpilogue{}; e.out = dframes; e.ldo = N; e.so_b = CN; e.alpha = 1.f; e.alpha_z = alpha_z; e.atomic = 1; e.idxA = qa; e.idxC = kb; e.k_chunks = -1;

@@ -276,7 +276,8 @@ DCNET_API int dcnet_coattn_bwd_ex(const float* frames, int F, const int* qa, con
 /* The backward keeps its N x N scratch (P, dP -> dS) resident in L2 by working through the problems in chunks whose scratch
  * fits `bytes` (default 64 MiB of the 126 MB L2; <= 0 = unlimited = one chunk); dcnet_coattn_workspace_bytes follows it. */
 DCNET_API int dcnet_coattn_bwd_l2_budget(long long bytes);
-/* 1 (default): the fp16 pipeline is used whenever `staged` is given; 0: always tf32 (comparison knob, process-wide) */
+/* 1 (default): the fp16 pipeline is used whenever `staged` is given; 0: always tf32 (comparison knob, process-wide); n > 1
+ * (profiling): the fp16 pipeline returns after its (n-1)-th contraction, so that dcnet_gemm_trace holds that launch */
 DCNET_API int dcnet_coattn_bwd_fp16(int on);
 
 /* ---- a4: inter-frame patch correspondence (model/DCNet_model.py:381-430) ------------------------------
