@@ -677,7 +677,7 @@ def kernel_rooflines(key, dev):
                    ms=ms, stage_ms=ms_stage, achieved_incl_staging=ach_incl, frac_incl_staging=ach_incl / peaks["tensor_burst"],
                    frac_of_sustained=ach / peaks["tensor_sustained"], executed_tflops=ach * 4.0 / 3.0,
                    l2="staged operands and outputs rotate over %d sets (%.0f MB)" % (NS2, NS2 * (stg[0].numel() + o_bufs[0].numel() * 4) / 1e6),
-                   note="algorithmic 6*c*N^2 per pair; the kernel executes 8*c*N^2 (S recomputed per direction); stage_ms = the bf16 staging pass "
+                   note="algorithmic 6*c*N^2 per pair; the kernel executes 8*c*N^2 (S recomputed per direction); stage_ms = the stand-alone fp16 staging pass "
                         "that precedes it in the step (frac_incl_staging counts it)",
                    peak_source=peaks["src"] + " bf16 burst (kernel timed alone)")
     del stg, o_bufs

@@ -147,7 +147,7 @@ class grounding_model(nn.Module):
         self._idx_cache = {}
         self._capture = None
         self.precision = ops.TENSOR_TF32   # GEMM-shaped ops on tcgen05 (TF32 operands, fp32 accumulate); ops.EXACT_FP32 = CUDA cores
-        self.fused_coattn = True           # co-attention forward: fused tcgen05 kernel (bf16 operands, S/P never leave the SM)
+        self.fused_coattn = True           # co-attention forward: fused tcgen05 kernel (fp16 operands, S/P never leave the SM)
 
     # ---------------------------------------------------------------------------------------------------------
     @property
@@ -156,7 +156,7 @@ class grounding_model(nn.Module):
             return self.coattn_precision_override
         if self.precision == ops.EXACT_FP32:
             return ops.EXACT_FP32
-        return ops.TENSOR_BF16_FUSED if self.fused_coattn else self.precision
+        return ops.TENSOR_F16_FUSED if self.fused_coattn else self.precision
 
     def _pair_index(self, B, device):
         key = ("pair", B, str(device))
@@ -207,7 +207,7 @@ class grounding_model(nn.Module):
         m = self.mapping_visu._modules[str(s)]
         N = raw_s.shape[2] * raw_s.shape[3]
         # ... and the same kernel writes the fused co-attention's staging (fp16 copy + column norms) from its registers
-        stage = (s > 0 and self.precision == ops.TENSOR_TF32 and self.coattn_precision == ops.TENSOR_BF16_FUSED and N >= ops.FUSED_MIN_N
+        stage = (s > 0 and self.precision == ops.TENSOR_TF32 and self.coattn_precision == ops.TENSOR_F16_FUSED and N >= ops.FUSED_MIN_N
                  and m.conv.out_channels % 128 == 0 and m.conv.out_channels <= 512)
         # (the Darknet map itself is read truncated: a pass over it would cost more than the layer's BN kernel, and a uniform
         # relative bias of z is removed by the BatchNorm that follows; the weight gradient carries it once, ~2e-4)

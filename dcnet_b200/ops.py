@@ -568,8 +568,9 @@ class _ConvBNAct(torch.autograd.Function):
         return (dx1, dx2, dW, sums[1], sums[0], du, dcc, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, dflang, None, None, None, None)
 
 
-EXACT_FP32, TENSOR_TF32, TENSOR_BF16_FUSED, EXACT_FWD_TF32_BWD = 0, 1, 2, 3
-FUSED_MIN_N = 128      # the fused bf16 co-attention forward is used from this many positions on (below: exact fp32, tiny)
+EXACT_FP32, TENSOR_TF32, TENSOR_F16_FUSED, EXACT_FWD_TF32_BWD = 0, 1, 2, 3
+TENSOR_BF16_FUSED = TENSOR_F16_FUSED      # round-1 name (the fused kernel ran on bf16 operands then)
+FUSED_MIN_N = 128      # the fused fp16 co-attention forward is used from this many positions on (below: exact fp32, tiny)
 
 
 def conv_bn_act(x1, weight, gamma, beta, running_mean, running_var, training, x2=None, u=None, cc=None, fa=None,
@@ -785,16 +786,14 @@ class _CoAttn(torch.autograd.Function):
             # exact fp32 forward (lse included); the backward is the tcgen05 one with fused epilogues, which recomputes its own tf32
             # logits and re-normalises them (the saved lse is only a shift there, so the two precisions cannot disagree about P)
             precision = EXACT_FP32
-            ctx.precision = TENSOR_BF16_FUSED
-        if precision == TENSOR_BF16_FUSED and N < FUSED_MIN_N:
-            # short key axes: with few keys the rounding of bf16 (and tf32) operands does not average out -- 1.6e-3 (1.15e-3) on the
+            ctx.precision = TENSOR_F16_FUSED
+        if precision == TENSOR_F16_FUSED and N < FUSED_MIN_N:
+            # short key axes: with few keys the rounding of reduced-precision operands does not average out -- bf16 / tf32 gave 1.6e-3 / 1.15e-3 on the
             # worst of 112 problems at N = 64, bar 1e-3 -- and the contraction is tiny: exact fp32 forward; the backward is the
             # precision-2 one either way (it recomputes its own tf32 logits and uses the saved lse only as a shift)
             precision = EXACT_FP32
-        if precision == TENSOR_BF16_FUSED and C % 128 == 0 and C <= 512:
-            # fused kernel: only the bf16 staging of the maps is needed.  Handing it to the backward (dcnet_coattn_bwd's `staged`:
-            # P recomputed from the same bf16 operands, exp fused into the GEMM epilogue, no softmax pass) was measured at
-            # -2 % step time but 1.3e-3 gradient error against 9e-4 with tf32 logits + re-normalisation: not used (bar 1e-3).
+        if precision == TENSOR_F16_FUSED and C % 128 == 0 and C <= 512:
+            # fused kernel: only the fp16 staging of the maps is needed; the backward's contractions read the same staging
             nbytes = _lib.lib().dcnet_coattn_stage_bytes(F_, C, N)
             if prestaged is not None:
                 if prestaged.numel() < nbytes or prestaged.dtype != torch.uint8:
@@ -805,7 +804,7 @@ class _CoAttn(torch.autograd.Function):
                 staged = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
                 # staging + fused kernel (dcnet_coattn_fwd at precision 2 needs only the staging bytes)
                 _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau,
-                          TENSOR_BF16_FUSED | rn_out, _p(staged), nbytes, _st())
+                          TENSOR_F16_FUSED | rn_out, _p(staged), nbytes, _st())
         else:
             nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, precision)
             ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
@@ -833,7 +832,7 @@ class _CoAttn(torch.autograd.Function):
 
 
 def coattn_stage(frames):
-    """bf16 staging + column norms of frames [F,C,N] for coattn_fused (forward only)."""
+    """fp16 staging + column norms of frames [F,C,N] for coattn_fused (forward only)."""
     frames = _c(frames.detach(), name="frames")
     F_, C, N = frames.shape
     nbytes = _lib.lib().dcnet_coattn_stage_bytes(F_, C, N)
@@ -923,7 +922,7 @@ class _Correspondence(torch.autograd.Function):
         return (dfv, None, None, None, None, dW, dgamma, dbeta, dfa, dfa_neg, None, None, None, None, None, None, None, None, None, None, None)
 
 
-def correspondence(fv, qa, kb, weight, gamma, beta, running_mean, running_var, training, fa=None, fa_neg=None, tau=10.0, cprecision=TENSOR_BF16_FUSED,
+def correspondence(fv, qa, kb, weight, gamma, beta, running_mean, running_var, training, fa=None, fa_neg=None, tau=10.0, cprecision=TENSOR_F16_FUSED,
                    momentum=0.999, eps=1e-5, slope=0.0, precision=TENSOR_TF32, num_batches_tracked=None, round_in=True, round_out=False,
                    staged=None):
     """fv [B,C,N] (pairs = consecutive frames via qa / kb) -> corr_feat [B,Cout,N] (channel-normalised) or (corr_feat, sim, neg_sim) with fa.
