@@ -54,6 +54,25 @@ __global__ void batchsum_kernel(const float* __restrict__ dz, float* __restrict_
   }
 }
 
+// both sums in ONE pass over dz (N % 4 == 0): CTA = (channel c, 1024 positions), thread = 4 consecutive positions, loop over the images.
+// dcc leaves as float4; the row sums go through a warp reduction and one atomicAdd per (image, warp) into du (caller zeroes).
+__global__ void __launch_bounds__(256) rowbatchsum_kernel(const float* __restrict__ dz, float* __restrict__ du, float* __restrict__ dcc, int B, int C,
+                                                          int N) {
+  const int c = blockIdx.y;
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const bool ok = n < N;
+  const int lane = threadIdx.x & 31;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; b++) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) v = *reinterpret_cast<const float4*>(dz + ((long long)b * C + c) * N + n);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const float r = warp_sum((v.x + v.y) + (v.z + v.w));
+    if (lane == 0) atomicAdd(du + (long long)b * C + c, r);
+  }
+  if (ok) *reinterpret_cast<float4*>(dcc + (long long)c * N + n) = acc;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // BatchNorm batch statistics: one CTA per channel, two passes (mean, then centred second moment) so the
 // variance has no E[z^2]-E[z]^2 cancellation (fp32 path: <= 1e-5 relative).
@@ -617,6 +636,13 @@ extern "C" int dcnet_conv1x1_bwd_weight(const float* dz, const float* x1, int K1
         DCNET_TRY(sgemm_launch(dz, x2, dW + K1, C, K2, N, B, 1, N, 1, (long long)C * N, 0, 1, N, (long long)K2 * N, 0, ldw, 1, 0,
                                nullptr, nullptr, nullptr, 1.f, 0.f, nullptr, 0, 1, st));
     }
+  }
+  if (du && dcc && N % 4 == 0 && reinterpret_cast<uintptr_t>(dz) % 16 == 0 && reinterpret_cast<uintptr_t>(dcc) % 16 == 0 && C <= 65535) {
+    // the fusion layer wants both: one pass over dz
+    DCNET_CUDA(cudaMemsetAsync(du, 0, (size_t)B * C * sizeof(float), st), "conv1x1_bwd_weight.memset");
+    rowbatchsum_kernel<<<dim3(ceil_div(N, 1024), C), 256, 0, st>>>(dz, du, dcc, B, C, N);
+    DCNET_LAUNCH_OK("conv1x1_bwd_weight.du_dcc");
+    return 0;
   }
   if (du) {
     const long long rows = (long long)B * C;
