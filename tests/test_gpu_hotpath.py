@@ -28,12 +28,16 @@ def _leaves(batch, dev):
 
 
 @pytest.mark.parametrize("precision", [0, 1])
-@pytest.mark.parametrize("size,pairs", [(256, 2), (256, 3), (416, 2)])
+@pytest.mark.parametrize("size,pairs", [(256, 2), (256, 3), (416, 2), (256, 1), (320, 1), (352, 2)])
 def test_hotpath_step_vs_oracle(size, pairs, precision):
+    # (256, 1): the smallest batch (one frame pair: every image is its own rank-loss partner's partner); 320 / 352: sizes the reference
+    # never ran (10/20/40 and 11/22/44 grids: N0 = 100 / 121, odd row pitches at 352)
     synth.seed_all(13)
     hp = HotPath(size)
     hp.net.precision = precision
     TL, TG = (1e-4, 2e-3) if precision == 0 else (3e-3, 6e-2)
+    if pairs == 1 and precision == 0:
+        TG = 5e-3      # two images: the batch statistics rest on 2 N values, and the CPU / GPU fp32 summation orders flip relatively more ReLU masks (3.3e-3)
     g = torch.Generator().manual_seed(500 + size + pairs)
     batch = synth.make_hotpath_batch(pairs, size, g)
     cpu = copy.deepcopy(hp.net).train()
