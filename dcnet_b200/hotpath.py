@@ -73,6 +73,7 @@ class HotPath(nn.Module):
     terms_on_aux = True
     # the finest scale's chain (the critical path of the step) on a stream of its own priority; None = the caller's stream (priority 0)
     finest_priority = None
+    coarse_on_one_stream = False   # both coarse scales' chains on one side stream (measured: see profiles/r3t_variants_c3.txt)
     finest_first = False     # measured: 7.96 ms against 7.85 ms (C3), 1.475 against 1.439 (C2), profiles/r2l_variants.txt
 
     def _run_scales(self, chain):
@@ -88,7 +89,7 @@ class HotPath(nn.Module):
         outs = [None, None, None]
         fork = cur.record_event()
         for s in (0, 1):
-            st = self._side[s]
+            st = self._side[0 if self.coarse_on_one_stream else s]
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 outs[s] = chain(s)
@@ -110,7 +111,8 @@ class HotPath(nn.Module):
                 cur.wait_stream(aux)
             self._aux_pending = False
         for s in (0, 1):
-            cur.wait_stream(self._side[s])
+            if not (self.coarse_on_one_stream and s == 1):
+                cur.wait_stream(self._side[s])
             for t in _tensors(outs[s]):
                 t.record_stream(cur)          # produced on a side stream, consumed (and later freed) on the caller's stream
         return outs

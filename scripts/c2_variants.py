@@ -16,14 +16,15 @@ def run(name):
 
 
 run("default")
-HotPath.side_priority = (-1, -1)
-HotPath.aux_priority = (-2, -2)
-run("coarse scales at priority -1, aux -2, finest 0")
-HotPath.side_priority = (-1, -1)
-HotPath.aux_priority = (-1, -1)
-run("coarse scales and aux at priority -1, finest 0")
-HotPath.side_priority = (-2, -1)
-HotPath.aux_priority = (-3, -3)
-run("coarsest -2, middle -1, aux -3, finest 0")
-HotPath.side_priority = (0, 0)
-HotPath.aux_priority = (-1, -1)
+HotPath.coarse_on_one_stream = True
+run("both coarse scales on one side stream")
+HotPath.coarse_on_one_stream = False
+_lib.lib().dcnet_gemm_select(7)
+run("4 epilogue warps in the fp16 exp / dS epilogues")
+_lib.lib().dcnet_gemm_select(0)
+ops.BWD_FP16 = False
+run("co-attention backward on tf32 operands (round-2a)")
+ops.BWD_FP16 = True
+ops.RN_TF32 = False
+run("operands truncated by the MMA instead of rounded by their producers (round 1)")
+ops.RN_TF32 = True
