@@ -389,9 +389,44 @@ def measure_hotpath(key, steps, warmup, rank, world, local, dev, dist, xneg=Fals
     d2h_bytes = h_out.numel() * 4
     del batches
 
+    # Data-parallel gradient all-reduce of the hot-path parameters.  DCNET_AR_BUCKETS=1 (default 0 = one flat all-reduce after the
+    # backward): one bucket per pyramid scale, issued on a communication stream from post-accumulate-grad hooks as soon as every
+    # parameter of that scale has its gradient -- the coarse scales finish their backward ~40 % before the end of the step.
+    ar_buckets = world > 1 and allreduce and os.environ.get("DCNET_AR_BUCKETS", "0") == "1"
+    ar_state = dict(pending={}, comm=None)
+    if ar_buckets:
+        import re
+        ar_state["comm"] = torch.cuda.Stream()
+        hot = {id(p) for p in hp.hot_parameters}
+        groups = {0: [], 1: [], 2: []}
+        for n_, p_ in hp.net.named_parameters():
+            if id(p_) in hot:
+                groups[int(re.search(r"\.(\d)(\.|$)", n_).group(1))].append(p_)
+
+        def make_hook(sc):
+            def hook(param):
+                comm = ar_state["comm"]
+                comm.wait_event(torch.cuda.current_stream().record_event())      # this parameter's gradient is complete on its stream
+                ar_state["pending"][sc] -= 1
+                if ar_state["pending"][sc] == 0:
+                    with torch.cuda.stream(comm):
+                        flat = torch.cat([q.grad.reshape(-1) for q in groups[sc] if q.grad is not None])
+                        dist.all_reduce(flat)
+            return hook
+        for sc, ps in groups.items():
+            for p_ in ps:
+                p_.register_post_accumulate_grad_hook(make_hook(sc))
+        ar_state["groups"] = groups
+
     def run_step():
-        return hp.step(static['raw'], static['flang'][0], static['fa'][0], static['context'][0], static['head'], static['loc'],
-                       static['dy_head'], static['bbox'][0], s_negpos, s_negidx)
+        if ar_buckets:
+            for sc, ps in ar_state["groups"].items():
+                ar_state["pending"][sc] = len(ps)
+        r_ = hp.step(static['raw'], static['flang'][0], static['fa'][0], static['context'][0], static['head'], static['loc'],
+                     static['dy_head'], static['bbox'][0], s_negpos, s_negidx)
+        if ar_buckets:
+            torch.cuda.current_stream().wait_stream(ar_state["comm"])
+        return r_
 
     def clear_grads():
         for p in hp.parameters():
@@ -414,6 +449,7 @@ def measure_hotpath(key, steps, warmup, rank, world, local, dev, dist, xneg=Fals
     graph = None
     ar_in_graph = False
     do_ar = world > 1 and allreduce
+    ar_in_graph = bool(ar_buckets and use_graph)
     if do_ar:
         dist.all_reduce(torch.zeros(1, device=dev))          # communicator up before any capture
         torch.cuda.synchronize()
@@ -422,7 +458,7 @@ def measure_hotpath(key, steps, warmup, rank, world, local, dev, dist, xneg=Fals
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             res = run_step()
-            if do_ar:
+            if do_ar and not ar_buckets:
                 # data-parallel gradient all-reduce of the hot-path parameters, one flat NCCL collective, captured with the step
                 flat_g = torch.cat([p.grad.reshape(-1) for p in hp.hot_parameters if p.grad is not None])
                 dist.all_reduce(flat_g)
@@ -435,7 +471,7 @@ def measure_hotpath(key, steps, warmup, rank, world, local, dev, dist, xneg=Fals
         else:
             clear_grads()
             res = run_step()
-        if do_ar and not ar_in_graph:
+        if do_ar and not ar_in_graph and not ar_buckets:
             flat = torch.cat([p.grad.reshape(-1) for p in hp.hot_parameters if p.grad is not None])
             dist.all_reduce(flat)
 
@@ -561,7 +597,8 @@ def measure_hotpath(key, steps, warmup, rank, world, local, dev, dist, xneg=Fals
                         pipeline="H2D of step i+1 (pinned host -> staging set, copy stream) under the kernels of step i; staged -> static inputs "
                                  "device-to-device, each set one packed buffer = one copy; every step's loss is copied back, the host reads it one step late"),
                launches_per_step=int(launches_per_step), clocks=clocks, launch="CUDA graph replay" if graph is not None else "eager",
-               grad_allreduce=bool(do_ar), cross_gpu_negatives=xneg, nccl_in_graph=bool(graph is not None and (xneg or ar_in_graph)))
+               grad_allreduce=bool(do_ar), allreduce_buckets=("per scale, from gradient hooks" if ar_buckets else ("one, after the backward" if do_ar else None)),
+               cross_gpu_negatives=xneg, nccl_in_graph=bool(graph is not None and (xneg or ar_in_graph)))
     # a CUDA graph that holds captured NCCL kernels must be gone before the communicator is torn down (and before the next capture)
     graph = None
     res = None
@@ -868,7 +905,8 @@ def main():
                                             "nearest tf32 by their producers; co-attention forward and backward on fp16 x fp16 -> fp32 (kind::f16: the "
                                             "11 significant bits of tf32, gradient-side operands scaled per problem into fp16's range); "
                                             "index-producing contractions and everything else in fp32",
-                                 grad_allreduce=m["grad_allreduce"], cross_gpu_negatives=m["cross_gpu_negatives"],
+                                 grad_allreduce=m["grad_allreduce"], allreduce_buckets=m.get("allreduce_buckets"),
+                                 cross_gpu_negatives=m["cross_gpu_negatives"],
                                  step_gemm_tflops=step_tf, step_gemm_frac_of_sustained=step_tf / peaks["tensor_sustained"]),
                     clocks=m["clocks"], e2e=m["e2e"], host_affinity=numa,
                     gpu_launches=int(m["launches_per_step"] * args.steps), gpu_launches_per_step=m["launches_per_step"],
