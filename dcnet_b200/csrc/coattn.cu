@@ -260,8 +260,14 @@ extern "C" int dcnet_coattn_bwd_l2_budget(long long bytes) { g_bwd_l2_budget = b
 // 1 (default): dcnet_coattn_bwd at precision 2 runs its contractions on fp16 operands when the caller hands over the forward's staging;
 // 0: always the tf32 contractions (bring-up / comparison knob, process-wide)
 static int g_bwd_fp16 = 1;
+static int g_bwd_use_keep = 1;    // 0 (dcnet_coattn_bwd_fp16(-1)): recompute E even when the forward kept it (comparison)
 static int g_bwd_stop = 0;         // profiling: on > 1 stops the fp16 pipeline after its (on - 1)-th contraction (dcnet_gemm_trace then holds that launch)
-extern "C" int dcnet_coattn_bwd_fp16(int on) { g_bwd_fp16 = on ? 1 : 0; g_bwd_stop = on > 1 ? on - 1 : 0; return 0; }
+extern "C" int dcnet_coattn_bwd_fp16(int on) {
+  g_bwd_fp16 = on ? 1 : 0;
+  g_bwd_stop = on > 1 ? on - 1 : 0;
+  g_bwd_use_keep = on == -1 ? 0 : 1;
+  return 0;
+}
 static int coattn_bwd_chunk(int nprob, int N) {
   const long long per = 2ll * N * N * (long long)sizeof(float);
   long long c = g_bwd_l2_budget / per;
@@ -345,14 +351,14 @@ extern "C" int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const
                                 const float* out, int n_out, const float* lse, const float* dout, float* dframes,
                                 int C, int N, float tau, int precision, const void* staged, void* workspace, size_t workspace_bytes,
                                 void* stream) {
-  return dcnet_coattn_bwd_ex(frames, F, qa, kb, oidx, nprob, out, n_out, lse, dout, nullptr, dframes, C, N, tau, precision, staged, workspace,
-                             workspace_bytes, stream);
+  return dcnet_coattn_bwd_ex(frames, F, qa, kb, oidx, nprob, out, n_out, lse, dout, nullptr, dframes, C, N, tau, precision, staged, nullptr,
+                             nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int dcnet_coattn_bwd_ex(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                    const float* out, int n_out, const float* lse, const float* dout, const unsigned int* dout_absmax,
-                                   float* dframes, int C, int N, float tau, int precision, const void* staged, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   float* dframes, int C, int N, float tau, int precision, const void* staged, const void* e_keep,
+                                   const float* r_keep, void* workspace, size_t workspace_bytes, void* stream) {
   DCNET_CHECK_ARG(frames && qa && kb && oidx && lse && dout && dframes && nprob >= 0 && C > 0 && N > 0 && F > 0 && n_out > 0, "coattn_bwd: bad arguments");
   DCNET_CHECK_ARG(out || precision != 2, "coattn_bwd: the saved forward output is needed (delta = <dO, O>)");
   if (nprob == 0) return 0;
@@ -419,7 +425,7 @@ extern "C" int dcnet_coattn_bwd_ex(const float* frames, int F, const int* qa, co
     };
     const UmmaOperand Fmn = H(F16, C, N, ldh, CLh, F, true), Fk = H(F16, C, N, ldh, CLh, F, false);
     const UmmaOperand Gmn = H(dO16, C, N, ldh, CLh, nprob, true), Gsk = H(dOs16, C, N, ldh, CLh, nprob, false);
-    const UmmaOperand Emn = H(E16, N, N, ldh, NLh, nprob, true);
+
     const UmmaOperand dSk = H(dS16, N, N, ldh, NLh, nprob, false), dSmn = H(dS16, N, N, ldh, NLh, nprob, true);
     const int mblk = ceil_div(N, 128) * nprob;
     const int zsl = mblk >= 592 ? 1 : (592 / mblk > 8 ? 8 : 592 / mblk);
@@ -431,18 +437,30 @@ extern "C" int dcnet_coattn_bwd_ex(const float* frames, int F, const int* qa, co
       coattn_absmax_kernel<<<dim3(8, nprob), 256, 0, st>>>(dout, oidx, mx, CN / 4);
       DCNET_LAUNCH_OK("coattn_bwd.absmax");
     }
-    // E' = 2^8 exp(tau S - lse_fwd) (fp16) with row sums r'
     UmmaEpilogue e{};
-    e.out = reinterpret_cast<float*>(E16); e.out_f16 = 1; e.ldo = ldh; e.so_b = NLh; e.alpha = tau; e.idxA = qa; e.idxB = kb;
-    e.epi_exp = 1; e.u = lse; e.ldu = N; e.exp_shift = E_SHIFT; e.sum = rsum; e.sum_ldz = N;
-    DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    int e_t = 0;
+    if (e_keep && r_keep && g_bwd_use_keep) {
+      // the forward kept its unnormalised weights -- transposed, E^T[z][key][q] (fp16, same pitch) -- and their row sums: no recomputation
+      // of S.  P = E / r holds exactly for the values the MMAs read, whatever common factor E carries.  The dS epilogue reads its E tile
+      // transposed, and dFb += dOs E takes E^T as a K-major operand
+      E16 = const_cast<__half*>(reinterpret_cast<const __half*>(e_keep));
+      e_t = 1;
+      DCNET_CUDA(cudaMemcpyAsync(rsum, r_keep, (size_t)nprob * N * sizeof(float), cudaMemcpyDeviceToDevice, st), "coattn_bwd.rsum");
+    } else {
+      // E' = 2^8 exp(tau S - lse_fwd) (fp16) with row sums r'
+      e.out = reinterpret_cast<float*>(E16); e.out_f16 = 1; e.ldo = ldh; e.so_b = NLh; e.alpha = tau; e.idxA = qa; e.idxB = kb;
+      e.epi_exp = 1; e.u = lse; e.ldu = N; e.exp_shift = E_SHIFT; e.sum = rsum; e.sum_ldz = N;
+      DCNET_TRY(umma_gemm(Fmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
+    }
     if (g_bwd_stop == 1) return 0;
+    // E as the B operand of dFb += dOs E (reduction over the queries): [q][k] memory = MN-major, [k][q] memory = K-major
+    const UmmaOperand Emn = H(E16, N, N, ldh, NLh, nprob, e_t == 0);
     coattn_delta16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, oidx, mxp, mx_by_oidx, rsum, delta, dO16, alpha_z, C, N, ldh);
     DCNET_LAUNCH_OK("coattn_bwd.delta16");
     // s dS' = tau (s dP - s delta) E' / r' (fp16) with row sums s rho
     e = UmmaEpilogue{};
     e.out = reinterpret_cast<float*>(dS16); e.out_f16 = 1; e.ldo = ldh; e.so_b = NLh; e.alpha = tau; e.idxB = kb;
-    e.epi_exp = 2; e.u = delta; e.u2 = rsum; e.ldu = N; e.cc = reinterpret_cast<const float*>(E16); e.ldcc = ldh; e.cc_sb = NLh; e.sum = rho; e.sum_ldz = N;
+    e.epi_exp = 2; e.u = delta; e.u2 = rsum; e.ldu = N; e.cc = reinterpret_cast<const float*>(E16); e.ldcc = ldh; e.cc_sb = NLh; e.cc_t = e_t; e.sum = rho; e.sum_ldz = N;
     DCNET_TRY(umma_gemm(Gmn, Fmn, nullptr, N, N, C, 0, 0, nprob, e, st));
     if (g_bwd_stop == 2) return 0;
     coattn_fix16_kernel<<<dim3(ceil_div(N, 128), nprob, zsl), dim3(32, 8), 0, st>>>(dout, out, F16, oidx, qa, rsum, rho, mxp, mx_by_oidx, dOs16, dframes, C, N, ldh);

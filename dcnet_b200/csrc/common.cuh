@@ -111,6 +111,7 @@ struct UmmaEpilogue {
   // ldcc / so_b / cc_sb in elements, multiples of 8 --, epi_exp values are rounded to fp16 instead of tf32; exp_shift is added to the
   // exponent of epi_exp = 1; alpha_z[z] (optional) multiplies alpha per batch item (undoes a per-problem operand scale)
   int out_f16 = 0;
+  int cc_t = 0;                  // dS epilogue, fp16: the E tensor is stored transposed, cc[z][col][row] (what the fused forward keeps)
   float exp_shift = 0.f;
   const float* alpha_z = nullptr;
   // plain epilogue with m_split: absmax2[z] = max |out2[z]| as the bit pattern of a non-negative float (caller zeroes) -- the

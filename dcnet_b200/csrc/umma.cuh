@@ -239,7 +239,7 @@ static inline dcnet_encode_tiled_fn dcnet_get_encode_tiled() {
 }
 
 static inline int make_tmap(CUtensorMap* m, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                            uint64_t stride2_elems, uint32_t b0, uint32_t b1, bool atom32b = false) {
+                            uint64_t stride2_elems, uint32_t b0, uint32_t b1, bool atom32b = false, bool no_swizzle = false) {
   dcnet_encode_tiled_fn enc = dcnet_get_encode_tiled();
   if (!enc) return -999;
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -247,7 +247,8 @@ static inline int make_tmap(CUtensorMap* m, const void* base, int elem_bytes, ui
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (int)r;

@@ -54,6 +54,11 @@ struct CoP {
   float scale;             // tau * log2(e)
   int tma_store;           // 1: epilogue through swizzled smem + TMA store (needs N % 4 == 0), 0: direct stores
   int round_out;           // 1: O leaves rounded to the nearest tf32 (DCNET_RN_TF32: it is the operand of a tf32 contraction)
+  // training: the unnormalised weights, TRANSPOSED as the kernel holds them -- E^T[z][key][q] (fp16, row pitch N rounded up to 8) -- and
+  // their row sums r[z][q] are kept for the backward, whose contractions then need no recomputation of S (memory is not scarce: 468 MB at
+  // 416x416 for 32 problems).  The E^T tile leaves straight from the swizzled shared-memory tile the second MMA reads: one TMA store per
+  // key tile, issued by the MMA thread.  keep_e = 0: not kept
+  int keep_e; float* r_out;
   int variant;             // experiment switches of the profiling entry point (0 in production)
   long long* trace;        // optional [CTA][tile][8] clock64 stamps (debug / profiling entry point); nullptr = off
 };
@@ -68,7 +73,8 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_out, const CoP p) {
+coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_e,
+                    const CoP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -156,12 +162,18 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
             mma_bf16(tmem + S_COL, ad, bd, idesc_s, (m | ks) != 0 ? 1u : 0u);
           }
         }
+        if (p.keep_e && j > 0) tma_store_wait_read();      // the previous tile's E^T has left sP before the exp warps may overwrite it
         mma_commit(s_full);
         TRACE(4);
         // O^T += KV E^T over the keys of the tile
         mbar_wait(p_full, ph);
         tc_fence_after();
         TRACE(5);
+        if (p.keep_e) {
+          // the exp warps fenced their writes of sP for the async proxy before arriving: the tile is ready for TMA as it is for the MMA
+          tma_store_3d(&map_e, sP, q0, j * KT, z);
+          tma_store_commit();
+        }
         for (int m = 0; m < ncb; m++) {
 #pragma unroll
           for (int ks = 0; ks < 8; ks++) {      // 16 keys (32 B inside the 128-B row; key half = ks / 4) per MMA
@@ -172,6 +184,7 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
           mma_commit(&kv_free[m]);              // channel block m of this tile may be overwritten
         }
       }
+      if (p.keep_e) tma_store_wait_read();
       mma_commit(o_full);
     }
   } else {
@@ -200,6 +213,7 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
         const float x1 = valid ? ex2(fmaf(v[e + 1], p.scale, -sh[e + 1])) : 0.f;
         const __half2 b = __floats2half2_rn(x0, x1);
         pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&b);
+
         const float2 bf = __half22float2(b);        // the row sum is the sum of exactly the weights the MMA reads
         sum[e] += bf.x;
         sum[e + 1] += bf.y;
@@ -232,7 +246,10 @@ coattn_fused_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
       const int q = half * 32 + lane;
       const float r = s_red[half * 4][lane] + s_red[half * 4 + 1][lane] + s_red[half * 4 + 2][lane] + s_red[half * 4 + 3][lane];
       s_inv[q] = 1.f / r;
-      if (q0 + q < p.N) p.lse[(long long)z * p.N + q0 + q] = (s_shift[q] + log2f(r)) * 0.6931471805599453f;
+      if (q0 + q < p.N) {
+        p.lse[(long long)z * p.N + q0 + q] = (s_shift[q] + log2f(r)) * 0.6931471805599453f;
+        if (p.r_out) p.r_out[(long long)z * p.N + q0 + q] = r;
+      }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     float inv[32];
@@ -411,7 +428,8 @@ int umma_coattn_stage(const float* frames, int F, int C, int N, void* ws, size_t
 
 // the fused kernel over a staged workspace
 int umma_coattn_run(const void* ws, int F, const int* qa, const int* kb, const int* oidx, int nprob, float* out, float* lse,
-                    int n_out, int C, int N, float tau, cudaStream_t st, long long* trace = nullptr, int variant = 0, int round_out = 0) {
+                    int n_out, int C, int N, float tau, cudaStream_t st, long long* trace = nullptr, int variant = 0, int round_out = 0,
+                    void* e_out = nullptr, float* r_out = nullptr) {
   DCNET_CHECK_ARG(umma_coattn_supported(C, N), "coattn (fused): C must be a multiple of 128, <= 512");
   DCNET_CHECK_ARG(ws && qa && kb && oidx && out && lse, "coattn (fused): null argument");
   DCNET_CHECK_ARG(reinterpret_cast<uintptr_t>(out) % 16 == 0 && reinterpret_cast<uintptr_t>(ws) % 256 == 0,
@@ -432,6 +450,15 @@ int umma_coattn_run(const void* ws, int F, const int* qa, const int* kb, const i
   p.variant = variant;
   p.tma_store = (N % 4 == 0) ? 1 : 0;
   p.round_out = round_out;
+  DCNET_CHECK_ARG((e_out == nullptr) == (r_out == nullptr), "coattn (fused): e_out and r_out go together");
+  DCNET_CHECK_ARG(!e_out || reinterpret_cast<uintptr_t>(e_out) % 16 == 0, "coattn (fused): the kept E^T buffer must be 16-byte aligned");
+  p.keep_e = e_out ? 1 : 0; p.r_out = r_out;
+  CUtensorMap map_e = map;     // unused when keep_e == 0
+  if (e_out) {
+    // E^T [nprob][N keys][ld q]: box = the [128 keys][64 q] shared-memory tile
+    const int re = make_tmap(&map_e, e_out, 2, (uint64_t)N, (uint64_t)N, (uint64_t)nprob, (uint64_t)ld, (uint64_t)N * ld, 64, 128);
+    if (re != 0) return dcnet_set_error(-3, "coattn (fused): cuTensorMapEncodeTiled(E) failed (%d)", re);
+  }
   CUtensorMap map_out = map;   // unused when tma_store == 0
   if (p.tma_store) {
     const int ro = make_tmap(&map_out, out, 4, (uint64_t)N, (uint64_t)C, (uint64_t)n_out, (uint64_t)N, (uint64_t)C * N, 32, 128);
@@ -439,7 +466,7 @@ int umma_coattn_run(const void* ws, int F, const int* qa, const int* kb, const i
   }
   DCNET_CUDA(cudaFuncSetAttribute(coattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM), "coattn_fused.attr");
   dim3 grid(ceil_div(N, QT), nprob);
-  coattn_fused_kernel<<<grid, NTHREADS, FUSED_SMEM, st>>>(map, map_out, p);
+  coattn_fused_kernel<<<grid, NTHREADS, FUSED_SMEM, st>>>(map, map_out, map_e, p);
   DCNET_LAUNCH_OK("coattn_fused");
   return 0;
 }
@@ -458,10 +485,18 @@ extern "C" int dcnet_coattn_stage(const float* frames, int F, int C, int N, void
 
 extern "C" int dcnet_coattn_fused_fwd(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                       float* out, int n_out, float* lse, int C, int N, float tau, int flags, void* stream) {
+  return dcnet_coattn_fused_fwd_keep(staged, F, qa, kb, oidx, nprob, out, n_out, lse, C, N, tau, flags, nullptr, nullptr, stream);
+}
+
+extern "C" size_t dcnet_coattn_keep_bytes(int nprob, int N) { return (nprob > 0 && N > 0) ? (size_t)nprob * N * pitch8(N) * 2 : 0; }
+
+extern "C" int dcnet_coattn_fused_fwd_keep(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                           float* out, int n_out, float* lse, int C, int N, float tau, int flags, void* e_keep, float* r_keep,
+                                           void* stream) {
   DCNET_CHECK_ARG(F > 0 && n_out > 0 && nprob >= 0, "coattn_fused_fwd: bad arguments");
   if (nprob == 0) return 0;
   return umma_coattn_run(staged, F, qa, kb, oidx, nprob, out, lse, n_out, C, N, tau, as_stream(stream), nullptr, 0,
-                         (flags & DCNET_RN_TF32) ? 1 : 0);
+                         (flags & DCNET_RN_TF32) ? 1 : 0, e_keep, r_keep);
 }
 
 // profiling variant: trace [grid CTAs][key tiles][8] receives clock64 stamps of the MMA-issuing thread (0-3: channel block m of

@@ -268,6 +268,7 @@ struct Gemm2P {
   //     coordinate (positions) shifted by dy * tap_w
   int tap_kper, tap_w, tap_flip, tap_n;
   int f16;             // 2-byte operands are __half (FMT_F16) instead of __nv_bfloat16
+  int cc_t;            // fp16 dS epilogue: E is stored transposed ([col][row]); its tile arrives as [64 k rows][32 q] without swizzle
   int out_f16;         // out / the E tile are __half tensors: two 32-column chunks share one 128-byte slot row, values rounded to fp16
   float exp_shift; const float* alpha_z;
   unsigned int* absmax2;
@@ -517,7 +518,8 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       float4 ecur[8];
       const float* erow = (p.epi_exp == 2 && row_ok && !e_tma && !h16) ? p.cc + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
       const __half* erow_h = (p.epi_exp == 2 && row_ok && !e_tma && h16)
-                                 ? reinterpret_cast<const __half*>(p.cc) + (long long)z * p.cc_sb + (long long)row * p.ldcc : nullptr;
+                                 ? reinterpret_cast<const __half*>(p.cc) + (long long)z * p.cc_sb + (p.cc_t ? (long long)row : (long long)row * p.ldcc)
+                                 : nullptr;
       auto load_e = [&](int c, float4 (&dst)[8]) {
         const int nb_ = n0 + c * 32;
         if (erow && nb_ + 32 <= p.N_valid) {
@@ -529,7 +531,8 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       auto tma_e = [&](int c) {          // lane 0: E block of chunk c -> slot (echunk + c) & 1
         const uint32_t k = echunk + (uint32_t)(h16 ? (EW == 8 ? c >> 2 : c >> 1) : c);
         mbar_expect_tx(&ebar[k & 1u], SLOT_BYTES);
-        tma_load_3d(eslots + (k & 1u) * SLOT_BYTES, &mapO2, &ebar[k & 1u], n0 + c * 32, row0, z);
+        if (p.cc_t) tma_load_3d(eslots + (k & 1u) * SLOT_BYTES, &mapO2, &ebar[k & 1u], row0, n0 + c * 32, z);   // box [64 k][32 q]
+        else tma_load_3d(eslots + (k & 1u) * SLOT_BYTES, &mapO2, &ebar[k & 1u], n0 + c * 32, row0, z);
       };
       if (e_tma) { if (lane == 0) tma_e(EW == 8 ? 2 * chalf : 0); }
       else if (p.epi_exp == 2 && !h16) load_e(0, ecur);
@@ -584,7 +587,18 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           } else {
             // dS = tau (dP - delta) E / r : per-row delta (bias) and tau / r (rowmul); E tile: this chunk's half of the 128-byte row
             uint32_t eh[16];
-            if (e_tma) {
+            if (e_tma && p.cc_t) {
+              // transposed E: the slot holds [64 k rows][32 q] (64-byte rows, no swizzle); this thread's query is column `lane`, the
+              // 32 lanes of a load read 64 consecutive bytes of one row
+              const uint32_t k = echunk + (uint32_t)(EW == 8 ? c >> 2 : c >> 1);
+              mbar_wait(&ebar[k & 1u], (k >> 1) & 1u);
+              const __half* er = reinterpret_cast<const __half*>(eslots + (k & 1u) * SLOT_BYTES) + (c & 1) * 32 * 32 + lane;
+#pragma unroll
+              for (int e = 0; e < 16; e++) {
+                const __half2 hh = __halves2half2(er[(2 * e) * 32], er[(2 * e + 1) * 32]);
+                eh[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+            } else if (e_tma) {
               const uint32_t k = echunk + (uint32_t)(EW == 8 ? c >> 2 : c >> 1);
               mbar_wait(&ebar[k & 1u], (k >> 1) & 1u);
               const uint8_t* er = eslots + (k & 1u) * SLOT_BYTES + lane * 128;
@@ -592,6 +606,15 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               for (int e = 0; e < 4; e++) {
                 const uint4 q = *reinterpret_cast<const uint4*>(er + ((((c & 1) * 4 + e) ^ (lane & 7)) * 16));
                 eh[4 * e] = q.x; eh[4 * e + 1] = q.y; eh[4 * e + 2] = q.z; eh[4 * e + 3] = q.w;
+              }
+            } else if (erow_h && p.cc_t) {
+              // transposed E from global memory (single-CTA tiles): element (row, nb + e) lives at cc[(nb + e) * ldcc + row]
+#pragma unroll
+              for (int e = 0; e < 16; e++) {
+                const __half z0 = __float2half(0.f);
+                const __half2 hh = __halves2half2(nb + 2 * e < p.N_valid ? erow_h[(long long)(nb + 2 * e) * p.ldcc] : z0,
+                                                  nb + 2 * e + 1 < p.N_valid ? erow_h[(long long)(nb + 2 * e + 1) * p.ldcc] : z0);
+                eh[e] = *reinterpret_cast<const uint32_t*>(&hh);
               }
             } else if (erow_h && full) {
 #pragma unroll
@@ -948,7 +971,7 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     q.epi_exp = e.epi_exp; q.u2 = e.u2; q.cc_sb = e.cc_sb; q.sum_ldz = e.sum_ldz;
     q.tap_kper = e.tap_kper; q.tap_w = e.tap_w; q.tap_flip = e.tap_flip; q.tap_n = e.tap_n;
     q.f16 = A.f16 ? 1 : 0; q.out_f16 = e.out_f16; q.exp_shift = e.exp_shift; q.alpha_z = e.alpha_z;
-    q.absmax2 = e.absmax2;
+    q.absmax2 = e.absmax2; q.cc_t = e.cc_t;
     int want_chunks = e.k_chunks;
     if (auto_split) {
       const long long tiles = (long long)q.ntiles;
@@ -972,6 +995,12 @@ int umma_gemm(const UmmaOperand& A, const UmmaOperand& B, const UmmaOperand* B2,
     mo2 = mo;
     if (e.epi_exp == 2) {
       DCNET_CHECK_ARG(e.m_split == 0 && al16(e.cc) && e.ldcc % oal == 0 && e.cc_sb % oal == 0, "umma_gemm: dS epilogue: E must be TMA-addressable, no m_split");
+      if (e.cc_t) {
+        DCNET_CHECK_ARG(e.out_f16, "umma_gemm: the transposed E tensor belongs to the fp16 dS epilogue");
+        // E^T [z][N cols of the output (k)][M rows of the output (q)]: tile [64 k][32 q], 64-byte rows, no swizzle
+        r = make_tmap(&mo2, e.cc, 2, (uint64_t)M, (uint64_t)N, e.cc_sb ? 65535u : 1u, (uint64_t)e.ldcc, e.cc_sb ? (uint64_t)e.cc_sb : (uint64_t)N * e.ldcc,
+                      32, 64, false, /*no_swizzle=*/true);
+      } else
       r = make_tmap(&mo2, e.cc, oeb, (uint64_t)N, (uint64_t)M, e.cc_sb ? 65535u : 1u, (uint64_t)e.ldcc, e.cc_sb ? (uint64_t)e.cc_sb : (uint64_t)M * e.ldcc, obox, 32);
       if (r != 0) return dcnet_set_error(-3, "umma_gemm: cuTensorMapEncodeTiled(E) failed (%d)", r);
     }

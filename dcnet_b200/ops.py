@@ -84,6 +84,8 @@ _RN_FLAG = 0x100
 # co-attention backward on fp16 operands (kind::f16 at twice the tf32 rate, the same 11 significant bits; include/dcnet_b200.h,
 # dcnet_coattn_bwd `staged`).  False = the tf32 contractions (comparison).
 BWD_FP16 = True
+# the fused co-attention forward keeps its softmax weights (fp16) for the backward instead of the backward recomputing S (False: recompute)
+KEEP_E = True
 
 
 def round_tf32(x, out=None):
@@ -779,7 +781,7 @@ class _CoAttn(torch.autograd.Function):
         out = torch.empty(n_out, C, N, device=frames.device, dtype=F32) if n_out == nprob else \
             torch.zeros(n_out, C, N, device=frames.device, dtype=F32)
         lse = torch.empty(nprob, N, device=frames.device, dtype=F32)
-        staged = None
+        staged = ekeep = rkeep = None
         ctx.precision = precision
         rn_out = _RN_FLAG if (RN_TF32 and round_out) else 0
         if precision == EXACT_FWD_TF32_BWD:
@@ -798,20 +800,24 @@ class _CoAttn(torch.autograd.Function):
             if prestaged is not None:
                 if prestaged.numel() < nbytes or prestaged.dtype != torch.uint8:
                     raise ValueError("coattention: prestaged buffer does not belong to frames of shape %s" % (tuple(frames.shape),))
-                _lib.call("dcnet_coattn_fused_fwd", _p(prestaged), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, rn_out, _st())
                 staged = prestaged
             else:
                 staged = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
-                # staging + fused kernel (dcnet_coattn_fwd at precision 2 needs only the staging bytes)
-                _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau,
-                          TENSOR_F16_FUSED | rn_out, _p(staged), nbytes, _st())
+                _lib.call("dcnet_coattn_stage", _p(frames), F_, C, N, _p(staged), nbytes, _st())
+            if BWD_FP16 and KEEP_E and ctx.needs_input_grad[0] and N % 4 == 0:
+                # training: the kernel keeps its unnormalised weights E (fp16) and their row sums -- the backward then starts without
+                # recomputing S = Fa^T Fb (HBM is not scarce: 468 MB at 416x416 for 32 problems)
+                ekeep = torch.empty(_lib.lib().dcnet_coattn_keep_bytes(nprob, N), device=frames.device, dtype=torch.uint8)
+                rkeep = torch.empty(nprob, N, device=frames.device, dtype=F32)
+            _lib.call("dcnet_coattn_fused_fwd_keep", _p(staged), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, rn_out,
+                      _p(ekeep), _p(rkeep), _st())
         else:
             nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, precision)
             ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
             _lib.call("dcnet_coattn_fwd", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), n_out, _p(lse), C, N, tau, precision | rn_out,
                       _p(ws), nbytes, _st())
         # the fp16 staging goes to the backward: its five contractions then run on fp16 operands (tf32's precision at twice the rate)
-        ctx.save_for_backward(frames, qa, kb, oidx, out, lse, staged if BWD_FP16 else None)
+        ctx.save_for_backward(frames, qa, kb, oidx, out, lse, staged if BWD_FP16 else None, ekeep, rkeep)
         ctx.tau = tau
         return out
 
@@ -819,7 +825,7 @@ class _CoAttn(torch.autograd.Function):
     def backward(ctx, dout, accumulate_into=None, dout_absmax=None):
         """accumulate_into (used by _Correspondence): a [F,C,N] gradient buffer that already holds the other consumers' contribution to
         d frames -- the kernels add into it (TMA reduce-add) instead of into a zero-filled tensor that autograd would add afterwards"""
-        frames, qa, kb, oidx, out, lse, staged = ctx.saved_tensors
+        frames, qa, kb, oidx, out, lse, staged, ekeep, rkeep = ctx.saved_tensors
         F_, C, N = frames.shape
         nprob = qa.numel()
         dout = _c(dout, name="dout")
@@ -827,7 +833,8 @@ class _CoAttn(torch.autograd.Function):
         nbytes = _lib.lib().dcnet_coattn_workspace_bytes(F_, nprob, C, N, ctx.precision)
         ws = torch.empty(nbytes, device=frames.device, dtype=torch.uint8)
         _lib.call("dcnet_coattn_bwd_ex", _p(frames), F_, _p(qa), _p(kb), _p(oidx), nprob, _p(out), out.shape[0], _p(lse), _p(dout),
-                  _p(dout_absmax) if staged is not None else None, _p(dframes), C, N, ctx.tau, ctx.precision, _p(staged), _p(ws), nbytes, _st())
+                  _p(dout_absmax) if staged is not None else None, _p(dframes), C, N, ctx.tau, ctx.precision, _p(staged), _p(ekeep), _p(rkeep),
+                  _p(ws), nbytes, _st())
         return dframes, None, None, None, None, None, None, None, None
 
 
@@ -887,7 +894,7 @@ class _Correspondence(torch.autograd.Function):
     @staticmethod
     def forward(ctx, fv, qa, kb, tau, cprecision, weight, gamma, beta, fa, fa_neg, running_mean, running_var, training, momentum, eps, slope,
                 precision, nbt, round_in, round_out, staged):
-        c1, c2 = _FakeCtx(), _FakeCtx()
+        c1, c2 = _FakeCtx((ctx.needs_input_grad[0],)), _FakeCtx()
         nprob = qa.numel()
         rn = RN_TF32 and precision == TENSOR_TF32
         if rn and round_in:

@@ -253,6 +253,14 @@ DCNET_API size_t dcnet_coattn_stage_bytes(int F, int C, int N);
 DCNET_API int dcnet_coattn_stage(const float* frames, int F, int C, int N, void* staged, size_t staged_bytes, void* stream);
 DCNET_API int dcnet_coattn_fused_fwd(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                      float* out, int n_out, float* lse, int C, int N, float tau, int flags, void* stream);
+/* training form: the kernel also keeps its unnormalised softmax weights, transposed as it holds them -- E^T[z][key][q] (fp16,
+ * dcnet_coattn_keep_bytes(nprob, N) bytes, row pitch N rounded up to 8; one TMA store per key tile from the shared-memory tile the
+ * second MMA reads) -- and their row sums r [nprob,N] for dcnet_coattn_bwd_ex, whose contractions then start without recomputing
+ * S = Fa^T Fb (HBM is not scarce: 468 MB for 32 problems at N = 2704 against a 240 GFLOP contraction per step)                        */
+DCNET_API size_t dcnet_coattn_keep_bytes(int nprob, int N);
+DCNET_API int dcnet_coattn_fused_fwd_keep(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
+                                          float* out, int n_out, float* lse, int C, int N, float tau, int flags, void* e_keep, float* r_keep,
+                                          void* stream);
 /* flags: 0 or DCNET_RN_TF32 (out leaves rounded to the nearest tf32) */
 /* profiling variant: trace [ceil(N/64) * nprob CTAs][ceil(N/128) key tiles + 1][8] int64 receives clock64 stamps (see umma_coattn.cu) */
 DCNET_API int dcnet_coattn_fused_fwd_trace(const void* staged, int F, const int* qa, const int* kb, const int* oidx, int nprob,
@@ -271,13 +279,15 @@ DCNET_API int dcnet_coattn_bwd(const float* frames, int F, const int* qa, const 
  * fp16 pipeline then skips its own pass over dout */
 DCNET_API int dcnet_coattn_bwd_ex(const float* frames, int F, const int* qa, const int* kb, const int* oidx, int nprob,
                                   const float* out, int n_out, const float* lse, const float* dout, const unsigned int* dout_absmax,
-                                  float* dframes, int C, int N, float tau, int precision, const void* staged, void* workspace,
-                                  size_t workspace_bytes, void* stream);
+                                  float* dframes, int C, int N, float tau, int precision, const void* staged, const void* e_keep,
+                                  const float* r_keep, void* workspace, size_t workspace_bytes, void* stream);
+/* e_keep / r_keep (optional, with `staged`): what dcnet_coattn_fused_fwd_keep left for the same problems */
 /* The backward keeps its N x N scratch (P, dP -> dS) resident in L2 by working through the problems in chunks whose scratch
  * fits `bytes` (default 64 MiB of the 126 MB L2; <= 0 = unlimited = one chunk); dcnet_coattn_workspace_bytes follows it. */
 DCNET_API int dcnet_coattn_bwd_l2_budget(long long bytes);
 /* 1 (default): the fp16 pipeline is used whenever `staged` is given; 0: always tf32 (comparison knob, process-wide); n > 1
- * (profiling): the fp16 pipeline returns after its (n-1)-th contraction, so that dcnet_gemm_trace holds that launch */
+ * (profiling): the fp16 pipeline returns after its (n-1)-th contraction, so that dcnet_gemm_trace holds that launch; -1: fp16 pipeline
+ * that recomputes E even when the forward kept it (comparison) */
 DCNET_API int dcnet_coattn_bwd_fp16(int on);
 
 /* ---- a4: inter-frame patch correspondence (model/DCNet_model.py:381-430) ------------------------------

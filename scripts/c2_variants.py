@@ -19,6 +19,9 @@ run("default")
 HotPath.coarse_on_one_stream = True
 run("both coarse scales on one side stream")
 HotPath.coarse_on_one_stream = False
+ops.KEEP_E = False
+run("backward recomputes S / E instead of reading what the forward kept")
+ops.KEEP_E = True
 _lib.lib().dcnet_gemm_select(7)
 run("4 epilogue warps in the fp16 exp / dS epilogues")
 _lib.lib().dcnet_gemm_select(0)
