@@ -461,7 +461,7 @@ class _ConvBNAct(torch.autograd.Function):
         outs = (y,) if fa is None else (y, sim, neg)
         if stage_out:
             # the staging buffer is an output without a gradient; autograd must not materialise a zero tensor of its size for it
-            # (88 MB at 416x416: a 35 us fill on the critical path, profiles/r3h_timeline_c3.txt)
+            # (88 MB at 416x416: a 35 us fill on the critical path, profiles/r3x_timeline_c3.txt)
             ctx.mark_non_differentiable(staged)
             ctx.set_materialize_grads(False)
             outs = outs + (staged,)
