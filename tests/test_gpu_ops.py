@@ -909,3 +909,58 @@ def test_coattention_backward_fp16_pipeline_is_scale_free(scale):
         errs[fp16] = max(rel(x.grad[i], ref_in.grad[i]) for i in range(2 * P))      # per frame: the small problem counts on its own
     print("coattn bwd at gradient scale %.0e: worst per-frame rel err fp16 %.2e, tf32 %.2e" % (scale, errs[True], errs[False]))
     assert errs[True] < 1e-3 and errs[True] < 1.5 * errs[False] + 1e-4, errs
+
+
+@pytest.mark.parametrize("N", [256, 676, 2704])
+def test_fused_forward_keeps_softmax_weights_for_the_backward(N):
+    """dcnet_coattn_fused_fwd_keep: E^T[z][key][q] / r[z][q] is the softmax matrix P[q][key] of the problem (to fp16 rounding of the
+    weights), for every problem of the batch and at ragged tile edges (N = 676, 2704 are not multiples of the 128-key / 64-query tiles)."""
+    from dcnet_b200 import _lib
+    g = gen(410 + N)
+    nf, C = 3, 512
+    fr = torch.nn.functional.normalize(torch.randn(nf, C, N, generator=g).abs(), dim=1)
+    x = fr.to(DEV)
+    qa = torch.tensor([0, 2, 1], dtype=torch.int32, device=DEV)
+    kb = torch.tensor([1, 0, 2], dtype=torch.int32, device=DEV)
+    oidx = torch.arange(3, dtype=torch.int32, device=DEV)
+    staged = ops.coattn_stage(x)
+    L = _lib.lib()
+    ld = (N + 7) // 8 * 8
+    ek = torch.zeros(L.dcnet_coattn_keep_bytes(3, N), dtype=torch.uint8, device=DEV)
+    rk = torch.empty(3, N, device=DEV)
+    out = torch.empty(3, C, N, device=DEV)
+    lse = torch.empty(3, N, device=DEV)
+    _lib.call("dcnet_coattn_fused_fwd_keep", staged.data_ptr(), nf, qa.data_ptr(), kb.data_ptr(), oidx.data_ptr(), 3, out.data_ptr(), 3, lse.data_ptr(),
+              C, N, 10.0, 0, ek.data_ptr(), rk.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    ET = ek.view(torch.float16).view(3, N, ld)[:, :, :N].float()                # [z][key][q]
+    for z in range(3):
+        S = 10.0 * fr[int(qa[z])].double().t() @ fr[int(kb[z])].double()
+        P = torch.softmax(S, 1)                                                  # [q][key]
+        got = (ET[z].t() / rk[z][:, None]).double().cpu()
+        assert rel(got, P) < 5e-4, (z, rel(got, P))
+        assert float((got.sum(1) - 1).abs().max()) < 1e-5                       # r is the sum of exactly the stored weights
+        assert float((lse[z].double().cpu() - torch.logsumexp(S, 1)).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("keep", [True, False])
+@pytest.mark.parametrize("N", [256, 1024])
+def test_coattention_backward_kept_weights_vs_recomputed(N, keep):
+    """the two forms of the fp16 backward -- starting from the weights the forward kept, or recomputing E = exp(tau S - lse) in the
+    epilogue of S = Fa^T Fb -- against the fp64 gradient"""
+    g = gen(420 + N)
+    P, C = 2, 512
+    fr = torch.nn.functional.normalize(torch.randn(2 * P, C, N, generator=g).abs(), dim=1)
+    go = torch.randn(2 * P, C, N, generator=g)
+    ref_in = fr.double().requires_grad_(True)
+    o1, o2 = O.coattention(ref_in.view(P, 2, C, N)[:, 0], ref_in.view(P, 2, C, N)[:, 1], 10.0)
+    O.interleave_pairs(o1, o2).backward(go.double())
+    qa = torch.arange(2 * P, device=DEV, dtype=torch.int32)
+    ops.KEEP_E = keep
+    try:
+        x = fr.to(DEV).requires_grad_(True)
+        ops.coattention(x, qa, qa ^ 1, tau=10.0, precision=2).backward(go.to(DEV))
+    finally:
+        ops.KEEP_E = True
+    e = rel(x.grad, ref_in.grad)
+    print("coattn bwd N=%d, weights %s: rel err %.2e" % (N, "kept by the forward" if keep else "recomputed", e))
+    assert e < 1e-3, e
